@@ -1,0 +1,1091 @@
+// cfr_core.cuh -- the classification hot path as per-task device functions.
+//
+// Everything here is written once and compiled twice: by nvcc for sm_100a (the
+// product) and by g++ with -DCFR_HOSTSIM for the host-side simulation harness
+// under tests/hostsim (a debugging twin; never part of the shipped library).
+//
+// Reference map (all file:line relative to the reference tree):
+//   rank9 query                DS_Rank.hpp:255-273          -> bv_rank1 / bv_rank_bit
+//   Bitvector::Rank0/Rank      Bitvector.hpp:45-57          -> bv_rank
+//   wavelet Rank/RankAndTest   Sequence_WaveletTree.hpp:235-293 -> wt_rank / wt_rank_test
+//   wavelet Access             Sequence_WaveletTree.hpp:215-232 -> wt_access
+//   run-block Rank / Access    Sequence_RunBlock.hpp:378-416 / :360-376 -> rb_rank / rb_access
+//   FMIndex::Rank              FMIndex.hpp:352-362          -> lastChr fix in *_extend / *_lf
+//   BackwardExtend             FMIndex.hpp:364-386          -> Bwt::extend / Bwt::lf
+//   BackwardSearch             FMIndex.hpp:388-422,487-510  -> backward_search
+//   GetSampledSA / locate      FMIndex.hpp:203-231,514-524  -> locate_row
+//   GetHitsFromRead            Classifier.hpp:274-293       -> get_hits_from_read
+//   AdjustHitBoundary...       Classifier.hpp:303-401       -> adjust_hit_boundary
+//   SearchForwardAndReverse    Classifier.hpp:509-583       -> select_task
+//   GetClassificationFromHits  Classifier.hpp:585-843       -> select_task (row plan) + score_task
+//   Taxonomy::LCA/ReduceTaxIds Taxonomy.hpp:733-973         -> tax_lca / tax_reduce
+//   Dustmasker                 Dustmasker.hpp:93-421        -> dust_task
+#pragma once
+#include "cfr_types.h"
+
+namespace cfrb200 {
+
+// ---------------------------------------------------------------------------
+// low-level helpers
+// ---------------------------------------------------------------------------
+CFR_HD int popc64(u64 x) {
+#if defined(__CUDA_ARCH__)
+  return __popcll(x);
+#else
+  return __builtin_popcountll(x);
+#endif
+}
+
+CFR_HD u64 ld64(const u64 *p) {
+#if defined(__CUDA_ARCH__)
+  return __ldg(p);
+#else
+  return *p;
+#endif
+}
+
+CFR_HD u32 ld32(const u32 *p) {
+#if defined(__CUDA_ARCH__)
+  return __ldg(p);
+#else
+  return *p;
+#endif
+}
+
+CFR_HD unsigned char ld8(const unsigned char *p) {
+#if defined(__CUDA_ARCH__)
+  return __ldg(p);
+#else
+  return *p;
+#endif
+}
+
+CFR_HD u64x2 ld128(const u64x2 *p) {
+#if defined(__CUDA_ARCH__)
+  ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2 *>(p));
+  u64x2 r;
+  r.x = v.x;
+  r.y = v.y;
+  return r;
+#else
+  return *p;
+#endif
+}
+
+// per-thread operation counters (flushed once per task batch)
+struct OpCount {
+  u32 rank, access, search, locate, lf, extend, bases;
+};
+
+// base byte -> code: A,C,G,T -> 0..3, anything else (incl. lowercase) -> 4
+CFR_HD int base_code(unsigned char c) {
+  return c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : 4;
+}
+
+// One strand of one read as the backward search sees it.  rc strands are never
+// materialised: rc[p] = comp(r[len-1-p]) (Classifier.hpp:99-111,846-856).
+struct StrandSeq {
+  const unsigned char *r;  // the mate as uploaded (after DUST)
+  int len;
+  int rc;
+  CFR_HD int operator()(int p) const {
+    if (!rc) return base_code(ld8(r + p));
+    int c = base_code(ld8(r + (len - 1 - p)));
+    return c > 3 ? 4 : 3 - c;
+  }
+};
+
+// ---------------------------------------------------------------------------
+// Layout 1: the reference's run-block BWT arrays as stored
+// ---------------------------------------------------------------------------
+
+// DS_Rank9::Query (inclusive) fused with Bitvector_Plain::Access on the same word
+CFR_HD u64 bv_rank_bit(const DevBV &v, u64 i, int &bit) {
+  const u64 wb = ld64(v.B + (i >> 6));
+  bit = (int)((wb >> (i & 63)) & 1ull);
+  const u64 wi = i >> 6;
+  const u64x2 r = ld128(reinterpret_cast<const u64x2 *>(v.R) + (wi >> 3));
+  const u64 t = (wi & 7) - 1;
+  return r.x + ((r.y >> ((t + ((t >> 60) & 8)) * 9)) & 0x1ff) + (u64)popc64(wb & ((2ull << (i & 63)) - 1ull));
+}
+
+CFR_HD u64 bv_rank1(const DevBV &v, u64 i) {
+  if (i >= v.n) i = v.n - 1;  // DS_Rank.hpp:259-260
+  int bit;
+  return bv_rank_bit(v, i, bit);
+}
+
+// Bitvector::Rank(type, i) inclusive; note Rank0 uses the UNclamped i (Bitvector.hpp:45-49)
+CFR_HD u64 bv_rank(const DevBV &v, int type, u64 i) {
+  const u64 r1 = bv_rank1(v, i);
+  return type ? r1 : i + 1 - r1;
+}
+
+CFR_HD int bv_access(const DevBV &v, u64 i) { return (int)((ld64(v.B + (i >> 6)) >> (i & 63)) & 1ull); }
+
+// Sequence_WaveletTree::Rank (inclusive), sigma = 4, code bits MSB first
+CFR_HD u64 wt_rank(const DevWT &t, int c, u64 i) {
+  const int b1 = c >> 1;
+  i = bv_rank(t.node[0], b1, i);
+  if (i == 0) return 0;
+  --i;
+  return bv_rank(t.node[t.child[0][b1]], c & 1, i);
+}
+
+// Sequence_WaveletTree::RankAndTest
+CFR_HD u64 wt_rank_test(const DevWT &t, int c, u64 i, bool &is_c) {
+  const int b1 = c >> 1, b0 = c & 1;
+  is_c = true;
+  if (b1 != bv_access(t.node[0], i)) is_c = false;
+  i = bv_rank(t.node[0], b1, i);
+  if (i == 0) return 0;
+  --i;
+  const DevBV &leaf = t.node[t.child[0][b1]];
+  if (is_c && b0 != bv_access(leaf, i)) is_c = false;
+  return bv_rank(leaf, b0, i);
+}
+
+// Sequence_WaveletTree::Access
+CFR_HD int wt_access(const DevWT &t, u64 i) {
+  int b1;
+  const u64 r1 = bv_rank_bit(t.node[0], i, b1);
+  i = (b1 ? r1 : i + 1 - r1) - 1;
+  return (b1 << 1) | bv_access(t.node[t.child[0][b1]], i);
+}
+
+// Sequence_RunBlock::Rank
+CFR_HD u64 rb_rank(const DevIndex &ix, int c, u64 i, int inclusive) {
+  if (!inclusive) {
+    if (i == 0) return 0;
+    --i;
+  }
+  const u64 bi = i / ix.b;
+  const u64 ib = i - bi * ix.b;
+  int type;
+  u64 ranki;
+  if (ix.b < ix.n) {
+    if (bi < ix.block_type.n) {
+      const u64 r1 = bv_rank_bit(ix.block_type, bi, type);
+      ranki = type ? r1 : bi + 1 - r1;
+    } else {
+      type = bv_access(ix.block_type, bi);
+      ranki = bv_rank(ix.block_type, type, bi);
+    }
+  } else {
+    type = bv_access(ix.block_type, bi);
+    ranki = 1;
+  }
+  const u64 other = (bi + 1) - ranki;
+  u64 ret;
+  if (type == 0) {
+    ret = wt_rank(ix.plain, c, (ranki - 1) * ix.b + ib);
+  } else {
+    bool in_run;
+    const u64 rb = wt_rank_test(ix.run, c, ranki - 1, in_run);
+    ret = in_run ? (rb - 1) * ix.b + ib + 1 : rb * ix.b;
+  }
+  if (other == 0) return ret;
+  if (type == 0)
+    ret += wt_rank(ix.run, c, other - 1) * ix.b;
+  else
+    ret += wt_rank(ix.plain, c, other * ix.b - 1);
+  return ret;
+}
+
+// Sequence_RunBlock::Access
+CFR_HD int rb_access(const DevIndex &ix, u64 i) {
+  const u64 bi = i / ix.b;
+  int type;
+  const u64 r1 = bv_rank_bit(ix.block_type, bi, type);
+  if (type == 0) {
+    return wt_access(ix.plain, i - ix.b * r1);  // r1 = Rank(1, bi)
+  } else {
+    const u64 r0 = bi + 1 - r1;  // Rank(0, bi)
+    return wt_access(ix.run, (i - ix.b * r0) / ix.b);
+  }
+}
+
+// FMIndex::Rank's correction for the missing '$' (FMIndex.hpp:359)
+CFR_HD u64 last_chr_fix(const DevIndex &ix, int c, u64 p, int inclusive) {
+  return (c == ix.last_code && (p < ix.first_isa || (!inclusive && p == ix.first_isa))) ? 1ull : 0ull;
+}
+
+struct BwtRunBlock {
+  // FMIndex::BackwardExtend (range form), FMIndex.hpp:364-379
+  static CFR_HD void extend(const DevIndex &ix, int c, u64 sp, u64 ep, u64 &nsp, u64 &nep, OpCount &oc) {
+    const u64 off = ix.C[c];
+    ++oc.extend;
+    ++oc.rank;
+    nsp = off + rb_rank(ix, c, sp, 0) + last_chr_fix(ix, c, sp, 0);
+    if (sp != ep) {
+      ++oc.rank;
+      nep = off + rb_rank(ix, c, ep, 1) + last_chr_fix(ix, c, ep, 1) - 1;
+    } else {
+      ++oc.access;
+      nep = nsp + ((rb_access(ix, ep) == c) ? 0ull : ~0ull);
+    }
+  }
+  // one LF step: i -> C[c] + Rank(c, i) - 1 with c = BWT[i]  (FMIndex.hpp:382-386,520)
+  static CFR_HD u64 lf(const DevIndex &ix, u64 i, OpCount &oc) {
+    ++oc.access;
+    ++oc.rank;
+    const int c = rb_access(ix, i);
+    return ix.C[c] + rb_rank(ix, c, i, 1) + last_chr_fix(ix, c, i, 1) - 1;
+  }
+  static CFR_HD u64 rank(const DevIndex &ix, int c, u64 i, int inclusive) { return rb_rank(ix, c, i, inclusive); }
+  static CFR_HD int access(const DevIndex &ix, u64 i) { return rb_access(ix, i); }
+};
+
+// ---------------------------------------------------------------------------
+// Layout 2: 64-byte occ lines (128 symbols + 4 absolute counters per line)
+// ---------------------------------------------------------------------------
+
+struct OccRegs {
+  u64 cnt[4];
+  u64 lo0, hi0, lo1, hi1;
+};
+
+CFR_HD OccRegs occ_load(const OccLine *p) {
+  OccRegs r;
+#if defined(__CUDA_ARCH__)
+  const ulonglong2 *q = reinterpret_cast<const ulonglong2 *>(p);
+  const ulonglong2 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2), d = __ldg(q + 3);
+  r.cnt[0] = a.x; r.cnt[1] = a.y; r.cnt[2] = b.x; r.cnt[3] = b.y;
+  r.lo0 = c.x; r.hi0 = c.y; r.lo1 = d.x; r.hi1 = d.y;
+#else
+  for (int i = 0; i < 4; ++i) r.cnt[i] = p->cnt[i];
+  r.lo0 = p->lo0; r.hi0 = p->hi0; r.lo1 = p->lo1; r.hi1 = p->hi1;
+#endif
+  return r;
+}
+
+// # of symbol c among the first `within` (0..127) symbols of the line, plus the line's base count
+CFR_HD u64 occ_count(const OccRegs &r, int c, int within) {
+  const u64 ml = (c & 1) ? ~0ull : 0ull, mh = (c & 2) ? ~0ull : 0ull;
+  const u64 m0 = ~(r.lo0 ^ ml) & ~(r.hi0 ^ mh);
+  const u64 m1 = ~(r.lo1 ^ ml) & ~(r.hi1 ^ mh);
+  u64 k0, k1;
+  if (within >= 64) {
+    k0 = ~0ull;
+    k1 = (1ull << (within - 64)) - 1ull;
+  } else {
+    k0 = (1ull << within) - 1ull;
+    k1 = 0ull;
+  }
+  return r.cnt[c] + (u64)popc64(m0 & k0) + (u64)popc64(m1 & k1);
+}
+
+CFR_HD int occ_symbol(const OccRegs &r, int within) {
+  const u64 lo = within >= 64 ? r.lo1 : r.lo0, hi = within >= 64 ? r.hi1 : r.hi0;
+  const int s = within & 63;
+  return (int)(((lo >> s) & 1ull) | (((hi >> s) & 1ull) << 1));
+}
+
+// occ(c, x) = # of c in BWT[0..x), x in [0, n]
+CFR_HD u64 occ_rank_excl(const DevIndex &ix, int c, u64 x) {
+  const OccRegs r = occ_load(ix.occ + (x >> 7));
+  return occ_count(r, c, (int)(x & 127));
+}
+
+struct BwtOccLine {
+  static CFR_HD void extend(const DevIndex &ix, int c, u64 sp, u64 ep, u64 &nsp, u64 &nep, OpCount &oc) {
+    const u64 off = ix.C[c];
+    ++oc.extend;
+    ++oc.rank;
+    const u64 lsp = sp >> 7;
+    const OccRegs a = occ_load(ix.occ + lsp);
+    nsp = off + occ_count(a, c, (int)(sp & 127)) + last_chr_fix(ix, c, sp, 0);
+    if (sp != ep) {
+      ++oc.rank;
+      const u64 x = ep + 1, lx = x >> 7;
+      if (lx == lsp) {
+        nep = off + occ_count(a, c, (int)(x & 127)) + last_chr_fix(ix, c, ep, 1) - 1;
+      } else {
+        const OccRegs e = occ_load(ix.occ + lx);
+        nep = off + occ_count(e, c, (int)(x & 127)) + last_chr_fix(ix, c, ep, 1) - 1;
+      }
+    } else {
+      ++oc.access;
+      nep = nsp + ((occ_symbol(a, (int)(ep & 127)) == c) ? 0ull : ~0ull);
+    }
+  }
+  static CFR_HD u64 lf(const DevIndex &ix, u64 i, OpCount &oc) {
+    ++oc.access;
+    ++oc.rank;
+    const OccRegs a = occ_load(ix.occ + (i >> 7));
+    const int w = (int)(i & 127);
+    const int c = occ_symbol(a, w);
+    // inclusive rank at i = exclusive count at i, plus the symbol itself
+    return ix.C[c] + occ_count(a, c, w) + 1 + last_chr_fix(ix, c, i, 1) - 1;
+  }
+  static CFR_HD u64 rank(const DevIndex &ix, int c, u64 i, int inclusive) {
+    if (!inclusive) return occ_rank_excl(ix, c, i);
+    return occ_rank_excl(ix, c, i + 1);
+  }
+  static CFR_HD int access(const DevIndex &ix, u64 i) {
+    const OccRegs a = occ_load(ix.occ + (i >> 7));
+    return occ_symbol(a, (int)(i & 127));
+  }
+};
+
+// ---------------------------------------------------------------------------
+// FM-index search and locate
+// ---------------------------------------------------------------------------
+
+// FMIndex::BackwardSearch with GetBackwardSearchInitialRange inlined
+template <class Bwt>
+CFR_HD int backward_search(const DevIndex &ix, const StrandSeq &s, int m, u64 &sp, u64 &ep, OpCount &oc) {
+  const int W = ix.pre_width;
+  if (m < W) return 0;
+  ++oc.search;
+  int l = 0;
+  if (W > 0) {
+    u64 w = 0;
+    for (int i = 0; i < W; ++i) {
+      const int c = s(m - 1 - i);
+      if (c > 3) {
+        sp = 1;
+        ep = 0;
+        return i;
+      }
+      w = (w << 2) | (u64)c;
+    }
+    const u64x2 e = ld128(ix.lookup + w);
+    if (e.y == 0) {
+      sp = 1;
+      ep = 0;
+      return W - 1;
+    }
+    sp = e.x;
+    ep = e.x + e.y - 1;
+    l = W;
+  } else {
+    sp = 0;
+    ep = ix.n - 1;
+  }
+  while (l < m) {
+    const int c = s(m - 1 - l);
+    if (c > 3) break;
+    u64 nsp, nep;
+    Bwt::extend(ix, c, sp, ep, nsp, nep, oc);
+    if (nsp > nep || nep > ix.n) break;
+    sp = nsp;
+    ep = nep;
+    ++l;
+  }
+  return l;
+}
+
+// FixedSizeElemArray::Read (FixedSizeElemArray.hpp:102, Utils.hpp:197-219)
+CFR_HD u64 sa_read(const DevIndex &ix, u64 i) {
+  const u64 s = i * (u64)ix.sa_bits, e = s + (u64)ix.sa_bits - 1;
+  const u64 is = s >> 6, ie = e >> 6;
+  const int rs = (int)(s & 63);
+  if (is == ie) {
+    const u64 m = ix.sa_bits >= 64 ? ~0ull : ((1ull << ix.sa_bits) - 1ull);
+    return (ld64(ix.sampled_sa + is) >> rs) & m;
+  }
+  const int re = (int)(e & 63);
+  return (ld64(ix.sampled_sa + is) >> rs) | ((ld64(ix.sampled_sa + ie) & ((1ull << (re + 1)) - 1ull)) << (64 - rs));
+}
+
+// FMIndex::GetSampledSA
+CFR_HD bool get_sampled_sa(const DevIndex &ix, u64 i, u64 &sa) {
+  if (i == ix.first_isa) {
+    sa = ix.adjusted_sa0;
+    return true;
+  }
+  if (i % (u64)ix.sample_rate == 0) {
+    sa = sa_read(ix, i / (u64)ix.sample_rate);
+    return true;
+  }
+  if (ix.sel_filter) {
+    const u64 fb = i / (u64)ix.sel_filter_rate;
+    if ((ld64(ix.sel_filter + (fb >> 6)) >> (fb & 63)) & 1ull) {
+      u64 lo = 0, hi = ix.sel_cnt;
+      while (lo < hi) {
+        const u64 mid = (lo + hi) >> 1;
+        if (ld64(&ix.sel[mid].x) < i) lo = mid + 1; else hi = mid;
+      }
+      if (lo < ix.sel_cnt && ld64(&ix.sel[lo].x) == i) {
+        sa = ld64(&ix.sel[lo].y);
+        return true;
+      }
+    }
+  }
+  return false;
+}
+
+// FMIndex::BackwardToSampledSA: the sampled SA holds sequence ids (Builder.hpp:27-71)
+template <class Bwt>
+CFR_HD u64 locate_row(const DevIndex &ix, u64 i, OpCount &oc) {
+  u64 sa = 0;
+  while (!get_sampled_sa(ix, i, sa)) {
+    i = Bwt::lf(ix, i, oc);
+    ++oc.lf;
+  }
+  ++oc.locate;
+  return sa;
+}
+
+// ---------------------------------------------------------------------------
+// Classifier: seed search
+// ---------------------------------------------------------------------------
+
+CFR_HD int max_hits_for_len(int len, int mhl) { return len < mhl ? 0 : (len + 1) / (mhl + 1); }
+
+// Classifier::CalculateHitScore (nucleotide, _scoreHitLenAdjust = 15)
+CFR_HD u64 hit_score(int l, int mhl) {
+  if (l < mhl) return 0;
+  return (u64)(long long)(l - 15) * (u64)(long long)(l - 15);
+}
+
+// Classifier::GetHitsFromRead; returns the number of hits written
+template <class Bwt>
+CFR_HD int get_hits_from_read(const DevIndex &ix, const StrandSeq &s, int mhl, Hit *out, int cap, OpCount &oc) {
+  u64 sp = 0, ep = 0;
+  int n = 0;
+  int remaining = s.len;
+  while (remaining >= mhl) {
+    const int l = backward_search<Bwt>(ix, s, remaining, sp, ep, oc);
+    if (l >= mhl && sp <= ep && n < cap) {
+      out[n].sp = sp;
+      out[n].ep = ep;
+      out[n].l = l;
+      out[n].offset = s.len - remaining;
+      ++n;
+    }
+    remaining -= (l + 1);
+  }
+  return n;
+}
+
+// Classifier::AdjustHitBoundaryFromStrandHits.  h1 = strandHits[1] (the mate as
+// read), h0 = strandHits[0] (its reverse complement).
+template <class Bwt>
+CFR_HD void adjust_hit_boundary(const DevIndex &ix, const unsigned char *r, int len, Hit *h0, int n0, Hit *h1,
+                                int n1, OpCount &oc) {
+  if (!n0 || !n1) return;
+  StrandSeq fw{r, len, 0}, rc{r, len, 1};
+  u64 sp = 0, ep = 0;
+  int j = n0 - 1;
+  bool need_fix0 = false, need_fix1 = false;
+  for (int i = 0; i < n1; ++i) {
+    const int right = len - h1[i].offset - 1;
+    const int left = right - h1[i].l + 1;
+    for (; j >= 0; --j) {
+      const int rc_left = h0[j].offset;
+      const int rc_right = rc_left + h0[j].l - 1;
+      if (rc_left >= right) continue;
+      if (left >= rc_right) break;
+      if (left == rc_left && right == rc_right) break;
+      if (left < rc_left && rc_right < right) break;
+      if (rc_left < left && right < rc_right) break;
+      if (rc_right > right) {
+        const int l = backward_search<Bwt>(ix, fw, rc_right + 1, sp, ep, oc);
+        if (rc_right - l + 1 == left && sp <= ep) {
+          h1[i].sp = sp;
+          h1[i].ep = ep;
+          h1[i].l = l;
+          h1[i].offset = len - rc_right - 1;
+          need_fix1 = true;
+        }
+      }
+      if (left < rc_left) {
+        const int l = backward_search<Bwt>(ix, rc, len - left, sp, ep, oc);
+        if (left + l - 1 == rc_right && sp <= ep) {
+          h0[j].sp = sp;
+          h0[j].ep = ep;
+          h0[j].l = l;
+          h0[j].offset = left;
+          need_fix0 = true;
+        }
+      }
+    }
+  }
+  for (int k = 0; k <= 1; ++k) {  // Classifier.hpp:361-400
+    Hit *h = k ? h1 : h0;
+    const int n = k ? n1 : n0;
+    if (!(k ? need_fix1 : need_fix0)) continue;
+    for (int i = 0; i < n - 1; ++i) {
+      const int starti = h[i].offset;
+      const int endi = starti + h[i].l - 1;
+      for (int q = i + 1; q < n; ++q) {
+        const int startj = h[q].offset;
+        if (startj > endi) break;
+        const int endj = startj + h[q].l - 1;
+        if (h[q].l >= h[i].l) {
+          h[i].l = startj - starti;
+          break;
+        } else {
+          if (endj <= endi)
+            h[q].l = 0;
+          else {
+            h[q].offset = endi + 1;
+            h[q].l = endj - (endi + 1) + 1;
+            break;
+          }
+        }
+      }
+    }
+  }
+}
+
+// number of BWT rows GetClassificationFromHits resolves for one hit and the
+// stride it uses (Classifier.hpp:620-666)
+struct RowPlan {
+  u64 step;   // 0: every row of [sp, ep]
+  u64 fwd;    // rows taken walking up from sp
+  u64 total;  // fwd + rows taken walking down from ep
+};
+
+CFR_HD RowPlan plan_rows(u64 sp, u64 ep, const DevParams &p) {
+  RowPlan rp;
+  const u64 range = ep - sp + 1;
+  const u64 max_entries = (u64)(long long)(p.max_result * p.hitk_factor);
+  if (range <= max_entries || p.hitk_factor <= 0 || p.max_result <= 0) {
+    rp.step = 0;
+    rp.fwd = range;
+    rp.total = range;
+    return rp;
+  }
+  const u64 step = (range % max_entries) ? range / max_entries + 1 : range / max_entries;
+  rp.step = step;
+  rp.fwd = (range - 1) / step + 1;  // j = sp, sp+step, ... <= ep
+  // walking down from ep: stops when resolved >= max_entries (checked after each
+  // locate) or when j would pass sp
+  const u64 down_avail = (range - 1) / step + 1;
+  u64 down = rp.fwd >= max_entries ? 1 : max_entries - rp.fwd;
+  if (down > down_avail) down = down_avail;
+  rp.total = rp.fwd + down;
+  return rp;
+}
+
+CFR_HD u64 plan_row_at(u64 sp, u64 ep, const RowPlan &rp, u64 t) {
+  if (rp.step == 0) return sp + t;
+  if (t < rp.fwd) return sp + t * rp.step;
+  return ep - (t - rp.fwd) * rp.step;
+}
+
+// ---------------------------------------------------------------------------
+// Taxonomy
+// ---------------------------------------------------------------------------
+
+CFR_HD u32 tax_parent(const DevIndex &ix, u32 t) { return ld32(ix.parent + t); }
+
+// Taxonomy::LCA (lcaChildTaxIds == NULL).  ids are all < node_cnt.
+// The backbone is the root path of the first non-root id; for every other id the
+// reference counts, per backbone position, the ids whose root-aligned path agrees
+// from the top down to it, and returns the lowest position all non-root ids share.
+// Equivalent without the count array: the answer index is the maximum over ids of
+// (highest mismatching aligned position + 1).
+CFR_HD u32 tax_lca(const DevIndex &ix, const u64 *ids, int cnt, u64 *err_flags) {
+  const u32 root = (u32)ix.root;
+  int k = 0;
+  while (k < cnt && (u32)ids[k] == root) ++k;
+  if (k >= cnt) return root;
+  u32 path[CFR_TAX_PATH_CAP];
+  int plen = 0;
+  u32 t = (u32)ids[k];
+  do {
+    if (plen >= CFR_TAX_PATH_CAP - 1) {
+      *err_flags |= 1ull;
+      return root;
+    }
+    path[plen++] = t;
+    t = tax_parent(ix, t);
+  } while (t != tax_parent(ix, t));
+  path[plen++] = root;
+  int first_common = 0;  // lowest backbone index shared by everybody seen so far
+  for (int i = 0; i < cnt; ++i) {
+    if (i == k) continue;
+    u32 x = (u32)ids[i];
+    if (x == tax_parent(ix, x)) continue;  // a root-level id: ignored (rootCount)
+    // length of x's path (nodes below the root-level node, plus the pushed root)
+    int tlen = 0;
+    t = x;
+    do {
+      ++tlen;
+      t = tax_parent(ix, t);
+    } while (t != tax_parent(ix, t));
+    ++tlen;
+    // align the two paths at their root ends
+    int ib, it;  // indices into backbone / tmp path of the lowest aligned pair
+    if (tlen >= plen) {
+      it = tlen - plen;
+      ib = 0;
+    } else {
+      it = 0;
+      ib = plen - tlen;
+    }
+    t = x;
+    for (int s = 0; s < it; ++s) t = tax_parent(ix, t);
+    int last_mismatch = ib - 1;  // positions below the aligned window are never counted
+    for (int q = ib; q < plen; ++q, ++it) {
+      const u32 node = (it == tlen - 1) ? root : t;
+      if (node != path[q]) last_mismatch = q;
+      if (it < tlen - 1) t = tax_parent(ix, t);
+    }
+    if (last_mismatch + 1 > first_common) first_common = last_mismatch + 1;
+  }
+  return first_common >= plen ? root : path[first_common];
+}
+
+CFR_HD int tax_level_of(const DevIndex &ix, u32 t) {
+  const unsigned char r = ld8(ix.rank + t);
+  return ix.rank_num[r < 31 ? r : 0];
+}
+
+// the node an id contributes to promotion level `ri` (Taxonomy.hpp:904-930), or
+// ~0u when its lineage ends below that level
+CFR_HD u32 tax_node_at_level(const DevIndex &ix, u32 id, int ri) {
+  if (ri == 0) return id;
+  const int unknown = ix.rank_num[0];
+  int prev = 0;
+  u32 t = id;
+  do {
+    const int rn = tax_level_of(ix, t);
+    if (rn != unknown && rn > prev) {
+      if (ri <= rn) return t;  // levels (prev, rn] all receive t
+      prev = rn;
+    }
+    t = tax_parent(ix, t);
+  } while (t != tax_parent(ix, t));
+  return ~0u;
+}
+
+// in-place ascending sort of u64 keys (heapsort above 24 entries: no recursion, O(n log n))
+CFR_HD void sort_u64(u64 *a, int n) {
+  if (n <= 24) {
+    for (int i = 1; i < n; ++i) {
+      const u64 x = a[i];
+      int j = i - 1;
+      while (j >= 0 && a[j] > x) {
+        a[j + 1] = a[j];
+        --j;
+      }
+      a[j + 1] = x;
+    }
+    return;
+  }
+  for (int start = n / 2 - 1; start >= 0; --start) {
+    int root = start;
+    for (;;) {
+      int child = 2 * root + 1;
+      if (child >= n) break;
+      if (child + 1 < n && a[child] < a[child + 1]) ++child;
+      if (a[root] >= a[child]) break;
+      const u64 tmp = a[root]; a[root] = a[child]; a[child] = tmp;
+      root = child;
+    }
+  }
+  for (int end = n - 1; end > 0; --end) {
+    u64 tmp = a[0]; a[0] = a[end]; a[end] = tmp;
+    int root = 0;
+    for (;;) {
+      int child = 2 * root + 1;
+      if (child >= end) break;
+      if (child + 1 < end && a[child] < a[child + 1]) ++child;
+      if (a[root] >= a[child]) break;
+      tmp = a[root]; a[root] = a[child]; a[child] = tmp;
+      root = child;
+    }
+  }
+}
+
+CFR_HD int unique_u64(u64 *a, int n) {
+  if (n == 0) return 0;
+  int m = 1;
+  for (int i = 1; i < n; ++i)
+    if (a[i] != a[m - 1]) a[m++] = a[i];
+  return m;
+}
+
+// Taxonomy::ReduceTaxIds (promotedChildTaxIds == NULL).  tax_ids[0..cnt) are the
+// compact tax ids of the best sequences (cnt > k guaranteed by the caller);
+// `scratch` has room for cnt entries.  Writes <= max(k,1) ids, ascending, to out.
+CFR_HD int tax_reduce(const DevIndex &ix, const u64 *tax_ids, int cnt, int k, u64 *scratch, u64 *out,
+                      u64 *err_flags) {
+  for (int i = 0; i < cnt; ++i)
+    if (tax_ids[i] >= ix.node_cnt) {  // Taxonomy.hpp:855-882
+      out[0] = ix.node_cnt;
+      return 1;
+    }
+  if (k == 1) {
+    out[0] = tax_lca(ix, tax_ids, cnt, err_flags);
+    return 1;
+  }
+  const int unknown = ix.rank_num[0];
+  for (int ri = 0; ri < unknown; ++ri) {  // Taxonomy.hpp:933-936
+    int m = 0;
+    for (int i = 0; i < cnt; ++i) {
+      const u32 node = tax_node_at_level(ix, (u32)tax_ids[i], ri);
+      if (node != ~0u) scratch[m++] = node;
+    }
+    sort_u64(scratch, m);
+    m = unique_u64(scratch, m);
+    if (m <= k) {
+      for (int i = 0; i < m; ++i) out[i] = scratch[i];
+      if (m == 0) {
+        out[0] = ix.root;
+        return 1;
+      }
+      return m;
+    }
+  }
+  out[0] = ix.root;  // level `unknown` is always empty
+  return 1;
+}
+
+// ---------------------------------------------------------------------------
+// Classifier: scoring (GetClassificationFromHits after the locate walks)
+// ---------------------------------------------------------------------------
+
+// sorted-by-seqId table standing in for std::map<size_t,_seqHitRecord>
+struct RecTable {
+  SeqRec *a;
+  int n;
+};
+
+CFR_HD int rec_lower_bound(const RecTable &t, u32 seq_id) {
+  int lo = 0, hi = t.n;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (t.a[mid].seq_id < seq_id) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+// operator[] semantics: default-constructs {score 0, hitLength 0} when absent
+CFR_HD SeqRec *rec_get(RecTable &t, u32 seq_id, bool &created) {
+  const int pos = rec_lower_bound(t, seq_id);
+  if (pos < t.n && t.a[pos].seq_id == seq_id) {
+    created = false;
+    return &t.a[pos];
+  }
+  for (int i = t.n; i > pos; --i) t.a[i] = t.a[i - 1];
+  t.a[pos].seq_id = seq_id;
+  t.a[pos].score = 0;
+  t.a[pos].hit_length = 0;
+  ++t.n;
+  created = true;
+  return &t.a[pos];
+}
+
+// Everything after the locate walks for one read.  `seq_ids` holds, hit after
+// hit, the located sequence ids (row_cnt entries per scored hit, same order as
+// the row plan).  rec0/rec1/best/tmp are per-read scratch with `arena_rows`
+// capacity each (a hit contributes at most row_cnt distinct ids).
+CFR_HD void score_read(const DevIndex &ix, const DevParams &p, const FinalHit *hits, int hit_cnt, u32 *seq_ids,
+                       SeqRec *rec0, SeqRec *rec1, u64 *best, u64 *tmp, DevResult &res, u64 *out_ids,
+                       u64 *err_flags) {
+  const int mhl = p.min_hit_len;
+  RecTable rec[2] = {{rec0, 0}, {rec1, 0}};
+  u32 prev_seq = 0;
+  u64 prev_score = 0;
+  int prev_len = 0;
+  bool mix_strand = false;
+  for (int i = 1; i < hit_cnt; ++i)
+    if (hits[i].strand != hits[i - 1].strand) {
+      mix_strand = true;
+      break;
+    }
+  u32 *ids = seq_ids;
+  for (int i = 0; i < hit_cnt; ++i) {
+    if (hits[i].l < mhl) continue;
+    const u64 score = hit_score(hits[i].l, mhl);
+    const int k = (hits[i].strand + 1) / 2;
+    int m = (int)hits[i].row_cnt;
+    // localSeqIdHit: ascending distinct ids of this hit
+    if (m <= 24) {
+      for (int a = 1; a < m; ++a) {
+        const u32 x = ids[a];
+        int b = a - 1;
+        while (b >= 0 && ids[b] > x) {
+          ids[b + 1] = ids[b];
+          --b;
+        }
+        ids[b + 1] = x;
+      }
+    } else {  // heapsort on u32
+      for (int start = m / 2 - 1; start >= 0; --start) {
+        int root = start;
+        for (;;) {
+          int child = 2 * root + 1;
+          if (child >= m) break;
+          if (child + 1 < m && ids[child] < ids[child + 1]) ++child;
+          if (ids[root] >= ids[child]) break;
+          const u32 t2 = ids[root]; ids[root] = ids[child]; ids[child] = t2;
+          root = child;
+        }
+      }
+      for (int end = m - 1; end > 0; --end) {
+        u32 t2 = ids[0]; ids[0] = ids[end]; ids[end] = t2;
+        int root = 0;
+        for (;;) {
+          int child = 2 * root + 1;
+          if (child >= end) break;
+          if (child + 1 < end && ids[child] < ids[child + 1]) ++child;
+          if (ids[root] >= ids[child]) break;
+          t2 = ids[root]; ids[root] = ids[child]; ids[child] = t2;
+          root = child;
+        }
+      }
+    }
+    const bool uniq = hits[i].ep == hits[i].sp;
+    const bool adjacent = !mix_strand && i > 0 && uniq && hits[i - 1].ep == hits[i - 1].sp &&
+                          hits[i - 1].strand == hits[i].strand &&
+                          hits[i - 1].offset + hits[i - 1].l + 1 == hits[i].offset;
+    for (int a = 0; a < m; ++a) {
+      const u32 seq_id = ids[a];
+      if (a > 0 && seq_id == ids[a - 1]) continue;
+      bool created;
+      if (adjacent && seq_id == prev_seq) {  // merge adjacent unique hits (Classifier.hpp:673-685)
+        SeqRec *r = rec_get(rec[k], seq_id, created);
+        r->score -= prev_score;
+        prev_len += hits[i].l;
+        prev_score = hit_score(prev_len, mhl);
+        r->score += prev_score;
+        r->hit_length += hits[i].l;
+      } else {
+        SeqRec *r = rec_get(rec[k], seq_id, created);
+        if (created) {
+          r->score = score;
+          r->hit_length = hits[i].l;
+        } else {
+          r->score += score;
+          r->hit_length += hits[i].l;
+        }
+        if (uniq) {
+          prev_seq = seq_id;
+          prev_score = score;
+          prev_len = hits[i].l;
+        }
+      }
+    }
+    ids += m;
+  }
+
+  // best / second best, strand 0 then strand 1, ascending seqId (Classifier.hpp:711-736)
+  u64 best_score = 0, second = 0, best_len = 0, second_len = 0;
+  for (int k = 0; k <= 1; ++k)
+    for (int i = 0; i < rec[k].n; ++i) {
+      const SeqRec &r = rec[k].a[i];
+      if (r.score > best_score) {
+        second = best_score;
+        second_len = best_len;
+        best_score = r.score;
+        best_len = (u64)(long long)r.hit_length;
+      } else if (r.score > second) {
+        second = r.score;
+        second_len = (u64)(long long)r.hit_length;
+      }
+    }
+  res.score = best_score;
+  res.secondary_score = second;
+  res.hit_length = (int)best_len;
+
+  int nb = 0;
+  for (int k = 0; k <= 1; ++k)  // Classifier.hpp:743-757
+    for (int i = 0; i < rec[k].n; ++i)
+      if (rec[k].a[i].score == best_score) {
+        const u64 id = rec[k].a[i].seq_id;
+        bool used = false;
+        for (int q = 0; q < nb; ++q)
+          if (best[q] == id) {
+            used = true;
+            break;
+          }
+        if (!used) best[nb++] = id;
+      }
+  if (nb > 1) res.secondary_score = best_score;
+  if (second_len >= p.secondary_len && second < best_score &&
+      second >= (u64)(p.secondary_factor * (double)best_score)) {  // Classifier.hpp:763-781
+    for (int k = 0; k <= 1; ++k)
+      for (int i = 0; i < rec[k].n; ++i)
+        if (rec[k].a[i].score == second) {
+          const u64 id = rec[k].a[i].seq_id;
+          bool used = false;
+          for (int q = 0; q < nb; ++q)
+            if (best[q] == id) {
+              used = true;
+              break;
+            }
+          if (!used) best[nb++] = id;
+        }
+    res.secondary_score = second;
+  }
+
+  if (nb <= p.max_result) {  // Classifier.hpp:784-797
+    for (int i = 0; i < nb; ++i) out_ids[i] = best[i];
+    res.n_assign = nb;
+    res.by_rank = 0;
+  } else {  // Classifier.hpp:798-841
+    for (int i = 0; i < nb; ++i) {
+      const u64 s = best[i];
+      best[i] = s < ix.seq_cnt ? (u64)ld32(ix.seq_to_tax + s) : ix.node_cnt;  // SeqIdToTaxId
+    }
+    res.n_assign = tax_reduce(ix, best, nb, p.max_result, tmp, out_ids, err_flags);
+    res.by_rank = 1;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// SDUST (Dustmasker.hpp), window 64, threshold 20, 5-symbol alphabet
+// ---------------------------------------------------------------------------
+//
+// The reference keeps the list P of "perfect intervals" as a std::vector that can
+// hold >1700 entries on low-complexity reads.  Only two facts about P are ever
+// used (Dustmasker.hpp:139-168, :200-224):
+//   (1) when the window start passes s, the LONGEST interval starting at s is
+//       masked (P.back()), and every interval starting at s is dropped;
+//   (2) FindPerfect compares the candidate suffix with the best score/length
+//       ratio among intervals whose start is >= the candidate's start.  A new
+//       interval is only inserted when its ratio is >= that maximum, so per start
+//       the most recent insertion carries both the largest end and the largest
+//       ratio of that start.
+// Interval ends are always the current window end, so they grow monotonically.
+// Hence one slot per start position (64 slots, indexed by start mod 64) is an
+// exact replacement for P: {score, span, end-start} of the latest insertion.
+// All ratio tests are cross-multiplications of positive integers (span >= 1 and
+// score >= 3 for every stored interval), so which of two equal ratios is kept
+// does not change any outcome.
+
+struct DustState {
+  unsigned char cw[125], cv[125];  // triplet counts, base-5 index
+  unsigned char win[64];           // ring buffer of triplet indices; size <= 62
+  unsigned short p_score[64];      // per start slot: score of the latest interval
+  unsigned char p_span[64];        // its end - start - 2
+  unsigned char p_len[64];         // its end - start
+  u64 p_valid;
+  int head, size;
+  int rv, rw, lv;
+};
+
+CFR_HD int dust_code(unsigned char c) { return base_code(c); }
+
+CFR_HD int dust_win_at(const DustState &d, int i) { return d.win[(d.head + i) & 63]; }
+
+// Dustmasker::SaveMaskedRegions for the single start that can leave the window
+CFR_HD void dust_evict(DustState &d, unsigned char *out, int seg_off, int start) {
+  const int slot = start & 63;
+  if ((d.p_valid >> slot) & 1ull) {
+    const int e = start + d.p_len[slot];
+    for (int q = start; q <= e; ++q) out[seg_off + q] = 'N';
+    d.p_valid &= ~(1ull << slot);
+  }
+}
+
+// SDust on S[0..n): masks into out[seg_off ...]
+CFR_HD void dust_sdust(const unsigned char *S, int n, unsigned char *out, int seg_off, DustState &d) {
+  const int W = 64, T = 20;
+  if (n < 3) return;
+  for (int i = 0; i < 125; ++i) d.cw[i] = d.cv[i] = 0;
+  d.head = d.size = 0;
+  d.rv = d.rw = d.lv = 0;
+  d.p_valid = 0;
+  int c1 = dust_code(ld8(S)), c2 = dust_code(ld8(S + 1));
+  int wfinish, wstart = 0;
+  for (wfinish = 2; wfinish < n; ++wfinish) {
+    wstart = 0;
+    if (wfinish + 1 > W) wstart = wfinish + 1 - W;
+    if (wstart > 0) dust_evict(d, out, seg_off, wstart - 1);
+    const int c3 = dust_code(ld8(S + wfinish));
+    const int t = c1 * 25 + c2 * 5 + c3;
+    c1 = c2;
+    c2 = c3;
+    // ShiftWindow (Dustmasker.hpp:106-136)
+    if (d.size >= W - 2) {
+      const int old = d.win[d.head];
+      --d.cw[old];
+      d.rw -= d.cw[old];
+      d.head = (d.head + 1) & 63;
+      --d.size;
+      if (d.lv > d.size) {
+        --d.cv[old];
+        d.rv -= d.cv[old];
+        --d.lv;
+      }
+    }
+    d.win[(d.head + d.size) & 63] = (unsigned char)t;
+    ++d.size;
+    ++d.lv;
+    d.rw += d.cw[t];
+    ++d.cw[t];
+    d.rv += d.cv[t];
+    ++d.cv[t];
+    if (d.cv[t] * 10 > 2 * T) {
+      for (;;) {
+        const int s = dust_win_at(d, d.size - d.lv);
+        --d.cv[s];
+        d.rv -= d.cv[s];
+        --d.lv;
+        if (s == t) break;
+      }
+    }
+    if (d.rw * 10 > d.lv * T) {  // FindPerfect (Dustmasker.hpp:173-242)
+      int rv = d.rv;
+      int max_score = 0, max_cnt = 1;
+      int folded = wstart + d.size;  // starts >= folded have been folded into (max_score, max_cnt)
+      for (int i = d.size - d.lv - 1; i >= 0; --i) {
+        const int tt = dust_win_at(d, i);
+        rv += d.cv[tt];
+        ++d.cv[tt];
+        const int span = d.size - i - 1;
+        if (rv * 10 > T * span) {
+          const int start = i + wstart;
+          while (folded > start) {  // the scan of P from its head (:203-211)
+            --folded;
+            const int slot = folded & 63;
+            if ((d.p_valid >> slot) & 1ull) {
+              if ((u64)d.p_score[slot] * (u64)max_cnt > (u64)max_score * (u64)d.p_span[slot]) {
+                max_score = d.p_score[slot];
+                max_cnt = d.p_span[slot];
+              }
+            }
+          }
+          if (rv * max_cnt >= max_score * span) {
+            max_score = rv;
+            max_cnt = span;
+            const int slot = start & 63;
+            d.p_score[slot] = (unsigned short)rv;
+            d.p_span[slot] = (unsigned char)span;
+            d.p_len[slot] = (unsigned char)(wstart + d.size + 1 - start);
+            d.p_valid |= 1ull << slot;
+          }
+        }
+      }
+      for (int i = d.size - d.lv - 1; i >= 0; --i) --d.cv[dust_win_at(d, i)];
+    }
+  }
+  // the tail loop of Dustmasker.hpp:343-350 saves every remaining start
+  int base = 0;
+  if (wfinish + 1 > W) base = wfinish + 1 - W;
+  if (base > 0) --base;  // the last in-loop save ran with wstart(n-1) = base - 1 ... so start base-1 may remain
+  for (int s = base; s < base + 64; ++s) dust_evict(d, out, seg_off, s);  // every slot exactly once
+}
+
+// Dustmasker::MaskWithBuffer + the in-place masking of CentrifugerClass.cpp:281-289.
+// `in` is the mate as uploaded, `out` the working copy the searches read.
+CFR_HD void dust_task(const unsigned char *in, int n, unsigned char *out, DustState &d) {
+  const int W = 64;
+  if (n < 3) return;
+  int i = 0;
+  while (i < n && dust_code(ld8(in + i)) == 4) ++i;
+  while (i < n) {
+    int n_count = 0, last_valid = i, j;
+    for (j = i; j < n; ++j) {
+      if (dust_code(ld8(in + j)) == 4)
+        ++n_count;
+      else {
+        if (n_count > W) break;
+        last_valid = j;
+        n_count = 0;
+      }
+    }
+    if (last_valid > i) dust_sdust(in + i, last_valid - i + 1, out, i, d);
+    i = j;
+  }
+}
+
+}  // namespace cfrb200

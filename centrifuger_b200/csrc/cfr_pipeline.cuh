@@ -1,0 +1,191 @@
+// cfr_pipeline.cuh -- the stages of one classification pass over a read chunk.
+//
+// Stage          unit of work                 reference code it replaces
+//   dust_stage     one mate                     CentrifugerClass.cpp:276-316 (Dustmasker::MaskWithBuffer)
+//   search_stage   one (read, mate, strand)     Classifier::GetHitsFromRead              Classifier.hpp:274
+//   select_stage   one read                     AdjustHitBoundaryFromStrandHits + strand pick :303,:509
+//                                               + the row plan of GetClassificationFromHits :620-666
+//   locate_stage   one BWT row                  FMIndex::BackwardToSampledSA             FMIndex.hpp:514
+//   score_stage    one read                     GetClassificationFromHits :668-843 + Taxonomy::ReduceTaxIds
+//
+// Each stage is a plain per-task function (compiled for the device by nvcc and
+// for the host by the tests' simulation harness); cfr_kernels.cu wraps them in
+// grid-stride __global__ kernels.
+#pragma once
+#include "cfr_core.cuh"
+
+namespace cfrb200 {
+
+#define CFR_ROW_SENTINEL (~0ull)
+
+struct ChunkDev {
+  u64 n_reads;
+  int mates;  // 1 or 2
+  int cap_h;  // hit slots per strand task
+  const unsigned char *seq_raw;  // bases as uploaded
+  unsigned char *seq;            // working copy the searches read (DUST-masked)
+  const u64 *off[2];             // per mate: n_reads + 1 offsets into seq
+  Hit *strand_hits;              // [n_reads * 2*mates * cap_h]
+  int *strand_nhits;             // [n_reads * 2*mates]
+  FinalHit *fhits;               // [n_reads * 2*mates * cap_h]
+  ReadWork *work;                // [n_reads]
+  // locate / scoring arena, one slot per planned BWT row
+  u64 arena_cap;
+  u64 *arena_used;
+  u64 *rows;
+  u32 *seq_ids;
+  SeqRec *rec0, *rec1;
+  u64 *best, *tmp;
+  // outputs
+  DevResult *results;  // [n_reads]
+  u64 *out_ids;        // [n_reads * max_result]
+  u64 *taxon_counts;   // [node_cnt + 3]
+  DevCounters *counters;
+  // reads that did not fit the arena in this pass
+  u32 *deferred;
+  u32 *n_deferred;
+  const u32 *read_list;  // nullptr = identity
+  u64 n_list;
+};
+
+CFR_HD u64 chunk_read_id(const ChunkDev &B, u64 t) { return B.read_list ? (u64)B.read_list[t] : t; }
+
+// ------------------------------------------------------------------ dust
+CFR_HD void dust_stage(const ChunkDev &B, u64 task, DustState &d) {
+  const u64 read = task / (u64)B.mates;
+  const int mate = (int)(task % (u64)B.mates);
+  const u64 base = B.off[mate][read];
+  const int len = (int)(B.off[mate][read + 1] - base);
+  dust_task(B.seq_raw + base, len, B.seq + base, d);
+}
+
+// ------------------------------------------------------------------ search
+// task = read * (2*mates) + mate*2 + s, s = 1: the mate as read (strandHits[1]),
+// s = 0: its reverse complement (strandHits[0])
+template <class Bwt>
+CFR_HD void search_stage(const DevIndex &ix, const DevParams &P, const ChunkDev &B, u64 task, OpCount &oc) {
+  const int S = 2 * B.mates;
+  const u64 read = task / (u64)S;
+  const int w = (int)(task % (u64)S);
+  const int mate = w >> 1;
+  const u64 base = B.off[mate][read];
+  const int len = (int)(B.off[mate][read + 1] - base);
+  StrandSeq s{B.seq + base, len, (w & 1) ? 0 : 1};
+  B.strand_nhits[task] = get_hits_from_read<Bwt>(ix, s, P.min_hit_len, B.strand_hits + task * (u64)B.cap_h, B.cap_h, oc);
+}
+
+// ------------------------------------------------------------------ select
+// Phase A: boundary adjustment, strand choice, final hit list, row plan.
+// Returns the number of arena rows the read needs.
+template <class Bwt>
+CFR_HD u32 select_plan(const DevIndex &ix, const DevParams &P, const ChunkDev &B, u64 read, OpCount &oc) {
+  const int S = 2 * B.mates;
+  const int mhl = P.min_hit_len;
+  Hit *h[2][2];
+  int n[2][2];
+  int qlen = 0;
+  for (int m = 0; m < B.mates; ++m) {
+    const u64 base = B.off[m][read];
+    const int len = (int)(B.off[m][read + 1] - base);
+    qlen += len;
+    for (int s = 0; s < 2; ++s) {
+      const u64 task = read * (u64)S + (u64)(m * 2 + s);
+      h[m][s] = B.strand_hits + task * (u64)B.cap_h;
+      n[m][s] = B.strand_nhits[task];
+    }
+    adjust_hit_boundary<Bwt>(ix, B.seq + base, len, h[m][0], n[m][0], h[m][1], n[m][1], oc);
+  }
+  B.results[read].query_length = qlen;
+  // template strand k: mate-1 hits of strand k, then mate-2 hits of strand 1-k (Classifier.hpp:551-552)
+  u64 score[2] = {0, 0};
+  for (int k = 0; k < 2; ++k) {
+    for (int i = 0; i < n[0][k]; ++i) score[k] += hit_score(h[0][k][i].l, mhl);
+    if (B.mates == 2)
+      for (int i = 0; i < n[1][1 - k]; ++i) score[k] += hit_score(h[1][1 - k][i].l, mhl);
+  }
+  int order[2], norder;
+  if (score[1] > score[0] + score[0] / 100) {
+    order[0] = 1;
+    norder = 1;
+  } else if (score[0] > score[1] + score[1] / 100) {
+    order[0] = 0;
+    norder = 1;
+  } else {
+    order[0] = 1;
+    order[1] = 0;
+    norder = 2;
+  }
+  FinalHit *fh = B.fhits + read * (u64)S * (u64)B.cap_h;
+  u32 nh = 0;
+  u64 rows = 0;
+  for (int q = 0; q < norder; ++q) {
+    const int k = order[q];
+    for (int part = 0; part < B.mates; ++part) {
+      const Hit *src = part == 0 ? h[0][k] : h[1][1 - k];
+      const int cnt = part == 0 ? n[0][k] : n[1][1 - k];
+      for (int i = 0; i < cnt; ++i) {
+        FinalHit f;
+        f.sp = src[i].sp;
+        f.ep = src[i].ep;
+        f.l = src[i].l;
+        f.offset = src[i].offset;
+        f.strand = 2 * k - 1;
+        f.row_cnt = 0;
+        if (f.l >= mhl) {
+          const RowPlan rp = plan_rows(f.sp, f.ep, P);
+          f.row_cnt = rp.total > 0xffffffffull ? 0xffffffffu : (u32)rp.total;
+          rows += rp.total;
+        }
+        fh[nh++] = f;
+      }
+    }
+  }
+  B.work[read].n_hits = nh;
+  B.work[read].arena_rows = rows > 0xffffffffull ? 0xffffffffu : (u32)rows;
+  return B.work[read].arena_rows;
+}
+
+// Phase B: with the arena slice known, expand the planned rows.
+CFR_HD void select_write_rows(const DevParams &P, const ChunkDev &B, u64 read, u64 arena_base, bool fits) {
+  const int S = 2 * B.mates;
+  ReadWork &w = B.work[read];
+  w.arena_base = arena_base;
+  w.status = fits ? 0 : 1;
+  if (!fits) return;
+  const FinalHit *fh = B.fhits + read * (u64)S * (u64)B.cap_h;
+  u64 o = arena_base;
+  for (u32 i = 0; i < w.n_hits; ++i) {
+    if (fh[i].row_cnt == 0) continue;
+    const RowPlan rp = plan_rows(fh[i].sp, fh[i].ep, P);
+    for (u64 t = 0; t < rp.total; ++t) B.rows[o++] = plan_row_at(fh[i].sp, fh[i].ep, rp, t);
+  }
+}
+
+// ------------------------------------------------------------------ locate
+template <class Bwt>
+CFR_HD void locate_stage(const DevIndex &ix, const ChunkDev &B, u64 slot, OpCount &oc) {
+  const u64 row = B.rows[slot];
+  if (row == CFR_ROW_SENTINEL) return;
+  B.seq_ids[slot] = (u32)locate_row<Bwt>(ix, row, oc);
+}
+
+// ------------------------------------------------------------------ score
+// returns the number of assignments (for the classified counter)
+CFR_HD int score_stage(const DevIndex &ix, const DevParams &P, const ChunkDev &B, u64 read, u64 *err_flags) {
+  const int S = 2 * B.mates;
+  const ReadWork &w = B.work[read];
+  const FinalHit *fh = B.fhits + read * (u64)S * (u64)B.cap_h;
+  DevResult res = B.results[read];  // query_length was filled by select_plan
+  res.score = res.secondary_score = 0;
+  res.hit_length = 0;
+  res.n_assign = 0;
+  res.by_rank = 0;
+  u64 *out = B.out_ids + read * (u64)P.max_result;
+  const u64 a = w.arena_base;
+  score_read(ix, P, fh, (int)w.n_hits, B.seq_ids + a, B.rec0 + a, B.rec1 + a, B.best + a, B.tmp + a, res, out,
+             err_flags);
+  B.results[read] = res;
+  return res.n_assign;
+}
+
+}  // namespace cfrb200

@@ -1,0 +1,129 @@
+// cfr_types.h -- PODs shared by the host runtime and the device kernels.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define CFR_HD __host__ __device__ __forceinline__
+#define CFR_D __device__ __forceinline__
+#else
+#define CFR_HD inline
+#define CFR_D inline
+#endif
+
+namespace cfrb200 {
+
+typedef unsigned long long u64;
+typedef unsigned int u32;
+
+struct u64x2 {
+  u64 x, y;
+};
+
+// rank9 bitvector as stored by the reference (Bitvector_Plain + DS_Rank9)
+struct DevBV {
+  const u64 *B;
+  const u64 *R;
+  u64 n;
+};
+
+// 3-node wavelet tree over {A,C,G,T} = codes {00,01,10,11}
+struct DevWT {
+  DevBV node[3];
+  int child[3][2];
+  u64 n;
+};
+
+// One 64-byte occ line of the transcoded layout: 128 BWT symbols.
+//   cnt[c]  = # of symbol c in BWT[0 .. 128*line)
+//   lo/hi   = bit planes of the 128 two-bit symbol codes (w = 64-symbol half)
+struct alignas(64) OccLine {
+  u64 cnt[4];
+  u64 lo0, hi0, lo1, hi1;
+};
+
+struct DevIndex {
+  // FM-index scalars (FMIndex.hpp:191-199)
+  u64 n;
+  u64 first_isa;
+  int last_code;  // code of _lastChr
+  u64 C[5];       // _plainAlphabetPartialSum
+  // run-block BWT exactly as stored (Sequence_RunBlock.hpp:15-20)
+  u64 b, block_cnt;
+  DevBV block_type;
+  DevWT plain, run;
+  // transcoded layout (nullptr when not built)
+  const OccLine *occ;
+  // locate (FMIndex.hpp:13-41)
+  int sample_rate;
+  int sa_bits;
+  const u64 *sampled_sa;
+  u64 adjusted_sa0;
+  const u64x2 *sel;  // {row, seqId}, ascending row
+  u64 sel_cnt;
+  const u64 *sel_filter;
+  int sel_filter_rate;
+  // 10-mer (precomputeWidth-mer) lookup table
+  int pre_width;
+  const u64x2 *lookup;  // {start, len}
+  // taxonomy (Taxonomy.hpp)
+  u64 node_cnt, seq_cnt, root;
+  const u32 *parent;
+  const unsigned char *rank;
+  const u32 *seq_to_tax;  // value node_cnt = unknown
+  unsigned char rank_num[32];
+};
+
+struct DevParams {
+  int max_result;
+  int min_hit_len;
+  int hitk_factor;
+  u64 secondary_len;
+  double secondary_factor;
+};
+
+// Classifier.hpp:70-85 (_BWTHit); strand is kept in the low bits of `meta`
+struct Hit {
+  u64 sp, ep;
+  int l;
+  int offset;
+};
+
+struct FinalHit {
+  u64 sp, ep;
+  int l;
+  int offset;
+  int strand;   // -1 / +1 (template strand, Classifier.hpp:560)
+  u32 row_cnt;  // rows expanded for locate
+};
+
+// per-read bookkeeping between the pipeline stages
+struct ReadWork {
+  u64 arena_base;  // first arena row of this read
+  u32 arena_rows;  // rows reserved
+  u32 n_hits;      // final hits
+  int status;      // 0 ok, 1 deferred (arena full)
+};
+
+struct SeqRec {  // value of std::map<size_t,_seqHitRecord> (Classifier.hpp:62-67,590)
+  u64 score;
+  u32 seq_id;
+  int hit_length;
+};
+
+struct DevResult {  // mirrors cfr_result
+  u64 score;
+  u64 secondary_score;
+  int hit_length;
+  int query_length;
+  int n_assign;
+  int by_rank;
+};
+
+struct DevCounters {
+  u64 n_rank, n_access, n_search, n_locate, n_lf, n_extend, n_bases, n_reads;
+  u64 error_flags;  // bit 0: taxonomy path deeper than the device cap
+};
+
+enum { CFR_TAX_PATH_CAP = 128 };
+
+}  // namespace cfrb200

@@ -1,0 +1,161 @@
+/*
+ * centrifuger_b200.h -- C ABI of the B200-native classification path.
+ *
+ * This is the drop-in boundary for the reference's
+ *     Classifier<Sequence_RunBlock>::Init(char *idxPrefix, _classifierParam)   Classifier.hpp:902
+ *     Classifier<Sequence_RunBlock>::Query(char *r1, char *r2, _classifierResult&) Classifier.hpp:950
+ * as they are driven, one batch at a time, from ClassifyReads_Thread
+ * (CentrifugerClass.cpp:240-340, incl. the DUST masking at :276-316), plus the
+ * name/taxonomy look-ups ResultWriter::Output needs (ResultWriter.hpp:199-236).
+ *
+ * Plain C, plain pointers and sizes; no torch / C++ types.  One handle per GPU;
+ * calls on one handle are stream-ordered and must not overlap; different
+ * handles are independent.  All functions return CFR_OK (0) or a negative
+ * cfr_status; cfr_last_error() gives the message.  There is NO CPU fallback:
+ * without a usable CUDA device every entry point fails with CFR_ERR_CUDA.
+ */
+#ifndef CENTRIFUGER_B200_H
+#define CENTRIFUGER_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CFR_B200_ABI_VERSION 1
+
+typedef enum {
+  CFR_OK = 0,
+  CFR_ERR_ARG = -1,          /* bad argument */
+  CFR_ERR_IO = -2,           /* index file missing / short */
+  CFR_ERR_FORMAT = -3,       /* .cfr grammar mismatch */
+  CFR_ERR_UNSUPPORTED = -4,  /* protein index, non-ACGT alphabet, k <= 0 ... */
+  CFR_ERR_CUDA = -5,         /* no device / CUDA runtime error */
+  CFR_ERR_NOMEM = -6,
+  CFR_ERR_OVERFLOW = -7      /* a per-read device work area was exceeded */
+} cfr_status;
+
+/* In-HBM layout of the BWT.  The *.cfr files are always read unchanged. */
+typedef enum {
+  CFR_LAYOUT_AUTO = 0,
+  CFR_LAYOUT_RUNBLOCK = 1, /* the run-block arrays exactly as stored (rank9 + wavelet trees) */
+  CFR_LAYOUT_OCCLINE = 2   /* transcoded on the GPU at load into 64-byte occ lines */
+} cfr_layout;
+
+/* replaces _classifierParam (Classifier.hpp:17-38) + the --no-dust switch
+ * (CentrifugerClass.cpp:367) */
+typedef struct {
+  int32_t max_result;                /* -k            [1]  */
+  int32_t min_hit_len;               /* --min-hitlen  [0 = infer, Classifier.hpp:113-129] */
+  int32_t max_result_per_hit_factor; /* --hitk-factor [40] */
+  int32_t dust;                      /* 1 = SDUST-mask reads first (reference default) */
+  uint64_t consider_secondary_hit_len;    /* [2000]  */
+  double consider_secondary_score_factor; /* [0.995] */
+  int32_t layout;                    /* cfr_layout */
+  int32_t max_batch_reads;           /* device chunk size, 0 = default */
+  uint64_t arena_rows;               /* locate work-area rows per chunk, 0 = default */
+} cfr_params;
+
+/* One batch of reads, structure-of-arrays, HOST memory (pinned recommended).
+ * Read i of mate m is seq[m][off[m][i] .. off[m][i+1]).  seq2/off2 NULL for
+ * single-end.  Bytes are used as given (no upper-casing; any byte outside
+ * "ACGT" stops a match, FMIndex.hpp:396,500). */
+typedef struct {
+  uint64_t n_reads;
+  const char *seq1;
+  const uint64_t *off1; /* n_reads + 1 entries */
+  const char *seq2;
+  const uint64_t *off2; /* n_reads + 1 entries, or NULL */
+} cfr_read_batch;
+
+/* replaces _classifierResult (Classifier.hpp:41-59).  The assignment ids of
+ * read i are ids[i*max_result .. i*max_result + min(n_assign, max_result)). */
+typedef struct {
+  uint64_t score;
+  uint64_t secondary_score;
+  int32_t hit_length;
+  int32_t query_length;
+  int32_t n_assign; /* 0 = unclassified */
+  int32_t by_rank;  /* 0: ids are sequence ids; 1: ids are compact taxonomy ids
+                       produced by Taxonomy::ReduceTaxIds (Classifier.hpp:798-841) */
+} cfr_result;
+
+/* operation counters, accumulated since the last reset; they feed the
+ * algorithmic-bytes formula of SURVEY.md 8(d) */
+typedef struct {
+  uint64_t n_rank;    /* Sequence_RunBlock::Rank-equivalent queries */
+  uint64_t n_access;  /* Sequence_RunBlock::Access-equivalent queries */
+  uint64_t n_search;  /* lookup-table probes (BackwardSearch calls) */
+  uint64_t n_locate;  /* resolved BWT rows */
+  uint64_t n_lf;      /* LF steps in locate walks */
+  uint64_t n_extend;  /* range BackwardExtend steps */
+  uint64_t n_bases;   /* read bases consumed */
+  uint64_t n_reads;   /* reads (pairs) classified */
+  uint64_t n_launches;/* kernels launched by this library */
+} cfr_counters;
+
+typedef struct cfr_handle cfr_handle;
+typedef struct cfr_device_batch cfr_device_batch;
+
+void cfr_default_params(cfr_params *p);
+
+/* Classifier::Init: parse <prefix>.1.cfr/.2.cfr (and .4.cfr for the sequence
+ * type), upload to `device`'s HBM. */
+int cfr_open(const char *idx_prefix, const cfr_params *p, int device, cfr_handle **out);
+void cfr_close(cfr_handle *h);
+const char *cfr_last_error(void);
+
+/* ClassifyReads_Thread for one batch: H2D, [DUST], search, locate, score,
+ * LCA, D2H.  `stream` is a cudaStream_t (NULL = the handle's own stream); the
+ * call returns after the results are in `results`/`ids` (host memory). */
+int cfr_classify_batch(cfr_handle *h, const cfr_read_batch *in, cfr_result *results,
+                       uint64_t *ids, void *stream);
+
+/* Same work with the batch already resident in HBM (kernel-only timing;
+ * multi-GPU shards).  upload = H2D + layout; classify_resident = kernels
+ * only, asynchronous on `stream`; fetch = D2H + synchronize. */
+int cfr_batch_upload(cfr_handle *h, const cfr_read_batch *in, void *stream, cfr_device_batch **out);
+int cfr_classify_resident(cfr_handle *h, cfr_device_batch *b, void *stream);
+int cfr_batch_fetch(cfr_handle *h, cfr_device_batch *b, cfr_result *results, uint64_t *ids, void *stream);
+void cfr_batch_free(cfr_handle *h, cfr_device_batch *b);
+
+/* index facts: 0 n, 1 b, 2 blockCnt, 3 firstISA, 4 min_hit_len in effect,
+ * 5 nodeCnt, 6 seqCnt(+extra), 7 root ctid, 8 layout in use, 9 HBM bytes held,
+ * 10 sampleRate, 11 precomputeWidth, 12 max_result */
+uint64_t cfr_index_info(const cfr_handle *h, int which);
+
+/* Taxonomy look-ups used by ResultWriter (host tables) */
+const char *cfr_seq_name(const cfr_handle *h, uint64_t seq_id);   /* Taxonomy::SeqIdToName   :704 */
+const char *cfr_rank_name(const cfr_handle *h, uint64_t ctid);    /* GetTaxRankString(GetTaxIdRank) :497/:659 */
+uint64_t cfr_orig_taxid(const cfr_handle *h, uint64_t ctid);      /* Taxonomy::GetOrigTaxId   :633 */
+uint64_t cfr_seq_taxid(const cfr_handle *h, uint64_t seq_id);     /* Taxonomy::SeqIdToTaxId   :718 */
+
+/* ResultWriter::Output (ResultWriter.hpp:199-236): TSV row(s) of one read.
+ * Returns bytes written or CFR_ERR_ARG if cap is too small. */
+int cfr_format_tsv(const cfr_handle *h, const char *read_id, const cfr_result *r,
+                   const uint64_t *ids, char *buf, size_t cap);
+
+/* Per-taxon assignment counters kept in HBM (uint64[nodeCnt + 3]: reads
+ * assigned per compact taxId, slot nodeCnt = unknown/root, then {reads,
+ * classified}).  The device pointer is handed out so the caller can
+ * all-reduce it over NCCL; cfr_taxon_counts_read copies it to the host. */
+int cfr_taxon_counts_device(cfr_handle *h, void **dev_ptr, uint64_t *n_entries);
+int cfr_taxon_counts_read(cfr_handle *h, uint64_t *out, uint64_t n_entries, void *stream);
+int cfr_taxon_counts_reset(cfr_handle *h, void *stream);
+
+int cfr_get_counters(cfr_handle *h, cfr_counters *c, void *stream);
+int cfr_reset_counters(cfr_handle *h, void *stream);
+
+/* Diagnostics used by the parity tests (device results copied to host). */
+int cfr_debug_bwt_rank(cfr_handle *h, const uint8_t *codes, const uint64_t *pos, const int32_t *inclusive,
+                       uint64_t n, uint64_t *out);   /* Sequence_RunBlock::Rank  Sequence_RunBlock.hpp:378 */
+int cfr_debug_bwt_access(cfr_handle *h, const uint64_t *pos, uint64_t n, uint8_t *out); /* ::Access :360 */
+int cfr_debug_locate(cfr_handle *h, const uint64_t *rows, uint64_t n, uint64_t *seq_ids); /* FMIndex::BackwardToSampledSA FMIndex.hpp:514 */
+int cfr_debug_dust(cfr_handle *h, const cfr_read_batch *in, char *masked1, char *masked2); /* Dustmasker.hpp:357 */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

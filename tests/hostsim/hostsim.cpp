@@ -1,0 +1,303 @@
+// hostsim.cpp -- TEST INFRASTRUCTURE: runs the product's per-task stage functions
+// (centrifuger_b200/csrc/cfr_core.cuh, cfr_pipeline.cuh) sequentially on the host
+// so the classification logic can be debugged in a container without a GPU.
+// It is compiled only by tests/ (g++ -DCFR_HOSTSIM); the shipped library never
+// contains it and has no CPU path.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../centrifuger_b200/csrc/cfr_format.hpp"
+#include "../../centrifuger_b200/csrc/cfr_pipeline.cuh"
+#include "../../include/centrifuger_b200.h"
+
+using namespace cfrb200;
+
+namespace {
+
+struct HostIndex {
+  CfrIndexFile file;
+  std::vector<std::vector<u64>> bufs;
+  std::vector<u32> parent, seq_to_tax;
+  std::vector<unsigned char> rank;
+  std::vector<u64> sel_filter;
+  std::vector<OccLine> occ;
+  DevIndex ix;
+  DevParams P;
+  int layout;
+  std::string err;
+
+  const u64 *copy_words(const uint8_t *p, u64 words) {
+    bufs.emplace_back(words + 2, 0);
+    if (p && words) memcpy(bufs.back().data(), p, words * 8);
+    return bufs.back().data();
+  }
+  DevBV mk_bv(const BvView &v) {
+    DevBV d;
+    d.n = v.nbits;
+    d.B = v.nbits ? copy_words(v.B, v.words) : nullptr;
+    d.R = v.nbits ? copy_words(v.R, v.rwords) : nullptr;
+    return d;
+  }
+  DevWT mk_wt(const WtView &t) {
+    DevWT d;
+    memset(&d, 0, sizeof(d));
+    d.n = t.n;
+    for (int i = 0; i < 3; ++i) {
+      d.child[i][0] = t.child[i][0];
+      d.child[i][1] = t.child[i][1];
+      if (i < t.node_cnt) d.node[i] = mk_bv(t.node[i]);
+    }
+    return d;
+  }
+};
+
+}  // namespace
+
+extern "C" {
+
+void *hostsim_open(const char *prefix, const cfr_params *p) {
+  HostIndex *h = new HostIndex();
+  int st = h->file.load(prefix, h->err);
+  if (st != 0) {
+    fprintf(stderr, "hostsim: %s\n", h->err.c_str());
+    delete h;
+    return nullptr;
+  }
+  CfrIndexFile &f = h->file;
+  DevIndex &ix = h->ix;
+  memset(&ix, 0, sizeof(ix));
+  ix.n = f.n;
+  ix.first_isa = f.first_isa;
+  ix.last_code = base_code((unsigned char)f.last_chr);
+  for (int i = 0; i < 5; ++i) ix.C[i] = f.C[i];
+  ix.b = f.b;
+  ix.block_cnt = f.block_cnt;
+  ix.block_type = h->mk_bv(f.block_type);
+  ix.plain = h->mk_wt(f.plain);
+  ix.run = h->mk_wt(f.run);
+  ix.sample_rate = f.sample_rate;
+  ix.sa_bits = f.sa_bits;
+  ix.sampled_sa = h->copy_words(f.sa_w, f.sa_words);
+  ix.adjusted_sa0 = f.adjusted_sa0;
+  ix.sel = (const u64x2 *)h->copy_words(f.sel, f.sel_cnt * 2);
+  ix.sel_cnt = f.sel_cnt;
+  ix.sel_filter_rate = f.sel_filter_rate;
+  if (f.sel_cnt > 0) {
+    u64 fbits = (f.n + f.sel_filter_rate - 1) / f.sel_filter_rate;
+    h->sel_filter.assign(fbits / 64 + 2, 0);
+    for (u64 i = 0; i < f.sel_cnt; ++i) {
+      u64 fb = load_u64(f.sel + i * 16) / (u64)f.sel_filter_rate;
+      h->sel_filter[fb >> 6] |= 1ull << (fb & 63);
+    }
+    ix.sel_filter = h->sel_filter.data();
+  }
+  ix.pre_width = (int)f.precompute_width;
+  ix.lookup = (const u64x2 *)h->copy_words(f.lookup, f.precompute_size * 2);
+  ix.node_cnt = f.tax.node_cnt;
+  ix.seq_cnt = f.tax.seq_cnt;
+  ix.root = f.tax.root;
+  h->parent.resize(f.tax.node_cnt + 1);
+  h->rank.resize(f.tax.node_cnt + 1);
+  for (u64 i = 0; i < f.tax.node_cnt; ++i) {
+    h->parent[i] = (u32)f.tax.parent[i];
+    h->rank[i] = f.tax.rank[i];
+  }
+  h->seq_to_tax.resize(f.tax.seq_cnt + 1);
+  for (u64 i = 0; i < f.tax.seq_cnt; ++i)
+    h->seq_to_tax[i] = f.tax.seq_to_tax[i] >= f.tax.node_cnt ? (u32)f.tax.node_cnt : (u32)f.tax.seq_to_tax[i];
+  ix.parent = h->parent.data();
+  ix.rank = h->rank.data();
+  ix.seq_to_tax = h->seq_to_tax.data();
+  init_tax_rank_num(ix.rank_num);
+  h->layout = p->layout == CFR_LAYOUT_OCCLINE ? 2 : 1;
+  if (h->layout == 2) {  // same construction the transcode kernel performs
+    const u64 lines = f.n / 128 + 1;
+    h->occ.resize(lines);
+    for (u64 L = 0; L < lines; ++L) {
+      OccLine o;
+      memset(&o, 0, sizeof(o));
+      for (int c = 0; c < 4; ++c) o.cnt[c] = rb_rank(ix, c, L * 128, 0);
+      for (int w = 0; w < 128; ++w) {
+        const u64 pos = L * 128 + (u64)w;
+        if (pos >= f.n) break;
+        const int s = rb_access(ix, pos);
+        u64 &lo = w < 64 ? o.lo0 : o.lo1, &hi = w < 64 ? o.hi0 : o.hi1;
+        lo |= (u64)(s & 1) << (w & 63);
+        hi |= (u64)(s >> 1) << (w & 63);
+      }
+      h->occ[L] = o;
+    }
+    ix.occ = h->occ.data();
+  }
+  h->P.max_result = p->max_result;
+  h->P.min_hit_len = p->min_hit_len > 0 ? p->min_hit_len : infer_min_hit_len(f.n);
+  h->P.hitk_factor = p->max_result_per_hit_factor;
+  h->P.secondary_len = p->consider_secondary_hit_len;
+  h->P.secondary_factor = p->consider_secondary_score_factor;
+  return h;
+}
+
+void hostsim_close(void *hh) { delete (HostIndex *)hh; }
+
+int hostsim_min_hit_len(void *hh) { return ((HostIndex *)hh)->P.min_hit_len; }
+
+uint64_t hostsim_bwt_rank(void *hh, int c, uint64_t i, int inclusive) {
+  HostIndex *h = (HostIndex *)hh;
+  return h->layout == 2 ? BwtOccLine::rank(h->ix, c, i, inclusive) : BwtRunBlock::rank(h->ix, c, i, inclusive);
+}
+int hostsim_bwt_access(void *hh, uint64_t i) {
+  HostIndex *h = (HostIndex *)hh;
+  return h->layout == 2 ? BwtOccLine::access(h->ix, i) : BwtRunBlock::access(h->ix, i);
+}
+uint64_t hostsim_locate(void *hh, uint64_t row) {
+  HostIndex *h = (HostIndex *)hh;
+  OpCount oc{};
+  return h->layout == 2 ? locate_row<BwtOccLine>(h->ix, row, oc) : locate_row<BwtRunBlock>(h->ix, row, oc);
+}
+
+void hostsim_dust(const char *in, int n, char *out) {
+  static DustState d;
+  memcpy(out, in, (size_t)n);
+  dust_task((const unsigned char *)in, n, (unsigned char *)out, d);
+}
+
+// the whole pipeline for one batch; arena_rows small values exercise the deferral loop
+int hostsim_classify(void *hh, int dust, uint64_t arena_rows, const cfr_read_batch *in, cfr_result *results,
+                     uint64_t *ids, cfr_counters *counters) {
+  HostIndex *h = (HostIndex *)hh;
+  const DevIndex &ix = h->ix;
+  const DevParams &P = h->P;
+  const u64 n = in->n_reads;
+  const int mates = in->seq2 ? 2 : 1;
+  const int S = 2 * mates;
+  // pack both mates into one buffer
+  const u64 len1 = in->off1[n], len2 = mates == 2 ? in->off2[n] : 0;
+  std::vector<unsigned char> raw(len1 + len2 + 16), work;
+  memcpy(raw.data(), in->seq1, len1);
+  if (mates == 2) memcpy(raw.data() + len1, in->seq2, len2);
+  work = raw;
+  std::vector<u64> off1(in->off1, in->off1 + n + 1), off2(n + 1, 0);
+  if (mates == 2)
+    for (u64 i = 0; i <= n; ++i) off2[i] = in->off2[i] + len1;
+  int max_len = 0;
+  for (u64 i = 0; i < n; ++i) {
+    max_len = std::max<int>(max_len, (int)(off1[i + 1] - off1[i]));
+    if (mates == 2) max_len = std::max<int>(max_len, (int)(off2[i + 1] - off2[i]));
+  }
+  ChunkDev B;
+  memset(&B, 0, sizeof(B));
+  B.n_reads = n;
+  B.mates = mates;
+  B.cap_h = std::max(1, max_hits_for_len(max_len, P.min_hit_len));
+  B.seq_raw = raw.data();
+  B.seq = work.data();
+  B.off[0] = off1.data();
+  B.off[1] = off2.data();
+  std::vector<Hit> strand_hits(n * S * B.cap_h + 1);
+  std::vector<int> strand_nhits(n * S + 1);
+  std::vector<FinalHit> fhits(n * S * B.cap_h + 1);
+  std::vector<ReadWork> work_v(n + 1);
+  if (arena_rows == 0) arena_rows = n * 64 + 1024;
+  std::vector<u64> rows(arena_rows), best(arena_rows), tmp(arena_rows);
+  std::vector<u32> seq_ids(arena_rows);
+  std::vector<SeqRec> rec0(arena_rows), rec1(arena_rows);
+  std::vector<DevResult> res(n + 1);
+  std::vector<u64> out_ids(n * P.max_result + 1);
+  std::vector<u64> taxon(ix.node_cnt + 3, 0);
+  DevCounters cnt;
+  memset(&cnt, 0, sizeof(cnt));
+  u64 arena_used = 0;
+  u32 n_deferred = 0;
+  std::vector<u32> deferred(n + 1), list;
+  B.strand_hits = strand_hits.data();
+  B.strand_nhits = strand_nhits.data();
+  B.fhits = fhits.data();
+  B.work = work_v.data();
+  B.arena_cap = arena_rows;
+  B.arena_used = &arena_used;
+  B.rows = rows.data();
+  B.seq_ids = seq_ids.data();
+  B.rec0 = rec0.data();
+  B.rec1 = rec1.data();
+  B.best = best.data();
+  B.tmp = tmp.data();
+  B.results = res.data();
+  B.out_ids = out_ids.data();
+  B.taxon_counts = taxon.data();
+  B.counters = &cnt;
+  B.deferred = deferred.data();
+  B.n_deferred = &n_deferred;
+  OpCount oc{};
+  static DustState ds;
+  if (dust)
+    for (u64 t = 0; t < n * mates; ++t) dust_stage(B, t, ds);
+  for (u64 t = 0; t < n * S; ++t) {
+    if (h->layout == 2) search_stage<BwtOccLine>(ix, P, B, t, oc);
+    else search_stage<BwtRunBlock>(ix, P, B, t, oc);
+  }
+  B.read_list = nullptr;
+  B.n_list = n;
+  u64 err_flags = 0;
+  bool first = true;
+  for (;;) {
+    arena_used = 0;
+    n_deferred = 0;
+    std::fill(rows.begin(), rows.end(), CFR_ROW_SENTINEL);
+    for (u64 t = 0; t < B.n_list; ++t) {
+      const u64 read = chunk_read_id(B, t);
+      u32 r;
+      if (first) {
+        r = h->layout == 2 ? select_plan<BwtOccLine>(ix, P, B, read, oc) : select_plan<BwtRunBlock>(ix, P, B, read, oc);
+      } else {
+        r = B.work[read].arena_rows;
+      }
+      const u64 base = arena_used;
+      arena_used += r;
+      const bool fits = base + r <= B.arena_cap;
+      select_write_rows(P, B, read, base, fits);
+      if (!fits) deferred[n_deferred++] = (u32)read;
+    }
+    const u64 used = std::min(arena_used, B.arena_cap);
+    for (u64 s = 0; s < used; ++s) {
+      if (h->layout == 2) locate_stage<BwtOccLine>(ix, B, s, oc);
+      else locate_stage<BwtRunBlock>(ix, B, s, oc);
+    }
+    for (u64 t = 0; t < B.n_list; ++t) {
+      const u64 read = chunk_read_id(B, t);
+      if (B.work[read].status != 0) continue;
+      score_stage(ix, P, B, read, &err_flags);
+    }
+    if (n_deferred == 0) break;
+    if (n_deferred == B.n_list && B.work[deferred[0]].arena_rows > B.arena_cap) return CFR_ERR_OVERFLOW;
+    list.assign(deferred.begin(), deferred.begin() + n_deferred);
+    B.read_list = list.data();
+    B.n_list = n_deferred;
+    first = false;
+  }
+  if (err_flags) return CFR_ERR_OVERFLOW;
+  for (u64 i = 0; i < n; ++i) {
+    results[i].score = res[i].score;
+    results[i].secondary_score = res[i].secondary_score;
+    results[i].hit_length = res[i].hit_length;
+    results[i].query_length = res[i].query_length;
+    results[i].n_assign = res[i].n_assign;
+    results[i].by_rank = res[i].by_rank;
+    for (int k = 0; k < P.max_result; ++k) ids[i * P.max_result + k] = out_ids[i * P.max_result + k];
+  }
+  if (counters) {
+    memset(counters, 0, sizeof(*counters));
+    counters->n_rank = oc.rank;
+    counters->n_access = oc.access;
+    counters->n_search = oc.search;
+    counters->n_locate = oc.locate;
+    counters->n_lf = oc.lf;
+    counters->n_extend = oc.extend;
+    counters->n_reads = n;
+  }
+  return 0;
+}
+
+}  // extern "C"
