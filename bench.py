@@ -1,0 +1,381 @@
+#!/usr/bin/env python
+"""bench.py -- reads/s of the classification hot path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|small|c3]
+
+One "step" = one pass of the hot path over one batch of synthetic reads.
+Workload (N=1): BASELINE.json configs[1] -- synthetic 100 Mbp / 50-taxa index,
+1M x 100 bp single-end reads (seeded generator, tools/gen_data.py; the index is
+built by the unmodified reference builder, tools/make_data.py).
+
+Numbers on the JSON line:
+  value     reads/s with the batch resident in HBM (cfr_classify_resident), device time
+  e2e       reads/s through cfr_classify_batch with pinned HOST buffers: H2D of the reads,
+            all kernels, D2H of the results, per step
+  roofline  dominant kernel (search): algorithmic index bytes (120 B per
+            run-block rank, 72 B per access, 16 B per lookup probe, counted in-kernel)
+            / its CUDA-event time, vs the measured HBM copy peak
+  cpu_baseline  the reference binary (oracle/_ref/centrifuger -t <cores>) on a bounded
+            sample of the same reads, same box
+
+Multi-GPU (torchrun, one rank per GPU): reads shard across ranks, the index is replicated
+per GPU, NCCL all-reduces the per-taxon counters at the end of every step; weak scaling.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    # name: dataset, reads per step per GPU, read length, paired, -k
+    "c2": dict(dataset="c2", reads=1_000_000, rlen=100, paired=False, k=1,
+               desc="synthetic 100 Mbp / 50-taxa index, 1M x 100 bp single-end reads (BASELINE configs[1])"),
+    "small": dict(dataset="small", reads=200_000, rlen=100, paired=False, k=1,
+                  desc="synthetic 10 Mbp / 100-sequence index, 200k x 100 bp single-end reads"),
+    "c3": dict(dataset="c3", reads=1_000_000, rlen=150, paired=True, k=5,
+               desc="synthetic 2 Gbp / 500-taxa index, 1M x 2x150 bp pairs per step, -k 5 (BASELINE configs[2])"),
+}
+
+
+def algorithmic_bytes(c, n_reads, bases):
+    """useful index bytes in the reference layout + read bytes + result bytes."""
+    return (120 * c["n_rank"] + 72 * c["n_access"] + 16 * c["n_search"] + 8 * c["n_locate"]
+            + bases + 64 * n_reads)
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu = gpu_index
+        self.stop_flag = False
+        self.samples = []
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], stdout=subprocess.PIPE,
+                                     stderr=subprocess.DEVNULL, timeout=5).stdout.decode().strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            try:
+                sm.append(float(s[0]))
+                mx.append(float(s[1]))
+            except Exception:
+                continue
+            for nm, v in zip(names, s[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def ensure_dataset(name):
+    import make_data
+    d = make_data.ensure(name, log=lambda *a: print("[bench]", *a, file=sys.stderr))
+    if d is None:
+        raise SystemExit("dataset %s is missing and cannot be built (needs oracle/_ref/centrifuger-build)" % name)
+    return os.path.join(d, "idx")
+
+
+def make_reads(w, seed):
+    import gen_data
+    import make_data
+    genomes = make_data.genomes_of(w["dataset"])
+    cat = gen_data.concat_genomes(genomes)
+    n, rl = w["reads"], w["rlen"]
+    off = (np.arange(n + 1, dtype=np.uint64) * np.uint64(rl))
+    if w["paired"]:
+        r1, r2 = gen_data.make_reads_pe_fast(genomes, n, rl, seed=seed, cat=cat)
+        return np.ascontiguousarray(r1).reshape(-1), off, np.ascontiguousarray(r2).reshape(-1), off.copy()
+    r1 = gen_data.make_reads_se_fast(genomes, n, rl, seed=seed, cat=cat)
+    return np.ascontiguousarray(r1).reshape(-1), off, None, None
+
+
+def write_fastq_sample(seq, off, n, path, suffix=""):
+    with open(path, "wb") as f:
+        for i in range(n):
+            s = seq[int(off[i]):int(off[i + 1])].tobytes()
+            f.write(b"@r%d%s\n%s\n+\n%s\n" % (i, suffix.encode(), s, b"I" * len(s)))
+
+
+def run_reference_cpu(idx, w, seq1, off1, seq2, off2, n_sample, threads):
+    """Time oracle/_ref/centrifuger (the unmodified reference) on the first n_sample reads.
+    Returns (reads/s, seconds, cores).  Index load time is measured with a 1-read run and subtracted."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "centrifuger")
+    if not os.path.exists(exe):
+        return None
+    d = tempfile.mkdtemp(prefix="cfr_bench_")
+    try:
+        f1 = os.path.join(d, "s_1.fq")
+        write_fastq_sample(seq1, off1, n_sample, f1, "/1" if seq2 is not None else "")
+        t1 = os.path.join(d, "t_1.fq")
+        write_fastq_sample(seq1, off1, 1, t1, "/1" if seq2 is not None else "")
+        if seq2 is not None:
+            f2 = os.path.join(d, "s_2.fq")
+            write_fastq_sample(seq2, off2, n_sample, f2, "/2")
+            t2 = os.path.join(d, "t_2.fq")
+            write_fastq_sample(seq2, off2, 1, t2, "/2")
+            files, tiny = ["-1", f1, "-2", f2], ["-1", t1, "-2", t2]
+        else:
+            files, tiny = ["-u", f1], ["-u", t1]
+        base = [exe, "-x", idx, "-t", str(threads), "-k", str(w["k"])]
+
+        def timed(args):
+            t = time.perf_counter()
+            with open(os.devnull, "wb") as dn:
+                subprocess.run(base + args, check=True, stdout=dn, stderr=dn)
+            return time.perf_counter() - t
+
+        timed(tiny)  # page the index in
+        t_load = min(timed(tiny), timed(tiny))
+        t_run = timed(files)
+        secs = max(t_run - t_load, 1e-6)
+        return n_sample / secs, secs, threads
+    finally:
+        import shutil
+        shutil.rmtree(d, ignore_errors=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--layout", type=int, default=0, help="0 auto, 1 run-block arrays, 2 occ lines")
+    ap.add_argument("--reads", type=int, default=0, help="override reads per step per GPU")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="reads in the CPU-baseline sample (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-dust", action="store_true")
+    a = ap.parse_args()
+
+    w = dict(WORKLOADS[a.workload])
+    if a.reads:
+        w["reads"] = a.reads
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    metric = "read pairs classified per second" if w["paired"] else "reads classified per second"
+    unit = "pairs/s" if w["paired"] else "reads/s"
+    config = {"workload": w["desc"], "index": "data/%s/idx" % w["dataset"], "reads_per_step_per_gpu": w["reads"],
+              "read_length": w["rlen"], "paired": w["paired"], "k": w["k"], "dust": not a.no_dust,
+              "parallelism": "reads sharded over %d GPU(s), index replicated" % max(world, a.gpus)}
+
+    # ------------------------------------------------------------------ reference arm
+    if a.impl == "reference":
+        if rank != 0:
+            return 0
+        idx = ensure_dataset(w["dataset"])
+        seq1, off1, seq2, off2 = make_reads(w, 7)
+        cores = os.cpu_count() or 1
+        n_sample = a.cpu_sample or min(w["reads"], 40_000 * max(1, cores // 8) if not w["paired"] else 15_000 * max(1, cores // 8))
+        vals = []
+        for i in range(a.warmup + a.steps):
+            r = run_reference_cpu(idx, w, seq1, off1, seq2, off2, n_sample, cores)
+            if r is None:
+                print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/centrifuger not built"}))
+                return 0
+            if i >= a.warmup:
+                vals.append(r)
+        secs = sum(v[1] for v in vals)
+        value = n_sample * len(vals) / secs
+        line = {"impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": a.gpus,
+                "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1000.0 * secs / len(vals),
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64",
+                "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": "reference",
+                                 "sample": "first %d reads of the step batch per step, centrifuger -t %d, index-load time subtracted" % (n_sample, cores)},
+                "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------ our arm
+    import torch
+    import centrifuger_b200 as cb
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
+    idx = ensure_dataset(w["dataset"]) if rank == 0 or world == 1 else None
+    if world > 1:
+        dist.barrier()
+        if idx is None:
+            idx = ensure_dataset(w["dataset"])
+    seq1, off1, seq2, off2 = make_reads(w, 7 + 1000 * rank)
+    n = w["reads"]
+    bases = int(seq1.size + (seq2.size if seq2 is not None else 0))
+
+    clf = cb.Classifier(idx, k=w["k"], dust=not a.no_dust, layout=a.layout, device=local_rank,
+                        max_batch_reads=max(n, 1 << 20))
+    stream = torch.cuda.current_stream()
+    sptr = stream.cuda_stream
+    # pinned host staging (torch supplies pinned memory and events; the work is in libcfrb200.so)
+    pin = lambda arr: torch.from_numpy(arr).pin_memory() if arr is not None else None
+    p_seq1, p_off1, p_seq2, p_off2 = pin(seq1), pin(off1), pin(seq2), pin(off2)
+    res_host = torch.empty(n * 32, dtype=torch.uint8).pin_memory()
+    ids_host = torch.empty(max(1, n * w["k"]), dtype=torch.int64).pin_memory()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+
+    tax_ptr, tax_n = clf.taxon_counts_device()
+
+    class _Wrap:  # exposes the library's HBM counter vector to torch for the NCCL all-reduce
+        __cuda_array_interface__ = {"shape": (tax_n,), "typestr": "<i8", "data": (tax_ptr, False), "version": 2}
+    tax_tensor = torch.as_tensor(_Wrap(), device="cuda") if world > 1 else None
+
+    batch = clf.upload(p_seq1, p_off1, p_seq2, p_off2, stream=sptr)
+
+    def step_resident():
+        clf.classify_resident(batch, stream=sptr)
+        if world > 1:
+            dist.all_reduce(tax_tensor)
+
+    def step_e2e():
+        clf.classify_packed(p_seq1, p_off1, p_seq2, p_off2, stream=sptr, out=(res_host, ids_host))
+        if world > 1:
+            dist.all_reduce(tax_tensor)
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- kernel-resident timing ----
+    for _ in range(a.warmup):
+        flush.zero_()
+        step_resident()
+    sync_all()
+    clf.reset_counters()
+    clf.stage_times(reset=True)
+    clf.set_profiling(True)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    evs = []
+    t_wall0 = time.perf_counter()
+    for _ in range(a.steps):
+        flush.zero_()  # L2 flush between timed iterations (outside the per-step events)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        step_resident()
+        e1.record(stream)
+        evs.append((e0, e1))
+    sync_all()
+    t_wall = time.perf_counter() - t_wall0
+    dev_ms = sum(e0.elapsed_time(e1) for e0, e1 in evs)
+    stage = clf.stage_times(reset=True)
+    clf.set_profiling(False)
+    counters = clf.counters()
+    search_c = clf.stage_counters("search")
+    # results must be complete (no reads left deferred) -- fetch also checks device error flags
+    clf.fetch(batch, stream=sptr, out=(res_host, ids_host))
+    launches_resident = counters["n_launches"]
+
+    # ---- end-to-end timing (pinned host buffers in, host results out) ----
+    for _ in range(a.warmup):
+        step_e2e()
+    sync_all()
+    clf.reset_counters()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        step_e2e()
+    sync_all()
+    e2e_s = time.perf_counter() - t0
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    launches_e2e = clf.counters()["n_launches"]
+
+    # ---- reduce over ranks (max time) ----
+    t = torch.tensor([dev_ms, e2e_s * 1000.0, t_wall * 1000.0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms_max, e2e_ms_max, wall_ms_max = [float(x) for x in t.tolist()]
+    total_reads = n * a.steps * world
+    value = total_reads / (dev_ms_max / 1000.0)
+    e2e_value = total_reads / (e2e_ms_max / 1000.0)
+
+    if rank == 0:
+        peak, peak_kind = measured_peak()
+        s_ms, s_launch = stage["search"]
+        s_bytes = 120 * search_c["n_rank"] + 72 * search_c["n_access"] + 16 * search_c["n_search"] + bases * a.steps
+        achieved = (s_bytes / max(s_launch, 1)) / ((s_ms / max(s_launch, 1)) / 1000.0) / 1e9 if s_ms > 0 else 0.0
+        total_alg = algorithmic_bytes(counters, n * a.steps, bases * a.steps)
+        line = {
+            "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": dev_ms_max / a.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "int64", "data": "synthetic", "config": dict(config, **{
+                "layout": {1: "run-block arrays as stored", 2: "64-byte occ lines (transcoded at load)"}[clf.layout],
+                "l2": "256 MiB device write between timed iterations (L2 flush)",
+                "index_hbm_bytes": clf.hbm_bytes, "min_hit_len": clf.min_hit_len}),
+            "e2e": {"value": e2e_value, "unit": unit,
+                    "h2d_bytes_per_step": int(bases + (n + 1) * 8 * (2 if seq2 is not None else 1)),
+                    "d2h_bytes_per_step": int(n * 32 + n * w["k"] * 8)},
+            "gpu_launches": int(launches_resident + launches_e2e),
+            "roofline": {"bound": "hbm", "kernel": "k_search", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_kind": peak_kind,
+                         "algorithmic_bytes_per_launch": s_bytes / max(s_launch, 1),
+                         "kernel_ms_per_launch": s_ms / max(s_launch, 1),
+                         "pipeline_algorithmic_gbs": total_alg / (dev_ms_max / 1000.0) / 1e9 / world},
+            "stage_ms_per_step": {k: v[0] / a.steps for k, v in stage.items()},
+            "ops_per_read": {k: counters[k] / (n * a.steps) for k in
+                             ("n_rank", "n_access", "n_search", "n_locate", "n_lf", "n_extend")},
+            "clocks": sampler.summary(),
+            "wall_ms_per_step_incl_flush": wall_ms_max / a.steps,
+        }
+        if not a.no_cpu_baseline and world == 1:
+            cores = os.cpu_count() or 1
+            n_sample = a.cpu_sample or min(n, (40_000 if not w["paired"] else 15_000) * max(1, cores // 8))
+            r = run_reference_cpu(idx, w, seq1, off1, seq2, off2, n_sample, cores)
+            if r is not None:
+                line["cpu_baseline"] = {"value": r[0], "unit": unit, "cores": cores, "kind": "reference",
+                                        "sample": "first %d reads of the step batch, centrifuger -t %d, %.1f s, index-load time subtracted" % (n_sample, cores, r[1])}
+        print(json.dumps(line))
+    batch.free()
+    clf.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

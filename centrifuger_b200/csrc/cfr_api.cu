@@ -1,0 +1,861 @@
+// cfr_api.cu -- the C ABI of include/centrifuger_b200.h: index load into HBM,
+// batch pipeline orchestration, result hand-back.  Host C++ + CUDA runtime only.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/centrifuger_b200.h"
+#include "cfr_format.hpp"
+#include "cfr_kernels.cuh"
+
+using namespace cfrb200;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string &msg) {
+  g_err = msg;
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                          \
+  do {                                                                                          \
+    cudaError_t e_ = (expr);                                                                    \
+    if (e_ != cudaSuccess)                                                                      \
+      return fail(e_ == cudaErrorMemoryAllocation ? CFR_ERR_NOMEM : CFR_ERR_CUDA,               \
+                  std::string(#expr) + ": " + cudaGetErrorString(e_));                          \
+  } while (0)
+
+struct DevBuf {
+  void *p = nullptr;
+  size_t bytes = 0;
+  int ensure(size_t need) {  // grow-only
+    if (need <= bytes) return CFR_OK;
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+    size_t want = need + need / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) return fail(CFR_ERR_NOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    bytes = want;
+    return CFR_OK;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+  }
+};
+
+}  // namespace
+
+// One device-resident chunk of reads with all the work areas its pipeline needs.
+struct cfr_device_batch {
+  u64 n_reads = 0;
+  int mates = 1;
+  int cap_h = 1;
+  u64 seq_bytes = 0, total_bases = 0;
+  u64 off_bias[2] = {0, 0};
+  u64 arena_cap = 0;
+  DevBuf seq_raw, seq, off, strand_hits, strand_nhits, fhits, work, rows, seq_ids, rec0, rec1, best, tmp,
+      results, out_ids, deferred, scalars;  // scalars: {u64 arena_used, u32 n_deferred, pad}
+  bool classified = false;
+  void release() {
+    DevBuf *all[] = {&seq_raw, &seq, &off, &strand_hits, &strand_nhits, &fhits, &work, &rows, &seq_ids,
+                     &rec0, &rec1, &best, &tmp, &results, &out_ids, &deferred, &scalars};
+    for (DevBuf *b : all) b->release();
+  }
+};
+
+struct cfr_handle {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cfr_params params;
+  CfrIndexFile file;
+  DevIndex ix;
+  DevParams P;
+  int layout = CFR_LAYOUT_RUNBLOCK;
+  std::vector<void *> index_allocs;
+  size_t hbm_bytes = 0;
+  int sm_count = 148;
+  u64 *d_taxon = nullptr;
+  DevCounters *d_counters = nullptr;
+  u64 launches = 0;
+  u64 host_bases = 0;
+  cfr_device_batch scratch;  // reused by cfr_classify_batch
+  // stage profiling (CUDA events on the launch stream)
+  bool profile = false;
+  struct EvPair {
+    cudaEvent_t a, b;
+    int stage;
+  };
+  std::vector<EvPair> ev_pending;
+  std::vector<cudaEvent_t> ev_pool;
+  double stage_ms[CFR_N_STAGES] = {0, 0, 0, 0, 0, 0};
+  u64 stage_launches[CFR_N_STAGES] = {0, 0, 0, 0, 0, 0};
+};
+
+namespace {
+
+int dev_alloc(cfr_handle *h, void **out, size_t bytes) {
+  void *p = nullptr;
+  cudaError_t e = cudaMalloc(&p, bytes ? bytes : 16);
+  if (e != cudaSuccess) return fail(CFR_ERR_NOMEM, std::string("cudaMalloc(index): ") + cudaGetErrorString(e));
+  h->index_allocs.push_back(p);
+  h->hbm_bytes += bytes;
+  *out = p;
+  return CFR_OK;
+}
+
+// upload `bytes` from an (unaligned) host view, padded with `pad` zero bytes
+int dev_upload(cfr_handle *h, const void *src, size_t bytes, size_t pad, void **out) {
+  int st = dev_alloc(h, out, bytes + pad);
+  if (st) return st;
+  if (pad) CUDA_TRY(cudaMemset((char *)*out + bytes, 0, pad));
+  if (bytes) CUDA_TRY(cudaMemcpy(*out, src, bytes, cudaMemcpyHostToDevice));
+  return CFR_OK;
+}
+
+int upload_bv(cfr_handle *h, const BvView &v, DevBV &d) {
+  d.n = v.nbits;
+  d.B = nullptr;
+  d.R = nullptr;
+  if (v.nbits == 0) return CFR_OK;
+  void *p;
+  int st = dev_upload(h, v.B, v.words * 8, 16, &p);
+  if (st) return st;
+  d.B = (const u64 *)p;
+  st = dev_upload(h, v.R, v.rwords * 8, 16, &p);
+  if (st) return st;
+  d.R = (const u64 *)p;
+  return CFR_OK;
+}
+
+int upload_wt(cfr_handle *h, const WtView &t, DevWT &d) {
+  memset(&d, 0, sizeof(d));
+  d.n = t.n;
+  for (int i = 0; i < 3; ++i) {
+    d.child[i][0] = t.child[i][0];
+    d.child[i][1] = t.child[i][1];
+    if (i < t.node_cnt) {
+      int st = upload_bv(h, t.node[i], d.node[i]);
+      if (st) return st;
+    }
+  }
+  return CFR_OK;
+}
+
+int grid_for(const cfr_handle *h, u64 tasks, int threads, int blocks_per_sm) {
+  u64 need = (tasks + threads - 1) / threads;
+  u64 cap = (u64)h->sm_count * blocks_per_sm;
+  if (need < 1) need = 1;
+  return (int)std::min(need, cap);
+}
+
+int upload_index(cfr_handle *h) {
+  CfrIndexFile &f = h->file;
+  DevIndex &ix = h->ix;
+  memset(&ix, 0, sizeof(ix));
+  ix.n = f.n;
+  ix.first_isa = f.first_isa;
+  ix.last_code = base_code((unsigned char)f.last_chr);
+  for (int i = 0; i < 5; ++i) ix.C[i] = f.C[i];
+  ix.b = f.b;
+  ix.block_cnt = f.block_cnt;
+  int st;
+  if ((st = upload_bv(h, f.block_type, ix.block_type))) return st;
+  if ((st = upload_wt(h, f.plain, ix.plain))) return st;
+  if ((st = upload_wt(h, f.run, ix.run))) return st;
+  ix.sample_rate = f.sample_rate;
+  ix.sa_bits = f.sa_bits;
+  void *p;
+  if ((st = dev_upload(h, f.sa_w, f.sa_words * 8, 16, &p))) return st;
+  ix.sampled_sa = (const u64 *)p;
+  ix.adjusted_sa0 = f.adjusted_sa0;
+  if ((st = dev_upload(h, f.sel, f.sel_cnt * 16, 16, &p))) return st;
+  ix.sel = (const u64x2 *)p;
+  ix.sel_cnt = f.sel_cnt;
+  ix.sel_filter_rate = f.sel_filter_rate;
+  ix.sel_filter = nullptr;
+  if (f.sel_cnt > 0) {  // rebuilt at load exactly as FMIndex.hpp:163-176 does
+    const u64 fbits = (f.n + (u64)f.sel_filter_rate - 1) / (u64)f.sel_filter_rate;
+    std::vector<u64> filt(fbits / 64 + 2, 0);
+    for (u64 i = 0; i < f.sel_cnt; ++i) {
+      const u64 fb = load_u64(f.sel + i * 16) / (u64)f.sel_filter_rate;
+      filt[fb >> 6] |= 1ull << (fb & 63);
+    }
+    if ((st = dev_upload(h, filt.data(), filt.size() * 8, 0, &p))) return st;
+    ix.sel_filter = (const u64 *)p;
+  }
+  ix.pre_width = (int)f.precompute_width;
+  if ((st = dev_upload(h, f.lookup, f.precompute_size * 16, 16, &p))) return st;
+  ix.lookup = (const u64x2 *)p;
+  // taxonomy
+  const TaxonomyHost &t = f.tax;
+  if (t.node_cnt >= 0xfffffff0ull || t.seq_cnt + t.extra_seq_cnt >= 0xfffffff0ull)
+    return fail(CFR_ERR_UNSUPPORTED, "taxonomy too large for 32-bit device ids");
+  ix.node_cnt = t.node_cnt;
+  ix.seq_cnt = t.seq_cnt;
+  ix.root = t.root;
+  std::vector<u32> parent(t.node_cnt + 1, 0), s2t(t.seq_cnt + 1, 0);
+  std::vector<unsigned char> rank(t.node_cnt + 1, 0);
+  for (u64 i = 0; i < t.node_cnt; ++i) {
+    parent[i] = (u32)t.parent[i];
+    rank[i] = t.rank[i];
+  }
+  for (u64 i = 0; i < t.seq_cnt; ++i) s2t[i] = t.seq_to_tax[i] >= t.node_cnt ? (u32)t.node_cnt : (u32)t.seq_to_tax[i];
+  if ((st = dev_upload(h, parent.data(), parent.size() * 4, 0, &p))) return st;
+  ix.parent = (const u32 *)p;
+  if ((st = dev_upload(h, rank.data(), rank.size(), 16, &p))) return st;
+  ix.rank = (const unsigned char *)p;
+  if ((st = dev_upload(h, s2t.data(), s2t.size() * 4, 0, &p))) return st;
+  ix.seq_to_tax = (const u32 *)p;
+  init_tax_rank_num(ix.rank_num);
+  return CFR_OK;
+}
+
+int build_occ_lines(cfr_handle *h) {
+  const u64 n_lines = h->ix.n / 128 + 1;
+  void *p;
+  int st = dev_alloc(h, &p, n_lines * sizeof(OccLine));
+  if (st) return st;
+  k_transcode<<<grid_for(h, n_lines, 128, 16), 128, 0, h->stream>>>(h->ix, (OccLine *)p, n_lines);
+  ++h->launches;
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  h->ix.occ = (const OccLine *)p;
+  return CFR_OK;
+}
+
+cudaStream_t pick_stream(cfr_handle *h, void *stream) { return stream ? (cudaStream_t)stream : h->stream; }
+
+cudaEvent_t ev_get(cfr_handle *h) {
+  if (!h->ev_pool.empty()) {
+    cudaEvent_t e = h->ev_pool.back();
+    h->ev_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  return e;
+}
+
+// brackets the work enqueued between construction and destruction
+struct StageScope {
+  cfr_handle *h;
+  cudaStream_t s;
+  int stage;
+  cudaEvent_t a = nullptr;
+  StageScope(cfr_handle *h_, cudaStream_t s_, int stage_) : h(h_), s(s_), stage(stage_) {
+    ++h->stage_launches[stage];
+    if (h->profile) {
+      a = ev_get(h);
+      cudaEventRecord(a, s);
+    }
+  }
+  ~StageScope() {
+    if (a) {
+      cudaEvent_t b = ev_get(h);
+      cudaEventRecord(b, s);
+      h->ev_pending.push_back({a, b, stage});
+    }
+  }
+};
+
+// -------------------------------------------------------------------------------------
+// batch upload: copies reads [r0, r1) of `in` into device batch `b` and sizes the work areas
+// -------------------------------------------------------------------------------------
+int upload_chunk(cfr_handle *h, const cfr_read_batch *in, u64 r0, u64 r1, cfr_device_batch *b, cudaStream_t s) {
+  const u64 n = r1 - r0;
+  const int mates = in->seq2 ? 2 : 1;
+  if (mates == 2 && !in->off2) return fail(CFR_ERR_ARG, "seq2 given without off2");
+  b->n_reads = n;
+  b->mates = mates;
+  b->classified = false;
+  const u64 s1 = in->off1[r0], e1 = in->off1[r1];
+  const u64 s2 = mates == 2 ? in->off2[r0] : 0, e2 = mates == 2 ? in->off2[r1] : 0;
+  if (e1 < s1 || e2 < s2) return fail(CFR_ERR_ARG, "read offsets are not ascending");
+  const u64 len1 = e1 - s1, len2 = e2 - s2;
+  const u64 pos2 = (len1 + 15) & ~15ull;
+  b->seq_bytes = pos2 + len2;
+  b->total_bases = len1 + len2;
+  b->off_bias[0] = s1;
+  b->off_bias[1] = s2 - pos2;  // wraps modulo 2^64 by design; positions are computed as off - bias
+  int max_len = 0;
+  for (u64 i = r0; i < r1; ++i) {
+    const u64 l = in->off1[i + 1] - in->off1[i];
+    if (l > 0x3fffffffull) return fail(CFR_ERR_ARG, "read longer than 2^30");
+    if ((int)l > max_len) max_len = (int)l;
+  }
+  if (mates == 2)
+    for (u64 i = r0; i < r1; ++i) {
+      const u64 l = in->off2[i + 1] - in->off2[i];
+      if (l > 0x3fffffffull) return fail(CFR_ERR_ARG, "read longer than 2^30");
+      if ((int)l > max_len) max_len = (int)l;
+    }
+  b->cap_h = std::max(1, max_hits_for_len(max_len, h->P.min_hit_len));
+  const u64 S = 2 * (u64)mates;
+  int st;
+  if ((st = b->seq_raw.ensure(b->seq_bytes + 64))) return st;
+  if ((st = b->seq.ensure(b->seq_bytes + 64))) return st;
+  if ((st = b->off.ensure((n + 1) * 8 * 2))) return st;
+  if ((st = b->strand_hits.ensure(n * S * b->cap_h * sizeof(Hit)))) return st;
+  if ((st = b->strand_nhits.ensure(n * S * sizeof(int)))) return st;
+  if ((st = b->fhits.ensure(n * S * b->cap_h * sizeof(FinalHit)))) return st;
+  if ((st = b->work.ensure(n * sizeof(ReadWork)))) return st;
+  u64 arena = h->params.arena_rows ? h->params.arena_rows : std::max<u64>(n * 32, 1u << 16);
+  b->arena_cap = arena;
+  if ((st = b->rows.ensure(arena * 8))) return st;
+  if ((st = b->seq_ids.ensure(arena * 4))) return st;
+  if ((st = b->rec0.ensure(arena * sizeof(SeqRec)))) return st;
+  if ((st = b->rec1.ensure(arena * sizeof(SeqRec)))) return st;
+  if ((st = b->best.ensure(arena * 8))) return st;
+  if ((st = b->tmp.ensure(arena * 8))) return st;
+  if ((st = b->results.ensure(n * sizeof(DevResult)))) return st;
+  if ((st = b->out_ids.ensure(n * (u64)h->P.max_result * 8))) return st;
+  if ((st = b->deferred.ensure(n * 4 * 2))) return st;
+  if ((st = b->scalars.ensure(64))) return st;
+  // H2D
+  if (len1) CUDA_TRY(cudaMemcpyAsync(b->seq_raw.p, in->seq1 + s1, len1, cudaMemcpyHostToDevice, s));
+  if (len2) CUDA_TRY(cudaMemcpyAsync((char *)b->seq_raw.p + pos2, in->seq2 + s2, len2, cudaMemcpyHostToDevice, s));
+  CUDA_TRY(cudaMemcpyAsync(b->off.p, in->off1 + r0, (n + 1) * 8, cudaMemcpyHostToDevice, s));
+  if (mates == 2)
+    CUDA_TRY(cudaMemcpyAsync((u64 *)b->off.p + (n + 1), in->off2 + r0, (n + 1) * 8, cudaMemcpyHostToDevice, s));
+  return CFR_OK;
+}
+
+void fill_chunk(cfr_handle *h, cfr_device_batch *b, ChunkDev &B) {
+  memset(&B, 0, sizeof(B));
+  B.n_reads = b->n_reads;
+  B.mates = b->mates;
+  B.cap_h = b->cap_h;
+  B.seq_raw = (const unsigned char *)b->seq_raw.p;
+  B.seq = h->params.dust ? (unsigned char *)b->seq.p : (unsigned char *)b->seq_raw.p;
+  B.off[0] = (const u64 *)b->off.p;
+  B.off[1] = (const u64 *)b->off.p + (b->n_reads + 1);
+  B.off_bias[0] = b->off_bias[0];
+  B.off_bias[1] = b->off_bias[1];
+  B.strand_hits = (Hit *)b->strand_hits.p;
+  B.strand_nhits = (int *)b->strand_nhits.p;
+  B.fhits = (FinalHit *)b->fhits.p;
+  B.work = (ReadWork *)b->work.p;
+  B.arena_cap = b->arena_cap;
+  B.arena_used = (u64 *)b->scalars.p;
+  B.n_deferred = (u32 *)((char *)b->scalars.p + 8);
+  B.rows = (u64 *)b->rows.p;
+  B.seq_ids = (u32 *)b->seq_ids.p;
+  B.rec0 = (SeqRec *)b->rec0.p;
+  B.rec1 = (SeqRec *)b->rec1.p;
+  B.best = (u64 *)b->best.p;
+  B.tmp = (u64 *)b->tmp.p;
+  B.results = (DevResult *)b->results.p;
+  B.out_ids = (u64 *)b->out_ids.p;
+  B.taxon_counts = h->d_taxon;
+  B.counters = h->d_counters;
+  B.deferred = (u32 *)b->deferred.p;
+  B.read_list = nullptr;
+  B.n_list = b->n_reads;
+}
+
+// one select -> locate -> score pass over B.read_list
+template <class Bwt>
+int run_pass(cfr_handle *h, const ChunkDev &B, int first_pass, cudaStream_t s) {
+  {
+    StageScope sc(h, s, CFR_STAGE_OTHER);
+    CUDA_TRY(cudaMemsetAsync(B.arena_used, 0, 16, s));
+    // unwritten arena rows (reads deferred to the next pass) must read as "skip"
+    CUDA_TRY(cudaMemsetAsync(B.rows, 0xff, B.arena_cap * 8, s));
+  }
+  {
+    StageScope sc(h, s, CFR_STAGE_SELECT);
+    k_select<Bwt><<<grid_for(h, B.n_list, 128, 16), 128, 0, s>>>(h->ix, h->P, B, first_pass);
+  }
+  {
+    StageScope sc(h, s, CFR_STAGE_LOCATE);
+    k_locate<Bwt><<<grid_for(h, B.arena_cap, 128, 16), 128, 0, s>>>(h->ix, B);
+  }
+  {
+    StageScope sc(h, s, CFR_STAGE_SCORE);
+    k_score<<<grid_for(h, B.n_list, 128, 16), 128, 0, s>>>(h->ix, h->P, B);
+  }
+  h->launches += 3;
+  CUDA_TRY(cudaGetLastError());
+  return CFR_OK;
+}
+
+template <class Bwt>
+int run_first(cfr_handle *h, cfr_device_batch *b, cudaStream_t s) {
+  ChunkDev B;
+  fill_chunk(h, b, B);
+  if (b->n_reads == 0) return CFR_OK;
+  if (h->params.dust) {
+    {
+      StageScope sc(h, s, CFR_STAGE_OTHER);
+      CUDA_TRY(cudaMemcpyAsync(b->seq.p, b->seq_raw.p, b->seq_bytes, cudaMemcpyDeviceToDevice, s));
+    }
+    StageScope sc(h, s, CFR_STAGE_DUST);
+    k_dust<<<grid_for(h, B.n_reads * B.mates, 128, 16), 128, 0, s>>>(B);
+    ++h->launches;
+  }
+  {
+    StageScope sc(h, s, CFR_STAGE_SEARCH);
+    k_search<Bwt><<<grid_for(h, B.n_reads * 2 * B.mates, 128, 16), 128, 0, s>>>(h->ix, h->P, B);
+    ++h->launches;
+  }
+  CUDA_TRY(cudaGetLastError());
+  return run_pass<Bwt>(h, B, 1, s);
+}
+
+// after the first pass: re-run select/locate/score for reads that did not fit the arena
+template <class Bwt>
+int finish_deferred(cfr_handle *h, cfr_device_batch *b, cudaStream_t s) {
+  if (b->n_reads == 0) return CFR_OK;
+  ChunkDev B;
+  fill_chunk(h, b, B);
+  u32 *lists[2] = {(u32 *)b->deferred.p, (u32 *)b->deferred.p + b->n_reads};
+  int cur = 0;
+  for (int iter = 0; iter < 1 << 20; ++iter) {
+    struct {
+      u64 used;
+      u32 n_def;
+      u32 pad;
+    } sc;
+    CUDA_TRY(cudaMemcpyAsync(&sc, b->scalars.p, 16, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    if (sc.n_def == 0) return CFR_OK;
+    if ((u64)sc.n_def == B.n_list) {
+      // nothing fitted: the first read of the list alone exceeds the arena
+      return fail(CFR_ERR_OVERFLOW, "a single read needs more locate rows than arena_rows; raise cfr_params.arena_rows");
+    }
+    B.read_list = lists[cur];
+    B.n_list = sc.n_def;
+    cur ^= 1;
+    B.deferred = lists[cur];
+    int st = run_pass<Bwt>(h, B, 0, s);
+    if (st) return st;
+  }
+  return fail(CFR_ERR_OVERFLOW, "deferral loop did not converge");
+}
+
+int check_device_errors(cfr_handle *h, cudaStream_t s) {
+  u64 flags = 0;
+  CUDA_TRY(cudaMemcpyAsync(&flags, &h->d_counters[CFR_STAGE_SCORE].error_flags, 8, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  if (flags & 1ull) return fail(CFR_ERR_OVERFLOW, "taxonomy lineage deeper than the device path capacity");
+  return CFR_OK;
+}
+
+}  // namespace
+
+// =====================================================================================
+// C ABI
+// =====================================================================================
+extern "C" {
+
+void cfr_default_params(cfr_params *p) {
+  memset(p, 0, sizeof(*p));
+  p->max_result = 1;
+  p->min_hit_len = 0;
+  p->max_result_per_hit_factor = 40;
+  p->dust = 1;
+  p->consider_secondary_hit_len = 2000;
+  p->consider_secondary_score_factor = 0.995;
+  p->layout = CFR_LAYOUT_AUTO;
+  p->max_batch_reads = 0;
+  p->arena_rows = 0;
+}
+
+const char *cfr_last_error(void) { return g_err.c_str(); }
+
+int cfr_open(const char *idx_prefix, const cfr_params *p, int device, cfr_handle **out) {
+  if (!idx_prefix || !out) return fail(CFR_ERR_ARG, "null argument");
+  *out = nullptr;
+  cfr_params params;
+  if (p) params = *p; else cfr_default_params(&params);
+  if (params.max_result <= 0) return fail(CFR_ERR_UNSUPPORTED, "-k must be >= 1 on the B200 path");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(CFR_ERR_CUDA, "no CUDA device available (this library has no CPU path)");
+  if (device < 0 || device >= ndev) return fail(CFR_ERR_ARG, "device ordinal out of range");
+  CUDA_TRY(cudaSetDevice(device));
+  cfr_handle *h = new cfr_handle();
+  h->device = device;
+  h->params = params;
+  std::string err;
+  int st = h->file.load(idx_prefix, err);
+  if (st) {
+    delete h;
+    return fail(st, err);
+  }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) h->sm_count = prop.multiProcessorCount;
+  auto bail = [&](int code) {
+    cfr_close(h);
+    return code;
+  };
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess)
+    return bail(fail(CFR_ERR_CUDA, "cudaStreamCreate failed"));
+  h->P.max_result = params.max_result;
+  h->P.min_hit_len = params.min_hit_len > 0 ? params.min_hit_len : infer_min_hit_len(h->file.n);
+  h->P.hitk_factor = params.max_result_per_hit_factor;
+  h->P.secondary_len = params.consider_secondary_hit_len;
+  h->P.secondary_factor = params.consider_secondary_score_factor;
+  if ((st = upload_index(h))) return bail(st);
+  void *p2;
+  if ((st = dev_alloc(h, &p2, (h->ix.node_cnt + 3) * 8))) return bail(st);
+  h->d_taxon = (u64 *)p2;
+  if ((st = dev_alloc(h, &p2, sizeof(DevCounters) * CFR_N_STAGES))) return bail(st);
+  h->d_counters = (DevCounters *)p2;
+  cudaMemset(h->d_taxon, 0, (h->ix.node_cnt + 3) * 8);
+  cudaMemset(h->d_counters, 0, sizeof(DevCounters) * CFR_N_STAGES);
+  h->layout = params.layout == CFR_LAYOUT_RUNBLOCK ? CFR_LAYOUT_RUNBLOCK : CFR_LAYOUT_OCCLINE;
+  if (params.layout == CFR_LAYOUT_AUTO) {
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    const u64 need = (h->ix.n / 128 + 1) * sizeof(OccLine);
+    if ((u64)free_b < need + (8ull << 30)) h->layout = CFR_LAYOUT_RUNBLOCK;  // keep 8 GiB for work areas
+  }
+  if (h->layout == CFR_LAYOUT_OCCLINE && (st = build_occ_lines(h))) return bail(st);
+  h->file.map1.close();  // everything needed from .1.cfr now lives in HBM
+  *out = h;
+  return CFR_OK;
+}
+
+void cfr_close(cfr_handle *h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  h->scratch.release();
+  for (void *p : h->index_allocs) cudaFree(p);
+  for (auto &e : h->ev_pending) {
+    cudaEventDestroy(e.a);
+    cudaEventDestroy(e.b);
+  }
+  for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+uint64_t cfr_index_info(const cfr_handle *h, int which) {
+  if (!h) return 0;
+  switch (which) {
+    case 0: return h->ix.n;
+    case 1: return h->ix.b;
+    case 2: return h->ix.block_cnt;
+    case 3: return h->ix.first_isa;
+    case 4: return (uint64_t)h->P.min_hit_len;
+    case 5: return h->ix.node_cnt;
+    case 6: return h->file.tax.seq_cnt + h->file.tax.extra_seq_cnt;
+    case 7: return h->ix.root;
+    case 8: return (uint64_t)h->layout;
+    case 9: return (uint64_t)h->hbm_bytes;
+    case 10: return (uint64_t)h->ix.sample_rate;
+    case 11: return (uint64_t)h->ix.pre_width;
+    case 12: return (uint64_t)h->P.max_result;
+    default: return 0;
+  }
+}
+
+int cfr_batch_upload(cfr_handle *h, const cfr_read_batch *in, void *stream, cfr_device_batch **out) {
+  if (!h || !in || !out) return fail(CFR_ERR_ARG, "null argument");
+  if (in->n_reads && (!in->seq1 || !in->off1)) return fail(CFR_ERR_ARG, "seq1/off1 missing");
+  CUDA_TRY(cudaSetDevice(h->device));
+  cfr_device_batch *b = new cfr_device_batch();
+  int st = upload_chunk(h, in, 0, in->n_reads, b, pick_stream(h, stream));
+  if (st) {
+    b->release();
+    delete b;
+    return st;
+  }
+  CUDA_TRY(cudaStreamSynchronize(pick_stream(h, stream)));
+  *out = b;
+  return CFR_OK;
+}
+
+int cfr_classify_resident(cfr_handle *h, cfr_device_batch *b, void *stream) {
+  if (!h || !b) return fail(CFR_ERR_ARG, "null argument");
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t s = pick_stream(h, stream);
+  h->host_bases += b->total_bases;
+  b->classified = true;
+  return h->layout == CFR_LAYOUT_OCCLINE ? run_first<BwtOccLine>(h, b, s) : run_first<BwtRunBlock>(h, b, s);
+}
+
+int cfr_batch_fetch(cfr_handle *h, cfr_device_batch *b, cfr_result *results, uint64_t *ids, void *stream) {
+  if (!h || !b || !results || !ids) return fail(CFR_ERR_ARG, "null argument");
+  if (!b->classified) return fail(CFR_ERR_ARG, "batch was not classified");
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t s = pick_stream(h, stream);
+  int st = h->layout == CFR_LAYOUT_OCCLINE ? finish_deferred<BwtOccLine>(h, b, s) : finish_deferred<BwtRunBlock>(h, b, s);
+  if (st) return st;
+  static_assert(sizeof(cfr_result) == sizeof(DevResult), "result layout");
+  if (b->n_reads) {
+    CUDA_TRY(cudaMemcpyAsync(results, b->results.p, b->n_reads * sizeof(DevResult), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(ids, b->out_ids.p, b->n_reads * (u64)h->P.max_result * 8, cudaMemcpyDeviceToHost, s));
+  }
+  return check_device_errors(h, s);
+}
+
+void cfr_batch_free(cfr_handle *h, cfr_device_batch *b) {
+  if (!b) return;
+  if (h) cudaSetDevice(h->device);
+  b->release();
+  delete b;
+}
+
+int cfr_classify_batch(cfr_handle *h, const cfr_read_batch *in, cfr_result *results, uint64_t *ids, void *stream) {
+  if (!h || !in || (in->n_reads && (!results || !ids))) return fail(CFR_ERR_ARG, "null argument");
+  if (in->n_reads && (!in->seq1 || !in->off1)) return fail(CFR_ERR_ARG, "seq1/off1 missing");
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t s = pick_stream(h, stream);
+  const u64 chunk = h->params.max_batch_reads > 0 ? (u64)h->params.max_batch_reads : (1ull << 20);
+  cfr_device_batch *b = &h->scratch;
+  for (u64 r0 = 0; r0 < in->n_reads; r0 += chunk) {
+    const u64 r1 = std::min<u64>(in->n_reads, r0 + chunk);
+    int st = upload_chunk(h, in, r0, r1, b, s);
+    if (st) return st;
+    if ((st = cfr_classify_resident(h, b, s))) return st;
+    if ((st = cfr_batch_fetch(h, b, results + r0, ids + r0 * (u64)h->P.max_result, s))) return st;
+  }
+  return CFR_OK;
+}
+
+const char *cfr_seq_name(const cfr_handle *h, uint64_t seq_id) {
+  if (!h || seq_id >= h->file.tax.seq_name.size()) return "";
+  return h->file.tax.seq_name[seq_id].c_str();
+}
+
+const char *cfr_rank_name(const cfr_handle *h, uint64_t ctid) {
+  if (!h) return "";
+  const uint8_t r = ctid < h->file.tax.node_cnt ? h->file.tax.rank[ctid] : 0;  // GetTaxIdRank: unknown -> RANK_UNKNOWN
+  return tax_rank_string(r);
+}
+
+uint64_t cfr_orig_taxid(const cfr_handle *h, uint64_t ctid) {
+  if (!h) return 0;
+  const TaxonomyHost &t = h->file.tax;
+  if (ctid >= t.node_cnt) ctid = t.root;
+  return ctid < t.orig_taxid.size() ? t.orig_taxid[ctid] : 0;
+}
+
+uint64_t cfr_seq_taxid(const cfr_handle *h, uint64_t seq_id) {
+  if (!h) return 0;
+  const TaxonomyHost &t = h->file.tax;
+  return seq_id < t.seq_cnt ? t.seq_to_tax[seq_id] : t.node_cnt;
+}
+
+int cfr_format_tsv(const cfr_handle *h, const char *read_id, const cfr_result *r, const uint64_t *ids, char *buf,
+                   size_t cap) {
+  if (!h || !read_id || !r || !buf) return CFR_ERR_ARG;
+  size_t off = 0;
+  if (r->n_assign > 0) {
+    const int m = std::min<int>(r->n_assign, h->P.max_result);
+    for (int i = 0; i < m; ++i) {
+      const char *name = r->by_rank ? cfr_rank_name(h, ids[i]) : cfr_seq_name(h, ids[i]);
+      const uint64_t tax = r->by_rank ? cfr_orig_taxid(h, ids[i]) : cfr_orig_taxid(h, cfr_seq_taxid(h, ids[i]));
+      int w = snprintf(buf + off, cap - off, "%s\t%s\t%lu\t%lu\t%lu\t%d\t%d\t%d\n", read_id, name, (unsigned long)tax,
+                       (unsigned long)r->score, (unsigned long)r->secondary_score, r->hit_length, r->query_length,
+                       r->n_assign);
+      if (w < 0 || (size_t)w >= cap - off) return CFR_ERR_ARG;
+      off += (size_t)w;
+    }
+  } else {
+    int w = snprintf(buf + off, cap - off, "%s\tunclassified\t0\t0\t0\t0\t%d\t1\n", read_id, r->query_length);
+    if (w < 0 || (size_t)w >= cap - off) return CFR_ERR_ARG;
+    off += (size_t)w;
+  }
+  return (int)off;
+}
+
+int cfr_taxon_counts_device(cfr_handle *h, void **dev_ptr, uint64_t *n_entries) {
+  if (!h || !dev_ptr || !n_entries) return fail(CFR_ERR_ARG, "null argument");
+  *dev_ptr = h->d_taxon;
+  *n_entries = h->ix.node_cnt + 3;
+  return CFR_OK;
+}
+
+int cfr_taxon_counts_read(cfr_handle *h, uint64_t *out, uint64_t n_entries, void *stream) {
+  if (!h || !out) return fail(CFR_ERR_ARG, "null argument");
+  if (n_entries > h->ix.node_cnt + 3) n_entries = h->ix.node_cnt + 3;
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t s = pick_stream(h, stream);
+  CUDA_TRY(cudaMemcpyAsync(out, h->d_taxon, n_entries * 8, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  return CFR_OK;
+}
+
+int cfr_taxon_counts_reset(cfr_handle *h, void *stream) {
+  if (!h) return fail(CFR_ERR_ARG, "null argument");
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaMemsetAsync(h->d_taxon, 0, (h->ix.node_cnt + 3) * 8, pick_stream(h, stream)));
+  return CFR_OK;
+}
+
+static int read_counters(cfr_handle *h, int stage, cfr_counters *c, cudaStream_t s) {
+  DevCounters d[CFR_N_STAGES];
+  CUDA_TRY(cudaMemcpyAsync(d, h->d_counters, sizeof(d), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  memset(c, 0, sizeof(*c));
+  for (int i = 0; i < CFR_N_STAGES; ++i) {
+    if (stage >= 0 && i != stage) continue;
+    c->n_rank += d[i].n_rank;
+    c->n_access += d[i].n_access;
+    c->n_search += d[i].n_search;
+    c->n_locate += d[i].n_locate;
+    c->n_lf += d[i].n_lf;
+    c->n_extend += d[i].n_extend;
+  }
+  c->n_bases = h->host_bases;
+  c->n_reads = d[CFR_STAGE_SCORE].n_reads;
+  c->n_launches = stage >= 0 ? h->stage_launches[stage] : h->launches;
+  return CFR_OK;
+}
+
+int cfr_get_counters(cfr_handle *h, cfr_counters *c, void *stream) {
+  if (!h || !c) return fail(CFR_ERR_ARG, "null argument");
+  CUDA_TRY(cudaSetDevice(h->device));
+  return read_counters(h, -1, c, pick_stream(h, stream));
+}
+
+int cfr_get_stage_counters(cfr_handle *h, int stage, cfr_counters *c, void *stream) {
+  if (!h || !c || stage < 0 || stage >= CFR_N_STAGES) return fail(CFR_ERR_ARG, "bad argument");
+  CUDA_TRY(cudaSetDevice(h->device));
+  return read_counters(h, stage, c, pick_stream(h, stream));
+}
+
+int cfr_reset_counters(cfr_handle *h, void *stream) {
+  if (!h) return fail(CFR_ERR_ARG, "null argument");
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaMemsetAsync(h->d_counters, 0, sizeof(DevCounters) * CFR_N_STAGES, pick_stream(h, stream)));
+  h->launches = 0;
+  h->host_bases = 0;
+  return CFR_OK;
+}
+
+int cfr_set_profiling(cfr_handle *h, int on) {
+  if (!h) return fail(CFR_ERR_ARG, "null argument");
+  h->profile = on != 0;
+  return CFR_OK;
+}
+
+int cfr_get_stage_times(cfr_handle *h, cfr_stage_times *out, int reset) {
+  if (!h || !out) return fail(CFR_ERR_ARG, "null argument");
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaDeviceSynchronize());
+  for (auto &e : h->ev_pending) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, e.a, e.b) == cudaSuccess) h->stage_ms[e.stage] += ms;
+    h->ev_pool.push_back(e.a);
+    h->ev_pool.push_back(e.b);
+  }
+  h->ev_pending.clear();
+  for (int i = 0; i < CFR_N_STAGES; ++i) {
+    out->ms[i] = h->stage_ms[i];
+    out->launches[i] = h->stage_launches[i];
+    if (reset) {
+      h->stage_ms[i] = 0;
+      h->stage_launches[i] = 0;
+    }
+  }
+  return CFR_OK;
+}
+
+// ---- diagnostics -------------------------------------------------------------------
+int cfr_debug_bwt_rank(cfr_handle *h, const uint8_t *codes, const uint64_t *pos, const int32_t *inclusive, uint64_t n,
+                       uint64_t *out) {
+  if (!h || !codes || !pos || !inclusive || !out) return fail(CFR_ERR_ARG, "null argument");
+  CUDA_TRY(cudaSetDevice(h->device));
+  DevBuf dc, dp, di, dout;
+  int st;
+  if ((st = dc.ensure(n)) || (st = dp.ensure(n * 8)) || (st = di.ensure(n * 4)) || (st = dout.ensure(n * 8))) return st;
+  CUDA_TRY(cudaMemcpy(dc.p, codes, n, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(dp.p, pos, n * 8, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(di.p, inclusive, n * 4, cudaMemcpyHostToDevice));
+  const int grid = (int)((n + 127) / 128);
+  if (h->layout == CFR_LAYOUT_OCCLINE)
+    k_debug_rank<BwtOccLine><<<grid, 128, 0, h->stream>>>(h->ix, (const unsigned char *)dc.p, (const u64 *)dp.p,
+                                                          (const int *)di.p, n, (u64 *)dout.p);
+  else
+    k_debug_rank<BwtRunBlock><<<grid, 128, 0, h->stream>>>(h->ix, (const unsigned char *)dc.p, (const u64 *)dp.p,
+                                                           (const int *)di.p, n, (u64 *)dout.p);
+  ++h->launches;
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  CUDA_TRY(cudaMemcpy(out, dout.p, n * 8, cudaMemcpyDeviceToHost));
+  dc.release(); dp.release(); di.release(); dout.release();
+  return CFR_OK;
+}
+
+int cfr_debug_bwt_access(cfr_handle *h, const uint64_t *pos, uint64_t n, uint8_t *out) {
+  if (!h || !pos || !out) return fail(CFR_ERR_ARG, "null argument");
+  CUDA_TRY(cudaSetDevice(h->device));
+  DevBuf dp, dout;
+  int st;
+  if ((st = dp.ensure(n * 8)) || (st = dout.ensure(n))) return st;
+  CUDA_TRY(cudaMemcpy(dp.p, pos, n * 8, cudaMemcpyHostToDevice));
+  const int grid = (int)((n + 127) / 128);
+  if (h->layout == CFR_LAYOUT_OCCLINE)
+    k_debug_access<BwtOccLine><<<grid, 128, 0, h->stream>>>(h->ix, (const u64 *)dp.p, n, (unsigned char *)dout.p);
+  else
+    k_debug_access<BwtRunBlock><<<grid, 128, 0, h->stream>>>(h->ix, (const u64 *)dp.p, n, (unsigned char *)dout.p);
+  ++h->launches;
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  CUDA_TRY(cudaMemcpy(out, dout.p, n, cudaMemcpyDeviceToHost));
+  dp.release(); dout.release();
+  return CFR_OK;
+}
+
+int cfr_debug_locate(cfr_handle *h, const uint64_t *rows, uint64_t n, uint64_t *seq_ids) {
+  if (!h || !rows || !seq_ids) return fail(CFR_ERR_ARG, "null argument");
+  CUDA_TRY(cudaSetDevice(h->device));
+  DevBuf dp, dout;
+  int st;
+  if ((st = dp.ensure(n * 8)) || (st = dout.ensure(n * 8))) return st;
+  CUDA_TRY(cudaMemcpy(dp.p, rows, n * 8, cudaMemcpyHostToDevice));
+  const int grid = (int)((n + 127) / 128);
+  if (h->layout == CFR_LAYOUT_OCCLINE)
+    k_debug_locate<BwtOccLine><<<grid, 128, 0, h->stream>>>(h->ix, (const u64 *)dp.p, n, (u64 *)dout.p);
+  else
+    k_debug_locate<BwtRunBlock><<<grid, 128, 0, h->stream>>>(h->ix, (const u64 *)dp.p, n, (u64 *)dout.p);
+  ++h->launches;
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  CUDA_TRY(cudaMemcpy(seq_ids, dout.p, n * 8, cudaMemcpyDeviceToHost));
+  dp.release(); dout.release();
+  return CFR_OK;
+}
+
+int cfr_debug_dust(cfr_handle *h, const cfr_read_batch *in, char *masked1, char *masked2) {
+  if (!h || !in || !masked1) return fail(CFR_ERR_ARG, "null argument");
+  CUDA_TRY(cudaSetDevice(h->device));
+  cfr_device_batch b;
+  int st = upload_chunk(h, in, 0, in->n_reads, &b, h->stream);
+  if (st) {
+    b.release();
+    return st;
+  }
+  ChunkDev B;
+  fill_chunk(h, &b, B);
+  B.seq = (unsigned char *)b.seq.p;
+  const u64 len1 = in->off1[in->n_reads] - in->off1[0];
+  const u64 len2 = in->seq2 ? in->off2[in->n_reads] - in->off2[0] : 0;
+  cudaMemcpyAsync(b.seq.p, b.seq_raw.p, b.seq_bytes, cudaMemcpyDeviceToDevice, h->stream);
+  if (in->n_reads) k_dust<<<grid_for(h, B.n_reads * B.mates, 128, 16), 128, 0, h->stream>>>(B);
+  ++h->launches;
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpyAsync(masked1, b.seq.p, len1, cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess && masked2 && len2)
+    e = cudaMemcpyAsync(masked2, (char *)b.seq.p + ((len1 + 15) & ~15ull), len2, cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  b.release();
+  if (e != cudaSuccess) return fail(CFR_ERR_CUDA, cudaGetErrorString(e));
+  return CFR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,171 @@
+// cfr_kernels.cuh -- __global__ wrappers around the stage functions of
+// cfr_pipeline.cuh.  sm_100a only.  All kernels are grid-stride so the launch
+// grid can be sized as a multiple of the SM count independent of the batch.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "cfr_pipeline.cuh"
+
+namespace cfrb200 {
+
+__device__ __forceinline__ void flush_counts(const OpCount &oc, DevCounters *c) {
+  const unsigned full = 0xffffffffu;
+  const u32 r = __reduce_add_sync(full, oc.rank), a = __reduce_add_sync(full, oc.access),
+            s = __reduce_add_sync(full, oc.search), l = __reduce_add_sync(full, oc.locate),
+            f = __reduce_add_sync(full, oc.lf), e = __reduce_add_sync(full, oc.extend);
+  if ((threadIdx.x & 31) == 0) {
+    if (r) atomicAdd(&c->n_rank, (u64)r);
+    if (a) atomicAdd(&c->n_access, (u64)a);
+    if (s) atomicAdd(&c->n_search, (u64)s);
+    if (l) atomicAdd(&c->n_locate, (u64)l);
+    if (f) atomicAdd(&c->n_lf, (u64)f);
+    if (e) atomicAdd(&c->n_extend, (u64)e);
+  }
+}
+
+__global__ void __launch_bounds__(128) k_dust(const __grid_constant__ ChunkDev B) {
+  DustState d;
+  const u64 ntask = B.n_reads * (u64)B.mates;
+  const u64 stride = (u64)gridDim.x * blockDim.x;
+  for (u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x; t < ntask; t += stride) dust_stage(B, t, d);
+}
+
+template <class Bwt>
+__global__ void __launch_bounds__(128) k_search(const __grid_constant__ DevIndex ix, const __grid_constant__ DevParams P,
+                                                const __grid_constant__ ChunkDev B) {
+  OpCount oc{};
+  const u64 ntask = B.n_reads * (u64)(2 * B.mates);
+  const u64 stride = (u64)gridDim.x * blockDim.x;
+  for (u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x; t < ntask; t += stride)
+    search_stage<Bwt>(ix, P, B, t, oc);
+  flush_counts(oc, B.counters + CFR_STAGE_SEARCH);
+}
+
+// One read per thread.  The arena slice of each read is reserved with ONE atomic
+// per warp (warp-wide inclusive scan of the row counts).
+template <class Bwt>
+__global__ void __launch_bounds__(128) k_select(const __grid_constant__ DevIndex ix, const __grid_constant__ DevParams P,
+                                                const __grid_constant__ ChunkDev B, const int first_pass) {
+  OpCount oc{};
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const u64 stride = (u64)gridDim.x * blockDim.x;
+  for (u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x; t - lane < B.n_list; t += stride) {
+    const bool active = t < B.n_list;
+    const u64 read = active ? chunk_read_id(B, t) : 0;
+    u32 r = 0;
+    if (active) r = first_pass ? select_plan<Bwt>(ix, P, B, read, oc) : B.work[read].arena_rows;
+    u64 incl = r;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const u64 v = __shfl_up_sync(full, incl, d);
+      if (lane >= d) incl += v;
+    }
+    const u64 total = __shfl_sync(full, incl, 31);
+    u64 base0 = 0;
+    if (lane == 0 && total) base0 = atomicAdd(B.arena_used, total);
+    base0 = __shfl_sync(full, base0, 0);
+    if (active) {
+      const u64 my_base = base0 + incl - r;
+      const bool fits = my_base + r <= B.arena_cap;
+      select_write_rows(P, B, read, my_base, fits);
+      if (!fits) B.deferred[atomicAdd(B.n_deferred, 1u)] = (u32)read;
+    }
+  }
+  flush_counts(oc, B.counters + CFR_STAGE_SELECT);
+}
+
+template <class Bwt>
+__global__ void __launch_bounds__(128) k_locate(const __grid_constant__ DevIndex ix, const __grid_constant__ ChunkDev B) {
+  OpCount oc{};
+  u64 used = *B.arena_used;
+  if (used > B.arena_cap) used = B.arena_cap;
+  const u64 stride = (u64)gridDim.x * blockDim.x;
+  for (u64 s = (u64)blockIdx.x * blockDim.x + threadIdx.x; s < used; s += stride) locate_stage<Bwt>(ix, B, s, oc);
+  flush_counts(oc, B.counters + CFR_STAGE_LOCATE);
+}
+
+__global__ void __launch_bounds__(128) k_score(const __grid_constant__ DevIndex ix, const __grid_constant__ DevParams P,
+                                               const __grid_constant__ ChunkDev B) {
+  const unsigned full = 0xffffffffu;
+  u64 err = 0;
+  u32 n_done = 0, n_cls = 0;
+  const u64 stride = (u64)gridDim.x * blockDim.x;
+  for (u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x; t < B.n_list; t += stride) {
+    const u64 read = chunk_read_id(B, t);
+    if (B.work[read].status != 0) continue;
+    const int na = score_stage(ix, P, B, read, &err);
+    ++n_done;
+    if (na > 0) {
+      ++n_cls;
+      const DevResult &res = B.results[read];
+      const u64 *ids = B.out_ids + read * (u64)P.max_result;
+      const int m = na < P.max_result ? na : P.max_result;
+      for (int i = 0; i < m; ++i) {
+        u64 ct = ids[i];
+        if (!res.by_rank) ct = ct < ix.seq_cnt ? (u64)ld32(ix.seq_to_tax + ct) : ix.node_cnt;
+        if (ct > ix.node_cnt) ct = ix.node_cnt;
+        atomicAdd(&B.taxon_counts[ct], 1ull);
+      }
+    }
+  }
+  n_done = __reduce_add_sync(full, n_done);
+  n_cls = __reduce_add_sync(full, n_cls);
+  if ((threadIdx.x & 31) == 0) {
+    if (n_done) {
+      atomicAdd(&B.counters[CFR_STAGE_SCORE].n_reads, (u64)n_done);
+      atomicAdd(&B.taxon_counts[ix.node_cnt + 1], (u64)n_done);
+    }
+    if (n_cls) atomicAdd(&B.taxon_counts[ix.node_cnt + 2], (u64)n_cls);
+  }
+  if (err) atomicOr(&B.counters[CFR_STAGE_SCORE].error_flags, err);
+}
+
+// Index transcoding at load time: run-block BWT (as stored) -> 64-byte occ lines.
+// One thread per line: 4 exclusive Sequence_RunBlock::Rank queries give the
+// absolute counters, 128 Sequence_RunBlock::Access queries give the symbols.
+__global__ void __launch_bounds__(128) k_transcode(const __grid_constant__ DevIndex ix, OccLine *out, u64 n_lines) {
+  const u64 stride = (u64)gridDim.x * blockDim.x;
+  for (u64 L = (u64)blockIdx.x * blockDim.x + threadIdx.x; L < n_lines; L += stride) {
+    OccLine o;
+    const u64 p0 = L * 128;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) o.cnt[c] = p0 <= ix.n ? rb_rank(ix, c, p0, 0) : 0;
+    u64 lo[2] = {0, 0}, hi[2] = {0, 0};
+    for (int w = 0; w < 128; ++w) {
+      const u64 pos = p0 + (u64)w;
+      if (pos >= ix.n) break;
+      const int s = rb_access(ix, pos);
+      lo[w >> 6] |= (u64)(s & 1) << (w & 63);
+      hi[w >> 6] |= (u64)(s >> 1) << (w & 63);
+    }
+    o.lo0 = lo[0];
+    o.hi0 = hi[0];
+    o.lo1 = lo[1];
+    o.hi1 = hi[1];
+    out[L] = o;
+  }
+}
+
+// ---- diagnostics for the parity tests ----
+template <class Bwt>
+__global__ void k_debug_rank(const __grid_constant__ DevIndex ix, const unsigned char *codes, const u64 *pos,
+                             const int *incl, u64 n, u64 *out) {
+  const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = Bwt::rank(ix, codes[i], pos[i], incl[i]);
+}
+
+template <class Bwt>
+__global__ void k_debug_access(const __grid_constant__ DevIndex ix, const u64 *pos, u64 n, unsigned char *out) {
+  const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (unsigned char)Bwt::access(ix, pos[i]);
+}
+
+template <class Bwt>
+__global__ void k_debug_locate(const __grid_constant__ DevIndex ix, const u64 *rows, u64 n, u64 *out) {
+  const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  OpCount oc{};
+  if (i < n) out[i] = locate_row<Bwt>(ix, rows[i], oc);
+}
+
+}  // namespace cfrb200

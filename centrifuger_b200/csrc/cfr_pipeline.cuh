@@ -24,7 +24,8 @@ struct ChunkDev {
   int cap_h;  // hit slots per strand task
   const unsigned char *seq_raw;  // bases as uploaded
   unsigned char *seq;            // working copy the searches read (DUST-masked)
-  const u64 *off[2];             // per mate: n_reads + 1 offsets into seq
+  const u64 *off[2];             // per mate: n_reads + 1 offsets as given by the caller
+  u64 off_bias[2];               // position in seq = off[m][i] - off_bias[m]
   Hit *strand_hits;              // [n_reads * 2*mates * cap_h]
   int *strand_nhits;             // [n_reads * 2*mates]
   FinalHit *fhits;               // [n_reads * 2*mates * cap_h]
@@ -54,8 +55,8 @@ CFR_HD u64 chunk_read_id(const ChunkDev &B, u64 t) { return B.read_list ? (u64)B
 CFR_HD void dust_stage(const ChunkDev &B, u64 task, DustState &d) {
   const u64 read = task / (u64)B.mates;
   const int mate = (int)(task % (u64)B.mates);
-  const u64 base = B.off[mate][read];
-  const int len = (int)(B.off[mate][read + 1] - base);
+  const u64 base = B.off[mate][read] - B.off_bias[mate];
+  const int len = (int)(B.off[mate][read + 1] - B.off[mate][read]);
   dust_task(B.seq_raw + base, len, B.seq + base, d);
 }
 
@@ -68,8 +69,8 @@ CFR_HD void search_stage(const DevIndex &ix, const DevParams &P, const ChunkDev 
   const u64 read = task / (u64)S;
   const int w = (int)(task % (u64)S);
   const int mate = w >> 1;
-  const u64 base = B.off[mate][read];
-  const int len = (int)(B.off[mate][read + 1] - base);
+  const u64 base = B.off[mate][read] - B.off_bias[mate];
+  const int len = (int)(B.off[mate][read + 1] - B.off[mate][read]);
   StrandSeq s{B.seq + base, len, (w & 1) ? 0 : 1};
   B.strand_nhits[task] = get_hits_from_read<Bwt>(ix, s, P.min_hit_len, B.strand_hits + task * (u64)B.cap_h, B.cap_h, oc);
 }
@@ -85,8 +86,8 @@ CFR_HD u32 select_plan(const DevIndex &ix, const DevParams &P, const ChunkDev &B
   int n[2][2];
   int qlen = 0;
   for (int m = 0; m < B.mates; ++m) {
-    const u64 base = B.off[m][read];
-    const int len = (int)(B.off[m][read + 1] - base);
+    const u64 base = B.off[m][read] - B.off_bias[m];
+    const int len = (int)(B.off[m][read + 1] - B.off[m][read]);
     qlen += len;
     for (int s = 0; s < 2; ++s) {
       const u64 task = read * (u64)S + (u64)(m * 2 + s);

@@ -126,4 +126,8 @@ struct DevCounters {
 
 enum { CFR_TAX_PATH_CAP = 128 };
 
+// pipeline stages (profiling slots; DevCounters is an array indexed by stage)
+enum { CFR_STAGE_DUST = 0, CFR_STAGE_SEARCH = 1, CFR_STAGE_SELECT = 2, CFR_STAGE_LOCATE = 3, CFR_STAGE_SCORE = 4,
+       CFR_STAGE_OTHER = 5, CFR_N_STAGES = 6 };
+
 }  // namespace cfrb200

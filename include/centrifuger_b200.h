@@ -148,6 +148,21 @@ int cfr_taxon_counts_reset(cfr_handle *h, void *stream);
 int cfr_get_counters(cfr_handle *h, cfr_counters *c, void *stream);
 int cfr_reset_counters(cfr_handle *h, void *stream);
 
+/* Per-stage profile.  Stages: 0 dust, 1 search, 2 select (boundary adjust +
+ * strand pick + row plan), 3 locate, 4 score (+LCA), 5 other (memsets / D2D).
+ * With profiling on, every kernel is bracketed by CUDA events on its launch
+ * stream; cfr_get_stage_times synchronises, folds the finished events into
+ * `out` (milliseconds and launch counts since the last reset) and optionally
+ * resets.  cfr_get_stage_counters gives the operation counters of one stage
+ * (search / select / locate are the stages that touch the index). */
+typedef struct {
+  double ms[6];
+  uint64_t launches[6];
+} cfr_stage_times;
+int cfr_set_profiling(cfr_handle *h, int on);
+int cfr_get_stage_times(cfr_handle *h, cfr_stage_times *out, int reset);
+int cfr_get_stage_counters(cfr_handle *h, int stage, cfr_counters *c, void *stream);
+
 /* Diagnostics used by the parity tests (device results copied to host). */
 int cfr_debug_bwt_rank(cfr_handle *h, const uint8_t *codes, const uint64_t *pos, const int32_t *inclusive,
                        uint64_t n, uint64_t *out);   /* Sequence_RunBlock::Rank  Sequence_RunBlock.hpp:378 */

@@ -1,0 +1,223 @@
+"""Parity of the CUDA path (through the C ABI, centrifuger_b200.Classifier) with the
+oracle and with the committed reference goldens.  Bit-exact: all work on this
+path is integer / byte / index arithmetic."""
+import hashlib
+import os
+import random
+
+import numpy as np
+import pytest
+
+import centrifuger_b200 as cb
+from conftest import golden_path
+from oracle_binding import Oracle, dust_mask, read_fastx
+
+pytestmark = pytest.mark.gpu
+
+LAYOUTS = [cb.LAYOUT_RUNBLOCK, cb.LAYOUT_OCCLINE]
+
+
+def _args_to_kw(args):
+    kw = dict(dust=True)
+    it = iter(args)
+    for a in it:
+        if a == "--no-dust":
+            kw["dust"] = False
+        elif a == "-k":
+            kw["k"] = int(next(it))
+        elif a == "--hitk-factor":
+            kw["hitk_factor"] = int(next(it))
+        elif a == "--min-hitlen":
+            kw["min_hit_len"] = int(next(it))
+    return kw
+
+
+def _tuples(res, ids, k):
+    out = []
+    for i in range(len(res)):
+        n = int(res["n_assign"][i])
+        out.append((int(res["score"][i]), int(res["secondary_score"][i]), int(res["hit_length"][i]),
+                    int(res["query_length"][i]), n, int(res["by_rank"][i]),
+                    tuple(int(x) for x in ids[i][:min(n, k)])))
+    return out
+
+
+def _oracle_tuples(o, r1, r2):
+    return [o.result_tuple(o.query(r1[i], r2[i] if r2 else None))[:7] for i in range(len(r1))]
+
+
+# ---------------------------------------------------------------- primitives
+@pytest.mark.parametrize("layout", LAYOUTS)
+def test_rank_access_locate(tiny_dir, layout):
+    rng = random.Random(3)
+    for v in ("idx", "idx_b1", "idx_b8", "idx_off3"):
+        idx = os.path.join(tiny_dir, v)
+        o = Oracle(idx)
+        g = cb.Classifier(idx, layout=layout)
+        assert g.layout == layout
+        n = o.n
+        pos = [0, 1, 2, n - 1, n - 2, n // 2] + [rng.randrange(n) for _ in range(3000)]
+        codes, ps, inc, exp = [], [], [], []
+        for p in pos:
+            for c in range(4):
+                for incl in (0, 1):
+                    codes.append(c)
+                    ps.append(p)
+                    inc.append(incl)
+                    exp.append(o.bwt_rank("ACGT"[c], p, incl))
+        got = g.debug_rank(codes, ps, inc)
+        assert got.tolist() == exp
+        acc = g.debug_access(pos)
+        assert ["ACGT"[a] for a in acc] == [o.bwt_access(p) for p in pos]
+        loc = g.debug_locate(pos)
+        assert loc.tolist() == [o.locate(p)[0] for p in pos]
+        g.close()
+        o.close()
+
+
+def test_dust_kernel(tiny_dir):
+    rng = random.Random(5)
+    reads = [b"A" * 100, b"AC" * 50, b"ACG" * 40, b"AAAC" * 30, b"N" * 10 + b"ACGT" * 10 + b"A" * 80, b"acgt" * 30,
+             b"AAGG" * 60, b"ACACG" * 80, b"A" * 70 + b"N" * 70 + b"A" * 70, b"AC", b"", b"ACG",
+             b"A" * 30 + b"N" * 66 + b"C" * 30]
+    for _ in range(3000):
+        L = rng.choice([30, 64, 65, 100, 150, 300, 700])
+        mode = rng.random()
+        if mode < 0.3:
+            s = bytes(rng.choice(b"ACGT") for _ in range(L))
+        elif mode < 0.6:
+            per = rng.randint(1, 8)
+            unit = bytes(rng.choice(b"ACGT") for _ in range(per))
+            s = bytes(unit[i % per] if rng.random() > 0.05 else rng.choice(b"ACGTN") for i in range(L))
+        else:
+            s = bytes(rng.choice(b"AAAAAAACGTN") for _ in range(L))
+        reads.append(s)
+    g = cb.Classifier(os.path.join(tiny_dir, "idx"))
+    m1, m2 = g.debug_dust(reads, reads[::-1])
+    assert m1 == [dust_mask(r) for r in reads]
+    assert m2 == [dust_mask(r) for r in reads[::-1]]
+    g.close()
+
+
+# ---------------------------------------------------------------- goldens
+@pytest.mark.parametrize("layout", LAYOUTS)
+def test_tiny_goldens_tsv(tiny_dir, manifest, layout):
+    """every committed reference TSV is reproduced byte for byte"""
+    for name, m in sorted(manifest["tiny"].items()):
+        files = [os.path.join(tiny_dir, f) for f in m["files"]]
+        ids, r1 = read_fastx(files[0])
+        r2 = read_fastx(files[1])[1] if len(files) == 2 else None
+        g = cb.Classifier(os.path.join(tiny_dir, m["index"]), layout=layout, **_args_to_kw(m["args"]))
+        got = g.classify_tsv(ids, r1, r2)
+        g.close()
+        assert got == open(golden_path("tiny", "expected", name + ".tsv")).read(), name
+        assert hashlib.md5(got.encode()).hexdigest() == m["md5"], name
+
+
+@pytest.mark.parametrize("layout", LAYOUTS)
+def test_example_goldens(example_idx, manifest, layout):
+    """BASELINE.json config 1: the bundled example, bit-exact vs example_class.out"""
+    for case, m in sorted(manifest["example"].items()):
+        files = [golden_path("example", f) for f in m["files"]]
+        ids, r1 = read_fastx(files[0])
+        r2 = read_fastx(files[1])[1] if len(files) == 2 else None
+        g = cb.Classifier(example_idx, layout=layout, **_args_to_kw(m["args"]))
+        got = g.classify_tsv(ids, r1, r2)
+        g.close()
+        assert hashlib.md5(got.encode()).hexdigest() == m["md5"], case
+        if case == "pe_nodust":
+            assert got == open(golden_path("example", "example_class.out")).read()
+
+
+# ---------------------------------------------------------------- vs oracle
+@pytest.mark.parametrize("layout", LAYOUTS)
+def test_small_vs_oracle(small_dir, layout):
+    idx = os.path.join(small_dir, "idx")
+    sets = {"se": ["se_100.fq"], "pe": ["pe_150_1.fq", "pe_150_2.fq"], "edge": ["edge_1.fq", "edge_2.fq"]}
+    for name, files in sets.items():
+        fs = [os.path.join(small_dir, f) for f in files]
+        _, r1 = read_fastx(fs[0])
+        r2 = read_fastx(fs[1])[1] if len(fs) == 2 else None
+        r1 = r1[:6000]
+        r2 = r2[:6000] if r2 else None
+        for kw in (dict(), dict(k=5), dict(k=2, hitk_factor=0, dust=False)):
+            o = Oracle(idx, **kw)
+            o.reset_counters()
+            exp = _oracle_tuples(o, r1, r2)
+            oc = o.counters()
+            o.close()
+            g = cb.Classifier(idx, layout=layout, **kw)
+            g.reset_counters()
+            res, ids = g.classify(r1, r2)
+            assert _tuples(res, ids, g.k) == exp, (name, kw)
+            c = g.counters()
+            for key in ("n_rank", "n_access", "n_search", "n_locate", "n_lf", "n_extend"):
+                assert c[key] == oc[key], (name, kw, key)
+            assert c["n_reads"] == len(r1)
+            tc = g.taxon_counts()
+            assert int(tc[g.node_cnt + 1]) == len(r1)
+            assert int(tc[g.node_cnt + 2]) == int((res["n_assign"] > 0).sum())
+            assert int(tc[:g.node_cnt + 1].sum()) == int(np.minimum(res["n_assign"], g.k).sum())
+            g.close()
+
+
+@pytest.mark.parametrize("layout", LAYOUTS)
+def test_deferral_chunking_and_resident_api(small_dir, layout):
+    idx = os.path.join(small_dir, "idx")
+    _, r1 = read_fastx(os.path.join(small_dir, "pe_150_1.fq"))
+    _, r2 = read_fastx(os.path.join(small_dir, "pe_150_2.fq"))
+    r1, r2 = r1[:5000], r2[:5000]
+    g = cb.Classifier(idx, layout=layout, k=5)
+    res0, ids0 = g.classify(r1, r2)
+    g.close()
+    base = _tuples(res0, ids0, 5)
+    # a tiny arena forces the multi-pass path
+    g = cb.Classifier(idx, layout=layout, k=5, arena_rows=1500)
+    res, ids = g.classify(r1, r2)
+    assert _tuples(res, ids, 5) == base
+    g.close()
+    # small device chunks
+    g = cb.Classifier(idx, layout=layout, k=5, max_batch_reads=777)
+    res, ids = g.classify(r1, r2)
+    assert _tuples(res, ids, 5) == base
+    # resident API
+    s1, o1 = cb.pack_reads(r1)
+    s2, o2 = cb.pack_reads(r2)
+    b = g.upload(s1, o1, s2, o2)
+    g.classify_resident(b)
+    res, ids = g.fetch(b)
+    assert _tuples(res, ids.reshape(-1, 5), 5) == base
+    g.classify_resident(b)  # idempotent: classifying a resident batch twice changes nothing
+    res, ids = g.fetch(b)
+    assert _tuples(res, ids.reshape(-1, 5), 5) == base
+    b.free()
+    g.close()
+
+
+def test_edge_inputs(tiny_dir):
+    idx = os.path.join(tiny_dir, "idx")
+    g = cb.Classifier(idx)
+    o = Oracle(idx)
+    res, ids = g.classify([], None)
+    assert len(res) == 0
+    reads = [b"", b"A", b"ACGTACGTAC", b"N" * 300, b"ACGT" * 200]
+    res, ids = g.classify(reads)
+    assert _tuples(res, ids, 1) == _oracle_tuples(o, reads, None)
+    res, ids = g.classify(reads, reads[::-1])
+    assert _tuples(res, ids, 1) == _oracle_tuples(o, reads, reads[::-1])
+    g.close()
+    o.close()
+    with pytest.raises(cb.CfrError):
+        cb.Classifier(idx, k=0)
+    with pytest.raises(cb.CfrError):
+        cb.Classifier(os.path.join(tiny_dir, "does_not_exist"))
+
+
+def test_single_huge_read_overflows_loudly(tiny_dir):
+    """a read whose rows exceed the whole arena is an error, never a silent truncation"""
+    g = cb.Classifier(os.path.join(tiny_dir, "idx"), k=5, arena_rows=8)
+    _, r1 = read_fastx(os.path.join(tiny_dir, "edge.fq"))
+    with pytest.raises(cb.CfrError) as e:
+        g.classify(r1)
+    assert e.value.code == -7
+    g.close()

@@ -1,0 +1,104 @@
+"""Host logic: the product's per-task stage functions (cfr_core.cuh /
+cfr_pipeline.cuh, compiled for the host by tests/hostsim) and its .cfr parser
+against the oracle.  No GPU needed; the CUDA path is checked by test_gpu_*.py."""
+import os
+import random
+
+import pytest
+
+from hostsim_binding import HostSim, hostsim_dust, result_tuples
+from oracle_binding import Oracle, dust_mask, read_fastx
+
+
+def _compare(idx, files, layout, arena_rows=0, limit=None, **kw):
+    _, r1 = read_fastx(files[0])
+    r2 = read_fastx(files[1])[1] if len(files) == 2 else None
+    if limit:
+        r1 = r1[:limit]
+        r2 = r2[:limit] if r2 else None
+    o = Oracle(idx, **kw)
+    hs = HostSim(idx, layout=layout, **kw)
+    try:
+        o.reset_counters()
+        exp = []
+        for i in range(len(r1)):
+            t = o.result_tuple(o.query(r1[i], r2[i] if r2 else None))
+            exp.append(t[:7])
+        res, ids, cnt = hs.classify(r1, r2, arena_rows=arena_rows)
+        got = result_tuples(res, ids, hs.p.max_result)
+        assert got == exp
+        oc = o.counters()
+        for k in ("n_rank", "n_access", "n_search", "n_locate", "n_lf", "n_extend"):
+            assert oc[k] == cnt[k], k
+    finally:
+        hs.close()
+        o.close()
+
+
+@pytest.mark.parametrize("layout", [1, 2])
+@pytest.mark.parametrize("variant", ["idx", "idx_b1", "idx_b8", "idx_off3"])
+def test_tiny_all_read_sets(tiny_dir, layout, variant):
+    idx = os.path.join(tiny_dir, variant)
+    sets = (["se_100.fq"], ["pe_100_1.fq", "pe_100_2.fq"], ["edge.fq"], ["edge_1.fq", "edge_2.fq"])
+    for files in sets:
+        fs = [os.path.join(tiny_dir, f) for f in files]
+        for kw in (dict(), dict(k=5), dict(k=3, hitk_factor=2), dict(dust=False, min_hit_len=16),
+                   dict(k=2, hitk_factor=0)):
+            _compare(idx, fs, layout, **kw)
+
+
+@pytest.mark.parametrize("layout", [1, 2])
+def test_small_arena_deferral(tiny_dir, layout):
+    """a locate arena much smaller than the batch needs forces the multi-pass path"""
+    idx = os.path.join(tiny_dir, "idx")
+    fs = [os.path.join(tiny_dir, "pe_100_1.fq"), os.path.join(tiny_dir, "pe_100_2.fq")]
+    _compare(idx, fs, layout, arena_rows=300, k=5)
+
+
+def test_example(example_idx):
+    from conftest import golden_path
+    fs = [golden_path("example", "example_1.fq"), golden_path("example", "example_2.fq")]
+    for layout in (1, 2):
+        _compare(example_idx, fs, layout)
+        _compare(example_idx, fs[:1], layout, k=5, dust=False)
+
+
+def test_dust_compressed_interval_table():
+    """the 64-slot replacement of the reference's perfect-interval vector is exact"""
+    rng = random.Random(5)
+    tests = [b"A" * 100, b"AC" * 50, b"ACG" * 40, b"AAAC" * 30, b"N" * 10 + b"ACGT" * 10 + b"A" * 80,
+             b"acgt" * 30, b"AAGG" * 60, b"ACACG" * 80, b"A" * 70 + b"N" * 70 + b"A" * 70, b"AC", b"", b"ACG",
+             b"A" * 30 + b"N" * 66 + b"C" * 30]
+    for _ in range(1500):
+        L = rng.choice([30, 64, 65, 100, 150, 300, 700])
+        mode = rng.random()
+        if mode < 0.3:
+            s = bytes(rng.choice(b"ACGT") for _ in range(L))
+        elif mode < 0.6:
+            per = rng.randint(1, 8)
+            unit = bytes(rng.choice(b"ACGT") for _ in range(per))
+            s = bytes(unit[i % per] if rng.random() > 0.05 else rng.choice(b"ACGTN") for i in range(L))
+        else:
+            s = bytes(rng.choice(b"AAAAAAACGTN") for _ in range(L))
+        tests.append(s)
+    for s in tests:
+        assert hostsim_dust(s) == dust_mask(s), s
+
+
+@pytest.mark.parametrize("layout", [1, 2])
+def test_rank_access_locate_primitives(tiny_dir, layout):
+    rng = random.Random(11)
+    for v in ("idx", "idx_b1", "idx_b8"):
+        idx = os.path.join(tiny_dir, v)
+        o = Oracle(idx)
+        hs = HostSim(idx, layout=layout)
+        n = o.n
+        pos = [0, 1, n - 1, n // 2] + [rng.randrange(n) for _ in range(400)]
+        for p in pos:
+            assert hs.bwt_access(p) == o.bwt_access(p)
+            for c in "ACGT":
+                assert hs.bwt_rank(c, p, 1) == o.bwt_rank(c, p, 1)
+                assert hs.bwt_rank(c, p, 0) == o.bwt_rank(c, p, 0)
+            assert hs.locate(p) == o.locate(p)[0]
+        hs.close()
+        o.close()

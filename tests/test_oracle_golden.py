@@ -1,0 +1,103 @@
+"""The oracle (oracle/cfr_oracle.c) against the golden vectors.
+
+Pins the CPU restatement to (1) the reference's own fixture
+example/example_class.out and (2) outputs of the unmodified reference binary
+committed under tests/golden (see tests/golden/make_golden.py).
+"""
+import hashlib
+import os
+
+import pytest
+
+from conftest import golden_path
+from oracle_binding import Oracle, dust_mask, read_fastx
+
+
+def _args_to_kw(args):
+    kw = dict(dust=True)
+    it = iter(args)
+    for a in it:
+        if a == "--no-dust":
+            kw["dust"] = False
+        elif a == "-k":
+            kw["k"] = int(next(it))
+        elif a == "--hitk-factor":
+            kw["hitk_factor"] = int(next(it))
+        elif a == "--min-hitlen":
+            kw["min_hit_len"] = int(next(it))
+    return kw
+
+
+def _run(idx, files, args):
+    ids, r1 = read_fastx(files[0])
+    r2 = read_fastx(files[1])[1] if len(files) == 2 else None
+    o = Oracle(idx, **_args_to_kw(args))
+    try:
+        return o.classify_tsv(ids, r1, r2)
+    finally:
+        o.close()
+
+
+def test_example_class_out(example_idx):
+    """README.md:195-209 fixture; matches the reference only with --no-dust."""
+    files = [golden_path("example", "example_1.fq"), golden_path("example", "example_2.fq")]
+    got = _run(example_idx, files, ["--no-dust"])
+    exp = open(golden_path("example", "example_class.out")).read()
+    assert got == exp
+    assert hashlib.md5(got.encode()).hexdigest() == "fd328aa27f2bf4c83ac4eaacde30920c"
+
+
+@pytest.mark.parametrize("case", ["pe_default", "pe_nodust", "pe_k5", "se_default", "se_k5_nodust"])
+def test_example_reference_outputs(example_idx, manifest, case):
+    m = manifest["example"][case]
+    files = [golden_path("example", f) for f in m["files"]]
+    got = _run(example_idx, files, m["args"])
+    assert got == open(golden_path("example", case + ".tsv")).read()
+    assert hashlib.md5(got.encode()).hexdigest() == m["md5"]
+
+
+def test_tiny_reference_outputs(tiny_dir, manifest):
+    """48 (index variant x read set x option) cases produced by the reference binary."""
+    assert len(manifest["tiny"]) >= 40
+    for name, m in sorted(manifest["tiny"].items()):
+        files = [os.path.join(tiny_dir, f) for f in m["files"]]
+        got = _run(os.path.join(tiny_dir, m["index"]), files, m["args"])
+        exp = open(golden_path("tiny", "expected", name + ".tsv")).read()
+        assert got == exp, name
+        assert hashlib.md5(got.encode()).hexdigest() == m["md5"], name
+
+
+def test_index_header_facts(example_idx):
+    """the example index header as parsed."""
+    o = Oracle(example_idx)
+    assert o.scalar(0) == 6901256 and o.scalar(1) == 2 and o.scalar(2) == 3450628
+    assert o.scalar(3) == 4901542 and chr(o.scalar(4)) == "C"
+    assert o.scalar(5) == 16 and o.scalar(6) == 1 and o.scalar(7) == 431329
+    assert o.scalar(8) == 10 and o.scalar(9) == 1 and o.scalar(14) == 23
+    assert [o.scalar(18 + i) for i in range(5)] == [0, 2131485, 3452524, 4776192, 6901256]
+    o.close()
+
+
+def test_rank_access_consistency(tiny_dir):
+    """Rank must be the prefix sum of Access (the check compactds/test.cpp:940-1002 performs)."""
+    for v in ("idx", "idx_b1", "idx_b8"):
+        o = Oracle(os.path.join(tiny_dir, v))
+        n = o.n
+        cnt = {c: 0 for c in "ACGT"}
+        step = 1
+        for i in range(0, min(n, 20000), step):
+            c = o.bwt_access(i)
+            for x in "ACGT":
+                assert o.bwt_rank(x, i, 0) == cnt[x]
+            cnt[c] += 1
+            assert o.bwt_rank(c, i, 1) == cnt[c]
+        o.close()
+
+
+def test_dust_known_answers():
+    assert dust_mask(b"A" * 100) == b"N" * 100
+    assert dust_mask(b"AC") == b"AC"
+    s = b"ACGTTGCAAGCTTGACCATGGTACCGATCGATTAGCCGTA"
+    assert dust_mask(s) == s  # high complexity: untouched
+    m = dust_mask(b"ACGTTGCAAGCTTGACCATGGTACCGATCG" + b"T" * 40 + b"ACGTTGCAAGCTTGACCATGGTACCGATCG")
+    assert m.count(b"N") >= 36 and m[:20] == b"ACGTTGCAAGCTTGACCATG"

@@ -145,6 +145,49 @@ def make_reads_pe(genomes, n, rlen, err=0.01, seed=11, insert_mu=300, insert_sd=
     return a1f, a2f
 
 
+def concat_genomes(genomes):
+    """(codes of all genomes back to back, start offset of each, lengths)"""
+    lens = np.array([len(g[2]) for g in genomes], dtype=np.int64)
+    starts = np.concatenate([[0], np.cumsum(lens)[:-1]])
+    return np.concatenate([g[2] for g in genomes]), starts, lens
+
+
+def make_reads_se_fast(genomes, n, rlen, err=0.01, seed=7, cat=None):
+    """Vectorised variant of make_reads_se for bench-sized batches (same model,
+    different random stream).  Returns a (n, rlen) uint8 ASCII array."""
+    rng = np.random.default_rng(seed)
+    allg, starts, lens = cat if cat is not None else concat_genomes(genomes)
+    gi = rng.integers(0, len(lens), size=n)
+    pos = starts[gi] + (rng.random(n) * (lens[gi] - rlen)).astype(np.int64)
+    out = allg[pos[:, None] + np.arange(rlen, dtype=np.int64)[None, :]]
+    e = rng.random((n, rlen)) < err
+    out = np.where(e, (out + rng.integers(1, 4, size=(n, rlen), dtype=np.uint8)) % 4, out).astype(np.uint8)
+    out = ACGT[out]
+    flip = rng.random(n) < 0.5
+    out[flip] = revcomp(out[flip])
+    return out
+
+
+def make_reads_pe_fast(genomes, n, rlen, err=0.01, seed=11, insert_mu=300, insert_sd=30, cat=None):
+    rng = np.random.default_rng(seed)
+    allg, starts, lens = cat if cat is not None else concat_genomes(genomes)
+    gi = rng.integers(0, len(lens), size=n)
+    ins = np.clip(rng.normal(insert_mu, insert_sd, size=n).astype(np.int64), rlen, None)
+    ins = np.minimum(ins, lens[gi] - 1)
+    pos = starts[gi] + (rng.random(n) * (lens[gi] - ins)).astype(np.int64)
+    ar = np.arange(rlen, dtype=np.int64)[None, :]
+    r1 = allg[pos[:, None] + ar]
+    r2 = allg[(pos + ins - rlen)[:, None] + ar]
+    outs = []
+    for r in (r1, r2):
+        e = rng.random((n, rlen)) < err
+        outs.append(np.where(e, (r + rng.integers(1, 4, size=(n, rlen), dtype=np.uint8)) % 4, r).astype(np.uint8))
+    a1 = ACGT[outs[0]]
+    a2 = revcomp(ACGT[outs[1]])
+    flip = rng.random(n) < 0.5
+    return np.where(flip[:, None], a2, a1), np.where(flip[:, None], a1, a2)
+
+
 def write_fastq(path, reads, prefix="r", suffix=""):
     """reads: 2-D uint8 ascii array or list of bytes."""
     with open(path, "wb") as f:
