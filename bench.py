@@ -248,8 +248,12 @@ def main():
 
     clf = cb.Classifier(idx, k=w["k"], dust=not a.no_dust, layout=a.layout, device=local_rank,
                         max_batch_reads=max(n, 1 << 20))
-    stream = torch.cuda.current_stream()
+    # a dedicated (non-default) torch stream: its handle is passed through the C ABI so the
+    # library's kernels and torch's CUDA events are on the same stream
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
     sptr = stream.cuda_stream
+    assert sptr != 0
     # pinned host staging (torch supplies pinned memory and events; the work is in libcfrb200.so)
     pin = lambda arr: torch.from_numpy(arr).pin_memory() if arr is not None else None
     p_seq1, p_off1, p_seq2, p_off2 = pin(seq1), pin(off1), pin(seq2), pin(off2)

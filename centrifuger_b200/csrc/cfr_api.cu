@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -81,6 +82,7 @@ struct cfr_handle {
   DevIndex ix;
   DevParams P;
   int layout = CFR_LAYOUT_RUNBLOCK;
+  bool coop = true;  // occ lines read by 4-lane groups (CFR_B200_SCALAR_OCC=1 selects one lane per task)
   std::vector<void *> index_allocs;
   size_t hbm_bytes = 0;
   int sm_count = 148;
@@ -364,7 +366,8 @@ void fill_chunk(cfr_handle *h, cfr_device_batch *b, ChunkDev &B) {
 }
 
 // one select -> locate -> score pass over B.read_list
-template <class Bwt>
+// Bwt = scalar layout policy (select stage), BwtWide = policy of the search / locate kernels
+template <class Bwt, class BwtWide>
 int run_pass(cfr_handle *h, const ChunkDev &B, int first_pass, cudaStream_t s) {
   {
     StageScope sc(h, s, CFR_STAGE_OTHER);
@@ -378,7 +381,7 @@ int run_pass(cfr_handle *h, const ChunkDev &B, int first_pass, cudaStream_t s) {
   }
   {
     StageScope sc(h, s, CFR_STAGE_LOCATE);
-    k_locate<Bwt><<<grid_for(h, B.arena_cap, 128, 16), 128, 0, s>>>(h->ix, B);
+    k_locate<BwtWide><<<grid_for(h, B.arena_cap * BwtWide::LANES, 128, 16), 128, 0, s>>>(h->ix, B);
   }
   {
     StageScope sc(h, s, CFR_STAGE_SCORE);
@@ -389,7 +392,7 @@ int run_pass(cfr_handle *h, const ChunkDev &B, int first_pass, cudaStream_t s) {
   return CFR_OK;
 }
 
-template <class Bwt>
+template <class Bwt, class BwtWide>
 int run_first(cfr_handle *h, cfr_device_batch *b, cudaStream_t s) {
   ChunkDev B;
   fill_chunk(h, b, B);
@@ -400,20 +403,20 @@ int run_first(cfr_handle *h, cfr_device_batch *b, cudaStream_t s) {
       CUDA_TRY(cudaMemcpyAsync(b->seq.p, b->seq_raw.p, b->seq_bytes, cudaMemcpyDeviceToDevice, s));
     }
     StageScope sc(h, s, CFR_STAGE_DUST);
-    k_dust<<<grid_for(h, B.n_reads * B.mates, 128, 16), 128, 0, s>>>(B);
+    k_dust<<<grid_for(h, B.n_reads * B.mates, CFR_DUST_THREADS, 5), CFR_DUST_THREADS, CFR_DUST_SMEM, s>>>(B);
     ++h->launches;
   }
   {
     StageScope sc(h, s, CFR_STAGE_SEARCH);
-    k_search<Bwt><<<grid_for(h, B.n_reads * 2 * B.mates, 128, 16), 128, 0, s>>>(h->ix, h->P, B);
+    k_search<BwtWide><<<grid_for(h, B.n_reads * 2 * B.mates * BwtWide::LANES, 128, 16), 128, 0, s>>>(h->ix, h->P, B);
     ++h->launches;
   }
   CUDA_TRY(cudaGetLastError());
-  return run_pass<Bwt>(h, B, 1, s);
+  return run_pass<Bwt, BwtWide>(h, B, 1, s);
 }
 
 // after the first pass: re-run select/locate/score for reads that did not fit the arena
-template <class Bwt>
+template <class Bwt, class BwtWide>
 int finish_deferred(cfr_handle *h, cfr_device_batch *b, cudaStream_t s) {
   if (b->n_reads == 0) return CFR_OK;
   ChunkDev B;
@@ -437,7 +440,7 @@ int finish_deferred(cfr_handle *h, cfr_device_batch *b, cudaStream_t s) {
     B.n_list = sc.n_def;
     cur ^= 1;
     B.deferred = lists[cur];
-    int st = run_pass<Bwt>(h, B, 0, s);
+    int st = run_pass<Bwt, BwtWide>(h, B, 0, s);
     if (st) return st;
   }
   return fail(CFR_ERR_OVERFLOW, "deferral loop did not converge");
@@ -522,6 +525,7 @@ int cfr_open(const char *idx_prefix, const cfr_params *p, int device, cfr_handle
     if ((u64)free_b < need + (8ull << 30)) h->layout = CFR_LAYOUT_RUNBLOCK;  // keep 8 GiB for work areas
   }
   if (h->layout == CFR_LAYOUT_OCCLINE && (st = build_occ_lines(h))) return bail(st);
+  if (const char *e = getenv("CFR_B200_SCALAR_OCC")) h->coop = !(e[0] == '1');
   h->file.map1.close();  // everything needed from .1.cfr now lives in HBM
   *out = h;
   return CFR_OK;
@@ -583,7 +587,9 @@ int cfr_classify_resident(cfr_handle *h, cfr_device_batch *b, void *stream) {
   cudaStream_t s = pick_stream(h, stream);
   h->host_bases += b->total_bases;
   b->classified = true;
-  return h->layout == CFR_LAYOUT_OCCLINE ? run_first<BwtOccLine>(h, b, s) : run_first<BwtRunBlock>(h, b, s);
+  if (h->layout == CFR_LAYOUT_OCCLINE)
+    return h->coop ? run_first<BwtOccLine, BwtOccCoop4>(h, b, s) : run_first<BwtOccLine, BwtOccLine>(h, b, s);
+  return run_first<BwtRunBlock, BwtRunBlock>(h, b, s);
 }
 
 int cfr_batch_fetch(cfr_handle *h, cfr_device_batch *b, cfr_result *results, uint64_t *ids, void *stream) {
@@ -591,7 +597,11 @@ int cfr_batch_fetch(cfr_handle *h, cfr_device_batch *b, cfr_result *results, uin
   if (!b->classified) return fail(CFR_ERR_ARG, "batch was not classified");
   CUDA_TRY(cudaSetDevice(h->device));
   cudaStream_t s = pick_stream(h, stream);
-  int st = h->layout == CFR_LAYOUT_OCCLINE ? finish_deferred<BwtOccLine>(h, b, s) : finish_deferred<BwtRunBlock>(h, b, s);
+  int st;
+  if (h->layout == CFR_LAYOUT_OCCLINE)
+    st = h->coop ? finish_deferred<BwtOccLine, BwtOccCoop4>(h, b, s) : finish_deferred<BwtOccLine, BwtOccLine>(h, b, s);
+  else
+    st = finish_deferred<BwtRunBlock, BwtRunBlock>(h, b, s);
   if (st) return st;
   static_assert(sizeof(cfr_result) == sizeof(DevResult), "result layout");
   if (b->n_reads) {
@@ -846,7 +856,7 @@ int cfr_debug_dust(cfr_handle *h, const cfr_read_batch *in, char *masked1, char 
   const u64 len1 = in->off1[in->n_reads] - in->off1[0];
   const u64 len2 = in->seq2 ? in->off2[in->n_reads] - in->off2[0] : 0;
   cudaMemcpyAsync(b.seq.p, b.seq_raw.p, b.seq_bytes, cudaMemcpyDeviceToDevice, h->stream);
-  if (in->n_reads) k_dust<<<grid_for(h, B.n_reads * B.mates, 128, 16), 128, 0, h->stream>>>(B);
+  if (in->n_reads) k_dust<<<grid_for(h, B.n_reads * B.mates, CFR_DUST_THREADS, 5), CFR_DUST_THREADS, CFR_DUST_SMEM, h->stream>>>(B);
   ++h->launches;
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess) e = cudaMemcpyAsync(masked1, b.seq.p, len1, cudaMemcpyDeviceToHost, h->stream);

@@ -82,15 +82,36 @@ CFR_HD int base_code(unsigned char c) {
   return c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : 4;
 }
 
+// Sequential byte reader with a 16-byte register window: one 128-bit load per
+// 16 bases instead of one byte load per base (read buffers are padded so the
+// aligned block around any valid byte is readable).
+struct ByteWindow {
+  u64 w0 = 0, w1 = 0;
+  unsigned long long blk = ~0ull;
+  CFR_HD unsigned get(const unsigned char *p) {
+    const unsigned long long a = (unsigned long long)p;
+    const unsigned long long b = a >> 4;
+    if (b != blk) {
+      const u64x2 v = ld128(reinterpret_cast<const u64x2 *>(a & ~15ull));
+      w0 = v.x;
+      w1 = v.y;
+      blk = b;
+    }
+    const int k = (int)(a & 15);
+    return (unsigned)(((k & 8) ? w1 : w0) >> ((k & 7) * 8)) & 0xffu;
+  }
+};
+
 // One strand of one read as the backward search sees it.  rc strands are never
 // materialised: rc[p] = comp(r[len-1-p]) (Classifier.hpp:99-111,846-856).
 struct StrandSeq {
   const unsigned char *r;  // the mate as uploaded (after DUST)
   int len;
   int rc;
-  CFR_HD int operator()(int p) const {
-    if (!rc) return base_code(ld8(r + p));
-    int c = base_code(ld8(r + (len - 1 - p)));
+  ByteWindow win;
+  CFR_HD int operator()(int p) {
+    if (!rc) return base_code((unsigned char)win.get(r + p));
+    const int c = base_code((unsigned char)win.get(r + (len - 1 - p)));
     return c > 3 ? 4 : 3 - c;
   }
 };
@@ -234,6 +255,8 @@ struct BwtRunBlock {
   }
   static CFR_HD u64 rank(const DevIndex &ix, int c, u64 i, int inclusive) { return rb_rank(ix, c, i, inclusive); }
   static CFR_HD int access(const DevIndex &ix, u64 i) { return rb_access(ix, i); }
+  static CFR_HD bool leader() { return true; }
+  enum { LANES = 1 };
 };
 
 // ---------------------------------------------------------------------------
@@ -326,7 +349,83 @@ struct BwtOccLine {
     const OccRegs a = occ_load(ix.occ + (i >> 7));
     return occ_symbol(a, (int)(i & 127));
   }
+  static CFR_HD bool leader() { return true; }
+  enum { LANES = 1 };
 };
+
+#if defined(__CUDACC__)
+// The same occ lines read cooperatively: 4 adjacent lanes own one search / walk.
+// Each lane pulls one 16-byte quarter of the 64-byte line (one coalesced 128-bit
+// load per line for the whole group instead of four divergent ones), counts its
+// quarter, and the group sums with two xor-shuffles.  All four lanes carry the
+// same scalar state (sp, ep, l, ...), so control flow is uniform inside a group.
+struct BwtOccCoop4 {
+  enum { LANES = 4 };
+  static __device__ __forceinline__ unsigned gmask() { return 0xFu << (threadIdx.x & 28); }
+  static __device__ __forceinline__ int gl() { return threadIdx.x & 3; }
+  static __device__ __forceinline__ bool leader() { return (threadIdx.x & 3) == 0; }
+  static __device__ __forceinline__ ulonglong2 quarter(const DevIndex &ix, u64 line) {
+    return __ldg(reinterpret_cast<const ulonglong2 *>(ix.occ + line) + gl());
+  }
+  // this lane's share of occ(c, within) for the line whose quarter it holds
+  static __device__ __forceinline__ u64 piece(const ulonglong2 &v, int c, int within) {
+    const int g = gl();
+    const int i0 = (g & 1) * 2;
+    const u64 cnt = (c == i0) ? v.x : ((c == i0 + 1) ? v.y : 0ull);
+    const u64 ml = (c & 1) ? ~0ull : 0ull, mh = (c & 2) ? ~0ull : 0ull;
+    const u64 m = ~(v.x ^ ml) & ~(v.y ^ mh);
+    const int w = within - (g & 1) * 64;
+    const u64 k = w >= 64 ? ~0ull : (w <= 0 ? 0ull : ((1ull << w) - 1ull));
+    return g < 2 ? cnt : (u64)__popcll(m & k);
+  }
+  static __device__ __forceinline__ u64 gsum(u64 p) {
+    const unsigned m = gmask();
+    p += __shfl_xor_sync(m, p, 1);
+    p += __shfl_xor_sync(m, p, 2);
+    return p;
+  }
+  static __device__ __forceinline__ int symbol(const ulonglong2 &v, int within) {
+    const int s = within & 63;
+    const int mine = (int)(((v.x >> s) & 1ull) | (((v.y >> s) & 1ull) << 1));
+    return __shfl_sync(gmask(), mine, 2 + (within >> 6), 4);
+  }
+  static __device__ __forceinline__ void extend(const DevIndex &ix, int c, u64 sp, u64 ep, u64 &nsp, u64 &nep,
+                                                OpCount &oc) {
+    const u64 off = ix.C[c];
+    ++oc.extend;
+    ++oc.rank;
+    const u64 lsp = sp >> 7;
+    const ulonglong2 a = quarter(ix, lsp);
+    u64 psp = piece(a, c, (int)(sp & 127));
+    if (sp != ep) {
+      ++oc.rank;
+      const u64 x = ep + 1, lx = x >> 7;
+      ulonglong2 e = a;
+      if (lx != lsp) e = quarter(ix, lx);
+      u64 pep = piece(e, c, (int)(x & 127));
+      psp = gsum(psp);
+      pep = gsum(pep);
+      nsp = off + psp + last_chr_fix(ix, c, sp, 0);
+      nep = off + pep + last_chr_fix(ix, c, ep, 1) - 1;
+    } else {
+      ++oc.access;
+      psp = gsum(psp);
+      const int sym = symbol(a, (int)(ep & 127));
+      nsp = off + psp + last_chr_fix(ix, c, sp, 0);
+      nep = nsp + ((sym == c) ? 0ull : ~0ull);
+    }
+  }
+  static __device__ __forceinline__ u64 lf(const DevIndex &ix, u64 i, OpCount &oc) {
+    ++oc.access;
+    ++oc.rank;
+    const ulonglong2 a = quarter(ix, i >> 7);
+    const int w = (int)(i & 127);
+    const int c = symbol(a, w);
+    const u64 p = gsum(piece(a, c, w));
+    return ix.C[c] + p + 1 + last_chr_fix(ix, c, i, 1) - 1;
+  }
+};
+#endif
 
 // ---------------------------------------------------------------------------
 // FM-index search and locate
@@ -334,7 +433,7 @@ struct BwtOccLine {
 
 // FMIndex::BackwardSearch with GetBackwardSearchInitialRange inlined
 template <class Bwt>
-CFR_HD int backward_search(const DevIndex &ix, const StrandSeq &s, int m, u64 &sp, u64 &ep, OpCount &oc) {
+CFR_HD int backward_search(const DevIndex &ix, StrandSeq &s, int m, u64 &sp, u64 &ep, OpCount &oc) {
   const int W = ix.pre_width;
   if (m < W) return 0;
   ++oc.search;
@@ -442,17 +541,19 @@ CFR_HD u64 hit_score(int l, int mhl) {
 
 // Classifier::GetHitsFromRead; returns the number of hits written
 template <class Bwt>
-CFR_HD int get_hits_from_read(const DevIndex &ix, const StrandSeq &s, int mhl, Hit *out, int cap, OpCount &oc) {
+CFR_HD int get_hits_from_read(const DevIndex &ix, StrandSeq &s, int mhl, Hit *out, int cap, OpCount &oc) {
   u64 sp = 0, ep = 0;
   int n = 0;
   int remaining = s.len;
   while (remaining >= mhl) {
     const int l = backward_search<Bwt>(ix, s, remaining, sp, ep, oc);
     if (l >= mhl && sp <= ep && n < cap) {
-      out[n].sp = sp;
-      out[n].ep = ep;
-      out[n].l = l;
-      out[n].offset = s.len - remaining;
+      if (Bwt::leader()) {
+        out[n].sp = sp;
+        out[n].ep = ep;
+        out[n].l = l;
+        out[n].offset = s.len - remaining;
+      }
       ++n;
     }
     remaining -= (l + 1);
@@ -466,7 +567,7 @@ template <class Bwt>
 CFR_HD void adjust_hit_boundary(const DevIndex &ix, const unsigned char *r, int len, Hit *h0, int n0, Hit *h1,
                                 int n1, OpCount &oc) {
   if (!n0 || !n1) return;
-  StrandSeq fw{r, len, 0}, rc{r, len, 1};
+  StrandSeq fw{r, len, 0, ByteWindow()}, rc{r, len, 1, ByteWindow()};
   u64 sp = 0, ep = 0;
   int j = n0 - 1;
   bool need_fix0 = false, need_fix1 = false;
@@ -951,23 +1052,48 @@ CFR_HD void score_read(const DevIndex &ix, const DevParams &p, const FinalHit *h
 // score >= 3 for every stored interval), so which of two equal ratios is kept
 // does not change any outcome.
 
-struct DustState {
-  unsigned char cw[125], cv[125];  // triplet counts, base-5 index
-  unsigned char win[64];           // ring buffer of triplet indices; size <= 62
-  unsigned short p_score[64];      // per start slot: score of the latest interval
-  unsigned char p_span[64];        // its end - start - 2
-  unsigned char p_len[64];         // its end - start
+// A per-thread byte array stored as a column of 32-bit words with a stride of SW
+// words between consecutive words: SW = 1 is a plain array (host / local memory);
+// SW = blockDim.x puts every thread's array in its own shared-memory bank, so the
+// data-dependent counter updates of a warp never conflict.
+template <int SW>
+struct ByteCol {
+  unsigned char *base;
+  CFR_HD unsigned char &operator[](int j) const { return base[(j >> 2) * (SW * 4) + (j & 3)]; }
+};
+
+template <int SW>
+struct DustStateT {
+  ByteCol<SW> cw, cv;          // triplet counts of the window / of its suffix v, base-5 index (125 used)
+  ByteCol<SW> win;             // ring buffer of triplet indices; size <= 62
+  unsigned short p_score[64];  // per start slot: score of the latest interval
+  unsigned char p_span[64];    // its end - start - 2
+  unsigned char p_len[64];     // its end - start
   u64 p_valid;
   int head, size;
   int rv, rw, lv;
 };
 
+// plain-array instantiation (host simulation, tests)
+struct DustState : DustStateT<1> {
+  alignas(4) unsigned char cw_store[128];
+  alignas(4) unsigned char cv_store[128];
+  alignas(4) unsigned char win_store[64];
+  CFR_HD DustState() {
+    cw.base = cw_store;
+    cv.base = cv_store;
+    win.base = win_store;
+  }
+};
+
 CFR_HD int dust_code(unsigned char c) { return base_code(c); }
 
-CFR_HD int dust_win_at(const DustState &d, int i) { return d.win[(d.head + i) & 63]; }
+template <int SW>
+CFR_HD int dust_win_at(const DustStateT<SW> &d, int i) { return d.win[(d.head + i) & 63]; }
 
 // Dustmasker::SaveMaskedRegions for the single start that can leave the window
-CFR_HD void dust_evict(DustState &d, unsigned char *out, int seg_off, int start) {
+template <int SW>
+CFR_HD void dust_evict(DustStateT<SW> &d, unsigned char *out, int seg_off, int start) {
   const int slot = start & 63;
   if ((d.p_valid >> slot) & 1ull) {
     const int e = start + d.p_len[slot];
@@ -977,33 +1103,38 @@ CFR_HD void dust_evict(DustState &d, unsigned char *out, int seg_off, int start)
 }
 
 // SDust on S[0..n): masks into out[seg_off ...]
-CFR_HD void dust_sdust(const unsigned char *S, int n, unsigned char *out, int seg_off, DustState &d) {
+template <int SW>
+CFR_HD void dust_sdust(const unsigned char *S, int n, unsigned char *out, int seg_off, DustStateT<SW> &d) {
   const int W = 64, T = 20;
   if (n < 3) return;
-  for (int i = 0; i < 125; ++i) d.cw[i] = d.cv[i] = 0;
+  for (int i = 0; i < 128; i += 4) {
+    *reinterpret_cast<u32 *>(&d.cw[i]) = 0;
+    *reinterpret_cast<u32 *>(&d.cv[i]) = 0;
+  }
   d.head = d.size = 0;
   d.rv = d.rw = d.lv = 0;
   d.p_valid = 0;
-  int c1 = dust_code(ld8(S)), c2 = dust_code(ld8(S + 1));
+  ByteWindow bw;
+  int c1 = dust_code((unsigned char)bw.get(S)), c2 = dust_code((unsigned char)bw.get(S + 1));
   int wfinish, wstart = 0;
   for (wfinish = 2; wfinish < n; ++wfinish) {
     wstart = 0;
     if (wfinish + 1 > W) wstart = wfinish + 1 - W;
     if (wstart > 0) dust_evict(d, out, seg_off, wstart - 1);
-    const int c3 = dust_code(ld8(S + wfinish));
+    const int c3 = dust_code((unsigned char)bw.get(S + wfinish));
     const int t = c1 * 25 + c2 * 5 + c3;
     c1 = c2;
     c2 = c3;
     // ShiftWindow (Dustmasker.hpp:106-136)
     if (d.size >= W - 2) {
       const int old = d.win[d.head];
-      --d.cw[old];
-      d.rw -= d.cw[old];
+      const int cwo = --d.cw[old];
+      d.rw -= cwo;
       d.head = (d.head + 1) & 63;
       --d.size;
       if (d.lv > d.size) {
-        --d.cv[old];
-        d.rv -= d.cv[old];
+        const int cvo = --d.cv[old];
+        d.rv -= cvo;
         --d.lv;
       }
     }
@@ -1012,13 +1143,14 @@ CFR_HD void dust_sdust(const unsigned char *S, int n, unsigned char *out, int se
     ++d.lv;
     d.rw += d.cw[t];
     ++d.cw[t];
-    d.rv += d.cv[t];
-    ++d.cv[t];
-    if (d.cv[t] * 10 > 2 * T) {
+    const int cvt = d.cv[t];
+    d.rv += cvt;
+    d.cv[t] = (unsigned char)(cvt + 1);
+    if ((cvt + 1) * 10 > 2 * T) {
       for (;;) {
         const int s = dust_win_at(d, d.size - d.lv);
-        --d.cv[s];
-        d.rv -= d.cv[s];
+        const int cvs = --d.cv[s];
+        d.rv -= cvs;
         --d.lv;
         if (s == t) break;
       }
@@ -1062,20 +1194,23 @@ CFR_HD void dust_sdust(const unsigned char *S, int n, unsigned char *out, int se
   int base = 0;
   if (wfinish + 1 > W) base = wfinish + 1 - W;
   if (base > 0) --base;  // the last in-loop save ran with wstart(n-1) = base - 1 ... so start base-1 may remain
-  for (int s = base; s < base + 64; ++s) dust_evict(d, out, seg_off, s);  // every slot exactly once
+  if (d.p_valid)
+    for (int s2 = base; s2 < base + 64; ++s2) dust_evict(d, out, seg_off, s2);  // every slot exactly once
 }
 
 // Dustmasker::MaskWithBuffer + the in-place masking of CentrifugerClass.cpp:281-289.
 // `in` is the mate as uploaded, `out` the working copy the searches read.
-CFR_HD void dust_task(const unsigned char *in, int n, unsigned char *out, DustState &d) {
+template <int SW>
+CFR_HD void dust_task(const unsigned char *in, int n, unsigned char *out, DustStateT<SW> &d) {
   const int W = 64;
   if (n < 3) return;
+  ByteWindow bw;
   int i = 0;
-  while (i < n && dust_code(ld8(in + i)) == 4) ++i;
+  while (i < n && dust_code((unsigned char)bw.get(in + i)) == 4) ++i;
   while (i < n) {
     int n_count = 0, last_valid = i, j;
     for (j = i; j < n; ++j) {
-      if (dust_code(ld8(in + j)) == 4)
+      if (dust_code((unsigned char)bw.get(in + j)) == 4)
         ++n_count;
       else {
         if (n_count > W) break;

@@ -23,8 +23,16 @@ __device__ __forceinline__ void flush_counts(const OpCount &oc, DevCounters *c) 
   }
 }
 
-__global__ void __launch_bounds__(128) k_dust(const __grid_constant__ ChunkDev B) {
-  DustState d;
+// SDUST: one mate per thread.  The data-dependent triplet counters and the window
+// ring live in shared memory, one bank column per thread (80 words x 128 threads
+// = 40 KiB per block), so their updates are conflict-free single wavefronts.
+enum { CFR_DUST_THREADS = 128, CFR_DUST_SMEM = 80 * CFR_DUST_THREADS * 4 };
+__global__ void __launch_bounds__(CFR_DUST_THREADS) k_dust(const __grid_constant__ ChunkDev B) {
+  extern __shared__ u32 dust_sm[];
+  DustStateT<CFR_DUST_THREADS> d;
+  d.cw.base = reinterpret_cast<unsigned char *>(&dust_sm[threadIdx.x]);
+  d.cv.base = reinterpret_cast<unsigned char *>(&dust_sm[32 * CFR_DUST_THREADS + threadIdx.x]);
+  d.win.base = reinterpret_cast<unsigned char *>(&dust_sm[64 * CFR_DUST_THREADS + threadIdx.x]);
   const u64 ntask = B.n_reads * (u64)B.mates;
   const u64 stride = (u64)gridDim.x * blockDim.x;
   for (u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x; t < ntask; t += stride) dust_stage(B, t, d);
@@ -35,9 +43,11 @@ __global__ void __launch_bounds__(128) k_search(const __grid_constant__ DevIndex
                                                 const __grid_constant__ ChunkDev B) {
   OpCount oc{};
   const u64 ntask = B.n_reads * (u64)(2 * B.mates);
-  const u64 stride = (u64)gridDim.x * blockDim.x;
-  for (u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x; t < ntask; t += stride)
+  const u64 stride = ((u64)gridDim.x * blockDim.x) / Bwt::LANES;
+  // Bwt::LANES adjacent lanes share one task (1 = one strand per thread)
+  for (u64 t = ((u64)blockIdx.x * blockDim.x + threadIdx.x) / Bwt::LANES; t < ntask; t += stride)
     search_stage<Bwt>(ix, P, B, t, oc);
+  if (!Bwt::leader()) oc = OpCount{};
   flush_counts(oc, B.counters + CFR_STAGE_SEARCH);
 }
 
@@ -80,8 +90,10 @@ __global__ void __launch_bounds__(128) k_locate(const __grid_constant__ DevIndex
   OpCount oc{};
   u64 used = *B.arena_used;
   if (used > B.arena_cap) used = B.arena_cap;
-  const u64 stride = (u64)gridDim.x * blockDim.x;
-  for (u64 s = (u64)blockIdx.x * blockDim.x + threadIdx.x; s < used; s += stride) locate_stage<Bwt>(ix, B, s, oc);
+  const u64 stride = ((u64)gridDim.x * blockDim.x) / Bwt::LANES;
+  for (u64 s = ((u64)blockIdx.x * blockDim.x + threadIdx.x) / Bwt::LANES; s < used; s += stride)
+    locate_stage<Bwt>(ix, B, s, oc);
+  if (!Bwt::leader()) oc = OpCount{};
   flush_counts(oc, B.counters + CFR_STAGE_LOCATE);
 }
 

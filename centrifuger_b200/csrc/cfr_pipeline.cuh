@@ -52,7 +52,8 @@ struct ChunkDev {
 CFR_HD u64 chunk_read_id(const ChunkDev &B, u64 t) { return B.read_list ? (u64)B.read_list[t] : t; }
 
 // ------------------------------------------------------------------ dust
-CFR_HD void dust_stage(const ChunkDev &B, u64 task, DustState &d) {
+template <int SW>
+CFR_HD void dust_stage(const ChunkDev &B, u64 task, DustStateT<SW> &d) {
   const u64 read = task / (u64)B.mates;
   const int mate = (int)(task % (u64)B.mates);
   const u64 base = B.off[mate][read] - B.off_bias[mate];
@@ -71,8 +72,9 @@ CFR_HD void search_stage(const DevIndex &ix, const DevParams &P, const ChunkDev 
   const int mate = w >> 1;
   const u64 base = B.off[mate][read] - B.off_bias[mate];
   const int len = (int)(B.off[mate][read + 1] - B.off[mate][read]);
-  StrandSeq s{B.seq + base, len, (w & 1) ? 0 : 1};
-  B.strand_nhits[task] = get_hits_from_read<Bwt>(ix, s, P.min_hit_len, B.strand_hits + task * (u64)B.cap_h, B.cap_h, oc);
+  StrandSeq s{B.seq + base, len, (w & 1) ? 0 : 1, ByteWindow()};
+  const int nh = get_hits_from_read<Bwt>(ix, s, P.min_hit_len, B.strand_hits + task * (u64)B.cap_h, B.cap_h, oc);
+  if (Bwt::leader()) B.strand_nhits[task] = nh;
 }
 
 // ------------------------------------------------------------------ select
@@ -167,7 +169,8 @@ template <class Bwt>
 CFR_HD void locate_stage(const DevIndex &ix, const ChunkDev &B, u64 slot, OpCount &oc) {
   const u64 row = B.rows[slot];
   if (row == CFR_ROW_SENTINEL) return;
-  B.seq_ids[slot] = (u32)locate_row<Bwt>(ix, row, oc);
+  const u32 id = (u32)locate_row<Bwt>(ix, row, oc);
+  if (Bwt::leader()) B.seq_ids[slot] = id;
 }
 
 // ------------------------------------------------------------------ score
