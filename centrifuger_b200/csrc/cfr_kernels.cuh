@@ -45,8 +45,7 @@ __global__ void __launch_bounds__(128) k_search(const __grid_constant__ DevIndex
   const u64 ntask = B.n_reads * (u64)(2 * B.mates);
   const u64 stride = ((u64)gridDim.x * blockDim.x) / Bwt::LANES;
   // Bwt::LANES adjacent lanes share one task (1 = one strand per thread)
-  for (u64 t = ((u64)blockIdx.x * blockDim.x + threadIdx.x) / Bwt::LANES; t < ntask; t += stride)
-    search_stage<Bwt>(ix, P, B, t, oc);
+  search_tasks<Bwt>(ix, P, B, ((u64)blockIdx.x * blockDim.x + threadIdx.x) / Bwt::LANES, stride, ntask, oc);
   if (!Bwt::leader()) oc = OpCount{};
   flush_counts(oc, B.counters + CFR_STAGE_SEARCH);
 }
@@ -91,8 +90,7 @@ __global__ void __launch_bounds__(128) k_locate(const __grid_constant__ DevIndex
   u64 used = *B.arena_used;
   if (used > B.arena_cap) used = B.arena_cap;
   const u64 stride = ((u64)gridDim.x * blockDim.x) / Bwt::LANES;
-  for (u64 s = ((u64)blockIdx.x * blockDim.x + threadIdx.x) / Bwt::LANES; s < used; s += stride)
-    locate_stage<Bwt>(ix, B, s, oc);
+  locate_rows<Bwt>(ix, B, ((u64)blockIdx.x * blockDim.x + threadIdx.x) / Bwt::LANES, stride, used, oc);
   if (!Bwt::leader()) oc = OpCount{};
   flush_counts(oc, B.counters + CFR_STAGE_LOCATE);
 }

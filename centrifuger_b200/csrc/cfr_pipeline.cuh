@@ -63,18 +63,125 @@ CFR_HD void dust_stage(const ChunkDev &B, u64 task, DustStateT<SW> &d) {
 
 // ------------------------------------------------------------------ search
 // task = read * (2*mates) + mate*2 + s, s = 1: the mate as read (strandHits[1]),
-// s = 0: its reverse complement (strandHits[0])
+// s = 0: its reverse complement (strandHits[0]).
+//
+// GetHitsFromRead + BackwardSearch (Classifier.hpp:274-293, FMIndex.hpp:388-422,
+// 487-510) flattened into ONE loop: every iteration a lane either starts a search
+// (packs the lookup-table key of the last W bases), extends its range by one base,
+// closes a search (records the hit, skips the mismatching base) or picks up its
+// next task.  The nested-loop form leaves most lanes of a warp idle while the
+// longest inner loop finishes; the flat form keeps them all on the extend step.
+enum { CFR_PH_FETCH = 0, CFR_PH_INIT = 1, CFR_PH_EXTEND = 2, CFR_PH_FINISH = 3 };
+
 template <class Bwt>
-CFR_HD void search_stage(const DevIndex &ix, const DevParams &P, const ChunkDev &B, u64 task, OpCount &oc) {
-  const int S = 2 * B.mates;
-  const u64 read = task / (u64)S;
-  const int w = (int)(task % (u64)S);
-  const int mate = w >> 1;
-  const u64 base = B.off[mate][read] - B.off_bias[mate];
-  const int len = (int)(B.off[mate][read + 1] - B.off[mate][read]);
-  StrandSeq s{B.seq + base, len, (w & 1) ? 0 : 1, ByteWindow()};
-  const int nh = get_hits_from_read<Bwt>(ix, s, P.min_hit_len, B.strand_hits + task * (u64)B.cap_h, B.cap_h, oc);
-  if (Bwt::leader()) B.strand_nhits[task] = nh;
+CFR_HD void search_tasks(const DevIndex &ix, const DevParams &P, const ChunkDev &B, u64 t, const u64 stride,
+                         const u64 ntask, OpCount &oc) {
+  const int W = ix.pre_width, mhl = P.min_hit_len, S = 2 * B.mates;
+  StrandSeq s{nullptr, 0, 0, ByteWindow()};
+  Hit *out = nullptr;
+  u64 cur = 0, sp = 0, ep = 0;
+  int nh = 0, remaining = 0, l = 0;
+  int phase = CFR_PH_FETCH;
+  for (;;) {
+    if (phase == CFR_PH_FETCH) {
+      if (t >= ntask) break;
+      cur = t;
+      t += stride;
+      const u64 read = cur / (u64)S;
+      const int w = (int)(cur % (u64)S);
+      const int mate = w >> 1;
+      const u64 base = B.off[mate][read] - B.off_bias[mate];
+      s.r = B.seq + base;
+      s.len = (int)(B.off[mate][read + 1] - B.off[mate][read]);
+      s.rc = (w & 1) ? 0 : 1;
+      s.win = ByteWindow();
+      out = B.strand_hits + cur * (u64)B.cap_h;
+      nh = 0;
+      remaining = s.len;
+      sp = ep = 0;
+      phase = remaining >= mhl ? CFR_PH_INIT : CFR_PH_FINISH;
+    }
+    bool search_done = false;
+    if (phase == CFR_PH_INIT) {  // FMIndex::BackwardSearch up to the initial range
+      if (remaining < W) {
+        l = 0;
+        search_done = true;
+      } else {
+        ++oc.search;
+        if (W > 0) {
+          u64 key = 0;
+          int i = 0;
+          bool bad = false;
+          for (; i < W; ++i) {
+            const int c = s(remaining - 1 - i);
+            if (c > 3) {
+              bad = true;
+              break;
+            }
+            key = (key << 2) | (u64)c;
+          }
+          if (bad) {
+            sp = 1;
+            ep = 0;
+            l = i;
+            search_done = true;
+          } else {
+            const u64x2 e = ld128(ix.lookup + key);
+            if (e.y == 0) {
+              sp = 1;
+              ep = 0;
+              l = W - 1;
+              search_done = true;
+            } else {
+              sp = e.x;
+              ep = e.x + e.y - 1;
+              l = W;
+              phase = CFR_PH_EXTEND;
+            }
+          }
+        } else {
+          sp = 0;
+          ep = ix.n - 1;
+          l = 0;
+          phase = CFR_PH_EXTEND;
+        }
+      }
+    }
+    if (phase == CFR_PH_EXTEND && !search_done) {  // one FMIndex::BackwardExtend
+      bool adv = false;
+      if (l < remaining) {
+        const int c = s(remaining - 1 - l);
+        if (c <= 3) {
+          u64 nsp, nep;
+          Bwt::extend(ix, c, sp, ep, nsp, nep, oc);
+          if (!(nsp > nep || nep > ix.n)) {
+            sp = nsp;
+            ep = nep;
+            ++l;
+            adv = l < remaining;
+          }
+        }
+      }
+      if (!adv) search_done = true;
+    }
+    if (search_done) {  // back in GetHitsFromRead
+      if (l >= mhl && sp <= ep && nh < B.cap_h) {
+        if (Bwt::leader()) {
+          out[nh].sp = sp;
+          out[nh].ep = ep;
+          out[nh].l = l;
+          out[nh].offset = s.len - remaining;
+        }
+        ++nh;
+      }
+      remaining -= (l + 1);
+      phase = remaining >= mhl ? CFR_PH_INIT : CFR_PH_FINISH;
+    }
+    if (phase == CFR_PH_FINISH) {
+      if (Bwt::leader()) B.strand_nhits[cur] = nh;
+      phase = CFR_PH_FETCH;
+    }
+  }
 }
 
 // ------------------------------------------------------------------ select
@@ -165,12 +272,33 @@ CFR_HD void select_write_rows(const DevParams &P, const ChunkDev &B, u64 read, u
 }
 
 // ------------------------------------------------------------------ locate
+// FMIndex::BackwardToSampledSA for the arena rows slot, slot+stride, ...  Flat
+// loop as above: a lane whose walk ends picks up its next row at once instead of
+// waiting for the longest walk (geometric lengths) in its warp.
 template <class Bwt>
-CFR_HD void locate_stage(const DevIndex &ix, const ChunkDev &B, u64 slot, OpCount &oc) {
-  const u64 row = B.rows[slot];
-  if (row == CFR_ROW_SENTINEL) return;
-  const u32 id = (u32)locate_row<Bwt>(ix, row, oc);
-  if (Bwt::leader()) B.seq_ids[slot] = id;
+CFR_HD void locate_rows(const DevIndex &ix, const ChunkDev &B, u64 slot, const u64 stride, const u64 used,
+                        OpCount &oc) {
+  u64 cur = 0, i = 0;
+  bool have = false;
+  for (;;) {
+    if (!have) {
+      if (slot >= used) break;
+      cur = slot;
+      slot += stride;
+      i = B.rows[cur];
+      if (i == CFR_ROW_SENTINEL) continue;
+      have = true;
+    }
+    u64 sa;
+    if (get_sampled_sa(ix, i, sa)) {
+      if (Bwt::leader()) B.seq_ids[cur] = (u32)sa;
+      ++oc.locate;
+      have = false;
+    } else {
+      i = Bwt::lf(ix, i, oc);
+      ++oc.lf;
+    }
+  }
 }
 
 // ------------------------------------------------------------------ score

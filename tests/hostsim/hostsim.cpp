@@ -234,9 +234,10 @@ int hostsim_classify(void *hh, int dust, uint64_t arena_rows, const cfr_read_bat
   static DustState ds;
   if (dust)
     for (u64 t = 0; t < n * mates; ++t) dust_stage(B, t, ds);
-  for (u64 t = 0; t < n * S; ++t) {
-    if (h->layout == 2) search_stage<BwtOccLine>(ix, P, B, t, oc);
-    else search_stage<BwtRunBlock>(ix, P, B, t, oc);
+  // several interleaved "lanes" (stride 3) so the task-fetch path of the flat loop is exercised
+  for (u64 lane = 0; lane < 3; ++lane) {
+    if (h->layout == 2) search_tasks<BwtOccLine>(ix, P, B, lane, 3, n * S, oc);
+    else search_tasks<BwtRunBlock>(ix, P, B, lane, 3, n * S, oc);
   }
   B.read_list = nullptr;
   B.n_list = n;
@@ -261,9 +262,9 @@ int hostsim_classify(void *hh, int dust, uint64_t arena_rows, const cfr_read_bat
       if (!fits) deferred[n_deferred++] = (u32)read;
     }
     const u64 used = std::min(arena_used, B.arena_cap);
-    for (u64 s = 0; s < used; ++s) {
-      if (h->layout == 2) locate_stage<BwtOccLine>(ix, B, s, oc);
-      else locate_stage<BwtRunBlock>(ix, B, s, oc);
+    for (u64 lane = 0; lane < 3; ++lane) {
+      if (h->layout == 2) locate_rows<BwtOccLine>(ix, B, lane, 3, used, oc);
+      else locate_rows<BwtRunBlock>(ix, B, lane, 3, used, oc);
     }
     for (u64 t = 0; t < B.n_list; ++t) {
       const u64 read = chunk_read_id(B, t);

@@ -33,6 +33,9 @@ DATASETS = {
                   variants={"idx": []}, se=(20000, 100), pe=(20000, 150), edge=True),
     "c2": dict(genomes=dict(species=10, strains=5, length=2000000, conserved=0),
                variants={"idx": []}, se=None, pe=None, edge=False),
+    # the largest index whose files fit the 512 MiB gpurun snapshot: its occ lines (350 MB) do not fit L2
+    "m700": dict(genomes=dict(species=35, strains=5, length=4000000, conserved=0),
+                 variants={"idx": []}, se=None, pe=None, edge=False),
     "c3": dict(genomes=dict(species=100, strains=5, length=4000000, conserved=0),
                variants={"idx": []}, se=None, pe=None, edge=False),
 }
