@@ -64,11 +64,11 @@ struct cfr_device_batch {
   u64 seq_bytes = 0, total_bases = 0;
   u64 off_bias[2] = {0, 0};
   u64 arena_cap = 0;
-  DevBuf seq_raw, seq, off, strand_hits, strand_nhits, fhits, work, rows, seq_ids, rec0, rec1, best, tmp,
+  DevBuf seq_raw, codes, mask_raw, mask, off, strand_hits, strand_nhits, fhits, work, rows, seq_ids, rec0, rec1, best, tmp,
       results, out_ids, deferred, scalars;  // scalars: {u64 arena_used, u32 n_deferred, pad}
   bool classified = false;
   void release() {
-    DevBuf *all[] = {&seq_raw, &seq, &off, &strand_hits, &strand_nhits, &fhits, &work, &rows, &seq_ids,
+    DevBuf *all[] = {&seq_raw, &codes, &mask_raw, &mask, &off, &strand_hits, &strand_nhits, &fhits, &work, &rows, &seq_ids,
                      &rec0, &rec1, &best, &tmp, &results, &out_ids, &deferred, &scalars};
     for (DevBuf *b : all) b->release();
   }
@@ -284,7 +284,7 @@ int upload_chunk(cfr_handle *h, const cfr_read_batch *in, u64 r0, u64 r1, cfr_de
   const u64 s2 = mates == 2 ? in->off2[r0] : 0, e2 = mates == 2 ? in->off2[r1] : 0;
   if (e1 < s1 || e2 < s2) return fail(CFR_ERR_ARG, "read offsets are not ascending");
   const u64 len1 = e1 - s1, len2 = e2 - s2;
-  const u64 pos2 = (len1 + 15) & ~15ull;
+  const u64 pos2 = (len1 + 31) & ~31ull;
   b->seq_bytes = pos2 + len2;
   b->total_bases = len1 + len2;
   b->off_bias[0] = s1;
@@ -304,8 +304,11 @@ int upload_chunk(cfr_handle *h, const cfr_read_batch *in, u64 r0, u64 r1, cfr_de
   b->cap_h = std::max(1, max_hits_for_len(max_len, h->P.min_hit_len));
   const u64 S = 2 * (u64)mates;
   int st;
+  const u64 n_words = b->seq_bytes / 32 + 2;
   if ((st = b->seq_raw.ensure(b->seq_bytes + 64))) return st;
-  if ((st = b->seq.ensure(b->seq_bytes + 64))) return st;
+  if ((st = b->codes.ensure(n_words * 8))) return st;
+  if ((st = b->mask_raw.ensure(n_words * 4))) return st;
+  if ((st = b->mask.ensure(n_words * 4))) return st;
   if ((st = b->off.ensure((n + 1) * 8 * 2))) return st;
   if ((st = b->strand_hits.ensure(n * S * b->cap_h * sizeof(Hit)))) return st;
   if ((st = b->strand_nhits.ensure(n * S * sizeof(int)))) return st;
@@ -338,7 +341,11 @@ void fill_chunk(cfr_handle *h, cfr_device_batch *b, ChunkDev &B) {
   B.mates = b->mates;
   B.cap_h = b->cap_h;
   B.seq_raw = (const unsigned char *)b->seq_raw.p;
-  B.seq = h->params.dust ? (unsigned char *)b->seq.p : (unsigned char *)b->seq_raw.p;
+  B.n_words = b->seq_bytes / 32 + 2;
+  B.codes = (u64 *)b->codes.p;
+  B.mask_raw = (u32 *)b->mask_raw.p;
+  B.mask = h->params.dust ? (u32 *)b->mask.p : (u32 *)b->mask_raw.p;
+  B.dust_bits = nullptr;
   B.off[0] = (const u64 *)b->off.p;
   B.off[1] = (const u64 *)b->off.p + (b->n_reads + 1);
   B.off_bias[0] = b->off_bias[0];
@@ -397,11 +404,12 @@ int run_first(cfr_handle *h, cfr_device_batch *b, cudaStream_t s) {
   ChunkDev B;
   fill_chunk(h, b, B);
   if (b->n_reads == 0) return CFR_OK;
+  {
+    StageScope sc(h, s, CFR_STAGE_OTHER);
+    k_encode<<<grid_for(h, B.n_words, 256, 8), 256, 0, s>>>(B, b->seq_bytes);
+    ++h->launches;
+  }
   if (h->params.dust) {
-    {
-      StageScope sc(h, s, CFR_STAGE_OTHER);
-      CUDA_TRY(cudaMemcpyAsync(b->seq.p, b->seq_raw.p, b->seq_bytes, cudaMemcpyDeviceToDevice, s));
-    }
     StageScope sc(h, s, CFR_STAGE_DUST);
     k_dust<<<grid_for(h, B.n_reads * B.mates, CFR_DUST_THREADS, 5), CFR_DUST_THREADS, CFR_DUST_SMEM, s>>>(B);
     ++h->launches;
@@ -846,24 +854,34 @@ int cfr_debug_dust(cfr_handle *h, const cfr_read_batch *in, char *masked1, char 
   CUDA_TRY(cudaSetDevice(h->device));
   cfr_device_batch b;
   int st = upload_chunk(h, in, 0, in->n_reads, &b, h->stream);
+  DevBuf dbits, outb;
+  if (!st) st = dbits.ensure((b.seq_bytes / 32 + 2) * 4);
+  if (!st) st = outb.ensure(b.seq_bytes + 64);
   if (st) {
     b.release();
+    dbits.release();
+    outb.release();
     return st;
   }
   ChunkDev B;
   fill_chunk(h, &b, B);
-  B.seq = (unsigned char *)b.seq.p;
+  B.mask = (u32 *)b.mask.p;
+  B.dust_bits = (u32 *)dbits.p;
   const u64 len1 = in->off1[in->n_reads] - in->off1[0];
   const u64 len2 = in->seq2 ? in->off2[in->n_reads] - in->off2[0] : 0;
-  cudaMemcpyAsync(b.seq.p, b.seq_raw.p, b.seq_bytes, cudaMemcpyDeviceToDevice, h->stream);
-  if (in->n_reads) k_dust<<<grid_for(h, B.n_reads * B.mates, CFR_DUST_THREADS, 5), CFR_DUST_THREADS, CFR_DUST_SMEM, h->stream>>>(B);
-  ++h->launches;
+  k_encode<<<grid_for(h, B.n_words, 256, 8), 256, 0, h->stream>>>(B, b.seq_bytes);
+  if (in->n_reads)
+    k_dust<<<grid_for(h, B.n_reads * B.mates, CFR_DUST_THREADS, 5), CFR_DUST_THREADS, CFR_DUST_SMEM, h->stream>>>(B);
+  k_apply_dust<<<grid_for(h, b.seq_bytes, 256, 8), 256, 0, h->stream>>>(B, (unsigned char *)outb.p, b.seq_bytes);
+  h->launches += 3;
   cudaError_t e = cudaGetLastError();
-  if (e == cudaSuccess) e = cudaMemcpyAsync(masked1, b.seq.p, len1, cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess && len1) e = cudaMemcpyAsync(masked1, outb.p, len1, cudaMemcpyDeviceToHost, h->stream);
   if (e == cudaSuccess && masked2 && len2)
-    e = cudaMemcpyAsync(masked2, (char *)b.seq.p + ((len1 + 15) & ~15ull), len2, cudaMemcpyDeviceToHost, h->stream);
+    e = cudaMemcpyAsync(masked2, (char *)outb.p + ((len1 + 31) & ~31ull), len2, cudaMemcpyDeviceToHost, h->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
   b.release();
+  dbits.release();
+  outb.release();
   if (e != cudaSuccess) return fail(CFR_ERR_CUDA, cudaGetErrorString(e));
   return CFR_OK;
 }

@@ -14,7 +14,7 @@
 //   BackwardExtend             FMIndex.hpp:364-386          -> Bwt::extend / Bwt::lf
 //   BackwardSearch             FMIndex.hpp:388-422,487-510  -> backward_search
 //   GetSampledSA / locate      FMIndex.hpp:203-231,514-524  -> locate_row
-//   GetHitsFromRead            Classifier.hpp:274-293       -> get_hits_from_read
+//   GetHitsFromRead            Classifier.hpp:274-293       -> search_tasks (cfr_pipeline.cuh)
 //   AdjustHitBoundary...       Classifier.hpp:303-401       -> adjust_hit_boundary
 //   SearchForwardAndReverse    Classifier.hpp:509-583       -> select_task
 //   GetClassificationFromHits  Classifier.hpp:585-843       -> select_task (row plan) + score_task
@@ -82,37 +82,119 @@ CFR_HD int base_code(unsigned char c) {
   return c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : 4;
 }
 
-// Sequential byte reader with a 16-byte register window: one 128-bit load per
-// 16 bases instead of one byte load per base (read buffers are padded so the
-// aligned block around any valid byte is readable).
-struct ByteWindow {
-  u64 w0 = 0, w1 = 0;
-  unsigned long long blk = ~0ull;
-  CFR_HD unsigned get(const unsigned char *p) {
-    const unsigned long long a = (unsigned long long)p;
-    const unsigned long long b = a >> 4;
-    if (b != blk) {
-      const u64x2 v = ld128(reinterpret_cast<const u64x2 *>(a & ~15ull));
-      w0 = v.x;
-      w1 = v.y;
-      blk = b;
-    }
-    const int k = (int)(a & 15);
-    return (unsigned)(((k & 8) ? w1 : w0) >> ((k & 7) * 8)) & 0xffu;
+// ---------------------------------------------------------------------------
+// Reads in HBM: 2-bit codes + an "N" bit per base
+// ---------------------------------------------------------------------------
+// The uploaded bytes are re-coded once per batch (k_encode): base q of the batch
+// buffer lives in bits [2(q&31), 2(q&31)+2) of codes[q>>5] and in bit (q&31) of
+// nmask[q>>5].  Any byte outside "ACGT" (lower case, IUPAC, N ...) sets the N bit:
+// on this path such bytes only ever stop a match (FMIndex.hpp:396,500), complement
+// to 'N' (Classifier.hpp:846-856) and form DUST's fifth symbol (Dustmasker.hpp:
+// 298-302), so the recoding loses nothing.  DUST masking = setting N bits.
+
+CFR_HD u32 brev32(u32 x) {
+#if defined(__CUDA_ARCH__)
+  return __brev(x);
+#else
+  x = ((x >> 1) & 0x55555555u) | ((x & 0x55555555u) << 1);
+  x = ((x >> 2) & 0x33333333u) | ((x & 0x33333333u) << 2);
+  x = ((x >> 4) & 0x0f0f0f0fu) | ((x & 0x0f0f0f0fu) << 4);
+  x = ((x >> 8) & 0x00ff00ffu) | ((x & 0x00ff00ffu) << 8);
+  return (x >> 16) | (x << 16);
+#endif
+}
+
+CFR_HD int clz32(u32 x) {
+#if defined(__CUDA_ARCH__)
+  return __clz((int)x);
+#else
+  return x ? __builtin_clz(x) : 32;
+#endif
+}
+
+CFR_HD int ctz32(u32 x) {
+#if defined(__CUDA_ARCH__)
+  return __ffs((int)x) - 1;
+#else
+  return x ? __builtin_ctz(x) : -1;
+#endif
+}
+
+// 32 bases -> one code word + one N-mask word (the body of k_encode)
+CFR_HD void encode_bases(const unsigned char *b, int n, u64 &codes, u32 &nmask) {
+  codes = 0;
+  nmask = 0;
+  for (int i = 0; i < n; ++i) {
+    const int c = base_code(b[i]);
+    if (c > 3) nmask |= 1u << i; else codes |= (u64)c << (2 * i);
   }
-};
+}
+
+// `cnt` (<= 16) consecutive bases starting at batch position q: their 2-bit codes
+// (little endian) and N bits
+CFR_HD void packed_field(const u64 *codes, const u32 *nmask, u64 q, int cnt, u32 &field, u32 &nbits) {
+  const u64 wi = q >> 5;
+  const int sh = (int)(q & 31);
+  u64 c = ld64(codes + wi) >> (2 * sh);
+  u32 m = ld32(nmask + wi) >> sh;
+  if (sh + cnt > 32) {
+    c |= ld64(codes + wi + 1) << (64 - 2 * sh);
+    m |= ld32(nmask + wi + 1) << (32 - sh);
+  }
+  field = (u32)c & (cnt >= 16 ? 0xffffffffu : ((1u << (2 * cnt)) - 1u));
+  nbits = m & ((1u << cnt) - 1u);
+}
 
 // One strand of one read as the backward search sees it.  rc strands are never
 // materialised: rc[p] = comp(r[len-1-p]) (Classifier.hpp:99-111,846-856).
 struct StrandSeq {
-  const unsigned char *r;  // the mate as uploaded (after DUST)
+  const u64 *codes;
+  const u32 *nmask;
+  u64 base;  // batch position of the mate's first base
   int len;
   int rc;
-  ByteWindow win;
+  u64 cw = 0;
+  u32 mw = 0;
+  u64 widx = ~0ull;
+  // base p of the strand: 0..3, or 4 for anything that is not ACGT
   CFR_HD int operator()(int p) {
-    if (!rc) return base_code((unsigned char)win.get(r + p));
-    const int c = base_code((unsigned char)win.get(r + (len - 1 - p)));
-    return c > 3 ? 4 : 3 - c;
+    const u64 q = base + (u64)(rc ? len - 1 - p : p);
+    const u64 wi = q >> 5;
+    if (wi != widx) {
+      cw = ld64(codes + wi);
+      mw = ld32(nmask + wi);
+      widx = wi;
+    }
+    const int sh = (int)(q & 31);
+    if ((mw >> sh) & 1u) return 4;
+    const int c = (int)((cw >> (2 * sh)) & 3ull);
+    return rc ? 3 - c : c;
+  }
+  // GetBackwardSearchInitialRange's loop (FMIndex.hpp:394-403) over the last W
+  // bases of strand[0..m): true + the table key, or false + the number of valid
+  // characters seen before the first non-ACGT one.
+  CFR_HD bool init_key(int m, int W, u64 &key, int &nvalid) const {
+    u32 field, nbits;
+    if (!rc) {
+      packed_field(codes, nmask, base + (u64)(m - W), W, field, nbits);
+      if (nbits) {
+        nvalid = W - 1 - (31 - clz32(nbits));
+        return false;
+      }
+      key = field;  // s[m-1-i] lands in bits 2(W-1-i): exactly the little-endian field
+      return true;
+    }
+    packed_field(codes, nmask, base + (u64)(len - m), W, field, nbits);
+    if (nbits) {
+      nvalid = ctz32(nbits);
+      return false;
+    }
+    // reverse the order of the 2-bit groups and complement them
+    u32 r = brev32(field);
+    r = ((r >> 1) & 0x55555555u) | ((r & 0x55555555u) << 1);
+    r >>= (32 - 2 * W);
+    key = (u64)(r ^ (W >= 16 ? 0xffffffffu : ((1u << (2 * W)) - 1u)));
+    return true;
   }
 };
 
@@ -263,51 +345,45 @@ struct BwtRunBlock {
 // Layout 2: 64-byte occ lines (128 symbols + 4 absolute counters per line)
 // ---------------------------------------------------------------------------
 
-struct OccRegs {
-  u64 cnt[4];
-  u64 lo0, hi0, lo1, hi1;
+// occ-line helpers (one lane reads what it needs of a line: the counter of the
+// symbol and the two plane pairs)
+CFR_HD u64 occ_match(const u64x2 &p, int c) {  // p = {lo, hi} planes of 64 symbols
+  const u64 ml = (c & 1) ? ~0ull : 0ull, mh = (c & 2) ? ~0ull : 0ull;
+  return ~(p.x ^ ml) & ~(p.y ^ mh);
+}
+CFR_HD u64 occ_k0(int within) { return within >= 64 ? ~0ull : ((1ull << within) - 1ull); }
+CFR_HD u64 occ_k1(int within) { return within > 64 ? ((1ull << (within - 64)) - 1ull) : 0ull; }
+
+struct OccView {  // the parts of one line a rank of symbol c needs
+  u64 cnt;
+  u64 m0, m1;  // match masks of the two 64-symbol halves
+  u64x2 p0, p1;
 };
 
-CFR_HD OccRegs occ_load(const OccLine *p) {
-  OccRegs r;
-#if defined(__CUDA_ARCH__)
-  const ulonglong2 *q = reinterpret_cast<const ulonglong2 *>(p);
-  const ulonglong2 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2), d = __ldg(q + 3);
-  r.cnt[0] = a.x; r.cnt[1] = a.y; r.cnt[2] = b.x; r.cnt[3] = b.y;
-  r.lo0 = c.x; r.hi0 = c.y; r.lo1 = d.x; r.hi1 = d.y;
-#else
-  for (int i = 0; i < 4; ++i) r.cnt[i] = p->cnt[i];
-  r.lo0 = p->lo0; r.hi0 = p->hi0; r.lo1 = p->lo1; r.hi1 = p->hi1;
-#endif
-  return r;
+CFR_HD OccView occ_view(const OccLine *L, int c) {
+  OccView v;
+  v.cnt = ld64(reinterpret_cast<const u64 *>(L) + c);
+  v.p0 = ld128(reinterpret_cast<const u64x2 *>(L) + 2);
+  v.p1 = ld128(reinterpret_cast<const u64x2 *>(L) + 3);
+  v.m0 = occ_match(v.p0, c);
+  v.m1 = occ_match(v.p1, c);
+  return v;
 }
 
-// # of symbol c among the first `within` (0..127) symbols of the line, plus the line's base count
-CFR_HD u64 occ_count(const OccRegs &r, int c, int within) {
-  const u64 ml = (c & 1) ? ~0ull : 0ull, mh = (c & 2) ? ~0ull : 0ull;
-  const u64 m0 = ~(r.lo0 ^ ml) & ~(r.hi0 ^ mh);
-  const u64 m1 = ~(r.lo1 ^ ml) & ~(r.hi1 ^ mh);
-  u64 k0, k1;
-  if (within >= 64) {
-    k0 = ~0ull;
-    k1 = (1ull << (within - 64)) - 1ull;
-  } else {
-    k0 = (1ull << within) - 1ull;
-    k1 = 0ull;
-  }
-  return r.cnt[c] + (u64)popc64(m0 & k0) + (u64)popc64(m1 & k1);
+CFR_HD u64 occ_view_count(const OccView &v, int within) {
+  return v.cnt + (u64)popc64(v.m0 & occ_k0(within)) + (u64)popc64(v.m1 & occ_k1(within));
 }
 
-CFR_HD int occ_symbol(const OccRegs &r, int within) {
-  const u64 lo = within >= 64 ? r.lo1 : r.lo0, hi = within >= 64 ? r.hi1 : r.hi0;
+CFR_HD int occ_planes_symbol(const u64x2 &p0, const u64x2 &p1, int within) {
+  const u64 lo = within >= 64 ? p1.x : p0.x, hi = within >= 64 ? p1.y : p0.y;
   const int s = within & 63;
   return (int)(((lo >> s) & 1ull) | (((hi >> s) & 1ull) << 1));
 }
 
 // occ(c, x) = # of c in BWT[0..x), x in [0, n]
 CFR_HD u64 occ_rank_excl(const DevIndex &ix, int c, u64 x) {
-  const OccRegs r = occ_load(ix.occ + (x >> 7));
-  return occ_count(r, c, (int)(x & 127));
+  const OccView v = occ_view(ix.occ + (x >> 7), c);
+  return occ_view_count(v, (int)(x & 127));
 }
 
 struct BwtOccLine {
@@ -316,38 +392,44 @@ struct BwtOccLine {
     ++oc.extend;
     ++oc.rank;
     const u64 lsp = sp >> 7;
-    const OccRegs a = occ_load(ix.occ + lsp);
-    nsp = off + occ_count(a, c, (int)(sp & 127)) + last_chr_fix(ix, c, sp, 0);
+    const OccView a = occ_view(ix.occ + lsp, c);
+    nsp = off + occ_view_count(a, (int)(sp & 127)) + last_chr_fix(ix, c, sp, 0);
     if (sp != ep) {
       ++oc.rank;
       const u64 x = ep + 1, lx = x >> 7;
       if (lx == lsp) {
-        nep = off + occ_count(a, c, (int)(x & 127)) + last_chr_fix(ix, c, ep, 1) - 1;
+        nep = off + occ_view_count(a, (int)(x & 127)) + last_chr_fix(ix, c, ep, 1) - 1;
       } else {
-        const OccRegs e = occ_load(ix.occ + lx);
-        nep = off + occ_count(e, c, (int)(x & 127)) + last_chr_fix(ix, c, ep, 1) - 1;
+        const OccView e = occ_view(ix.occ + lx, c);
+        nep = off + occ_view_count(e, (int)(x & 127)) + last_chr_fix(ix, c, ep, 1) - 1;
       }
     } else {
       ++oc.access;
-      nep = nsp + ((occ_symbol(a, (int)(ep & 127)) == c) ? 0ull : ~0ull);
+      nep = nsp + ((occ_planes_symbol(a.p0, a.p1, (int)(ep & 127)) == c) ? 0ull : ~0ull);
     }
   }
   static CFR_HD u64 lf(const DevIndex &ix, u64 i, OpCount &oc) {
     ++oc.access;
     ++oc.rank;
-    const OccRegs a = occ_load(ix.occ + (i >> 7));
+    const OccLine *L = ix.occ + (i >> 7);
     const int w = (int)(i & 127);
-    const int c = occ_symbol(a, w);
+    const u64x2 p0 = ld128(reinterpret_cast<const u64x2 *>(L) + 2);
+    const u64x2 p1 = ld128(reinterpret_cast<const u64x2 *>(L) + 3);
+    const int c = occ_planes_symbol(p0, p1, w);
+    const u64 cnt = ld64(reinterpret_cast<const u64 *>(L) + c);
+    const u64 r = cnt + (u64)popc64(occ_match(p0, c) & occ_k0(w)) + (u64)popc64(occ_match(p1, c) & occ_k1(w));
     // inclusive rank at i = exclusive count at i, plus the symbol itself
-    return ix.C[c] + occ_count(a, c, w) + 1 + last_chr_fix(ix, c, i, 1) - 1;
+    return ix.C[c] + r + 1 + last_chr_fix(ix, c, i, 1) - 1;
   }
   static CFR_HD u64 rank(const DevIndex &ix, int c, u64 i, int inclusive) {
     if (!inclusive) return occ_rank_excl(ix, c, i);
     return occ_rank_excl(ix, c, i + 1);
   }
   static CFR_HD int access(const DevIndex &ix, u64 i) {
-    const OccRegs a = occ_load(ix.occ + (i >> 7));
-    return occ_symbol(a, (int)(i & 127));
+    const OccLine *L = ix.occ + (i >> 7);
+    const u64x2 p0 = ld128(reinterpret_cast<const u64x2 *>(L) + 2);
+    const u64x2 p1 = ld128(reinterpret_cast<const u64x2 *>(L) + 3);
+    return occ_planes_symbol(p0, p1, (int)(i & 127));
   }
   static CFR_HD bool leader() { return true; }
   enum { LANES = 1 };
@@ -431,7 +513,8 @@ struct BwtOccCoop4 {
 // FM-index search and locate
 // ---------------------------------------------------------------------------
 
-// FMIndex::BackwardSearch with GetBackwardSearchInitialRange inlined
+// FMIndex::BackwardSearch with GetBackwardSearchInitialRange inlined (nested-loop
+// form; the bulk search uses the flattened loop in cfr_pipeline.cuh)
 template <class Bwt>
 CFR_HD int backward_search(const DevIndex &ix, StrandSeq &s, int m, u64 &sp, u64 &ep, OpCount &oc) {
   const int W = ix.pre_width;
@@ -439,17 +522,14 @@ CFR_HD int backward_search(const DevIndex &ix, StrandSeq &s, int m, u64 &sp, u64
   ++oc.search;
   int l = 0;
   if (W > 0) {
-    u64 w = 0;
-    for (int i = 0; i < W; ++i) {
-      const int c = s(m - 1 - i);
-      if (c > 3) {
-        sp = 1;
-        ep = 0;
-        return i;
-      }
-      w = (w << 2) | (u64)c;
+    u64 key;
+    int nvalid;
+    if (!s.init_key(m, W, key, nvalid)) {
+      sp = 1;
+      ep = 0;
+      return nvalid;
     }
-    const u64x2 e = ld128(ix.lookup + w);
+    const u64x2 e = ld128(ix.lookup + key);
     if (e.y == 0) {
       sp = 1;
       ep = 0;
@@ -539,35 +619,14 @@ CFR_HD u64 hit_score(int l, int mhl) {
   return (u64)(long long)(l - 15) * (u64)(long long)(l - 15);
 }
 
-// Classifier::GetHitsFromRead; returns the number of hits written
-template <class Bwt>
-CFR_HD int get_hits_from_read(const DevIndex &ix, StrandSeq &s, int mhl, Hit *out, int cap, OpCount &oc) {
-  u64 sp = 0, ep = 0;
-  int n = 0;
-  int remaining = s.len;
-  while (remaining >= mhl) {
-    const int l = backward_search<Bwt>(ix, s, remaining, sp, ep, oc);
-    if (l >= mhl && sp <= ep && n < cap) {
-      if (Bwt::leader()) {
-        out[n].sp = sp;
-        out[n].ep = ep;
-        out[n].l = l;
-        out[n].offset = s.len - remaining;
-      }
-      ++n;
-    }
-    remaining -= (l + 1);
-  }
-  return n;
-}
-
 // Classifier::AdjustHitBoundaryFromStrandHits.  h1 = strandHits[1] (the mate as
 // read), h0 = strandHits[0] (its reverse complement).
 template <class Bwt>
-CFR_HD void adjust_hit_boundary(const DevIndex &ix, const unsigned char *r, int len, Hit *h0, int n0, Hit *h1,
-                                int n1, OpCount &oc) {
+CFR_HD void adjust_hit_boundary(const DevIndex &ix, StrandSeq fw, Hit *h0, int n0, Hit *h1, int n1, OpCount &oc) {
   if (!n0 || !n1) return;
-  StrandSeq fw{r, len, 0, ByteWindow()}, rc{r, len, 1, ByteWindow()};
+  const int len = fw.len;
+  StrandSeq rc = fw;
+  rc.rc = 1;
   u64 sp = 0, ep = 0;
   int j = n0 - 1;
   bool need_fix0 = false, need_fix1 = false;
@@ -1086,25 +1145,72 @@ struct DustState : DustStateT<1> {
   }
 };
 
-CFR_HD int dust_code(unsigned char c) { return base_code(c); }
+// DUST input: the mate's bases as uploaded (codes + original N bits)
+struct DustIn {
+  const u64 *codes;
+  const u32 *nmask;  // N bits before masking
+  u64 base;
+  u64 cw = 0;
+  u32 mw = 0;
+  u64 widx = ~0ull;
+  CFR_HD int operator()(int i) {  // 0..3, or 4 = the catch-all fifth symbol
+    const u64 q = base + (u64)i;
+    const u64 wi = q >> 5;
+    if (wi != widx) {
+      cw = ld64(codes + wi);
+      mw = ld32(nmask + wi);
+      widx = wi;
+    }
+    const int sh = (int)(q & 31);
+    if ((mw >> sh) & 1u) return 4;
+    return (int)((cw >> (2 * sh)) & 3ull);
+  }
+};
+
+// DUST output: N bits of the working mask (+ an optional copy of just the masked
+// intervals, used by the parity diagnostics).  Mask words are shared between
+// neighbouring reads, hence the atomics.
+struct DustOut {
+  u32 *mask;
+  u32 *dust_bits;  // may be nullptr
+  u64 base;
+  CFR_HD void set_range(int s, int e) const {  // positions s..e of the mate, inclusive
+    u64 q = base + (u64)s;
+    const u64 qe = base + (u64)e;
+    while (q <= qe) {
+      const u64 wi = q >> 5;
+      const int lo = (int)(q & 31);
+      const u64 wend = (wi << 5) + 31;
+      const int hi = (int)((qe < wend ? qe : wend) & 31);
+      const u32 bits = (hi == 31 ? 0xffffffffu : ((1u << (hi + 1)) - 1u)) & ~((1u << lo) - 1u);
+#if defined(__CUDA_ARCH__)
+      atomicOr(mask + wi, bits);
+      if (dust_bits) atomicOr(dust_bits + wi, bits);
+#else
+      mask[wi] |= bits;
+      if (dust_bits) dust_bits[wi] |= bits;
+#endif
+      q = wend + 1;
+    }
+  }
+};
 
 template <int SW>
 CFR_HD int dust_win_at(const DustStateT<SW> &d, int i) { return d.win[(d.head + i) & 63]; }
 
 // Dustmasker::SaveMaskedRegions for the single start that can leave the window
 template <int SW>
-CFR_HD void dust_evict(DustStateT<SW> &d, unsigned char *out, int seg_off, int start) {
+CFR_HD void dust_evict(DustStateT<SW> &d, const DustOut &out, int seg_off, int start) {
   const int slot = start & 63;
   if ((d.p_valid >> slot) & 1ull) {
-    const int e = start + d.p_len[slot];
-    for (int q = start; q <= e; ++q) out[seg_off + q] = 'N';
+    out.set_range(seg_off + start, seg_off + start + d.p_len[slot]);
     d.p_valid &= ~(1ull << slot);
   }
 }
 
-// SDust on S[0..n): masks into out[seg_off ...]
+// SDust on in[seg_off .. seg_off+n): masks into out
 template <int SW>
-CFR_HD void dust_sdust(const unsigned char *S, int n, unsigned char *out, int seg_off, DustStateT<SW> &d) {
+CFR_HD void dust_sdust(DustIn &in, int n, const DustOut &out, int seg_off, DustStateT<SW> &d) {
   const int W = 64, T = 20;
   if (n < 3) return;
   for (int i = 0; i < 128; i += 4) {
@@ -1114,14 +1220,13 @@ CFR_HD void dust_sdust(const unsigned char *S, int n, unsigned char *out, int se
   d.head = d.size = 0;
   d.rv = d.rw = d.lv = 0;
   d.p_valid = 0;
-  ByteWindow bw;
-  int c1 = dust_code((unsigned char)bw.get(S)), c2 = dust_code((unsigned char)bw.get(S + 1));
+  int c1 = in(seg_off), c2 = in(seg_off + 1);
   int wfinish, wstart = 0;
   for (wfinish = 2; wfinish < n; ++wfinish) {
     wstart = 0;
     if (wfinish + 1 > W) wstart = wfinish + 1 - W;
     if (wstart > 0) dust_evict(d, out, seg_off, wstart - 1);
-    const int c3 = dust_code((unsigned char)bw.get(S + wfinish));
+    const int c3 = in(seg_off + wfinish);
     const int t = c1 * 25 + c2 * 5 + c3;
     c1 = c2;
     c2 = c3;
@@ -1199,18 +1304,17 @@ CFR_HD void dust_sdust(const unsigned char *S, int n, unsigned char *out, int se
 }
 
 // Dustmasker::MaskWithBuffer + the in-place masking of CentrifugerClass.cpp:281-289.
-// `in` is the mate as uploaded, `out` the working copy the searches read.
+// `in` is the mate as uploaded, `out` the working N mask the searches read.
 template <int SW>
-CFR_HD void dust_task(const unsigned char *in, int n, unsigned char *out, DustStateT<SW> &d) {
+CFR_HD void dust_task(DustIn &in, int n, const DustOut &out, DustStateT<SW> &d) {
   const int W = 64;
   if (n < 3) return;
-  ByteWindow bw;
   int i = 0;
-  while (i < n && dust_code((unsigned char)bw.get(in + i)) == 4) ++i;
+  while (i < n && in(i) == 4) ++i;
   while (i < n) {
     int n_count = 0, last_valid = i, j;
     for (j = i; j < n; ++j) {
-      if (dust_code((unsigned char)bw.get(in + j)) == 4)
+      if (in(j) == 4)
         ++n_count;
       else {
         if (n_count > W) break;
@@ -1218,7 +1322,7 @@ CFR_HD void dust_task(const unsigned char *in, int n, unsigned char *out, DustSt
         n_count = 0;
       }
     }
-    if (last_valid > i) dust_sdust(in + i, last_valid - i + 1, out, i, d);
+    if (last_valid > i) dust_sdust(in, last_valid - i + 1, out, i, d);
     i = j;
   }
 }

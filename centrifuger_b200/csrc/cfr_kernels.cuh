@@ -23,6 +23,19 @@ __device__ __forceinline__ void flush_counts(const OpCount &oc, DevCounters *c) 
   }
 }
 
+// bytes -> 2-bit codes + N bits, one 32-base word per thread (coalesced 32-byte reads)
+__global__ void __launch_bounds__(256) k_encode(const __grid_constant__ ChunkDev B, const u64 total_bytes) {
+  const u64 stride = (u64)gridDim.x * blockDim.x;
+  for (u64 w = (u64)blockIdx.x * blockDim.x + threadIdx.x; w < B.n_words; w += stride) encode_stage(B, w, total_bytes);
+}
+
+// diagnostics: the uploaded bytes with the DUST intervals replaced by 'N'
+__global__ void k_apply_dust(const __grid_constant__ ChunkDev B, unsigned char *out, const u64 total_bytes) {
+  const u64 stride = (u64)gridDim.x * blockDim.x;
+  for (u64 q = (u64)blockIdx.x * blockDim.x + threadIdx.x; q < total_bytes; q += stride)
+    out[q] = ((B.dust_bits[q >> 5] >> (q & 31)) & 1u) ? (unsigned char)'N' : B.seq_raw[q];
+}
+
 // SDUST: one mate per thread.  The data-dependent triplet counters and the window
 // ring live in shared memory, one bank column per thread (80 words x 128 threads
 // = 40 KiB per block), so their updates are conflict-free single wavefronts.

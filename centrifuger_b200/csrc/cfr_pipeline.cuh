@@ -22,8 +22,12 @@ struct ChunkDev {
   u64 n_reads;
   int mates;  // 1 or 2
   int cap_h;  // hit slots per strand task
-  const unsigned char *seq_raw;  // bases as uploaded
-  unsigned char *seq;            // working copy the searches read (DUST-masked)
+  const unsigned char *seq_raw;  // bases as uploaded (input of encode_stage only)
+  u64 n_words;                   // 32-base words covering the batch buffer
+  u64 *codes;                    // 2-bit codes, 32 bases per word
+  u32 *mask_raw;                 // N bits as uploaded
+  u32 *mask;                     // N bits the searches see (= mask_raw | DUST intervals)
+  u32 *dust_bits;                // optional: just the DUST intervals (diagnostics)
   const u64 *off[2];             // per mate: n_reads + 1 offsets as given by the caller
   u64 off_bias[2];               // position in seq = off[m][i] - off_bias[m]
   Hit *strand_hits;              // [n_reads * 2*mates * cap_h]
@@ -51,6 +55,35 @@ struct ChunkDev {
 
 CFR_HD u64 chunk_read_id(const ChunkDev &B, u64 t) { return B.read_list ? (u64)B.read_list[t] : t; }
 
+// ------------------------------------------------------------------ encode
+// word w of the batch buffer: 32 uploaded bytes -> 2-bit codes + N bits
+CFR_HD void encode_stage(const ChunkDev &B, u64 w, u64 total_bytes) {
+  const u64 b0 = w * 32;
+  const int n = b0 + 32 <= total_bytes ? 32 : (b0 < total_bytes ? (int)(total_bytes - b0) : 0);
+  // two aligned 16-byte loads (the buffer is padded past total_bytes), then bytes from registers
+  const u64x2 v0 = ld128(reinterpret_cast<const u64x2 *>(B.seq_raw + b0));
+  const u64x2 v1 = ld128(reinterpret_cast<const u64x2 *>(B.seq_raw + b0) + 1);
+  const u64 q[4] = {v0.x, v0.y, v1.x, v1.y};
+  u64 codes = 0;
+  u32 nm = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int i = 0; i < 32; ++i) {
+    const int c = base_code((unsigned char)(q[i >> 3] >> ((i & 7) * 8)));
+    if (c > 3) nm |= 1u << i; else codes |= (u64)c << (2 * i);
+  }
+  if (n < 32) {  // padding reads as N
+    const u32 keep = n == 0 ? 0u : ((1u << n) - 1u);
+    nm |= ~keep;
+    codes &= n == 0 ? 0ull : ((1ull << (2 * n)) - 1ull);
+  }
+  B.codes[w] = codes;
+  B.mask_raw[w] = nm;
+  if (B.mask != B.mask_raw) B.mask[w] = nm;
+  if (B.dust_bits) B.dust_bits[w] = 0;
+}
+
 // ------------------------------------------------------------------ dust
 template <int SW>
 CFR_HD void dust_stage(const ChunkDev &B, u64 task, DustStateT<SW> &d) {
@@ -58,7 +91,9 @@ CFR_HD void dust_stage(const ChunkDev &B, u64 task, DustStateT<SW> &d) {
   const int mate = (int)(task % (u64)B.mates);
   const u64 base = B.off[mate][read] - B.off_bias[mate];
   const int len = (int)(B.off[mate][read + 1] - B.off[mate][read]);
-  dust_task(B.seq_raw + base, len, B.seq + base, d);
+  DustIn in{B.codes, B.mask_raw, base};
+  const DustOut out{B.mask, B.dust_bits, base};
+  dust_task(in, len, out, d);
 }
 
 // ------------------------------------------------------------------ search
@@ -77,7 +112,7 @@ template <class Bwt>
 CFR_HD void search_tasks(const DevIndex &ix, const DevParams &P, const ChunkDev &B, u64 t, const u64 stride,
                          const u64 ntask, OpCount &oc) {
   const int W = ix.pre_width, mhl = P.min_hit_len, S = 2 * B.mates;
-  StrandSeq s{nullptr, 0, 0, ByteWindow()};
+  StrandSeq s{B.codes, B.mask, 0, 0, 0};
   Hit *out = nullptr;
   u64 cur = 0, sp = 0, ep = 0;
   int nh = 0, remaining = 0, l = 0;
@@ -91,10 +126,10 @@ CFR_HD void search_tasks(const DevIndex &ix, const DevParams &P, const ChunkDev 
       const int w = (int)(cur % (u64)S);
       const int mate = w >> 1;
       const u64 base = B.off[mate][read] - B.off_bias[mate];
-      s.r = B.seq + base;
+      s.base = base;
       s.len = (int)(B.off[mate][read + 1] - B.off[mate][read]);
       s.rc = (w & 1) ? 0 : 1;
-      s.win = ByteWindow();
+      s.widx = ~0ull;
       out = B.strand_hits + cur * (u64)B.cap_h;
       nh = 0;
       remaining = s.len;
@@ -109,21 +144,12 @@ CFR_HD void search_tasks(const DevIndex &ix, const DevParams &P, const ChunkDev 
       } else {
         ++oc.search;
         if (W > 0) {
-          u64 key = 0;
-          int i = 0;
-          bool bad = false;
-          for (; i < W; ++i) {
-            const int c = s(remaining - 1 - i);
-            if (c > 3) {
-              bad = true;
-              break;
-            }
-            key = (key << 2) | (u64)c;
-          }
-          if (bad) {
+          u64 key;
+          int nvalid;
+          if (!s.init_key(remaining, W, key, nvalid)) {
             sp = 1;
             ep = 0;
-            l = i;
+            l = nvalid;
             search_done = true;
           } else {
             const u64x2 e = ld128(ix.lookup + key);
@@ -203,7 +229,7 @@ CFR_HD u32 select_plan(const DevIndex &ix, const DevParams &P, const ChunkDev &B
       h[m][s] = B.strand_hits + task * (u64)B.cap_h;
       n[m][s] = B.strand_nhits[task];
     }
-    adjust_hit_boundary<Bwt>(ix, B.seq + base, len, h[m][0], n[m][0], h[m][1], n[m][1], oc);
+    adjust_hit_boundary<Bwt>(ix, StrandSeq{B.codes, B.mask, base, len, 0}, h[m][0], n[m][0], h[m][1], n[m][1], oc);
   }
   B.results[read].query_length = qlen;
   // template strand k: mate-1 hits of strand k, then mate-2 hits of strand 1-k (Classifier.hpp:551-552)

@@ -161,7 +161,24 @@ uint64_t hostsim_locate(void *hh, uint64_t row) {
 void hostsim_dust(const char *in, int n, char *out) {
   static DustState d;
   memcpy(out, in, (size_t)n);
-  dust_task((const unsigned char *)in, n, (unsigned char *)out, d);
+  const u64 words = (u64)n / 32 + 2;
+  std::vector<unsigned char> raw((size_t)words * 32 + 32, 0);
+  memcpy(raw.data(), in, (size_t)n);
+  std::vector<u64> codes(words);
+  std::vector<u32> mraw(words), mwork(words), dbits(words, 0);
+  ChunkDev B;
+  memset(&B, 0, sizeof(B));
+  B.seq_raw = raw.data();
+  B.codes = codes.data();
+  B.mask_raw = mraw.data();
+  B.mask = mwork.data();
+  B.dust_bits = dbits.data();
+  for (u64 w = 0; w < words; ++w) encode_stage(B, w, (u64)n);
+  DustIn din{B.codes, B.mask_raw, 0};
+  const DustOut dout{B.mask, B.dust_bits, 0};
+  dust_task(din, n, dout, d);
+  for (int i = 0; i < n; ++i)
+    if ((dbits[i >> 5] >> (i & 31)) & 1u) out[i] = 'N';
 }
 
 // the whole pipeline for one batch; arena_rows small values exercise the deferral loop
@@ -175,10 +192,12 @@ int hostsim_classify(void *hh, int dust, uint64_t arena_rows, const cfr_read_bat
   const int S = 2 * mates;
   // pack both mates into one buffer
   const u64 len1 = in->off1[n], len2 = mates == 2 ? in->off2[n] : 0;
-  std::vector<unsigned char> raw(len1 + len2 + 16), work;
+  std::vector<unsigned char> raw(len1 + len2 + 64);
   memcpy(raw.data(), in->seq1, len1);
   if (mates == 2) memcpy(raw.data() + len1, in->seq2, len2);
-  work = raw;
+  const u64 n_words = (len1 + len2) / 32 + 2;
+  std::vector<u64> codes(n_words);
+  std::vector<u32> mask_raw(n_words), mask_work(n_words);
   std::vector<u64> off1(in->off1, in->off1 + n + 1), off2(n + 1, 0);
   if (mates == 2)
     for (u64 i = 0; i <= n; ++i) off2[i] = in->off2[i] + len1;
@@ -193,7 +212,10 @@ int hostsim_classify(void *hh, int dust, uint64_t arena_rows, const cfr_read_bat
   B.mates = mates;
   B.cap_h = std::max(1, max_hits_for_len(max_len, P.min_hit_len));
   B.seq_raw = raw.data();
-  B.seq = work.data();
+  B.n_words = n_words;
+  B.codes = codes.data();
+  B.mask_raw = mask_raw.data();
+  B.mask = dust ? mask_work.data() : mask_raw.data();
   B.off[0] = off1.data();
   B.off[1] = off2.data();
   std::vector<Hit> strand_hits(n * S * B.cap_h + 1);
@@ -232,6 +254,7 @@ int hostsim_classify(void *hh, int dust, uint64_t arena_rows, const cfr_read_bat
   B.n_deferred = &n_deferred;
   OpCount oc{};
   static DustState ds;
+  for (u64 w = 0; w < n_words; ++w) encode_stage(B, w, len1 + len2);
   if (dust)
     for (u64 t = 0; t < n * mates; ++t) dust_stage(B, t, ds);
   // several interleaved "lanes" (stride 3) so the task-fetch path of the flat loop is exercised

@@ -1,26 +1,24 @@
 #!/bin/bash
-# quick GPU iteration: parity tests then the bench in the variants named by $VARIANTS
+# quick GPU iteration: parity tests, then bench variants. usage: gpu_iter.sh "<workloads>" "<variants>"
 mkdir -p gpurun_out
+WL=${1:-"c2 m700"}
+VARS=${2:-"coop scalar"}
 ( time timeout 900 python -m pytest tests -m gpu -x -q ) > gpurun_out/pytest_gpu.log 2>&1
-tail -6 gpurun_out/pytest_gpu.log
-W=${WORKLOAD:-c2}
-timeout 600 python bench.py --workload $W --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_${W}_coop.json 2> gpurun_out/bench_${W}_coop.err
-python - <<PY
+tail -4 gpurun_out/pytest_gpu.log
+for W in $WL; do
+  for V in $VARS; do
+    if [ $V = scalar ]; then export CFR_B200_SCALAR_OCC=1; else unset CFR_B200_SCALAR_OCC; fi
+    EXTRA=""
+    if [ $V = rb ]; then EXTRA="--layout 1"; fi
+    timeout 600 python bench.py --workload $W --steps 5 --warmup 3 --no-cpu-baseline $EXTRA > gpurun_out/bench_${W}_${V}.json 2> gpurun_out/bench_${W}_${V}.err
+    python - <<PY
 import json
-for f in ["gpurun_out/bench_${W}_coop.json"]:
-    try:
-        d=json.loads(open(f).read().strip().splitlines()[-1])
-        print(f, "value %.3g e2e %.3g ms/step %.3f"%(d["value"], d["e2e"]["value"], d["ms_per_step"]), d["stage_ms_per_step"], "roofline", d["roofline"]["achieved"], d["clocks"])
-    except Exception as e:
-        print(f, "FAILED", e); print(open(f.replace(".json",".err")).read()[-2000:])
+f="gpurun_out/bench_${W}_${V}.json"
+try:
+    d=json.loads(open(f).read().strip().splitlines()[-1])
+    print("${W} ${V}: value %.4g e2e %.4g ms/step %.3f"%(d["value"], d["e2e"]["value"], d["ms_per_step"]), {k:round(v,3) for k,v in d["stage_ms_per_step"].items()}, "search GB/s %.0f"%d["roofline"]["achieved"], d["clocks"]["sm_mhz"], d["clocks"]["reasons"])
+except Exception as e:
+    print(f, "FAILED", e); print(open(f.replace(".json",".err")).read()[-1500:])
 PY
-CFR_B200_SCALAR_OCC=1 timeout 600 python bench.py --workload $W --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_${W}_scalar.json 2> gpurun_out/bench_${W}_scalar.err
-python - <<PY
-import json
-for f in ["gpurun_out/bench_${W}_scalar.json"]:
-    try:
-        d=json.loads(open(f).read().strip().splitlines()[-1])
-        print(f, "value %.3g e2e %.3g ms/step %.3f"%(d["value"], d["e2e"]["value"], d["ms_per_step"]), d["stage_ms_per_step"])
-    except Exception as e:
-        print(f, "FAILED", e); print(open(f.replace(".json",".err")).read()[-2000:])
-PY
+  done
+done
