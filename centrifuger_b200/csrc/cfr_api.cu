@@ -175,6 +175,7 @@ int upload_index(cfr_handle *h) {
   if ((st = upload_wt(h, f.plain, ix.plain))) return st;
   if ((st = upload_wt(h, f.run, ix.run))) return st;
   ix.sample_rate = f.sample_rate;
+  ix.sample_shift = (f.sample_rate & (f.sample_rate - 1)) == 0 ? __builtin_ctz((unsigned)f.sample_rate) : -1;
   ix.sa_bits = f.sa_bits;
   void *p;
   if ((st = dev_upload(h, f.sa_w, f.sa_words * 8, 16, &p))) return st;
@@ -184,6 +185,7 @@ int upload_index(cfr_handle *h) {
   ix.sel = (const u64x2 *)p;
   ix.sel_cnt = f.sel_cnt;
   ix.sel_filter_rate = f.sel_filter_rate;
+  ix.filter_shift = (f.sel_filter_rate & (f.sel_filter_rate - 1)) == 0 ? __builtin_ctz((unsigned)f.sel_filter_rate) : -1;
   ix.sel_filter = nullptr;
   if (f.sel_cnt > 0) {  // rebuilt at load exactly as FMIndex.hpp:163-176 does
     const u64 fbits = (f.n + (u64)f.sel_filter_rate - 1) / (u64)f.sel_filter_rate;

@@ -387,26 +387,26 @@ CFR_HD u64 occ_rank_excl(const DevIndex &ix, int c, u64 x) {
 }
 
 struct BwtOccLine {
+  // straight-line: both ranks and the symbol test are always computed, the range /
+  // single-row forms of FMIndex::BackwardExtend are selected at the end
   static CFR_HD void extend(const DevIndex &ix, int c, u64 sp, u64 ep, u64 &nsp, u64 &nep, OpCount &oc) {
     const u64 off = ix.C[c];
+    const u64 lsp = sp >> 7, x = ep + 1, lx = x >> 7;
+    const bool range = sp != ep;
     ++oc.extend;
     ++oc.rank;
-    const u64 lsp = sp >> 7;
+    oc.rank += range ? 1u : 0u;
+    oc.access += range ? 0u : 1u;
     const OccView a = occ_view(ix.occ + lsp, c);
-    nsp = off + occ_view_count(a, (int)(sp & 127)) + last_chr_fix(ix, c, sp, 0);
-    if (sp != ep) {
-      ++oc.rank;
-      const u64 x = ep + 1, lx = x >> 7;
-      if (lx == lsp) {
-        nep = off + occ_view_count(a, (int)(x & 127)) + last_chr_fix(ix, c, ep, 1) - 1;
-      } else {
-        const OccView e = occ_view(ix.occ + lx, c);
-        nep = off + occ_view_count(e, (int)(x & 127)) + last_chr_fix(ix, c, ep, 1) - 1;
-      }
-    } else {
-      ++oc.access;
-      nep = nsp + ((occ_planes_symbol(a.p0, a.p1, (int)(ep & 127)) == c) ? 0ull : ~0ull);
-    }
+    OccView e = a;
+    if (lx != lsp) e = occ_view(ix.occ + lx, c);
+    const u64 rsp = occ_view_count(a, (int)(sp & 127));
+    const u64 rep = occ_view_count(e, (int)(x & 127));
+    const int sym = occ_planes_symbol(a.p0, a.p1, (int)(ep & 127));
+    nsp = off + rsp + last_chr_fix(ix, c, sp, 0);
+    const u64 nep_range = off + rep + last_chr_fix(ix, c, ep, 1) - 1;
+    const u64 nep_single = nsp + ((sym == c) ? 0ull : ~0ull);
+    nep = range ? nep_range : nep_single;
   }
   static CFR_HD u64 lf(const DevIndex &ix, u64 i, OpCount &oc) {
     ++oc.access;
@@ -474,28 +474,22 @@ struct BwtOccCoop4 {
   static __device__ __forceinline__ void extend(const DevIndex &ix, int c, u64 sp, u64 ep, u64 &nsp, u64 &nep,
                                                 OpCount &oc) {
     const u64 off = ix.C[c];
+    const u64 lsp = sp >> 7, x = ep + 1, lx = x >> 7;
+    const bool range = sp != ep;
     ++oc.extend;
     ++oc.rank;
-    const u64 lsp = sp >> 7;
+    oc.rank += range ? 1u : 0u;
+    oc.access += range ? 0u : 1u;
     const ulonglong2 a = quarter(ix, lsp);
-    u64 psp = piece(a, c, (int)(sp & 127));
-    if (sp != ep) {
-      ++oc.rank;
-      const u64 x = ep + 1, lx = x >> 7;
-      ulonglong2 e = a;
-      if (lx != lsp) e = quarter(ix, lx);
-      u64 pep = piece(e, c, (int)(x & 127));
-      psp = gsum(psp);
-      pep = gsum(pep);
-      nsp = off + psp + last_chr_fix(ix, c, sp, 0);
-      nep = off + pep + last_chr_fix(ix, c, ep, 1) - 1;
-    } else {
-      ++oc.access;
-      psp = gsum(psp);
-      const int sym = symbol(a, (int)(ep & 127));
-      nsp = off + psp + last_chr_fix(ix, c, sp, 0);
-      nep = nsp + ((sym == c) ? 0ull : ~0ull);
-    }
+    ulonglong2 e = a;
+    if (lx != lsp) e = quarter(ix, lx);
+    const u64 psp = gsum(piece(a, c, (int)(sp & 127)));
+    const u64 pep = gsum(piece(e, c, (int)(x & 127)));
+    const int sym = symbol(a, (int)(ep & 127));
+    nsp = off + psp + last_chr_fix(ix, c, sp, 0);
+    const u64 nep_range = off + pep + last_chr_fix(ix, c, ep, 1) - 1;
+    const u64 nep_single = nsp + ((sym == c) ? 0ull : ~0ull);
+    nep = range ? nep_range : nep_single;
   }
   static __device__ __forceinline__ u64 lf(const DevIndex &ix, u64 i, OpCount &oc) {
     ++oc.access;
@@ -568,18 +562,27 @@ CFR_HD u64 sa_read(const DevIndex &ix, u64 i) {
   return (ld64(ix.sampled_sa + is) >> rs) | ((ld64(ix.sampled_sa + ie) & ((1ull << (re + 1)) - 1ull)) << (64 - rs));
 }
 
+// i % sampleRate == 0 and i / filterRate; both rates are powers of two in every
+// index the reference builder writes (--offrate, 1024), the general form is kept
+CFR_HD bool is_sampled_row(const DevIndex &ix, u64 i) {
+  return ix.sample_shift >= 0 ? (i & ((1ull << ix.sample_shift) - 1ull)) == 0 : (i % (u64)ix.sample_rate) == 0;
+}
+CFR_HD u64 filter_bit_index(const DevIndex &ix, u64 i) {
+  return ix.filter_shift >= 0 ? (i >> ix.filter_shift) : i / (u64)ix.sel_filter_rate;
+}
+
 // FMIndex::GetSampledSA
 CFR_HD bool get_sampled_sa(const DevIndex &ix, u64 i, u64 &sa) {
   if (i == ix.first_isa) {
     sa = ix.adjusted_sa0;
     return true;
   }
-  if (i % (u64)ix.sample_rate == 0) {
-    sa = sa_read(ix, i / (u64)ix.sample_rate);
+  if (is_sampled_row(ix, i)) {
+    sa = sa_read(ix, ix.sample_shift >= 0 ? (i >> ix.sample_shift) : i / (u64)ix.sample_rate);
     return true;
   }
   if (ix.sel_filter) {
-    const u64 fb = i / (u64)ix.sel_filter_rate;
+    const u64 fb = filter_bit_index(ix, i);
     if ((ld64(ix.sel_filter + (fb >> 6)) >> (fb & 63)) & 1ull) {
       u64 lo = 0, hi = ix.sel_cnt;
       while (lo < hi) {

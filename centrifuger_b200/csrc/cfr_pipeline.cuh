@@ -101,12 +101,28 @@ CFR_HD void dust_stage(const ChunkDev &B, u64 task, DustStateT<SW> &d) {
 // s = 0: its reverse complement (strandHits[0]).
 //
 // GetHitsFromRead + BackwardSearch (Classifier.hpp:274-293, FMIndex.hpp:388-422,
-// 487-510) flattened into ONE loop: every iteration a lane either starts a search
-// (packs the lookup-table key of the last W bases), extends its range by one base,
-// closes a search (records the hit, skips the mismatching base) or picks up its
-// next task.  The nested-loop form leaves most lanes of a warp idle while the
-// longest inner loop finishes; the flat form keeps them all on the extend step.
-enum { CFR_PH_FETCH = 0, CFR_PH_INIT = 1, CFR_PH_EXTEND = 2, CFR_PH_FINISH = 3 };
+// 487-510) as a warp-synchronous state machine.  Every iteration the lanes that
+// are inside a search do ONE BackwardExtend together (straight-line code).  The
+// rare events -- closing a search (record the hit, skip the mismatching base),
+// starting the next one (lookup-table probe of the last W bases) and fetching the
+// next task -- are deferred until a quorum of lanes is waiting for them (or nobody
+// can extend), so that block runs with many lanes instead of one or two.
+#if defined(__CUDA_ARCH__)
+#define CFR_BALLOT(pred) __ballot_sync(0xffffffffu, (pred))
+#else
+#define CFR_BALLOT(pred) ((pred) ? 1u : 0u)
+#endif
+
+CFR_HD int popc32(u32 x) {
+#if defined(__CUDA_ARCH__)
+  return __popc(x);
+#else
+  return __builtin_popcount(x);
+#endif
+}
+
+enum { CFR_ST_EXTEND = 0, CFR_ST_CLOSE = 1, CFR_ST_FETCH = 2, CFR_ST_DONE = 3 };
+enum { CFR_QUORUM = 8 };  // tasks waiting before the transition block runs
 
 template <class Bwt>
 CFR_HD void search_tasks(const DevIndex &ix, const DevParams &P, const ChunkDev &B, u64 t, const u64 stride,
@@ -116,96 +132,105 @@ CFR_HD void search_tasks(const DevIndex &ix, const DevParams &P, const ChunkDev 
   Hit *out = nullptr;
   u64 cur = 0, sp = 0, ep = 0;
   int nh = 0, remaining = 0, l = 0;
-  int phase = CFR_PH_FETCH;
+  int st = CFR_ST_FETCH;
   for (;;) {
-    if (phase == CFR_PH_FETCH) {
-      if (t >= ntask) break;
-      cur = t;
-      t += stride;
-      const u64 read = cur / (u64)S;
-      const int w = (int)(cur % (u64)S);
-      const int mate = w >> 1;
-      const u64 base = B.off[mate][read] - B.off_bias[mate];
-      s.base = base;
-      s.len = (int)(B.off[mate][read + 1] - B.off[mate][read]);
-      s.rc = (w & 1) ? 0 : 1;
-      s.widx = ~0ull;
-      out = B.strand_hits + cur * (u64)B.cap_h;
-      nh = 0;
-      remaining = s.len;
-      sp = ep = 0;
-      phase = remaining >= mhl ? CFR_PH_INIT : CFR_PH_FINISH;
-    }
-    bool search_done = false;
-    if (phase == CFR_PH_INIT) {  // FMIndex::BackwardSearch up to the initial range
-      if (remaining < W) {
-        l = 0;
-        search_done = true;
-      } else {
-        ++oc.search;
-        if (W > 0) {
-          u64 key;
-          int nvalid;
-          if (!s.init_key(remaining, W, key, nvalid)) {
-            sp = 1;
-            ep = 0;
-            l = nvalid;
-            search_done = true;
-          } else {
-            const u64x2 e = ld128(ix.lookup + key);
-            if (e.y == 0) {
-              sp = 1;
-              ep = 0;
-              l = W - 1;
-              search_done = true;
-            } else {
-              sp = e.x;
-              ep = e.x + e.y - 1;
-              l = W;
-              phase = CFR_PH_EXTEND;
+    const u32 ext = CFR_BALLOT(st == CFR_ST_EXTEND);
+    const u32 trn = CFR_BALLOT(st == CFR_ST_CLOSE || st == CFR_ST_FETCH);
+    if ((ext | trn) == 0) break;
+    if (trn != 0 && (ext == 0 || popc32(trn) >= CFR_QUORUM * (int)Bwt::LANES)) {
+      // ---- transition block: CLOSE -> (FETCH ->) start of the next search
+      for (int tries = 0; tries < 4 && (st == CFR_ST_CLOSE || st == CFR_ST_FETCH); ++tries) {
+        bool start = false;
+        if (st == CFR_ST_CLOSE) {  // back in GetHitsFromRead
+          if (l >= mhl && sp <= ep && nh < B.cap_h) {
+            if (Bwt::leader()) {
+              out[nh].sp = sp;
+              out[nh].ep = ep;
+              out[nh].l = l;
+              out[nh].offset = s.len - remaining;
             }
+            ++nh;
+          }
+          remaining -= (l + 1);
+          if (remaining >= mhl) {
+            start = true;
+          } else {
+            if (Bwt::leader()) B.strand_nhits[cur] = nh;
+            st = CFR_ST_FETCH;
           }
         } else {
-          sp = 0;
-          ep = ix.n - 1;
-          l = 0;
-          phase = CFR_PH_EXTEND;
+          if (t >= ntask) {
+            st = CFR_ST_DONE;
+            break;
+          }
+          cur = t;
+          t += stride;
+          const u64 read = cur / (u64)S;
+          const int w = (int)(cur % (u64)S);
+          const int mate = w >> 1;
+          s.base = B.off[mate][read] - B.off_bias[mate];
+          s.len = (int)(B.off[mate][read + 1] - B.off[mate][read]);
+          s.rc = (w & 1) ? 0 : 1;
+          s.widx = ~0ull;
+          out = B.strand_hits + cur * (u64)B.cap_h;
+          nh = 0;
+          remaining = s.len;
+          sp = ep = 0;
+          if (remaining >= mhl) {
+            start = true;
+          } else if (Bwt::leader()) {
+            B.strand_nhits[cur] = 0;
+          }
         }
-      }
-    }
-    if (phase == CFR_PH_EXTEND && !search_done) {  // one FMIndex::BackwardExtend
-      bool adv = false;
-      if (l < remaining) {
-        const int c = s(remaining - 1 - l);
-        if (c <= 3) {
-          u64 nsp, nep;
-          Bwt::extend(ix, c, sp, ep, nsp, nep, oc);
-          if (!(nsp > nep || nep > ix.n)) {
-            sp = nsp;
-            ep = nep;
-            ++l;
-            adv = l < remaining;
+        if (start) {  // FMIndex::BackwardSearch up to the initial range
+          st = CFR_ST_CLOSE;
+          if (remaining < W) {
+            l = 0;
+          } else {
+            ++oc.search;
+            if (W > 0) {
+              u64 key;
+              int nvalid;
+              if (!s.init_key(remaining, W, key, nvalid)) {
+                sp = 1;
+                ep = 0;
+                l = nvalid;
+              } else {
+                const u64x2 e = ld128(ix.lookup + key);
+                if (e.y == 0) {
+                  sp = 1;
+                  ep = 0;
+                  l = W - 1;
+                } else {
+                  sp = e.x;
+                  ep = e.x + e.y - 1;
+                  l = W;
+                  if (l < remaining) st = CFR_ST_EXTEND;
+                }
+              }
+            } else {
+              sp = 0;
+              ep = ix.n - 1;
+              l = 0;
+              if (l < remaining) st = CFR_ST_EXTEND;
+            }
           }
         }
       }
-      if (!adv) search_done = true;
     }
-    if (search_done) {  // back in GetHitsFromRead
-      if (l >= mhl && sp <= ep && nh < B.cap_h) {
-        if (Bwt::leader()) {
-          out[nh].sp = sp;
-          out[nh].ep = ep;
-          out[nh].l = l;
-          out[nh].offset = s.len - remaining;
+    if (st == CFR_ST_EXTEND) {  // one FMIndex::BackwardExtend; l < remaining holds here
+      const int c = s(remaining - 1 - l);
+      st = CFR_ST_CLOSE;
+      if (c <= 3) {
+        u64 nsp, nep;
+        Bwt::extend(ix, c, sp, ep, nsp, nep, oc);
+        if (!(nsp > nep || nep > ix.n)) {
+          sp = nsp;
+          ep = nep;
+          ++l;
+          if (l < remaining) st = CFR_ST_EXTEND;
         }
-        ++nh;
       }
-      remaining -= (l + 1);
-      phase = remaining >= mhl ? CFR_PH_INIT : CFR_PH_FINISH;
-    }
-    if (phase == CFR_PH_FINISH) {
-      if (Bwt::leader()) B.strand_nhits[cur] = nh;
-      phase = CFR_PH_FETCH;
     }
   }
 }
@@ -298,31 +323,59 @@ CFR_HD void select_write_rows(const DevParams &P, const ChunkDev &B, u64 read, u
 }
 
 // ------------------------------------------------------------------ locate
-// FMIndex::BackwardToSampledSA for the arena rows slot, slot+stride, ...  Flat
-// loop as above: a lane whose walk ends picks up its next row at once instead of
-// waiting for the longest walk (geometric lengths) in its warp.
+// FMIndex::BackwardToSampledSA for the arena rows slot, slot+stride, ...  Same
+// scheme: lanes that are walking do one LF step together; resolving a sampled
+// row (sampled-SA read / selected-SA look-up), storing the sequence id and
+// fetching the next row wait for a quorum.
+enum { CFR_LS_WALK = 0, CFR_LS_CHECK = 1, CFR_LS_NEED = 2, CFR_LS_DONE = 3 };
+
 template <class Bwt>
 CFR_HD void locate_rows(const DevIndex &ix, const ChunkDev &B, u64 slot, const u64 stride, const u64 used,
                         OpCount &oc) {
   u64 cur = 0, i = 0;
-  bool have = false;
+  int st = CFR_LS_NEED;
   for (;;) {
-    if (!have) {
-      if (slot >= used) break;
-      cur = slot;
-      slot += stride;
-      i = B.rows[cur];
-      if (i == CFR_ROW_SENTINEL) continue;
-      have = true;
+    const u32 walk = CFR_BALLOT(st == CFR_LS_WALK);
+    const u32 trn = CFR_BALLOT(st == CFR_LS_CHECK || st == CFR_LS_NEED);
+    if ((walk | trn) == 0) break;
+    if (trn != 0 && (walk == 0 || popc32(trn) >= CFR_QUORUM * (int)Bwt::LANES)) {
+      for (int tries = 0; tries < 4 && (st == CFR_LS_CHECK || st == CFR_LS_NEED); ++tries) {
+        if (st == CFR_LS_CHECK) {  // FMIndex::GetSampledSA, literally
+          u64 sa;
+          if (get_sampled_sa(ix, i, sa)) {
+            if (Bwt::leader()) B.seq_ids[cur] = (u32)sa;
+            ++oc.locate;
+            st = CFR_LS_NEED;
+          } else {  // filter bit set but the row is not a selected one: keep walking
+            i = Bwt::lf(ix, i, oc);
+            ++oc.lf;
+            st = CFR_LS_WALK;
+          }
+        } else {
+          if (slot >= used) {
+            st = CFR_LS_DONE;
+            break;
+          }
+          cur = slot;
+          slot += stride;
+          i = B.rows[cur];
+          if (i != CFR_ROW_SENTINEL) st = CFR_LS_WALK;
+        }
+      }
     }
-    u64 sa;
-    if (get_sampled_sa(ix, i, sa)) {
-      if (Bwt::leader()) B.seq_ids[cur] = (u32)sa;
-      ++oc.locate;
-      have = false;
-    } else {
-      i = Bwt::lf(ix, i, oc);
-      ++oc.lf;
+    if (st == CFR_LS_WALK) {
+      // cheap pre-test of GetSampledSA's three conditions; the loads happen in the transition block
+      bool maybe = i == ix.first_isa || is_sampled_row(ix, i);
+      if (!maybe && ix.sel_filter) {
+        const u64 fb = filter_bit_index(ix, i);
+        maybe = (ld64(ix.sel_filter + (fb >> 6)) >> (fb & 63)) & 1ull;
+      }
+      if (maybe) {
+        st = CFR_LS_CHECK;
+      } else {
+        i = Bwt::lf(ix, i, oc);
+        ++oc.lf;
+      }
     }
   }
 }

@@ -55,6 +55,7 @@ struct DevIndex {
   const OccLine *occ;
   // locate (FMIndex.hpp:13-41)
   int sample_rate;
+  int sample_shift;  // log2(sample_rate) or -1
   int sa_bits;
   const u64 *sampled_sa;
   u64 adjusted_sa0;
@@ -62,6 +63,7 @@ struct DevIndex {
   u64 sel_cnt;
   const u64 *sel_filter;
   int sel_filter_rate;
+  int filter_shift;  // log2(sel_filter_rate) or -1
   // 10-mer (precomputeWidth-mer) lookup table
   int pre_width;
   const u64x2 *lookup;  // {start, len}

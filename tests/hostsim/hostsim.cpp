@@ -79,12 +79,14 @@ void *hostsim_open(const char *prefix, const cfr_params *p) {
   ix.plain = h->mk_wt(f.plain);
   ix.run = h->mk_wt(f.run);
   ix.sample_rate = f.sample_rate;
+  ix.sample_shift = (f.sample_rate & (f.sample_rate - 1)) == 0 ? __builtin_ctz((unsigned)f.sample_rate) : -1;
   ix.sa_bits = f.sa_bits;
   ix.sampled_sa = h->copy_words(f.sa_w, f.sa_words);
   ix.adjusted_sa0 = f.adjusted_sa0;
   ix.sel = (const u64x2 *)h->copy_words(f.sel, f.sel_cnt * 2);
   ix.sel_cnt = f.sel_cnt;
   ix.sel_filter_rate = f.sel_filter_rate;
+  ix.filter_shift = (f.sel_filter_rate & (f.sel_filter_rate - 1)) == 0 ? __builtin_ctz((unsigned)f.sel_filter_rate) : -1;
   if (f.sel_cnt > 0) {
     u64 fbits = (f.n + f.sel_filter_rate - 1) / f.sel_filter_rate;
     h->sel_filter.assign(fbits / 64 + 2, 0);
