@@ -82,7 +82,6 @@ struct cfr_handle {
   DevIndex ix;
   DevParams P;
   int layout = CFR_LAYOUT_RUNBLOCK;
-  bool coop = true;  // occ lines read by 4-lane groups (CFR_B200_SCALAR_OCC=1 selects one lane per task)
   std::vector<void *> index_allocs;
   size_t hbm_bytes = 0;
   int sm_count = 148;
@@ -359,6 +358,8 @@ void fill_chunk(cfr_handle *h, cfr_device_batch *b, ChunkDev &B) {
   B.arena_cap = b->arena_cap;
   B.arena_used = (u64 *)b->scalars.p;
   B.n_deferred = (u32 *)((char *)b->scalars.p + 8);
+  B.task_counter = (u64 *)((char *)b->scalars.p + 16);
+  B.row_counter = (u64 *)((char *)b->scalars.p + 24);
   B.rows = (u64 *)b->rows.p;
   B.seq_ids = (u32 *)b->seq_ids.p;
   B.rec0 = (SeqRec *)b->rec0.p;
@@ -381,6 +382,7 @@ int run_pass(cfr_handle *h, const ChunkDev &B, int first_pass, cudaStream_t s) {
   {
     StageScope sc(h, s, CFR_STAGE_OTHER);
     CUDA_TRY(cudaMemsetAsync(B.arena_used, 0, 16, s));
+    CUDA_TRY(cudaMemsetAsync(B.row_counter, 0, 8, s));
     // unwritten arena rows (reads deferred to the next pass) must read as "skip"
     CUDA_TRY(cudaMemsetAsync(B.rows, 0xff, B.arena_cap * 8, s));
   }
@@ -390,7 +392,7 @@ int run_pass(cfr_handle *h, const ChunkDev &B, int first_pass, cudaStream_t s) {
   }
   {
     StageScope sc(h, s, CFR_STAGE_LOCATE);
-    k_locate<BwtWide><<<grid_for(h, B.arena_cap * BwtWide::LANES, 128, 16), 128, 0, s>>>(h->ix, B);
+    k_locate<BwtWide><<<grid_for(h, B.arena_cap * BwtWide::LANES, 128, 16), 128, 0, s>>>(h->ix, h->P, B);
   }
   {
     StageScope sc(h, s, CFR_STAGE_SCORE);
@@ -416,6 +418,7 @@ int run_first(cfr_handle *h, cfr_device_batch *b, cudaStream_t s) {
     k_dust<<<grid_for(h, B.n_reads * B.mates, CFR_DUST_THREADS, 5), CFR_DUST_THREADS, CFR_DUST_SMEM, s>>>(B);
     ++h->launches;
   }
+  CUDA_TRY(cudaMemsetAsync(B.task_counter, 0, 8, s));
   {
     StageScope sc(h, s, CFR_STAGE_SEARCH);
     k_search<BwtWide><<<grid_for(h, B.n_reads * 2 * B.mates * BwtWide::LANES, 128, 16), 128, 0, s>>>(h->ix, h->P, B);
@@ -519,6 +522,8 @@ int cfr_open(const char *idx_prefix, const cfr_params *p, int device, cfr_handle
   h->P.hitk_factor = params.max_result_per_hit_factor;
   h->P.secondary_len = params.consider_secondary_hit_len;
   h->P.secondary_factor = params.consider_secondary_score_factor;
+  h->P.quorum = 8;
+  if (const char *e = getenv("CFR_B200_QUORUM")) h->P.quorum = std::max(1, atoi(e));
   if ((st = upload_index(h))) return bail(st);
   void *p2;
   if ((st = dev_alloc(h, &p2, (h->ix.node_cnt + 3) * 8))) return bail(st);
@@ -535,7 +540,6 @@ int cfr_open(const char *idx_prefix, const cfr_params *p, int device, cfr_handle
     if ((u64)free_b < need + (8ull << 30)) h->layout = CFR_LAYOUT_RUNBLOCK;  // keep 8 GiB for work areas
   }
   if (h->layout == CFR_LAYOUT_OCCLINE && (st = build_occ_lines(h))) return bail(st);
-  if (const char *e = getenv("CFR_B200_SCALAR_OCC")) h->coop = !(e[0] == '1');
   h->file.map1.close();  // everything needed from .1.cfr now lives in HBM
   *out = h;
   return CFR_OK;
@@ -597,8 +601,7 @@ int cfr_classify_resident(cfr_handle *h, cfr_device_batch *b, void *stream) {
   cudaStream_t s = pick_stream(h, stream);
   h->host_bases += b->total_bases;
   b->classified = true;
-  if (h->layout == CFR_LAYOUT_OCCLINE)
-    return h->coop ? run_first<BwtOccLine, BwtOccCoop4>(h, b, s) : run_first<BwtOccLine, BwtOccLine>(h, b, s);
+  if (h->layout == CFR_LAYOUT_OCCLINE) return run_first<BwtOccLine, BwtOccLine>(h, b, s);
   return run_first<BwtRunBlock, BwtRunBlock>(h, b, s);
 }
 
@@ -609,7 +612,7 @@ int cfr_batch_fetch(cfr_handle *h, cfr_device_batch *b, cfr_result *results, uin
   cudaStream_t s = pick_stream(h, stream);
   int st;
   if (h->layout == CFR_LAYOUT_OCCLINE)
-    st = h->coop ? finish_deferred<BwtOccLine, BwtOccCoop4>(h, b, s) : finish_deferred<BwtOccLine, BwtOccLine>(h, b, s);
+    st = finish_deferred<BwtOccLine, BwtOccLine>(h, b, s);
   else
     st = finish_deferred<BwtRunBlock, BwtRunBlock>(h, b, s);
   if (st) return st;

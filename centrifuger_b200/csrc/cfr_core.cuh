@@ -345,45 +345,33 @@ struct BwtRunBlock {
 // Layout 2: 64-byte occ lines (128 symbols + 4 absolute counters per line)
 // ---------------------------------------------------------------------------
 
-// occ-line helpers (one lane reads what it needs of a line: the counter of the
-// symbol and the two plane pairs)
+// occ(c, x) = # of symbol c in BWT[0..x), x in [0, n].  One rank touches the
+// symbol's counter word (8 B) and the plane pair of ONE 64-symbol half (16 B):
+//   word w = cnt[c]: bits 0..55  # of c before the line
+//                    bits 56..62 # of c in the line's first half
+struct OccRank {
+  u64 count;   // occ(c, x)
+  u64x2 half;  // {lo, hi} planes of the half that holds position x
+};
+
 CFR_HD u64 occ_match(const u64x2 &p, int c) {  // p = {lo, hi} planes of 64 symbols
   const u64 ml = (c & 1) ? ~0ull : 0ull, mh = (c & 2) ? ~0ull : 0ull;
   return ~(p.x ^ ml) & ~(p.y ^ mh);
 }
-CFR_HD u64 occ_k0(int within) { return within >= 64 ? ~0ull : ((1ull << within) - 1ull); }
-CFR_HD u64 occ_k1(int within) { return within > 64 ? ((1ull << (within - 64)) - 1ull) : 0ull; }
 
-struct OccView {  // the parts of one line a rank of symbol c needs
-  u64 cnt;
-  u64 m0, m1;  // match masks of the two 64-symbol halves
-  u64x2 p0, p1;
-};
-
-CFR_HD OccView occ_view(const OccLine *L, int c) {
-  OccView v;
-  v.cnt = ld64(reinterpret_cast<const u64 *>(L) + c);
-  v.p0 = ld128(reinterpret_cast<const u64x2 *>(L) + 2);
-  v.p1 = ld128(reinterpret_cast<const u64x2 *>(L) + 3);
-  v.m0 = occ_match(v.p0, c);
-  v.m1 = occ_match(v.p1, c);
-  return v;
+CFR_HD OccRank occ_rank(const DevIndex &ix, int c, u64 x) {
+  const OccLine *L = ix.occ + (x >> 7);
+  const int within = (int)(x & 127), h = within >> 6, s = within & 63;
+  OccRank r;
+  const u64 w = ld64(reinterpret_cast<const u64 *>(L) + c);
+  r.half = ld128(reinterpret_cast<const u64x2 *>(L) + 2 + h);
+  const u64 below = (1ull << s) - 1ull;
+  r.count = (w & 0x00ffffffffffffffull) + (h ? (w >> 56) : 0ull) + (u64)popc64(occ_match(r.half, c) & below);
+  return r;
 }
 
-CFR_HD u64 occ_view_count(const OccView &v, int within) {
-  return v.cnt + (u64)popc64(v.m0 & occ_k0(within)) + (u64)popc64(v.m1 & occ_k1(within));
-}
-
-CFR_HD int occ_planes_symbol(const u64x2 &p0, const u64x2 &p1, int within) {
-  const u64 lo = within >= 64 ? p1.x : p0.x, hi = within >= 64 ? p1.y : p0.y;
-  const int s = within & 63;
-  return (int)(((lo >> s) & 1ull) | (((hi >> s) & 1ull) << 1));
-}
-
-// occ(c, x) = # of c in BWT[0..x), x in [0, n]
-CFR_HD u64 occ_rank_excl(const DevIndex &ix, int c, u64 x) {
-  const OccView v = occ_view(ix.occ + (x >> 7), c);
-  return occ_view_count(v, (int)(x & 127));
+CFR_HD int occ_half_symbol(const u64x2 &half, int s) {
+  return (int)(((half.x >> s) & 1ull) | (((half.y >> s) & 1ull) << 1));
 }
 
 struct BwtOccLine {
@@ -391,20 +379,16 @@ struct BwtOccLine {
   // single-row forms of FMIndex::BackwardExtend are selected at the end
   static CFR_HD void extend(const DevIndex &ix, int c, u64 sp, u64 ep, u64 &nsp, u64 &nep, OpCount &oc) {
     const u64 off = ix.C[c];
-    const u64 lsp = sp >> 7, x = ep + 1, lx = x >> 7;
     const bool range = sp != ep;
     ++oc.extend;
     ++oc.rank;
     oc.rank += range ? 1u : 0u;
     oc.access += range ? 0u : 1u;
-    const OccView a = occ_view(ix.occ + lsp, c);
-    OccView e = a;
-    if (lx != lsp) e = occ_view(ix.occ + lx, c);
-    const u64 rsp = occ_view_count(a, (int)(sp & 127));
-    const u64 rep = occ_view_count(e, (int)(x & 127));
-    const int sym = occ_planes_symbol(a.p0, a.p1, (int)(ep & 127));
-    nsp = off + rsp + last_chr_fix(ix, c, sp, 0);
-    const u64 nep_range = off + rep + last_chr_fix(ix, c, ep, 1) - 1;
+    const OccRank a = occ_rank(ix, c, sp);      // Rank(c, sp, exclusive)
+    const OccRank e = occ_rank(ix, c, ep + 1);  // Rank(c, ep, inclusive)
+    const int sym = occ_half_symbol(a.half, (int)(ep & 63));  // BWT[ep] when sp == ep (same half as sp)
+    nsp = off + a.count + last_chr_fix(ix, c, sp, 0);
+    const u64 nep_range = off + e.count + last_chr_fix(ix, c, ep, 1) - 1;
     const u64 nep_single = nsp + ((sym == c) ? 0ull : ~0ull);
     nep = range ? nep_range : nep_single;
   }
@@ -412,96 +396,27 @@ struct BwtOccLine {
     ++oc.access;
     ++oc.rank;
     const OccLine *L = ix.occ + (i >> 7);
-    const int w = (int)(i & 127);
-    const u64x2 p0 = ld128(reinterpret_cast<const u64x2 *>(L) + 2);
-    const u64x2 p1 = ld128(reinterpret_cast<const u64x2 *>(L) + 3);
-    const int c = occ_planes_symbol(p0, p1, w);
-    const u64 cnt = ld64(reinterpret_cast<const u64 *>(L) + c);
-    const u64 r = cnt + (u64)popc64(occ_match(p0, c) & occ_k0(w)) + (u64)popc64(occ_match(p1, c) & occ_k1(w));
+    const int within = (int)(i & 127), h = within >> 6, s = within & 63;
+    const u64x2 half = ld128(reinterpret_cast<const u64x2 *>(L) + 2 + h);
+    const int c = occ_half_symbol(half, s);
+    const u64 w = ld64(reinterpret_cast<const u64 *>(L) + c);
+    const u64 r = (w & 0x00ffffffffffffffull) + (h ? (w >> 56) : 0ull) +
+                  (u64)popc64(occ_match(half, c) & ((1ull << s) - 1ull));
     // inclusive rank at i = exclusive count at i, plus the symbol itself
     return ix.C[c] + r + 1 + last_chr_fix(ix, c, i, 1) - 1;
   }
   static CFR_HD u64 rank(const DevIndex &ix, int c, u64 i, int inclusive) {
-    if (!inclusive) return occ_rank_excl(ix, c, i);
-    return occ_rank_excl(ix, c, i + 1);
+    return occ_rank(ix, c, inclusive ? i + 1 : i).count;
   }
   static CFR_HD int access(const DevIndex &ix, u64 i) {
     const OccLine *L = ix.occ + (i >> 7);
-    const u64x2 p0 = ld128(reinterpret_cast<const u64x2 *>(L) + 2);
-    const u64x2 p1 = ld128(reinterpret_cast<const u64x2 *>(L) + 3);
-    return occ_planes_symbol(p0, p1, (int)(i & 127));
+    const int within = (int)(i & 127);
+    const u64x2 half = ld128(reinterpret_cast<const u64x2 *>(L) + 2 + (within >> 6));
+    return occ_half_symbol(half, within & 63);
   }
   static CFR_HD bool leader() { return true; }
   enum { LANES = 1 };
 };
-
-#if defined(__CUDACC__)
-// The same occ lines read cooperatively: 4 adjacent lanes own one search / walk.
-// Each lane pulls one 16-byte quarter of the 64-byte line (one coalesced 128-bit
-// load per line for the whole group instead of four divergent ones), counts its
-// quarter, and the group sums with two xor-shuffles.  All four lanes carry the
-// same scalar state (sp, ep, l, ...), so control flow is uniform inside a group.
-struct BwtOccCoop4 {
-  enum { LANES = 4 };
-  static __device__ __forceinline__ unsigned gmask() { return 0xFu << (threadIdx.x & 28); }
-  static __device__ __forceinline__ int gl() { return threadIdx.x & 3; }
-  static __device__ __forceinline__ bool leader() { return (threadIdx.x & 3) == 0; }
-  static __device__ __forceinline__ ulonglong2 quarter(const DevIndex &ix, u64 line) {
-    return __ldg(reinterpret_cast<const ulonglong2 *>(ix.occ + line) + gl());
-  }
-  // this lane's share of occ(c, within) for the line whose quarter it holds
-  static __device__ __forceinline__ u64 piece(const ulonglong2 &v, int c, int within) {
-    const int g = gl();
-    const int i0 = (g & 1) * 2;
-    const u64 cnt = (c == i0) ? v.x : ((c == i0 + 1) ? v.y : 0ull);
-    const u64 ml = (c & 1) ? ~0ull : 0ull, mh = (c & 2) ? ~0ull : 0ull;
-    const u64 m = ~(v.x ^ ml) & ~(v.y ^ mh);
-    const int w = within - (g & 1) * 64;
-    const u64 k = w >= 64 ? ~0ull : (w <= 0 ? 0ull : ((1ull << w) - 1ull));
-    return g < 2 ? cnt : (u64)__popcll(m & k);
-  }
-  static __device__ __forceinline__ u64 gsum(u64 p) {
-    const unsigned m = gmask();
-    p += __shfl_xor_sync(m, p, 1);
-    p += __shfl_xor_sync(m, p, 2);
-    return p;
-  }
-  static __device__ __forceinline__ int symbol(const ulonglong2 &v, int within) {
-    const int s = within & 63;
-    const int mine = (int)(((v.x >> s) & 1ull) | (((v.y >> s) & 1ull) << 1));
-    return __shfl_sync(gmask(), mine, 2 + (within >> 6), 4);
-  }
-  static __device__ __forceinline__ void extend(const DevIndex &ix, int c, u64 sp, u64 ep, u64 &nsp, u64 &nep,
-                                                OpCount &oc) {
-    const u64 off = ix.C[c];
-    const u64 lsp = sp >> 7, x = ep + 1, lx = x >> 7;
-    const bool range = sp != ep;
-    ++oc.extend;
-    ++oc.rank;
-    oc.rank += range ? 1u : 0u;
-    oc.access += range ? 0u : 1u;
-    const ulonglong2 a = quarter(ix, lsp);
-    ulonglong2 e = a;
-    if (lx != lsp) e = quarter(ix, lx);
-    const u64 psp = gsum(piece(a, c, (int)(sp & 127)));
-    const u64 pep = gsum(piece(e, c, (int)(x & 127)));
-    const int sym = symbol(a, (int)(ep & 127));
-    nsp = off + psp + last_chr_fix(ix, c, sp, 0);
-    const u64 nep_range = off + pep + last_chr_fix(ix, c, ep, 1) - 1;
-    const u64 nep_single = nsp + ((sym == c) ? 0ull : ~0ull);
-    nep = range ? nep_range : nep_single;
-  }
-  static __device__ __forceinline__ u64 lf(const DevIndex &ix, u64 i, OpCount &oc) {
-    ++oc.access;
-    ++oc.rank;
-    const ulonglong2 a = quarter(ix, i >> 7);
-    const int w = (int)(i & 127);
-    const int c = symbol(a, w);
-    const u64 p = gsum(piece(a, c, w));
-    return ix.C[c] + p + 1 + last_chr_fix(ix, c, i, 1) - 1;
-  }
-};
-#endif
 
 // ---------------------------------------------------------------------------
 // FM-index search and locate

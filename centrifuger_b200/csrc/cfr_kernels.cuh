@@ -56,9 +56,7 @@ __global__ void __launch_bounds__(128) k_search(const __grid_constant__ DevIndex
                                                 const __grid_constant__ ChunkDev B) {
   OpCount oc{};
   const u64 ntask = B.n_reads * (u64)(2 * B.mates);
-  const u64 stride = ((u64)gridDim.x * blockDim.x) / Bwt::LANES;
-  // Bwt::LANES adjacent lanes share one task (1 = one strand per thread)
-  search_tasks<Bwt>(ix, P, B, ((u64)blockIdx.x * blockDim.x + threadIdx.x) / Bwt::LANES, stride, ntask, oc);
+  search_tasks<Bwt>(ix, P, B, ntask, oc);  // tasks are claimed dynamically from B.task_counter
   if (!Bwt::leader()) oc = OpCount{};
   flush_counts(oc, B.counters + CFR_STAGE_SEARCH);
 }
@@ -98,12 +96,12 @@ __global__ void __launch_bounds__(128) k_select(const __grid_constant__ DevIndex
 }
 
 template <class Bwt>
-__global__ void __launch_bounds__(128) k_locate(const __grid_constant__ DevIndex ix, const __grid_constant__ ChunkDev B) {
+__global__ void __launch_bounds__(128) k_locate(const __grid_constant__ DevIndex ix, const __grid_constant__ DevParams P,
+                                                const __grid_constant__ ChunkDev B) {
   OpCount oc{};
   u64 used = *B.arena_used;
   if (used > B.arena_cap) used = B.arena_cap;
-  const u64 stride = ((u64)gridDim.x * blockDim.x) / Bwt::LANES;
-  locate_rows<Bwt>(ix, B, ((u64)blockIdx.x * blockDim.x + threadIdx.x) / Bwt::LANES, stride, used, oc);
+  locate_rows<Bwt>(ix, P, B, used, oc);  // rows are claimed dynamically from B.row_counter
   if (!Bwt::leader()) oc = OpCount{};
   flush_counts(oc, B.counters + CFR_STAGE_LOCATE);
 }
@@ -166,6 +164,11 @@ __global__ void __launch_bounds__(128) k_transcode(const __grid_constant__ DevIn
     o.hi0 = hi[0];
     o.lo1 = lo[1];
     o.hi1 = hi[1];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {  // first-half counts ride in the counter words' top byte
+      const u64x2 h0{lo[0], hi[0]};
+      o.cnt[c] |= (u64)__popcll(occ_match(h0, c) & (p0 + 64 <= ix.n ? ~0ull : (p0 >= ix.n ? 0ull : ((1ull << (ix.n - p0)) - 1ull)))) << 56;
+    }
     out[L] = o;
   }
 }

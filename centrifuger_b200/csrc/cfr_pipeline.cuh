@@ -37,6 +37,8 @@ struct ChunkDev {
   // locate / scoring arena, one slot per planned BWT row
   u64 arena_cap;
   u64 *arena_used;
+  u64 *task_counter;  // next strand task (dynamic fetch by the search warps)
+  u64 *row_counter;   // next arena row (dynamic fetch by the locate warps)
   u64 *rows;
   u32 *seq_ids;
   SeqRec *rec0, *rec1;
@@ -121,12 +123,28 @@ CFR_HD int popc32(u32 x) {
 #endif
 }
 
+// Warp-aggregated claim of work items from a global counter: the lanes that `want`
+// one (LANES adjacent lanes share an item) get consecutive indices with a single
+// atomic per warp.  Must be called by all 32 lanes.
+template <int LANES>
+CFR_HD u64 warp_claim(u64 *counter, bool want) {
+#if defined(__CUDA_ARCH__)
+  const u32 m = __ballot_sync(0xffffffffu, want);
+  if (m == 0) return 0;
+  const int lane = threadIdx.x & 31, leader = __ffs((int)m) - 1;
+  u64 base = 0;
+  if (lane == leader) base = atomicAdd(counter, (u64)(__popc(m) / LANES));
+  base = __shfl_sync(0xffffffffu, base, leader);
+  return base + (u64)(__popc(m & ((1u << lane) - 1u)) / LANES);
+#else
+  return want ? (*counter)++ : 0;
+#endif
+}
+
 enum { CFR_ST_EXTEND = 0, CFR_ST_CLOSE = 1, CFR_ST_FETCH = 2, CFR_ST_DONE = 3 };
-enum { CFR_QUORUM = 8 };  // tasks waiting before the transition block runs
 
 template <class Bwt>
-CFR_HD void search_tasks(const DevIndex &ix, const DevParams &P, const ChunkDev &B, u64 t, const u64 stride,
-                         const u64 ntask, OpCount &oc) {
+CFR_HD void search_tasks(const DevIndex &ix, const DevParams &P, const ChunkDev &B, const u64 ntask, OpCount &oc) {
   const int W = ix.pre_width, mhl = P.min_hit_len, S = 2 * B.mates;
   StrandSeq s{B.codes, B.mask, 0, 0, 0};
   Hit *out = nullptr;
@@ -137,9 +155,10 @@ CFR_HD void search_tasks(const DevIndex &ix, const DevParams &P, const ChunkDev 
     const u32 ext = CFR_BALLOT(st == CFR_ST_EXTEND);
     const u32 trn = CFR_BALLOT(st == CFR_ST_CLOSE || st == CFR_ST_FETCH);
     if ((ext | trn) == 0) break;
-    if (trn != 0 && (ext == 0 || popc32(trn) >= CFR_QUORUM * (int)Bwt::LANES)) {
-      // ---- transition block: CLOSE -> (FETCH ->) start of the next search
-      for (int tries = 0; tries < 4 && (st == CFR_ST_CLOSE || st == CFR_ST_FETCH); ++tries) {
+    if (trn != 0 && (ext == 0 || popc32(trn) >= P.quorum * (int)Bwt::LANES)) {
+      // ---- transition block (warp-uniform entry): CLOSE -> (FETCH ->) start of the next search
+      for (int tries = 0; tries < 3; ++tries) {
+        if (CFR_BALLOT(st == CFR_ST_CLOSE || st == CFR_ST_FETCH) == 0) break;
         bool start = false;
         if (st == CFR_ST_CLOSE) {  // back in GetHitsFromRead
           if (l >= mhl && sp <= ep && nh < B.cap_h) {
@@ -158,28 +177,29 @@ CFR_HD void search_tasks(const DevIndex &ix, const DevParams &P, const ChunkDev 
             if (Bwt::leader()) B.strand_nhits[cur] = nh;
             st = CFR_ST_FETCH;
           }
-        } else {
-          if (t >= ntask) {
+        }
+        const u64 claimed = warp_claim<Bwt::LANES>(B.task_counter, st == CFR_ST_FETCH);
+        if (st == CFR_ST_FETCH) {
+          if (claimed >= ntask) {
             st = CFR_ST_DONE;
-            break;
-          }
-          cur = t;
-          t += stride;
-          const u64 read = cur / (u64)S;
-          const int w = (int)(cur % (u64)S);
-          const int mate = w >> 1;
-          s.base = B.off[mate][read] - B.off_bias[mate];
-          s.len = (int)(B.off[mate][read + 1] - B.off[mate][read]);
-          s.rc = (w & 1) ? 0 : 1;
-          s.widx = ~0ull;
-          out = B.strand_hits + cur * (u64)B.cap_h;
-          nh = 0;
-          remaining = s.len;
-          sp = ep = 0;
-          if (remaining >= mhl) {
-            start = true;
-          } else if (Bwt::leader()) {
-            B.strand_nhits[cur] = 0;
+          } else {
+            cur = claimed;
+            const u64 read = cur / (u64)S;
+            const int w = (int)(cur % (u64)S);
+            const int mate = w >> 1;
+            s.base = B.off[mate][read] - B.off_bias[mate];
+            s.len = (int)(B.off[mate][read + 1] - B.off[mate][read]);
+            s.rc = (w & 1) ? 0 : 1;
+            s.widx = ~0ull;
+            out = B.strand_hits + cur * (u64)B.cap_h;
+            nh = 0;
+            remaining = s.len;
+            sp = ep = 0;
+            if (remaining >= mhl) {
+              start = true;
+            } else if (Bwt::leader()) {
+              B.strand_nhits[cur] = 0;
+            }
           }
         }
         if (start) {  // FMIndex::BackwardSearch up to the initial range
@@ -230,6 +250,65 @@ CFR_HD void search_tasks(const DevIndex &ix, const DevParams &P, const ChunkDev 
           ++l;
           if (l < remaining) st = CFR_ST_EXTEND;
         }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ locate
+// FMIndex::BackwardToSampledSA for the arena rows.  Same scheme: lanes that are
+// walking do one LF step together; resolving a sampled row (sampled-SA read /
+// selected-SA look-up), storing the sequence id and claiming the next row wait
+// for a quorum.
+enum { CFR_LS_WALK = 0, CFR_LS_CHECK = 1, CFR_LS_NEED = 2, CFR_LS_DONE = 3 };
+
+template <class Bwt>
+CFR_HD void locate_rows(const DevIndex &ix, const DevParams &P, const ChunkDev &B, const u64 used, OpCount &oc) {
+  u64 cur = 0, i = 0;
+  int st = CFR_LS_NEED;
+  for (;;) {
+    const u32 walk = CFR_BALLOT(st == CFR_LS_WALK);
+    const u32 trn = CFR_BALLOT(st == CFR_LS_CHECK || st == CFR_LS_NEED);
+    if ((walk | trn) == 0) break;
+    if (trn != 0 && (walk == 0 || popc32(trn) >= P.quorum * (int)Bwt::LANES)) {
+      for (int tries = 0; tries < 3; ++tries) {
+        if (CFR_BALLOT(st == CFR_LS_CHECK || st == CFR_LS_NEED) == 0) break;
+        if (st == CFR_LS_CHECK) {  // FMIndex::GetSampledSA, literally
+          u64 sa;
+          if (get_sampled_sa(ix, i, sa)) {
+            if (Bwt::leader()) B.seq_ids[cur] = (u32)sa;
+            ++oc.locate;
+            st = CFR_LS_NEED;
+          } else {  // filter bit set but the row is not a selected one: keep walking
+            i = Bwt::lf(ix, i, oc);
+            ++oc.lf;
+            st = CFR_LS_WALK;
+          }
+        }
+        const u64 claimed = warp_claim<Bwt::LANES>(B.row_counter, st == CFR_LS_NEED);
+        if (st == CFR_LS_NEED) {
+          if (claimed >= used) {
+            st = CFR_LS_DONE;
+          } else {
+            cur = claimed;
+            i = B.rows[cur];
+            if (i != CFR_ROW_SENTINEL) st = CFR_LS_WALK;
+          }
+        }
+      }
+    }
+    if (st == CFR_LS_WALK) {
+      // cheap pre-test of GetSampledSA's three conditions; the loads happen in the transition block
+      bool maybe = i == ix.first_isa || is_sampled_row(ix, i);
+      if (!maybe && ix.sel_filter) {
+        const u64 fb = filter_bit_index(ix, i);
+        maybe = (ld64(ix.sel_filter + (fb >> 6)) >> (fb & 63)) & 1ull;
+      }
+      if (maybe) {
+        st = CFR_LS_CHECK;
+      } else {
+        i = Bwt::lf(ix, i, oc);
+        ++oc.lf;
       }
     }
   }
@@ -319,64 +398,6 @@ CFR_HD void select_write_rows(const DevParams &P, const ChunkDev &B, u64 read, u
     if (fh[i].row_cnt == 0) continue;
     const RowPlan rp = plan_rows(fh[i].sp, fh[i].ep, P);
     for (u64 t = 0; t < rp.total; ++t) B.rows[o++] = plan_row_at(fh[i].sp, fh[i].ep, rp, t);
-  }
-}
-
-// ------------------------------------------------------------------ locate
-// FMIndex::BackwardToSampledSA for the arena rows slot, slot+stride, ...  Same
-// scheme: lanes that are walking do one LF step together; resolving a sampled
-// row (sampled-SA read / selected-SA look-up), storing the sequence id and
-// fetching the next row wait for a quorum.
-enum { CFR_LS_WALK = 0, CFR_LS_CHECK = 1, CFR_LS_NEED = 2, CFR_LS_DONE = 3 };
-
-template <class Bwt>
-CFR_HD void locate_rows(const DevIndex &ix, const ChunkDev &B, u64 slot, const u64 stride, const u64 used,
-                        OpCount &oc) {
-  u64 cur = 0, i = 0;
-  int st = CFR_LS_NEED;
-  for (;;) {
-    const u32 walk = CFR_BALLOT(st == CFR_LS_WALK);
-    const u32 trn = CFR_BALLOT(st == CFR_LS_CHECK || st == CFR_LS_NEED);
-    if ((walk | trn) == 0) break;
-    if (trn != 0 && (walk == 0 || popc32(trn) >= CFR_QUORUM * (int)Bwt::LANES)) {
-      for (int tries = 0; tries < 4 && (st == CFR_LS_CHECK || st == CFR_LS_NEED); ++tries) {
-        if (st == CFR_LS_CHECK) {  // FMIndex::GetSampledSA, literally
-          u64 sa;
-          if (get_sampled_sa(ix, i, sa)) {
-            if (Bwt::leader()) B.seq_ids[cur] = (u32)sa;
-            ++oc.locate;
-            st = CFR_LS_NEED;
-          } else {  // filter bit set but the row is not a selected one: keep walking
-            i = Bwt::lf(ix, i, oc);
-            ++oc.lf;
-            st = CFR_LS_WALK;
-          }
-        } else {
-          if (slot >= used) {
-            st = CFR_LS_DONE;
-            break;
-          }
-          cur = slot;
-          slot += stride;
-          i = B.rows[cur];
-          if (i != CFR_ROW_SENTINEL) st = CFR_LS_WALK;
-        }
-      }
-    }
-    if (st == CFR_LS_WALK) {
-      // cheap pre-test of GetSampledSA's three conditions; the loads happen in the transition block
-      bool maybe = i == ix.first_isa || is_sampled_row(ix, i);
-      if (!maybe && ix.sel_filter) {
-        const u64 fb = filter_bit_index(ix, i);
-        maybe = (ld64(ix.sel_filter + (fb >> 6)) >> (fb & 63)) & 1ull;
-      }
-      if (maybe) {
-        st = CFR_LS_CHECK;
-      } else {
-        i = Bwt::lf(ix, i, oc);
-        ++oc.lf;
-      }
-    }
   }
 }
 

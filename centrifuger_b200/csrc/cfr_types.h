@@ -34,8 +34,9 @@ struct DevWT {
 };
 
 // One 64-byte occ line of the transcoded layout: 128 BWT symbols.
-//   cnt[c]  = # of symbol c in BWT[0 .. 128*line)
-//   lo/hi   = bit planes of the 128 two-bit symbol codes (w = 64-symbol half)
+//   cnt[c]  bits 0..55  = # of symbol c in BWT[0 .. 128*line)
+//           bits 56..62 = # of symbol c among the line's first 64 symbols
+//   lo/hi   = bit planes of the 128 two-bit symbol codes (0/1 = 64-symbol half)
 struct alignas(64) OccLine {
   u64 cnt[4];
   u64 lo0, hi0, lo1, hi1;
@@ -81,6 +82,7 @@ struct DevParams {
   int hitk_factor;
   u64 secondary_len;
   double secondary_factor;
+  int quorum;  // tasks that must be waiting before a warp runs its transition block
 };
 
 // Classifier.hpp:70-85 (_BWTHit); strand is kept in the low bits of `meta`

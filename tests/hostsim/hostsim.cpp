@@ -130,6 +130,11 @@ void *hostsim_open(const char *prefix, const cfr_params *p) {
         lo |= (u64)(s & 1) << (w & 63);
         hi |= (u64)(s >> 1) << (w & 63);
       }
+      for (int c = 0; c < 4; ++c) {
+        const u64x2 h0{o.lo0, o.hi0};
+        const u64 valid = L * 128 + 64 <= f.n ? ~0ull : (L * 128 >= f.n ? 0ull : ((1ull << (f.n - L * 128)) - 1ull));
+        o.cnt[c] |= (u64)popc64(occ_match(h0, c) & valid) << 56;
+      }
       h->occ[L] = o;
     }
     ix.occ = h->occ.data();
@@ -139,6 +144,7 @@ void *hostsim_open(const char *prefix, const cfr_params *p) {
   h->P.hitk_factor = p->max_result_per_hit_factor;
   h->P.secondary_len = p->consider_secondary_hit_len;
   h->P.secondary_factor = p->consider_secondary_score_factor;
+  h->P.quorum = 8;
   return h;
 }
 
@@ -259,11 +265,11 @@ int hostsim_classify(void *hh, int dust, uint64_t arena_rows, const cfr_read_bat
   for (u64 w = 0; w < n_words; ++w) encode_stage(B, w, len1 + len2);
   if (dust)
     for (u64 t = 0; t < n * mates; ++t) dust_stage(B, t, ds);
-  // several interleaved "lanes" (stride 3) so the task-fetch path of the flat loop is exercised
-  for (u64 lane = 0; lane < 3; ++lane) {
-    if (h->layout == 2) search_tasks<BwtOccLine>(ix, P, B, lane, 3, n * S, oc);
-    else search_tasks<BwtRunBlock>(ix, P, B, lane, 3, n * S, oc);
-  }
+  u64 task_counter = 0, row_counter = 0;
+  B.task_counter = &task_counter;
+  B.row_counter = &row_counter;
+  if (h->layout == 2) search_tasks<BwtOccLine>(ix, P, B, n * S, oc);
+  else search_tasks<BwtRunBlock>(ix, P, B, n * S, oc);
   B.read_list = nullptr;
   B.n_list = n;
   u64 err_flags = 0;
@@ -287,10 +293,9 @@ int hostsim_classify(void *hh, int dust, uint64_t arena_rows, const cfr_read_bat
       if (!fits) deferred[n_deferred++] = (u32)read;
     }
     const u64 used = std::min(arena_used, B.arena_cap);
-    for (u64 lane = 0; lane < 3; ++lane) {
-      if (h->layout == 2) locate_rows<BwtOccLine>(ix, B, lane, 3, used, oc);
-      else locate_rows<BwtRunBlock>(ix, B, lane, 3, used, oc);
-    }
+    row_counter = 0;
+    if (h->layout == 2) locate_rows<BwtOccLine>(ix, P, B, used, oc);
+    else locate_rows<BwtRunBlock>(ix, P, B, used, oc);
     for (u64 t = 0; t < B.n_list; ++t) {
       const u64 read = chunk_read_id(B, t);
       if (B.work[read].status != 0) continue;

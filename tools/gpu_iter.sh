@@ -2,12 +2,12 @@
 # quick GPU iteration: parity tests, then bench variants. usage: gpu_iter.sh "<workloads>" "<variants>"
 mkdir -p gpurun_out
 WL=${1:-"c2 m700"}
-VARS=${2:-"coop scalar"}
+VARS=${2:-"occ rb"}
 ( time timeout 900 python -m pytest tests -m gpu -x -q ) > gpurun_out/pytest_gpu.log 2>&1
 tail -4 gpurun_out/pytest_gpu.log
 for W in $WL; do
   for V in $VARS; do
-    if [ $V = scalar ]; then export CFR_B200_SCALAR_OCC=1; else unset CFR_B200_SCALAR_OCC; fi
+    if [[ $V == q* ]]; then export CFR_B200_QUORUM=${V#q}; else unset CFR_B200_QUORUM; fi
     EXTRA=""
     if [ $V = rb ]; then EXTRA="--layout 1"; fi
     timeout 600 python bench.py --workload $W --steps 5 --warmup 3 --no-cpu-baseline $EXTRA > gpurun_out/bench_${W}_${V}.json 2> gpurun_out/bench_${W}_${V}.err
