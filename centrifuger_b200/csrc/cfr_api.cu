@@ -360,6 +360,7 @@ void fill_chunk(cfr_handle *h, cfr_device_batch *b, ChunkDev &B) {
   B.n_deferred = (u32 *)((char *)b->scalars.p + 8);
   B.task_counter = (u64 *)((char *)b->scalars.p + 16);
   B.row_counter = (u64 *)((char *)b->scalars.p + 24);
+  B.dust_counter = (u64 *)((char *)b->scalars.p + 32);
   B.rows = (u64 *)b->rows.p;
   B.seq_ids = (u32 *)b->seq_ids.p;
   B.rec0 = (SeqRec *)b->rec0.p;
@@ -408,6 +409,7 @@ int run_first(cfr_handle *h, cfr_device_batch *b, cudaStream_t s) {
   ChunkDev B;
   fill_chunk(h, b, B);
   if (b->n_reads == 0) return CFR_OK;
+  CUDA_TRY(cudaMemsetAsync(b->scalars.p, 0, 64, s));
   {
     StageScope sc(h, s, CFR_STAGE_OTHER);
     k_encode<<<grid_for(h, B.n_words, 256, 8), 256, 0, s>>>(B, b->seq_bytes);
@@ -415,7 +417,7 @@ int run_first(cfr_handle *h, cfr_device_batch *b, cudaStream_t s) {
   }
   if (h->params.dust) {
     StageScope sc(h, s, CFR_STAGE_DUST);
-    k_dust<<<grid_for(h, B.n_reads * B.mates, CFR_DUST_THREADS, 5), CFR_DUST_THREADS, CFR_DUST_SMEM, s>>>(B);
+    k_dust<<<grid_for(h, B.n_reads * B.mates, CFR_DUST_THREADS, 5), CFR_DUST_THREADS, CFR_DUST_SMEM, s>>>(B, h->P.quorum);
     ++h->launches;
   }
   CUDA_TRY(cudaMemsetAsync(B.task_counter, 0, 8, s));
@@ -874,9 +876,10 @@ int cfr_debug_dust(cfr_handle *h, const cfr_read_batch *in, char *masked1, char 
   B.dust_bits = (u32 *)dbits.p;
   const u64 len1 = in->off1[in->n_reads] - in->off1[0];
   const u64 len2 = in->seq2 ? in->off2[in->n_reads] - in->off2[0] : 0;
+  cudaMemsetAsync(b.scalars.p, 0, 64, h->stream);
   k_encode<<<grid_for(h, B.n_words, 256, 8), 256, 0, h->stream>>>(B, b.seq_bytes);
   if (in->n_reads)
-    k_dust<<<grid_for(h, B.n_reads * B.mates, CFR_DUST_THREADS, 5), CFR_DUST_THREADS, CFR_DUST_SMEM, h->stream>>>(B);
+    k_dust<<<grid_for(h, B.n_reads * B.mates, CFR_DUST_THREADS, 5), CFR_DUST_THREADS, CFR_DUST_SMEM, h->stream>>>(B, h->P.quorum);
   k_apply_dust<<<grid_for(h, b.seq_bytes, 256, 8), 256, 0, h->stream>>>(B, (unsigned char *)outb.p, b.seq_bytes);
   h->launches += 3;
   cudaError_t e = cudaGetLastError();

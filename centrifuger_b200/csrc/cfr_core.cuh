@@ -1126,11 +1126,12 @@ CFR_HD void dust_evict(DustStateT<SW> &d, const DustOut &out, int seg_off, int s
   }
 }
 
-// SDust on in[seg_off .. seg_off+n): masks into out
+// ---- SDust (Dustmasker.hpp:312-354) split into resumable pieces so that the
+// kernel can run it as a warp-synchronous state machine (cfr_pipeline.cuh) ----
+
+// start of SDust on a segment: clears the counters, primes the first two bases
 template <int SW>
-CFR_HD void dust_sdust(DustIn &in, int n, const DustOut &out, int seg_off, DustStateT<SW> &d) {
-  const int W = 64, T = 20;
-  if (n < 3) return;
+CFR_HD void dust_seg_init(DustIn &in, int seg_off, DustStateT<SW> &d, int &c1, int &c2) {
   for (int i = 0; i < 128; i += 4) {
     *reinterpret_cast<u32 *>(&d.cw[i]) = 0;
     *reinterpret_cast<u32 *>(&d.cv[i]) = 0;
@@ -1138,110 +1139,142 @@ CFR_HD void dust_sdust(DustIn &in, int n, const DustOut &out, int seg_off, DustS
   d.head = d.size = 0;
   d.rv = d.rw = d.lv = 0;
   d.p_valid = 0;
-  int c1 = in(seg_off), c2 = in(seg_off + 1);
-  int wfinish, wstart = 0;
-  for (wfinish = 2; wfinish < n; ++wfinish) {
-    wstart = 0;
-    if (wfinish + 1 > W) wstart = wfinish + 1 - W;
-    if (wstart > 0) dust_evict(d, out, seg_off, wstart - 1);
-    const int c3 = in(seg_off + wfinish);
-    const int t = c1 * 25 + c2 * 5 + c3;
-    c1 = c2;
-    c2 = c3;
-    // ShiftWindow (Dustmasker.hpp:106-136)
-    if (d.size >= W - 2) {
-      const int old = d.win[d.head];
-      const int cwo = --d.cw[old];
-      d.rw -= cwo;
-      d.head = (d.head + 1) & 63;
-      --d.size;
-      if (d.lv > d.size) {
-        const int cvo = --d.cv[old];
-        d.rv -= cvo;
-        --d.lv;
-      }
+  c1 = in(seg_off);
+  c2 = in(seg_off + 1);
+}
+
+CFR_HD int dust_wstart(int wfinish) { return wfinish + 1 > 64 ? wfinish + 1 - 64 : 0; }
+
+// one iteration of SDust's main loop up to the FindPerfect test (:330-340);
+// returns true when FindPerfect has to run for this position
+template <int SW>
+CFR_HD bool dust_step(DustIn &in, const DustOut &out, int seg_off, int wfinish, DustStateT<SW> &d, int &c1, int &c2) {
+  const int W = 64, T = 20;
+  const int wstart = dust_wstart(wfinish);
+  if (wstart > 0) dust_evict(d, out, seg_off, wstart - 1);
+  const int c3 = in(seg_off + wfinish);
+  const int t = c1 * 25 + c2 * 5 + c3;
+  c1 = c2;
+  c2 = c3;
+  // ShiftWindow (Dustmasker.hpp:106-136)
+  if (d.size >= W - 2) {
+    const int old = d.win[d.head];
+    const int cwo = --d.cw[old];
+    d.rw -= cwo;
+    d.head = (d.head + 1) & 63;
+    --d.size;
+    if (d.lv > d.size) {
+      const int cvo = --d.cv[old];
+      d.rv -= cvo;
+      --d.lv;
     }
-    d.win[(d.head + d.size) & 63] = (unsigned char)t;
-    ++d.size;
-    ++d.lv;
-    d.rw += d.cw[t];
-    ++d.cw[t];
-    const int cvt = d.cv[t];
-    d.rv += cvt;
-    d.cv[t] = (unsigned char)(cvt + 1);
-    if ((cvt + 1) * 10 > 2 * T) {
-      for (;;) {
-        const int s = dust_win_at(d, d.size - d.lv);
-        const int cvs = --d.cv[s];
-        d.rv -= cvs;
-        --d.lv;
-        if (s == t) break;
-      }
+  }
+  d.win[(d.head + d.size) & 63] = (unsigned char)t;
+  ++d.size;
+  ++d.lv;
+  d.rw += d.cw[t];
+  ++d.cw[t];
+  const int cvt = d.cv[t];
+  d.rv += cvt;
+  d.cv[t] = (unsigned char)(cvt + 1);
+  if ((cvt + 1) * 10 > 2 * T) {
+    for (;;) {
+      const int s = dust_win_at(d, d.size - d.lv);
+      const int cvs = --d.cv[s];
+      d.rv -= cvs;
+      --d.lv;
+      if (s == t) break;
     }
-    if (d.rw * 10 > d.lv * T) {  // FindPerfect (Dustmasker.hpp:173-242)
-      int rv = d.rv;
-      int max_score = 0, max_cnt = 1;
-      int folded = wstart + d.size;  // starts >= folded have been folded into (max_score, max_cnt)
-      for (int i = d.size - d.lv - 1; i >= 0; --i) {
-        const int tt = dust_win_at(d, i);
-        rv += d.cv[tt];
-        ++d.cv[tt];
-        const int span = d.size - i - 1;
-        if (rv * 10 > T * span) {
-          const int start = i + wstart;
-          while (folded > start) {  // the scan of P from its head (:203-211)
-            --folded;
-            const int slot = folded & 63;
-            if ((d.p_valid >> slot) & 1ull) {
-              if ((u64)d.p_score[slot] * (u64)max_cnt > (u64)max_score * (u64)d.p_span[slot]) {
-                max_score = d.p_score[slot];
-                max_cnt = d.p_span[slot];
-              }
-            }
-          }
-          if (rv * max_cnt >= max_score * span) {
-            max_score = rv;
-            max_cnt = span;
-            const int slot = start & 63;
-            d.p_score[slot] = (unsigned short)rv;
-            d.p_span[slot] = (unsigned char)span;
-            d.p_len[slot] = (unsigned char)(wstart + d.size + 1 - start);
-            d.p_valid |= 1ull << slot;
+  }
+  return d.rw * 10 > d.lv * T;
+}
+
+// FindPerfect (Dustmasker.hpp:173-242) over the per-start slots
+template <int SW>
+CFR_HD void dust_find_perfect(int wfinish, DustStateT<SW> &d) {
+  const int T = 20;
+  const int wstart = dust_wstart(wfinish);
+  int rv = d.rv;
+  int max_score = 0, max_cnt = 1;
+  int folded = wstart + d.size;  // starts >= folded have been folded into (max_score, max_cnt)
+  for (int i = d.size - d.lv - 1; i >= 0; --i) {
+    const int tt = dust_win_at(d, i);
+    rv += d.cv[tt];
+    ++d.cv[tt];
+    const int span = d.size - i - 1;
+    if (rv * 10 > T * span) {
+      const int start = i + wstart;
+      while (folded > start) {  // the scan of P from its head (:203-211)
+        --folded;
+        const int slot = folded & 63;
+        if ((d.p_valid >> slot) & 1ull) {
+          if ((u64)d.p_score[slot] * (u64)max_cnt > (u64)max_score * (u64)d.p_span[slot]) {
+            max_score = d.p_score[slot];
+            max_cnt = d.p_span[slot];
           }
         }
       }
-      for (int i = d.size - d.lv - 1; i >= 0; --i) --d.cv[dust_win_at(d, i)];
+      if (rv * max_cnt >= max_score * span) {
+        max_score = rv;
+        max_cnt = span;
+        const int slot = start & 63;
+        d.p_score[slot] = (unsigned short)rv;
+        d.p_span[slot] = (unsigned char)span;
+        d.p_len[slot] = (unsigned char)(wstart + d.size + 1 - start);
+        d.p_valid |= 1ull << slot;
+      }
     }
   }
-  // the tail loop of Dustmasker.hpp:343-350 saves every remaining start
-  int base = 0;
-  if (wfinish + 1 > W) base = wfinish + 1 - W;
-  if (base > 0) --base;  // the last in-loop save ran with wstart(n-1) = base - 1 ... so start base-1 may remain
-  if (d.p_valid)
-    for (int s2 = base; s2 < base + 64; ++s2) dust_evict(d, out, seg_off, s2);  // every slot exactly once
+  for (int i = d.size - d.lv - 1; i >= 0; --i) --d.cv[dust_win_at(d, i)];
 }
 
-// Dustmasker::MaskWithBuffer + the in-place masking of CentrifugerClass.cpp:281-289.
+// the tail loop of Dustmasker.hpp:343-350 (n = segment length): saves every remaining start
+template <int SW>
+CFR_HD void dust_seg_tail(const DustOut &out, int seg_off, int n, DustStateT<SW> &d) {
+  if (!d.p_valid) return;
+  int base = dust_wstart(n);
+  if (base > 0) --base;  // the last in-loop save ran with wstart(n-1): start base-1 may remain
+  for (int s2 = base; s2 < base + 64; ++s2) dust_evict(d, out, seg_off, s2);  // every slot exactly once
+}
+
+// MaskWithBuffer's segment finder (Dustmasker.hpp:369-401): starting at cursor i,
+// the next run [i, last_valid] to hand to SDust, and the cursor after it
+CFR_HD void dust_next_segment(DustIn &in, int n, int i, int &last_valid, int &next_i) {
+  const int W = 64;
+  int n_count = 0, j;
+  last_valid = i;
+  for (j = i; j < n; ++j) {
+    if (in(j) == 4)
+      ++n_count;
+    else {
+      if (n_count > W) break;
+      last_valid = j;
+      n_count = 0;
+    }
+  }
+  next_i = j;
+}
+
+// Dustmasker::MaskWithBuffer + the in-place masking of CentrifugerClass.cpp:281-289,
+// sequential form (host simulation / reference for the state machine).
 // `in` is the mate as uploaded, `out` the working N mask the searches read.
 template <int SW>
 CFR_HD void dust_task(DustIn &in, int n, const DustOut &out, DustStateT<SW> &d) {
-  const int W = 64;
   if (n < 3) return;
   int i = 0;
   while (i < n && in(i) == 4) ++i;
   while (i < n) {
-    int n_count = 0, last_valid = i, j;
-    for (j = i; j < n; ++j) {
-      if (in(j) == 4)
-        ++n_count;
-      else {
-        if (n_count > W) break;
-        last_valid = j;
-        n_count = 0;
-      }
+    int last_valid, next_i;
+    dust_next_segment(in, n, i, last_valid, next_i);
+    const int seg_n = last_valid - i + 1;
+    if (last_valid > i && seg_n >= 3) {
+      int c1, c2;
+      dust_seg_init(in, i, d, c1, c2);
+      for (int wfinish = 2; wfinish < seg_n; ++wfinish)
+        if (dust_step(in, out, i, wfinish, d, c1, c2)) dust_find_perfect(wfinish, d);
+      dust_seg_tail(out, i, seg_n, d);
     }
-    if (last_valid > i) dust_sdust(in, last_valid - i + 1, out, i, d);
-    i = j;
+    i = next_i;
   }
 }
 

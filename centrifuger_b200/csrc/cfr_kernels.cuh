@@ -40,15 +40,13 @@ __global__ void k_apply_dust(const __grid_constant__ ChunkDev B, unsigned char *
 // ring live in shared memory, one bank column per thread (80 words x 128 threads
 // = 40 KiB per block), so their updates are conflict-free single wavefronts.
 enum { CFR_DUST_THREADS = 128, CFR_DUST_SMEM = 80 * CFR_DUST_THREADS * 4 };
-__global__ void __launch_bounds__(CFR_DUST_THREADS) k_dust(const __grid_constant__ ChunkDev B) {
+__global__ void __launch_bounds__(CFR_DUST_THREADS) k_dust(const __grid_constant__ ChunkDev B, const int quorum) {
   extern __shared__ u32 dust_sm[];
   DustStateT<CFR_DUST_THREADS> d;
   d.cw.base = reinterpret_cast<unsigned char *>(&dust_sm[threadIdx.x]);
   d.cv.base = reinterpret_cast<unsigned char *>(&dust_sm[32 * CFR_DUST_THREADS + threadIdx.x]);
   d.win.base = reinterpret_cast<unsigned char *>(&dust_sm[64 * CFR_DUST_THREADS + threadIdx.x]);
-  const u64 ntask = B.n_reads * (u64)B.mates;
-  const u64 stride = (u64)gridDim.x * blockDim.x;
-  for (u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x; t < ntask; t += stride) dust_stage(B, t, d);
+  dust_tasks(B, B.n_reads * (u64)B.mates, d, quorum);  // mates are claimed dynamically from B.dust_counter
 }
 
 template <class Bwt>

@@ -39,6 +39,7 @@ struct ChunkDev {
   u64 *arena_used;
   u64 *task_counter;  // next strand task (dynamic fetch by the search warps)
   u64 *row_counter;   // next arena row (dynamic fetch by the locate warps)
+  u64 *dust_counter;  // next mate (dynamic fetch by the DUST warps)
   u64 *rows;
   u32 *seq_ids;
   SeqRec *rec0, *rec1;
@@ -57,58 +58,7 @@ struct ChunkDev {
 
 CFR_HD u64 chunk_read_id(const ChunkDev &B, u64 t) { return B.read_list ? (u64)B.read_list[t] : t; }
 
-// ------------------------------------------------------------------ encode
-// word w of the batch buffer: 32 uploaded bytes -> 2-bit codes + N bits
-CFR_HD void encode_stage(const ChunkDev &B, u64 w, u64 total_bytes) {
-  const u64 b0 = w * 32;
-  const int n = b0 + 32 <= total_bytes ? 32 : (b0 < total_bytes ? (int)(total_bytes - b0) : 0);
-  // two aligned 16-byte loads (the buffer is padded past total_bytes), then bytes from registers
-  const u64x2 v0 = ld128(reinterpret_cast<const u64x2 *>(B.seq_raw + b0));
-  const u64x2 v1 = ld128(reinterpret_cast<const u64x2 *>(B.seq_raw + b0) + 1);
-  const u64 q[4] = {v0.x, v0.y, v1.x, v1.y};
-  u64 codes = 0;
-  u32 nm = 0;
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-  for (int i = 0; i < 32; ++i) {
-    const int c = base_code((unsigned char)(q[i >> 3] >> ((i & 7) * 8)));
-    if (c > 3) nm |= 1u << i; else codes |= (u64)c << (2 * i);
-  }
-  if (n < 32) {  // padding reads as N
-    const u32 keep = n == 0 ? 0u : ((1u << n) - 1u);
-    nm |= ~keep;
-    codes &= n == 0 ? 0ull : ((1ull << (2 * n)) - 1ull);
-  }
-  B.codes[w] = codes;
-  B.mask_raw[w] = nm;
-  if (B.mask != B.mask_raw) B.mask[w] = nm;
-  if (B.dust_bits) B.dust_bits[w] = 0;
-}
-
-// ------------------------------------------------------------------ dust
-template <int SW>
-CFR_HD void dust_stage(const ChunkDev &B, u64 task, DustStateT<SW> &d) {
-  const u64 read = task / (u64)B.mates;
-  const int mate = (int)(task % (u64)B.mates);
-  const u64 base = B.off[mate][read] - B.off_bias[mate];
-  const int len = (int)(B.off[mate][read + 1] - B.off[mate][read]);
-  DustIn in{B.codes, B.mask_raw, base};
-  const DustOut out{B.mask, B.dust_bits, base};
-  dust_task(in, len, out, d);
-}
-
-// ------------------------------------------------------------------ search
-// task = read * (2*mates) + mate*2 + s, s = 1: the mate as read (strandHits[1]),
-// s = 0: its reverse complement (strandHits[0]).
-//
-// GetHitsFromRead + BackwardSearch (Classifier.hpp:274-293, FMIndex.hpp:388-422,
-// 487-510) as a warp-synchronous state machine.  Every iteration the lanes that
-// are inside a search do ONE BackwardExtend together (straight-line code).  The
-// rare events -- closing a search (record the hit, skip the mismatching base),
-// starting the next one (lookup-table probe of the last W bases) and fetching the
-// next task -- are deferred until a quorum of lanes is waiting for them (or nobody
-// can extend), so that block runs with many lanes instead of one or two.
+// ---- warp-level helpers shared by the state-machine stages ----
 #if defined(__CUDA_ARCH__)
 #define CFR_BALLOT(pred) __ballot_sync(0xffffffffu, (pred))
 #else
@@ -141,6 +91,141 @@ CFR_HD u64 warp_claim(u64 *counter, bool want) {
 #endif
 }
 
+
+// ------------------------------------------------------------------ encode
+// word w of the batch buffer: 32 uploaded bytes -> 2-bit codes + N bits
+CFR_HD void encode_stage(const ChunkDev &B, u64 w, u64 total_bytes) {
+  const u64 b0 = w * 32;
+  const int n = b0 + 32 <= total_bytes ? 32 : (b0 < total_bytes ? (int)(total_bytes - b0) : 0);
+  // two aligned 16-byte loads (the buffer is padded past total_bytes), then bytes from registers
+  const u64x2 v0 = ld128(reinterpret_cast<const u64x2 *>(B.seq_raw + b0));
+  const u64x2 v1 = ld128(reinterpret_cast<const u64x2 *>(B.seq_raw + b0) + 1);
+  const u64 q[4] = {v0.x, v0.y, v1.x, v1.y};
+  u64 codes = 0;
+  u32 nm = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int i = 0; i < 32; ++i) {
+    const int c = base_code((unsigned char)(q[i >> 3] >> ((i & 7) * 8)));
+    if (c > 3) nm |= 1u << i; else codes |= (u64)c << (2 * i);
+  }
+  if (n < 32) {  // padding reads as N
+    const u32 keep = n == 0 ? 0u : ((1u << n) - 1u);
+    nm |= ~keep;
+    codes &= n == 0 ? 0ull : ((1ull << (2 * n)) - 1ull);
+  }
+  B.codes[w] = codes;
+  B.mask_raw[w] = nm;
+  if (B.mask != B.mask_raw) B.mask[w] = nm;
+  if (B.dust_bits) B.dust_bits[w] = 0;
+}
+
+// ------------------------------------------------------------------ dust
+// SDUST over all mates of the chunk as a warp-synchronous state machine: lanes in
+// STEP advance their window by one base together; FindPerfect (long, data
+// dependent, needed by a minority of positions) and the per-mate set-up run when a
+// quorum of lanes waits for them.  Mates are claimed dynamically.
+enum { CFR_DS_FETCH = 0, CFR_DS_SEG = 1, CFR_DS_STEP = 2, CFR_DS_FP = 3, CFR_DS_DONE = 4 };
+
+template <int SW>
+CFR_HD void dust_tasks(const ChunkDev &B, const u64 ntask, DustStateT<SW> &d, const int quorum) {
+  DustIn in{B.codes, B.mask_raw, 0};
+  DustOut out{B.mask, B.dust_bits, 0};
+  int st = CFR_DS_FETCH;
+  int len = 0, cursor = 0, seg_off = 0, seg_n = 0, wfinish = 0, c1 = 0, c2 = 0;
+  for (;;) {
+    const u32 m_step = CFR_BALLOT(st == CFR_DS_STEP);
+    const u32 m_fp = CFR_BALLOT(st == CFR_DS_FP);
+    const u32 m_trn = CFR_BALLOT(st == CFR_DS_FETCH || st == CFR_DS_SEG);
+    if ((m_step | m_fp | m_trn) == 0) break;
+    if (m_trn != 0 && ((m_step | m_fp) == 0 || popc32(m_trn) >= quorum)) {
+      for (int tries = 0; tries < 3; ++tries) {
+        if (CFR_BALLOT(st == CFR_DS_FETCH || st == CFR_DS_SEG) == 0) break;
+        const u64 claimed = warp_claim<1>(B.dust_counter, st == CFR_DS_FETCH);
+        if (st == CFR_DS_FETCH) {
+          if (claimed >= ntask) {
+            st = CFR_DS_DONE;
+          } else {
+            const u64 read = claimed / (u64)B.mates;
+            const int mate = (int)(claimed % (u64)B.mates);
+            const u64 base = B.off[mate][read] - B.off_bias[mate];
+            len = (int)(B.off[mate][read + 1] - B.off[mate][read]);
+            in.base = base;
+            in.widx = ~0ull;
+            out.base = base;
+            if (len >= 3) {  // MaskWithBuffer: skip the leading Ns (Dustmasker.hpp:365-367)
+              cursor = 0;
+              while (cursor < len && in(cursor) == 4) ++cursor;
+              st = CFR_DS_SEG;
+            }
+          }
+        }
+        if (st == CFR_DS_SEG) {
+          if (cursor >= len) {
+            st = CFR_DS_FETCH;
+          } else {
+            int last_valid, next_i;
+            dust_next_segment(in, len, cursor, last_valid, next_i);
+            seg_off = cursor;
+            seg_n = last_valid - cursor + 1;
+            cursor = next_i;
+            if (last_valid > seg_off && seg_n >= 3) {
+              dust_seg_init(in, seg_off, d, c1, c2);
+              wfinish = 2;
+              st = CFR_DS_STEP;
+            }
+          }
+        }
+      }
+    }
+    bool advance = false;
+    if (m_fp != 0 && (m_step == 0 || popc32(m_fp) >= quorum)) {
+      if (st == CFR_DS_FP) {
+        dust_find_perfect(wfinish, d);
+        advance = true;
+      }
+    }
+    if (st == CFR_DS_STEP) {
+      if (dust_step(in, out, seg_off, wfinish, d, c1, c2))
+        st = CFR_DS_FP;
+      else
+        advance = true;
+    }
+    if (advance) {
+      ++wfinish;
+      st = CFR_DS_STEP;
+      if (wfinish >= seg_n) {
+        dust_seg_tail(out, seg_off, seg_n, d);
+        st = CFR_DS_SEG;
+      }
+    }
+  }
+}
+
+// sequential form: one mate (host-side diagnostics)
+template <int SW>
+CFR_HD void dust_stage(const ChunkDev &B, u64 task, DustStateT<SW> &d) {
+  const u64 read = task / (u64)B.mates;
+  const int mate = (int)(task % (u64)B.mates);
+  const u64 base = B.off[mate][read] - B.off_bias[mate];
+  const int len = (int)(B.off[mate][read + 1] - B.off[mate][read]);
+  DustIn in{B.codes, B.mask_raw, base};
+  const DustOut out{B.mask, B.dust_bits, base};
+  dust_task(in, len, out, d);
+}
+
+// ------------------------------------------------------------------ search
+// task = read * (2*mates) + mate*2 + s, s = 1: the mate as read (strandHits[1]),
+// s = 0: its reverse complement (strandHits[0]).
+//
+// GetHitsFromRead + BackwardSearch (Classifier.hpp:274-293, FMIndex.hpp:388-422,
+// 487-510) as a warp-synchronous state machine.  Every iteration the lanes that
+// are inside a search do ONE BackwardExtend together (straight-line code).  The
+// rare events -- closing a search (record the hit, skip the mismatching base),
+// starting the next one (lookup-table probe of the last W bases) and fetching the
+// next task -- are deferred until a quorum of lanes is waiting for them (or nobody
+// can extend), so that block runs with many lanes instead of one or two.
 enum { CFR_ST_EXTEND = 0, CFR_ST_CLOSE = 1, CFR_ST_FETCH = 2, CFR_ST_DONE = 3 };
 
 template <class Bwt>

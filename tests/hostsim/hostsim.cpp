@@ -263,8 +263,9 @@ int hostsim_classify(void *hh, int dust, uint64_t arena_rows, const cfr_read_bat
   OpCount oc{};
   static DustState ds;
   for (u64 w = 0; w < n_words; ++w) encode_stage(B, w, len1 + len2);
-  if (dust)
-    for (u64 t = 0; t < n * mates; ++t) dust_stage(B, t, ds);
+  u64 dust_counter = 0;
+  B.dust_counter = &dust_counter;
+  if (dust) dust_tasks(B, n * mates, ds, P.quorum);
   u64 task_counter = 0, row_counter = 0;
   B.task_counter = &task_counter;
   B.row_counter = &row_counter;
