@@ -45,14 +45,14 @@ def build(force=False, verbose=False):
     if force or _stale(LIB, deps):
         cmd = [_nvcc()] + NVCC_FLAGS + ["-shared", "-o", LIB,
                                         os.path.join(CSRC, "cfr_api.cu"),
-                                        os.path.join(CSRC, "cfr_format.cpp"), "-lcudart"]
+                                        os.path.join(CSRC, "cfr_format.cpp")]  # cudart is linked statically (nvcc default)
         if verbose:
             print(" ".join(cmd))
         subprocess.check_call(cmd)
     main_cpp = os.path.join(CSRC, "cfr_main.cpp")
     if os.path.exists(main_cpp) and (force or _stale(CLI, deps + [LIB])):
-        cmd = [_nvcc(), "-std=c++17", "-O2", "-o", CLI, main_cpp, "-L" + HERE, "-lcfrb200",
-               "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN", "-lz", "-lpthread"]
+        cmd = ["g++", "-std=c++17", "-O2", "-Wall", "-o", CLI, main_cpp, "-L" + HERE, "-lcfrb200",
+               "-Wl,-rpath,$ORIGIN", "-lz", "-lpthread"]  # host-only C++: no CUDA code in the CLI
         if verbose:
             print(" ".join(cmd))
         subprocess.check_call(cmd)

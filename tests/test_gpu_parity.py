@@ -221,3 +221,27 @@ def test_single_huge_read_overflows_loudly(tiny_dir):
         g.classify(r1)
     assert e.value.code == -7
     g.close()
+
+
+# ---------------------------------------------------------------- drop-in CLI
+def test_cli_binary_reproduces_reference_tsv(tiny_dir, manifest):
+    """centrifuger-b200 (host C++ over the C ABI) prints the reference's TSV byte for byte"""
+    import subprocess
+    exe = os.path.join(os.path.dirname(cb.LIB_PATH), "centrifuger-b200")
+    assert os.path.exists(exe), "run python -m centrifuger_b200.build"
+    for name in ("idx__pe__default", "idx__se__k5", "idx__edgepe__k3_hitk2", "idx_b8__edge__default",
+                 "idx__edge__mhl16_nodust"):
+        m = manifest["tiny"][name]
+        files = [os.path.join(tiny_dir, f) for f in m["files"]]
+        cmd = [exe, "-x", os.path.join(tiny_dir, m["index"]), "-t", "4", "--batch", "97"]
+        cmd += ["-u", files[0]] if len(files) == 1 else ["-1", files[0], "-2", files[1]]
+        r = subprocess.run(cmd + m["args"], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+        assert r.returncode == 0, r.stderr.decode()
+        assert r.stdout.decode() == open(golden_path("tiny", "expected", name + ".tsv")).read(), name
+        err = r.stderr.decode()
+        assert "Finishes loading index." in err and "can be classified." in err
+    # no arguments: usage on stderr, exit 0 (the reference's CI depends on it)
+    r = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert r.returncode == 0 and b"-x FILE: index prefix" in r.stderr
+    r = subprocess.run([exe, "-v"], stdout=subprocess.PIPE)
+    assert r.stdout.decode().strip() == "Centrifuger v1.1.3-r347"
