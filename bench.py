@@ -265,23 +265,21 @@ def main():
     ids_host = torch.empty(max(1, n * w["k"]), dtype=torch.int64).pin_memory()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
 
-    tax_ptr, tax_n = clf.taxon_counts_device()
-
-    class _Wrap:  # exposes the library's HBM counter vector to torch for the NCCL all-reduce
-        __cuda_array_interface__ = {"shape": (tax_n,), "typestr": "<i8", "data": (tax_ptr, False), "version": 2}
-    tax_tensor = torch.as_tensor(_Wrap(), device="cuda") if world > 1 else None
+    from centrifuger_b200 import distributed as cdist
+    # the library's per-taxon counter vector in HBM, aliased as a torch tensor for the NCCL all-reduce
+    tax_tensor = cdist.device_counts_tensor(clf) if world > 1 else None
 
     batch = clf.upload(p_seq1, p_off1, p_seq2, p_off2, stream=sptr)
 
     def step_resident():
         clf.classify_resident(batch, stream=sptr)
         if world > 1:
-            dist.all_reduce(tax_tensor)
+            cdist.allreduce_counts(tax_tensor)
 
     def step_e2e():
         clf.classify_packed(p_seq1, p_off1, p_seq2, p_off2, stream=sptr, out=(res_host, ids_host))
         if world > 1:
-            dist.all_reduce(tax_tensor)
+            cdist.allreduce_counts(tax_tensor)
 
     def sync_all():
         if world > 1:
