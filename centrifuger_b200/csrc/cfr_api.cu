@@ -89,7 +89,16 @@ struct cfr_handle {
   DevCounters *d_counters = nullptr;
   u64 launches = 0;
   u64 host_bases = 0;
-  cfr_device_batch scratch;  // reused by cfr_classify_batch
+  // cfr_classify_batch pipeline: two chunk slots, H2D / compute / D2H on three streams
+  cfr_device_batch slots[2];
+  cudaStream_t s_in = nullptr, s_out = nullptr;
+  cudaEvent_t ev_start = nullptr, ev_h2d[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr},
+              ev_d2h[2] = {nullptr, nullptr};
+  struct PinnedScalars {
+    u64 used;
+    u32 n_def;
+    u32 pad;
+  } *pinned_scalars = nullptr;  // [2], cudaHostAlloc
   // stage profiling (CUDA events on the launch stream)
   bool profile = false;
   struct EvPair {
@@ -550,7 +559,17 @@ int cfr_open(const char *idx_prefix, const cfr_params *p, int device, cfr_handle
 void cfr_close(cfr_handle *h) {
   if (!h) return;
   cudaSetDevice(h->device);
-  h->scratch.release();
+  h->slots[0].release();
+  h->slots[1].release();
+  if (h->s_in) cudaStreamDestroy(h->s_in);
+  if (h->s_out) cudaStreamDestroy(h->s_out);
+  if (h->ev_start) cudaEventDestroy(h->ev_start);
+  for (int i = 0; i < 2; ++i) {
+    if (h->ev_h2d[i]) cudaEventDestroy(h->ev_h2d[i]);
+    if (h->ev_comp[i]) cudaEventDestroy(h->ev_comp[i]);
+    if (h->ev_d2h[i]) cudaEventDestroy(h->ev_d2h[i]);
+  }
+  if (h->pinned_scalars) cudaFreeHost(h->pinned_scalars);
   for (void *p : h->index_allocs) cudaFree(p);
   for (auto &e : h->ev_pending) {
     cudaEventDestroy(e.a);
@@ -633,21 +652,84 @@ void cfr_batch_free(cfr_handle *h, cfr_device_batch *b) {
   delete b;
 }
 
+// Host <-> device copies overlap the kernels: the batch is cut into chunks that go
+// through two slots; chunk c's H2D (stream s_in), kernels (the caller's stream) and
+// D2H (stream s_out) are chained with events, so while chunk c computes, chunk c+1
+// uploads and chunk c-1 downloads.  Pinned host buffers are needed for real overlap.
+static int pipeline_init(cfr_handle *h) {
+  if (h->s_in) return CFR_OK;
+  CUDA_TRY(cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
+  CUDA_TRY(cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
+  CUDA_TRY(cudaEventCreateWithFlags(&h->ev_start, cudaEventDisableTiming));
+  for (int i = 0; i < 2; ++i) {
+    CUDA_TRY(cudaEventCreateWithFlags(&h->ev_h2d[i], cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&h->ev_comp[i], cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&h->ev_d2h[i], cudaEventDisableTiming));
+  }
+  CUDA_TRY(cudaHostAlloc((void **)&h->pinned_scalars, 2 * sizeof(*h->pinned_scalars), cudaHostAllocDefault));
+  return CFR_OK;
+}
+
+// wait for a chunk's results; run the (rare) follow-up passes for reads that did not fit the arena
+static int pipeline_drain(cfr_handle *h, int slot, cfr_result *results, uint64_t *ids, cudaStream_t sc) {
+  cfr_device_batch *b = &h->slots[slot];
+  CUDA_TRY(cudaEventSynchronize(h->ev_d2h[slot]));
+  if (h->pinned_scalars[slot].n_def != 0) {
+    int st = h->layout == CFR_LAYOUT_OCCLINE ? finish_deferred<BwtOccLine, BwtOccLine>(h, b, sc)
+                                             : finish_deferred<BwtRunBlock, BwtRunBlock>(h, b, sc);
+    if (st) return st;
+    CUDA_TRY(cudaMemcpyAsync(results, b->results.p, b->n_reads * sizeof(DevResult), cudaMemcpyDeviceToHost, sc));
+    CUDA_TRY(cudaMemcpyAsync(ids, b->out_ids.p, b->n_reads * (u64)h->P.max_result * 8, cudaMemcpyDeviceToHost, sc));
+    CUDA_TRY(cudaStreamSynchronize(sc));
+  }
+  return CFR_OK;
+}
+
 int cfr_classify_batch(cfr_handle *h, const cfr_read_batch *in, cfr_result *results, uint64_t *ids, void *stream) {
   if (!h || !in || (in->n_reads && (!results || !ids))) return fail(CFR_ERR_ARG, "null argument");
   if (in->n_reads && (!in->seq1 || !in->off1)) return fail(CFR_ERR_ARG, "seq1/off1 missing");
+  if (in->n_reads == 0) return CFR_OK;
   CUDA_TRY(cudaSetDevice(h->device));
-  cudaStream_t s = pick_stream(h, stream);
-  const u64 chunk = h->params.max_batch_reads > 0 ? (u64)h->params.max_batch_reads : (1ull << 20);
-  cfr_device_batch *b = &h->scratch;
-  for (u64 r0 = 0; r0 < in->n_reads; r0 += chunk) {
+  cudaStream_t sc = pick_stream(h, stream);
+  int st = pipeline_init(h);
+  if (st) return st;
+  const u64 cap = h->params.max_batch_reads > 0 ? (u64)h->params.max_batch_reads : (1ull << 20);
+  // at least 4 chunks once the batch is large enough for the copies to matter
+  u64 chunk = std::min<u64>(cap, std::max<u64>(1u << 16, (in->n_reads + 3) / 4));
+  if (h->params.max_batch_reads > 0) chunk = std::min<u64>(chunk, cap);
+  const u64 k = (u64)h->P.max_result;
+  CUDA_TRY(cudaEventRecord(h->ev_start, sc));  // everything below is ordered after the caller's stream
+  CUDA_TRY(cudaStreamWaitEvent(h->s_in, h->ev_start, 0));
+  u64 starts[2] = {0, 0};
+  u64 c = 0;
+  for (u64 r0 = 0; r0 < in->n_reads; r0 += chunk, ++c) {
+    const int slot = (int)(c & 1);
     const u64 r1 = std::min<u64>(in->n_reads, r0 + chunk);
-    int st = upload_chunk(h, in, r0, r1, b, s);
-    if (st) return st;
-    if ((st = cfr_classify_resident(h, b, s))) return st;
-    if ((st = cfr_batch_fetch(h, b, results + r0, ids + r0 * (u64)h->P.max_result, s))) return st;
+    cfr_device_batch *b = &h->slots[slot];
+    if (c >= 2) {  // the slot's previous chunk must have left the device before its buffers are reused
+      if ((st = pipeline_drain(h, slot, results + starts[slot], ids + starts[slot] * k, sc))) return st;
+    }
+    starts[slot] = r0;
+    if ((st = upload_chunk(h, in, r0, r1, b, h->s_in))) return st;
+    CUDA_TRY(cudaEventRecord(h->ev_h2d[slot], h->s_in));
+    CUDA_TRY(cudaStreamWaitEvent(sc, h->ev_h2d[slot], 0));
+    if ((st = cfr_classify_resident(h, b, sc))) return st;
+    CUDA_TRY(cudaEventRecord(h->ev_comp[slot], sc));
+    CUDA_TRY(cudaStreamWaitEvent(h->s_out, h->ev_comp[slot], 0));
+    CUDA_TRY(cudaMemcpyAsync(results + r0, b->results.p, (r1 - r0) * sizeof(DevResult), cudaMemcpyDeviceToHost, h->s_out));
+    CUDA_TRY(cudaMemcpyAsync(ids + r0 * k, b->out_ids.p, (r1 - r0) * k * 8, cudaMemcpyDeviceToHost, h->s_out));
+    CUDA_TRY(cudaMemcpyAsync(&h->pinned_scalars[slot], b->scalars.p, 16, cudaMemcpyDeviceToHost, h->s_out));
+    CUDA_TRY(cudaEventRecord(h->ev_d2h[slot], h->s_out));
+    // the next upload into the OTHER slot may start at once; an upload into THIS slot (chunk c+2)
+    // is issued only after pipeline_drain() above has seen ev_d2h[slot]
   }
-  return CFR_OK;
+  // drain the last (up to two) chunks in order
+  for (u64 d = c >= 2 ? c - 2 : 0; d < c; ++d) {
+    const int slot = (int)(d & 1);
+    if ((st = pipeline_drain(h, slot, results + starts[slot], ids + starts[slot] * k, sc))) return st;
+  }
+  CUDA_TRY(cudaStreamSynchronize(sc));
+  return check_device_errors(h, sc);
 }
 
 const char *cfr_seq_name(const cfr_handle *h, uint64_t seq_id) {

@@ -176,6 +176,11 @@ def test_deferral_chunking_and_resident_api(small_dir, layout):
     res, ids = g.classify(r1, r2)
     assert _tuples(res, ids, 5) == base
     g.close()
+    # small chunks AND a tiny arena: the copy/compute pipeline with follow-up passes in its drain step
+    g = cb.Classifier(idx, layout=layout, k=5, max_batch_reads=601, arena_rows=900)
+    res, ids = g.classify(r1, r2)
+    assert _tuples(res, ids, 5) == base
+    g.close()
     # small device chunks
     g = cb.Classifier(idx, layout=layout, k=5, max_batch_reads=777)
     res, ids = g.classify(r1, r2)
