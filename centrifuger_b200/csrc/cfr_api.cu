@@ -85,6 +85,7 @@ struct cfr_handle {
   std::vector<void *> index_allocs;
   size_t hbm_bytes = 0;
   int sm_count = 148;
+  int search_blocks = 10;  // resident 128-thread blocks per SM targeted by k_search (CFR_B200_SEARCH_BLOCKS)
   u64 *d_taxon = nullptr;
   DevCounters *d_counters = nullptr;
   u64 launches = 0;
@@ -233,7 +234,7 @@ int upload_index(cfr_handle *h) {
 }
 
 int build_occ_lines(cfr_handle *h) {
-  const u64 n_lines = h->ix.n / 128 + 1;
+  const u64 n_lines = h->ix.n / 64 + 1;
   void *p;
   int st = dev_alloc(h, &p, n_lines * sizeof(OccLine));
   if (st) return st;
@@ -432,7 +433,11 @@ int run_first(cfr_handle *h, cfr_device_batch *b, cudaStream_t s) {
   CUDA_TRY(cudaMemsetAsync(B.task_counter, 0, 8, s));
   {
     StageScope sc(h, s, CFR_STAGE_SEARCH);
-    k_search<BwtWide><<<grid_for(h, B.n_reads * 2 * B.mates * BwtWide::LANES, 128, 16), 128, 0, s>>>(h->ix, h->P, B);
+    const int g = grid_for(h, B.n_reads * 2 * B.mates, 128, h->search_blocks);
+    if (h->search_blocks >= 16) k_search<BwtWide, 16><<<g, 128, 0, s>>>(h->ix, h->P, B);
+    else if (h->search_blocks >= 12) k_search<BwtWide, 12><<<g, 128, 0, s>>>(h->ix, h->P, B);
+    else if (h->search_blocks >= 10) k_search<BwtWide, 10><<<g, 128, 0, s>>>(h->ix, h->P, B);
+    else k_search<BwtWide, 8><<<g, 128, 0, s>>>(h->ix, h->P, B);
     ++h->launches;
   }
   CUDA_TRY(cudaGetLastError());
@@ -535,6 +540,7 @@ int cfr_open(const char *idx_prefix, const cfr_params *p, int device, cfr_handle
   h->P.secondary_factor = params.consider_secondary_score_factor;
   h->P.quorum = 8;
   if (const char *e = getenv("CFR_B200_QUORUM")) h->P.quorum = std::max(1, atoi(e));
+  if (const char *e = getenv("CFR_B200_SEARCH_BLOCKS")) h->search_blocks = std::max(1, atoi(e));
   if ((st = upload_index(h))) return bail(st);
   void *p2;
   if ((st = dev_alloc(h, &p2, (h->ix.node_cnt + 3) * 8))) return bail(st);
@@ -547,8 +553,12 @@ int cfr_open(const char *idx_prefix, const cfr_params *p, int device, cfr_handle
   if (params.layout == CFR_LAYOUT_AUTO) {
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
-    const u64 need = (h->ix.n / 128 + 1) * sizeof(OccLine);
+    const u64 need = (h->ix.n / 64 + 1) * sizeof(OccLine);
     if ((u64)free_b < need + (8ull << 30)) h->layout = CFR_LAYOUT_RUNBLOCK;  // keep 8 GiB for work areas
+  }
+  if (h->layout == CFR_LAYOUT_OCCLINE && h->ix.n >= (1ull << 40)) {  // 40-bit sector counters
+    if (params.layout == CFR_LAYOUT_OCCLINE) return bail(fail(CFR_ERR_UNSUPPORTED, "occ-sector layout needs n < 2^40"));
+    h->layout = CFR_LAYOUT_RUNBLOCK;
   }
   if (h->layout == CFR_LAYOUT_OCCLINE && (st = build_occ_lines(h))) return bail(st);
   h->file.map1.close();  // everything needed from .1.cfr now lives in HBM

@@ -345,34 +345,47 @@ struct BwtRunBlock {
 // Layout 2: 64-byte occ lines (128 symbols + 4 absolute counters per line)
 // ---------------------------------------------------------------------------
 
-// occ(c, x) = # of symbol c in BWT[0..x), x in [0, n].  One rank touches the
-// symbol's counter word (8 B) and the plane pair of ONE 64-symbol half (16 B):
-//   word w = cnt[c]: bits 0..55  # of c before the line
-//                    bits 56..62 # of c in the line's first half
+// occ(c, x) = # of symbol c in BWT[0..x), x in [0, n]: ONE 32-byte sector.
 struct OccRank {
-  u64 count;   // occ(c, x)
-  u64x2 half;  // {lo, hi} planes of the half that holds position x
+  u64 count;  // occ(c, x)
+  u64 lo, hi; // planes of the sector that holds position x
 };
 
-CFR_HD u64 occ_match(const u64x2 &p, int c) {  // p = {lo, hi} planes of 64 symbols
+CFR_HD u64 occ_match(u64 lo, u64 hi, int c) {
   const u64 ml = (c & 1) ? ~0ull : 0ull, mh = (c & 2) ? ~0ull : 0ull;
-  return ~(p.x ^ ml) & ~(p.y ^ mh);
+  return ~(lo ^ ml) & ~(hi ^ mh);
+}
+
+// # of symbol c before sector `sec` from its packed counters
+CFR_HD u64 occ_base(u64 w2, u64 w3, int c, u64 sec) {
+  const u64 M40 = 0xffffffffffull;
+  const u64 a = w2 & M40;
+  const u64 cc = (w2 >> 40) | ((w3 & 0xffffull) << 24);
+  const u64 g = (w3 >> 16) & M40;
+  const u64 t = (sec << 6) - (a + cc + g);
+  return c == 0 ? a : (c == 1 ? cc : (c == 2 ? g : t));
+}
+
+CFR_HD void occ_load(const OccLine *L, u64 &lo, u64 &hi, u64 &w2, u64 &w3) {
+  const u64x2 p = ld128(reinterpret_cast<const u64x2 *>(L));
+  const u64x2 q = ld128(reinterpret_cast<const u64x2 *>(L) + 1);
+  lo = p.x;
+  hi = p.y;
+  w2 = q.x;
+  w3 = q.y;
 }
 
 CFR_HD OccRank occ_rank(const DevIndex &ix, int c, u64 x) {
-  const OccLine *L = ix.occ + (x >> 7);
-  const int within = (int)(x & 127), h = within >> 6, s = within & 63;
+  const u64 sec = x >> 6;
+  const int s = (int)(x & 63);
   OccRank r;
-  const u64 w = ld64(reinterpret_cast<const u64 *>(L) + c);
-  r.half = ld128(reinterpret_cast<const u64x2 *>(L) + 2 + h);
-  const u64 below = (1ull << s) - 1ull;
-  r.count = (w & 0x00ffffffffffffffull) + (h ? (w >> 56) : 0ull) + (u64)popc64(occ_match(r.half, c) & below);
+  u64 w2, w3;
+  occ_load(ix.occ + sec, r.lo, r.hi, w2, w3);
+  r.count = occ_base(w2, w3, c, sec) + (u64)popc64(occ_match(r.lo, r.hi, c) & ((1ull << s) - 1ull));
   return r;
 }
 
-CFR_HD int occ_half_symbol(const u64x2 &half, int s) {
-  return (int)(((half.x >> s) & 1ull) | (((half.y >> s) & 1ull) << 1));
-}
+CFR_HD int occ_symbol(u64 lo, u64 hi, int s) { return (int)(((lo >> s) & 1ull) | (((hi >> s) & 1ull) << 1)); }
 
 struct BwtOccLine {
   // straight-line: both ranks and the symbol test are always computed, the range /
@@ -386,7 +399,7 @@ struct BwtOccLine {
     oc.access += range ? 0u : 1u;
     const OccRank a = occ_rank(ix, c, sp);      // Rank(c, sp, exclusive)
     const OccRank e = occ_rank(ix, c, ep + 1);  // Rank(c, ep, inclusive)
-    const int sym = occ_half_symbol(a.half, (int)(ep & 63));  // BWT[ep] when sp == ep (same half as sp)
+    const int sym = occ_symbol(a.lo, a.hi, (int)(ep & 63));  // BWT[ep] when sp == ep (same sector as sp)
     nsp = off + a.count + last_chr_fix(ix, c, sp, 0);
     const u64 nep_range = off + e.count + last_chr_fix(ix, c, ep, 1) - 1;
     const u64 nep_single = nsp + ((sym == c) ? 0ull : ~0ull);
@@ -395,13 +408,12 @@ struct BwtOccLine {
   static CFR_HD u64 lf(const DevIndex &ix, u64 i, OpCount &oc) {
     ++oc.access;
     ++oc.rank;
-    const OccLine *L = ix.occ + (i >> 7);
-    const int within = (int)(i & 127), h = within >> 6, s = within & 63;
-    const u64x2 half = ld128(reinterpret_cast<const u64x2 *>(L) + 2 + h);
-    const int c = occ_half_symbol(half, s);
-    const u64 w = ld64(reinterpret_cast<const u64 *>(L) + c);
-    const u64 r = (w & 0x00ffffffffffffffull) + (h ? (w >> 56) : 0ull) +
-                  (u64)popc64(occ_match(half, c) & ((1ull << s) - 1ull));
+    const u64 sec = i >> 6;
+    const int s = (int)(i & 63);
+    u64 lo, hi, w2, w3;
+    occ_load(ix.occ + sec, lo, hi, w2, w3);
+    const int c = occ_symbol(lo, hi, s);
+    const u64 r = occ_base(w2, w3, c, sec) + (u64)popc64(occ_match(lo, hi, c) & ((1ull << s) - 1ull));
     // inclusive rank at i = exclusive count at i, plus the symbol itself
     return ix.C[c] + r + 1 + last_chr_fix(ix, c, i, 1) - 1;
   }
@@ -409,10 +421,8 @@ struct BwtOccLine {
     return occ_rank(ix, c, inclusive ? i + 1 : i).count;
   }
   static CFR_HD int access(const DevIndex &ix, u64 i) {
-    const OccLine *L = ix.occ + (i >> 7);
-    const int within = (int)(i & 127);
-    const u64x2 half = ld128(reinterpret_cast<const u64x2 *>(L) + 2 + (within >> 6));
-    return occ_half_symbol(half, within & 63);
+    const u64x2 p = ld128(reinterpret_cast<const u64x2 *>(ix.occ + (i >> 6)));
+    return occ_symbol(p.x, p.y, (int)(i & 63));
   }
   static CFR_HD bool leader() { return true; }
   enum { LANES = 1 };

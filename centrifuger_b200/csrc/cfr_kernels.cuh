@@ -49,9 +49,11 @@ __global__ void __launch_bounds__(CFR_DUST_THREADS) k_dust(const __grid_constant
   dust_tasks(B, B.n_reads * (u64)B.mates, d, quorum);  // mates are claimed dynamically from B.dust_counter
 }
 
-template <class Bwt>
-__global__ void __launch_bounds__(128) k_search(const __grid_constant__ DevIndex ix, const __grid_constant__ DevParams P,
-                                                const __grid_constant__ ChunkDev B) {
+// MINB = resident blocks per SM the register allocation must allow (occupancy knob)
+template <class Bwt, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_search(const __grid_constant__ DevIndex ix,
+                                                      const __grid_constant__ DevParams P,
+                                                      const __grid_constant__ ChunkDev B) {
   OpCount oc{};
   const u64 ntask = B.n_reads * (u64)(2 * B.mates);
   search_tasks<Bwt>(ix, P, B, ntask, oc);  // tasks are claimed dynamically from B.task_counter
@@ -140,34 +142,35 @@ __global__ void __launch_bounds__(128) k_score(const __grid_constant__ DevIndex 
   if (err) atomicOr(&B.counters[CFR_STAGE_SCORE].error_flags, err);
 }
 
-// Index transcoding at load time: run-block BWT (as stored) -> 64-byte occ lines.
-// One thread per line: 4 exclusive Sequence_RunBlock::Rank queries give the
-// absolute counters, 128 Sequence_RunBlock::Access queries give the symbols.
+// Index transcoding at load time: run-block BWT (as stored) -> 32-byte occ sectors.
+// One thread per sector: 3 exclusive Sequence_RunBlock::Rank queries give the
+// counters, 64 Sequence_RunBlock::Access queries give the symbols -- the literal
+// device port of the reference's rank/access does the decoding.
+CFR_HD OccLine occ_pack(u64 lo, u64 hi, u64 a, u64 c, u64 g) {
+  OccLine o;
+  o.lo = lo;
+  o.hi = hi;
+  o.w2 = (a & 0xffffffffffull) | (c << 40);
+  o.w3 = ((c >> 24) & 0xffffull) | ((g & 0xffffffffffull) << 16);
+  return o;
+}
+
 __global__ void __launch_bounds__(128) k_transcode(const __grid_constant__ DevIndex ix, OccLine *out, u64 n_lines) {
   const u64 stride = (u64)gridDim.x * blockDim.x;
   for (u64 L = (u64)blockIdx.x * blockDim.x + threadIdx.x; L < n_lines; L += stride) {
-    OccLine o;
-    const u64 p0 = L * 128;
+    const u64 p0 = L * 64;
+    u64 cnt[3];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) o.cnt[c] = p0 <= ix.n ? rb_rank(ix, c, p0, 0) : 0;
-    u64 lo[2] = {0, 0}, hi[2] = {0, 0};
-    for (int w = 0; w < 128; ++w) {
+    for (int c = 0; c < 3; ++c) cnt[c] = p0 <= ix.n ? rb_rank(ix, c, p0, 0) : 0;
+    u64 lo = 0, hi = 0;
+    for (int w = 0; w < 64; ++w) {
       const u64 pos = p0 + (u64)w;
       if (pos >= ix.n) break;
       const int s = rb_access(ix, pos);
-      lo[w >> 6] |= (u64)(s & 1) << (w & 63);
-      hi[w >> 6] |= (u64)(s >> 1) << (w & 63);
+      lo |= (u64)(s & 1) << w;
+      hi |= (u64)(s >> 1) << w;
     }
-    o.lo0 = lo[0];
-    o.hi0 = hi[0];
-    o.lo1 = lo[1];
-    o.hi1 = hi[1];
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {  // first-half counts ride in the counter words' top byte
-      const u64x2 h0{lo[0], hi[0]};
-      o.cnt[c] |= (u64)__popcll(occ_match(h0, c) & (p0 + 64 <= ix.n ? ~0ull : (p0 >= ix.n ? 0ull : ((1ull << (ix.n - p0)) - 1ull)))) << 56;
-    }
-    out[L] = o;
+    out[L] = occ_pack(lo, hi, cnt[0], cnt[1], cnt[2]);
   }
 }
 

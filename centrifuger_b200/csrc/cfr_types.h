@@ -33,13 +33,16 @@ struct DevWT {
   u64 n;
 };
 
-// One 64-byte occ line of the transcoded layout: 128 BWT symbols.
-//   cnt[c]  bits 0..55  = # of symbol c in BWT[0 .. 128*line)
-//           bits 56..62 = # of symbol c among the line's first 64 symbols
-//   lo/hi   = bit planes of the 128 two-bit symbol codes (0/1 = 64-symbol half)
-struct alignas(64) OccLine {
-  u64 cnt[4];
-  u64 lo0, hi0, lo1, hi1;
+// One 32-byte occ sector of the transcoded layout: 64 BWT symbols and the number
+// of A, C and G before them; the number of T follows because every BWT row holds
+// one of the four symbols (the text has no '$', FMIndex.hpp:355-358):
+//     #T before the sector = 64 * sector - (#A + #C + #G).
+//   lo, hi  bit planes of the 64 two-bit symbol codes
+//   w2      bits 0..39 #A, bits 40..63 low 24 bits of #C
+//   w3      bits 0..15 high 16 bits of #C, bits 16..55 #G       (40-bit counters: n < 2^40)
+// 32 bytes = one L2 / HBM3e sector: a rank or an LF step reads exactly one sector.
+struct alignas(32) OccLine {
+  u64 lo, hi, w2, w3;
 };
 
 struct DevIndex {

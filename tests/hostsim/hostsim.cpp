@@ -116,25 +116,23 @@ void *hostsim_open(const char *prefix, const cfr_params *p) {
   init_tax_rank_num(ix.rank_num);
   h->layout = p->layout == CFR_LAYOUT_OCCLINE ? 2 : 1;
   if (h->layout == 2) {  // same construction the transcode kernel performs
-    const u64 lines = f.n / 128 + 1;
+    const u64 lines = f.n / 64 + 1;
     h->occ.resize(lines);
     for (u64 L = 0; L < lines; ++L) {
-      OccLine o;
-      memset(&o, 0, sizeof(o));
-      for (int c = 0; c < 4; ++c) o.cnt[c] = rb_rank(ix, c, L * 128, 0);
-      for (int w = 0; w < 128; ++w) {
-        const u64 pos = L * 128 + (u64)w;
+      u64 cnt[3], lo = 0, hi = 0;
+      for (int c = 0; c < 3; ++c) cnt[c] = rb_rank(ix, c, L * 64, 0);
+      for (int w = 0; w < 64; ++w) {
+        const u64 pos = L * 64 + (u64)w;
         if (pos >= f.n) break;
         const int s = rb_access(ix, pos);
-        u64 &lo = w < 64 ? o.lo0 : o.lo1, &hi = w < 64 ? o.hi0 : o.hi1;
-        lo |= (u64)(s & 1) << (w & 63);
-        hi |= (u64)(s >> 1) << (w & 63);
+        lo |= (u64)(s & 1) << w;
+        hi |= (u64)(s >> 1) << w;
       }
-      for (int c = 0; c < 4; ++c) {
-        const u64x2 h0{o.lo0, o.hi0};
-        const u64 valid = L * 128 + 64 <= f.n ? ~0ull : (L * 128 >= f.n ? 0ull : ((1ull << (f.n - L * 128)) - 1ull));
-        o.cnt[c] |= (u64)popc64(occ_match(h0, c) & valid) << 56;
-      }
+      OccLine o;
+      o.lo = lo;
+      o.hi = hi;
+      o.w2 = (cnt[0] & 0xffffffffffull) | (cnt[1] << 40);
+      o.w3 = ((cnt[1] >> 24) & 0xffffull) | ((cnt[2] & 0xffffffffffull) << 16);
       h->occ[L] = o;
     }
     ix.occ = h->occ.data();
