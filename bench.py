@@ -187,6 +187,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=0, help="reads in the CPU-baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-dust", action="store_true")
+    ap.add_argument("--chunk", type=int, default=0, help="reads per device chunk in the end-to-end path (0 = auto)")
     a = ap.parse_args()
 
     w = dict(WORKLOADS[a.workload])
@@ -208,7 +209,7 @@ def main():
         idx = ensure_dataset(w["dataset"])
         seq1, off1, seq2, off2 = make_reads(w, 7)
         cores = os.cpu_count() or 1
-        n_sample = a.cpu_sample or min(w["reads"], 40_000 * max(1, cores // 8) if not w["paired"] else 15_000 * max(1, cores // 8))
+        n_sample = a.cpu_sample or min(w["reads"], (250_000 if not w["paired"] else 100_000) * max(1, cores // 8))
         vals = []
         for i in range(a.warmup + a.steps):
             r = run_reference_cpu(idx, w, seq1, off1, seq2, off2, n_sample, cores)
@@ -251,7 +252,7 @@ def main():
     bases = int(seq1.size + (seq2.size if seq2 is not None else 0))
 
     clf = cb.Classifier(idx, k=w["k"], dust=not a.no_dust, layout=a.layout, device=local_rank,
-                        max_batch_reads=max(n, 1 << 20))
+                        max_batch_reads=a.chunk)
     # a dedicated (non-default) torch stream: its handle is passed through the C ABI so the
     # library's kernels and torch's CUDA events are on the same stream
     stream = torch.cuda.Stream()
@@ -329,6 +330,13 @@ def main():
     sampler.stop_flag = True
     sampler.join(timeout=2)
     launches_e2e = clf.counters()["n_launches"]
+    # diagnostic (untimed): per-stage kernel time of one end-to-end step (chunked launches)
+    clf.stage_times(reset=True)
+    clf.set_profiling(True)
+    step_e2e()
+    sync_all()
+    e2e_stage = clf.stage_times(reset=True)
+    clf.set_profiling(False)
 
     # ---- reduce over ranks (max time) ----
     t = torch.tensor([dev_ms, e2e_s * 1000.0, t_wall * 1000.0], dtype=torch.float64, device="cuda")
@@ -362,6 +370,7 @@ def main():
                          "kernel_ms_per_launch": s_ms / max(s_launch, 1),
                          "pipeline_algorithmic_gbs": total_alg / (dev_ms_max / 1000.0) / 1e9 / world},
             "stage_ms_per_step": {k: v[0] / a.steps for k, v in stage.items()},
+            "e2e_stage_ms_per_step": {k: v[0] for k, v in e2e_stage.items()},
             "ops_per_read": {k: counters[k] / (n * a.steps) for k in
                              ("n_rank", "n_access", "n_search", "n_locate", "n_lf", "n_extend")},
             "clocks": sampler.summary(),
@@ -369,7 +378,7 @@ def main():
         }
         if not a.no_cpu_baseline and world == 1:
             cores = os.cpu_count() or 1
-            n_sample = a.cpu_sample or min(n, (40_000 if not w["paired"] else 15_000) * max(1, cores // 8))
+            n_sample = a.cpu_sample or min(n, (250_000 if not w["paired"] else 100_000) * max(1, cores // 8))
             r = run_reference_cpu(idx, w, seq1, off1, seq2, off2, n_sample, cores)
             if r is not None:
                 line["cpu_baseline"] = {"value": r[0], "unit": unit, "cores": cores, "kind": "reference",

@@ -371,6 +371,7 @@ void fill_chunk(cfr_handle *h, cfr_device_batch *b, ChunkDev &B) {
   B.task_counter = (u64 *)((char *)b->scalars.p + 16);
   B.row_counter = (u64 *)((char *)b->scalars.p + 24);
   B.dust_counter = (u64 *)((char *)b->scalars.p + 32);
+  B.arena_valid = (u64 *)((char *)b->scalars.p + 40);
   B.rows = (u64 *)b->rows.p;
   B.seq_ids = (u32 *)b->seq_ids.p;
   B.rec0 = (SeqRec *)b->rec0.p;
@@ -394,8 +395,7 @@ int run_pass(cfr_handle *h, const ChunkDev &B, int first_pass, cudaStream_t s) {
     StageScope sc(h, s, CFR_STAGE_OTHER);
     CUDA_TRY(cudaMemsetAsync(B.arena_used, 0, 16, s));
     CUDA_TRY(cudaMemsetAsync(B.row_counter, 0, 8, s));
-    // unwritten arena rows (reads deferred to the next pass) must read as "skip"
-    CUDA_TRY(cudaMemsetAsync(B.rows, 0xff, B.arena_cap * 8, s));
+    CUDA_TRY(cudaMemsetAsync(B.arena_valid, 0xff, 8, s));
   }
   {
     StageScope sc(h, s, CFR_STAGE_SELECT);
@@ -704,8 +704,10 @@ int cfr_classify_batch(cfr_handle *h, const cfr_read_batch *in, cfr_result *resu
   int st = pipeline_init(h);
   if (st) return st;
   const u64 cap = h->params.max_batch_reads > 0 ? (u64)h->params.max_batch_reads : (1ull << 20);
-  // at least 4 chunks once the batch is large enough for the copies to matter
-  u64 chunk = std::min<u64>(cap, std::max<u64>(1u << 16, (in->n_reads + 3) / 4));
+  // a few chunks once the batch is large enough for the copies to matter
+  u64 nchunks = 4;
+  if (const char *e = getenv("CFR_B200_PIPE_CHUNKS")) nchunks = (u64)std::max(1, atoi(e));
+  u64 chunk = std::min<u64>(cap, std::max<u64>(1u << 16, (in->n_reads + nchunks - 1) / nchunks));
   if (h->params.max_batch_reads > 0) chunk = std::min<u64>(chunk, cap);
   const u64 k = (u64)h->P.max_result;
   CUDA_TRY(cudaEventRecord(h->ev_start, sc));  // everything below is ordered after the caller's stream

@@ -1155,15 +1155,17 @@ CFR_HD void dust_seg_init(DustIn &in, int seg_off, DustStateT<SW> &d, int &c1, i
 
 CFR_HD int dust_wstart(int wfinish) { return wfinish + 1 > 64 ? wfinish + 1 - 64 : 0; }
 
-// one iteration of SDust's main loop up to the FindPerfect test (:330-340);
-// returns true when FindPerfect has to run for this position
+// one iteration of SDust's main loop (:330-340) up to the point where the suffix v may
+// have to be shrunk (ShiftWindow's inner loop, :125-135); returns true when it must.
+// `t` receives the triplet that entered the window.
 template <int SW>
-CFR_HD bool dust_step(DustIn &in, const DustOut &out, int seg_off, int wfinish, DustStateT<SW> &d, int &c1, int &c2) {
+CFR_HD bool dust_step(DustIn &in, const DustOut &out, int seg_off, int wfinish, DustStateT<SW> &d, int &c1, int &c2,
+                      int &t) {
   const int W = 64, T = 20;
   const int wstart = dust_wstart(wfinish);
   if (wstart > 0) dust_evict(d, out, seg_off, wstart - 1);
   const int c3 = in(seg_off + wfinish);
-  const int t = c1 * 25 + c2 * 5 + c3;
+  t = c1 * 25 + c2 * 5 + c3;
   c1 = c2;
   c2 = c3;
   // ShiftWindow (Dustmasker.hpp:106-136)
@@ -1187,17 +1189,24 @@ CFR_HD bool dust_step(DustIn &in, const DustOut &out, int seg_off, int wfinish, 
   const int cvt = d.cv[t];
   d.rv += cvt;
   d.cv[t] = (unsigned char)(cvt + 1);
-  if ((cvt + 1) * 10 > 2 * T) {
-    for (;;) {
-      const int s = dust_win_at(d, d.size - d.lv);
-      const int cvs = --d.cv[s];
-      d.rv -= cvs;
-      --d.lv;
-      if (s == t) break;
-    }
-  }
-  return d.rw * 10 > d.lv * T;
+  return (cvt + 1) * 10 > 2 * T;
 }
+
+// the suffix no longer satisfies max c(v) <= 2T: drop its head up to the first t (:127-134)
+template <int SW>
+CFR_HD void dust_shrink(DustStateT<SW> &d, int t) {
+  for (;;) {
+    const int s = dust_win_at(d, d.size - d.lv);
+    const int cvs = --d.cv[s];
+    d.rv -= cvs;
+    --d.lv;
+    if (s == t) break;
+  }
+}
+
+// SDust :340 -- does the window hold a candidate perfect interval?
+template <int SW>
+CFR_HD bool dust_needs_find_perfect(const DustStateT<SW> &d) { return d.rw * 10 > d.lv * 20; }
 
 // FindPerfect (Dustmasker.hpp:173-242) over the per-start slots
 template <int SW>
@@ -1280,8 +1289,11 @@ CFR_HD void dust_task(DustIn &in, int n, const DustOut &out, DustStateT<SW> &d) 
     if (last_valid > i && seg_n >= 3) {
       int c1, c2;
       dust_seg_init(in, i, d, c1, c2);
-      for (int wfinish = 2; wfinish < seg_n; ++wfinish)
-        if (dust_step(in, out, i, wfinish, d, c1, c2)) dust_find_perfect(wfinish, d);
+      for (int wfinish = 2; wfinish < seg_n; ++wfinish) {
+        int t;
+        if (dust_step(in, out, i, wfinish, d, c1, c2, t)) dust_shrink(d, t);
+        if (dust_needs_find_perfect(d)) dust_find_perfect(wfinish, d);
+      }
       dust_seg_tail(out, i, seg_n, d);
     }
     i = next_i;

@@ -89,7 +89,10 @@ __global__ void __launch_bounds__(128) k_select(const __grid_constant__ DevIndex
       const u64 my_base = base0 + incl - r;
       const bool fits = my_base + r <= B.arena_cap;
       select_write_rows(P, B, read, my_base, fits);
-      if (!fits) B.deferred[atomicAdd(B.n_deferred, 1u)] = (u32)read;
+      if (!fits) {
+        B.deferred[atomicAdd(B.n_deferred, 1u)] = (u32)read;
+        atomicMin(B.arena_valid, my_base);
+      }
     }
   }
   flush_counts(oc, B.counters + CFR_STAGE_SELECT);
@@ -99,7 +102,9 @@ template <class Bwt>
 __global__ void __launch_bounds__(128) k_locate(const __grid_constant__ DevIndex ix, const __grid_constant__ DevParams P,
                                                 const __grid_constant__ ChunkDev B) {
   OpCount oc{};
+  // reservations are monotone, so the rows below the first read that did not fit are exactly the written ones
   u64 used = *B.arena_used;
+  if (used > *B.arena_valid) used = *B.arena_valid;
   if (used > B.arena_cap) used = B.arena_cap;
   locate_rows<Bwt>(ix, P, B, used, oc);  // rows are claimed dynamically from B.row_counter
   if (!Bwt::leader()) oc = OpCount{};

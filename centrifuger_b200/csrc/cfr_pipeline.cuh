@@ -37,6 +37,7 @@ struct ChunkDev {
   // locate / scoring arena, one slot per planned BWT row
   u64 arena_cap;
   u64 *arena_used;
+  u64 *arena_valid;   // lowest arena row of a read that did NOT fit: rows below it are all written
   u64 *task_counter;  // next strand task (dynamic fetch by the search warps)
   u64 *row_counter;   // next arena row (dynamic fetch by the locate warps)
   u64 *dust_counter;  // next mate (dynamic fetch by the DUST warps)
@@ -126,20 +127,22 @@ CFR_HD void encode_stage(const ChunkDev &B, u64 w, u64 total_bytes) {
 // STEP advance their window by one base together; FindPerfect (long, data
 // dependent, needed by a minority of positions) and the per-mate set-up run when a
 // quorum of lanes waits for them.  Mates are claimed dynamically.
-enum { CFR_DS_FETCH = 0, CFR_DS_SEG = 1, CFR_DS_STEP = 2, CFR_DS_FP = 3, CFR_DS_DONE = 4 };
+enum { CFR_DS_FETCH = 0, CFR_DS_SEG = 1, CFR_DS_STEP = 2, CFR_DS_SLOW = 3, CFR_DS_DONE = 4 };
 
 template <int SW>
 CFR_HD void dust_tasks(const ChunkDev &B, const u64 ntask, DustStateT<SW> &d, const int quorum) {
   DustIn in{B.codes, B.mask_raw, 0};
   DustOut out{B.mask, B.dust_bits, 0};
   int st = CFR_DS_FETCH;
-  int len = 0, cursor = 0, seg_off = 0, seg_n = 0, wfinish = 0, c1 = 0, c2 = 0;
+  int len = 0, cursor = 0, seg_off = 0, seg_n = 0, wfinish = 0, c1 = 0, c2 = 0, t_last = 0;
+  bool pend_shrink = false;
+  const int slow_quorum = quorum > 1 ? quorum / 2 : 1;
   for (;;) {
     const u32 m_step = CFR_BALLOT(st == CFR_DS_STEP);
-    const u32 m_fp = CFR_BALLOT(st == CFR_DS_FP);
+    const u32 m_slow = CFR_BALLOT(st == CFR_DS_SLOW);
     const u32 m_trn = CFR_BALLOT(st == CFR_DS_FETCH || st == CFR_DS_SEG);
-    if ((m_step | m_fp | m_trn) == 0) break;
-    if (m_trn != 0 && ((m_step | m_fp) == 0 || popc32(m_trn) >= quorum)) {
+    if ((m_step | m_slow | m_trn) == 0) break;
+    if (m_trn != 0 && ((m_step | m_slow) == 0 || popc32(m_trn) >= quorum)) {
       for (int tries = 0; tries < 3; ++tries) {
         if (CFR_BALLOT(st == CFR_DS_FETCH || st == CFR_DS_SEG) == 0) break;
         const u64 claimed = warp_claim<1>(B.dust_counter, st == CFR_DS_FETCH);
@@ -180,15 +183,18 @@ CFR_HD void dust_tasks(const ChunkDev &B, const u64 ntask, DustStateT<SW> &d, co
       }
     }
     bool advance = false;
-    if (m_fp != 0 && (m_step == 0 || popc32(m_fp) >= quorum)) {
-      if (st == CFR_DS_FP) {
-        dust_find_perfect(wfinish, d);
+    // the slow, data-dependent loops (suffix shrink, FindPerfect) of the lanes that need them
+    if (m_slow != 0 && (m_step == 0 || popc32(m_slow) >= slow_quorum)) {
+      if (st == CFR_DS_SLOW) {
+        if (pend_shrink) dust_shrink(d, t_last);
+        if (dust_needs_find_perfect(d)) dust_find_perfect(wfinish, d);
         advance = true;
       }
     }
     if (st == CFR_DS_STEP) {
-      if (dust_step(in, out, seg_off, wfinish, d, c1, c2))
-        st = CFR_DS_FP;
+      pend_shrink = dust_step(in, out, seg_off, wfinish, d, c1, c2, t_last);
+      if (pend_shrink || dust_needs_find_perfect(d))
+        st = CFR_DS_SLOW;
       else
         advance = true;
     }

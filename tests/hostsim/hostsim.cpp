@@ -276,7 +276,7 @@ int hostsim_classify(void *hh, int dust, uint64_t arena_rows, const cfr_read_bat
   for (;;) {
     arena_used = 0;
     n_deferred = 0;
-    std::fill(rows.begin(), rows.end(), CFR_ROW_SENTINEL);
+    u64 arena_valid = ~0ull;
     for (u64 t = 0; t < B.n_list; ++t) {
       const u64 read = chunk_read_id(B, t);
       u32 r;
@@ -289,9 +289,12 @@ int hostsim_classify(void *hh, int dust, uint64_t arena_rows, const cfr_read_bat
       arena_used += r;
       const bool fits = base + r <= B.arena_cap;
       select_write_rows(P, B, read, base, fits);
-      if (!fits) deferred[n_deferred++] = (u32)read;
+      if (!fits) {
+        deferred[n_deferred++] = (u32)read;
+        arena_valid = std::min(arena_valid, base);
+      }
     }
-    const u64 used = std::min(arena_used, B.arena_cap);
+    const u64 used = std::min(std::min(arena_used, arena_valid), B.arena_cap);
     row_counter = 0;
     if (h->layout == 2) locate_rows<BwtOccLine>(ix, P, B, used, oc);
     else locate_rows<BwtRunBlock>(ix, P, B, used, oc);
