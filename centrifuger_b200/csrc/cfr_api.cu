@@ -92,7 +92,7 @@ struct cfr_handle {
   u64 host_bases = 0;
   // cfr_classify_batch pipeline: two chunk slots, H2D / compute / D2H on three streams
   cfr_device_batch slots[2];
-  cudaStream_t s_in = nullptr, s_out = nullptr;
+  cudaStream_t s_in = nullptr, s_out = nullptr, s_comp[2] = {nullptr, nullptr};
   cudaEvent_t ev_start = nullptr, ev_h2d[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr},
               ev_d2h[2] = {nullptr, nullptr};
   struct PinnedScalars {
@@ -573,6 +573,8 @@ void cfr_close(cfr_handle *h) {
   h->slots[1].release();
   if (h->s_in) cudaStreamDestroy(h->s_in);
   if (h->s_out) cudaStreamDestroy(h->s_out);
+  for (int i = 0; i < 2; ++i)
+    if (h->s_comp[i]) cudaStreamDestroy(h->s_comp[i]);
   if (h->ev_start) cudaEventDestroy(h->ev_start);
   for (int i = 0; i < 2; ++i) {
     if (h->ev_h2d[i]) cudaEventDestroy(h->ev_h2d[i]);
@@ -663,13 +665,16 @@ void cfr_batch_free(cfr_handle *h, cfr_device_batch *b) {
 }
 
 // Host <-> device copies overlap the kernels: the batch is cut into chunks that go
-// through two slots; chunk c's H2D (stream s_in), kernels (the caller's stream) and
-// D2H (stream s_out) are chained with events, so while chunk c computes, chunk c+1
-// uploads and chunk c-1 downloads.  Pinned host buffers are needed for real overlap.
+// through two slots; chunk c's H2D (stream s_in), kernels (one compute stream per
+// slot, so the head of chunk c+1 fills the SMs the tail of chunk c leaves idle) and
+// D2H (stream s_out) are chained with events.  Everything is ordered after the
+// caller's stream, and the call returns when the results are on the host.  Pinned
+// host buffers are needed for real copy/compute overlap.
 static int pipeline_init(cfr_handle *h) {
   if (h->s_in) return CFR_OK;
   CUDA_TRY(cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
   CUDA_TRY(cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; ++i) CUDA_TRY(cudaStreamCreateWithFlags(&h->s_comp[i], cudaStreamNonBlocking));
   CUDA_TRY(cudaEventCreateWithFlags(&h->ev_start, cudaEventDisableTiming));
   for (int i = 0; i < 2; ++i) {
     CUDA_TRY(cudaEventCreateWithFlags(&h->ev_h2d[i], cudaEventDisableTiming));
@@ -712,6 +717,8 @@ int cfr_classify_batch(cfr_handle *h, const cfr_read_batch *in, cfr_result *resu
   const u64 k = (u64)h->P.max_result;
   CUDA_TRY(cudaEventRecord(h->ev_start, sc));  // everything below is ordered after the caller's stream
   CUDA_TRY(cudaStreamWaitEvent(h->s_in, h->ev_start, 0));
+  CUDA_TRY(cudaStreamWaitEvent(h->s_comp[0], h->ev_start, 0));
+  CUDA_TRY(cudaStreamWaitEvent(h->s_comp[1], h->ev_start, 0));
   u64 starts[2] = {0, 0};
   u64 c = 0;
   for (u64 r0 = 0; r0 < in->n_reads; r0 += chunk, ++c) {
@@ -719,14 +726,14 @@ int cfr_classify_batch(cfr_handle *h, const cfr_read_batch *in, cfr_result *resu
     const u64 r1 = std::min<u64>(in->n_reads, r0 + chunk);
     cfr_device_batch *b = &h->slots[slot];
     if (c >= 2) {  // the slot's previous chunk must have left the device before its buffers are reused
-      if ((st = pipeline_drain(h, slot, results + starts[slot], ids + starts[slot] * k, sc))) return st;
+      if ((st = pipeline_drain(h, slot, results + starts[slot], ids + starts[slot] * k, h->s_comp[slot]))) return st;
     }
     starts[slot] = r0;
     if ((st = upload_chunk(h, in, r0, r1, b, h->s_in))) return st;
     CUDA_TRY(cudaEventRecord(h->ev_h2d[slot], h->s_in));
-    CUDA_TRY(cudaStreamWaitEvent(sc, h->ev_h2d[slot], 0));
-    if ((st = cfr_classify_resident(h, b, sc))) return st;
-    CUDA_TRY(cudaEventRecord(h->ev_comp[slot], sc));
+    CUDA_TRY(cudaStreamWaitEvent(h->s_comp[slot], h->ev_h2d[slot], 0));
+    if ((st = cfr_classify_resident(h, b, h->s_comp[slot]))) return st;
+    CUDA_TRY(cudaEventRecord(h->ev_comp[slot], h->s_comp[slot]));
     CUDA_TRY(cudaStreamWaitEvent(h->s_out, h->ev_comp[slot], 0));
     CUDA_TRY(cudaMemcpyAsync(results + r0, b->results.p, (r1 - r0) * sizeof(DevResult), cudaMemcpyDeviceToHost, h->s_out));
     CUDA_TRY(cudaMemcpyAsync(ids + r0 * k, b->out_ids.p, (r1 - r0) * k * 8, cudaMemcpyDeviceToHost, h->s_out));
@@ -738,9 +745,10 @@ int cfr_classify_batch(cfr_handle *h, const cfr_read_batch *in, cfr_result *resu
   // drain the last (up to two) chunks in order
   for (u64 d = c >= 2 ? c - 2 : 0; d < c; ++d) {
     const int slot = (int)(d & 1);
-    if ((st = pipeline_drain(h, slot, results + starts[slot], ids + starts[slot] * k, sc))) return st;
+    if ((st = pipeline_drain(h, slot, results + starts[slot], ids + starts[slot] * k, h->s_comp[slot]))) return st;
   }
-  CUDA_TRY(cudaStreamSynchronize(sc));
+  CUDA_TRY(cudaStreamSynchronize(h->s_comp[0]));
+  CUDA_TRY(cudaStreamSynchronize(h->s_comp[1]));
   return check_device_errors(h, sc);
 }
 

@@ -135,14 +135,14 @@ CFR_HD void dust_tasks(const ChunkDev &B, const u64 ntask, DustStateT<SW> &d, co
   DustOut out{B.mask, B.dust_bits, 0};
   int st = CFR_DS_FETCH;
   int len = 0, cursor = 0, seg_off = 0, seg_n = 0, wfinish = 0, c1 = 0, c2 = 0, t_last = 0;
-  bool pend_shrink = false;
-  const int slow_quorum = quorum > 1 ? quorum / 2 : 1;
   for (;;) {
     const u32 m_step = CFR_BALLOT(st == CFR_DS_STEP);
     const u32 m_slow = CFR_BALLOT(st == CFR_DS_SLOW);
     const u32 m_trn = CFR_BALLOT(st == CFR_DS_FETCH || st == CFR_DS_SEG);
     if ((m_step | m_slow | m_trn) == 0) break;
-    if (m_trn != 0 && ((m_step | m_slow) == 0 || popc32(m_trn) >= quorum)) {
+    const int alive = popc32(m_step | m_slow | m_trn);
+    const int q_now = (alive + 3) / 4 < quorum ? ((alive + 3) / 4 < 1 ? 1 : (alive + 3) / 4) : quorum;
+    if (m_trn != 0 && ((m_step | m_slow) == 0 || popc32(m_trn) >= q_now)) {
       for (int tries = 0; tries < 3; ++tries) {
         if (CFR_BALLOT(st == CFR_DS_FETCH || st == CFR_DS_SEG) == 0) break;
         const u64 claimed = warp_claim<1>(B.dust_counter, st == CFR_DS_FETCH);
@@ -183,17 +183,16 @@ CFR_HD void dust_tasks(const ChunkDev &B, const u64 ntask, DustStateT<SW> &d, co
       }
     }
     bool advance = false;
-    // the slow, data-dependent loops (suffix shrink, FindPerfect) of the lanes that need them
-    if (m_slow != 0 && (m_step == 0 || popc32(m_slow) >= slow_quorum)) {
+    // FindPerfect (long, data dependent) for the lanes that need it
+    if (m_slow != 0 && (m_step == 0 || popc32(m_slow) >= q_now)) {
       if (st == CFR_DS_SLOW) {
-        if (pend_shrink) dust_shrink(d, t_last);
-        if (dust_needs_find_perfect(d)) dust_find_perfect(wfinish, d);
+        dust_find_perfect(wfinish, d);
         advance = true;
       }
     }
     if (st == CFR_DS_STEP) {
-      pend_shrink = dust_step(in, out, seg_off, wfinish, d, c1, c2, t_last);
-      if (pend_shrink || dust_needs_find_perfect(d))
+      if (dust_step(in, out, seg_off, wfinish, d, c1, c2, t_last)) dust_shrink(d, t_last);  // short loop: inline
+      if (dust_needs_find_perfect(d))
         st = CFR_DS_SLOW;
       else
         advance = true;
@@ -232,6 +231,15 @@ CFR_HD void dust_stage(const ChunkDev &B, u64 task, DustStateT<SW> &d) {
 // starting the next one (lookup-table probe of the last W bases) and fetching the
 // next task -- are deferred until a quorum of lanes is waiting for them (or nobody
 // can extend), so that block runs with many lanes instead of one or two.
+// How many waiting tasks trigger the deferred block: the configured quorum, but never
+// more than a quarter of the tasks the warp still has alive (so a draining warp does
+// not stall its last lanes behind a quorum it can no longer reach).
+CFR_HD int adaptive_quorum(int quorum, u32 alive_mask, int lanes_per_task) {
+  const int alive = popc32(alive_mask) / lanes_per_task;
+  const int q = (alive + 3) / 4;
+  return (q < quorum ? (q < 1 ? 1 : q) : quorum) * lanes_per_task;
+}
+
 enum { CFR_ST_EXTEND = 0, CFR_ST_CLOSE = 1, CFR_ST_FETCH = 2, CFR_ST_DONE = 3 };
 
 template <class Bwt>
@@ -246,7 +254,7 @@ CFR_HD void search_tasks(const DevIndex &ix, const DevParams &P, const ChunkDev 
     const u32 ext = CFR_BALLOT(st == CFR_ST_EXTEND);
     const u32 trn = CFR_BALLOT(st == CFR_ST_CLOSE || st == CFR_ST_FETCH);
     if ((ext | trn) == 0) break;
-    if (trn != 0 && (ext == 0 || popc32(trn) >= P.quorum * (int)Bwt::LANES)) {
+    if (trn != 0 && (ext == 0 || popc32(trn) >= adaptive_quorum(P.quorum, ext | trn, (int)Bwt::LANES))) {
       // ---- transition block (warp-uniform entry): CLOSE -> (FETCH ->) start of the next search
       for (int tries = 0; tries < 3; ++tries) {
         if (CFR_BALLOT(st == CFR_ST_CLOSE || st == CFR_ST_FETCH) == 0) break;
@@ -361,7 +369,7 @@ CFR_HD void locate_rows(const DevIndex &ix, const DevParams &P, const ChunkDev &
     const u32 walk = CFR_BALLOT(st == CFR_LS_WALK);
     const u32 trn = CFR_BALLOT(st == CFR_LS_CHECK || st == CFR_LS_NEED);
     if ((walk | trn) == 0) break;
-    if (trn != 0 && (walk == 0 || popc32(trn) >= P.quorum * (int)Bwt::LANES)) {
+    if (trn != 0 && (walk == 0 || popc32(trn) >= adaptive_quorum(P.quorum, walk | trn, (int)Bwt::LANES))) {
       for (int tries = 0; tries < 3; ++tries) {
         if (CFR_BALLOT(st == CFR_LS_CHECK || st == CFR_LS_NEED) == 0) break;
         if (st == CFR_LS_CHECK) {  // FMIndex::GetSampledSA, literally
