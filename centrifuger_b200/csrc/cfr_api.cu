@@ -709,11 +709,32 @@ int cfr_classify_batch(cfr_handle *h, const cfr_read_batch *in, cfr_result *resu
   int st = pipeline_init(h);
   if (st) return st;
   const u64 cap = h->params.max_batch_reads > 0 ? (u64)h->params.max_batch_reads : (1ull << 20);
-  // a few chunks once the batch is large enough for the copies to matter
-  u64 nchunks = 4;
-  if (const char *e = getenv("CFR_B200_PIPE_CHUNKS")) nchunks = (u64)std::max(1, atoi(e));
-  u64 chunk = std::min<u64>(cap, std::max<u64>(1u << 16, (in->n_reads + nchunks - 1) / nchunks));
-  if (h->params.max_batch_reads > 0) chunk = std::min<u64>(chunk, cap);
+  // Chunk plan.  Every chunk pays a fixed cost (the critical path of its slowest read in each
+  // kernel), so few chunks are better for the GPU; but the first upload and the last download are
+  // not overlapped with anything, so those two chunks are kept small: n/8, 3n/8, 3n/8, n/8.
+  std::vector<u64> bounds;  // chunk start offsets + n_reads
+  {
+    const u64 n = in->n_reads;
+    int plan = 1;  // 1 = tapered, N>1 = N equal chunks (CFR_B200_PIPE_CHUNKS)
+    if (const char *e = getenv("CFR_B200_PIPE_CHUNKS")) plan = std::max(1, atoi(e));
+    bounds.push_back(0);
+    if (plan == 1 && n >= (1u << 18) && n <= 4 * cap) {
+      bounds.push_back(n / 8);
+      bounds.push_back(n / 2);
+      bounds.push_back(n - n / 8);
+    } else {
+      u64 chunk = plan > 1 ? (n + plan - 1) / plan : cap;
+      chunk = std::min<u64>(cap, std::max<u64>(chunk, 1));
+      for (u64 r = chunk; r < n; r += chunk) bounds.push_back(r);
+    }
+    bounds.push_back(n);
+    // respect the device chunk cap
+    std::vector<u64> capped;
+    for (size_t i = 0; i + 1 < bounds.size(); ++i)
+      for (u64 r = bounds[i]; r < bounds[i + 1]; r += cap) capped.push_back(r);
+    capped.push_back(n);
+    bounds.swap(capped);
+  }
   const u64 k = (u64)h->P.max_result;
   CUDA_TRY(cudaEventRecord(h->ev_start, sc));  // everything below is ordered after the caller's stream
   CUDA_TRY(cudaStreamWaitEvent(h->s_in, h->ev_start, 0));
@@ -721,9 +742,9 @@ int cfr_classify_batch(cfr_handle *h, const cfr_read_batch *in, cfr_result *resu
   CUDA_TRY(cudaStreamWaitEvent(h->s_comp[1], h->ev_start, 0));
   u64 starts[2] = {0, 0};
   u64 c = 0;
-  for (u64 r0 = 0; r0 < in->n_reads; r0 += chunk, ++c) {
+  for (; c + 1 < bounds.size(); ++c) {
     const int slot = (int)(c & 1);
-    const u64 r1 = std::min<u64>(in->n_reads, r0 + chunk);
+    const u64 r0 = bounds[c], r1 = bounds[c + 1];
     cfr_device_batch *b = &h->slots[slot];
     if (c >= 2) {  // the slot's previous chunk must have left the device before its buffers are reused
       if ((st = pipeline_drain(h, slot, results + starts[slot], ids + starts[slot] * k, h->s_comp[slot]))) return st;
