@@ -69,7 +69,8 @@ def measured_peak():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md), sampled in-process
+    through NVML every 10 ms (nvidia-smi as a fallback)."""
 
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -78,34 +79,56 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.gpu = gpu_index
         self.stop_flag = False
-        self.samples = []
+        self.sm, self.mx, self.reasons = [], [], set()
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[gpu_index]) if vis and vis.split(",")[gpu_index].isdigit() else gpu_index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _nvml_sample(self):
+        n = self.nvml
+        self.sm.append(float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)))
+        self.mx.append(float(n.nvmlDeviceGetMaxClockInfo(self.h, n.NVML_CLOCK_SM)))
+        get = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
+        r = get(self.h)
+        for nm, bit in (("hw_slowdown", 0x8), ("sw_power_cap", 0x4), ("hw_thermal_slowdown", 0x40),
+                        ("sw_thermal_slowdown", 0x20)):
+            if r & bit:
+                self.reasons.add(nm)
+
+    def _smi_sample(self):
+        out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                              "--format=csv,noheader,nounits"], stdout=subprocess.PIPE,
+                             stderr=subprocess.DEVNULL, timeout=5).stdout.decode().strip()
+        s = [x.strip() for x in out.split(",")]
+        self.sm.append(float(s[0]))
+        self.mx.append(float(s[1]))
+        for nm, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], s[2:6]):
+            if v.lower().startswith("active"):
+                self.reasons.add(nm)
 
     def run(self):
         while not self.stop_flag:
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], stdout=subprocess.PIPE,
-                                     stderr=subprocess.DEVNULL, timeout=5).stdout.decode().strip()
-                if out:
-                    self.samples.append([x.strip() for x in out.split(",")])
+                if self.nvml is not None:
+                    self._nvml_sample()
+                else:
+                    self._smi_sample()
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.01 if self.nvml is not None else 0.2)
 
     def summary(self):
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for s in self.samples:
-            try:
-                sm.append(float(s[0]))
-                mx.append(float(s[1]))
-            except Exception:
-                continue
-            for nm, v in zip(names, s[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": statistics.median(self.sm) if self.sm else None,
+                "sm_max_mhz": max(self.mx) if self.mx else None,
+                "reasons": sorted(self.reasons), "samples": len(self.sm),
+                "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 def ensure_dataset(name):
@@ -178,8 +201,8 @@ def run_reference_cpu(idx, w, seq1, off1, seq2, off2, n_sample, threads):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--layout", type=int, default=0, help="0 auto, 1 run-block arrays, 2 occ lines")
@@ -232,6 +255,8 @@ def main():
         return 0
 
     # ------------------------------------------------------------------ our arm
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line
     import torch
     import centrifuger_b200 as cb
 
@@ -350,14 +375,33 @@ def main():
     if rank == 0:
         peak, peak_kind = measured_peak()
         s_ms, s_launch = stage["search"]
-        s_bytes = 120 * search_c["n_rank"] + 72 * search_c["n_access"] + 16 * search_c["n_search"] + bases * a.steps
-        achieved = (s_bytes / max(s_launch, 1)) / ((s_ms / max(s_launch, 1)) / 1000.0) / 1e9 if s_ms > 0 else 0.0
+        # Algorithmic bytes of the search kernel = what its counted operations must read in THIS
+        # library's HBM layout: one 32-byte occ sector per rank (the sp==ep symbol test reuses the
+        # sp sector), 16 B per lookup-table probe, 2.25 bits per read base (2-bit code + N bit).
+        # DESIGN.md section 3 states both this figure and the reference-layout one (120 B per
+        # Sequence_RunBlock::Rank, 72 B per Access: SURVEY.md 8(d)), reported below as well.
+        occ = clf.layout == 2
+        per_rank = 32 if occ else 120
+        per_access = 0 if occ else 72
+        s_bytes = (per_rank * search_c["n_rank"] + per_access * search_c["n_access"] + 16 * search_c["n_search"]
+                   + (bases * a.steps * 9) // 32)
+        s_bytes_ref = 120 * search_c["n_rank"] + 72 * search_c["n_access"] + 16 * search_c["n_search"] + bases * a.steps
+        per_launch_s = (s_ms / max(s_launch, 1)) / 1000.0
+        achieved = (s_bytes / max(s_launch, 1)) / per_launch_s / 1e9 if s_ms > 0 else 0.0
+        achieved_ref = (s_bytes_ref / max(s_launch, 1)) / per_launch_s / 1e9 if s_ms > 0 else 0.0
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get(a.workload, {}).get("k_search_dram_bytes_per_launch")
+            except Exception:
+                traffic = None
         total_alg = algorithmic_bytes(counters, n * a.steps, bases * a.steps)
         line = {
             "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": dev_ms_max / a.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "int64", "data": "synthetic", "config": dict(config, **{
-                "layout": {1: "run-block arrays as stored", 2: "64-byte occ lines (transcoded at load)"}[clf.layout],
+                "layout": {1: "run-block arrays as stored", 2: "32-byte occ sectors (transcoded on the GPU at load)"}[clf.layout],
                 "l2": "256 MiB device write between timed iterations (L2 flush)",
                 "index_hbm_bytes": clf.hbm_bytes, "min_hit_len": clf.min_hit_len}),
             "e2e": {"value": e2e_value, "unit": unit,
@@ -365,9 +409,12 @@ def main():
                     "d2h_bytes_per_step": int(n * 32 + n * w["k"] * 8)},
             "gpu_launches": int(launches_resident + launches_e2e),
             "roofline": {"bound": "hbm", "kernel": "k_search", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_kind": peak_kind,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_kind": peak_kind,
                          "algorithmic_bytes_per_launch": s_bytes / max(s_launch, 1),
                          "kernel_ms_per_launch": s_ms / max(s_launch, 1),
+                         "reference_layout_gbs": achieved_ref,
+                         "note": ("index fits the 126 MB L2: the sectors are served from L2, DRAM traffic is in `traffic`"
+                                  if clf.hbm_bytes < (120 << 20) else "index larger than L2"),
                          "pipeline_algorithmic_gbs": total_alg / (dev_ms_max / 1000.0) / 1e9 / world},
             "stage_ms_per_step": {k: v[0] / a.steps for k, v in stage.items()},
             "e2e_stage_ms_per_step": {k: v[0] for k, v in e2e_stage.items()},
