@@ -1059,7 +1059,6 @@ struct DustStateT {
   u64 p_valid;
   int head, size;
   int rv, rw, lv;
-  bool fast;  // suffix v == whole window and no interval pending: only cw is maintained (see dust_step)
 };
 
 // plain-array instantiation (host simulation, tests)
@@ -1150,7 +1149,6 @@ CFR_HD void dust_seg_init(DustIn &in, int seg_off, DustStateT<SW> &d, int &c1, i
   d.head = d.size = 0;
   d.rv = d.rw = d.lv = 0;
   d.p_valid = 0;
-  d.fast = true;
   c1 = in(seg_off);
   c2 = in(seg_off + 1);
 }
@@ -1160,53 +1158,16 @@ CFR_HD int dust_wstart(int wfinish) { return wfinish + 1 > 64 ? wfinish + 1 - 64
 // one iteration of SDust's main loop (:330-340) up to the point where the suffix v may
 // have to be shrunk (ShiftWindow's inner loop, :125-135); returns true when it must.
 // `t` receives the triplet that entered the window.
-//
-// FAST MODE.  While the suffix v is the whole window (lv == size) and no perfect
-// interval is pending, the literal algorithm keeps cv == cw, rv == rw, lv == size,
-// and every triplet count is <= 4 (the suffix invariant max c(v) <= 2T/10 = 4).  Then
-//   rw = sum C(cw,2) <= 6 * size/4 = 1.5 size  <  2 lv,
-// so the FindPerfect test (rw*10 > lv*T, T = 20) cannot fire and nothing is evicted:
-// the only thing that can happen is a fifth occurrence of a triplet.  Fast mode
-// therefore maintains just the window ring and cw, and materialises cv / rv / rw / lv
-// (cv := cw, rw := sum C(cw,2), rv := rw, lv := size) at the step where a count
-// reaches 5 -- exactly the state the literal code would be in -- before shrinking.
-// Literal mode returns to fast mode as soon as lv == size and no interval is pending.
 template <int SW>
 CFR_HD bool dust_step(DustIn &in, const DustOut &out, int seg_off, int wfinish, DustStateT<SW> &d, int &c1, int &c2,
                       int &t) {
   const int W = 64, T = 20;
+  const int wstart = dust_wstart(wfinish);
+  if (wstart > 0) dust_evict(d, out, seg_off, wstart - 1);
   const int c3 = in(seg_off + wfinish);
   t = c1 * 25 + c2 * 5 + c3;
   c1 = c2;
   c2 = c3;
-  if (!d.fast && d.lv == d.size && d.p_valid == 0) d.fast = true;
-  if (d.fast) {
-    if (d.size >= W - 2) {
-      const int old = d.win[d.head];
-      --d.cw[old];
-      d.head = (d.head + 1) & 63;
-      --d.size;
-    }
-    d.win[(d.head + d.size) & 63] = (unsigned char)t;
-    ++d.size;
-    const int cwt = ++d.cw[t];
-    if (cwt * 10 <= 2 * T) return false;
-    // leave fast mode: rebuild the literal state after this push
-    int rw = 0;
-    for (int i = 0; i < 128; i += 4) {
-      const u32 w = *reinterpret_cast<const u32 *>(&d.cw[i]);
-      *reinterpret_cast<u32 *>(&d.cv[i]) = w;
-      const int b0 = (int)(w & 0xff), b1 = (int)((w >> 8) & 0xff), b2 = (int)((w >> 16) & 0xff), b3 = (int)(w >> 24);
-      rw += (b0 * (b0 - 1) + b1 * (b1 - 1) + b2 * (b2 - 1) + b3 * (b3 - 1)) >> 1;
-    }
-    d.rw = rw;
-    d.rv = rw;
-    d.lv = d.size;
-    d.fast = false;
-    return true;  // cv[t] == 5: the suffix must be shrunk
-  }
-  const int wstart = dust_wstart(wfinish);
-  if (wstart > 0) dust_evict(d, out, seg_off, wstart - 1);
   // ShiftWindow (Dustmasker.hpp:106-136)
   if (d.size >= W - 2) {
     const int old = d.win[d.head];
@@ -1245,7 +1206,7 @@ CFR_HD void dust_shrink(DustStateT<SW> &d, int t) {
 
 // SDust :340 -- does the window hold a candidate perfect interval?
 template <int SW>
-CFR_HD bool dust_needs_find_perfect(const DustStateT<SW> &d) { return !d.fast && d.rw * 10 > d.lv * 20; }
+CFR_HD bool dust_needs_find_perfect(const DustStateT<SW> &d) { return d.rw * 10 > d.lv * 20; }
 
 // FindPerfect (Dustmasker.hpp:173-242) over the per-start slots
 template <int SW>
