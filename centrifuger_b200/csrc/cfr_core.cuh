@@ -1049,9 +1049,20 @@ struct ByteCol {
   CFR_HD unsigned char &operator[](int j) const { return base[(j >> 2) * (SW * 4) + (j & 3)]; }
 };
 
+// same column layout for 16-bit entries
+template <int SW>
+struct HalfCol {
+  unsigned char *base;
+  CFR_HD unsigned short &operator[](int j) const {
+    return *reinterpret_cast<unsigned short *>(base + (j >> 1) * (SW * 4) + (j & 1) * 2);
+  }
+};
+
 template <int SW>
 struct DustStateT {
-  ByteCol<SW> cw, cv;          // triplet counts of the window / of its suffix v, base-5 index (125 used)
+  // per triplet (base-5 index, 125 used): low byte = count in the window (cw), high byte = count
+  // in its suffix v (cv); one load / store updates both
+  HalfCol<SW> cc;
   ByteCol<SW> win;             // ring buffer of triplet indices; size <= 62
   unsigned short p_score[64];  // per start slot: score of the latest interval
   unsigned char p_span[64];    // its end - start - 2
@@ -1063,12 +1074,10 @@ struct DustStateT {
 
 // plain-array instantiation (host simulation, tests)
 struct DustState : DustStateT<1> {
-  alignas(4) unsigned char cw_store[128];
-  alignas(4) unsigned char cv_store[128];
+  alignas(4) unsigned char cc_store[256];
   alignas(4) unsigned char win_store[64];
   CFR_HD DustState() {
-    cw.base = cw_store;
-    cv.base = cv_store;
+    cc.base = cc_store;
     win.base = win_store;
   }
 };
@@ -1142,10 +1151,7 @@ CFR_HD void dust_evict(DustStateT<SW> &d, const DustOut &out, int seg_off, int s
 // start of SDust on a segment: clears the counters, primes the first two bases
 template <int SW>
 CFR_HD void dust_seg_init(DustIn &in, int seg_off, DustStateT<SW> &d, int &c1, int &c2) {
-  for (int i = 0; i < 128; i += 4) {
-    *reinterpret_cast<u32 *>(&d.cw[i]) = 0;
-    *reinterpret_cast<u32 *>(&d.cv[i]) = 0;
-  }
+  for (int i = 0; i < 128; i += 2) *reinterpret_cast<u32 *>(&d.cc[i]) = 0;
   d.head = d.size = 0;
   d.rv = d.rw = d.lv = 0;
   d.p_valid = 0;
@@ -1171,24 +1177,27 @@ CFR_HD bool dust_step(DustIn &in, const DustOut &out, int seg_off, int wfinish, 
   // ShiftWindow (Dustmasker.hpp:106-136)
   if (d.size >= W - 2) {
     const int old = d.win[d.head];
-    const int cwo = --d.cw[old];
-    d.rw -= cwo;
+    unsigned short &eo = d.cc[old];
+    int e = (int)eo - 1;  // --cw[old]
+    d.rw -= e & 0xff;
     d.head = (d.head + 1) & 63;
     --d.size;
     if (d.lv > d.size) {
-      const int cvo = --d.cv[old];
-      d.rv -= cvo;
+      e -= 0x100;  // --cv[old]
+      d.rv -= e >> 8;
       --d.lv;
     }
+    eo = (unsigned short)e;
   }
   d.win[(d.head + d.size) & 63] = (unsigned char)t;
   ++d.size;
   ++d.lv;
-  d.rw += d.cw[t];
-  ++d.cw[t];
-  const int cvt = d.cv[t];
+  unsigned short &et = d.cc[t];
+  const int e = et;
+  d.rw += e & 0xff;
+  const int cvt = e >> 8;
   d.rv += cvt;
-  d.cv[t] = (unsigned char)(cvt + 1);
+  et = (unsigned short)(e + 0x101);  // ++cw[t], ++cv[t]
   return (cvt + 1) * 10 > 2 * T;
 }
 
@@ -1197,8 +1206,10 @@ template <int SW>
 CFR_HD void dust_shrink(DustStateT<SW> &d, int t) {
   for (;;) {
     const int s = dust_win_at(d, d.size - d.lv);
-    const int cvs = --d.cv[s];
-    d.rv -= cvs;
+    unsigned short &es = d.cc[s];
+    const int e = (int)es - 0x100;  // --cv[s]
+    es = (unsigned short)e;
+    d.rv -= e >> 8;
     --d.lv;
     if (s == t) break;
   }
@@ -1218,8 +1229,9 @@ CFR_HD void dust_find_perfect(int wfinish, DustStateT<SW> &d) {
   int folded = wstart + d.size;  // starts >= folded have been folded into (max_score, max_cnt)
   for (int i = d.size - d.lv - 1; i >= 0; --i) {
     const int tt = dust_win_at(d, i);
-    rv += d.cv[tt];
-    ++d.cv[tt];
+    unsigned short &ett = d.cc[tt];
+    rv += ett >> 8;
+    ett = (unsigned short)(ett + 0x100);  // ++cv[tt]
     const int span = d.size - i - 1;
     if (rv * 10 > T * span) {
       const int start = i + wstart;
@@ -1244,7 +1256,7 @@ CFR_HD void dust_find_perfect(int wfinish, DustStateT<SW> &d) {
       }
     }
   }
-  for (int i = d.size - d.lv - 1; i >= 0; --i) --d.cv[dust_win_at(d, i)];
+  for (int i = d.size - d.lv - 1; i >= 0; --i) d.cc[dust_win_at(d, i)] -= 0x100;
 }
 
 // the tail loop of Dustmasker.hpp:343-350 (n = segment length): saves every remaining start

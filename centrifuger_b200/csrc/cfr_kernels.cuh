@@ -43,9 +43,8 @@ enum { CFR_DUST_THREADS = 128, CFR_DUST_SMEM = 80 * CFR_DUST_THREADS * 4 };
 __global__ void __launch_bounds__(CFR_DUST_THREADS) k_dust(const __grid_constant__ ChunkDev B, const int quorum) {
   extern __shared__ u32 dust_sm[];
   DustStateT<CFR_DUST_THREADS> d;
-  d.cw.base = reinterpret_cast<unsigned char *>(&dust_sm[threadIdx.x]);
-  d.cv.base = reinterpret_cast<unsigned char *>(&dust_sm[32 * CFR_DUST_THREADS + threadIdx.x]);
-  d.win.base = reinterpret_cast<unsigned char *>(&dust_sm[64 * CFR_DUST_THREADS + threadIdx.x]);
+  d.cc.base = reinterpret_cast<unsigned char *>(&dust_sm[threadIdx.x]);                          // 64 words
+  d.win.base = reinterpret_cast<unsigned char *>(&dust_sm[64 * CFR_DUST_THREADS + threadIdx.x]);  // 16 words
   dust_tasks(B, B.n_reads * (u64)B.mates, d, quorum);  // mates are claimed dynamically from B.dust_counter
 }
 
