@@ -19,5 +19,7 @@ PY
 done
 timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches_m700.csv python bench.py --workload m700 --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_launch_m700.log 2>&1
 timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches_c2.csv python bench.py --workload c2 --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_launch_c2.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_search|k_locate|k_dust" -s 3 -c 3 -o gpurun_out/prof4_m700 -f python bench.py --workload m700 --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu4.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_search|k_locate|k_dust|k_score|k_select|k_encode" -s 6 -c 6 -o gpurun_out/prof_r01_m700 -f python bench.py --workload m700 --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu4.log 2>&1
 tail -1 gpurun_out/ncu4.log
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_search|k_locate|k_dust|k_score|k_select|k_encode" -s 6 -c 6 -o gpurun_out/prof_r01_c2 -f python bench.py --workload c2 --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_c2_full.log 2>&1
+tail -1 gpurun_out/ncu_c2_full.log
