@@ -1268,6 +1268,22 @@ CFR_HD void dust_seg_tail(const DustOut &out, int seg_off, int n, DustStateT<SW>
   for (int s2 = base; s2 < base + 64; ++s2) dust_evict(d, out, seg_off, s2);  // every slot exactly once
 }
 
+// true when the mate holds no non-ACGT base at all (then MaskWithBuffer hands the whole
+// mate to SDust as one segment: no leading Ns to skip, no N run to split at)
+CFR_HD bool dust_all_acgt(const u32 *nmask, u64 base, int n) {
+  if (n <= 0) return true;
+  const u64 q0 = base, q1 = base + (u64)n - 1;
+  const u64 w0 = q0 >> 5, w1 = q1 >> 5;
+  u32 any = 0;
+  for (u64 w = w0; w <= w1; ++w) {
+    u32 m = ld32(nmask + w);
+    if (w == w0) m &= ~((1u << (q0 & 31)) - 1u);
+    if (w == w1 && (q1 & 31) != 31) m &= (1u << ((q1 & 31) + 1)) - 1u;
+    any |= m;
+  }
+  return any == 0;
+}
+
 // MaskWithBuffer's segment finder (Dustmasker.hpp:369-401): starting at cursor i,
 // the next run [i, last_valid] to hand to SDust, and the cursor after it
 CFR_HD void dust_next_segment(DustIn &in, int n, int i, int &last_valid, int &next_i) {

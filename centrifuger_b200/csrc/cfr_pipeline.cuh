@@ -107,9 +107,13 @@ CFR_HD void encode_stage(const ChunkDev &B, u64 w, u64 total_bytes) {
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-  for (int i = 0; i < 32; ++i) {
-    const int c = base_code((unsigned char)(q[i >> 3] >> ((i & 7) * 8)));
-    if (c > 3) nm |= 1u << i; else codes |= (u64)c << (2 * i);
+  for (int i = 0; i < 32; ++i) {  // branch-free: A,C,G,T = 0x41,0x43,0x47,0x54 -> ((b>>1)&3) = 0,1,3,2
+    const u32 b = (u32)(q[i >> 3] >> ((i & 7) * 8)) & 0xffu;
+    const u32 x = (b >> 1) & 3u;
+    const u32 c = x ^ (x >> 1);
+    const u32 valid = (b == 'A') | (b == 'C') | (b == 'G') | (b == 'T');
+    nm |= (valid ^ 1u) << i;
+    codes |= (u64)(c & (0u - valid)) << (2 * i);
   }
   if (n < 32) {  // padding reads as N
     const u32 keep = n == 0 ? 0u : ((1u << n) - 1u);
@@ -157,10 +161,19 @@ CFR_HD void dust_tasks(const ChunkDev &B, const u64 ntask, DustStateT<SW> &d, co
             in.base = base;
             in.widx = ~0ull;
             out.base = base;
-            if (len >= 3) {  // MaskWithBuffer: skip the leading Ns (Dustmasker.hpp:365-367)
-              cursor = 0;
-              while (cursor < len && in(cursor) == 4) ++cursor;
-              st = CFR_DS_SEG;
+            if (len >= 3) {
+              if (dust_all_acgt(B.mask_raw, base, len)) {  // common case: one segment, the whole mate
+                seg_off = 0;
+                seg_n = len;
+                cursor = len;
+                dust_seg_init(in, seg_off, d, c1, c2);
+                wfinish = 2;
+                st = CFR_DS_STEP;
+              } else {  // MaskWithBuffer: skip the leading Ns (Dustmasker.hpp:365-367)
+                cursor = 0;
+                while (cursor < len && in(cursor) == 4) ++cursor;
+                st = CFR_DS_SEG;
+              }
             }
           }
         }
