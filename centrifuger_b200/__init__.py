@@ -58,7 +58,7 @@ RESULT_DTYPE = np.dtype([("score", "<u8"), ("secondary_score", "<u8"), ("hit_len
 ABI_SYMBOLS = [
     "cfr_default_params", "cfr_open", "cfr_close", "cfr_last_error", "cfr_classify_batch",
     "cfr_batch_upload", "cfr_classify_resident", "cfr_batch_fetch", "cfr_batch_free",
-    "cfr_index_info", "cfr_seq_name", "cfr_rank_name", "cfr_orig_taxid", "cfr_seq_taxid",
+    "cfr_host_alloc", "cfr_host_free", "cfr_index_info", "cfr_seq_name", "cfr_rank_name", "cfr_orig_taxid", "cfr_seq_taxid",
     "cfr_format_tsv", "cfr_taxon_counts_device", "cfr_taxon_counts_read", "cfr_taxon_counts_reset",
     "cfr_get_counters", "cfr_reset_counters", "cfr_set_profiling", "cfr_get_stage_times",
     "cfr_get_stage_counters", "cfr_debug_bwt_rank", "cfr_debug_bwt_access",
@@ -90,6 +90,10 @@ def load_library():
     L.cfr_batch_fetch.argtypes = [vp, vp, vp, vp, vp]
     L.cfr_batch_free.argtypes = [vp, vp]
     L.cfr_batch_free.restype = None
+    L.cfr_host_alloc.argtypes = [C.c_size_t]
+    L.cfr_host_alloc.restype = vp
+    L.cfr_host_free.argtypes = [vp]
+    L.cfr_host_free.restype = None
     L.cfr_index_info.argtypes = [vp, i32]
     L.cfr_index_info.restype = u64
     L.cfr_seq_name.argtypes = [vp, u64]

@@ -592,6 +592,19 @@ void cfr_close(cfr_handle *h) {
   delete h;
 }
 
+void *cfr_host_alloc(size_t bytes) {
+  void *p = nullptr;
+  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+    fail(CFR_ERR_NOMEM, "cudaHostAlloc failed");
+    return nullptr;
+  }
+  return p;
+}
+
+void cfr_host_free(void *p) {
+  if (p) cudaFreeHost(p);
+}
+
 uint64_t cfr_index_info(const cfr_handle *h, int which) {
   if (!h) return 0;
   switch (which) {

@@ -12,12 +12,16 @@
 #include <getopt.h>
 #include <zlib.h>
 
+#include <algorithm>
+#include <condition_variable>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <ctime>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/centrifuger_b200.h"
@@ -48,7 +52,7 @@ static const char usage[] =
 
 enum {
   ARGV_NO_DUST = 256, ARGV_MIN_HITLEN, ARGV_HITK, ARGV_SECONDARY, ARGV_GPU, ARGV_BATCH, ARGV_LAYOUT,
-  ARGV_UNSUPPORTED
+  ARGV_UNSUPPORTED, ARGV_DRY_RUN
 };
 
 static const char *short_options = "x:1:2:u:i:o:t:k:hv";
@@ -60,6 +64,7 @@ static struct option long_options[] = {
     {"gpu", required_argument, 0, ARGV_GPU},
     {"batch", required_argument, 0, ARGV_BATCH},
     {"layout", required_argument, 0, ARGV_LAYOUT},
+    {"dry-run", no_argument, 0, ARGV_DRY_RUN},
     {"un", required_argument, 0, ARGV_UNSUPPORTED},
     {"cl", required_argument, 0, ARGV_UNSUPPORTED},
     {"merge-readpair", no_argument, 0, ARGV_UNSUPPORTED},
@@ -86,78 +91,98 @@ static void PrintLog(const char *fmt, ...) {
   fprintf(stderr, "[%s] %s\n", stime, buffer);
 }
 
-// Minimal FASTA/FASTQ reader with kseq.h semantics: name = first token after '>'/'@',
-// sequence lines concatenated, FASTQ quality skipped by length; '-' = stdin; gz ok.
+// FASTA/FASTQ reader with kseq.h semantics (name = first token after '>'/'@', sequence
+// lines concatenated, FASTQ quality skipped by length; '-' = stdin; gz ok), block-buffered
+// with memchr line splitting.
 class SeqReader {
  public:
   bool open(const std::string &path) {
     fp_ = path == "-" ? gzdopen(fileno(stdin), "r") : gzopen(path.c_str(), "r");
     if (!fp_) return false;
     gzbuffer(fp_, 1 << 20);
+    buf_.resize(4 << 20);
     len_ = pos_ = 0;
     eof_ = false;
-    last_ = 0;
     return true;
   }
   void close() {
     if (fp_) gzclose(fp_);
     fp_ = nullptr;
   }
-  // returns false at end of file
+  // appends the record's sequence to `seq`; returns false at end of file
   bool next(std::string &name, std::string &seq) {
-    int c;
-    if (last_ == 0) {
-      while ((c = getc_()) != -1 && c != '>' && c != '@') {
-      }
-      if (c == -1) return false;
-      last_ = c;
+    const char *ln;
+    size_t n;
+    // header line
+    for (;;) {
+      if (!line(ln, n)) return false;
+      if (n > 0 && (ln[0] == '>' || ln[0] == '@')) break;
     }
-    name.clear();
-    seq.clear();
-    // name up to the first space; the rest of the line is the comment
-    while ((c = getc_()) != -1 && c != '\n' && c != ' ' && c != '\t' && c != '\r') name.push_back((char)c);
-    while (c != -1 && c != '\n') c = getc_();
-    // sequence lines
-    while ((c = getc_()) != -1 && c != '>' && c != '+' && c != '@') {
-      if (c == '\n' || c == '\r') continue;
-      seq.push_back((char)c);
-      while ((c = getc_()) != -1 && c != '\n')
-        if (c != '\r') seq.push_back((char)c);
+    const bool fastq = ln[0] == '@';
+    size_t e = 1;
+    while (e < n && ln[e] != ' ' && ln[e] != '\t') ++e;
+    name.assign(ln + 1, e - 1);
+    // sequence lines: until a line starting with '+' (FASTQ), '>' or '@' (next record)
+    const size_t start = seq.size();
+    for (;;) {
+      if (!peek_line(ln, n)) return true;  // EOF ends the record
+      if (n > 0 && (ln[0] == '+' || ln[0] == '>' || ln[0] == '@')) break;
+      seq.append(ln, n);
+      consume();
     }
-    if (c == '>' || c == '@') {
-      last_ = c;
-      return true;
-    }
-    last_ = 0;
-    if (c != '+') return true;  // FASTA at EOF
-    // FASTQ: skip the '+' line, then read quality of the same length
-    while ((c = getc_()) != -1 && c != '\n') {
-    }
+    if (ln[0] != '+') return true;  // FASTA: next header stays in the buffer
+    (void)fastq;
+    consume();  // the '+' line
     size_t q = 0;
-    while (q < seq.size() && (c = getc_()) != -1)
-      if (c != '\n' && c != '\r') ++q;
+    const size_t want = seq.size() - start;
+    while (q < want) {  // quality lines (may start with '@' or '+'): by length
+      if (!line(ln, n)) return true;
+      q += n;
+    }
     return true;
   }
 
  private:
-  int getc_() {
-    if (pos_ >= len_) {
-      if (eof_) return -1;
-      len_ = gzread(fp_, buf_, sizeof(buf_));
-      pos_ = 0;
-      if (len_ <= 0) {
-        eof_ = true;
-        len_ = 0;
-        return -1;
-      }
-    }
-    return (unsigned char)buf_[pos_++];
+  // returns the next line without its terminator ('\r' stripped) and consumes it
+  bool line(const char *&p, size_t &n) {
+    if (!peek_line(p, n)) return false;
+    consume();
+    return true;
   }
+  bool peek_line(const char *&p, size_t &n) {
+    for (;;) {
+      const char *nl = (const char *)memchr(buf_.data() + pos_, '\n', len_ - pos_);
+      if (nl) {
+        p = buf_.data() + pos_;
+        n = (size_t)(nl - p);
+        next_ = pos_ + n + 1;
+        if (n > 0 && p[n - 1] == '\r') --n;
+        return true;
+      }
+      if (eof_) {
+        if (pos_ >= len_) return false;
+        p = buf_.data() + pos_;  // last line without '\n'
+        n = len_ - pos_;
+        next_ = len_;
+        if (n > 0 && p[n - 1] == '\r') --n;
+        return true;
+      }
+      // refill: keep the partial line at the front
+      if (pos_ > 0) {
+        memmove(&buf_[0], buf_.data() + pos_, len_ - pos_);
+        len_ -= pos_;
+        pos_ = 0;
+      }
+      if (len_ == buf_.size()) buf_.resize(buf_.size() * 2);
+      const int got = gzread(fp_, &buf_[len_], (unsigned)std::min<size_t>(buf_.size() - len_, 1u << 30));
+      if (got <= 0) eof_ = true; else len_ += (size_t)got;
+    }
+  }
+  void consume() { pos_ = next_; }
   gzFile fp_ = nullptr;
-  char buf_[1 << 16];
-  int len_ = 0, pos_ = 0;
+  std::string buf_;
+  size_t len_ = 0, pos_ = 0, next_ = 0;
   bool eof_ = false;
-  int last_ = 0;
 };
 
 // ReadFiles::RemoveReadIdSuffix (ReadFiles.hpp:82-90)
@@ -189,6 +214,77 @@ struct ReadSource {  // a list of files read back to back (ReadFiles::AddReadFil
   }
 };
 
+// One batch travelling through the ingest -> classify -> output pipeline.
+struct Batch {
+  std::string ids;              // read ids back to back
+  std::vector<uint32_t> id_off;  // n + 1
+  std::string seq1, seq2;
+  std::vector<uint64_t> off1, off2;
+  std::vector<cfr_result> results;
+  std::vector<uint64_t> assign;
+  size_t n = 0;
+  bool last = false;
+  void clear() {
+    ids.clear();
+    id_off.assign(1, 0);
+    seq1.clear();
+    seq2.clear();
+    off1.assign(1, 0);
+    off2.assign(1, 0);
+    n = 0;
+    last = false;
+  }
+};
+
+// a tiny blocking hand-off slot between two pipeline stages
+template <class T>
+class Slot {
+ public:
+  void put(T v) {
+    std::unique_lock<std::mutex> lk(m_);
+    cv_.wait(lk, [&] { return !full_; });
+    v_ = v;
+    full_ = true;
+    cv_.notify_all();
+  }
+  T take() {
+    std::unique_lock<std::mutex> lk(m_);
+    cv_.wait(lk, [&] { return full_; });
+    T v = v_;
+    full_ = false;
+    cv_.notify_all();
+    return v;
+  }
+
+ private:
+  std::mutex m_;
+  std::condition_variable cv_;
+  T v_{};
+  bool full_ = false;
+};
+
+static inline char *put_u64(char *p, uint64_t v) {
+  char tmp[24];
+  int n = 0;
+  do {
+    tmp[n++] = (char)('0' + v % 10);
+    v /= 10;
+  } while (v);
+  while (n) *p++ = tmp[--n];
+  return p;
+}
+static inline char *put_i32(char *p, int v) {
+  if (v < 0) {
+    *p++ = '-';
+    return put_u64(p, (uint64_t)(-(int64_t)v));
+  }
+  return put_u64(p, (uint64_t)v);
+}
+static inline char *put_str(char *p, const char *s, size_t n) {
+  memcpy(p, s, n);
+  return p + n;
+}
+
 int main(int argc, char *argv[]) {
   if (argc <= 1) {  // CentrifugerClass.cpp:347-351: usage on stderr, exit 0
     fprintf(stderr, "%s", usage);
@@ -201,6 +297,7 @@ int main(int argc, char *argv[]) {
   bool hasMate = false, interleaved = false;
   int device = 0;
   long batchReads = 1 << 20;
+  bool dryRun = false;  // diagnostics: parse the inputs and print id<TAB>mate1<TAB>mate2, no GPU work
   int c, option_index = 0;
   while ((c = getopt_long(argc, argv, short_options, long_options, &option_index)) != -1) {
     if (c == 'x') idxPrefix = optarg;
@@ -231,13 +328,30 @@ int main(int argc, char *argv[]) {
       if (!strcmp(optarg, "occ")) params.layout = CFR_LAYOUT_OCCLINE;
       else if (!strcmp(optarg, "runblock")) params.layout = CFR_LAYOUT_RUNBLOCK;
       else params.layout = CFR_LAYOUT_AUTO;
-    } else if (c == ARGV_UNSUPPORTED) {
+    } else if (c == ARGV_DRY_RUN) dryRun = true;
+    else if (c == ARGV_UNSUPPORTED) {
       PrintLog("Option --%s is not supported by the B200 classification path.", long_options[option_index].name);
       return EXIT_FAILURE;
     } else {
       fprintf(stderr, "%s", usage);
       return EXIT_FAILURE;
     }
+  }
+  if (dryRun) {
+    std::string name, name2, s1, s2;
+    for (;;) {
+      name.clear();
+      s1.clear();
+      s2.clear();
+      if (!reads.next(name, s1)) break;
+      RemoveReadIdSuffix(name);
+      if (hasMate && !(interleaved ? reads.next(name2, s2) : mates.next(name2, s2))) {
+        PrintLog("ERROR: The two mate-pair read files have different number of reads.");
+        return EXIT_FAILURE;
+      }
+      printf("%s\t%s\t%s\n", name.c_str(), s1.c_str(), s2.c_str());
+    }
+    return 0;
   }
   PrintLog("Centrifuger v" CENTRIFUGER_VERSION " starts.");
   if (idxPrefix == NULL) {
@@ -256,78 +370,140 @@ int main(int argc, char *argv[]) {
   PrintLog("Finishes loading index.");
   if (params.min_hit_len <= 0) PrintLog("Inferred --min-hitlen: %d", (int)cfr_index_info(h, 4));
 
-  // ResultWriter::OutputHeader (ResultWriter.hpp:186-197)
-  std::string out;
-  out.reserve(64 << 20);
-  out += "readID\tseqID\ttaxID\tscore\t2ndBestScore\thitLength\tqueryLength\tnumMatches\n";
-
+  // Three-stage pipeline over three rotating batches: the ingest thread parses batch i+1 while
+  // the GPU classifies batch i and the output thread formats batch i-1 (ResultWriter::Output,
+  // ResultWriter.hpp:199-236; rows in input order as in CentrifugerClass.cpp:690).
   const int k = params.max_result;
-  std::vector<std::string> ids;
-  std::string seq1, seq2, name, s, name2;
-  std::vector<uint64_t> off1, off2, assign;
-  std::vector<cfr_result> results;
+  Batch batches[3];
+  Slot<Batch *> free_slots[3];
+  Slot<Batch *> to_gpu, to_out;
+  for (auto &bt : batches) bt.clear();
   unsigned long totalCnt = 0, classifiedCnt = 0;
-  char line[1 << 16];
-  for (;;) {
-    ids.clear();
-    seq1.clear();
-    seq2.clear();
-    off1.assign(1, 0);
-    off2.assign(1, 0);
-    while ((long)ids.size() < batchReads) {
-      if (!reads.next(name, s)) break;
-      RemoveReadIdSuffix(name);
-      ids.push_back(name);
-      seq1 += s;
-      off1.push_back(seq1.size());
-      if (hasMate) {
-        bool ok = interleaved ? reads.next(name2, s) : mates.next(name2, s);
-        if (!ok) {
-          PrintLog("ERROR: The two mate-pair read files have different number of reads.");
-          return EXIT_FAILURE;
+  bool mate_mismatch = false;
+
+  std::thread ingest([&] {
+    std::string name, name2, tmp;
+    int bi = 0;
+    for (;;) {
+      Batch *bt = free_slots[bi].take();
+      bi = (bi + 1) % 3;
+      bt->clear();
+      while ((long)bt->n < batchReads) {
+        name.clear();
+        if (!reads.next(name, bt->seq1)) break;
+        RemoveReadIdSuffix(name);
+        bt->ids += name;
+        bt->id_off.push_back((uint32_t)bt->ids.size());
+        bt->off1.push_back(bt->seq1.size());
+        if (hasMate) {
+          const bool ok = interleaved ? reads.next(name2, bt->seq2) : mates.next(name2, bt->seq2);
+          if (!ok) {
+            mate_mismatch = true;
+            break;
+          }
+          bt->off2.push_back(bt->seq2.size());
         }
-        seq2 += s;
-        off2.push_back(seq2.size());
+        ++bt->n;
+      }
+      if (!mate_mismatch && hasMate && !interleaved && (long)bt->n < batchReads) {
+        tmp.clear();
+        if (mates.next(name2, tmp)) mate_mismatch = true;  // mate 1 ended first
+      }
+      bt->last = (long)bt->n < batchReads || mate_mismatch;
+      to_gpu.put(bt);
+      if (bt->last) break;
+    }
+  });
+
+  std::thread output([&] {
+    std::string out;
+    out.reserve(64 << 20);
+    // ResultWriter::OutputHeader (ResultWriter.hpp:186-197)
+    out += "readID\tseqID\ttaxID\tscore\t2ndBestScore\thitLength\tqueryLength\tnumMatches\n";
+    int bi = 0;
+    for (;;) {
+      Batch *bt = to_out.take();
+      for (size_t i = 0; i < bt->n; ++i) {
+        const cfr_result &r = bt->results[i];
+        const char *id = bt->ids.data() + bt->id_off[i];
+        const size_t idn = bt->id_off[i + 1] - bt->id_off[i];
+        const size_t base = out.size();
+        ++totalCnt;
+        if (r.n_assign > 0) {
+          ++classifiedCnt;
+          const int m = r.n_assign < k ? r.n_assign : k;
+          for (int j = 0; j < m; ++j) {
+            const uint64_t a = bt->assign[i * (size_t)k + j];
+            const char *nm = r.by_rank ? cfr_rank_name(h, a) : cfr_seq_name(h, a);
+            const uint64_t tax = r.by_rank ? cfr_orig_taxid(h, a) : cfr_orig_taxid(h, cfr_seq_taxid(h, a));
+            const size_t nn = strlen(nm);
+            const size_t at = out.size();
+            out.resize(at + idn + nn + 160);
+            char *p = &out[at];
+            p = put_str(p, id, idn); *p++ = '\t';
+            p = put_str(p, nm, nn); *p++ = '\t';
+            p = put_u64(p, tax); *p++ = '\t';
+            p = put_u64(p, r.score); *p++ = '\t';
+            p = put_u64(p, r.secondary_score); *p++ = '\t';
+            p = put_i32(p, r.hit_length); *p++ = '\t';
+            p = put_i32(p, r.query_length); *p++ = '\t';
+            p = put_i32(p, r.n_assign); *p++ = '\n';
+            out.resize((size_t)(p - out.data()));
+          }
+        } else {
+          out.resize(base + idn + 64);
+          char *p = &out[base];
+          p = put_str(p, id, idn);
+          p = put_str(p, "\tunclassified\t0\t0\t0\t0\t", 22);
+          p = put_i32(p, r.query_length);
+          p = put_str(p, "\t1\n", 3);
+          out.resize((size_t)(p - out.data()));
+        }
+        if (out.size() > (48u << 20)) {
+          fwrite(out.data(), 1, out.size(), stdout);
+          out.clear();
+        }
+      }
+      const bool last = bt->last;
+      free_slots[bi].put(bt);
+      bi = (bi + 1) % 3;
+      if (last) break;
+    }
+    fwrite(out.data(), 1, out.size(), stdout);
+    fflush(stdout);
+  });
+
+  for (int i = 0; i < 3; ++i) free_slots[i].put(&batches[i]);
+  int rc = 0;
+  for (;;) {
+    Batch *bt = to_gpu.take();
+    if (rc == 0 && bt->n > 0) {
+      bt->results.resize(bt->n);
+      bt->assign.resize(bt->n * (size_t)k);
+      cfr_read_batch b;
+      b.n_reads = bt->n;
+      b.seq1 = bt->seq1.data();
+      b.off1 = bt->off1.data();
+      b.seq2 = hasMate ? bt->seq2.data() : NULL;
+      b.off2 = hasMate ? bt->off2.data() : NULL;
+      st = cfr_classify_batch(h, &b, bt->results.data(), bt->assign.data(), NULL);
+      if (st != CFR_OK) {
+        PrintLog("ERROR: %s", cfr_last_error());
+        rc = EXIT_FAILURE;
+        bt->n = 0;
       }
     }
-    if (hasMate && !interleaved && (long)ids.size() < batchReads) {  // mate 1 ended: mate 2 must end too
-      if (mates.next(name2, s)) {
-        PrintLog("ERROR: The two mate-pair read files have different number of reads.");
-        return EXIT_FAILURE;
-      }
-    }
-    if (ids.empty()) break;
-    const size_t n = ids.size();
-    results.resize(n);
-    assign.resize(n * (size_t)k);
-    cfr_read_batch b;
-    b.n_reads = n;
-    b.seq1 = seq1.data();
-    b.off1 = off1.data();
-    b.seq2 = hasMate ? seq2.data() : NULL;
-    b.off2 = hasMate ? off2.data() : NULL;
-    st = cfr_classify_batch(h, &b, results.data(), assign.data(), NULL);
-    if (st != CFR_OK) {
-      PrintLog("ERROR: %s", cfr_last_error());
-      return EXIT_FAILURE;
-    }
-    for (size_t i = 0; i < n; ++i) {  // ResultWriter::Output (ResultWriter.hpp:199-236)
-      const int w = cfr_format_tsv(h, ids[i].c_str(), &results[i], &assign[i * (size_t)k], line, sizeof(line));
-      if (w < 0) {
-        PrintLog("ERROR: output row too long for read %s", ids[i].c_str());
-        return EXIT_FAILURE;
-      }
-      out.append(line, (size_t)w);
-      ++totalCnt;
-      if (results[i].n_assign > 0) ++classifiedCnt;
-      if (out.size() > (48u << 20)) {
-        fwrite(out.data(), 1, out.size(), stdout);
-        out.clear();
-      }
-    }
+    const bool last = bt->last;
+    to_out.put(bt);
+    if (last) break;
   }
-  fwrite(out.data(), 1, out.size(), stdout);
-  fflush(stdout);
+  ingest.join();
+  output.join();
+  if (mate_mismatch) {
+    PrintLog("ERROR: The two mate-pair read files have different number of reads.");  // CentrifugerClass.cpp:121-125
+    return EXIT_FAILURE;
+  }
+  if (rc) return rc;
   // ResultWriter::Finalize (ResultWriter.hpp:279-283)
   PrintLog("Processed %lu read fragments, and %lu (%.2lf%%) can be classified.", totalCnt, classifiedCnt,
            (double)classifiedCnt / (double)totalCnt * 100.0);

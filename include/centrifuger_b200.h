@@ -121,6 +121,11 @@ int cfr_classify_resident(cfr_handle *h, cfr_device_batch *b, void *stream);
 int cfr_batch_fetch(cfr_handle *h, cfr_device_batch *b, cfr_result *results, uint64_t *ids, void *stream);
 void cfr_batch_free(cfr_handle *h, cfr_device_batch *b);
 
+/* Page-locked host memory for read / result buffers (cudaHostAlloc), so callers that do
+ * not link the CUDA runtime can still get asynchronous, overlapped copies. */
+void *cfr_host_alloc(size_t bytes);
+void cfr_host_free(void *p);
+
 /* index facts: 0 n, 1 b, 2 blockCnt, 3 firstISA, 4 min_hit_len in effect,
  * 5 nodeCnt, 6 seqCnt(+extra), 7 root ctid, 8 layout in use, 9 HBM bytes held,
  * 10 sampleRate, 11 precomputeWidth, 12 max_result */
