@@ -57,7 +57,7 @@ RESULT_DTYPE = np.dtype([("score", "<u8"), ("secondary_score", "<u8"), ("hit_len
 # every symbol include/centrifuger_b200.h declares
 ABI_SYMBOLS = [
     "cfr_default_params", "cfr_open", "cfr_close", "cfr_last_error", "cfr_classify_batch",
-    "cfr_batch_upload", "cfr_classify_resident", "cfr_batch_fetch", "cfr_batch_free",
+    "cfr_submit_batch", "cfr_wait_batch", "cfr_batch_upload", "cfr_classify_resident", "cfr_batch_fetch", "cfr_batch_free",
     "cfr_host_alloc", "cfr_host_free", "cfr_index_info", "cfr_seq_name", "cfr_rank_name", "cfr_orig_taxid", "cfr_seq_taxid",
     "cfr_format_tsv", "cfr_taxon_counts_device", "cfr_taxon_counts_read", "cfr_taxon_counts_reset",
     "cfr_get_counters", "cfr_reset_counters", "cfr_set_profiling", "cfr_get_stage_times",
@@ -85,6 +85,8 @@ def load_library():
     L.cfr_close.restype = None
     L.cfr_last_error.restype = C.c_char_p
     L.cfr_classify_batch.argtypes = [vp, C.POINTER(ReadBatch), vp, vp, vp]
+    L.cfr_submit_batch.argtypes = [vp, C.POINTER(ReadBatch), vp, vp, vp, C.POINTER(C.c_int)]
+    L.cfr_wait_batch.argtypes = [vp, C.c_int]
     L.cfr_batch_upload.argtypes = [vp, C.POINTER(ReadBatch), vp, C.POINTER(vp)]
     L.cfr_classify_resident.argtypes = [vp, vp, vp]
     L.cfr_batch_fetch.argtypes = [vp, vp, vp, vp, vp]
@@ -258,6 +260,23 @@ class Classifier:
     def query(self, r1, r2=None):
         res, ids = self.classify([r1], None if r2 is None else [r2])
         return res[0], ids[0]
+
+    def submit(self, seq1, off1, seq2=None, off2=None, stream=None, out=None):
+        """Streaming form: enqueue one batch (pinned host buffers) and return (ticket, results, ids, keep).
+        Results are valid after wait(ticket); keep the returned objects alive until then."""
+        n = len(off1) - 1
+        b = make_batch(seq1, off1, seq2, off2, n)
+        if out is None:
+            res = np.zeros(n, dtype=RESULT_DTYPE)
+            ids = np.zeros(max(1, n * self.k), dtype=np.uint64)
+        else:
+            res, ids = out
+        t = C.c_int(-1)
+        self._check(self.L.cfr_submit_batch(self.h, C.byref(b), _ptr(res), _ptr(ids), stream, C.byref(t)))
+        return t.value, res, ids, (b, seq1, off1, seq2, off2)
+
+    def wait(self, ticket):
+        self._check(self.L.cfr_wait_batch(self.h, ticket))
 
     def upload(self, seq1, off1, seq2=None, off2=None, stream=None):
         n = len(off1) - 1

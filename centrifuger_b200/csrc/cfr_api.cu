@@ -100,6 +100,13 @@ struct cfr_handle {
     u32 n_def;
     u32 pad;
   } *pinned_scalars = nullptr;  // [2], cudaHostAlloc
+  // cfr_submit_batch / cfr_wait_batch: one job per slot
+  struct Job {
+    int ticket = -1;  // -1 = slot idle
+    cfr_result *results = nullptr;
+    uint64_t *ids = nullptr;
+  } jobs[2];
+  int next_ticket = 0;
   // stage profiling (CUDA events on the launch stream)
   bool profile = false;
   struct EvPair {
@@ -713,6 +720,15 @@ static int pipeline_drain(cfr_handle *h, int slot, cfr_result *results, uint64_t
   return CFR_OK;
 }
 
+static int job_finish(cfr_handle *h, int slot) {
+  cfr_handle::Job &j = h->jobs[slot];
+  if (j.ticket < 0) return CFR_OK;
+  int st = pipeline_drain(h, slot, j.results, j.ids, h->s_comp[slot]);
+  j.ticket = -1;
+  if (st) return st;
+  return check_device_errors(h, h->s_comp[slot]);
+}
+
 int cfr_classify_batch(cfr_handle *h, const cfr_read_batch *in, cfr_result *results, uint64_t *ids, void *stream) {
   if (!h || !in || (in->n_reads && (!results || !ids))) return fail(CFR_ERR_ARG, "null argument");
   if (in->n_reads && (!in->seq1 || !in->off1)) return fail(CFR_ERR_ARG, "seq1/off1 missing");
@@ -721,6 +737,7 @@ int cfr_classify_batch(cfr_handle *h, const cfr_read_batch *in, cfr_result *resu
   cudaStream_t sc = pick_stream(h, stream);
   int st = pipeline_init(h);
   if (st) return st;
+  if ((st = job_finish(h, 0)) || (st = job_finish(h, 1))) return st;  // complete streaming jobs first
   const u64 cap = h->params.max_batch_reads > 0 ? (u64)h->params.max_batch_reads : (1ull << 20);
   // Chunk plan.  Every chunk pays a fixed cost (the critical path of its slowest read in each
   // kernel), so few chunks are better for the GPU; but the first upload and the last download are
@@ -784,6 +801,53 @@ int cfr_classify_batch(cfr_handle *h, const cfr_read_batch *in, cfr_result *resu
   CUDA_TRY(cudaStreamSynchronize(h->s_comp[0]));
   CUDA_TRY(cudaStreamSynchronize(h->s_comp[1]));
   return check_device_errors(h, sc);
+}
+
+int cfr_submit_batch(cfr_handle *h, const cfr_read_batch *in, cfr_result *results, uint64_t *ids, void *stream,
+                     int *ticket) {
+  if (!h || !in || !ticket || (in->n_reads && (!results || !ids))) return fail(CFR_ERR_ARG, "null argument");
+  if (in->n_reads && (!in->seq1 || !in->off1)) return fail(CFR_ERR_ARG, "seq1/off1 missing");
+  const u64 cap = h->params.max_batch_reads > 0 ? (u64)h->params.max_batch_reads : (1ull << 20);
+  if (in->n_reads > cap) return fail(CFR_ERR_ARG, "cfr_submit_batch: n_reads exceeds max_batch_reads");
+  CUDA_TRY(cudaSetDevice(h->device));
+  int st = pipeline_init(h);
+  if (st) return st;
+  const int slot = h->next_ticket & 1;
+  if ((st = job_finish(h, slot))) return st;  // at most two batches in flight
+  cfr_device_batch *b = &h->slots[slot];
+  cudaStream_t sc = pick_stream(h, stream);
+  CUDA_TRY(cudaEventRecord(h->ev_start, sc));  // ordered after the caller's stream
+  CUDA_TRY(cudaStreamWaitEvent(h->s_in, h->ev_start, 0));
+  CUDA_TRY(cudaStreamWaitEvent(h->s_comp[slot], h->ev_start, 0));
+  if ((st = upload_chunk(h, in, 0, in->n_reads, b, h->s_in))) return st;
+  CUDA_TRY(cudaEventRecord(h->ev_h2d[slot], h->s_in));
+  CUDA_TRY(cudaStreamWaitEvent(h->s_comp[slot], h->ev_h2d[slot], 0));
+  if ((st = cfr_classify_resident(h, b, h->s_comp[slot]))) return st;
+  CUDA_TRY(cudaEventRecord(h->ev_comp[slot], h->s_comp[slot]));
+  CUDA_TRY(cudaStreamWaitEvent(h->s_out, h->ev_comp[slot], 0));
+  const u64 k = (u64)h->P.max_result;
+  if (in->n_reads) {
+    CUDA_TRY(cudaMemcpyAsync(results, b->results.p, in->n_reads * sizeof(DevResult), cudaMemcpyDeviceToHost, h->s_out));
+    CUDA_TRY(cudaMemcpyAsync(ids, b->out_ids.p, in->n_reads * k * 8, cudaMemcpyDeviceToHost, h->s_out));
+  }
+  CUDA_TRY(cudaMemcpyAsync(&h->pinned_scalars[slot], b->scalars.p, 16, cudaMemcpyDeviceToHost, h->s_out));
+  CUDA_TRY(cudaEventRecord(h->ev_d2h[slot], h->s_out));
+  h->jobs[slot].ticket = h->next_ticket;
+  h->jobs[slot].results = results;
+  h->jobs[slot].ids = ids;
+  *ticket = h->next_ticket++;
+  return CFR_OK;
+}
+
+int cfr_wait_batch(cfr_handle *h, int ticket) {
+  if (!h || ticket < 0) return fail(CFR_ERR_ARG, "bad ticket");
+  CUDA_TRY(cudaSetDevice(h->device));
+  const int slot = ticket & 1;
+  if (h->jobs[slot].ticket != ticket) {
+    if (ticket < h->next_ticket) return CFR_OK;  // already completed (by a later submit)
+    return fail(CFR_ERR_ARG, "unknown ticket");
+  }
+  return job_finish(h, slot);
 }
 
 const char *cfr_seq_name(const cfr_handle *h, uint64_t seq_id) {

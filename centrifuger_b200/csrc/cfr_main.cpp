@@ -374,8 +374,9 @@ int main(int argc, char *argv[]) {
   // the GPU classifies batch i and the output thread formats batch i-1 (ResultWriter::Output,
   // ResultWriter.hpp:199-236; rows in input order as in CentrifugerClass.cpp:690).
   const int k = params.max_result;
-  Batch batches[3];
-  Slot<Batch *> free_slots[3];
+  enum { NBATCH = 4 };  // ingest (1) + in flight on the GPU (2) + output (1)
+  Batch batches[NBATCH];
+  Slot<Batch *> free_slots[NBATCH];
   Slot<Batch *> to_gpu, to_out;
   for (auto &bt : batches) bt.clear();
   unsigned long totalCnt = 0, classifiedCnt = 0;
@@ -386,7 +387,7 @@ int main(int argc, char *argv[]) {
     int bi = 0;
     for (;;) {
       Batch *bt = free_slots[bi].take();
-      bi = (bi + 1) % 3;
+      bi = (bi + 1) % NBATCH;
       bt->clear();
       while ((long)bt->n < batchReads) {
         name.clear();
@@ -466,17 +467,20 @@ int main(int argc, char *argv[]) {
       }
       const bool last = bt->last;
       free_slots[bi].put(bt);
-      bi = (bi + 1) % 3;
+      bi = (bi + 1) % NBATCH;
       if (last) break;
     }
     fwrite(out.data(), 1, out.size(), stdout);
     fflush(stdout);
   });
 
-  for (int i = 0; i < 3; ++i) free_slots[i].put(&batches[i]);
+  for (int i = 0; i < NBATCH; ++i) free_slots[i].put(&batches[i]);
   int rc = 0;
+  Batch *pending = NULL;  // submitted, not yet waited for
+  int pending_ticket = -1;
   for (;;) {
     Batch *bt = to_gpu.take();
+    int ticket = -1;
     if (rc == 0 && bt->n > 0) {
       bt->results.resize(bt->n);
       bt->assign.resize(bt->n * (size_t)k);
@@ -486,16 +490,33 @@ int main(int argc, char *argv[]) {
       b.off1 = bt->off1.data();
       b.seq2 = hasMate ? bt->seq2.data() : NULL;
       b.off2 = hasMate ? bt->off2.data() : NULL;
-      st = cfr_classify_batch(h, &b, bt->results.data(), bt->assign.data(), NULL);
+      // streaming form: this batch's upload overlaps the previous batch's kernels
+      st = cfr_submit_batch(h, &b, bt->results.data(), bt->assign.data(), NULL, &ticket);
       if (st != CFR_OK) {
         PrintLog("ERROR: %s", cfr_last_error());
         rc = EXIT_FAILURE;
         bt->n = 0;
       }
     }
-    const bool last = bt->last;
-    to_out.put(bt);
-    if (last) break;
+    if (pending) {
+      if (pending_ticket >= 0 && cfr_wait_batch(h, pending_ticket) != CFR_OK) {
+        PrintLog("ERROR: %s", cfr_last_error());
+        rc = EXIT_FAILURE;
+        pending->n = 0;
+      }
+      to_out.put(pending);
+    }
+    pending = bt;
+    pending_ticket = ticket;
+    if (bt->last) {
+      if (pending_ticket >= 0 && cfr_wait_batch(h, pending_ticket) != CFR_OK) {
+        PrintLog("ERROR: %s", cfr_last_error());
+        rc = EXIT_FAILURE;
+        pending->n = 0;
+      }
+      to_out.put(pending);
+      break;
+    }
   }
   ingest.join();
   output.join();

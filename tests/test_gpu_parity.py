@@ -250,3 +250,23 @@ def test_cli_binary_reproduces_reference_tsv(tiny_dir, manifest):
     assert r.returncode == 0 and b"-x FILE: index prefix" in r.stderr
     r = subprocess.run([exe, "-v"], stdout=subprocess.PIPE)
     assert r.stdout.decode().strip() == "Centrifuger v1.1.3-r347"
+
+
+def test_streaming_submit_wait(small_dir):
+    """cfr_submit_batch / cfr_wait_batch: several batches in flight give the same answers as the
+    synchronous call, in any wait order"""
+    idx = os.path.join(small_dir, "idx")
+    _, r1 = read_fastx(os.path.join(small_dir, "pe_150_1.fq"))
+    _, r2 = read_fastx(os.path.join(small_dir, "pe_150_2.fq"))
+    g = cb.Classifier(idx, k=5, arena_rows=6000)
+    parts = [(r1[i:i + 1500], r2[i:i + 1500]) for i in range(0, 7500, 1500)]
+    exp = [g.classify(a, b) for a, b in parts]
+    jobs = []
+    for a, b in parts:
+        s1, o1 = cb.pack_reads(a)
+        s2, o2 = cb.pack_reads(b)
+        jobs.append(g.submit(s1, o1, s2, o2))
+    for (tk, res, ids, keep), (eres, eids) in zip(reversed(jobs), reversed(exp)):
+        g.wait(tk)
+        assert np.array_equal(res, eres) and np.array_equal(ids.reshape(-1, 5), eids)
+    g.close()
