@@ -65,11 +65,11 @@ struct cfr_device_batch {
   u64 off_bias[2] = {0, 0};
   u64 arena_cap = 0;
   DevBuf seq_raw, codes, mask_raw, mask, off, strand_hits, strand_nhits, fhits, work, rows, seq_ids, rec0, rec1, best, tmp,
-      results, out_ids, deferred, scalars;  // scalars: {u64 arena_used, u32 n_deferred, pad}
+      results, out_ids, deferred, dust_list, scalars;  // scalars: {u64 arena_used, u32 n_deferred, pad}
   bool classified = false;
   void release() {
     DevBuf *all[] = {&seq_raw, &codes, &mask_raw, &mask, &off, &strand_hits, &strand_nhits, &fhits, &work, &rows, &seq_ids,
-                     &rec0, &rec1, &best, &tmp, &results, &out_ids, &deferred, &scalars};
+                     &rec0, &rec1, &best, &tmp, &results, &out_ids, &deferred, &dust_list, &scalars};
     for (DevBuf *b : all) b->release();
   }
 };
@@ -86,6 +86,7 @@ struct cfr_handle {
   size_t hbm_bytes = 0;
   int sm_count = 148;
   int search_blocks = 10;  // resident 128-thread blocks per SM targeted by k_search (CFR_B200_SEARCH_BLOCKS)
+  bool dust_screen = true;  // register-only screen in front of the full SDUST (CFR_B200_DUST_SCREEN=0 disables)
   u64 *d_taxon = nullptr;
   DevCounters *d_counters = nullptr;
   u64 launches = 0;
@@ -174,6 +175,18 @@ int grid_for(const cfr_handle *h, u64 tasks, int threads, int blocks_per_sm) {
   u64 cap = (u64)h->sm_count * blocks_per_sm;
   if (need < 1) need = 1;
   return (int)std::min(need, cap);
+}
+
+// DUST over the chunk: the register-only screen clears most mates, the full SDUST state
+// machine runs on the rest (scalars must be zero: dust_counter, dust_list_n)
+void launch_dust(cfr_handle *h, const ChunkDev &B, cudaStream_t s) {
+  const u64 ntask = B.n_reads * (u64)B.mates;
+  if (B.dust_list) {
+    k_dust_screen<<<grid_for(h, ntask, 128, 16), 128, 0, s>>>(B);
+    ++h->launches;
+  }
+  k_dust<<<grid_for(h, ntask, CFR_DUST_THREADS, 5), CFR_DUST_THREADS, CFR_DUST_SMEM, s>>>(B, h->P.quorum);
+  ++h->launches;
 }
 
 int upload_index(cfr_handle *h) {
@@ -343,6 +356,7 @@ int upload_chunk(cfr_handle *h, const cfr_read_batch *in, u64 r0, u64 r1, cfr_de
   if ((st = b->results.ensure(n * sizeof(DevResult)))) return st;
   if ((st = b->out_ids.ensure(n * (u64)h->P.max_result * 8))) return st;
   if ((st = b->deferred.ensure(n * 4 * 2))) return st;
+  if ((st = b->dust_list.ensure(n * 4 * (u64)mates))) return st;
   if ((st = b->scalars.ensure(64))) return st;
   // H2D
   if (len1) CUDA_TRY(cudaMemcpyAsync(b->seq_raw.p, in->seq1 + s1, len1, cudaMemcpyHostToDevice, s));
@@ -379,6 +393,8 @@ void fill_chunk(cfr_handle *h, cfr_device_batch *b, ChunkDev &B) {
   B.row_counter = (u64 *)((char *)b->scalars.p + 24);
   B.dust_counter = (u64 *)((char *)b->scalars.p + 32);
   B.arena_valid = (u64 *)((char *)b->scalars.p + 40);
+  B.dust_list_n = (u32 *)((char *)b->scalars.p + 48);
+  B.dust_list = h->dust_screen ? (u32 *)b->dust_list.p : nullptr;
   B.rows = (u64 *)b->rows.p;
   B.seq_ids = (u32 *)b->seq_ids.p;
   B.rec0 = (SeqRec *)b->rec0.p;
@@ -434,8 +450,7 @@ int run_first(cfr_handle *h, cfr_device_batch *b, cudaStream_t s) {
   }
   if (h->params.dust) {
     StageScope sc(h, s, CFR_STAGE_DUST);
-    k_dust<<<grid_for(h, B.n_reads * B.mates, CFR_DUST_THREADS, 5), CFR_DUST_THREADS, CFR_DUST_SMEM, s>>>(B, h->P.quorum);
-    ++h->launches;
+    launch_dust(h, B, s);
   }
   CUDA_TRY(cudaMemsetAsync(B.task_counter, 0, 8, s));
   {
@@ -548,6 +563,15 @@ int cfr_open(const char *idx_prefix, const cfr_params *p, int device, cfr_handle
   h->P.quorum = 8;
   if (const char *e = getenv("CFR_B200_QUORUM")) h->P.quorum = std::max(1, atoi(e));
   if (const char *e = getenv("CFR_B200_SEARCH_BLOCKS")) h->search_blocks = std::max(1, atoi(e));
+  if (const char *e = getenv("CFR_B200_DUST_SCREEN")) h->dust_screen = atoi(e) != 0;
+  // The index is read as independent random 32-byte sectors: ask L2 not to fetch the neighbouring
+  // sector(s) with every miss (the default fetch granularity is larger).  A hint; 32, 64 or 128.
+  {
+    size_t gran = 0;  // 0 = leave the device default
+    if (const char *e = getenv("CFR_B200_L2_FETCH")) gran = (size_t)std::max(0, atoi(e));
+    if (gran) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran);
+    cudaGetLastError();  // a device that ignores the hint is not an error
+  }
   if ((st = upload_index(h))) return bail(st);
   void *p2;
   if ((st = dev_alloc(h, &p2, (h->ix.node_cnt + 3) * 8))) return bail(st);
@@ -1078,10 +1102,9 @@ int cfr_debug_dust(cfr_handle *h, const cfr_read_batch *in, char *masked1, char 
   const u64 len2 = in->seq2 ? in->off2[in->n_reads] - in->off2[0] : 0;
   cudaMemsetAsync(b.scalars.p, 0, 64, h->stream);
   k_encode<<<grid_for(h, B.n_words, 256, 8), 256, 0, h->stream>>>(B, b.seq_bytes);
-  if (in->n_reads)
-    k_dust<<<grid_for(h, B.n_reads * B.mates, CFR_DUST_THREADS, 5), CFR_DUST_THREADS, CFR_DUST_SMEM, h->stream>>>(B, h->P.quorum);
+  if (in->n_reads) launch_dust(h, B, h->stream);
   k_apply_dust<<<grid_for(h, b.seq_bytes, 256, 8), 256, 0, h->stream>>>(B, (unsigned char *)outb.p, b.seq_bytes);
-  h->launches += 3;
+  h->launches += 2;
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess && len1) e = cudaMemcpyAsync(masked1, outb.p, len1, cudaMemcpyDeviceToHost, h->stream);
   if (e == cudaSuccess && masked2 && len2)

@@ -75,7 +75,17 @@ CFR_HD u64x2 ld128(const u64x2 *p) {
 // per-thread operation counters (flushed once per task batch)
 struct OpCount {
   u32 rank, access, search, locate, lf, extend, bases;
+  // occ-sector extends are counted as (steps, single-row steps) in the hot loop and folded into
+  // rank / access / extend by oc_fold: a range step is two ranks, a single-row step one rank + one access
+  u32 xext, xsingle;
 };
+
+CFR_HD void oc_fold(OpCount &oc) {
+  oc.extend += oc.xext;
+  oc.rank += 2u * oc.xext - oc.xsingle;
+  oc.access += oc.xsingle;
+  oc.xext = oc.xsingle = 0;
+}
 
 // base byte -> code: A,C,G,T -> 0..3, anything else (incl. lowercase) -> 4
 CFR_HD int base_code(unsigned char c) {
@@ -169,6 +179,29 @@ struct StrandSeq {
     if ((mw >> sh) & 1u) return 4;
     const int c = (int)((cw >> (2 * sh)) & 3ull);
     return rc ? 3 - c : c;
+  }
+  // ---- sequential cursor for the extend loop: a backward search reads strand positions
+  // p, p-1, p-2, ... ; in batch coordinates that is a walk by -1 (as read) or +1 (reverse complement)
+  int csh = 0;  // base index of the cursor inside the cached word
+  CFR_HD void seek(int p) {
+    const u64 q = base + (u64)(rc ? len - 1 - p : p);
+    widx = q >> 5;
+    csh = (int)(q & 31);
+    cw = ld64(codes + widx);
+    mw = ld32(nmask + widx);
+  }
+  CFR_HD int peek() const {  // 0..3, or 4 for anything that is not ACGT
+    const int c = (int)((cw >> (2 * csh)) & 3ull) ^ (rc ? 3 : 0);
+    return ((mw >> csh) & 1u) ? 4 : c;
+  }
+  CFR_HD void advance() {  // to the next lower strand position (which must exist)
+    csh += rc ? 1 : -1;
+    if (csh & ~31) {
+      widx += rc ? 1ull : ~0ull;
+      csh &= 31;
+      cw = ld64(codes + widx);
+      mw = ld32(nmask + widx);
+    }
   }
   // GetBackwardSearchInitialRange's loop (FMIndex.hpp:394-403) over the last W
   // bases of strand[0..m): true + the table key, or false + the number of valid
@@ -328,6 +361,10 @@ struct BwtRunBlock {
       nep = nsp + ((rb_access(ix, ep) == c) ? 0ull : ~0ull);
     }
   }
+  enum { STEPS_COUNTED_AT_CLOSE = 0 };
+  static CFR_HD void extend_step(const DevIndex &ix, int c, u64 sp, u64 ep, u64 &nsp, u64 &nep, OpCount &oc) {
+    extend(ix, c, sp, ep, nsp, nep, oc);
+  }
   // one LF step: i -> C[c] + Rank(c, i) - 1 with c = BWT[i]  (FMIndex.hpp:382-386,520)
   static CFR_HD u64 lf(const DevIndex &ix, u64 i, OpCount &oc) {
     ++oc.access;
@@ -356,14 +393,26 @@ CFR_HD u64 occ_match(u64 lo, u64 hi, int c) {
   return ~(lo ^ ml) & ~(hi ^ mh);
 }
 
-// # of symbol c before sector `sec` from its packed counters
+// # of symbol c before sector `sec` from its packed counters (branch-free: the four
+// symbols of a warp's lanes differ, a switch on c would serialise them)
 CFR_HD u64 occ_base(u64 w2, u64 w3, int c, u64 sec) {
-  const u64 M40 = 0xffffffffffull;
-  const u64 a = w2 & M40;
-  const u64 cc = (w2 >> 40) | ((w3 & 0xffffull) << 24);
-  const u64 g = (w3 >> 16) & M40;
+  const u32 x3 = (u32)(w3 >> 32);
+  const u64 a = (w2 & 0xffffffffull) | ((u64)(x3 & 0xffu) << 32);
+  const u64 cc = (w2 >> 32) | ((u64)((x3 >> 8) & 0xffu) << 32);
+  const u64 g = (w3 & 0xffffffffull) | ((u64)((x3 >> 16) & 0xffu) << 32);
   const u64 t = (sec << 6) - (a + cc + g);
-  return c == 0 ? a : (c == 1 ? cc : (c == 2 ? g : t));
+  const u64 r01 = (c & 1) ? cc : a;
+  const u64 r23 = (c & 1) ? t : g;
+  return (c & 2) ? r23 : r01;
+}
+
+CFR_HD OccLine occ_pack(u64 lo, u64 hi, u64 a, u64 c, u64 g) {
+  OccLine o;
+  o.lo = lo;
+  o.hi = hi;
+  o.w2 = (a & 0xffffffffull) | (c << 32);
+  o.w3 = (g & 0xffffffffull) | (((a >> 32) & 0xffull) << 32) | (((c >> 32) & 0xffull) << 40) | (((g >> 32) & 0xffull) << 48);
+  return o;
 }
 
 CFR_HD void occ_load(const OccLine *L, u64 &lo, u64 &hi, u64 &w2, u64 &w3) {
@@ -389,21 +438,30 @@ CFR_HD int occ_symbol(u64 lo, u64 hi, int s) { return (int)(((lo >> s) & 1ull) |
 
 struct BwtOccLine {
   // straight-line: both ranks and the symbol test are always computed, the range /
-  // single-row forms of FMIndex::BackwardExtend are selected at the end
-  static CFR_HD void extend(const DevIndex &ix, int c, u64 sp, u64 ep, u64 &nsp, u64 &nep, OpCount &oc) {
+  // single-row forms of FMIndex::BackwardExtend are selected at the end.  Returns sp != ep.
+  static CFR_HD bool extend_core(const DevIndex &ix, int c, u64 sp, u64 ep, u64 &nsp, u64 &nep) {
     const u64 off = ix.C[c];
     const bool range = sp != ep;
-    ++oc.extend;
-    ++oc.rank;
-    oc.rank += range ? 1u : 0u;
-    oc.access += range ? 0u : 1u;
     const OccRank a = occ_rank(ix, c, sp);      // Rank(c, sp, exclusive)
     const OccRank e = occ_rank(ix, c, ep + 1);  // Rank(c, ep, inclusive)
     const int sym = occ_symbol(a.lo, a.hi, (int)(ep & 63));  // BWT[ep] when sp == ep (same sector as sp)
-    nsp = off + a.count + last_chr_fix(ix, c, sp, 0);
-    const u64 nep_range = off + e.count + last_chr_fix(ix, c, ep, 1) - 1;
+    // FMIndex::Rank's correction for the missing '$' (FMIndex.hpp:359), both forms at once
+    const u64 is_last = c == ix.last_code ? 1ull : 0ull;
+    nsp = off + a.count + (is_last & (sp <= ix.first_isa ? 1ull : 0ull));
+    const u64 nep_range = off + e.count + (is_last & (ep < ix.first_isa ? 1ull : 0ull)) - 1;
     const u64 nep_single = nsp + ((sym == c) ? 0ull : ~0ull);
     nep = range ? nep_range : nep_single;
+    return range;
+  }
+  static CFR_HD void extend(const DevIndex &ix, int c, u64 sp, u64 ep, u64 &nsp, u64 &nep, OpCount &oc) {
+    ++oc.xext;
+    oc.xsingle += extend_core(ix, c, sp, ep, nsp, nep) ? 0u : 1u;
+  }
+  // the search state machine's form: the number of steps of a search is added when the search
+  // closes (search_tasks), only the single-row steps are counted here
+  enum { STEPS_COUNTED_AT_CLOSE = 1 };
+  static CFR_HD void extend_step(const DevIndex &ix, int c, u64 sp, u64 ep, u64 &nsp, u64 &nep, OpCount &oc) {
+    oc.xsingle += extend_core(ix, c, sp, ep, nsp, nep) ? 0u : 1u;
   }
   static CFR_HD u64 lf(const DevIndex &ix, u64 i, OpCount &oc) {
     ++oc.access;
@@ -1282,6 +1340,82 @@ CFR_HD bool dust_all_acgt(const u32 *nmask, u64 base, int n) {
     any |= m;
   }
   return any == 0;
+}
+
+// ---- register-only screen: can SDUST mask anything in this (all-ACGT) mate? ----
+//
+// FindPerfect (Dustmasker.hpp:173-242) masks a run of k triplets S only when its
+// score exceeds the threshold: sum_t C(c_t,2) * 10 > T * (k-1) with T = 20, i.e.
+//     f(S) = sum_t C(c_t,2) - 2(k-1) = 2 + sum_t g(c_t) > 0,   g(c) = c(c-5)/2,
+// c_t = multiplicity of triplet t in S.  g(1..4) = -2,-3,-3,-2, g(5) = 0, g(6) = 3,
+// so f(S) > 0 needs either a triplet with c_t >= 6, or every triplet of S having
+// c_t = 5 exactly (k = 5m; m = 1 is a homopolymer run, m >= 2 puts two classes with
+// five copies into one window).  S lies inside the 62-triplet window that ends at its
+// last triplet, so when that triplet (or the 6th copy) enters the window the window
+// counts satisfy: some count >= 6, or the entering class has >= 5 copies and either ends a
+// run of five identical triplets (seven identical bases) or a second class has >= 5 copies too.  If that never happens
+// while the window slides over the mate, SDUST masks nothing and the mate can skip
+// the full algorithm.  The window counts are kept bit-sliced in three 64-bit
+// registers (one bit per triplet class and plane), so the screen touches no memory
+// beyond the packed read itself.  Returns true when the full SDUST must run.
+CFR_HD u64 dust_stream_word(const u64 *codes, u64 q0, int k) {  // 32 bases from q0 + 32k
+  const u64 wi = (q0 >> 5) + (u64)k;
+  const int sh = 2 * (int)(q0 & 31);
+  const u64 a = ld64(codes + wi);
+  if (sh == 0) return a;
+  return (a >> sh) | (ld64(codes + wi + 1) << (64 - sh));
+}
+
+CFR_HD bool dust_screen(const u64 *codes, u64 q0, int len) {
+  const int nt = len - 2;  // triplets; fewer than 5 can never reach the threshold
+  if (nt < 5) return false;
+  const u64 HOMO = 1ull | (1ull << 21) | (1ull << 42) | (1ull << 63);  // AAA, CCC, GGG, TTT
+  u64 b0 = 0, b1 = 0, b2 = 0;  // bit planes of the per-class window counts
+  u64 prev2 = 0, prev1 = 0, cur = dust_stream_word(codes, q0, 0);
+  bool need = false;
+  for (int k = 0; 32 * k < nt; ++k) {
+    const u64 nxt = 32 * (k + 1) < len ? dust_stream_word(codes, q0, k + 1) : 0ull;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int j = 0; j < 32; ++j) {
+      const int i = 32 * k + j;
+      if (i < nt) {
+        if (i >= 62) {  // the window holds 62 triplets: triplet i-62 = base 32(k-2) + j+2 leaves first
+          const int jj = j + 2;
+          u64 o;
+          if (jj <= 29) o = prev2 >> (2 * jj);
+          else if (jj <= 31) o = (prev2 >> (2 * jj)) | (prev1 << (64 - 2 * jj));
+          else o = prev1 >> (2 * (jj - 32));
+          const u64 mo = 1ull << (o & 63ull);
+          const u64 br0 = ~b0 & mo;  // borrow chain of count[o] -= 1
+          b0 ^= mo;
+          const u64 br1 = ~b1 & br0;
+          b1 ^= br0;
+          b2 ^= br1;
+        }
+        u64 t = cur >> (2 * j);
+        if (j > 29) t |= nxt << (64 - 2 * j);
+        const u64 m = 1ull << (t & 63ull);
+        const u64 c0 = b0 & m;  // carry chain of count[t] += 1
+        b0 ^= m;
+        const u64 c1 = b1 & c0;
+        b1 ^= c0;
+        b2 ^= c1;
+        const u64 h5 = b2 & (b0 | b1);  // classes with >= 5 copies in the window
+        if (h5 & m) {
+          // the four bases in front of triplet i (8 bits); i >= 4 here because count[t] >= 5
+          const u64 x = j >= 4 ? cur >> (2 * (j - 4)) : (prev1 >> (56 + 2 * j)) | (cur << (8 - 2 * j));
+          const bool homo7 = (m & HOMO) != 0 && (x & 0xffull) == (t & 3ull) * 0x55ull;  // five identical triplets in a row
+          need = need || (b2 & b1 & m) != 0 || (h5 & ~m) != 0 || homo7;
+        }
+      }
+    }
+    prev2 = prev1;
+    prev1 = cur;
+    cur = nxt;
+  }
+  return need;
 }
 
 // MaskWithBuffer's segment finder (Dustmasker.hpp:369-401): starting at cursor i,

@@ -8,8 +8,9 @@
 
 namespace cfrb200 {
 
-__device__ __forceinline__ void flush_counts(const OpCount &oc, DevCounters *c) {
+__device__ __forceinline__ void flush_counts(OpCount oc, DevCounters *c) {
   const unsigned full = 0xffffffffu;
+  oc_fold(oc);
   const u32 r = __reduce_add_sync(full, oc.rank), a = __reduce_add_sync(full, oc.access),
             s = __reduce_add_sync(full, oc.search), l = __reduce_add_sync(full, oc.locate),
             f = __reduce_add_sync(full, oc.lf), e = __reduce_add_sync(full, oc.extend);
@@ -36,6 +37,24 @@ __global__ void k_apply_dust(const __grid_constant__ ChunkDev B, unsigned char *
     out[q] = ((B.dust_bits[q >> 5] >> (q & 31)) & 1u) ? (unsigned char)'N' : B.seq_raw[q];
 }
 
+// SDUST screen: one mate per thread, registers only.  Mates that may hold a masked interval are
+// appended to B.dust_list (one atomic per warp); k_dust then runs the full SDUST on those only.
+__global__ void __launch_bounds__(128) k_dust_screen(const __grid_constant__ ChunkDev B) {
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const u64 ntask = B.n_reads * (u64)B.mates;
+  const u64 stride = (u64)gridDim.x * blockDim.x;
+  for (u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x; t - lane < ntask; t += stride) {
+    const bool need = t < ntask && dust_screen_stage(B, t);
+    const u32 m = __ballot_sync(full, need);
+    if (m == 0) continue;
+    u32 base = 0;
+    if (lane == 0) base = atomicAdd(B.dust_list_n, (u32)__popc(m));
+    base = __shfl_sync(full, base, 0);
+    if (need) B.dust_list[base + (u32)__popc(m & ((1u << lane) - 1u))] = (u32)t;
+  }
+}
+
 // SDUST: one mate per thread.  The data-dependent triplet counters and the window
 // ring live in shared memory, one bank column per thread (80 words x 128 threads
 // = 40 KiB per block), so their updates are conflict-free single wavefronts.
@@ -45,7 +64,8 @@ __global__ void __launch_bounds__(CFR_DUST_THREADS) k_dust(const __grid_constant
   DustStateT<CFR_DUST_THREADS> d;
   d.cc.base = reinterpret_cast<unsigned char *>(&dust_sm[threadIdx.x]);                          // 64 words
   d.win.base = reinterpret_cast<unsigned char *>(&dust_sm[64 * CFR_DUST_THREADS + threadIdx.x]);  // 16 words
-  dust_tasks(B, B.n_reads * (u64)B.mates, d, quorum);  // mates are claimed dynamically from B.dust_counter
+  // mates are claimed dynamically from B.dust_counter (through B.dust_list when the screen ran)
+  dust_tasks(B, B.dust_list ? (u64)*B.dust_list_n : B.n_reads * (u64)B.mates, d, quorum);
 }
 
 // MINB = resident blocks per SM the register allocation must allow (occupancy knob)
@@ -150,15 +170,6 @@ __global__ void __launch_bounds__(128) k_score(const __grid_constant__ DevIndex 
 // One thread per sector: 3 exclusive Sequence_RunBlock::Rank queries give the
 // counters, 64 Sequence_RunBlock::Access queries give the symbols -- the literal
 // device port of the reference's rank/access does the decoding.
-CFR_HD OccLine occ_pack(u64 lo, u64 hi, u64 a, u64 c, u64 g) {
-  OccLine o;
-  o.lo = lo;
-  o.hi = hi;
-  o.w2 = (a & 0xffffffffffull) | (c << 40);
-  o.w3 = ((c >> 24) & 0xffffull) | ((g & 0xffffffffffull) << 16);
-  return o;
-}
-
 __global__ void __launch_bounds__(128) k_transcode(const __grid_constant__ DevIndex ix, OccLine *out, u64 n_lines) {
   const u64 stride = (u64)gridDim.x * blockDim.x;
   for (u64 L = (u64)blockIdx.x * blockDim.x + threadIdx.x; L < n_lines; L += stride) {

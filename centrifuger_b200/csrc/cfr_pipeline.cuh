@@ -41,6 +41,8 @@ struct ChunkDev {
   u64 *task_counter;  // next strand task (dynamic fetch by the search warps)
   u64 *row_counter;   // next arena row (dynamic fetch by the locate warps)
   u64 *dust_counter;  // next mate (dynamic fetch by the DUST warps)
+  u32 *dust_list;     // mates the register-only screen could not clear (nullptr = every mate runs SDUST)
+  u32 *dust_list_n;   // number of entries in dust_list
   u64 *rows;
   u32 *seq_ids;
   SeqRec *rec0, *rec1;
@@ -154,8 +156,9 @@ CFR_HD void dust_tasks(const ChunkDev &B, const u64 ntask, DustStateT<SW> &d, co
           if (claimed >= ntask) {
             st = CFR_DS_DONE;
           } else {
-            const u64 read = claimed / (u64)B.mates;
-            const int mate = (int)(claimed % (u64)B.mates);
+            const u64 task = B.dust_list ? (u64)B.dust_list[claimed] : claimed;
+            const u64 read = task / (u64)B.mates;
+            const int mate = (int)(task % (u64)B.mates);
             const u64 base = B.off[mate][read] - B.off_bias[mate];
             len = (int)(B.off[mate][read + 1] - B.off[mate][read]);
             in.base = base;
@@ -221,6 +224,19 @@ CFR_HD void dust_tasks(const ChunkDev &B, const u64 ntask, DustStateT<SW> &d, co
   }
 }
 
+// The register-only screen (dust_screen, cfr_core.cuh) for mate `task`: true when the mate
+// must go through the full SDUST (it holds a non-ACGT byte, or the screen cannot rule
+// out a masked interval).
+CFR_HD bool dust_screen_stage(const ChunkDev &B, u64 task) {
+  const u64 read = task / (u64)B.mates;
+  const int mate = (int)(task % (u64)B.mates);
+  const u64 base = B.off[mate][read] - B.off_bias[mate];
+  const int len = (int)(B.off[mate][read + 1] - B.off[mate][read]);
+  if (len < 3) return false;  // MaskWithBuffer returns at once
+  if (!dust_all_acgt(B.mask_raw, base, len)) return true;
+  return dust_screen(B.codes, base, len);
+}
+
 // sequential form: one mate (host-side diagnostics)
 template <int SW>
 CFR_HD void dust_stage(const ChunkDev &B, u64 task, DustStateT<SW> &d) {
@@ -259,7 +275,6 @@ template <class Bwt>
 CFR_HD void search_tasks(const DevIndex &ix, const DevParams &P, const ChunkDev &B, const u64 ntask, OpCount &oc) {
   const int W = ix.pre_width, mhl = P.min_hit_len, S = 2 * B.mates;
   StrandSeq s{B.codes, B.mask, 0, 0, 0};
-  Hit *out = nullptr;
   u64 cur = 0, sp = 0, ep = 0;
   int nh = 0, remaining = 0, l = 0;
   int st = CFR_ST_FETCH;
@@ -273,12 +288,18 @@ CFR_HD void search_tasks(const DevIndex &ix, const DevParams &P, const ChunkDev 
         if (CFR_BALLOT(st == CFR_ST_CLOSE || st == CFR_ST_FETCH) == 0) break;
         bool start = false;
         if (st == CFR_ST_CLOSE) {  // back in GetHitsFromRead
+          if (Bwt::STEPS_COUNTED_AT_CLOSE && l >= W) {
+            // BackwardExtend calls of this search: l - W that succeeded, plus the one that failed when
+            // the search stopped on an ACGT base before the start of the strand (the cursor is still on it)
+            oc.xext += (u32)(l - W) + ((l < remaining && s.peek() <= 3) ? 1u : 0u);
+          }
           if (l >= mhl && sp <= ep && nh < B.cap_h) {
             if (Bwt::leader()) {
-              out[nh].sp = sp;
-              out[nh].ep = ep;
-              out[nh].l = l;
-              out[nh].offset = s.len - remaining;
+              Hit &o = B.strand_hits[cur * (u64)B.cap_h + (u64)nh];
+              o.sp = sp;
+              o.ep = ep;
+              o.l = l;
+              o.offset = s.len - remaining;
             }
             ++nh;
           }
@@ -303,7 +324,6 @@ CFR_HD void search_tasks(const DevIndex &ix, const DevParams &P, const ChunkDev 
             s.len = (int)(B.off[mate][read + 1] - B.off[mate][read]);
             s.rc = (w & 1) ? 0 : 1;
             s.widx = ~0ull;
-            out = B.strand_hits + cur * (u64)B.cap_h;
             nh = 0;
             remaining = s.len;
             sp = ep = 0;
@@ -337,30 +357,39 @@ CFR_HD void search_tasks(const DevIndex &ix, const DevParams &P, const ChunkDev 
                   sp = e.x;
                   ep = e.x + e.y - 1;
                   l = W;
-                  if (l < remaining) st = CFR_ST_EXTEND;
+                  if (l < remaining) {
+                    st = CFR_ST_EXTEND;
+                    s.seek(remaining - 1 - l);
+                  }
                 }
               }
             } else {
               sp = 0;
               ep = ix.n - 1;
               l = 0;
-              if (l < remaining) st = CFR_ST_EXTEND;
+              if (l < remaining) {
+                st = CFR_ST_EXTEND;
+                s.seek(remaining - 1 - l);
+              }
             }
           }
         }
       }
     }
     if (st == CFR_ST_EXTEND) {  // one FMIndex::BackwardExtend; l < remaining holds here
-      const int c = s(remaining - 1 - l);
+      const int c = s.peek();   // the cursor stands on strand position remaining - 1 - l
       st = CFR_ST_CLOSE;
       if (c <= 3) {
         u64 nsp, nep;
-        Bwt::extend(ix, c, sp, ep, nsp, nep, oc);
+        Bwt::extend_step(ix, c, sp, ep, nsp, nep, oc);
         if (!(nsp > nep || nep > ix.n)) {
           sp = nsp;
           ep = nep;
           ++l;
-          if (l < remaining) st = CFR_ST_EXTEND;
+          if (l < remaining) {
+            st = CFR_ST_EXTEND;
+            s.advance();
+          }
         }
       }
     }

@@ -38,8 +38,8 @@ struct DevWT {
 // one of the four symbols (the text has no '$', FMIndex.hpp:355-358):
 //     #T before the sector = 64 * sector - (#A + #C + #G).
 //   lo, hi  bit planes of the 64 two-bit symbol codes
-//   w2      bits 0..39 #A, bits 40..63 low 24 bits of #C
-//   w3      bits 0..15 high 16 bits of #C, bits 16..55 #G       (40-bit counters: n < 2^40)
+//   w2      low 32 bits of #A | low 32 bits of #C << 32
+//   w3      low 32 bits of #G | (bits 32..39 of #A, #C, #G as three bytes) << 32   (40-bit counters: n < 2^40)
 // 32 bytes = one L2 / HBM3e sector: a rank or an LF step reads exactly one sector.
 struct alignas(32) OccLine {
   u64 lo, hi, w2, w3;

@@ -128,12 +128,7 @@ void *hostsim_open(const char *prefix, const cfr_params *p) {
         lo |= (u64)(s & 1) << w;
         hi |= (u64)(s >> 1) << w;
       }
-      OccLine o;
-      o.lo = lo;
-      o.hi = hi;
-      o.w2 = (cnt[0] & 0xffffffffffull) | (cnt[1] << 40);
-      o.w3 = ((cnt[1] >> 24) & 0xffffull) | ((cnt[2] & 0xffffffffffull) << 16);
-      h->occ[L] = o;
+      h->occ[L] = occ_pack(lo, hi, cnt[0], cnt[1], cnt[2]);
     }
     ix.occ = h->occ.data();
   }
@@ -185,6 +180,27 @@ void hostsim_dust(const char *in, int n, char *out) {
   dust_task(din, n, dout, d);
   for (int i = 0; i < n; ++i)
     if ((dbits[i >> 5] >> (i & 31)) & 1u) out[i] = 'N';
+}
+
+// the register-only screen on one read: 1 = the full SDUST must run, 0 = provably nothing is masked
+int hostsim_dust_screen(const char *in, int n) {
+  const u64 words = (u64)n / 32 + 2;
+  std::vector<unsigned char> raw((size_t)words * 32 + 32, 0);
+  memcpy(raw.data(), in, (size_t)n);
+  std::vector<u64> codes(words);
+  std::vector<u32> mraw(words), mwork(words);
+  std::vector<u64> off = {0, (u64)n};
+  ChunkDev B;
+  memset(&B, 0, sizeof(B));
+  B.n_reads = 1;
+  B.mates = 1;
+  B.seq_raw = raw.data();
+  B.codes = codes.data();
+  B.mask_raw = mraw.data();
+  B.mask = mwork.data();
+  B.off[0] = off.data();
+  for (u64 w = 0; w < words; ++w) encode_stage(B, w, (u64)n);
+  return dust_screen_stage(B, 0) ? 1 : 0;
 }
 
 // the whole pipeline for one batch; arena_rows small values exercise the deferral loop
@@ -263,7 +279,15 @@ int hostsim_classify(void *hh, int dust, uint64_t arena_rows, const cfr_read_bat
   for (u64 w = 0; w < n_words; ++w) encode_stage(B, w, len1 + len2);
   u64 dust_counter = 0;
   B.dust_counter = &dust_counter;
-  if (dust) dust_tasks(B, n * mates, ds, P.quorum);
+  std::vector<u32> dust_list(n * mates + 1);
+  u32 dust_list_n = 0;
+  if (dust && !getenv("HOSTSIM_NO_DUST_SCREEN")) {  // the screen kernel's loop, one lane
+    for (u64 t = 0; t < n * mates; ++t)
+      if (dust_screen_stage(B, t)) dust_list[dust_list_n++] = (u32)t;
+    B.dust_list = dust_list.data();
+    B.dust_list_n = &dust_list_n;
+  }
+  if (dust) dust_tasks(B, B.dust_list ? (u64)dust_list_n : n * mates, ds, P.quorum);
   u64 task_counter = 0, row_counter = 0;
   B.task_counter = &task_counter;
   B.row_counter = &row_counter;
@@ -320,6 +344,7 @@ int hostsim_classify(void *hh, int dust, uint64_t arena_rows, const cfr_read_bat
     results[i].by_rank = res[i].by_rank;
     for (int k = 0; k < P.max_result; ++k) ids[i * P.max_result + k] = out_ids[i * P.max_result + k];
   }
+  oc_fold(oc);
   if (counters) {
     memset(counters, 0, sizeof(*counters));
     counters->n_rank = oc.rank;

@@ -99,6 +99,8 @@ def lib():
         L.hostsim_locate.restype = C.c_uint64
         L.hostsim_locate.argtypes = [C.c_void_p, C.c_uint64]
         L.hostsim_dust.argtypes = [C.c_char_p, C.c_int, C.c_char_p]
+        L.hostsim_dust_screen.argtypes = [C.c_char_p, C.c_int]
+        L.hostsim_dust_screen.restype = C.c_int
         L.hostsim_classify.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.POINTER(ReadBatch), C.c_void_p,
                                        C.c_void_p, C.POINTER(Counters)]
         _lib = L
@@ -122,6 +124,11 @@ def hostsim_dust(seq: bytes) -> bytes:
     out = C.create_string_buffer(len(seq) + 1)
     lib().hostsim_dust(seq, len(seq), out)
     return out.raw[:len(seq)]
+
+
+def hostsim_dust_screen(seq: bytes) -> bool:
+    """True when the register-only screen sends the read to the full SDUST"""
+    return bool(lib().hostsim_dust_screen(seq, len(seq)))
 
 
 class HostSim:

@@ -6,7 +6,7 @@ import random
 
 import pytest
 
-from hostsim_binding import HostSim, hostsim_dust, result_tuples
+from hostsim_binding import HostSim, hostsim_dust, hostsim_dust_screen, result_tuples
 from oracle_binding import Oracle, dust_mask, read_fastx
 
 
@@ -83,6 +83,43 @@ def test_dust_compressed_interval_table():
         tests.append(s)
     for s in tests:
         assert hostsim_dust(s) == dust_mask(s), s
+
+
+def test_dust_screen_is_safe():
+    """a read the register-only screen clears is never masked by the reference's SDUST, and the
+    screen clears the bulk of random reads (that is its point)"""
+    rng = random.Random(17)
+    tests = [b"A" * 7, b"A" * 6, b"ACACACACACAC", b"ACACACACACA", b"ACGACGACGACGACGAC", b"ACGACGACGACGACGA",
+             b"ACGT" * 5 + b"A", b"ACGTA" * 5 + b"AC", b"ACGTAC" * 5 + b"AC", b"ACGTACG" * 5 + b"AC", b"", b"AC",
+             b"ACGTTGCATGCATGACGATCGATCGTAGCTAGCTAGCTGATCGATGCATCGA" * 3]
+    n_random = n_cleared = 0
+    for it in range(6000):
+        L = rng.choice([7, 8, 12, 30, 63, 64, 65, 66, 95, 96, 97, 100, 128, 150, 151, 300])
+        mode = rng.random()
+        if mode < 0.5:
+            s = bytes(rng.choice(b"ACGT") for _ in range(L))
+            n_random += 1
+            n_cleared += 0 if hostsim_dust_screen(s) else 1
+        elif mode < 0.8:  # periodic with noise: right at the masking threshold
+            per = rng.randint(1, 13)
+            unit = bytes(rng.choice(b"ACGT") for _ in range(per))
+            s = bytes(unit[i % per] if rng.random() > 0.04 else rng.choice(b"ACGT") for i in range(L))
+        elif mode < 0.9:  # a short repeat planted in a random read
+            s = bytearray(rng.choice(b"ACGT") for _ in range(L))
+            per = rng.randint(1, 6)
+            unit = bytes(rng.choice(b"ACGT") for _ in range(per))
+            rl = rng.randint(5, 30)
+            p0 = rng.randrange(max(1, L - rl))
+            for i in range(p0, min(L, p0 + rl)):
+                s[i] = unit[(i - p0) % per]
+            s = bytes(s)
+        else:
+            s = bytes(rng.choice(b"AAAAAACGT") for _ in range(L))
+        tests.append(s)
+    for s in tests:
+        if not hostsim_dust_screen(s):
+            assert dust_mask(s) == s, s
+    assert n_cleared > 0.7 * n_random, (n_cleared, n_random)
 
 
 @pytest.mark.parametrize("layout", [1, 2])
