@@ -557,6 +557,7 @@ CFR_HD int score_stage(const DevIndex &ix, const DevParams &P, const ChunkDev &B
   const u64 a = w.arena_base;
   score_read(ix, P, fh, (int)w.n_hits, B.seq_ids + a, B.rec0 + a, B.rec1 + a, B.best + a, B.tmp + a, res, out,
              err_flags);
+  for (int i = res.n_assign; i < P.max_result; ++i) out[i] = 0;  // unused id slots read as 0
   B.results[read] = res;
   return res.n_assign;
 }
