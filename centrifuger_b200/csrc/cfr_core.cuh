@@ -207,26 +207,20 @@ struct StrandSeq {
   // bases of strand[0..m): true + the table key, or false + the number of valid
   // characters seen before the first non-ACGT one.
   CFR_HD bool init_key(int m, int W, u64 &key, int &nvalid) const {
+    // one code path for both strands (the lanes of a warp mix them): the W bases are the same
+    // packed field either way; the reverse complement reverses the 2-bit groups and complements
     u32 field, nbits;
-    if (!rc) {
-      packed_field(codes, nmask, base + (u64)(m - W), W, field, nbits);
-      if (nbits) {
-        nvalid = W - 1 - (31 - clz32(nbits));
-        return false;
-      }
-      key = field;  // s[m-1-i] lands in bits 2(W-1-i): exactly the little-endian field
-      return true;
-    }
-    packed_field(codes, nmask, base + (u64)(len - m), W, field, nbits);
+    packed_field(codes, nmask, base + (u64)(rc ? len - m : m - W), W, field, nbits);
     if (nbits) {
-      nvalid = ctz32(nbits);
+      nvalid = rc ? ctz32(nbits) : W - 1 - (31 - clz32(nbits));
       return false;
     }
-    // reverse the order of the 2-bit groups and complement them
     u32 r = brev32(field);
     r = ((r >> 1) & 0x55555555u) | ((r & 0x55555555u) << 1);
     r >>= (32 - 2 * W);
-    key = (u64)(r ^ (W >= 16 ? 0xffffffffu : ((1u << (2 * W)) - 1u)));
+    r ^= (W >= 16 ? 0xffffffffu : ((1u << (2 * W)) - 1u));
+    // as read: s[m-1-i] lands in bits 2(W-1-i), exactly the little-endian field
+    key = rc ? (u64)r : (u64)field;
     return true;
   }
 };
@@ -1347,17 +1341,24 @@ CFR_HD bool dust_all_acgt(const u32 *nmask, u64 base, int n) {
 // FindPerfect (Dustmasker.hpp:173-242) masks a run of k triplets S only when its
 // score exceeds the threshold: sum_t C(c_t,2) * 10 > T * (k-1) with T = 20, i.e.
 //     f(S) = sum_t C(c_t,2) - 2(k-1) = 2 + sum_t g(c_t) > 0,   g(c) = c(c-5)/2,
-// c_t = multiplicity of triplet t in S.  g(1..4) = -2,-3,-3,-2, g(5) = 0, g(6) = 3,
-// so f(S) > 0 needs either a triplet with c_t >= 6, or every triplet of S having
-// c_t = 5 exactly (k = 5m; m = 1 is a homopolymer run, m >= 2 puts two classes with
-// five copies into one window).  S lies inside the 62-triplet window that ends at its
-// last triplet, so when that triplet (or the 6th copy) enters the window the window
-// counts satisfy: some count >= 6, or the entering class has >= 5 copies and either ends a
-// run of five identical triplets (seven identical bases) or a second class has >= 5 copies too.  If that never happens
-// while the window slides over the mate, SDUST masks nothing and the mate can skip
-// the full algorithm.  The window counts are kept bit-sliced in three 64-bit
-// registers (one bit per triplet class and plane), so the screen touches no memory
-// beyond the packed read itself.  Returns true when the full SDUST must run.
+// c_t = multiplicity of triplet class t in S.  g(1..4) = -2,-3,-3,-2, g(5) = 0 and g grows
+// from there, so S needs "heavy" classes (c_t >= 5), and every other element of S costs
+// at least 1/2: with heavy multiplicities c_1..c_h
+//     |S| <= L(S) = 2 + sum_i c_i (c_i - 4)                                   (*)
+// (5 identical triplets = 7 identical bases give L = 7; one class with 6 copies L = 14).
+// Take the LAST heavy element of S, entering the window at time tau with class t.  The
+// window (62 triplets) then holds all of S up to tau, so every heavy class of S has a
+// window count >= its multiplicity in S, count[t] >= 5, and by (*) -- L evaluated on the
+// window's heavy classes only grows -- the >= 5 copies of t in S lie among the last L
+// triplets.  Hence, whenever a triplet enters whose class then has >= 5 copies in the
+// window: compute L from the window's heavy classes and count the copies of t among
+// the last L triplets; if that count never reaches 5 (and the conservative outs below
+// never fire) no perfect interval exists and SDUST masks nothing.
+// The window counts are kept bit-sliced in three 64-bit registers (one bit per triplet
+// class and plane), so the screen touches no memory beyond the packed read itself.
+// Conservative outs: a count of 7 (the planes would wrap), three heavy classes at
+// once, or L > 30 (the history examined is one 32-base word).
+// Returns true when the full SDUST must run.
 CFR_HD u64 dust_stream_word(const u64 *codes, u64 q0, int k) {  // 32 bases from q0 + 32k
   const u64 wi = (q0 >> 5) + (u64)k;
   const int sh = 2 * (int)(q0 & 31);
@@ -1366,10 +1367,36 @@ CFR_HD u64 dust_stream_word(const u64 *codes, u64 q0, int k) {  // 32 bases from
   return (a >> sh) | (ld64(codes + wi + 1) << (64 - sh));
 }
 
+// bit 2p set iff base p of the 32-base word w equals the 2-bit code b
+CFR_HD u64 dust_base_eq(u64 w, u64 b) {
+  const u64 REP = 0x5555555555555555ull;
+  const u64 x = w ^ (b * REP);
+  return ~(x | (x >> 1)) & REP;
+}
+
+// the rare part of the screen: class t (mask m) has >= 5 copies in the window after triplet
+// i entered.  `hist` = the 32 bases ending with triplet i (triplet i-d starts at base 29-d).
+CFR_HD bool dust_screen_event(u64 b0, u64 b1, u64 b2, u64 m, u64 t, u64 hist, int i) {
+  if (b2 & b1 & b0 & m) return true;  // 7 copies
+  u64 hh = b2 & (b0 | b1);            // heavy classes
+  int L = 2;
+  for (int q = 0; q < 2; ++q) {
+    if (!hh) break;
+    const u64 bit = hh & (~hh + 1ull);
+    hh ^= bit;
+    const int c = 4 + ((b1 & bit) ? 2 : 0) + ((b0 & bit) ? 1 : 0);
+    L += c * (c - 4);
+  }
+  if (hh || L > 30) return true;  // three heavy classes, or more history than one word
+  const int leff = L < i + 1 ? L : i + 1;
+  const u64 occ = dust_base_eq(hist, t & 3ull) & (dust_base_eq(hist, (t >> 2) & 3ull) >> 2) &
+                  (dust_base_eq(hist, (t >> 4) & 3ull) >> 4);
+  return popc64(occ >> (2 * (30 - leff))) >= 5;
+}
+
 CFR_HD bool dust_screen(const u64 *codes, u64 q0, int len) {
   const int nt = len - 2;  // triplets; fewer than 5 can never reach the threshold
   if (nt < 5) return false;
-  const u64 HOMO = 1ull | (1ull << 21) | (1ull << 42) | (1ull << 63);  // AAA, CCC, GGG, TTT
   u64 b0 = 0, b1 = 0, b2 = 0;  // bit planes of the per-class window counts
   u64 prev2 = 0, prev1 = 0, cur = dust_stream_word(codes, q0, 0);
   bool need = false;
@@ -1396,18 +1423,19 @@ CFR_HD bool dust_screen(const u64 *codes, u64 q0, int len) {
         }
         u64 t = cur >> (2 * j);
         if (j > 29) t |= nxt << (64 - 2 * j);
-        const u64 m = 1ull << (t & 63ull);
+        t &= 63ull;
+        const u64 m = 1ull << t;
         const u64 c0 = b0 & m;  // carry chain of count[t] += 1
         b0 ^= m;
         const u64 c1 = b1 & c0;
         b1 ^= c0;
         b2 ^= c1;
-        const u64 h5 = b2 & (b0 | b1);  // classes with >= 5 copies in the window
-        if (h5 & m) {
-          // the four bases in front of triplet i (8 bits); i >= 4 here because count[t] >= 5
-          const u64 x = j >= 4 ? cur >> (2 * (j - 4)) : (prev1 >> (56 + 2 * j)) | (cur << (8 - 2 * j));
-          const bool homo7 = (m & HOMO) != 0 && (x & 0xffull) == (t & 3ull) * 0x55ull;  // five identical triplets in a row
-          need = need || (b2 & b1 & m) != 0 || (h5 & ~m) != 0 || homo7;
+        if (b2 & (b0 | b1) & m) {  // class t has >= 5 copies in the window
+          u64 hist;                // the 32 bases ending with triplet i
+          if (j == 29) hist = cur;
+          else if (j > 29) hist = (cur >> (2 * (j - 29))) | (nxt << (64 - 2 * (j - 29)));
+          else hist = (prev1 >> (2 * (j + 3))) | (cur << (64 - 2 * (j + 3)));
+          need = need || dust_screen_event(b0, b1, b2, m, t, hist, i);
         }
       }
     }

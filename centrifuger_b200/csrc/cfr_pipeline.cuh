@@ -269,108 +269,100 @@ CFR_HD int adaptive_quorum(int quorum, u32 alive_mask, int lanes_per_task) {
   return (q < quorum ? (q < 1 ? 1 : q) : quorum) * lanes_per_task;
 }
 
-enum { CFR_ST_EXTEND = 0, CFR_ST_CLOSE = 1, CFR_ST_FETCH = 2, CFR_ST_DONE = 3 };
+enum { CFR_ST_EXTEND = 0, CFR_ST_CLOSE = 1, CFR_ST_FETCH = 2, CFR_ST_DONE = 3, CFR_ST_LOOKUP = 4 };
 
 template <class Bwt>
 CFR_HD void search_tasks(const DevIndex &ix, const DevParams &P, const ChunkDev &B, const u64 ntask, OpCount &oc) {
-  const int W = ix.pre_width, mhl = P.min_hit_len, S = 2 * B.mates;
+  const int W = ix.pre_width, mhl = P.min_hit_len;
+  const int sshift = B.mates == 2 ? 2 : 1;  // strand tasks per read = 2 * mates = 1 << sshift
   StrandSeq s{B.codes, B.mask, 0, 0, 0};
   u64 cur = 0, sp = 0, ep = 0;
   int nh = 0, remaining = 0, l = 0;
   int st = CFR_ST_FETCH;
+  u64x2 pend;  // lookup-table entry in flight between the two halves of a transition
+  pend.x = pend.y = 0;
   for (;;) {
     const u32 ext = CFR_BALLOT(st == CFR_ST_EXTEND);
     const u32 trn = CFR_BALLOT(st == CFR_ST_CLOSE || st == CFR_ST_FETCH);
     if ((ext | trn) == 0) break;
-    if (trn != 0 && (ext == 0 || popc32(trn) >= adaptive_quorum(P.quorum, ext | trn, (int)Bwt::LANES))) {
-      // ---- transition block (warp-uniform entry): CLOSE -> (FETCH ->) start of the next search
-      for (int tries = 0; tries < 3; ++tries) {
-        if (CFR_BALLOT(st == CFR_ST_CLOSE || st == CFR_ST_FETCH) == 0) break;
-        bool start = false;
-        if (st == CFR_ST_CLOSE) {  // back in GetHitsFromRead
-          if (Bwt::STEPS_COUNTED_AT_CLOSE && l >= W) {
-            // BackwardExtend calls of this search: l - W that succeeded, plus the one that failed when
-            // the search stopped on an ACGT base before the start of the strand (the cursor is still on it)
-            oc.xext += (u32)(l - W) + ((l < remaining && s.peek() <= 3) ? 1u : 0u);
-          }
-          if (l >= mhl && sp <= ep && nh < B.cap_h) {
-            if (Bwt::leader()) {
-              Hit &o = B.strand_hits[cur * (u64)B.cap_h + (u64)nh];
-              o.sp = sp;
-              o.ep = ep;
-              o.l = l;
-              o.offset = s.len - remaining;
-            }
-            ++nh;
-          }
-          remaining -= (l + 1);
-          if (remaining >= mhl) {
-            start = true;
-          } else {
-            if (Bwt::leader()) B.strand_nhits[cur] = nh;
-            st = CFR_ST_FETCH;
-          }
+    // warp-uniform: does the deferred transition block run in this iteration?
+    const bool transit = trn != 0 && (ext == 0 || popc32(trn) >= adaptive_quorum(P.quorum, ext | trn, (int)Bwt::LANES));
+    if (transit) {
+      // ---- first half: CLOSE -> (FETCH ->) start of the next search, up to the ISSUE of the
+      // lookup-table load.  Its latency overlaps the extend step below; the entry is consumed
+      // in the second half, after that step.
+      bool start = false;
+      if (st == CFR_ST_CLOSE) {  // back in GetHitsFromRead
+        if (Bwt::STEPS_COUNTED_AT_CLOSE && l >= W) {
+          // BackwardExtend calls of this search: l - W that succeeded, plus the one that failed when
+          // the search stopped on an ACGT base before the start of the strand (the cursor is still on it)
+          oc.xext += (u32)(l - W) + ((l < remaining && s.peek() <= 3) ? 1u : 0u);
         }
-        const u64 claimed = warp_claim<Bwt::LANES>(B.task_counter, st == CFR_ST_FETCH);
-        if (st == CFR_ST_FETCH) {
-          if (claimed >= ntask) {
-            st = CFR_ST_DONE;
-          } else {
-            cur = claimed;
-            const u64 read = cur / (u64)S;
-            const int w = (int)(cur % (u64)S);
-            const int mate = w >> 1;
-            s.base = B.off[mate][read] - B.off_bias[mate];
-            s.len = (int)(B.off[mate][read + 1] - B.off[mate][read]);
-            s.rc = (w & 1) ? 0 : 1;
-            s.widx = ~0ull;
-            nh = 0;
-            remaining = s.len;
-            sp = ep = 0;
-            if (remaining >= mhl) {
-              start = true;
-            } else if (Bwt::leader()) {
-              B.strand_nhits[cur] = 0;
-            }
+        if (l >= mhl && sp <= ep && nh < B.cap_h) {
+          if (Bwt::leader()) {
+            Hit &o = B.strand_hits[cur * (u64)B.cap_h + (u64)nh];
+            o.sp = sp;
+            o.ep = ep;
+            o.l = l;
+            o.offset = s.len - remaining;
           }
+          ++nh;
         }
-        if (start) {  // FMIndex::BackwardSearch up to the initial range
-          st = CFR_ST_CLOSE;
-          if (remaining < W) {
-            l = 0;
-          } else {
-            ++oc.search;
-            if (W > 0) {
-              u64 key;
-              int nvalid;
-              if (!s.init_key(remaining, W, key, nvalid)) {
-                sp = 1;
-                ep = 0;
-                l = nvalid;
-              } else {
-                const u64x2 e = ld128(ix.lookup + key);
-                if (e.y == 0) {
-                  sp = 1;
-                  ep = 0;
-                  l = W - 1;
-                } else {
-                  sp = e.x;
-                  ep = e.x + e.y - 1;
-                  l = W;
-                  if (l < remaining) {
-                    st = CFR_ST_EXTEND;
-                    s.seek(remaining - 1 - l);
-                  }
-                }
-              }
+        remaining -= (l + 1);
+        if (remaining >= mhl) {
+          start = true;
+        } else {
+          if (Bwt::leader()) B.strand_nhits[cur] = nh;
+          st = CFR_ST_FETCH;
+        }
+      }
+      const u64 claimed = warp_claim<Bwt::LANES>(B.task_counter, st == CFR_ST_FETCH);
+      if (st == CFR_ST_FETCH) {
+        if (claimed >= ntask) {
+          st = CFR_ST_DONE;
+        } else {
+          cur = claimed;
+          const u64 read = cur >> sshift;
+          const int w = (int)(cur & ((1ull << sshift) - 1ull));
+          const int mate = w >> 1;
+          const u64 *off = mate ? B.off[1] : B.off[0];
+          const u64 o0 = off[read], o1 = off[read + 1];
+          s.base = o0 - (mate ? B.off_bias[1] : B.off_bias[0]);
+          s.len = (int)(o1 - o0);
+          s.rc = (w & 1) ? 0 : 1;
+          s.widx = ~0ull;
+          nh = 0;
+          remaining = s.len;
+          sp = ep = 0;
+          st = CFR_ST_CLOSE;  // a strand shorter than minHitLen closes at once with no hits
+          l = -1;             // (remaining -= l + 1 leaves it unchanged; xext sees l < W)
+          if (remaining >= mhl) start = true;
+        }
+      }
+      if (start) {  // FMIndex::BackwardSearch up to the initial range
+        st = CFR_ST_CLOSE;
+        if (remaining < W) {
+          l = 0;
+        } else {
+          ++oc.search;
+          if (W > 0) {
+            u64 key;
+            int nvalid;
+            if (!s.init_key(remaining, W, key, nvalid)) {
+              sp = 1;
+              ep = 0;
+              l = nvalid;
             } else {
-              sp = 0;
-              ep = ix.n - 1;
-              l = 0;
-              if (l < remaining) {
-                st = CFR_ST_EXTEND;
-                s.seek(remaining - 1 - l);
-              }
+              pend = ld128(ix.lookup + key);
+              st = CFR_ST_LOOKUP;
+            }
+          } else {
+            sp = 0;
+            ep = ix.n - 1;
+            l = 0;
+            if (l < remaining) {
+              st = CFR_ST_EXTEND;
+              s.seek(remaining - 1 - l);
             }
           }
         }
@@ -390,6 +382,22 @@ CFR_HD void search_tasks(const DevIndex &ix, const DevParams &P, const ChunkDev 
             st = CFR_ST_EXTEND;
             s.advance();
           }
+        }
+      }
+    }
+    if (transit && st == CFR_ST_LOOKUP) {  // ---- second half: the lookup-table entry has arrived
+      st = CFR_ST_CLOSE;
+      if (pend.y == 0) {
+        sp = 1;
+        ep = 0;
+        l = W - 1;
+      } else {
+        sp = pend.x;
+        ep = pend.x + pend.y - 1;
+        l = W;
+        if (l < remaining) {
+          st = CFR_ST_EXTEND;
+          s.seek(remaining - 1 - l);
         }
       }
     }
