@@ -409,7 +409,33 @@ CFR_HD OccLine occ_pack(u64 lo, u64 hi, u64 a, u64 c, u64 g) {
   return o;
 }
 
+// How a sector is fetched (LOAD template parameter of BwtOccLineT):
+//   0  two 128-bit loads through the read-only (nc) path
+//   1  two 128-bit plain loads (L1 + L2)
+//   2  two 128-bit loads that bypass L1 (.cg)
+//   3  one 256-bit plain load           4  one 256-bit load through the read-only path
+template <int LOAD>
 CFR_HD void occ_load(const OccLine *L, u64 &lo, u64 &hi, u64 &w2, u64 &w3) {
+#if defined(__CUDA_ARCH__)
+  if (LOAD == 1) {
+    asm volatile("ld.global.v2.u64 {%0,%1}, [%2];" : "=l"(lo), "=l"(hi) : "l"(L));
+    asm volatile("ld.global.v2.u64 {%0,%1}, [%2+16];" : "=l"(w2), "=l"(w3) : "l"(L));
+    return;
+  }
+  if (LOAD == 2) {
+    asm volatile("ld.global.cg.v2.u64 {%0,%1}, [%2];" : "=l"(lo), "=l"(hi) : "l"(L));
+    asm volatile("ld.global.cg.v2.u64 {%0,%1}, [%2+16];" : "=l"(w2), "=l"(w3) : "l"(L));
+    return;
+  }
+  if (LOAD == 3) {
+    asm volatile("ld.global.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(lo), "=l"(hi), "=l"(w2), "=l"(w3) : "l"(L));
+    return;
+  }
+  if (LOAD == 4) {
+    asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(lo), "=l"(hi), "=l"(w2), "=l"(w3) : "l"(L));
+    return;
+  }
+#endif
   const u64x2 p = ld128(reinterpret_cast<const u64x2 *>(L));
   const u64x2 q = ld128(reinterpret_cast<const u64x2 *>(L) + 1);
   lo = p.x;
@@ -418,26 +444,28 @@ CFR_HD void occ_load(const OccLine *L, u64 &lo, u64 &hi, u64 &w2, u64 &w3) {
   w3 = q.y;
 }
 
+template <int LOAD>
 CFR_HD OccRank occ_rank(const DevIndex &ix, int c, u64 x) {
   const u64 sec = x >> 6;
   const int s = (int)(x & 63);
   OccRank r;
   u64 w2, w3;
-  occ_load(ix.occ + sec, r.lo, r.hi, w2, w3);
+  occ_load<LOAD>(ix.occ + sec, r.lo, r.hi, w2, w3);
   r.count = occ_base(w2, w3, c, sec) + (u64)popc64(occ_match(r.lo, r.hi, c) & ((1ull << s) - 1ull));
   return r;
 }
 
 CFR_HD int occ_symbol(u64 lo, u64 hi, int s) { return (int)(((lo >> s) & 1ull) | (((hi >> s) & 1ull) << 1)); }
 
-struct BwtOccLine {
+template <int LOAD>
+struct BwtOccLineT {
   // straight-line: both ranks and the symbol test are always computed, the range /
   // single-row forms of FMIndex::BackwardExtend are selected at the end.  Returns sp != ep.
   static CFR_HD bool extend_core(const DevIndex &ix, int c, u64 sp, u64 ep, u64 &nsp, u64 &nep) {
     const u64 off = ix.C[c];
     const bool range = sp != ep;
-    const OccRank a = occ_rank(ix, c, sp);      // Rank(c, sp, exclusive)
-    const OccRank e = occ_rank(ix, c, ep + 1);  // Rank(c, ep, inclusive)
+    const OccRank a = occ_rank<LOAD>(ix, c, sp);      // Rank(c, sp, exclusive)
+    const OccRank e = occ_rank<LOAD>(ix, c, ep + 1);  // Rank(c, ep, inclusive)
     const int sym = occ_symbol(a.lo, a.hi, (int)(ep & 63));  // BWT[ep] when sp == ep (same sector as sp)
     // FMIndex::Rank's correction for the missing '$' (FMIndex.hpp:359), both forms at once
     const u64 is_last = c == ix.last_code ? 1ull : 0ull;
@@ -463,14 +491,14 @@ struct BwtOccLine {
     const u64 sec = i >> 6;
     const int s = (int)(i & 63);
     u64 lo, hi, w2, w3;
-    occ_load(ix.occ + sec, lo, hi, w2, w3);
+    occ_load<LOAD>(ix.occ + sec, lo, hi, w2, w3);
     const int c = occ_symbol(lo, hi, s);
     const u64 r = occ_base(w2, w3, c, sec) + (u64)popc64(occ_match(lo, hi, c) & ((1ull << s) - 1ull));
     // inclusive rank at i = exclusive count at i, plus the symbol itself
     return ix.C[c] + r + 1 + last_chr_fix(ix, c, i, 1) - 1;
   }
   static CFR_HD u64 rank(const DevIndex &ix, int c, u64 i, int inclusive) {
-    return occ_rank(ix, c, inclusive ? i + 1 : i).count;
+    return occ_rank<LOAD>(ix, c, inclusive ? i + 1 : i).count;
   }
   static CFR_HD int access(const DevIndex &ix, u64 i) {
     const u64x2 p = ld128(reinterpret_cast<const u64x2 *>(ix.occ + (i >> 6)));
@@ -479,6 +507,8 @@ struct BwtOccLine {
   static CFR_HD bool leader() { return true; }
   enum { LANES = 1 };
 };
+
+typedef BwtOccLineT<0> BwtOccLine;
 
 // ---------------------------------------------------------------------------
 // FM-index search and locate
@@ -1359,12 +1389,20 @@ CFR_HD bool dust_all_acgt(const u32 *nmask, u64 base, int n) {
 // Conservative outs: a count of 7 (the planes would wrap), three heavy classes at
 // once, or L > 30 (the history examined is one 32-base word).
 // Returns true when the full SDUST must run.
-CFR_HD u64 dust_stream_word(const u64 *codes, u64 q0, int k) {  // 32 bases from q0 + 32k
-  const u64 wi = (q0 >> 5) + (u64)k;
-  const int sh = 2 * (int)(q0 & 31);
-  const u64 a = ld64(codes + wi);
-  if (sh == 0) return a;
-  return (a >> sh) | (ld64(codes + wi + 1) << (64 - sh));
+// (lo, hi) >> s for 0 <= s < 32, low word
+CFR_HD u32 funnel_r(u32 lo, u32 hi, int s) {
+#if defined(__CUDA_ARCH__)
+  return __funnelshift_r(lo, hi, (unsigned)s);
+#else
+  return s ? (lo >> s) | (hi << (32 - s)) : lo;
+#endif
+}
+
+CFR_HD u32 dust_stream_word(const u64 *codes, u64 q0, int k) {  // 16 bases from q0 + 16k
+  const u32 *c32 = reinterpret_cast<const u32 *>(codes);
+  const u64 q = q0 + 16ull * (u64)k;
+  const u64 wi = q >> 4;
+  return funnel_r(ld32(c32 + wi), ld32(c32 + wi + 1), 2 * (int)(q & 15));
 }
 
 // bit 2p set iff base p of the 32-base word w equals the 2-bit code b
@@ -1376,7 +1414,13 @@ CFR_HD u64 dust_base_eq(u64 w, u64 b) {
 
 // the rare part of the screen: class t (mask m) has >= 5 copies in the window after triplet
 // i entered.  `hist` = the 32 bases ending with triplet i (triplet i-d starts at base 29-d).
-CFR_HD bool dust_screen_event(u64 b0, u64 b1, u64 b2, u64 m, u64 t, u64 hist, int i) {
+// One copy of this code for all unrolled steps of the screen loop (instruction cache).
+#if defined(__CUDA_ARCH__)
+__device__ __noinline__
+#else
+inline
+#endif
+bool dust_screen_event(u64 b0, u64 b1, u64 b2, u64 m, u32 t, u64 hist, int i) {
   if (b2 & b1 & b0 & m) return true;  // 7 copies
   u64 hh = b2 & (b0 | b1);            // heavy classes
   int L = 2;
@@ -1389,8 +1433,8 @@ CFR_HD bool dust_screen_event(u64 b0, u64 b1, u64 b2, u64 m, u64 t, u64 hist, in
   }
   if (hh || L > 30) return true;  // three heavy classes, or more history than one word
   const int leff = L < i + 1 ? L : i + 1;
-  const u64 occ = dust_base_eq(hist, t & 3ull) & (dust_base_eq(hist, (t >> 2) & 3ull) >> 2) &
-                  (dust_base_eq(hist, (t >> 4) & 3ull) >> 4);
+  const u64 occ = dust_base_eq(hist, t & 3u) & (dust_base_eq(hist, (t >> 2) & 3u) >> 2) &
+                  (dust_base_eq(hist, (t >> 4) & 3u) >> 4);
   return popc64(occ >> (2 * (30 - leff))) >= 5;
 }
 
@@ -1398,32 +1442,30 @@ CFR_HD bool dust_screen(const u64 *codes, u64 q0, int len) {
   const int nt = len - 2;  // triplets; fewer than 5 can never reach the threshold
   if (nt < 5) return false;
   u64 b0 = 0, b1 = 0, b2 = 0;  // bit planes of the per-class window counts
-  u64 prev2 = 0, prev1 = 0, cur = dust_stream_word(codes, q0, 0);
+  // sliding view of the mate in 16-base words: w0 holds the bases of the current block,
+  // wm4..wm1 the four blocks before it (the triplet leaving the 62-triplet window starts
+  // 62 bases back), w1 the next one
+  u32 wm4 = 0, wm3 = 0, wm2 = 0, wm1 = 0, w0 = dust_stream_word(codes, q0, 0);
   bool need = false;
-  for (int k = 0; 32 * k < nt; ++k) {
-    const u64 nxt = 32 * (k + 1) < len ? dust_stream_word(codes, q0, k + 1) : 0ull;
+  for (int k = 0; 16 * k < nt; ++k) {
+    const u32 w1 = 16 * (k + 1) < len ? dust_stream_word(codes, q0, k + 1) : 0u;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-    for (int j = 0; j < 32; ++j) {
-      const int i = 32 * k + j;
+    for (int j = 0; j < 16; ++j) {
+      const int i = 16 * k + j;
       if (i < nt) {
-        if (i >= 62) {  // the window holds 62 triplets: triplet i-62 = base 32(k-2) + j+2 leaves first
+        if (i >= 62) {  // triplet i-62 starts at base j+2 of block k-4
           const int jj = j + 2;
-          u64 o;
-          if (jj <= 29) o = prev2 >> (2 * jj);
-          else if (jj <= 31) o = (prev2 >> (2 * jj)) | (prev1 << (64 - 2 * jj));
-          else o = prev1 >> (2 * (jj - 32));
-          const u64 mo = 1ull << (o & 63ull);
+          const u32 o = (jj <= 13 ? wm4 >> (2 * jj) : jj <= 15 ? funnel_r(wm4, wm3, 2 * jj) : wm3 >> (2 * (jj - 16))) & 63u;
+          const u64 mo = 1ull << o;
           const u64 br0 = ~b0 & mo;  // borrow chain of count[o] -= 1
           b0 ^= mo;
           const u64 br1 = ~b1 & br0;
           b1 ^= br0;
           b2 ^= br1;
         }
-        u64 t = cur >> (2 * j);
-        if (j > 29) t |= nxt << (64 - 2 * j);
-        t &= 63ull;
+        const u32 t = (j <= 13 ? w0 >> (2 * j) : funnel_r(w0, w1, 2 * j)) & 63u;
         const u64 m = 1ull << t;
         const u64 c0 = b0 & m;  // carry chain of count[t] += 1
         b0 ^= m;
@@ -1431,17 +1473,24 @@ CFR_HD bool dust_screen(const u64 *codes, u64 q0, int len) {
         b1 ^= c0;
         b2 ^= c1;
         if (b2 & (b0 | b1) & m) {  // class t has >= 5 copies in the window
-          u64 hist;                // the 32 bases ending with triplet i
-          if (j == 29) hist = cur;
-          else if (j > 29) hist = (cur >> (2 * (j - 29))) | (nxt << (64 - 2 * (j - 29)));
-          else hist = (prev1 >> (2 * (j + 3))) | (cur << (64 - 2 * (j + 3)));
-          need = need || dust_screen_event(b0, b1, b2, m, t, hist, i);
+          // the 32 bases ending with triplet i: from base j+3 of block k-2 on
+          u32 lo, hi;
+          if (j <= 12) {
+            lo = funnel_r(wm2, wm1, 2 * (j + 3));
+            hi = funnel_r(wm1, w0, 2 * (j + 3));
+          } else {
+            lo = funnel_r(wm1, w0, 2 * (j - 13));
+            hi = funnel_r(w0, w1, 2 * (j - 13));
+          }
+          if (dust_screen_event(b0, b1, b2, m, t, (u64)lo | ((u64)hi << 32), i)) need = true;
         }
       }
     }
-    prev2 = prev1;
-    prev1 = cur;
-    cur = nxt;
+    wm4 = wm3;
+    wm3 = wm2;
+    wm2 = wm1;
+    wm1 = w0;
+    w0 = w1;
   }
   return need;
 }

@@ -271,7 +271,7 @@ CFR_HD int adaptive_quorum(int quorum, u32 alive_mask, int lanes_per_task) {
 
 enum { CFR_ST_EXTEND = 0, CFR_ST_CLOSE = 1, CFR_ST_FETCH = 2, CFR_ST_DONE = 3, CFR_ST_LOOKUP = 4 };
 
-template <class Bwt>
+template <class Bwt, bool SPLIT = true>
 CFR_HD void search_tasks(const DevIndex &ix, const DevParams &P, const ChunkDev &B, const u64 ntask, OpCount &oc) {
   const int W = ix.pre_width, mhl = P.min_hit_len;
   const int sshift = B.mates == 2 ? 2 : 1;  // strand tasks per read = 2 * mates = 1 << sshift
@@ -355,6 +355,22 @@ CFR_HD void search_tasks(const DevIndex &ix, const DevParams &P, const ChunkDev 
             } else {
               pend = ld128(ix.lookup + key);
               st = CFR_ST_LOOKUP;
+              if (!SPLIT) {
+                st = CFR_ST_CLOSE;
+                if (pend.y == 0) {
+                  sp = 1;
+                  ep = 0;
+                  l = W - 1;
+                } else {
+                  sp = pend.x;
+                  ep = pend.x + pend.y - 1;
+                  l = W;
+                  if (l < remaining) {
+                    st = CFR_ST_EXTEND;
+                    s.seek(remaining - 1 - l);
+                  }
+                }
+              }
             }
           } else {
             sp = 0;
@@ -385,7 +401,7 @@ CFR_HD void search_tasks(const DevIndex &ix, const DevParams &P, const ChunkDev 
         }
       }
     }
-    if (transit && st == CFR_ST_LOOKUP) {  // ---- second half: the lookup-table entry has arrived
+    if (SPLIT && transit && st == CFR_ST_LOOKUP) {  // ---- second half: the lookup-table entry has arrived
       st = CFR_ST_CLOSE;
       if (pend.y == 0) {
         sp = 1;
