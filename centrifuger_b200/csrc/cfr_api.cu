@@ -86,8 +86,9 @@ struct cfr_handle {
   size_t hbm_bytes = 0;
   int sm_count = 148;
   int search_blocks = 10;  // resident 128-thread blocks per SM targeted by k_search (CFR_B200_SEARCH_BLOCKS)
-  bool split_lookup = true;  // lookup-table load of a new search overlaps the extend step (CFR_B200_SPLIT_LOOKUP)
-  int occ_load = 0;          // how k_search / k_locate fetch a sector: see occ_load<> (CFR_B200_OCC_LOAD)
+  bool split_lookup = false;  // lookup-table load of a new search overlaps the extend step (CFR_B200_SPLIT_LOOKUP)
+  int occ_load = 4;          // how k_search / k_locate fetch a sector: see occ_load<> (CFR_B200_OCC_LOAD)
+  int dust_lanes = 16;  // lanes per warp that take mates in the post-screen SDUST launch (CFR_B200_DUST_LANES)
   bool dust_screen = true;  // register-only screen in front of the full SDUST (CFR_B200_DUST_SCREEN=0 disables)
   u64 *d_taxon = nullptr;
   DevCounters *d_counters = nullptr;
@@ -187,7 +188,9 @@ void launch_dust(cfr_handle *h, const ChunkDev &B, cudaStream_t s) {
     k_dust_screen<<<grid_for(h, ntask, 128, 16), 128, 0, s>>>(B);
     ++h->launches;
   }
-  k_dust<<<grid_for(h, ntask, CFR_DUST_THREADS, 5), CFR_DUST_THREADS, CFR_DUST_SMEM, s>>>(B, h->P.quorum);
+  // after the screen only the few mates that need the whole algorithm are left: fewer lanes per warp
+  k_dust<<<grid_for(h, ntask, CFR_DUST_THREADS, 5), CFR_DUST_THREADS, CFR_DUST_SMEM, s>>>(
+      B, h->P.quorum, B.dust_list ? h->dust_lanes : 32);
   ++h->launches;
 }
 
@@ -569,6 +572,7 @@ int cfr_open(const char *idx_prefix, const cfr_params *p, int device, cfr_handle
   if (const char *e = getenv("CFR_B200_QUORUM")) h->P.quorum = std::max(1, atoi(e));
   if (const char *e = getenv("CFR_B200_SEARCH_BLOCKS")) h->search_blocks = std::max(1, atoi(e));
   if (const char *e = getenv("CFR_B200_DUST_SCREEN")) h->dust_screen = atoi(e) != 0;
+  if (const char *e = getenv("CFR_B200_DUST_LANES")) h->dust_lanes = std::min(32, std::max(1, atoi(e)));
   if (const char *e = getenv("CFR_B200_SPLIT_LOOKUP")) h->split_lookup = atoi(e) != 0;
   if (const char *e = getenv("CFR_B200_OCC_LOAD")) h->occ_load = std::min(4, std::max(0, atoi(e)));
   // The index is read as independent random 32-byte sectors: ask L2 not to fetch the neighbouring

@@ -1309,12 +1309,18 @@ CFR_HD void dust_find_perfect(int wfinish, DustStateT<SW> &d) {
   int rv = d.rv;
   int max_score = 0, max_cnt = 1;
   int folded = wstart + d.size;  // starts >= folded have been folded into (max_score, max_cnt)
-  for (int i = d.size - d.lv - 1; i >= 0; --i) {
+  const int first = d.size - d.lv - 1;
+  int i = first;
+  for (; i >= 0; --i) {
+    const int span = d.size - i - 1;
+    // A candidate needs rv * 10 > T * span.  rv counts pairs inside a part of the window, so it
+    // never exceeds rw (the pairs of the whole window), and span only grows from here: once
+    // T * span >= rw * 10 no candidate is left and the rest of the scan cannot change anything.
+    if (d.rw * 10 <= T * span) break;
     const int tt = dust_win_at(d, i);
     unsigned short &ett = d.cc[tt];
     rv += ett >> 8;
     ett = (unsigned short)(ett + 0x100);  // ++cv[tt]
-    const int span = d.size - i - 1;
     if (rv * 10 > T * span) {
       const int start = i + wstart;
       while (folded > start) {  // the scan of P from its head (:203-211)
@@ -1338,7 +1344,7 @@ CFR_HD void dust_find_perfect(int wfinish, DustStateT<SW> &d) {
       }
     }
   }
-  for (int i = d.size - d.lv - 1; i >= 0; --i) d.cc[dust_win_at(d, i)] -= 0x100;
+  for (int q = first; q > i; --q) d.cc[dust_win_at(d, q)] -= 0x100;  // undo the visited ++cv
 }
 
 // the tail loop of Dustmasker.hpp:343-350 (n = segment length): saves every remaining start

@@ -59,13 +59,15 @@ __global__ void __launch_bounds__(128) k_dust_screen(const __grid_constant__ Chu
 // ring live in shared memory, one bank column per thread (80 words x 128 threads
 // = 40 KiB per block), so their updates are conflict-free single wavefronts.
 enum { CFR_DUST_THREADS = 128, CFR_DUST_SMEM = 80 * CFR_DUST_THREADS * 4 };
-__global__ void __launch_bounds__(CFR_DUST_THREADS) k_dust(const __grid_constant__ ChunkDev B, const int quorum) {
+__global__ void __launch_bounds__(CFR_DUST_THREADS) k_dust(const __grid_constant__ ChunkDev B, const int quorum,
+                                                           const int lanes_per_warp) {
   extern __shared__ u32 dust_sm[];
   DustStateT<CFR_DUST_THREADS> d;
   d.cc.base = reinterpret_cast<unsigned char *>(&dust_sm[threadIdx.x]);                          // 64 words
   d.win.base = reinterpret_cast<unsigned char *>(&dust_sm[64 * CFR_DUST_THREADS + threadIdx.x]);  // 16 words
   // mates are claimed dynamically from B.dust_counter (through B.dust_list when the screen ran)
-  dust_tasks(B, B.dust_list ? (u64)*B.dust_list_n : B.n_reads * (u64)B.mates, d, quorum);
+  dust_tasks(B, B.dust_list ? (u64)*B.dust_list_n : B.n_reads * (u64)B.mates, d, quorum,
+             (int)(threadIdx.x & 31) < lanes_per_warp);
 }
 
 // MINB = resident blocks per SM the register allocation must allow (occupancy knob)

@@ -136,10 +136,12 @@ CFR_HD void encode_stage(const ChunkDev &B, u64 w, u64 total_bytes) {
 enum { CFR_DS_FETCH = 0, CFR_DS_SEG = 1, CFR_DS_STEP = 2, CFR_DS_SLOW = 3, CFR_DS_DONE = 4 };
 
 template <int SW>
-CFR_HD void dust_tasks(const ChunkDev &B, const u64 ntask, DustStateT<SW> &d, const int quorum) {
+CFR_HD void dust_tasks(const ChunkDev &B, const u64 ntask, DustStateT<SW> &d, const int quorum, const bool active = true) {
   DustIn in{B.codes, B.mask_raw, 0};
   DustOut out{B.mask, B.dust_bits, 0};
-  int st = CFR_DS_FETCH;
+  // `active` = false parks the lane: the deferred loops (FindPerfect, shrink) of one mate stall the
+  // other mates of its warp, so a launch over few, all slow mates spreads them over more warps
+  int st = active ? CFR_DS_FETCH : CFR_DS_DONE;
   int len = 0, cursor = 0, seg_off = 0, seg_n = 0, wfinish = 0, c1 = 0, c2 = 0, t_last = 0;
   for (;;) {
     const u32 m_step = CFR_BALLOT(st == CFR_DS_STEP);
