@@ -17,6 +17,7 @@
 namespace cfrb200 {
 
 #define CFR_ROW_SENTINEL (~0ull)
+enum { CFR_SCORE_LOCAL_ROWS = 8 };
 
 struct ChunkDev {
   u64 n_reads;
@@ -64,8 +65,10 @@ CFR_HD u64 chunk_read_id(const ChunkDev &B, u64 t) { return B.read_list ? (u64)B
 // ---- warp-level helpers shared by the state-machine stages ----
 #if defined(__CUDA_ARCH__)
 #define CFR_BALLOT(pred) __ballot_sync(0xffffffffu, (pred))
+#define CFR_SYNCWARP() __syncwarp()
 #else
 #define CFR_BALLOT(pred) ((pred) ? 1u : 0u)
+#define CFR_SYNCWARP() ((void)0)
 #endif
 
 CFR_HD int popc32(u32 x) {
@@ -341,6 +344,9 @@ CFR_HD void search_tasks(const DevIndex &ix, const DevParams &P, const ChunkDev 
           if (remaining >= mhl) start = true;
         }
       }
+      // the lanes that continue a strand and the lanes that just fetched one start their searches
+      // together (without the barrier the compiler runs the block below once per group)
+      CFR_SYNCWARP();
       if (start) {  // FMIndex::BackwardSearch up to the initial range
         st = CFR_ST_CLOSE;
         if (remaining < W) {
@@ -438,29 +444,27 @@ CFR_HD void locate_rows(const DevIndex &ix, const DevParams &P, const ChunkDev &
     const u32 trn = CFR_BALLOT(st == CFR_LS_CHECK || st == CFR_LS_NEED);
     if ((walk | trn) == 0) break;
     if (trn != 0 && (walk == 0 || popc32(trn) >= adaptive_quorum(P.quorum, walk | trn, (int)Bwt::LANES))) {
-      for (int tries = 0; tries < 3; ++tries) {
-        if (CFR_BALLOT(st == CFR_LS_CHECK || st == CFR_LS_NEED) == 0) break;
-        if (st == CFR_LS_CHECK) {  // FMIndex::GetSampledSA, literally
-          u64 sa;
-          if (get_sampled_sa(ix, i, sa)) {
-            if (Bwt::leader()) B.seq_ids[cur] = (u32)sa;
-            ++oc.locate;
-            st = CFR_LS_NEED;
-          } else {  // filter bit set but the row is not a selected one: keep walking
-            i = Bwt::lf(ix, i, oc);
-            ++oc.lf;
-            st = CFR_LS_WALK;
-          }
+      if (st == CFR_LS_CHECK) {  // FMIndex::GetSampledSA, literally
+        u64 sa;
+        if (get_sampled_sa(ix, i, sa)) {
+          if (Bwt::leader()) B.seq_ids[cur] = (u32)sa;
+          ++oc.locate;
+          st = CFR_LS_NEED;
+        } else {  // filter bit set but the row is not a selected one: keep walking
+          i = Bwt::lf(ix, i, oc);
+          ++oc.lf;
+          st = CFR_LS_WALK;
         }
-        const u64 claimed = warp_claim<Bwt::LANES>(B.row_counter, st == CFR_LS_NEED);
-        if (st == CFR_LS_NEED) {
-          if (claimed >= used) {
-            st = CFR_LS_DONE;
-          } else {
-            cur = claimed;
-            i = B.rows[cur];
-            if (i != CFR_ROW_SENTINEL) st = CFR_LS_WALK;
-          }
+      }
+      CFR_SYNCWARP();
+      const u64 claimed = warp_claim<Bwt::LANES>(B.row_counter, st == CFR_LS_NEED);
+      if (st == CFR_LS_NEED) {
+        if (claimed >= used) {
+          st = CFR_LS_DONE;
+        } else {
+          cur = claimed;
+          i = B.rows[cur];
+          if (i != CFR_ROW_SENTINEL) st = CFR_LS_WALK;
         }
       }
     }
@@ -581,8 +585,18 @@ CFR_HD int score_stage(const DevIndex &ix, const DevParams &P, const ChunkDev &B
   res.by_rank = 0;
   u64 *out = B.out_ids + read * (u64)P.max_result;
   const u64 a = w.arena_base;
-  score_read(ix, P, fh, (int)w.n_hits, B.seq_ids + a, B.rec0 + a, B.rec1 + a, B.best + a, B.tmp + a, res, out,
-             err_flags);
+  if (w.arena_rows <= CFR_SCORE_LOCAL_ROWS) {
+    // the common case (a few located rows): the per-read tables fit thread-local storage, which
+    // keeps the dependent read-modify-write chain of the scoring out of L2
+    u32 ids[CFR_SCORE_LOCAL_ROWS];
+    SeqRec r0[CFR_SCORE_LOCAL_ROWS], r1[CFR_SCORE_LOCAL_ROWS];
+    u64 best[CFR_SCORE_LOCAL_ROWS], tmp[CFR_SCORE_LOCAL_ROWS];
+    for (u32 i = 0; i < w.arena_rows; ++i) ids[i] = B.seq_ids[a + i];
+    score_read(ix, P, fh, (int)w.n_hits, ids, r0, r1, best, tmp, res, out, err_flags);
+  } else {
+    score_read(ix, P, fh, (int)w.n_hits, B.seq_ids + a, B.rec0 + a, B.rec1 + a, B.best + a, B.tmp + a, res, out,
+               err_flags);
+  }
   for (int i = res.n_assign; i < P.max_result; ++i) out[i] = 0;  // unused id slots read as 0
   B.results[read] = res;
   return res.n_assign;
