@@ -86,8 +86,8 @@ struct cfr_handle {
   size_t hbm_bytes = 0;
   int sm_count = 148;
   int search_blocks = 10;  // resident 128-thread blocks per SM targeted by k_search (CFR_B200_SEARCH_BLOCKS)
-  bool split_lookup = false;  // lookup-table load of a new search overlaps the extend step (CFR_B200_SPLIT_LOOKUP)
-  int occ_load = 4;          // how k_search / k_locate fetch a sector: see occ_load<> (CFR_B200_OCC_LOAD)
+  int occ_load = 4;    // how k_search / k_locate fetch a sector: 4 = one 256-bit load, 0 = two 128-bit loads (CFR_B200_OCC_LOAD)
+  bool pos32 = false;  // 32-bit BWT positions in k_search / k_locate (collections below 2^32 rows; CFR_B200_POS64=1 disables)
   int dust_lanes = 16;  // lanes per warp that take mates in the post-screen SDUST launch (CFR_B200_DUST_LANES)
   bool dust_screen = true;  // register-only screen in front of the full SDUST (CFR_B200_DUST_SCREEN=0 disables)
   u64 *d_taxon = nullptr;
@@ -461,13 +461,9 @@ int run_first(cfr_handle *h, cfr_device_batch *b, cudaStream_t s) {
   {
     StageScope sc(h, s, CFR_STAGE_SEARCH);
     const int g = grid_for(h, B.n_reads * 2 * B.mates, 128, h->search_blocks);
-    if (h->search_blocks >= 10) {
-      if (h->split_lookup) k_search<BwtWide, 10, true><<<g, 128, 0, s>>>(h->ix, h->P, B);
-      else k_search<BwtWide, 10, false><<<g, 128, 0, s>>>(h->ix, h->P, B);
-    } else {
-      if (h->split_lookup) k_search<BwtWide, 8, true><<<g, 128, 0, s>>>(h->ix, h->P, B);
-      else k_search<BwtWide, 8, false><<<g, 128, 0, s>>>(h->ix, h->P, B);
-    }
+    if (h->search_blocks >= 12) k_search<BwtWide, 12, false><<<g, 128, 0, s>>>(h->ix, h->P, B);
+    else if (h->search_blocks >= 10) k_search<BwtWide, 10, false><<<g, 128, 0, s>>>(h->ix, h->P, B);
+    else k_search<BwtWide, 8, false><<<g, 128, 0, s>>>(h->ix, h->P, B);
     ++h->launches;
   }
   CUDA_TRY(cudaGetLastError());
@@ -573,8 +569,9 @@ int cfr_open(const char *idx_prefix, const cfr_params *p, int device, cfr_handle
   if (const char *e = getenv("CFR_B200_SEARCH_BLOCKS")) h->search_blocks = std::max(1, atoi(e));
   if (const char *e = getenv("CFR_B200_DUST_SCREEN")) h->dust_screen = atoi(e) != 0;
   if (const char *e = getenv("CFR_B200_DUST_LANES")) h->dust_lanes = std::min(32, std::max(1, atoi(e)));
-  if (const char *e = getenv("CFR_B200_SPLIT_LOOKUP")) h->split_lookup = atoi(e) != 0;
-  if (const char *e = getenv("CFR_B200_OCC_LOAD")) h->occ_load = std::min(4, std::max(0, atoi(e)));
+  if (const char *e = getenv("CFR_B200_OCC_LOAD")) h->occ_load = atoi(e) == 0 ? 0 : 4;
+  h->pos32 = h->file.n < CFR_POS32_MAX_N;
+  if (const char *e = getenv("CFR_B200_POS64")) if (atoi(e) != 0) h->pos32 = false;
   // The index is read as independent random 32-byte sectors: ask L2 not to fetch the neighbouring
   // sector(s) with every miss (the default fetch granularity is larger).  A hint; 32, 64 or 128.
   {
@@ -690,13 +687,12 @@ int cfr_classify_resident(cfr_handle *h, cfr_device_batch *b, void *stream) {
   h->host_bases += b->total_bases;
   b->classified = true;
   if (h->layout == CFR_LAYOUT_OCCLINE) {
-    switch (h->occ_load) {
-      case 1: return run_first<BwtOccLine, BwtOccLineT<1>>(h, b, s);
-      case 2: return run_first<BwtOccLine, BwtOccLineT<2>>(h, b, s);
-      case 3: return run_first<BwtOccLine, BwtOccLineT<3>>(h, b, s);
-      case 4: return run_first<BwtOccLine, BwtOccLineT<4>>(h, b, s);
-      default: return run_first<BwtOccLine, BwtOccLine>(h, b, s);
+    if (h->pos32) {
+      if (h->occ_load == 0) return run_first<BwtOccLine, BwtOccLine32T<0>>(h, b, s);
+      return run_first<BwtOccLine, BwtOccLine32T<4>>(h, b, s);
     }
+    if (h->occ_load == 0) return run_first<BwtOccLine, BwtOccLine>(h, b, s);
+    return run_first<BwtOccLine, BwtOccLineT<4>>(h, b, s);
   }
   return run_first<BwtRunBlock, BwtRunBlock>(h, b, s);
 }

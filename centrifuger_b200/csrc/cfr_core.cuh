@@ -341,6 +341,7 @@ CFR_HD u64 last_chr_fix(const DevIndex &ix, int c, u64 p, int inclusive) {
 }
 
 struct BwtRunBlock {
+  typedef u64 pos_t;
   // FMIndex::BackwardExtend (range form), FMIndex.hpp:364-379
   static CFR_HD void extend(const DevIndex &ix, int c, u64 sp, u64 ep, u64 &nsp, u64 &nep, OpCount &oc) {
     const u64 off = ix.C[c];
@@ -459,6 +460,7 @@ CFR_HD int occ_symbol(u64 lo, u64 hi, int s) { return (int)(((lo >> s) & 1ull) |
 
 template <int LOAD>
 struct BwtOccLineT {
+  typedef u64 pos_t;
   // straight-line: both ranks and the symbol test are always computed, the range /
   // single-row forms of FMIndex::BackwardExtend are selected at the end.  Returns sp != ep.
   static CFR_HD bool extend_core(const DevIndex &ix, int c, u64 sp, u64 ep, u64 &nsp, u64 &nep) {
@@ -509,6 +511,65 @@ struct BwtOccLineT {
 };
 
 typedef BwtOccLineT<0> BwtOccLine;
+
+// The same sectors walked with 32-bit positions, for collections below 2^32 - 16 BWT rows (the
+// high count bytes of every sector are zero then): BackwardExtend and LF are a chain of
+// position arithmetic, and half-width positions shorten it and free registers for more
+// resident warps.  Wrap-around plays the role it plays in the reference's size_t arithmetic:
+// "C + rank - 1" wraps to 2^32 - 1 > n exactly where the 64-bit form wraps past n
+// (FMIndex.hpp:371-378,503).
+CFR_HD u32 occ_base32(u64 w2, u64 w3, int c, u32 sec) {
+  const u32 a = (u32)w2, cc = (u32)(w2 >> 32), g = (u32)w3;
+  const u32 t = (sec << 6) - (a + cc + g);
+  const u32 r01 = (c & 1) ? cc : a;
+  const u32 r23 = (c & 1) ? t : g;
+  return (c & 2) ? r23 : r01;
+}
+
+template <int LOAD>
+struct BwtOccLine32T {
+  typedef u32 pos_t;
+  static CFR_HD bool extend_core(const DevIndex &ix, int c, u32 sp, u32 ep, u32 &nsp, u32 &nep) {
+    const u32 off = (u32)ix.C[c];
+    const bool range = sp != ep;
+    const u32 xe = ep + 1;
+    const u32 sa = sp >> 6, se = xe >> 6;
+    u64 alo, ahi, aw2, aw3, elo, ehi, ew2, ew3;
+    occ_load<LOAD>(ix.occ + sa, alo, ahi, aw2, aw3);  // Rank(c, sp, exclusive)
+    occ_load<LOAD>(ix.occ + se, elo, ehi, ew2, ew3);  // Rank(c, ep, inclusive)
+    const u32 ca = occ_base32(aw2, aw3, c, sa) + (u32)popc64(occ_match(alo, ahi, c) & ((1ull << (sp & 63)) - 1ull));
+    const u32 ce = occ_base32(ew2, ew3, c, se) + (u32)popc64(occ_match(elo, ehi, c) & ((1ull << (xe & 63)) - 1ull));
+    const int sym = occ_symbol(alo, ahi, (int)(ep & 63));  // BWT[ep] when sp == ep (same sector as sp)
+    const u32 is_last = c == ix.last_code ? 1u : 0u;
+    const u32 fisa = (u32)ix.first_isa;
+    nsp = off + ca + (is_last & (sp <= fisa ? 1u : 0u));
+    const u32 nep_range = off + ce + (is_last & (ep < fisa ? 1u : 0u)) - 1u;
+    const u32 nep_single = nsp + ((sym == c) ? 0u : ~0u);
+    nep = range ? nep_range : nep_single;
+    return range;
+  }
+  enum { STEPS_COUNTED_AT_CLOSE = 1 };
+  static CFR_HD void extend_step(const DevIndex &ix, int c, u32 sp, u32 ep, u32 &nsp, u32 &nep, OpCount &oc) {
+    oc.xsingle += extend_core(ix, c, sp, ep, nsp, nep) ? 0u : 1u;
+  }
+  static CFR_HD u32 lf(const DevIndex &ix, u32 i, OpCount &oc) {
+    ++oc.access;
+    ++oc.rank;
+    const u32 sec = i >> 6;
+    const int s = (int)(i & 63);
+    u64 lo, hi, w2, w3;
+    occ_load<LOAD>(ix.occ + sec, lo, hi, w2, w3);
+    const int c = occ_symbol(lo, hi, s);
+    const u32 r = occ_base32(w2, w3, c, sec) + (u32)popc64(occ_match(lo, hi, c) & ((1ull << s) - 1ull));
+    // inclusive rank at i = exclusive count at i, plus the symbol itself; FMIndex::Rank's lastChr fix
+    return (u32)ix.C[c] + r + ((c == ix.last_code && i < (u32)ix.first_isa) ? 1u : 0u);
+  }
+  static CFR_HD bool leader() { return true; }
+  enum { LANES = 1 };
+};
+
+// largest row count the 32-bit walkers accept
+#define CFR_POS32_MAX_N 0xfffffff0ull
 
 // ---------------------------------------------------------------------------
 // FM-index search and locate
@@ -571,11 +632,13 @@ CFR_HD u64 sa_read(const DevIndex &ix, u64 i) {
 
 // i % sampleRate == 0 and i / filterRate; both rates are powers of two in every
 // index the reference builder writes (--offrate, 1024), the general form is kept
-CFR_HD bool is_sampled_row(const DevIndex &ix, u64 i) {
-  return ix.sample_shift >= 0 ? (i & ((1ull << ix.sample_shift) - 1ull)) == 0 : (i % (u64)ix.sample_rate) == 0;
+template <typename Pos>
+CFR_HD bool is_sampled_row(const DevIndex &ix, Pos i) {
+  return ix.sample_shift >= 0 ? (i & (((Pos)1 << ix.sample_shift) - (Pos)1)) == 0 : (i % (Pos)ix.sample_rate) == 0;
 }
-CFR_HD u64 filter_bit_index(const DevIndex &ix, u64 i) {
-  return ix.filter_shift >= 0 ? (i >> ix.filter_shift) : i / (u64)ix.sel_filter_rate;
+template <typename Pos>
+CFR_HD Pos filter_bit_index(const DevIndex &ix, Pos i) {
+  return ix.filter_shift >= 0 ? (i >> ix.filter_shift) : i / (Pos)ix.sel_filter_rate;
 }
 
 // FMIndex::GetSampledSA

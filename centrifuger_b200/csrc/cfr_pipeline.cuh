@@ -17,7 +17,6 @@
 namespace cfrb200 {
 
 #define CFR_ROW_SENTINEL (~0ull)
-enum { CFR_SCORE_LOCAL_ROWS = 8 };
 
 struct ChunkDev {
   u64 n_reads;
@@ -280,8 +279,11 @@ template <class Bwt, bool SPLIT = true>
 CFR_HD void search_tasks(const DevIndex &ix, const DevParams &P, const ChunkDev &B, const u64 ntask, OpCount &oc) {
   const int W = ix.pre_width, mhl = P.min_hit_len;
   const int sshift = B.mates == 2 ? 2 : 1;  // strand tasks per read = 2 * mates = 1 << sshift
+  typedef typename Bwt::pos_t pos_t;
+  const pos_t n_rows = (pos_t)ix.n;
   StrandSeq s{B.codes, B.mask, 0, 0, 0};
-  u64 cur = 0, sp = 0, ep = 0;
+  u64 cur = 0;
+  pos_t sp = 0, ep = 0;
   int nh = 0, remaining = 0, l = 0;
   int st = CFR_ST_FETCH;
   u64x2 pend;  // lookup-table entry in flight between the two halves of a transition
@@ -370,8 +372,8 @@ CFR_HD void search_tasks(const DevIndex &ix, const DevParams &P, const ChunkDev 
                   ep = 0;
                   l = W - 1;
                 } else {
-                  sp = pend.x;
-                  ep = pend.x + pend.y - 1;
+                  sp = (pos_t)pend.x;
+                  ep = (pos_t)(pend.x + pend.y - 1);
                   l = W;
                   if (l < remaining) {
                     st = CFR_ST_EXTEND;
@@ -382,7 +384,7 @@ CFR_HD void search_tasks(const DevIndex &ix, const DevParams &P, const ChunkDev 
             }
           } else {
             sp = 0;
-            ep = ix.n - 1;
+            ep = n_rows - 1;
             l = 0;
             if (l < remaining) {
               st = CFR_ST_EXTEND;
@@ -396,9 +398,9 @@ CFR_HD void search_tasks(const DevIndex &ix, const DevParams &P, const ChunkDev 
       const int c = s.peek();   // the cursor stands on strand position remaining - 1 - l
       st = CFR_ST_CLOSE;
       if (c <= 3) {
-        u64 nsp, nep;
+        pos_t nsp, nep;
         Bwt::extend_step(ix, c, sp, ep, nsp, nep, oc);
-        if (!(nsp > nep || nep > ix.n)) {
+        if (!(nsp > nep || nep > n_rows)) {
           sp = nsp;
           ep = nep;
           ++l;
@@ -416,8 +418,8 @@ CFR_HD void search_tasks(const DevIndex &ix, const DevParams &P, const ChunkDev 
         ep = 0;
         l = W - 1;
       } else {
-        sp = pend.x;
-        ep = pend.x + pend.y - 1;
+        sp = (pos_t)pend.x;
+        ep = (pos_t)(pend.x + pend.y - 1);
         l = W;
         if (l < remaining) {
           st = CFR_ST_EXTEND;
@@ -437,7 +439,9 @@ enum { CFR_LS_WALK = 0, CFR_LS_CHECK = 1, CFR_LS_NEED = 2, CFR_LS_DONE = 3 };
 
 template <class Bwt>
 CFR_HD void locate_rows(const DevIndex &ix, const DevParams &P, const ChunkDev &B, const u64 used, OpCount &oc) {
-  u64 cur = 0, i = 0;
+  typedef typename Bwt::pos_t pos_t;
+  u64 cur = 0;
+  pos_t i = 0;
   int st = CFR_LS_NEED;
   for (;;) {
     const u32 walk = CFR_BALLOT(st == CFR_LS_WALK);
@@ -463,16 +467,17 @@ CFR_HD void locate_rows(const DevIndex &ix, const DevParams &P, const ChunkDev &
           st = CFR_LS_DONE;
         } else {
           cur = claimed;
-          i = B.rows[cur];
-          if (i != CFR_ROW_SENTINEL) st = CFR_LS_WALK;
+          const u64 row = B.rows[cur];
+          i = (pos_t)row;
+          if (row != CFR_ROW_SENTINEL) st = CFR_LS_WALK;
         }
       }
     }
     if (st == CFR_LS_WALK) {
       // cheap pre-test of GetSampledSA's three conditions; the loads happen in the transition block
-      bool maybe = i == ix.first_isa || is_sampled_row(ix, i);
+      bool maybe = i == (pos_t)ix.first_isa || is_sampled_row(ix, i);
       if (!maybe && ix.sel_filter) {
-        const u64 fb = filter_bit_index(ix, i);
+        const pos_t fb = filter_bit_index(ix, i);
         maybe = (ld64(ix.sel_filter + (fb >> 6)) >> (fb & 63)) & 1ull;
       }
       if (maybe) {
@@ -585,18 +590,8 @@ CFR_HD int score_stage(const DevIndex &ix, const DevParams &P, const ChunkDev &B
   res.by_rank = 0;
   u64 *out = B.out_ids + read * (u64)P.max_result;
   const u64 a = w.arena_base;
-  if (w.arena_rows <= CFR_SCORE_LOCAL_ROWS) {
-    // the common case (a few located rows): the per-read tables fit thread-local storage, which
-    // keeps the dependent read-modify-write chain of the scoring out of L2
-    u32 ids[CFR_SCORE_LOCAL_ROWS];
-    SeqRec r0[CFR_SCORE_LOCAL_ROWS], r1[CFR_SCORE_LOCAL_ROWS];
-    u64 best[CFR_SCORE_LOCAL_ROWS], tmp[CFR_SCORE_LOCAL_ROWS];
-    for (u32 i = 0; i < w.arena_rows; ++i) ids[i] = B.seq_ids[a + i];
-    score_read(ix, P, fh, (int)w.n_hits, ids, r0, r1, best, tmp, res, out, err_flags);
-  } else {
-    score_read(ix, P, fh, (int)w.n_hits, B.seq_ids + a, B.rec0 + a, B.rec1 + a, B.best + a, B.tmp + a, res, out,
-               err_flags);
-  }
+  score_read(ix, P, fh, (int)w.n_hits, B.seq_ids + a, B.rec0 + a, B.rec1 + a, B.best + a, B.tmp + a, res, out,
+             err_flags);
   for (int i = res.n_assign; i < P.max_result; ++i) out[i] = 0;  // unused id slots read as 0
   B.results[read] = res;
   return res.n_assign;

@@ -24,6 +24,7 @@ struct HostIndex {
   std::vector<unsigned char> rank;
   std::vector<u64> sel_filter;
   std::vector<OccLine> occ;
+  bool pos32 = false;
   DevIndex ix;
   DevParams P;
   int layout;
@@ -114,7 +115,11 @@ void *hostsim_open(const char *prefix, const cfr_params *p) {
   ix.rank = h->rank.data();
   ix.seq_to_tax = h->seq_to_tax.data();
   init_tax_rank_num(ix.rank_num);
-  h->layout = p->layout == CFR_LAYOUT_OCCLINE ? 2 : 1;
+  // layout 2 = occ sectors (32-bit positions when the index allows, as the library does), 3 = occ
+  // sectors with 64-bit positions forced, anything else = the run-block arrays
+  h->layout = p->layout == CFR_LAYOUT_OCCLINE ? 2 : (p->layout == 3 ? 3 : 1);
+  h->pos32 = h->layout == 2 && f.n < CFR_POS32_MAX_N;
+  if (h->layout == 3) h->layout = 2;
   if (h->layout == 2) {  // same construction the transcode kernel performs
     const u64 lines = f.n / 64 + 1;
     h->occ.resize(lines);
@@ -291,7 +296,8 @@ int hostsim_classify(void *hh, int dust, uint64_t arena_rows, const cfr_read_bat
   u64 task_counter = 0, row_counter = 0;
   B.task_counter = &task_counter;
   B.row_counter = &row_counter;
-  if (h->layout == 2) search_tasks<BwtOccLine>(ix, P, B, n * S, oc);
+  if (h->layout == 2 && h->pos32) search_tasks<BwtOccLine32T<0>>(ix, P, B, n * S, oc);
+  else if (h->layout == 2) search_tasks<BwtOccLine>(ix, P, B, n * S, oc);
   else search_tasks<BwtRunBlock>(ix, P, B, n * S, oc);
   B.read_list = nullptr;
   B.n_list = n;
@@ -320,7 +326,8 @@ int hostsim_classify(void *hh, int dust, uint64_t arena_rows, const cfr_read_bat
     }
     const u64 used = std::min(std::min(arena_used, arena_valid), B.arena_cap);
     row_counter = 0;
-    if (h->layout == 2) locate_rows<BwtOccLine>(ix, P, B, used, oc);
+    if (h->layout == 2 && h->pos32) locate_rows<BwtOccLine32T<0>>(ix, P, B, used, oc);
+    else if (h->layout == 2) locate_rows<BwtOccLine>(ix, P, B, used, oc);
     else locate_rows<BwtRunBlock>(ix, P, B, used, oc);
     for (u64 t = 0; t < B.n_list; ++t) {
       const u64 read = chunk_read_id(B, t);

@@ -35,7 +35,7 @@ def _compare(idx, files, layout, arena_rows=0, limit=None, **kw):
         o.close()
 
 
-@pytest.mark.parametrize("layout", [1, 2])
+@pytest.mark.parametrize("layout", [1, 2, 3])  # 3 = occ sectors walked with 64-bit positions
 @pytest.mark.parametrize("variant", ["idx", "idx_b1", "idx_b8", "idx_off3"])
 def test_tiny_all_read_sets(tiny_dir, layout, variant):
     idx = os.path.join(tiny_dir, variant)
@@ -58,7 +58,7 @@ def test_small_arena_deferral(tiny_dir, layout):
 def test_example(example_idx):
     from conftest import golden_path
     fs = [golden_path("example", "example_1.fq"), golden_path("example", "example_2.fq")]
-    for layout in (1, 2):
+    for layout in (1, 2, 3):
         _compare(example_idx, fs, layout)
         _compare(example_idx, fs[:1], layout, k=5, dust=False)
 
