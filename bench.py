@@ -43,6 +43,8 @@ WORKLOADS = {
                desc="synthetic 100 Mbp / 50-taxa index, 1M x 100 bp single-end reads (BASELINE configs[1])"),
     "small": dict(dataset="small", reads=200_000, rlen=100, paired=False, k=1,
                   desc="synthetic 10 Mbp / 100-sequence index, 200k x 100 bp single-end reads"),
+    "small1m": dict(dataset="small", reads=1_000_000, rlen=100, paired=False, k=1,
+                    desc="synthetic 10 Mbp / 100-sequence index (occ sectors 5 MB), 1M x 100 bp single-end reads"),
     "m700": dict(dataset="m700", reads=1_000_000, rlen=100, paired=False, k=1,
                  desc="synthetic 700 Mbp / 175-taxa index (occ lines 350 MB > L2), 1M x 100 bp single-end reads"),
     "m700pe": dict(dataset="m700", reads=500_000, rlen=150, paired=True, k=5,
