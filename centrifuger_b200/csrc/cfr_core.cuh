@@ -445,6 +445,24 @@ CFR_HD void occ_load(const OccLine *L, u64 &lo, u64 &hi, u64 &w2, u64 &w3) {
   w3 = q.y;
 }
 
+// the same fetch, issued only by the lanes with `pred` (the other lanes keep the zeros passed in);
+// predicated inside the asm block so that the compiler cannot tie it to an earlier load
+template <int LOAD>
+CFR_HD void occ_load_if(const OccLine *L, bool pred, u64 &lo, u64 &hi, u64 &w2, u64 &w3) {
+#if defined(__CUDA_ARCH__)
+  const u32 p = pred ? 1u : 0u;
+  if (LOAD == 4) {
+    asm volatile("{ .reg .pred q; setp.ne.u32 q, %5, 0; @q ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4]; }"
+                 : "+l"(lo), "+l"(hi), "+l"(w2), "+l"(w3) : "l"(L), "r"(p));
+  } else {
+    asm volatile("{ .reg .pred q; setp.ne.u32 q, %5, 0; @q ld.global.nc.v2.u64 {%0,%1}, [%4]; @q ld.global.nc.v2.u64 {%2,%3}, [%4+16]; }"
+                 : "+l"(lo), "+l"(hi), "+l"(w2), "+l"(w3) : "l"(L), "r"(p));
+  }
+#else
+  if (pred) occ_load<LOAD>(L, lo, hi, w2, w3);
+#endif
+}
+
 template <int LOAD>
 CFR_HD OccRank occ_rank(const DevIndex &ix, int c, u64 x) {
   const u64 sec = x >> 6;
@@ -466,13 +484,25 @@ struct BwtOccLineT {
   static CFR_HD bool extend_core(const DevIndex &ix, int c, u64 sp, u64 ep, u64 &nsp, u64 &nep) {
     const u64 off = ix.C[c];
     const bool range = sp != ep;
-    const OccRank a = occ_rank<LOAD>(ix, c, sp);      // Rank(c, sp, exclusive)
-    const OccRank e = occ_rank<LOAD>(ix, c, ep + 1);  // Rank(c, ep, inclusive)
-    const int sym = occ_symbol(a.lo, a.hi, (int)(ep & 63));  // BWT[ep] when sp == ep (same sector as sp)
+    const u64 xe = ep + 1;
+    const u64 sa = sp >> 6, se = xe >> 6;
+    u64 alo, ahi, aw2, aw3, elo = 0, ehi = 0, ew2 = 0, ew3 = 0;
+    occ_load<LOAD>(ix.occ + sa, alo, ahi, aw2, aw3);  // Rank(c, sp, exclusive)
+    // Rank(c, ep, inclusive): ep + 1 mostly falls into the sector just requested; a second request
+    // for it right behind the first one is not merged by L1 and goes to L2 again
+    const bool other = se != sa;
+    occ_load_if<LOAD>(ix.occ + se, other, elo, ehi, ew2, ew3);
+    elo = other ? elo : alo;
+    ehi = other ? ehi : ahi;
+    ew2 = other ? ew2 : aw2;
+    ew3 = other ? ew3 : aw3;
+    const u64 a_count = occ_base(aw2, aw3, c, sa) + (u64)popc64(occ_match(alo, ahi, c) & ((1ull << (sp & 63)) - 1ull));
+    const u64 e_count = occ_base(ew2, ew3, c, se) + (u64)popc64(occ_match(elo, ehi, c) & ((1ull << (xe & 63)) - 1ull));
+    const int sym = occ_symbol(alo, ahi, (int)(ep & 63));  // BWT[ep] when sp == ep (same sector as sp)
     // FMIndex::Rank's correction for the missing '$' (FMIndex.hpp:359), both forms at once
     const u64 is_last = c == ix.last_code ? 1ull : 0ull;
-    nsp = off + a.count + (is_last & (sp <= ix.first_isa ? 1ull : 0ull));
-    const u64 nep_range = off + e.count + (is_last & (ep < ix.first_isa ? 1ull : 0ull)) - 1;
+    nsp = off + a_count + (is_last & (sp <= ix.first_isa ? 1ull : 0ull));
+    const u64 nep_range = off + e_count + (is_last & (ep < ix.first_isa ? 1ull : 0ull)) - 1;
     const u64 nep_single = nsp + ((sym == c) ? 0ull : ~0ull);
     nep = range ? nep_range : nep_single;
     return range;
@@ -534,9 +564,16 @@ struct BwtOccLine32T {
     const bool range = sp != ep;
     const u32 xe = ep + 1;
     const u32 sa = sp >> 6, se = xe >> 6;
-    u64 alo, ahi, aw2, aw3, elo, ehi, ew2, ew3;
+    u64 alo, ahi, aw2, aw3, elo = 0, ehi = 0, ew2 = 0, ew3 = 0;
     occ_load<LOAD>(ix.occ + sa, alo, ahi, aw2, aw3);  // Rank(c, sp, exclusive)
-    occ_load<LOAD>(ix.occ + se, elo, ehi, ew2, ew3);  // Rank(c, ep, inclusive)
+    // Rank(c, ep, inclusive): ep + 1 mostly falls into the sector just requested; a second request
+    // for it right behind the first one is not merged by L1 and goes to L2 again
+    const bool other = se != sa;
+    occ_load_if<LOAD>(ix.occ + se, other, elo, ehi, ew2, ew3);
+    elo = other ? elo : alo;
+    ehi = other ? ehi : ahi;
+    ew2 = other ? ew2 : aw2;
+    ew3 = other ? ew3 : aw3;
     const u32 ca = occ_base32(aw2, aw3, c, sa) + (u32)popc64(occ_match(alo, ahi, c) & ((1ull << (sp & 63)) - 1ull));
     const u32 ce = occ_base32(ew2, ew3, c, se) + (u32)popc64(occ_match(elo, ehi, c) & ((1ull << (xe & 63)) - 1ull));
     const int sym = occ_symbol(alo, ahi, (int)(ep & 63));  // BWT[ep] when sp == ep (same sector as sp)
