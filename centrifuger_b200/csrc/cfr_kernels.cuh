@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(CFR_DUST_THREADS) k_dust(const __grid_constant
   d.win.base = reinterpret_cast<unsigned char *>(&dust_sm[64 * CFR_DUST_THREADS + threadIdx.x]);  // 16 words
   // mates are claimed dynamically from B.dust_counter (through B.dust_list when the screen ran)
   dust_tasks(B, B.dust_list ? (u64)*B.dust_list_n : B.n_reads * (u64)B.mates, d, quorum,
-             (int)(threadIdx.x & 31) < lanes_per_warp);
+             (int)(threadIdx.x & 31) < lanes_per_warp, B.dust_list != nullptr);
 }
 
 // MINB = resident blocks per SM the register allocation must allow (occupancy knob)

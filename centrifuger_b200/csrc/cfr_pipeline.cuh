@@ -135,10 +135,11 @@ CFR_HD void encode_stage(const ChunkDev &B, u64 w, u64 total_bytes) {
 // STEP advance their window by one base together; FindPerfect (long, data
 // dependent, needed by a minority of positions) and the per-mate set-up run when a
 // quorum of lanes waits for them.  Mates are claimed dynamically.
-enum { CFR_DS_FETCH = 0, CFR_DS_SEG = 1, CFR_DS_STEP = 2, CFR_DS_SLOW = 3, CFR_DS_DONE = 4 };
+enum { CFR_DS_FETCH = 0, CFR_DS_SEG = 1, CFR_DS_STEP = 2, CFR_DS_SLOW = 3, CFR_DS_DONE = 4, CFR_DS_SHRINK = 5 };
 
 template <int SW>
-CFR_HD void dust_tasks(const ChunkDev &B, const u64 ntask, DustStateT<SW> &d, const int quorum, const bool active = true) {
+CFR_HD void dust_tasks(const ChunkDev &B, const u64 ntask, DustStateT<SW> &d, const int quorum, const bool active = true,
+                       const bool defer_shrink = false) {
   DustIn in{B.codes, B.mask_raw, 0};
   DustOut out{B.mask, B.dust_bits, 0};
   // `active` = false parks the lane: the deferred loops (FindPerfect, shrink) of one mate stall the
@@ -147,7 +148,7 @@ CFR_HD void dust_tasks(const ChunkDev &B, const u64 ntask, DustStateT<SW> &d, co
   int len = 0, cursor = 0, seg_off = 0, seg_n = 0, wfinish = 0, c1 = 0, c2 = 0, t_last = 0;
   for (;;) {
     const u32 m_step = CFR_BALLOT(st == CFR_DS_STEP);
-    const u32 m_slow = CFR_BALLOT(st == CFR_DS_SLOW);
+    const u32 m_slow = CFR_BALLOT(st == CFR_DS_SLOW || st == CFR_DS_SHRINK);
     const u32 m_trn = CFR_BALLOT(st == CFR_DS_FETCH || st == CFR_DS_SEG);
     if ((m_step | m_slow | m_trn) == 0) break;
     const int alive = popc32(m_step | m_slow | m_trn);
@@ -204,18 +205,30 @@ CFR_HD void dust_tasks(const ChunkDev &B, const u64 ntask, DustStateT<SW> &d, co
     }
     bool advance = false;
     // FindPerfect (long, data dependent) for the lanes that need it
+    // the two data-dependent loops of a step -- shrinking the suffix and FindPerfect -- for the lanes
+    // that wait for them
     if (m_slow != 0 && (m_step == 0 || popc32(m_slow) >= q_now)) {
-      if (st == CFR_DS_SLOW) {
+      if (st == CFR_DS_SHRINK) {
+        dust_shrink(d, t_last);
+        st = CFR_DS_SLOW;
+        if (!dust_needs_find_perfect(d)) advance = true;
+      }
+      if (st == CFR_DS_SLOW && !advance) {
         dust_find_perfect(wfinish, d);
         advance = true;
       }
     }
     if (st == CFR_DS_STEP) {
-      if (dust_step(in, out, seg_off, wfinish, d, c1, c2, t_last)) dust_shrink(d, t_last);  // short loop: inline
-      if (dust_needs_find_perfect(d))
-        st = CFR_DS_SLOW;
-      else
-        advance = true;
+      const bool shrink = dust_step(in, out, seg_off, wfinish, d, c1, c2, t_last);
+      if (shrink && defer_shrink) {
+        st = CFR_DS_SHRINK;  // mates that reach the full masker after the screen shrink often: batch the loop
+      } else {
+        if (shrink) dust_shrink(d, t_last);  // rare on unscreened input and short: inline
+        if (dust_needs_find_perfect(d))
+          st = CFR_DS_SLOW;
+        else
+          advance = true;
+      }
     }
     if (advance) {
       ++wfinish;

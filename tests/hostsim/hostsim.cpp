@@ -292,7 +292,7 @@ int hostsim_classify(void *hh, int dust, uint64_t arena_rows, const cfr_read_bat
     B.dust_list = dust_list.data();
     B.dust_list_n = &dust_list_n;
   }
-  if (dust) dust_tasks(B, B.dust_list ? (u64)dust_list_n : n * mates, ds, P.quorum);
+  if (dust) dust_tasks(B, B.dust_list ? (u64)dust_list_n : n * mates, ds, P.quorum, true, B.dust_list != nullptr);
   u64 task_counter = 0, row_counter = 0;
   B.task_counter = &task_counter;
   B.row_counter = &row_counter;

@@ -11,7 +11,7 @@ import sys
 def main():
     rep, kern = sys.argv[1], sys.argv[2]
     min_pct = float(sys.argv[3]) if len(sys.argv) > 3 else 0.4
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + kern],
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", kern if kern.startswith("=") is False and "|" not in kern and "\\" not in kern and "(" not in kern else "regex:" + kern],
                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL).stdout.decode()
     rows = list(csv.reader(io.StringIO(raw)))
     hdr = rows[1]
