@@ -65,20 +65,12 @@ struct cfr_device_batch {
   u64 off_bias[2] = {0, 0};
   u64 arena_cap = 0;
   DevBuf seq_raw, codes, mask_raw, mask, off, strand_hits, strand_nhits, fhits, work, rows, seq_ids, rec0, rec1, best, tmp,
-      results, out_ids, deferred, dust_list, dust_flags, scalars;  // scalars: {u64 arena_used, u32 n_deferred, pad}
+      results, out_ids, deferred, dust_list, scalars;  // scalars: {u64 arena_used, u32 n_deferred, pad}
   bool classified = false;
-  // the full SDUST of the mates the screen could not clear runs on `aux`, next to the search of the others
-  cudaStream_t aux = nullptr;
-  cudaEvent_t ev_screen = nullptr, ev_dust = nullptr;
   void release() {
     DevBuf *all[] = {&seq_raw, &codes, &mask_raw, &mask, &off, &strand_hits, &strand_nhits, &fhits, &work, &rows, &seq_ids,
-                     &rec0, &rec1, &best, &tmp, &results, &out_ids, &deferred, &dust_list, &dust_flags, &scalars};
+                     &rec0, &rec1, &best, &tmp, &results, &out_ids, &deferred, &dust_list, &scalars};
     for (DevBuf *b : all) b->release();
-    if (aux) cudaStreamDestroy(aux);
-    if (ev_screen) cudaEventDestroy(ev_screen);
-    if (ev_dust) cudaEventDestroy(ev_dust);
-    aux = nullptr;
-    ev_screen = ev_dust = nullptr;
   }
 };
 
@@ -99,7 +91,6 @@ struct cfr_handle {
   size_t occ_bytes = 0;
   int max_window = 0;
   bool pos32 = false;  // 32-bit BWT positions in k_search / k_locate (collections below 2^32 rows; CFR_B200_POS64=1 disables)
-  bool dust_overlap = true;  // full SDUST of the listed mates overlaps the search of the others (CFR_B200_DUST_OVERLAP)
   int dust_lanes = 16;  // lanes per warp that take mates in the post-screen SDUST launch (CFR_B200_DUST_LANES)
   bool dust_screen = true;  // register-only screen in front of the full SDUST (CFR_B200_DUST_SCREEN=0 disables)
   u64 *d_taxon = nullptr;
@@ -194,23 +185,16 @@ int grid_for(const cfr_handle *h, u64 tasks, int threads, int blocks_per_sm) {
 
 // DUST over the chunk: the register-only screen clears most mates, the full SDUST state
 // machine runs on the rest (scalars must be zero: dust_counter, dust_list_n)
-void launch_dust_screen(cfr_handle *h, const ChunkDev &B, cudaStream_t s) {
+void launch_dust(cfr_handle *h, const ChunkDev &B, cudaStream_t s) {
   const u64 ntask = B.n_reads * (u64)B.mates;
-  k_dust_screen<<<grid_for(h, ntask, 128, 16), 128, 0, s>>>(B);
-  ++h->launches;
-}
-
-void launch_dust_full(cfr_handle *h, const ChunkDev &B, cudaStream_t s) {
-  const u64 ntask = B.n_reads * (u64)B.mates;
+  if (B.dust_list) {
+    k_dust_screen<<<grid_for(h, ntask, 128, 16), 128, 0, s>>>(B);
+    ++h->launches;
+  }
   // after the screen only the few mates that need the whole algorithm are left: fewer lanes per warp
   k_dust<<<grid_for(h, ntask, CFR_DUST_THREADS, 5), CFR_DUST_THREADS, CFR_DUST_SMEM, s>>>(
       B, h->P.quorum, B.dust_list ? h->dust_lanes : 32);
   ++h->launches;
-}
-
-void launch_dust(cfr_handle *h, const ChunkDev &B, cudaStream_t s) {
-  if (B.dust_list) launch_dust_screen(h, B, s);
-  launch_dust_full(h, B, s);
 }
 
 int upload_index(cfr_handle *h) {
@@ -382,7 +366,6 @@ int upload_chunk(cfr_handle *h, const cfr_read_batch *in, u64 r0, u64 r1, cfr_de
   if ((st = b->out_ids.ensure(n * (u64)h->P.max_result * 8))) return st;
   if ((st = b->deferred.ensure(n * 4 * 2))) return st;
   if ((st = b->dust_list.ensure(n * 4 * (u64)mates))) return st;
-  if ((st = b->dust_flags.ensure((n * (u64)mates / 32 + 2) * 4))) return st;
   if ((st = b->scalars.ensure(64))) return st;
   // H2D
   if (len1) CUDA_TRY(cudaMemcpyAsync(b->seq_raw.p, in->seq1 + s1, len1, cudaMemcpyHostToDevice, s));
@@ -421,7 +404,6 @@ void fill_chunk(cfr_handle *h, cfr_device_batch *b, ChunkDev &B) {
   B.arena_valid = (u64 *)((char *)b->scalars.p + 40);
   B.dust_list_n = (u32 *)((char *)b->scalars.p + 48);
   B.dust_list = h->dust_screen ? (u32 *)b->dust_list.p : nullptr;
-  B.dust_flags = h->dust_screen && h->dust_overlap ? (u32 *)b->dust_flags.p : nullptr;
   B.rows = (u64 *)b->rows.p;
   B.seq_ids = (u32 *)b->seq_ids.p;
   B.rec0 = (SeqRec *)b->rec0.p;
@@ -490,47 +472,18 @@ int run_first(cfr_handle *h, cfr_device_batch *b, cudaStream_t s) {
     k_encode<<<grid_for(h, B.n_words, 256, 8), 256, 0, s>>>(B, b->seq_bytes);
     ++h->launches;
   }
-  auto launch_search = [&](int mode) {
+  if (h->params.dust) {
+    StageScope sc(h, s, CFR_STAGE_DUST);
+    launch_dust(h, B, s);
+  }
+  CUDA_TRY(cudaMemsetAsync(B.task_counter, 0, 8, s));
+  {
+    StageScope sc(h, s, CFR_STAGE_SEARCH);
     const int g = grid_for(h, B.n_reads * 2 * B.mates, 128, h->search_blocks);
-    if (h->search_blocks >= 12) k_search<BwtWide, 12, false><<<g, 128, 0, s>>>(h->ix, h->P, B, mode);
-    else if (h->search_blocks >= 10) k_search<BwtWide, 10, false><<<g, 128, 0, s>>>(h->ix, h->P, B, mode);
-    else k_search<BwtWide, 8, false><<<g, 128, 0, s>>>(h->ix, h->P, B, mode);
+    if (h->search_blocks >= 12) k_search<BwtWide, 12, false><<<g, 128, 0, s>>>(h->ix, h->P, B);
+    else if (h->search_blocks >= 10) k_search<BwtWide, 10, false><<<g, 128, 0, s>>>(h->ix, h->P, B);
+    else k_search<BwtWide, 8, false><<<g, 128, 0, s>>>(h->ix, h->P, B);
     ++h->launches;
-  };
-  const bool overlap = h->params.dust && B.dust_list && B.dust_flags;
-  if (overlap) {
-    if (!b->aux) {
-      CUDA_TRY(cudaStreamCreateWithFlags(&b->aux, cudaStreamNonBlocking));
-      CUDA_TRY(cudaEventCreateWithFlags(&b->ev_screen, cudaEventDisableTiming));
-      CUDA_TRY(cudaEventCreateWithFlags(&b->ev_dust, cudaEventDisableTiming));
-    }
-    {
-      StageScope sc(h, s, CFR_STAGE_DUST);
-      CUDA_TRY(cudaMemsetAsync(b->dust_flags.p, 0, (B.n_reads * (u64)B.mates / 32 + 2) * 4, s));
-      launch_dust_screen(h, B, s);
-      CUDA_TRY(cudaEventRecord(b->ev_screen, s));
-      CUDA_TRY(cudaStreamWaitEvent(b->aux, b->ev_screen, 0));
-      launch_dust_full(h, B, b->aux);  // next to the search of the cleared mates
-      CUDA_TRY(cudaEventRecord(b->ev_dust, b->aux));
-    }
-    CUDA_TRY(cudaMemsetAsync(B.task_counter, 0, 8, s));
-    {
-      StageScope sc(h, s, CFR_STAGE_SEARCH);
-      launch_search(CFR_SEARCH_CLEARED);
-      CUDA_TRY(cudaStreamWaitEvent(s, b->ev_dust, 0));
-      CUDA_TRY(cudaMemsetAsync(B.task_counter, 0, 8, s));
-      launch_search(CFR_SEARCH_LISTED);
-    }
-  } else {
-    if (h->params.dust) {
-      StageScope sc(h, s, CFR_STAGE_DUST);
-      launch_dust(h, B, s);
-    }
-    CUDA_TRY(cudaMemsetAsync(B.task_counter, 0, 8, s));
-    {
-      StageScope sc(h, s, CFR_STAGE_SEARCH);
-      launch_search(CFR_SEARCH_ALL);
-    }
   }
   CUDA_TRY(cudaGetLastError());
   return run_pass<Bwt, BwtWide>(h, B, 1, s);
@@ -637,7 +590,6 @@ int cfr_open(const char *idx_prefix, const cfr_params *p, int device, cfr_handle
   if (const char *e = getenv("CFR_B200_QUORUM")) h->P.quorum = std::max(1, atoi(e));
   if (const char *e = getenv("CFR_B200_SEARCH_BLOCKS")) h->search_blocks = std::max(1, atoi(e));
   if (const char *e = getenv("CFR_B200_DUST_SCREEN")) h->dust_screen = atoi(e) != 0;
-  if (const char *e = getenv("CFR_B200_DUST_OVERLAP")) h->dust_overlap = atoi(e) != 0;
   if (const char *e = getenv("CFR_B200_DUST_LANES")) h->dust_lanes = std::min(32, std::max(1, atoi(e)));
   if (const char *e = getenv("CFR_B200_OCC_LOAD")) h->occ_load = atoi(e) == 0 ? 0 : 4;
   h->pos32 = h->file.n < CFR_POS32_MAX_N;

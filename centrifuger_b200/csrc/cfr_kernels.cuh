@@ -51,10 +51,7 @@ __global__ void __launch_bounds__(128) k_dust_screen(const __grid_constant__ Chu
     u32 base = 0;
     if (lane == 0) base = atomicAdd(B.dust_list_n, (u32)__popc(m));
     base = __shfl_sync(full, base, 0);
-    if (need) {
-      B.dust_list[base + (u32)__popc(m & ((1u << lane) - 1u))] = (u32)t;
-      if (B.dust_flags) atomicOr(B.dust_flags + (t >> 5), 1u << (t & 31));
-    }
+    if (need) B.dust_list[base + (u32)__popc(m & ((1u << lane) - 1u))] = (u32)t;
   }
 }
 
@@ -77,11 +74,10 @@ __global__ void __launch_bounds__(CFR_DUST_THREADS) k_dust(const __grid_constant
 template <class Bwt, int MINB, bool SPLIT>
 __global__ void __launch_bounds__(128, MINB) k_search(const __grid_constant__ DevIndex ix,
                                                       const __grid_constant__ DevParams P,
-                                                      const __grid_constant__ ChunkDev B, const int mode) {
+                                                      const __grid_constant__ ChunkDev B) {
   OpCount oc{};
-  // tasks are claimed dynamically from B.task_counter
-  const u64 ntask = mode == CFR_SEARCH_LISTED ? 2ull * (u64)*B.dust_list_n : B.n_reads * (u64)(2 * B.mates);
-  search_tasks<Bwt, SPLIT>(ix, P, B, ntask, oc, mode);
+  const u64 ntask = B.n_reads * (u64)(2 * B.mates);
+  search_tasks<Bwt, SPLIT>(ix, P, B, ntask, oc);  // tasks are claimed dynamically from B.task_counter
   if (!Bwt::leader()) oc = OpCount{};
   flush_counts(oc, B.counters + CFR_STAGE_SEARCH);
 }

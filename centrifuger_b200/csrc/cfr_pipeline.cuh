@@ -43,7 +43,6 @@ struct ChunkDev {
   u64 *dust_counter;  // next mate (dynamic fetch by the DUST warps)
   u32 *dust_list;     // mates the register-only screen could not clear (nullptr = every mate runs SDUST)
   u32 *dust_list_n;   // number of entries in dust_list
-  u32 *dust_flags;    // bit per mate: set for the mates on dust_list (nullptr = not kept)
   u64 *rows;
   u32 *seq_ids;
   SeqRec *rec0, *rec1;
@@ -289,16 +288,8 @@ CFR_HD int adaptive_quorum(int quorum, u32 alive_mask, int lanes_per_task) {
 
 enum { CFR_ST_EXTEND = 0, CFR_ST_CLOSE = 1, CFR_ST_FETCH = 2, CFR_ST_DONE = 3, CFR_ST_LOOKUP = 4 };
 
-// `mode` selects the strand tasks of a launch (the full SDUST of the few mates the screen could not
-// clear runs concurrently with the search of all the others):
-//   CFR_SEARCH_ALL      every strand task of the chunk
-//   CFR_SEARCH_CLEARED  every task whose mate is NOT on B.dust_list (their masks are final after the screen)
-//   CFR_SEARCH_LISTED   the two strands of each mate on B.dust_list (ntask = 2 * entries)
-enum { CFR_SEARCH_ALL = 0, CFR_SEARCH_CLEARED = 1, CFR_SEARCH_LISTED = 2 };
-
 template <class Bwt, bool SPLIT = true>
-CFR_HD void search_tasks(const DevIndex &ix, const DevParams &P, const ChunkDev &B, const u64 ntask, OpCount &oc,
-                         const int mode = CFR_SEARCH_ALL) {
+CFR_HD void search_tasks(const DevIndex &ix, const DevParams &P, const ChunkDev &B, const u64 ntask, OpCount &oc) {
   const int W = ix.pre_width, mhl = P.min_hit_len;
   const int sshift = B.mates == 2 ? 2 : 1;  // strand tasks per read = 2 * mates = 1 << sshift
   typedef typename Bwt::pos_t pos_t;
@@ -351,7 +342,6 @@ CFR_HD void search_tasks(const DevIndex &ix, const DevParams &P, const ChunkDev 
           st = CFR_ST_DONE;
         } else {
           cur = claimed;
-          if (mode == CFR_SEARCH_LISTED) cur = ((u64)B.dust_list[claimed >> 1] << 1) | (claimed & 1ull);
           const u64 read = cur >> sshift;
           const int w = (int)(cur & ((1ull << sshift) - 1ull));
           const int mate = w >> 1;
@@ -367,13 +357,6 @@ CFR_HD void search_tasks(const DevIndex &ix, const DevParams &P, const ChunkDev 
           st = CFR_ST_CLOSE;  // a strand shorter than minHitLen closes at once with no hits
           l = -1;             // (remaining -= l + 1 leaves it unchanged; xext sees l < W)
           if (remaining >= mhl) start = true;
-          if (mode == CFR_SEARCH_CLEARED) {
-            const u64 m = cur >> 1;  // the mate: this launch leaves the listed ones to the next
-            if ((B.dust_flags[m >> 5] >> (m & 31)) & 1u) {
-              st = CFR_ST_FETCH;
-              start = false;
-            }
-          }
         }
       }
       // the lanes that continue a strand and the lanes that just fetched one start their searches

@@ -284,32 +284,21 @@ int hostsim_classify(void *hh, int dust, uint64_t arena_rows, const cfr_read_bat
   for (u64 w = 0; w < n_words; ++w) encode_stage(B, w, len1 + len2);
   u64 dust_counter = 0;
   B.dust_counter = &dust_counter;
-  std::vector<u32> dust_list(n * mates + 1), dust_flags(n * mates / 32 + 2, 0);
+  std::vector<u32> dust_list(n * mates + 1);
   u32 dust_list_n = 0;
   if (dust && !getenv("HOSTSIM_NO_DUST_SCREEN")) {  // the screen kernel's loop, one lane
     for (u64 t = 0; t < n * mates; ++t)
-      if (dust_screen_stage(B, t)) {
-        dust_list[dust_list_n++] = (u32)t;
-        dust_flags[t >> 5] |= 1u << (t & 31);
-      }
+      if (dust_screen_stage(B, t)) dust_list[dust_list_n++] = (u32)t;
     B.dust_list = dust_list.data();
     B.dust_list_n = &dust_list_n;
-    B.dust_flags = dust_flags.data();
   }
   if (dust) dust_tasks(B, B.dust_list ? (u64)dust_list_n : n * mates, ds, P.quorum, true, B.dust_list != nullptr);
   u64 task_counter = 0, row_counter = 0;
   B.task_counter = &task_counter;
   B.row_counter = &row_counter;
-  // with the screen: the two launches of the library (cleared mates, then the listed ones)
-  const int n_pass = B.dust_flags ? 2 : 1;
-  for (int pass = 0; pass < n_pass; ++pass) {
-    const int mode = n_pass == 1 ? CFR_SEARCH_ALL : (pass == 0 ? CFR_SEARCH_CLEARED : CFR_SEARCH_LISTED);
-    const u64 nt = mode == CFR_SEARCH_LISTED ? 2ull * dust_list_n : n * S;
-    task_counter = 0;
-    if (h->layout == 2 && h->pos32) search_tasks<BwtOccLine32T<0>>(ix, P, B, nt, oc, mode);
-    else if (h->layout == 2) search_tasks<BwtOccLine>(ix, P, B, nt, oc, mode);
-    else search_tasks<BwtRunBlock>(ix, P, B, nt, oc, mode);
-  }
+  if (h->layout == 2 && h->pos32) search_tasks<BwtOccLine32T<0>>(ix, P, B, n * S, oc);
+  else if (h->layout == 2) search_tasks<BwtOccLine>(ix, P, B, n * S, oc);
+  else search_tasks<BwtRunBlock>(ix, P, B, n * S, oc);
   B.read_list = nullptr;
   B.n_list = n;
   u64 err_flags = 0;

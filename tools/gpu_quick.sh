@@ -15,11 +15,10 @@ grep -E "passed|failed|rror" gpurun_out/pytest_gpu.log | tail -3
 for W in $WL; do
   if [[ $W == m700* ]] && [ -n "$BUILD_PID" ]; then wait $BUILD_PID; BUILD_PID=""; fi
   for V in $VARS; do
-    unset CFR_B200_QUORUM CFR_B200_SEARCH_BLOCKS CFR_B200_DUST_SCREEN CFR_B200_L2_FETCH CFR_B200_DUST_OVERLAP
+    unset CFR_B200_QUORUM CFR_B200_SEARCH_BLOCKS CFR_B200_DUST_SCREEN CFR_B200_L2_FETCH
     case $V in
       noscreen) export CFR_B200_DUST_SCREEN=0 ;;
       sb*) export CFR_B200_SEARCH_BLOCKS=${V#sb} ;;
-      noov) export CFR_B200_DUST_OVERLAP=0 ;;
       l2*) export CFR_B200_L2_FETCH=${V#l2} ;;
       q*) export CFR_B200_QUORUM=${V#q} ;;
     esac
@@ -35,4 +34,4 @@ except Exception as e:
 PY
   done
 done
-unset CFR_B200_QUORUM CFR_B200_SEARCH_BLOCKS CFR_B200_DUST_SCREEN CFR_B200_L2_FETCH CFR_B200_DUST_OVERLAP
+unset CFR_B200_QUORUM CFR_B200_SEARCH_BLOCKS CFR_B200_DUST_SCREEN CFR_B200_L2_FETCH
