@@ -87,9 +87,6 @@ struct cfr_handle {
   int sm_count = 148;
   int search_blocks = 10;  // resident 128-thread blocks per SM targeted by k_search (CFR_B200_SEARCH_BLOCKS)
   int occ_load = 4;    // how k_search / k_locate fetch a sector: 4 = one 256-bit load, 0 = two 128-bit loads (CFR_B200_OCC_LOAD)
-  size_t l2_persist = 0;  // bytes of L2 set aside for the occ sectors (CFR_B200_L2_PERSIST_MB; 0 = off)
-  size_t occ_bytes = 0;
-  int max_window = 0;
   bool pos32 = false;  // 32-bit BWT positions in k_search / k_locate (collections below 2^32 rows; CFR_B200_POS64=1 disables)
   int dust_lanes = 16;  // lanes per warp that take mates in the post-screen SDUST launch (CFR_B200_DUST_LANES)
   bool dust_screen = true;  // register-only screen in front of the full SDUST (CFR_B200_DUST_SCREEN=0 disables)
@@ -271,7 +268,6 @@ int build_occ_lines(cfr_handle *h) {
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaStreamSynchronize(h->stream));
   h->ix.occ = (const OccLine *)p;
-  h->occ_bytes = n_lines * sizeof(OccLine);
   return CFR_OK;
 }
 
@@ -419,20 +415,6 @@ void fill_chunk(cfr_handle *h, cfr_device_batch *b, ChunkDev &B) {
   B.n_list = b->n_reads;
 }
 
-// access-policy window over the occ sectors for the kernels of stream s (no-op unless enabled)
-void apply_l2_window(cfr_handle *h, cudaStream_t s) {
-  if (!h->l2_persist || !h->ix.occ) return;
-  cudaStreamAttrValue v;
-  memset(&v, 0, sizeof(v));
-  v.accessPolicyWindow.base_ptr = const_cast<OccLine *>(h->ix.occ);
-  v.accessPolicyWindow.num_bytes = std::min(h->occ_bytes, (size_t)h->max_window);
-  v.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)h->l2_persist / (double)v.accessPolicyWindow.num_bytes);
-  v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-  v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-  cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &v);
-  cudaGetLastError();
-}
-
 // one select -> locate -> score pass over B.read_list
 // Bwt = scalar layout policy (select stage), BwtWide = policy of the search / locate kernels
 template <class Bwt, class BwtWide>
@@ -465,7 +447,6 @@ int run_first(cfr_handle *h, cfr_device_batch *b, cudaStream_t s) {
   ChunkDev B;
   fill_chunk(h, b, B);
   if (b->n_reads == 0) return CFR_OK;
-  apply_l2_window(h, s);
   CUDA_TRY(cudaMemsetAsync(b->scalars.p, 0, 64, s));
   {
     StageScope sc(h, s, CFR_STAGE_OTHER);
@@ -480,9 +461,9 @@ int run_first(cfr_handle *h, cfr_device_batch *b, cudaStream_t s) {
   {
     StageScope sc(h, s, CFR_STAGE_SEARCH);
     const int g = grid_for(h, B.n_reads * 2 * B.mates, 128, h->search_blocks);
-    if (h->search_blocks >= 12) k_search<BwtWide, 12, false><<<g, 128, 0, s>>>(h->ix, h->P, B);
-    else if (h->search_blocks >= 10) k_search<BwtWide, 10, false><<<g, 128, 0, s>>>(h->ix, h->P, B);
-    else k_search<BwtWide, 8, false><<<g, 128, 0, s>>>(h->ix, h->P, B);
+    if (h->search_blocks >= 12) k_search<BwtWide, 12><<<g, 128, 0, s>>>(h->ix, h->P, B);
+    else if (h->search_blocks >= 10) k_search<BwtWide, 10><<<g, 128, 0, s>>>(h->ix, h->P, B);
+    else k_search<BwtWide, 8><<<g, 128, 0, s>>>(h->ix, h->P, B);
     ++h->launches;
   }
   CUDA_TRY(cudaGetLastError());
@@ -571,10 +552,7 @@ int cfr_open(const char *idx_prefix, const cfr_params *p, int device, cfr_handle
     return fail(st, err);
   }
   cudaDeviceProp prop;
-  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) {
-    h->sm_count = prop.multiProcessorCount;
-    h->max_window = prop.accessPolicyMaxWindowSize;
-  }
+  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) h->sm_count = prop.multiProcessorCount;
   auto bail = [&](int code) {
     cfr_close(h);
     return code;
@@ -594,14 +572,6 @@ int cfr_open(const char *idx_prefix, const cfr_params *p, int device, cfr_handle
   if (const char *e = getenv("CFR_B200_OCC_LOAD")) h->occ_load = atoi(e) == 0 ? 0 : 4;
   h->pos32 = h->file.n < CFR_POS32_MAX_N;
   if (const char *e = getenv("CFR_B200_POS64")) if (atoi(e) != 0) h->pos32 = false;
-  // The index is read as independent random 32-byte sectors: ask L2 not to fetch the neighbouring
-  // sector(s) with every miss (the default fetch granularity is larger).  A hint; 32, 64 or 128.
-  {
-    size_t gran = 0;  // 0 = leave the device default
-    if (const char *e = getenv("CFR_B200_L2_FETCH")) gran = (size_t)std::max(0, atoi(e));
-    if (gran) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran);
-    cudaGetLastError();  // a device that ignores the hint is not an error
-  }
   if ((st = upload_index(h))) return bail(st);
   void *p2;
   if ((st = dev_alloc(h, &p2, (h->ix.node_cnt + 3) * 8))) return bail(st);
@@ -622,16 +592,6 @@ int cfr_open(const char *idx_prefix, const cfr_params *p, int device, cfr_handle
     h->layout = CFR_LAYOUT_RUNBLOCK;
   }
   if (h->layout == CFR_LAYOUT_OCCLINE && (st = build_occ_lines(h))) return bail(st);
-  if (const char *e = getenv("CFR_B200_L2_PERSIST_MB")) {
-    // experiment: keep (part of) the occ sectors in the persisting part of L2 so that the
-    // streaming buffers of a batch do not evict them
-    size_t want = (size_t)std::max(0, atoi(e)) << 20;
-    if (want && h->ix.occ) {
-      want = std::min(want, (size_t)prop.persistingL2CacheMaxSize);
-      if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) h->l2_persist = want;
-      cudaGetLastError();
-    }
-  }
   h->file.map1.close();  // everything needed from .1.cfr now lives in HBM
   *out = h;
   return CFR_OK;

@@ -71,13 +71,13 @@ __global__ void __launch_bounds__(CFR_DUST_THREADS) k_dust(const __grid_constant
 }
 
 // MINB = resident blocks per SM the register allocation must allow (occupancy knob)
-template <class Bwt, int MINB, bool SPLIT>
+template <class Bwt, int MINB>
 __global__ void __launch_bounds__(128, MINB) k_search(const __grid_constant__ DevIndex ix,
                                                       const __grid_constant__ DevParams P,
                                                       const __grid_constant__ ChunkDev B) {
   OpCount oc{};
   const u64 ntask = B.n_reads * (u64)(2 * B.mates);
-  search_tasks<Bwt, SPLIT>(ix, P, B, ntask, oc);  // tasks are claimed dynamically from B.task_counter
+  search_tasks<Bwt>(ix, P, B, ntask, oc);  // tasks are claimed dynamically from B.task_counter
   if (!Bwt::leader()) oc = OpCount{};
   flush_counts(oc, B.counters + CFR_STAGE_SEARCH);
 }

@@ -286,9 +286,9 @@ CFR_HD int adaptive_quorum(int quorum, u32 alive_mask, int lanes_per_task) {
   return (q < quorum ? (q < 1 ? 1 : q) : quorum) * lanes_per_task;
 }
 
-enum { CFR_ST_EXTEND = 0, CFR_ST_CLOSE = 1, CFR_ST_FETCH = 2, CFR_ST_DONE = 3, CFR_ST_LOOKUP = 4 };
+enum { CFR_ST_EXTEND = 0, CFR_ST_CLOSE = 1, CFR_ST_FETCH = 2, CFR_ST_DONE = 3 };
 
-template <class Bwt, bool SPLIT = true>
+template <class Bwt>
 CFR_HD void search_tasks(const DevIndex &ix, const DevParams &P, const ChunkDev &B, const u64 ntask, OpCount &oc) {
   const int W = ix.pre_width, mhl = P.min_hit_len;
   const int sshift = B.mates == 2 ? 2 : 1;  // strand tasks per read = 2 * mates = 1 << sshift
@@ -299,8 +299,6 @@ CFR_HD void search_tasks(const DevIndex &ix, const DevParams &P, const ChunkDev 
   pos_t sp = 0, ep = 0;
   int nh = 0, remaining = 0, l = 0;
   int st = CFR_ST_FETCH;
-  u64x2 pend;  // lookup-table entry in flight between the two halves of a transition
-  pend.x = pend.y = 0;
   for (;;) {
     const u32 ext = CFR_BALLOT(st == CFR_ST_EXTEND);
     const u32 trn = CFR_BALLOT(st == CFR_ST_CLOSE || st == CFR_ST_FETCH);
@@ -308,9 +306,7 @@ CFR_HD void search_tasks(const DevIndex &ix, const DevParams &P, const ChunkDev 
     // warp-uniform: does the deferred transition block run in this iteration?
     const bool transit = trn != 0 && (ext == 0 || popc32(trn) >= adaptive_quorum(P.quorum, ext | trn, (int)Bwt::LANES));
     if (transit) {
-      // ---- first half: CLOSE -> (FETCH ->) start of the next search, up to the ISSUE of the
-      // lookup-table load.  Its latency overlaps the extend step below; the entry is consumed
-      // in the second half, after that step.
+      // ---- transition block (warp-uniform entry): CLOSE -> (FETCH ->) start of the next search
       bool start = false;
       if (st == CFR_ST_CLOSE) {  // back in GetHitsFromRead
         if (Bwt::STEPS_COUNTED_AT_CLOSE && l >= W) {
@@ -376,22 +372,18 @@ CFR_HD void search_tasks(const DevIndex &ix, const DevParams &P, const ChunkDev 
               ep = 0;
               l = nvalid;
             } else {
-              pend = ld128(ix.lookup + key);
-              st = CFR_ST_LOOKUP;
-              if (!SPLIT) {
-                st = CFR_ST_CLOSE;
-                if (pend.y == 0) {
-                  sp = 1;
-                  ep = 0;
-                  l = W - 1;
-                } else {
-                  sp = (pos_t)pend.x;
-                  ep = (pos_t)(pend.x + pend.y - 1);
-                  l = W;
-                  if (l < remaining) {
-                    st = CFR_ST_EXTEND;
-                    s.seek(remaining - 1 - l);
-                  }
+              const u64x2 e = ld128(ix.lookup + key);
+              if (e.y == 0) {
+                sp = 1;
+                ep = 0;
+                l = W - 1;
+              } else {
+                sp = (pos_t)e.x;
+                ep = (pos_t)(e.x + e.y - 1);
+                l = W;
+                if (l < remaining) {
+                  st = CFR_ST_EXTEND;
+                  s.seek(remaining - 1 - l);
                 }
               }
             }
@@ -421,22 +413,6 @@ CFR_HD void search_tasks(const DevIndex &ix, const DevParams &P, const ChunkDev 
             st = CFR_ST_EXTEND;
             s.advance();
           }
-        }
-      }
-    }
-    if (SPLIT && transit && st == CFR_ST_LOOKUP) {  // ---- second half: the lookup-table entry has arrived
-      st = CFR_ST_CLOSE;
-      if (pend.y == 0) {
-        sp = 1;
-        ep = 0;
-        l = W - 1;
-      } else {
-        sp = (pos_t)pend.x;
-        ep = (pos_t)(pend.x + pend.y - 1);
-        l = W;
-        if (l < remaining) {
-          st = CFR_ST_EXTEND;
-          s.seek(remaining - 1 - l);
         }
       }
     }
