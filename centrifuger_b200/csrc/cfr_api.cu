@@ -2,6 +2,8 @@
 // batch pipeline orchestration, result hand-back.  Host C++ + CUDA runtime only.
 #include <cuda_runtime.h>
 
+#include <chrono>
+
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -111,6 +113,10 @@ struct cfr_handle {
     uint64_t *ids = nullptr;
   } jobs[2];
   int next_ticket = 0;
+  // CFR_B200_TRACE=1: device timeline of the streaming path (printed by cfr_wait_batch)
+  bool trace = false;
+  cudaEvent_t tr_base = nullptr, tr_ev[2][4] = {{nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr}};
+  double tr_host_submit[2] = {0, 0};
   // stage profiling (CUDA events on the launch stream)
   bool profile = false;
   struct EvPair {
@@ -565,6 +571,7 @@ int cfr_open(const char *idx_prefix, const cfr_params *p, int device, cfr_handle
   h->P.secondary_len = params.consider_secondary_hit_len;
   h->P.secondary_factor = params.consider_secondary_score_factor;
   h->P.quorum = 8;
+  if (const char *e = getenv("CFR_B200_TRACE")) h->trace = atoi(e) != 0;
   if (const char *e = getenv("CFR_B200_QUORUM")) h->P.quorum = std::max(1, atoi(e));
   if (const char *e = getenv("CFR_B200_SEARCH_BLOCKS")) h->search_blocks = std::max(1, atoi(e));
   if (const char *e = getenv("CFR_B200_DUST_SCREEN")) h->dust_screen = atoi(e) != 0;
@@ -850,11 +857,26 @@ int cfr_submit_batch(cfr_handle *h, const cfr_read_batch *in, cfr_result *result
   CUDA_TRY(cudaEventRecord(h->ev_start, sc));  // ordered after the caller's stream
   CUDA_TRY(cudaStreamWaitEvent(h->s_in, h->ev_start, 0));
   CUDA_TRY(cudaStreamWaitEvent(h->s_comp[slot], h->ev_start, 0));
+  const auto host_t0 = std::chrono::steady_clock::now();
+  if (h->trace) {
+    if (!h->tr_base) {
+      cudaEventCreate(&h->tr_base);
+      for (int a = 0; a < 2; ++a)
+        for (int q = 0; q < 4; ++q) cudaEventCreate(&h->tr_ev[a][q]);
+      cudaEventRecord(h->tr_base, h->s_in);
+    }
+    cudaEventRecord(h->tr_ev[slot][0], h->s_in);
+  }
   if ((st = upload_chunk(h, in, 0, in->n_reads, b, h->s_in))) return st;
   CUDA_TRY(cudaEventRecord(h->ev_h2d[slot], h->s_in));
+  if (h->trace) cudaEventRecord(h->tr_ev[slot][1], h->s_in);
   CUDA_TRY(cudaStreamWaitEvent(h->s_comp[slot], h->ev_h2d[slot], 0));
   if ((st = cfr_classify_resident(h, b, h->s_comp[slot]))) return st;
   CUDA_TRY(cudaEventRecord(h->ev_comp[slot], h->s_comp[slot]));
+  if (h->trace) {
+    cudaEventRecord(h->tr_ev[slot][2], h->s_comp[slot]);
+    h->tr_host_submit[slot] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count();
+  }
   CUDA_TRY(cudaStreamWaitEvent(h->s_out, h->ev_comp[slot], 0));
   const u64 k = (u64)h->P.max_result;
   if (in->n_reads) {
@@ -863,6 +885,7 @@ int cfr_submit_batch(cfr_handle *h, const cfr_read_batch *in, cfr_result *result
   }
   CUDA_TRY(cudaMemcpyAsync(&h->pinned_scalars[slot], b->scalars.p, 16, cudaMemcpyDeviceToHost, h->s_out));
   CUDA_TRY(cudaEventRecord(h->ev_d2h[slot], h->s_out));
+  if (h->trace) cudaEventRecord(h->tr_ev[slot][3], h->s_out);
   h->jobs[slot].ticket = h->next_ticket;
   h->jobs[slot].results = results;
   h->jobs[slot].ids = ids;
@@ -878,7 +901,14 @@ int cfr_wait_batch(cfr_handle *h, int ticket) {
     if (ticket < h->next_ticket) return CFR_OK;  // already completed (by a later submit)
     return fail(CFR_ERR_ARG, "unknown ticket");
   }
-  return job_finish(h, slot);
+  const int rc = job_finish(h, slot);
+  if (h->trace && rc == CFR_OK) {
+    float t[4] = {0, 0, 0, 0};
+    for (int q = 0; q < 4; ++q) cudaEventElapsedTime(&t[q], h->tr_base, h->tr_ev[slot][q]);
+    fprintf(stderr, "[cfr trace] ticket %d: h2d %.2f..%.2f ms, kernels end %.2f, d2h end %.2f (host submit %.2f ms)\n", ticket,
+            t[0], t[1], t[2], t[3], h->tr_host_submit[slot]);
+  }
+  return rc;
 }
 
 const char *cfr_seq_name(const cfr_handle *h, uint64_t seq_id) {
