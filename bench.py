@@ -292,8 +292,10 @@ def main():
     p_seq1, p_off1, p_seq2, p_off2 = pin(seq1), pin(off1), pin(seq2), pin(off2)
     res_host = torch.empty(n * 32, dtype=torch.uint8).pin_memory()
     ids_host = torch.empty(max(1, n * w["k"]), dtype=torch.int64).pin_memory()
-    res_host2 = torch.empty(n * 32, dtype=torch.uint8).pin_memory()  # second set for the streaming e2e loop
+    res_host2 = torch.empty(n * 32, dtype=torch.uint8).pin_memory()  # more sets for the streaming e2e loop
     ids_host2 = torch.empty(max(1, n * w["k"]), dtype=torch.int64).pin_memory()
+    res_host3 = torch.empty(n * 32, dtype=torch.uint8).pin_memory()
+    ids_host3 = torch.empty(max(1, n * w["k"]), dtype=torch.int64).pin_memory()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
 
     from centrifuger_b200 import distributed as cdist
@@ -349,24 +351,21 @@ def main():
 
     # ---- end-to-end timing (pinned host buffers in, host results out) ----
     # The streaming form of the C ABI (cfr_submit_batch / cfr_wait_batch, what the CLI uses): every step
-    # uploads its reads from pinned host memory, runs all kernels and downloads its results; two steps
-    # are in flight so the copies of one overlap the kernels of the other.  All K steps' copies and
+    # uploads its reads from pinned host memory, runs all kernels and downloads its results; three steps
+    # are in flight so the copies of one overlap the kernels of the others.  All K steps' copies and
     # kernels are inside the timed region.
-    outs = [(res_host, ids_host), (res_host2, ids_host2)]
+    outs = [(res_host, ids_host), (res_host2, ids_host2), (res_host3, ids_host3)]
 
     def run_e2e(k_steps):
-        prev = None
-        keep = []
+        inflight = []
         for i in range(k_steps):
-            tk = clf.submit(p_seq1, p_off1, p_seq2, p_off2, stream=sptr, out=outs[i & 1])
-            keep.append(tk)
-            if prev is not None:
-                clf.wait(prev[0])
+            inflight.append(clf.submit(p_seq1, p_off1, p_seq2, p_off2, stream=sptr, out=outs[i % 3]))
+            if len(inflight) == 3:
+                clf.wait(inflight.pop(0)[0])
                 if world > 1:
                     cdist.allreduce_counts(tax_tensor)
-            prev = tk
-        if prev is not None:
-            clf.wait(prev[0])
+        while inflight:
+            clf.wait(inflight.pop(0)[0])
             if world > 1:
                 cdist.allreduce_counts(tax_tensor)
 
@@ -451,7 +450,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": unit,
                     "h2d_bytes_per_step": int(bases + (n + 1) * 8 * (2 if seq2 is not None else 1)),
                     "d2h_bytes_per_step": int(n * 32 + n * w["k"] * 8),
-                    "api": "cfr_submit_batch / cfr_wait_batch, two steps in flight, pinned host buffers",
+                    "api": "cfr_submit_batch / cfr_wait_batch, three steps in flight, pinned host buffers",
                     "single_call_value": n * world / e2e_single_s,
                     "host_link_h2d_gbs": h2d_gbs},
             "gpu_launches": int(launches_resident + launches_e2e),

@@ -97,26 +97,29 @@ struct cfr_handle {
   u64 launches = 0;
   u64 host_bases = 0;
   // cfr_classify_batch pipeline: two chunk slots, H2D / compute / D2H on three streams
-  cfr_device_batch slots[2];
-  cudaStream_t s_in = nullptr, s_out = nullptr, s_comp[2] = {nullptr, nullptr};
-  cudaEvent_t ev_start = nullptr, ev_h2d[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr},
-              ev_d2h[2] = {nullptr, nullptr};
+  // NSLOT batches can be in flight in the streaming form (upload of batch i+2 next to the kernels of
+  // i+1 and the download of i); cfr_classify_batch's chunk pipeline uses the first two
+  enum { NSLOT = 3 };
+  cfr_device_batch slots[NSLOT];
+  cudaStream_t s_in = nullptr, s_out = nullptr, s_comp[NSLOT] = {nullptr, nullptr, nullptr};
+  cudaEvent_t ev_start = nullptr, ev_h2d[NSLOT] = {nullptr, nullptr, nullptr}, ev_comp[NSLOT] = {nullptr, nullptr, nullptr},
+              ev_d2h[NSLOT] = {nullptr, nullptr, nullptr};
   struct PinnedScalars {
     u64 used;
     u32 n_def;
     u32 pad;
-  } *pinned_scalars = nullptr;  // [2], cudaHostAlloc
+  } *pinned_scalars = nullptr;  // [NSLOT], cudaHostAlloc
   // cfr_submit_batch / cfr_wait_batch: one job per slot
   struct Job {
     int ticket = -1;  // -1 = slot idle
     cfr_result *results = nullptr;
     uint64_t *ids = nullptr;
-  } jobs[2];
+  } jobs[NSLOT];
   int next_ticket = 0;
   // CFR_B200_TRACE=1: device timeline of the streaming path (printed by cfr_wait_batch)
   bool trace = false;
-  cudaEvent_t tr_base = nullptr, tr_ev[2][4] = {{nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr}};
-  double tr_host_submit[2] = {0, 0};
+  cudaEvent_t tr_base = nullptr, tr_ev[NSLOT][4] = {};
+  double tr_host_submit[NSLOT] = {};
   // stage profiling (CUDA events on the launch stream)
   bool profile = false;
   struct EvPair {
@@ -607,14 +610,13 @@ int cfr_open(const char *idx_prefix, const cfr_params *p, int device, cfr_handle
 void cfr_close(cfr_handle *h) {
   if (!h) return;
   cudaSetDevice(h->device);
-  h->slots[0].release();
-  h->slots[1].release();
+  for (int i = 0; i < cfr_handle::NSLOT; ++i) h->slots[i].release();
   if (h->s_in) cudaStreamDestroy(h->s_in);
   if (h->s_out) cudaStreamDestroy(h->s_out);
-  for (int i = 0; i < 2; ++i)
+  for (int i = 0; i < cfr_handle::NSLOT; ++i)
     if (h->s_comp[i]) cudaStreamDestroy(h->s_comp[i]);
   if (h->ev_start) cudaEventDestroy(h->ev_start);
-  for (int i = 0; i < 2; ++i) {
+  for (int i = 0; i < cfr_handle::NSLOT; ++i) {
     if (h->ev_h2d[i]) cudaEventDestroy(h->ev_h2d[i]);
     if (h->ev_comp[i]) cudaEventDestroy(h->ev_comp[i]);
     if (h->ev_d2h[i]) cudaEventDestroy(h->ev_d2h[i]);
@@ -732,14 +734,14 @@ static int pipeline_init(cfr_handle *h) {
   if (h->s_in) return CFR_OK;
   CUDA_TRY(cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
   CUDA_TRY(cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
-  for (int i = 0; i < 2; ++i) CUDA_TRY(cudaStreamCreateWithFlags(&h->s_comp[i], cudaStreamNonBlocking));
+  for (int i = 0; i < cfr_handle::NSLOT; ++i) CUDA_TRY(cudaStreamCreateWithFlags(&h->s_comp[i], cudaStreamNonBlocking));
   CUDA_TRY(cudaEventCreateWithFlags(&h->ev_start, cudaEventDisableTiming));
-  for (int i = 0; i < 2; ++i) {
+  for (int i = 0; i < cfr_handle::NSLOT; ++i) {
     CUDA_TRY(cudaEventCreateWithFlags(&h->ev_h2d[i], cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&h->ev_comp[i], cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&h->ev_d2h[i], cudaEventDisableTiming));
   }
-  CUDA_TRY(cudaHostAlloc((void **)&h->pinned_scalars, 2 * sizeof(*h->pinned_scalars), cudaHostAllocDefault));
+  CUDA_TRY(cudaHostAlloc((void **)&h->pinned_scalars, cfr_handle::NSLOT * sizeof(*h->pinned_scalars), cudaHostAllocDefault));
   return CFR_OK;
 }
 
@@ -775,7 +777,8 @@ int cfr_classify_batch(cfr_handle *h, const cfr_read_batch *in, cfr_result *resu
   cudaStream_t sc = pick_stream(h, stream);
   int st = pipeline_init(h);
   if (st) return st;
-  if ((st = job_finish(h, 0)) || (st = job_finish(h, 1))) return st;  // complete streaming jobs first
+  for (int i = 0; i < cfr_handle::NSLOT; ++i)
+    if ((st = job_finish(h, i))) return st;  // complete streaming jobs first
   const u64 cap = h->params.max_batch_reads > 0 ? (u64)h->params.max_batch_reads : (1ull << 20);
   // Chunk plan.  Every chunk pays a fixed cost (the critical path of its slowest read in each
   // kernel), so few chunks are better for the GPU; but the first upload and the last download are
@@ -850,8 +853,8 @@ int cfr_submit_batch(cfr_handle *h, const cfr_read_batch *in, cfr_result *result
   CUDA_TRY(cudaSetDevice(h->device));
   int st = pipeline_init(h);
   if (st) return st;
-  const int slot = h->next_ticket & 1;
-  if ((st = job_finish(h, slot))) return st;  // at most two batches in flight
+  const int slot = h->next_ticket % cfr_handle::NSLOT;
+  if ((st = job_finish(h, slot))) return st;  // at most NSLOT batches in flight
   cfr_device_batch *b = &h->slots[slot];
   cudaStream_t sc = pick_stream(h, stream);
   CUDA_TRY(cudaEventRecord(h->ev_start, sc));  // ordered after the caller's stream
@@ -861,7 +864,7 @@ int cfr_submit_batch(cfr_handle *h, const cfr_read_batch *in, cfr_result *result
   if (h->trace) {
     if (!h->tr_base) {
       cudaEventCreate(&h->tr_base);
-      for (int a = 0; a < 2; ++a)
+      for (int a = 0; a < cfr_handle::NSLOT; ++a)
         for (int q = 0; q < 4; ++q) cudaEventCreate(&h->tr_ev[a][q]);
       cudaEventRecord(h->tr_base, h->s_in);
     }
@@ -896,7 +899,7 @@ int cfr_submit_batch(cfr_handle *h, const cfr_read_batch *in, cfr_result *result
 int cfr_wait_batch(cfr_handle *h, int ticket) {
   if (!h || ticket < 0) return fail(CFR_ERR_ARG, "bad ticket");
   CUDA_TRY(cudaSetDevice(h->device));
-  const int slot = ticket & 1;
+  const int slot = ticket % cfr_handle::NSLOT;
   if (h->jobs[slot].ticket != ticket) {
     if (ticket < h->next_ticket) return CFR_OK;  // already completed (by a later submit)
     return fail(CFR_ERR_ARG, "unknown ticket");

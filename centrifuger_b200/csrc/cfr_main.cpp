@@ -22,6 +22,7 @@
 #include <mutex>
 #include <string>
 #include <thread>
+#include <deque>
 #include <vector>
 
 #include "../../include/centrifuger_b200.h"
@@ -374,7 +375,7 @@ int main(int argc, char *argv[]) {
   // the GPU classifies batch i and the output thread formats batch i-1 (ResultWriter::Output,
   // ResultWriter.hpp:199-236; rows in input order as in CentrifugerClass.cpp:690).
   const int k = params.max_result;
-  enum { NBATCH = 4 };  // ingest (1) + in flight on the GPU (2) + output (1)
+  enum { NBATCH = 5 };  // ingest (1) + in flight on the GPU (3) + output (1)
   Batch batches[NBATCH];
   Slot<Batch *> free_slots[NBATCH];
   Slot<Batch *> to_gpu, to_out;
@@ -476,8 +477,19 @@ int main(int argc, char *argv[]) {
 
   for (int i = 0; i < NBATCH; ++i) free_slots[i].put(&batches[i]);
   int rc = 0;
-  Batch *pending = NULL;  // submitted, not yet waited for
-  int pending_ticket = -1;
+  // submitted, not yet waited for: up to two stay behind the batch just submitted (three in flight)
+  std::deque<std::pair<Batch *, int>> pending;
+  auto retire = [&]() {
+    Batch *pb = pending.front().first;
+    const int tk = pending.front().second;
+    pending.pop_front();
+    if (tk >= 0 && cfr_wait_batch(h, tk) != CFR_OK) {
+      PrintLog("ERROR: %s", cfr_last_error());
+      rc = EXIT_FAILURE;
+      pb->n = 0;
+    }
+    to_out.put(pb);
+  };
   for (;;) {
     Batch *bt = to_gpu.take();
     int ticket = -1;
@@ -490,7 +502,7 @@ int main(int argc, char *argv[]) {
       b.off1 = bt->off1.data();
       b.seq2 = hasMate ? bt->seq2.data() : NULL;
       b.off2 = hasMate ? bt->off2.data() : NULL;
-      // streaming form: this batch's upload overlaps the previous batch's kernels
+      // streaming form: this batch's upload overlaps the previous batches' kernels
       st = cfr_submit_batch(h, &b, bt->results.data(), bt->assign.data(), NULL, &ticket);
       if (st != CFR_OK) {
         PrintLog("ERROR: %s", cfr_last_error());
@@ -498,23 +510,10 @@ int main(int argc, char *argv[]) {
         bt->n = 0;
       }
     }
-    if (pending) {
-      if (pending_ticket >= 0 && cfr_wait_batch(h, pending_ticket) != CFR_OK) {
-        PrintLog("ERROR: %s", cfr_last_error());
-        rc = EXIT_FAILURE;
-        pending->n = 0;
-      }
-      to_out.put(pending);
-    }
-    pending = bt;
-    pending_ticket = ticket;
+    pending.push_back(std::make_pair(bt, ticket));
+    if (pending.size() > 2) retire();
     if (bt->last) {
-      if (pending_ticket >= 0 && cfr_wait_batch(h, pending_ticket) != CFR_OK) {
-        PrintLog("ERROR: %s", cfr_last_error());
-        rc = EXIT_FAILURE;
-        pending->n = 0;
-      }
-      to_out.put(pending);
+      while (!pending.empty()) retire();
       break;
     }
   }

@@ -115,8 +115,8 @@ int cfr_classify_batch(cfr_handle *h, const cfr_read_batch *in, cfr_result *resu
 
 /* Streaming form of cfr_classify_batch for callers that feed batch after batch (the CLI, bench.py's
  * end-to-end loop): submit returns as soon as the copies and kernels are enqueued, so the upload of
- * batch i+1 overlaps the kernels of batch i and the download of batch i-1.  At most two batches are
- * in flight; submitting a third first completes the oldest one.  `in`, `results` and `ids` must stay
+ * batch i+1 overlaps the kernels of batch i and the download of batch i-1.  At most three batches are
+ * in flight; submitting a fourth first completes the oldest one.  `in`, `results` and `ids` must stay
  * valid (and should be pinned) until cfr_wait_batch(ticket) returns.  n_reads must not exceed
  * cfr_params.max_batch_reads (default 2^20). */
 int cfr_submit_batch(cfr_handle *h, const cfr_read_batch *in, cfr_result *results, uint64_t *ids, void *stream,
