@@ -16,6 +16,21 @@ pytestmark = pytest.mark.gpu
 
 LAYOUTS = [cb.LAYOUT_RUNBLOCK, cb.LAYOUT_OCCLINE]
 
+# kernel variants the library picks by index size or environment: the occ sectors walked with 32-bit
+# positions (default below 2^32 rows) or 64-bit positions, one 256-bit sector load or two 128-bit
+# loads, SDUST with or without the register-only screen
+VARIANTS = {"default": {}, "pos64": {"CFR_B200_POS64": "1"}, "pos64_ld128": {"CFR_B200_POS64": "1", "CFR_B200_OCC_LOAD": "0"},
+            "ld128": {"CFR_B200_OCC_LOAD": "0"}, "noscreen": {"CFR_B200_DUST_SCREEN": "0"}}
+
+
+@pytest.fixture(params=sorted(VARIANTS))
+def variant_env(request, monkeypatch):
+    for k in ("CFR_B200_POS64", "CFR_B200_OCC_LOAD", "CFR_B200_DUST_SCREEN"):
+        monkeypatch.delenv(k, raising=False)
+    for k, v in VARIANTS[request.param].items():
+        monkeypatch.setenv(k, v)  # read by cfr_open
+    return request.param
+
 
 def _args_to_kw(args):
     kw = dict(dust=True)
@@ -250,6 +265,30 @@ def test_cli_binary_reproduces_reference_tsv(tiny_dir, manifest):
     assert r.returncode == 0 and b"-x FILE: index prefix" in r.stderr
     r = subprocess.run([exe, "-v"], stdout=subprocess.PIPE)
     assert r.stdout.decode().strip() == "Centrifuger v1.1.3-r347"
+
+
+def test_kernel_variants_vs_oracle(small_dir, variant_env):
+    """every kernel variant gives the oracle's answers and operation counts (occ-sector layout)"""
+    idx = os.path.join(small_dir, "idx")
+    _, r1 = read_fastx(os.path.join(small_dir, "pe_150_1.fq"))
+    _, r2 = read_fastx(os.path.join(small_dir, "pe_150_2.fq"))
+    _, e1 = read_fastx(os.path.join(small_dir, "edge_1.fq"))
+    _, e2 = read_fastx(os.path.join(small_dir, "edge_2.fq"))
+    r1, r2 = r1[:4000] + e1, r2[:4000] + e2
+    for kw in (dict(), dict(k=5)):
+        o = Oracle(idx, **kw)
+        o.reset_counters()
+        exp = _oracle_tuples(o, r1, r2)
+        oc = o.counters()
+        o.close()
+        g = cb.Classifier(idx, layout=cb.LAYOUT_OCCLINE, **kw)
+        g.reset_counters()
+        res, ids = g.classify(r1, r2)
+        assert _tuples(res, ids, g.k) == exp, (variant_env, kw)
+        c = g.counters()
+        for key in ("n_rank", "n_access", "n_search", "n_locate", "n_lf", "n_extend"):
+            assert c[key] == oc[key], (variant_env, kw, key)
+        g.close()
 
 
 def test_streaming_submit_wait(small_dir):
