@@ -280,6 +280,26 @@ int build_occ_lines(cfr_handle *h) {
   return CFR_OK;
 }
 
+// Wide lookup table (DevIndex::wide): for an index that lives in HBM every rank is a DRAM line, and the
+// first steps of a search -- wide ranges, two sectors each -- are the same for every read that ends
+// in the same WW-mer.  One probe of a 4^WW-entry table replaces the W-mer probe and WW - W extends.
+int build_wide_lookup(cfr_handle *h, int WW) {
+  if (WW <= h->ix.pre_width || WW > 15 || h->ix.pre_width <= 0) return CFR_OK;
+  const u64 n_keys = 1ull << (2 * WW);
+  void *p;
+  int st = dev_alloc(h, &p, n_keys * sizeof(u64x2));
+  if (st) return st;
+  const int grid = grid_for(h, n_keys, 128, 16);
+  if (h->layout == CFR_LAYOUT_OCCLINE) k_build_wide<BwtOccLine><<<grid, 128, 0, h->stream>>>(h->ix, (u64x2 *)p, WW);
+  else k_build_wide<BwtRunBlock><<<grid, 128, 0, h->stream>>>(h->ix, (u64x2 *)p, WW);
+  ++h->launches;
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  h->ix.wide = (const u64x2 *)p;
+  h->ix.wide_width = WW;
+  return CFR_OK;
+}
+
 cudaStream_t pick_stream(cfr_handle *h, void *stream) { return stream ? (cudaStream_t)stream : h->stream; }
 
 cudaEvent_t ev_get(cfr_handle *h) {
@@ -602,6 +622,21 @@ int cfr_open(const char *idx_prefix, const cfr_params *p, int device, cfr_handle
     h->layout = CFR_LAYOUT_RUNBLOCK;
   }
   if (h->layout == CFR_LAYOUT_OCCLINE && (st = build_occ_lines(h))) return bail(st);
+  {
+    // wide lookup table: on by default when the BWT does not fit L2 (there the W-mer table and the
+    // first extends are L2 hits and a 1 GB table would only add DRAM misses); CFR_B200_WIDE_LOOKUP=WW
+    // forces a width (0 = off)
+    int ww = 0;
+    const u64 bwt_bytes = h->layout == CFR_LAYOUT_OCCLINE ? (h->ix.n / 64 + 1) * sizeof(OccLine) : h->ix.n / 2;
+    if (bwt_bytes > (96ull << 20) && h->ix.n < (1ull << 56)) {
+      ww = 13;
+      size_t free_b = 0, total_b = 0;
+      cudaMemGetInfo(&free_b, &total_b);
+      while (ww > h->ix.pre_width && ((16ull << (2 * ww)) + (8ull << 30)) > (u64)free_b) --ww;
+    }
+    if (const char *e = getenv("CFR_B200_WIDE_LOOKUP")) ww = atoi(e);
+    if ((st = build_wide_lookup(h, ww))) return bail(st);
+  }
   h->file.map1.close();  // everything needed from .1.cfr now lives in HBM
   *out = h;
   return CFR_OK;

@@ -648,6 +648,38 @@ CFR_HD int backward_search(const DevIndex &ix, StrandSeq &s, int m, u64 &sp, u64
   return l;
 }
 
+// One entry of the wide lookup table: FMIndex::BackwardSearch over exactly the WW bases packed in
+// `key` (base j of the field = the base WW-1-j steps from the end, as in init_key): the W-mer table
+// probe on the last W bases, then BackwardExtend base by base until it fails.  (sp, ep) is the last
+// valid range, l the number of bases matched -- exactly where the search stands, or ended, after
+// these WW bases whatever precedes them.
+template <class Bwt>
+CFR_HD u64x2 wide_lookup_entry(const DevIndex &ix, u64 key, int WW) {
+  const int W = ix.pre_width;
+  u64x2 r;
+  const u64x2 e = ld128(ix.lookup + (key >> (2 * (WW - W))));
+  if (e.y == 0) {
+    r.x = 1;
+    r.y = 0 | ((u64)(W - 1) << 56);
+    return r;
+  }
+  u64 sp = e.x, ep = e.x + e.y - 1;
+  int l = W;
+  OpCount oc{};
+  while (l < WW) {
+    const int c = (int)((key >> (2 * (WW - 1 - l))) & 3ull);
+    u64 nsp, nep;
+    Bwt::extend(ix, c, sp, ep, nsp, nep, oc);
+    if (nsp > nep || nep > ix.n) break;
+    sp = nsp;
+    ep = nep;
+    ++l;
+  }
+  r.x = sp;
+  r.y = ep | ((u64)l << 56);
+  return r;
+}
+
 // FixedSizeElemArray::Read (FixedSizeElemArray.hpp:102, Utils.hpp:197-219)
 CFR_HD u64 sa_read(const DevIndex &ix, u64 i) {
   const u64 s = i * (u64)ix.sa_bits, e = s + (u64)ix.sa_bits - 1;

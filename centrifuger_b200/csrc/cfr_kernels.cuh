@@ -191,6 +191,15 @@ __global__ void __launch_bounds__(128) k_transcode(const __grid_constant__ DevIn
   }
 }
 
+// Wide lookup table at load time: one entry per WW-mer (see wide_lookup_entry)
+template <class Bwt>
+__global__ void __launch_bounds__(128) k_build_wide(const __grid_constant__ DevIndex ix, u64x2 *out, int WW) {
+  const u64 n_keys = 1ull << (2 * WW);
+  const u64 stride = (u64)gridDim.x * blockDim.x;
+  for (u64 key = (u64)blockIdx.x * blockDim.x + threadIdx.x; key < n_keys; key += stride)
+    out[key] = wide_lookup_entry<Bwt>(ix, key, WW);
+}
+
 // ---- diagnostics for the parity tests ----
 template <class Bwt>
 __global__ void k_debug_rank(const __grid_constant__ DevIndex ix, const unsigned char *codes, const u64 *pos,

@@ -290,7 +290,7 @@ enum { CFR_ST_EXTEND = 0, CFR_ST_CLOSE = 1, CFR_ST_FETCH = 2, CFR_ST_DONE = 3 };
 
 template <class Bwt>
 CFR_HD void search_tasks(const DevIndex &ix, const DevParams &P, const ChunkDev &B, const u64 ntask, OpCount &oc) {
-  const int W = ix.pre_width, mhl = P.min_hit_len;
+  const int W = ix.pre_width, WW = ix.wide_width, mhl = P.min_hit_len;
   const int sshift = B.mates == 2 ? 2 : 1;  // strand tasks per read = 2 * mates = 1 << sshift
   typedef typename Bwt::pos_t pos_t;
   const pos_t n_rows = (pos_t)ix.n;
@@ -298,6 +298,7 @@ CFR_HD void search_tasks(const DevIndex &ix, const DevParams &P, const ChunkDev 
   u64 cur = 0;
   pos_t sp = 0, ep = 0;
   int nh = 0, remaining = 0, l = 0;
+  int l0 = 0;  // bases of the current search that came out of a lookup table (no BackwardExtend ran for them)
   int st = CFR_ST_FETCH;
   for (;;) {
     const u32 ext = CFR_BALLOT(st == CFR_ST_EXTEND);
@@ -309,10 +310,10 @@ CFR_HD void search_tasks(const DevIndex &ix, const DevParams &P, const ChunkDev 
       // ---- transition block (warp-uniform entry): CLOSE -> (FETCH ->) start of the next search
       bool start = false;
       if (st == CFR_ST_CLOSE) {  // back in GetHitsFromRead
-        if (Bwt::STEPS_COUNTED_AT_CLOSE && l >= W) {
-          // BackwardExtend calls of this search: l - W that succeeded, plus the one that failed when
+        if (Bwt::STEPS_COUNTED_AT_CLOSE && l >= l0 && l0 >= W) {
+          // BackwardExtend calls of this search: l - l0 that succeeded, plus the one that failed when
           // the search stopped on an ACGT base before the start of the strand (the cursor is still on it)
-          oc.xext += (u32)(l - W) + ((l < remaining && s.peek() <= 3) ? 1u : 0u);
+          oc.xext += (u32)(l - l0) + ((l < remaining && s.peek() <= 3) ? 1u : 0u);
         }
         if (l >= mhl && sp <= ep && nh < B.cap_h) {
           if (Bwt::leader()) {
@@ -360,7 +361,27 @@ CFR_HD void search_tasks(const DevIndex &ix, const DevParams &P, const ChunkDev 
       CFR_SYNCWARP();
       if (start) {  // FMIndex::BackwardSearch up to the initial range
         st = CFR_ST_CLOSE;
-        if (remaining < W) {
+        l0 = W;
+        bool wide_done = false;
+        if (WW > 0 && remaining >= WW) {  // the wide table answers for the last WW bases unless one is not ACGT
+          u64 key;
+          int nvalid;
+          if (s.init_key(remaining, WW, key, nvalid)) {
+            ++oc.search;
+            const u64x2 e = ld128(ix.wide + key);
+            l = (int)(e.y >> 56);
+            sp = (pos_t)e.x;
+            ep = (pos_t)(e.y & 0xffffffffffffffull);
+            wide_done = true;
+            l0 = WW;  // l < WW: the search ended inside the table (xext sees l < l0)
+            if (l == WW && l < remaining) {
+              st = CFR_ST_EXTEND;
+              s.seek(remaining - 1 - l);
+            }
+          }
+        }
+        if (wide_done) {
+        } else if (remaining < W) {
           l = 0;
         } else {
           ++oc.search;

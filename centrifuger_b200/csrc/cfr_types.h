@@ -71,6 +71,11 @@ struct DevIndex {
   // 10-mer (precomputeWidth-mer) lookup table
   int pre_width;
   const u64x2 *lookup;  // {start, len}
+  // optional wide table, built at load from `lookup` + BackwardExtend for indexes that live in HBM:
+  // entry of a WW-mer = where FMIndex::BackwardSearch stands after its last WW bases
+  // {sp, ep | l << 56}: l < WW means the search ended inside them (l = W - 1: empty W-mer)
+  int wide_width;  // 0 = none
+  const u64x2 *wide;
   // taxonomy (Taxonomy.hpp)
   u64 node_cnt, seq_cnt, root;
   const u32 *parent;

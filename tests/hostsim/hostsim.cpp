@@ -24,6 +24,7 @@ struct HostIndex {
   std::vector<unsigned char> rank;
   std::vector<u64> sel_filter;
   std::vector<OccLine> occ;
+  std::vector<u64x2> wide;
   bool pos32 = false;
   DevIndex ix;
   DevParams P;
@@ -136,6 +137,16 @@ void *hostsim_open(const char *prefix, const cfr_params *p) {
       h->occ[L] = occ_pack(lo, hi, cnt[0], cnt[1], cnt[2]);
     }
     ix.occ = h->occ.data();
+  }
+  if (const char *e = getenv("HOSTSIM_WIDE_LOOKUP")) {  // the library's wide lookup table, any width
+    const int ww = atoi(e);
+    if (ww > ix.pre_width && ix.pre_width > 0) {
+      h->wide.resize(1ull << (2 * ww));
+      for (u64 key = 0; key < h->wide.size(); ++key)
+        h->wide[key] = h->layout == 2 ? wide_lookup_entry<BwtOccLine>(ix, key, ww) : wide_lookup_entry<BwtRunBlock>(ix, key, ww);
+      ix.wide = h->wide.data();
+      ix.wide_width = ww;
+    }
   }
   h->P.max_result = p->max_result;
   h->P.min_hit_len = p->min_hit_len > 0 ? p->min_hit_len : infer_min_hit_len(f.n);

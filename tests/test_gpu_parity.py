@@ -20,12 +20,13 @@ LAYOUTS = [cb.LAYOUT_RUNBLOCK, cb.LAYOUT_OCCLINE]
 # positions (default below 2^32 rows) or 64-bit positions, one 256-bit sector load or two 128-bit
 # loads, SDUST with or without the register-only screen
 VARIANTS = {"default": {}, "pos64": {"CFR_B200_POS64": "1"}, "pos64_ld128": {"CFR_B200_POS64": "1", "CFR_B200_OCC_LOAD": "0"},
-            "ld128": {"CFR_B200_OCC_LOAD": "0"}, "noscreen": {"CFR_B200_DUST_SCREEN": "0"}}
+            "ld128": {"CFR_B200_OCC_LOAD": "0"}, "noscreen": {"CFR_B200_DUST_SCREEN": "0"},
+            "wide12": {"CFR_B200_WIDE_LOOKUP": "12"}, "wide11_pos64": {"CFR_B200_WIDE_LOOKUP": "11", "CFR_B200_POS64": "1"}}
 
 
 @pytest.fixture(params=sorted(VARIANTS))
 def variant_env(request, monkeypatch):
-    for k in ("CFR_B200_POS64", "CFR_B200_OCC_LOAD", "CFR_B200_DUST_SCREEN"):
+    for k in ("CFR_B200_POS64", "CFR_B200_OCC_LOAD", "CFR_B200_DUST_SCREEN", "CFR_B200_WIDE_LOOKUP"):
         monkeypatch.delenv(k, raising=False)
     for k, v in VARIANTS[request.param].items():
         monkeypatch.setenv(k, v)  # read by cfr_open
@@ -287,7 +288,10 @@ def test_kernel_variants_vs_oracle(small_dir, variant_env):
         assert _tuples(res, ids, g.k) == exp, (variant_env, kw)
         c = g.counters()
         for key in ("n_rank", "n_access", "n_search", "n_locate", "n_lf", "n_extend"):
-            assert c[key] == oc[key], (variant_env, kw, key)
+            if not variant_env.startswith("wide"):
+                assert c[key] == oc[key], (variant_env, kw, key)
+            elif key in ("n_rank", "n_extend"):  # the wide table replaces the first extends of a search
+                assert c[key] < oc[key], (variant_env, kw, key)
         g.close()
 
 
