@@ -240,6 +240,7 @@ int upload_index(cfr_handle *h) {
     if ((st = dev_upload(h, filt.data(), filt.size() * 8, 0, &p))) return st;
     ix.sel_filter = (const u64 *)p;
   }
+  ix.dense_shift = -1;
   ix.pre_width = (int)f.precompute_width;
   if ((st = dev_upload(h, f.lookup, f.precompute_size * 16, 16, &p))) return st;
   ix.lookup = (const u64x2 *)p;
@@ -297,6 +298,27 @@ int build_wide_lookup(cfr_handle *h, int WW) {
   CUDA_TRY(cudaStreamSynchronize(h->stream));
   h->ix.wide = (const u64x2 *)p;
   h->ix.wide_width = WW;
+  return CFR_OK;
+}
+
+// Dense locate table (DevIndex::dense): the stored samples are 2^offrate rows apart, so a locate walks
+// 2^offrate - 1 LF steps on average, each one a sector from wherever the BWT lives.  HBM has room
+// for a denser table; its entries are computed by the reference's own walk, so results cannot change.
+int build_dense_locate(cfr_handle *h, int shift) {
+  if (shift < 0 || h->ix.sample_shift < 0 || shift >= h->ix.sample_shift) return CFR_OK;
+  const u64 n_rows = (h->ix.n >> shift) + 1;
+  void *p;
+  int st = dev_alloc(h, &p, n_rows * 4);
+  if (st) return st;
+  h->ix.dense_shift = -1;
+  const int grid = grid_for(h, n_rows, 128, 16);
+  if (h->layout == CFR_LAYOUT_OCCLINE) k_build_dense<BwtOccLine><<<grid, 128, 0, h->stream>>>(h->ix, (u32 *)p, shift, n_rows);
+  else k_build_dense<BwtRunBlock><<<grid, 128, 0, h->stream>>>(h->ix, (u32 *)p, shift, n_rows);
+  ++h->launches;
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  h->ix.dense = (const u32 *)p;
+  h->ix.dense_shift = shift;
   return CFR_OK;
 }
 
@@ -641,6 +663,16 @@ int cfr_open(const char *idx_prefix, const cfr_params *p, int device, cfr_handle
     }
     if (const char *e = getenv("CFR_B200_WIDE_LOOKUP")) ww = atoi(e);
     if ((st = build_wide_lookup(h, ww))) return bail(st);
+  }
+  {
+    // dense locate table: every 4th row when n bytes fit comfortably (1 byte per base), else every
+    // 8th; CFR_B200_DENSE_LOCATE=shift forces a spacing (-1 = off)
+    int shift = 2;
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    while (shift < 8 && ((h->ix.n >> shift) * 4 + (8ull << 30)) > (u64)free_b / 2) ++shift;
+    if (const char *e = getenv("CFR_B200_DENSE_LOCATE")) shift = atoi(e);
+    if ((st = build_dense_locate(h, shift))) return bail(st);
   }
   h->file.map1.close();  // everything needed from .1.cfr now lives in HBM
   *out = h;

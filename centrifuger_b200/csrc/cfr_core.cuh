@@ -731,6 +731,22 @@ CFR_HD bool get_sampled_sa(const DevIndex &ix, u64 i, u64 &sa) {
   return false;
 }
 
+// rows answered by the dense locate table (when built)
+template <typename Pos>
+CFR_HD bool is_dense_row(const DevIndex &ix, Pos i) {
+  return ix.dense_shift >= 0 && (i & (((Pos)1 << ix.dense_shift) - (Pos)1)) == 0;
+}
+
+// GetSampledSA with the dense table in front: a dense row's entry is what the literal procedure
+// below returns for the walk that starts there (checks at the row itself included)
+CFR_HD bool get_located(const DevIndex &ix, u64 i, u64 &sa) {
+  if (is_dense_row(ix, i)) {
+    sa = (u64)ld32(ix.dense + (i >> ix.dense_shift));
+    return true;
+  }
+  return get_sampled_sa(ix, i, sa);
+}
+
 // FMIndex::BackwardToSampledSA: the sampled SA holds sequence ids (Builder.hpp:27-71)
 template <class Bwt>
 CFR_HD u64 locate_row(const DevIndex &ix, u64 i, OpCount &oc) {

@@ -200,6 +200,16 @@ __global__ void __launch_bounds__(128) k_build_wide(const __grid_constant__ DevI
     out[key] = wide_lookup_entry<Bwt>(ix, key, WW);
 }
 
+// Dense locate table at load time: the literal walk (FMIndex::BackwardToSampledSA over the stored
+// samples only) from every row that is a multiple of 2^shift
+template <class Bwt>
+__global__ void __launch_bounds__(128) k_build_dense(const __grid_constant__ DevIndex ix, u32 *out, int shift, u64 n_rows) {
+  const u64 stride = (u64)gridDim.x * blockDim.x;
+  OpCount oc{};
+  for (u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x; j < n_rows; j += stride)
+    out[j] = (u32)locate_row<Bwt>(ix, j << shift, oc);  // ix.dense_shift is still -1 here
+}
+
 // ---- diagnostics for the parity tests ----
 template <class Bwt>
 __global__ void k_debug_rank(const __grid_constant__ DevIndex ix, const unsigned char *codes, const u64 *pos,

@@ -458,9 +458,9 @@ CFR_HD void locate_rows(const DevIndex &ix, const DevParams &P, const ChunkDev &
     const u32 trn = CFR_BALLOT(st == CFR_LS_CHECK || st == CFR_LS_NEED);
     if ((walk | trn) == 0) break;
     if (trn != 0 && (walk == 0 || popc32(trn) >= adaptive_quorum(P.quorum, walk | trn, (int)Bwt::LANES))) {
-      if (st == CFR_LS_CHECK) {  // FMIndex::GetSampledSA, literally
+      if (st == CFR_LS_CHECK) {  // FMIndex::GetSampledSA, literally (behind the dense table, when built)
         u64 sa;
-        if (get_sampled_sa(ix, i, sa)) {
+        if (get_located(ix, i, sa)) {
           if (Bwt::leader()) B.seq_ids[cur] = (u32)sa;
           ++oc.locate;
           st = CFR_LS_NEED;
@@ -485,7 +485,7 @@ CFR_HD void locate_rows(const DevIndex &ix, const DevParams &P, const ChunkDev &
     }
     if (st == CFR_LS_WALK) {
       // cheap pre-test of GetSampledSA's three conditions; the loads happen in the transition block
-      bool maybe = i == (pos_t)ix.first_isa || is_sampled_row(ix, i);
+      bool maybe = i == (pos_t)ix.first_isa || is_sampled_row(ix, i) || is_dense_row(ix, i);
       if (!maybe && ix.sel_filter) {
         const pos_t fb = filter_bit_index(ix, i);
         maybe = (ld64(ix.sel_filter + (fb >> 6)) >> (fb & 63)) & 1ull;

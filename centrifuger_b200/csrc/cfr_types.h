@@ -76,6 +76,11 @@ struct DevIndex {
   // {sp, ep | l << 56}: l < WW means the search ended inside them (l = W - 1: empty W-mer)
   int wide_width;  // 0 = none
   const u64x2 *wide;
+  // optional dense locate table, built at load by running FMIndex::BackwardToSampledSA once from
+  // every row that is a multiple of 2^dense_shift: dense[row >> dense_shift] = its sequence id.  A walk
+  // that reaches such a row ends there with the answer the reference's longer walk would find.
+  int dense_shift;  // -1 = none
+  const u32 *dense;
   // taxonomy (Taxonomy.hpp)
   u64 node_cnt, seq_cnt, root;
   const u32 *parent;

@@ -25,6 +25,7 @@ struct HostIndex {
   std::vector<u64> sel_filter;
   std::vector<OccLine> occ;
   std::vector<u64x2> wide;
+  std::vector<u32> dense;
   bool pos32 = false;
   DevIndex ix;
   DevParams P;
@@ -137,6 +138,18 @@ void *hostsim_open(const char *prefix, const cfr_params *p) {
       h->occ[L] = occ_pack(lo, hi, cnt[0], cnt[1], cnt[2]);
     }
     ix.occ = h->occ.data();
+  }
+  ix.dense_shift = -1;
+  if (const char *e = getenv("HOSTSIM_DENSE_LOCATE")) {  // the library's dense locate table
+    const int shift = atoi(e);
+    if (shift >= 0 && ix.sample_shift > shift) {
+      h->dense.resize((ix.n >> shift) + 1);
+      OpCount oc{};
+      for (u64 j = 0; j < h->dense.size(); ++j)
+        h->dense[j] = (u32)(h->layout == 2 ? locate_row<BwtOccLine>(ix, j << shift, oc) : locate_row<BwtRunBlock>(ix, j << shift, oc));
+      ix.dense = h->dense.data();
+      ix.dense_shift = shift;
+    }
   }
   if (const char *e = getenv("HOSTSIM_WIDE_LOOKUP")) {  // the library's wide lookup table, any width
     const int ww = atoi(e);

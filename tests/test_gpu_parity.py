@@ -21,12 +21,14 @@ LAYOUTS = [cb.LAYOUT_RUNBLOCK, cb.LAYOUT_OCCLINE]
 # loads, SDUST with or without the register-only screen
 VARIANTS = {"default": {}, "pos64": {"CFR_B200_POS64": "1"}, "pos64_ld128": {"CFR_B200_POS64": "1", "CFR_B200_OCC_LOAD": "0"},
             "ld128": {"CFR_B200_OCC_LOAD": "0"}, "noscreen": {"CFR_B200_DUST_SCREEN": "0"},
-            "wide12": {"CFR_B200_WIDE_LOOKUP": "12"}, "wide11_pos64": {"CFR_B200_WIDE_LOOKUP": "11", "CFR_B200_POS64": "1"}}
+            "wide12": {"CFR_B200_WIDE_LOOKUP": "12"}, "wide11_pos64": {"CFR_B200_WIDE_LOOKUP": "11", "CFR_B200_POS64": "1"},
+            "literal": {"CFR_B200_DENSE_LOCATE": "-1"}, "dense1_pos64": {"CFR_B200_DENSE_LOCATE": "1", "CFR_B200_POS64": "1"},
+            "dense3": {"CFR_B200_DENSE_LOCATE": "3"}}
 
 
 @pytest.fixture(params=sorted(VARIANTS))
 def variant_env(request, monkeypatch):
-    for k in ("CFR_B200_POS64", "CFR_B200_OCC_LOAD", "CFR_B200_DUST_SCREEN", "CFR_B200_WIDE_LOOKUP"):
+    for k in ("CFR_B200_POS64", "CFR_B200_OCC_LOAD", "CFR_B200_DUST_SCREEN", "CFR_B200_WIDE_LOOKUP", "CFR_B200_DENSE_LOCATE"):
         monkeypatch.delenv(k, raising=False)
     for k, v in VARIANTS[request.param].items():
         monkeypatch.setenv(k, v)  # read by cfr_open
@@ -147,7 +149,11 @@ def test_example_goldens(example_idx, manifest, layout):
 
 # ---------------------------------------------------------------- vs oracle
 @pytest.mark.parametrize("layout", LAYOUTS)
-def test_small_vs_oracle(small_dir, layout):
+def test_small_vs_oracle(small_dir, layout, monkeypatch):
+    # operation counts equal the oracle's when every rank / LF step of the reference really runs:
+    # the load-time tables that skip steps (dense locate table, wide lookup) are switched off here
+    monkeypatch.setenv("CFR_B200_DENSE_LOCATE", "-1")
+    monkeypatch.setenv("CFR_B200_WIDE_LOOKUP", "0")
     idx = os.path.join(small_dir, "idx")
     sets = {"se": ["se_100.fq"], "pe": ["pe_150_1.fq", "pe_150_2.fq"], "edge": ["edge_1.fq", "edge_2.fq"]}
     for name, files in sets.items():
@@ -287,11 +293,13 @@ def test_kernel_variants_vs_oracle(small_dir, variant_env):
         res, ids = g.classify(r1, r2)
         assert _tuples(res, ids, g.k) == exp, (variant_env, kw)
         c = g.counters()
-        for key in ("n_rank", "n_access", "n_search", "n_locate", "n_lf", "n_extend"):
-            if not variant_env.startswith("wide"):
+        assert c["n_search"] == oc["n_search"] and c["n_locate"] == oc["n_locate"], (variant_env, kw)
+        if variant_env == "literal":  # no load-time table skips a step: every count equals the oracle's
+            for key in ("n_rank", "n_access", "n_lf", "n_extend"):
                 assert c[key] == oc[key], (variant_env, kw, key)
-            elif key in ("n_rank", "n_extend"):  # the wide table replaces the first extends of a search
-                assert c[key] < oc[key], (variant_env, kw, key)
+        else:  # the dense locate table (default) shortens LF walks, the wide lookup table skips extends
+            assert c["n_lf"] < oc["n_lf"] and c["n_rank"] < oc["n_rank"], (variant_env, kw)
+            assert (c["n_extend"] < oc["n_extend"]) == variant_env.startswith("wide"), (variant_env, kw)
         g.close()
 
 

@@ -31,8 +31,8 @@ def _compare(idx, files, layout, arena_rows=0, limit=None, check_counters=True, 
         for k in ("n_rank", "n_access", "n_search", "n_locate", "n_lf", "n_extend"):
             if check_counters:
                 assert oc[k] == cnt[k], k
-            elif k in ("n_rank", "n_extend"):
-                assert cnt[k] <= oc[k], k  # a wide lookup table only removes BackwardExtend calls
+            elif k in ("n_rank", "n_extend", "n_lf"):
+                assert cnt[k] <= oc[k], k  # the load-time tables only remove BackwardExtend / LF steps
     finally:
         hs.close()
         o.close()
@@ -69,6 +69,20 @@ def test_wide_lookup_table_same_answers(tiny_dir, layout, width, monkeypatch):
         for files in (["se_100.fq"], ["pe_100_1.fq", "pe_100_2.fq"], ["edge.fq"], ["edge_1.fq", "edge_2.fq"]):
             fs = [os.path.join(tiny_dir, f) for f in files]
             for kw in (dict(), dict(k=5), dict(dust=False, min_hit_len=16)):
+                _compare(idx, fs, layout, check_counters=False, **kw)
+
+
+@pytest.mark.parametrize("layout", [1, 2, 3])
+@pytest.mark.parametrize("shift", [0, 1, 2, 3])
+def test_dense_locate_table_same_answers(tiny_dir, layout, shift, monkeypatch):
+    """the dense locate table (answers of the reference's own walk, stored for every 2^shift-th row)
+    changes no result; idx_off3 samples every 8th row, the others every 16th"""
+    monkeypatch.setenv("HOSTSIM_DENSE_LOCATE", str(shift))
+    for variant in ("idx", "idx_off3", "idx_b8"):
+        idx = os.path.join(tiny_dir, variant)
+        for files in (["se_100.fq"], ["pe_100_1.fq", "pe_100_2.fq"], ["edge_1.fq", "edge_2.fq"]):
+            fs = [os.path.join(tiny_dir, f) for f in files]
+            for kw in (dict(), dict(k=5), dict(k=3, hitk_factor=2)):
                 _compare(idx, fs, layout, check_counters=False, **kw)
 
 
