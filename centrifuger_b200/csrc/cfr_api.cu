@@ -665,12 +665,15 @@ int cfr_open(const char *idx_prefix, const cfr_params *p, int device, cfr_handle
     if ((st = build_wide_lookup(h, ww))) return bail(st);
   }
   {
-    // dense locate table: every 4th row when n bytes fit comfortably (1 byte per base), else every
-    // 8th; CFR_B200_DENSE_LOCATE=shift forces a spacing (-1 = off)
-    int shift = 2;
+    // dense locate table: the densest spacing whose table (4 bytes per entry) stays below a quarter
+    // of the free HBM and 24 GB -- every row for collections up to 6 Gbp; CFR_B200_DENSE_LOCATE=shift
+    // forces a spacing (-1 = off).  Measured on configs[1]: every 8th / 4th / 2nd row -> 0.39 / 0.33 /
+    // 0.24 ms per 1 M reads (0.49 with the stored samples only, every 16th row).
+    int shift = 0;
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
-    while (shift < 8 && ((h->ix.n >> shift) * 4 + (8ull << 30)) > (u64)free_b / 2) ++shift;
+    const u64 budget = std::min<u64>((u64)free_b / 4, 24ull << 30);
+    while (shift < 8 && ((h->ix.n >> shift) + 1) * 4 > budget) ++shift;
     if (const char *e = getenv("CFR_B200_DENSE_LOCATE")) shift = atoi(e);
     if ((st = build_dense_locate(h, shift))) return bail(st);
   }

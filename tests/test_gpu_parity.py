@@ -23,7 +23,7 @@ VARIANTS = {"default": {}, "pos64": {"CFR_B200_POS64": "1"}, "pos64_ld128": {"CF
             "ld128": {"CFR_B200_OCC_LOAD": "0"}, "noscreen": {"CFR_B200_DUST_SCREEN": "0"},
             "wide12": {"CFR_B200_WIDE_LOOKUP": "12"}, "wide11_pos64": {"CFR_B200_WIDE_LOOKUP": "11", "CFR_B200_POS64": "1"},
             "literal": {"CFR_B200_DENSE_LOCATE": "-1"}, "dense1_pos64": {"CFR_B200_DENSE_LOCATE": "1", "CFR_B200_POS64": "1"},
-            "dense3": {"CFR_B200_DENSE_LOCATE": "3"}}
+            "dense3": {"CFR_B200_DENSE_LOCATE": "3"}, "dense2_ld128": {"CFR_B200_DENSE_LOCATE": "2", "CFR_B200_OCC_LOAD": "0"}}
 
 
 @pytest.fixture(params=sorted(VARIANTS))
