@@ -480,7 +480,8 @@ int run_pass(cfr_handle *h, const ChunkDev &B, int first_pass, cudaStream_t s) {
     StageScope sc(h, s, CFR_STAGE_SELECT);
     k_select<Bwt><<<grid_for(h, B.n_list, 128, 16), 128, 0, s>>>(h->ix, h->P, B, first_pass);
   }
-  {
+  const bool need_locate = !locate_in_select(h->ix);  // the dense table answered every row in k_select
+  if (need_locate) {
     StageScope sc(h, s, CFR_STAGE_LOCATE);
     k_locate<BwtWide><<<grid_for(h, B.arena_cap * BwtWide::LANES, 128, 16), 128, 0, s>>>(h->ix, h->P, B);
   }
@@ -488,7 +489,7 @@ int run_pass(cfr_handle *h, const ChunkDev &B, int first_pass, cudaStream_t s) {
     StageScope sc(h, s, CFR_STAGE_SCORE);
     k_score<<<grid_for(h, B.n_list, 128, 16), 128, 0, s>>>(h->ix, h->P, B);
   }
-  h->launches += 3;
+  h->launches += need_locate ? 3 : 2;
   CUDA_TRY(cudaGetLastError());
   return CFR_OK;
 }

@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(128) k_select(const __grid_constant__ DevIndex
     if (active) {
       const u64 my_base = base0 + incl - r;
       const bool fits = my_base + r <= B.arena_cap;
-      select_write_rows(P, B, read, my_base, fits);
+      oc.locate += select_write_rows(ix, P, B, read, my_base, fits);
       if (!fits) {
         B.deferred[atomicAdd(B.n_deferred, 1u)] = (u32)read;
         atomicMin(B.arena_valid, my_base);

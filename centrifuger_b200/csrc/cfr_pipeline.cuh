@@ -572,19 +572,32 @@ CFR_HD u32 select_plan(const DevIndex &ix, const DevParams &P, const ChunkDev &B
 }
 
 // Phase B: with the arena slice known, expand the planned rows.
-CFR_HD void select_write_rows(const DevParams &P, const ChunkDev &B, u64 read, u64 arena_base, bool fits) {
+// When the dense locate table answers every row (dense_shift == 0) the sequence ids are written here
+// and the locate launch is skipped (locate_in_select); returns the number of rows resolved that way.
+CFR_HD bool locate_in_select(const DevIndex &ix) { return ix.dense_shift == 0; }
+
+CFR_HD u32 select_write_rows(const DevIndex &ix, const DevParams &P, const ChunkDev &B, u64 read, u64 arena_base,
+                             bool fits) {
   const int S = 2 * B.mates;
   ReadWork &w = B.work[read];
   w.arena_base = arena_base;
   w.status = fits ? 0 : 1;
-  if (!fits) return;
+  if (!fits) return 0;
   const FinalHit *fh = B.fhits + read * (u64)S * (u64)B.cap_h;
+  const bool direct = locate_in_select(ix);
   u64 o = arena_base;
   for (u32 i = 0; i < w.n_hits; ++i) {
     if (fh[i].row_cnt == 0) continue;
     const RowPlan rp = plan_rows(fh[i].sp, fh[i].ep, P);
-    for (u64 t = 0; t < rp.total; ++t) B.rows[o++] = plan_row_at(fh[i].sp, fh[i].ep, rp, t);
+    for (u64 t = 0; t < rp.total; ++t) {
+      const u64 row = plan_row_at(fh[i].sp, fh[i].ep, rp, t);
+      if (direct)
+        B.seq_ids[o++] = ld32(ix.dense + row);
+      else
+        B.rows[o++] = row;
+    }
   }
+  return direct ? (u32)(o - arena_base) : 0u;
 }
 
 // ------------------------------------------------------------------ score

@@ -342,7 +342,7 @@ int hostsim_classify(void *hh, int dust, uint64_t arena_rows, const cfr_read_bat
       const u64 base = arena_used;
       arena_used += r;
       const bool fits = base + r <= B.arena_cap;
-      select_write_rows(P, B, read, base, fits);
+      oc.locate += select_write_rows(ix, P, B, read, base, fits);
       if (!fits) {
         deferred[n_deferred++] = (u32)read;
         arena_valid = std::min(arena_valid, base);
@@ -350,7 +350,8 @@ int hostsim_classify(void *hh, int dust, uint64_t arena_rows, const cfr_read_bat
     }
     const u64 used = std::min(std::min(arena_used, arena_valid), B.arena_cap);
     row_counter = 0;
-    if (h->layout == 2 && h->pos32) locate_rows<BwtOccLine32T<0>>(ix, P, B, used, oc);
+    if (locate_in_select(ix)) {
+    } else if (h->layout == 2 && h->pos32) locate_rows<BwtOccLine32T<0>>(ix, P, B, used, oc);
     else if (h->layout == 2) locate_rows<BwtOccLine>(ix, P, B, used, oc);
     else locate_rows<BwtRunBlock>(ix, P, B, used, oc);
     for (u64 t = 0; t < B.n_list; ++t) {
