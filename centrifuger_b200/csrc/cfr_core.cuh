@@ -896,6 +896,22 @@ CFR_HD u32 tax_lca(const DevIndex &ix, const u64 *ids, int cnt, u64 *err_flags) 
   int k = 0;
   while (k < cnt && (u32)ids[k] == root) ++k;
   if (k >= cnt) return root;
+  {
+    // Shortcut for the common case (strains of one species tie): no id is a root-level node and all
+    // share one parent.  Their root paths have equal length and differ at most in the lowest node,
+    // so the general procedure below returns the id itself when all are equal, else the parent.
+    // `cnt` independent loads instead of several dependent parent-chain walks.
+    const u32 x0 = (u32)ids[0];
+    const u32 p0 = tax_parent(ix, x0);
+    bool same_parent = p0 != x0, all_equal = true;
+    for (int i = 1; i < cnt; ++i) {
+      const u32 x = (u32)ids[i];
+      const u32 px = tax_parent(ix, x);
+      same_parent = same_parent && px == p0 && px != x;
+      all_equal = all_equal && x == x0;
+    }
+    if (same_parent) return all_equal ? x0 : p0;
+  }
   u32 path[CFR_TAX_PATH_CAP];
   int plen = 0;
   u32 t = (u32)ids[k];
