@@ -910,7 +910,10 @@ CFR_HD u32 tax_lca(const DevIndex &ix, const u64 *ids, int cnt, u64 *err_flags) 
       same_parent = same_parent && px == p0 && px != x;
       all_equal = all_equal && x == x0;
     }
-    if (same_parent) return all_equal ? x0 : p0;
+    if (same_parent) {
+      if (all_equal) return x0;
+      return tax_parent(ix, p0) == p0 ? root : p0;  // a root-level parent is reported as the root (the pushed path end)
+    }
   }
   u32 path[CFR_TAX_PATH_CAP];
   int plen = 0;

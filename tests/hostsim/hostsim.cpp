@@ -188,6 +188,17 @@ uint64_t hostsim_locate(void *hh, uint64_t row) {
   return h->layout == 2 ? locate_row<BwtOccLine>(h->ix, row, oc) : locate_row<BwtRunBlock>(h->ix, row, oc);
 }
 
+// Taxonomy::ReduceTaxIds as the scoring stage runs it (tax_reduce / tax_lca); returns the number of ids
+int hostsim_reduce_taxids(void *hh, const uint64_t *tax_ids, int cnt, int k, uint64_t *out) {
+  HostIndex *h = (HostIndex *)hh;
+  std::vector<u64> scratch(cnt + 1), o(cnt + 1 + (k > 0 ? k : 1));
+  u64 err = 0;
+  const int n = tax_reduce(h->ix, (const u64 *)tax_ids, cnt, k, scratch.data(), o.data(), &err);
+  if (err) return -1;
+  for (int i = 0; i < n; ++i) out[i] = o[i];
+  return n;
+}
+
 void hostsim_dust(const char *in, int n, char *out) {
   static DustState d;
   memcpy(out, in, (size_t)n);

@@ -98,6 +98,8 @@ def lib():
         L.hostsim_bwt_access.argtypes = [C.c_void_p, C.c_uint64]
         L.hostsim_locate.restype = C.c_uint64
         L.hostsim_locate.argtypes = [C.c_void_p, C.c_uint64]
+        L.hostsim_reduce_taxids.restype = C.c_int
+        L.hostsim_reduce_taxids.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.c_int, C.c_int, C.POINTER(C.c_uint64)]
         L.hostsim_dust.argtypes = [C.c_char_p, C.c_int, C.c_char_p]
         L.hostsim_dust_screen.argtypes = [C.c_char_p, C.c_int]
         L.hostsim_dust_screen.restype = C.c_int
@@ -152,6 +154,12 @@ class HostSim:
 
     def locate(self, row):
         return self.L.hostsim_locate(self.h, row)
+
+    def reduce_taxids(self, tax_ids, k):
+        arr = (C.c_uint64 * len(tax_ids))(*tax_ids)
+        out = (C.c_uint64 * (len(tax_ids) + max(k, 1) + 1))()
+        n = self.L.hostsim_reduce_taxids(self.h, arr, len(tax_ids), k, out)
+        return [int(out[i]) for i in range(n)]
 
     def classify(self, reads1, reads2=None, arena_rows=0):
         b, keep = make_batch(reads1, reads2)

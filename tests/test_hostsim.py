@@ -86,6 +86,32 @@ def test_dense_locate_table_same_answers(tiny_dir, layout, shift, monkeypatch):
                 _compare(idx, fs, layout, check_counters=False, **kw)
 
 
+def test_reduce_taxids_fuzz(tiny_dir, example_idx):
+    """Taxonomy::ReduceTaxIds / LCA on random id sets (siblings, mixed depths, root-level and
+    out-of-range ids, duplicates) against the oracle"""
+    rng = random.Random(29)
+    for idx in (os.path.join(tiny_dir, "idx"), example_idx):
+        o = Oracle(idx)
+        hs = HostSim(idx)
+        nodes = o.scalar(10)
+        for it in range(3000):
+            cnt = rng.randint(2, 9)
+            mode = rng.random()
+            if mode < 0.5:
+                ids = [rng.randrange(nodes) for _ in range(cnt)]
+            elif mode < 0.8:  # few distinct values: ties, siblings, duplicates
+                pool = [rng.randrange(nodes) for _ in range(3)]
+                ids = [rng.choice(pool) for _ in range(cnt)]
+            else:  # now and then an id the taxonomy does not know
+                ids = [rng.randrange(nodes + 2) for _ in range(cnt)]
+            for k in (1, 2, 5):
+                if cnt <= k:
+                    continue
+                assert hs.reduce_taxids(ids, k) == o.reduce_taxids(ids, k), (ids, k)
+        hs.close()
+        o.close()
+
+
 def test_example(example_idx):
     from conftest import golden_path
     fs = [golden_path("example", "example_1.fq"), golden_path("example", "example_2.fq")]
