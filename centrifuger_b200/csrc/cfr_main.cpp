@@ -10,6 +10,7 @@
 // of scope"): --un/--cl, --merge-readpair, --expand-taxid, barcode/UMI/read-format
 // options, --sample-sheet.  They are rejected with a log line and EXIT_FAILURE.
 #include <getopt.h>
+#include <sys/stat.h>
 #include <zlib.h>
 
 #include <algorithm>
@@ -362,6 +363,28 @@ int main(int argc, char *argv[]) {
   if (batchReads < 1) batchReads = 1;
   params.max_batch_reads = (int32_t)(batchReads > (1 << 22) ? (1 << 22) : batchReads);
 
+  {
+    // The library's load-time tables (dense locate table, wide lookup table: DESIGN.md section 2) take
+    // about a second per Gbp of index to build and pay off over tens of millions of reads.  For a small
+    // input -- estimated from the file sizes -- they are left out, unless the environment already says
+    // otherwise.  Results are identical either way.
+    double bases = 0;
+    bool known = true;
+    for (int m = 0; m < 2; ++m)
+      for (const std::string &f : (m ? mates : reads).files) {
+        struct stat sb;
+        if (f == "-" || stat(f.c_str(), &sb) != 0 || !S_ISREG(sb.st_mode)) {
+          known = false;
+          continue;
+        }
+        const bool gz = f.size() > 3 && f.compare(f.size() - 3, 3, ".gz") == 0;
+        bases += (double)sb.st_size * (gz ? 2.0 : 0.45);  // FASTQ: sequence + qualities + header
+      }
+    if (known && bases < 3e9) {
+      setenv("CFR_B200_DENSE_LOCATE", "-1", 0);
+      setenv("CFR_B200_WIDE_LOOKUP", "0", 0);
+    }
+  }
   cfr_handle *h = NULL;
   int st = cfr_open(idxPrefix, &params, device, &h);
   if (st != CFR_OK) {
