@@ -90,6 +90,7 @@ struct cfr_handle {
   int search_blocks = 10;  // resident 128-thread blocks per SM targeted by k_search (CFR_B200_SEARCH_BLOCKS)
   int occ_load = 4;    // how k_search / k_locate fetch a sector: 4 = one 256-bit load, 0 = two 128-bit loads (CFR_B200_OCC_LOAD)
   bool pos32 = false;  // 32-bit BWT positions in k_search / k_locate (collections below 2^32 rows; CFR_B200_POS64=1 disables)
+  int dust_quorum = 0;  // quorum of the SDUST state machine (0 = the search quorum; CFR_B200_DUST_QUORUM)
   int dust_lanes = 16;  // lanes per warp that take mates in the post-screen SDUST launch (CFR_B200_DUST_LANES)
   bool dust_screen = true;  // register-only screen in front of the full SDUST (CFR_B200_DUST_SCREEN=0 disables)
   u64 *d_taxon = nullptr;
@@ -199,7 +200,7 @@ void launch_dust(cfr_handle *h, const ChunkDev &B, cudaStream_t s) {
   }
   // after the screen only the few mates that need the whole algorithm are left: fewer lanes per warp
   k_dust<<<grid_for(h, ntask, CFR_DUST_THREADS, 5), CFR_DUST_THREADS, CFR_DUST_SMEM, s>>>(
-      B, h->P.quorum, B.dust_list ? h->dust_lanes : 32);
+      B, h->dust_quorum ? h->dust_quorum : h->P.quorum, B.dust_list ? h->dust_lanes : 32);
   ++h->launches;
 }
 
@@ -621,6 +622,7 @@ int cfr_open(const char *idx_prefix, const cfr_params *p, int device, cfr_handle
   if (const char *e = getenv("CFR_B200_QUORUM")) h->P.quorum = std::max(1, atoi(e));
   if (const char *e = getenv("CFR_B200_SEARCH_BLOCKS")) h->search_blocks = std::max(1, atoi(e));
   if (const char *e = getenv("CFR_B200_DUST_SCREEN")) h->dust_screen = atoi(e) != 0;
+  if (const char *e = getenv("CFR_B200_DUST_QUORUM")) h->dust_quorum = std::max(0, atoi(e));
   if (const char *e = getenv("CFR_B200_DUST_LANES")) h->dust_lanes = std::min(32, std::max(1, atoi(e)));
   if (const char *e = getenv("CFR_B200_OCC_LOAD")) h->occ_load = atoi(e) == 0 ? 0 : 4;
   h->pos32 = h->file.n < CFR_POS32_MAX_N;
