@@ -198,9 +198,12 @@ void launch_dust(cfr_handle *h, const ChunkDev &B, cudaStream_t s) {
     k_dust_screen<<<grid_for(h, ntask, 128, 16), 128, 0, s>>>(B);
     ++h->launches;
   }
-  // after the screen only the few mates that need the whole algorithm are left: fewer lanes per warp
-  k_dust<<<grid_for(h, ntask, CFR_DUST_THREADS, 5), CFR_DUST_THREADS, CFR_DUST_SMEM, s>>>(
-      B, h->dust_quorum ? h->dust_quorum : h->P.quorum, B.dust_list ? h->dust_lanes : 32);
+  // after the screen only the few mates that need the whole algorithm are left: 16 lanes per warp
+  const int q = h->dust_quorum ? h->dust_quorum : h->P.quorum;
+  if (B.dust_list && h->dust_lanes <= 16)
+    k_dust<16><<<grid_for(h, ntask, CFR_DUST_THREADS, 10), CFR_DUST_THREADS, dust_smem_bytes<16>(), s>>>(B, q);
+  else
+    k_dust<32><<<grid_for(h, ntask, CFR_DUST_THREADS, 5), CFR_DUST_THREADS, dust_smem_bytes<32>(), s>>>(B, q);
   ++h->launches;
 }
 

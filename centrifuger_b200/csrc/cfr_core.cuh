@@ -1557,10 +1557,10 @@ CFR_HD bool dust_all_acgt(const u32 *nmask, u64 base, int n) {
 // window: compute L from the window's heavy classes and count the copies of t among
 // the last L triplets; if that count never reaches 5 (and the conservative outs below
 // never fire) no perfect interval exists and SDUST masks nothing.
-// The window counts are kept bit-sliced in four 64-bit registers (one bit per triplet
+// The window counts are kept bit-sliced in three 64-bit registers (one bit per triplet
 // class and plane), so the screen touches no memory beyond the packed read itself.
-// Conservative outs: three heavy classes at once, or L > 30 (the history examined is
-// one 32-base word; a single class reaches that at 8 copies).
+// Conservative outs: a count of 7 (the planes would wrap), three heavy classes at
+// once, or L > 30 (the history examined is one 32-base word).
 // Returns true when the full SDUST must run.
 // (lo, hi) >> s for 0 <= s < 32, low word
 CFR_HD u32 funnel_r(u32 lo, u32 hi, int s) {
@@ -1593,19 +1593,18 @@ __device__ __noinline__
 #else
 inline
 #endif
-bool dust_screen_event(u64 b0, u64 b1, u64 b2, u64 b3, u64 m, u32 t, u64 hist, int i) {
-  u64 hh = b3 | (b2 & (b0 | b1));  // heavy classes (>= 5 copies)
+bool dust_screen_event(u64 b0, u64 b1, u64 b2, u64 m, u32 t, u64 hist, int i) {
+  if (b2 & b1 & b0 & m) return true;  // 7 copies
+  u64 hh = b2 & (b0 | b1);            // heavy classes
   int L = 2;
   for (int q = 0; q < 2; ++q) {
     if (!hh) break;
     const u64 bit = hh & (~hh + 1ull);
     hh ^= bit;
-    const int c = ((b3 & bit) ? 8 : 0) + ((b2 & bit) ? 4 : 0) + ((b1 & bit) ? 2 : 0) + ((b0 & bit) ? 1 : 0);
+    const int c = 4 + ((b1 & bit) ? 2 : 0) + ((b0 & bit) ? 1 : 0);
     L += c * (c - 4);
   }
-  // three heavy classes, or more history than one word (a count of 8 alone gives L = 34: the four
-  // planes never wrap before the mate is flagged)
-  if (hh || L > 30) return true;
+  if (hh || L > 30) return true;  // three heavy classes, or more history than one word
   const int leff = L < i + 1 ? L : i + 1;
   const u64 occ = dust_base_eq(hist, t & 3u) & (dust_base_eq(hist, (t >> 2) & 3u) >> 2) &
                   (dust_base_eq(hist, (t >> 4) & 3u) >> 4);
@@ -1615,7 +1614,7 @@ bool dust_screen_event(u64 b0, u64 b1, u64 b2, u64 b3, u64 m, u32 t, u64 hist, i
 CFR_HD bool dust_screen(const u64 *codes, u64 q0, int len) {
   const int nt = len - 2;  // triplets; fewer than 5 can never reach the threshold
   if (nt < 5) return false;
-  u64 b0 = 0, b1 = 0, b2 = 0, b3 = 0;  // bit planes of the per-class window counts (0..15)
+  u64 b0 = 0, b1 = 0, b2 = 0;  // bit planes of the per-class window counts
   // sliding view of the mate in 16-base words: w0 holds the bases of the current block,
   // wm4..wm1 the four blocks before it (the triplet leaving the 62-triplet window starts
   // 62 bases back), w1 the next one
@@ -1637,9 +1636,7 @@ CFR_HD bool dust_screen(const u64 *codes, u64 q0, int len) {
           b0 ^= mo;
           const u64 br1 = ~b1 & br0;
           b1 ^= br0;
-          const u64 br2 = ~b2 & br1;
           b2 ^= br1;
-          b3 ^= br2;
         }
         const u32 t = (j <= 13 ? w0 >> (2 * j) : funnel_r(w0, w1, 2 * j)) & 63u;
         const u64 m = 1ull << t;
@@ -1647,10 +1644,8 @@ CFR_HD bool dust_screen(const u64 *codes, u64 q0, int len) {
         b0 ^= m;
         const u64 c1 = b1 & c0;
         b1 ^= c0;
-        const u64 c2 = b2 & c1;
         b2 ^= c1;
-        b3 ^= c2;
-        if ((b3 | (b2 & (b0 | b1))) & m) {  // class t has >= 5 copies in the window
+        if (b2 & (b0 | b1) & m) {  // class t has >= 5 copies in the window
           // the 32 bases ending with triplet i: from base j+3 of block k-2 on
           u32 lo, hi;
           if (j <= 12) {
@@ -1660,7 +1655,7 @@ CFR_HD bool dust_screen(const u64 *codes, u64 q0, int len) {
             lo = funnel_r(wm1, w0, 2 * (j - 13));
             hi = funnel_r(w0, w1, 2 * (j - 13));
           }
-          if (dust_screen_event(b0, b1, b2, b3, m, t, (u64)lo | ((u64)hi << 32), i)) need = true;
+          if (dust_screen_event(b0, b1, b2, m, t, (u64)lo | ((u64)hi << 32), i)) need = true;
         }
       }
     }

@@ -56,19 +56,28 @@ __global__ void __launch_bounds__(128) k_dust_screen(const __grid_constant__ Chu
 }
 
 // SDUST: one mate per thread.  The data-dependent triplet counters and the window
-// ring live in shared memory, one bank column per thread (80 words x 128 threads
-// = 40 KiB per block), so their updates are conflict-free single wavefronts.
-enum { CFR_DUST_THREADS = 128, CFR_DUST_SMEM = 80 * CFR_DUST_THREADS * 4 };
-__global__ void __launch_bounds__(CFR_DUST_THREADS) k_dust(const __grid_constant__ ChunkDev B, const int quorum,
-                                                           const int lanes_per_warp) {
+// ring live in shared memory, one bank column per ACTIVE thread (80 words each), so their
+// updates are conflict-free single wavefronts.  AL = lanes per warp that take mates:
+//   32  every lane (unscreened input: most mates never leave the common step): 40 KiB per block
+//   16  the launch behind the screen: every mate runs the serial loops (shrink, FindPerfect),
+//       which stall the other mates of its warp, so the mates are spread over twice as many warps;
+//       columns only for the active lanes (20 KiB per block) let twice as many blocks be resident
+enum { CFR_DUST_THREADS = 128 };
+template <int AL>
+__global__ void __launch_bounds__(CFR_DUST_THREADS) k_dust(const __grid_constant__ ChunkDev B, const int quorum) {
   extern __shared__ u32 dust_sm[];
-  DustStateT<CFR_DUST_THREADS> d;
-  d.cc.base = reinterpret_cast<unsigned char *>(&dust_sm[threadIdx.x]);                          // 64 words
-  d.win.base = reinterpret_cast<unsigned char *>(&dust_sm[64 * CFR_DUST_THREADS + threadIdx.x]);  // 16 words
+  constexpr int COLS = (CFR_DUST_THREADS / 32) * AL;  // active threads per block
+  const int lane = threadIdx.x & 31;
+  const int col = (threadIdx.x >> 5) * AL + (lane < AL ? lane : 0);
+  DustStateT<COLS> d;
+  d.cc.base = reinterpret_cast<unsigned char *>(&dust_sm[col]);               // 64 words
+  d.win.base = reinterpret_cast<unsigned char *>(&dust_sm[64 * COLS + col]);  // 16 words
   // mates are claimed dynamically from B.dust_counter (through B.dust_list when the screen ran)
-  dust_tasks(B, B.dust_list ? (u64)*B.dust_list_n : B.n_reads * (u64)B.mates, d, quorum,
-             (int)(threadIdx.x & 31) < lanes_per_warp, B.dust_list != nullptr);
+  dust_tasks(B, B.dust_list ? (u64)*B.dust_list_n : B.n_reads * (u64)B.mates, d, quorum, lane < AL,
+             B.dust_list != nullptr);
 }
+template <int AL>
+constexpr int dust_smem_bytes() { return 80 * (CFR_DUST_THREADS / 32) * AL * 4; }
 
 // MINB = resident blocks per SM the register allocation must allow (occupancy knob)
 template <class Bwt, int MINB>
