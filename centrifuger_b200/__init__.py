@@ -57,7 +57,7 @@ RESULT_DTYPE = np.dtype([("score", "<u8"), ("secondary_score", "<u8"), ("hit_len
 # every symbol include/centrifuger_b200.h declares
 ABI_SYMBOLS = [
     "cfr_default_params", "cfr_open", "cfr_close", "cfr_last_error", "cfr_classify_batch",
-    "cfr_submit_batch", "cfr_wait_batch", "cfr_batch_upload", "cfr_classify_resident", "cfr_batch_fetch", "cfr_batch_free",
+    "cfr_submit_batch", "cfr_submit_batch_masked", "cfr_wait_batch", "cfr_batch_upload", "cfr_classify_resident", "cfr_batch_fetch", "cfr_batch_free",
     "cfr_host_alloc", "cfr_host_free", "cfr_index_info", "cfr_seq_name", "cfr_rank_name", "cfr_orig_taxid", "cfr_seq_taxid",
     "cfr_format_tsv", "cfr_taxon_counts_device", "cfr_taxon_counts_read", "cfr_taxon_counts_reset",
     "cfr_get_counters", "cfr_reset_counters", "cfr_set_profiling", "cfr_get_stage_times",
@@ -86,6 +86,7 @@ def load_library():
     L.cfr_last_error.restype = C.c_char_p
     L.cfr_classify_batch.argtypes = [vp, C.POINTER(ReadBatch), vp, vp, vp]
     L.cfr_submit_batch.argtypes = [vp, C.POINTER(ReadBatch), vp, vp, vp, C.POINTER(C.c_int)]
+    L.cfr_submit_batch_masked.argtypes = [vp, C.POINTER(ReadBatch), vp, vp, vp, vp, vp, C.POINTER(C.c_int)]
     L.cfr_wait_batch.argtypes = [vp, C.c_int]
     L.cfr_batch_upload.argtypes = [vp, C.POINTER(ReadBatch), vp, C.POINTER(vp)]
     L.cfr_classify_resident.argtypes = [vp, vp, vp]
@@ -277,6 +278,24 @@ class Classifier:
 
     def wait(self, ticket):
         self._check(self.L.cfr_wait_batch(self.h, ticket))
+
+    def classify_masked(self, reads1, reads2=None):
+        """One batch through the streaming form that also returns the reads as they were classified
+        (DUST intervals as N): (results, ids, masked1, masked2)."""
+        s1, o1 = pack_reads(reads1)
+        s2, o2 = pack_reads(reads2) if reads2 is not None else (None, None)
+        n = len(o1) - 1
+        b = make_batch(s1, o1, s2, o2, n)
+        res = np.zeros(n, dtype=RESULT_DTYPE)
+        ids = np.zeros(max(1, n * self.k), dtype=np.uint64)
+        m1 = np.zeros(max(1, len(s1)), dtype=np.uint8)
+        m2 = np.zeros(max(1, len(s2)), dtype=np.uint8) if s2 is not None else None
+        t = C.c_int(-1)
+        self._check(self.L.cfr_submit_batch_masked(self.h, C.byref(b), _ptr(res), _ptr(ids), _ptr(m1),
+                                                   _ptr(m2) if m2 is not None else None, None, C.byref(t)))
+        self.wait(t.value)
+        split = lambda m, o: [bytes(m[int(o[i]):int(o[i + 1])]) for i in range(n)]
+        return res, ids.reshape(n, self.k), split(m1, o1), (split(m2, o2) if m2 is not None else None)
 
     def upload(self, seq1, off1, seq2=None, off2=None, stream=None):
         n = len(off1) - 1

@@ -68,10 +68,12 @@ struct cfr_device_batch {
   u64 arena_cap = 0;
   DevBuf seq_raw, codes, mask_raw, mask, off, strand_hits, strand_nhits, fhits, work, rows, seq_ids, rec0, rec1, best, tmp,
       results, out_ids, deferred, dust_list, scalars;  // scalars: {u64 arena_used, u32 n_deferred, pad}
+  DevBuf dust_bits, masked;  // only when the caller wants the masked reads back (cfr_submit_batch_masked)
+  bool want_masked = false;
   bool classified = false;
   void release() {
     DevBuf *all[] = {&seq_raw, &codes, &mask_raw, &mask, &off, &strand_hits, &strand_nhits, &fhits, &work, &rows, &seq_ids,
-                     &rec0, &rec1, &best, &tmp, &results, &out_ids, &deferred, &dust_list, &scalars};
+                     &rec0, &rec1, &best, &tmp, &results, &out_ids, &deferred, &dust_list, &scalars, &dust_bits, &masked};
     for (DevBuf *b : all) b->release();
   }
 };
@@ -418,6 +420,10 @@ int upload_chunk(cfr_handle *h, const cfr_read_batch *in, u64 r0, u64 r1, cfr_de
   if ((st = b->deferred.ensure(n * 4 * 2))) return st;
   if ((st = b->dust_list.ensure(n * 4 * (u64)mates))) return st;
   if ((st = b->scalars.ensure(64))) return st;
+  if (b->want_masked) {
+    if ((st = b->dust_bits.ensure(n_words * 4))) return st;
+    if ((st = b->masked.ensure(b->seq_bytes + 64))) return st;
+  }
   // H2D
   if (len1) CUDA_TRY(cudaMemcpyAsync(b->seq_raw.p, in->seq1 + s1, len1, cudaMemcpyHostToDevice, s));
   if (len2) CUDA_TRY(cudaMemcpyAsync((char *)b->seq_raw.p + pos2, in->seq2 + s2, len2, cudaMemcpyHostToDevice, s));
@@ -437,7 +443,7 @@ void fill_chunk(cfr_handle *h, cfr_device_batch *b, ChunkDev &B) {
   B.codes = (u64 *)b->codes.p;
   B.mask_raw = (u32 *)b->mask_raw.p;
   B.mask = h->params.dust ? (u32 *)b->mask.p : (u32 *)b->mask_raw.p;
-  B.dust_bits = nullptr;
+  B.dust_bits = b->want_masked ? (u32 *)b->dust_bits.p : nullptr;
   B.off[0] = (const u64 *)b->off.p;
   B.off[1] = (const u64 *)b->off.p + (b->n_reads + 1);
   B.off_bias[0] = b->off_bias[0];
@@ -512,6 +518,10 @@ int run_first(cfr_handle *h, cfr_device_batch *b, cudaStream_t s) {
   if (h->params.dust) {
     StageScope sc(h, s, CFR_STAGE_DUST);
     launch_dust(h, B, s);
+  }
+  if (b->want_masked) {  // the reads as the searches see them, for the caller's --un / --cl files
+    k_apply_dust<<<grid_for(h, b->seq_bytes, 256, 8), 256, 0, s>>>(B, (unsigned char *)b->masked.p, b->seq_bytes);
+    ++h->launches;
   }
   CUDA_TRY(cudaMemsetAsync(B.task_counter, 0, 8, s));
   {
@@ -902,6 +912,7 @@ int cfr_classify_batch(cfr_handle *h, const cfr_read_batch *in, cfr_result *resu
       if ((st = pipeline_drain(h, slot, results + starts[slot], ids + starts[slot] * k, h->s_comp[slot]))) return st;
     }
     starts[slot] = r0;
+    b->want_masked = false;
     if ((st = upload_chunk(h, in, r0, r1, b, h->s_in))) return st;
     CUDA_TRY(cudaEventRecord(h->ev_h2d[slot], h->s_in));
     CUDA_TRY(cudaStreamWaitEvent(h->s_comp[slot], h->ev_h2d[slot], 0));
@@ -927,6 +938,11 @@ int cfr_classify_batch(cfr_handle *h, const cfr_read_batch *in, cfr_result *resu
 
 int cfr_submit_batch(cfr_handle *h, const cfr_read_batch *in, cfr_result *results, uint64_t *ids, void *stream,
                      int *ticket) {
+  return cfr_submit_batch_masked(h, in, results, ids, nullptr, nullptr, stream, ticket);
+}
+
+int cfr_submit_batch_masked(cfr_handle *h, const cfr_read_batch *in, cfr_result *results, uint64_t *ids,
+                            char *masked1, char *masked2, void *stream, int *ticket) {
   if (!h || !in || !ticket || (in->n_reads && (!results || !ids))) return fail(CFR_ERR_ARG, "null argument");
   if (in->n_reads && (!in->seq1 || !in->off1)) return fail(CFR_ERR_ARG, "seq1/off1 missing");
   const u64 cap = h->params.max_batch_reads > 0 ? (u64)h->params.max_batch_reads : (1ull << 20);
@@ -937,6 +953,7 @@ int cfr_submit_batch(cfr_handle *h, const cfr_read_batch *in, cfr_result *result
   const int slot = h->next_ticket % cfr_handle::NSLOT;
   if ((st = job_finish(h, slot))) return st;  // at most NSLOT batches in flight
   cfr_device_batch *b = &h->slots[slot];
+  b->want_masked = masked1 != nullptr;
   cudaStream_t sc = pick_stream(h, stream);
   CUDA_TRY(cudaEventRecord(h->ev_start, sc));  // ordered after the caller's stream
   CUDA_TRY(cudaStreamWaitEvent(h->s_in, h->ev_start, 0));
@@ -966,6 +983,13 @@ int cfr_submit_batch(cfr_handle *h, const cfr_read_batch *in, cfr_result *result
   if (in->n_reads) {
     CUDA_TRY(cudaMemcpyAsync(results, b->results.p, in->n_reads * sizeof(DevResult), cudaMemcpyDeviceToHost, h->s_out));
     CUDA_TRY(cudaMemcpyAsync(ids, b->out_ids.p, in->n_reads * k * 8, cudaMemcpyDeviceToHost, h->s_out));
+  }
+  if (b->want_masked && in->n_reads) {
+    const u64 len1 = in->off1[in->n_reads] - in->off1[0];
+    const u64 len2 = in->seq2 ? in->off2[in->n_reads] - in->off2[0] : 0;
+    if (len1) CUDA_TRY(cudaMemcpyAsync(masked1, b->masked.p, len1, cudaMemcpyDeviceToHost, h->s_out));
+    if (len2 && masked2)
+      CUDA_TRY(cudaMemcpyAsync(masked2, (char *)b->masked.p + ((len1 + 31) & ~31ull), len2, cudaMemcpyDeviceToHost, h->s_out));
   }
   CUDA_TRY(cudaMemcpyAsync(&h->pinned_scalars[slot], b->scalars.p, 16, cudaMemcpyDeviceToHost, h->s_out));
   CUDA_TRY(cudaEventRecord(h->ev_d2h[slot], h->s_out));

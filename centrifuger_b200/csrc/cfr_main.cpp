@@ -42,6 +42,8 @@ static const char usage[] =
     "Optional:\n"
     "\t-t INT: number of threads [1] (accepted for compatibility; the work runs on the GPU)\n"
     "\t-k INT: report upto <int> distinct, primary assignments for each read pair [1]\n"
+    "\t--un STR: output unclassified reads to files with the prefix of <str>\n"
+    "\t--cl STR: output classified reads to files with the prefix of <str>\n"
     "\t--no-dust: do not DUST-mask low-complexity regions of reads [mask]\n"
     "\t--min-hitlen INT: minimum length of partial hits [auto]\n"
     "\t--hitk-factor INT: resolve at most <int>*k entries for each hit [40; use 0 for no restriction]\n"
@@ -54,7 +56,7 @@ static const char usage[] =
 
 enum {
   ARGV_NO_DUST = 256, ARGV_MIN_HITLEN, ARGV_HITK, ARGV_SECONDARY, ARGV_GPU, ARGV_BATCH, ARGV_LAYOUT,
-  ARGV_UNSUPPORTED, ARGV_DRY_RUN
+  ARGV_UNSUPPORTED, ARGV_DRY_RUN, ARGV_UN, ARGV_CL
 };
 
 static const char *short_options = "x:1:2:u:i:o:t:k:hv";
@@ -67,8 +69,8 @@ static struct option long_options[] = {
     {"batch", required_argument, 0, ARGV_BATCH},
     {"layout", required_argument, 0, ARGV_LAYOUT},
     {"dry-run", no_argument, 0, ARGV_DRY_RUN},
-    {"un", required_argument, 0, ARGV_UNSUPPORTED},
-    {"cl", required_argument, 0, ARGV_UNSUPPORTED},
+    {"un", required_argument, 0, ARGV_UN},
+    {"cl", required_argument, 0, ARGV_CL},
     {"merge-readpair", no_argument, 0, ARGV_UNSUPPORTED},
     {"expand-taxid", no_argument, 0, ARGV_UNSUPPORTED},
     {"read-format", required_argument, 0, ARGV_UNSUPPORTED},
@@ -111,8 +113,9 @@ class SeqReader {
     if (fp_) gzclose(fp_);
     fp_ = nullptr;
   }
-  // appends the record's sequence to `seq`; returns false at end of file
-  bool next(std::string &name, std::string &seq) {
+  // appends the record's sequence to `seq` (and, for FASTQ records, its quality string to `qual` when
+  // given: a FASTA record appends nothing there); returns false at end of file
+  bool next(std::string &name, std::string &seq, std::string *qual = nullptr) {
     const char *ln;
     size_t n;
     // header line
@@ -139,6 +142,7 @@ class SeqReader {
     const size_t want = seq.size() - start;
     while (q < want) {  // quality lines (may start with '@' or '+'): by length
       if (!line(ln, n)) return true;
+      if (qual) qual->append(ln, n);
       q += n;
     }
     return true;
@@ -198,7 +202,7 @@ struct ReadSource {  // a list of files read back to back (ReadFiles::AddReadFil
   size_t cur = 0;
   bool opened = false;
   SeqReader rd;
-  bool next(std::string &name, std::string &seq) {
+  bool next(std::string &name, std::string &seq, std::string *qual = nullptr) {
     for (;;) {
       if (!opened) {
         if (cur >= files.size()) return false;
@@ -208,7 +212,7 @@ struct ReadSource {  // a list of files read back to back (ReadFiles::AddReadFil
         }
         opened = true;
       }
-      if (rd.next(name, seq)) return true;
+      if (rd.next(name, seq, qual)) return true;
       rd.close();
       opened = false;
       ++cur;
@@ -224,9 +228,17 @@ struct Batch {
   std::vector<uint64_t> off1, off2;
   std::vector<cfr_result> results;
   std::vector<uint64_t> assign;
+  // --un / --cl only: quality strings (empty for a FASTA record) and the reads as classified
+  // (DUST intervals as 'N'), which is what the reference writes (ResultWriter.hpp:244-262)
+  std::string qual1, qual2, masked1, masked2;
+  std::vector<uint64_t> qoff1, qoff2;
   size_t n = 0;
   bool last = false;
   void clear() {
+    qual1.clear();
+    qual2.clear();
+    qoff1.assign(1, 0);
+    qoff2.assign(1, 0);
     ids.clear();
     id_off.assign(1, 0);
     seq1.clear();
@@ -299,6 +311,7 @@ int main(int argc, char *argv[]) {
   bool hasMate = false, interleaved = false;
   int device = 0;
   long batchReads = 1 << 20;
+  const char *unPrefix = NULL, *clPrefix = NULL;  // --un / --cl
   bool dryRun = false;  // diagnostics: parse the inputs and print id<TAB>mate1<TAB>mate2, no GPU work
   int c, option_index = 0;
   while ((c = getopt_long(argc, argv, short_options, long_options, &option_index)) != -1) {
@@ -331,6 +344,8 @@ int main(int argc, char *argv[]) {
       else if (!strcmp(optarg, "runblock")) params.layout = CFR_LAYOUT_RUNBLOCK;
       else params.layout = CFR_LAYOUT_AUTO;
     } else if (c == ARGV_DRY_RUN) dryRun = true;
+    else if (c == ARGV_UN) unPrefix = optarg;
+    else if (c == ARGV_CL) clPrefix = optarg;
     else if (c == ARGV_UNSUPPORTED) {
       PrintLog("Option --%s is not supported by the B200 classification path.", long_options[option_index].name);
       return EXIT_FAILURE;
@@ -405,6 +420,21 @@ int main(int argc, char *argv[]) {
   for (auto &bt : batches) bt.clear();
   unsigned long totalCnt = 0, classifiedCnt = 0;
   bool mate_mismatch = false;
+  // --un / --cl (ResultWriter::SetOutputReads, ResultWriter.hpp:118-172): <prefix>_1.fq.gz / _2.fq.gz with
+  // mates, <prefix>.fq.gz without, gzip level 1
+  const bool keepReads = unPrefix != NULL || clPrefix != NULL;
+  gzFile readOut[2][2] = {{NULL, NULL}, {NULL, NULL}};  // [0 = unclassified, 1 = classified][mate]
+  for (int cat = 0; cat < 2; ++cat) {
+    const char *prefix = cat ? clPrefix : unPrefix;
+    if (!prefix) continue;
+    const std::string p(prefix);
+    readOut[cat][0] = gzopen((hasMate ? p + "_1.fq.gz" : p + ".fq.gz").c_str(), "w1");
+    if (hasMate) readOut[cat][1] = gzopen((p + "_2.fq.gz").c_str(), "w1");
+    if (!readOut[cat][0] || (hasMate && !readOut[cat][1])) {
+      PrintLog("ERROR: cannot open the read output files with prefix %s", prefix);
+      return EXIT_FAILURE;
+    }
+  }
 
   std::thread ingest([&] {
     std::string name, name2, tmp;
@@ -415,18 +445,21 @@ int main(int argc, char *argv[]) {
       bt->clear();
       while ((long)bt->n < batchReads) {
         name.clear();
-        if (!reads.next(name, bt->seq1)) break;
+        if (!reads.next(name, bt->seq1, keepReads ? &bt->qual1 : nullptr)) break;
         RemoveReadIdSuffix(name);
         bt->ids += name;
         bt->id_off.push_back((uint32_t)bt->ids.size());
         bt->off1.push_back(bt->seq1.size());
+        if (keepReads) bt->qoff1.push_back(bt->qual1.size());
         if (hasMate) {
-          const bool ok = interleaved ? reads.next(name2, bt->seq2) : mates.next(name2, bt->seq2);
+          std::string *q2 = keepReads ? &bt->qual2 : nullptr;
+          const bool ok = interleaved ? reads.next(name2, bt->seq2, q2) : mates.next(name2, bt->seq2, q2);
           if (!ok) {
             mate_mismatch = true;
             break;
           }
           bt->off2.push_back(bt->seq2.size());
+          if (keepReads) bt->qoff2.push_back(bt->qual2.size());
         }
         ++bt->n;
       }
@@ -441,7 +474,7 @@ int main(int argc, char *argv[]) {
   });
 
   std::thread output([&] {
-    std::string out;
+    std::string out, rec;
     out.reserve(64 << 20);
     // ResultWriter::OutputHeader (ResultWriter.hpp:186-197)
     out += "readID\tseqID\ttaxID\tscore\t2ndBestScore\thitLength\tqueryLength\tnumMatches\n";
@@ -488,6 +521,29 @@ int main(int argc, char *argv[]) {
           fwrite(out.data(), 1, out.size(), stdout);
           out.clear();
         }
+        if (keepReads) {  // ResultWriter::Output, ResultWriter.hpp:244-262
+          const int cat = r.n_assign > 0 ? 1 : 0;
+          if (readOut[cat][0]) {
+            for (int m = 0; m < (hasMate ? 2 : 1); ++m) {
+              const std::string &ms = m ? bt->masked2 : bt->masked1, &qs = m ? bt->qual2 : bt->qual1;
+              const std::vector<uint64_t> &so = m ? bt->off2 : bt->off1, &qo = m ? bt->qoff2 : bt->qoff1;
+              const size_t sl = (size_t)(so[i + 1] - so[i]), ql = (size_t)(qo[i + 1] - qo[i]);
+              const bool fq = ql > 0;  // qual == NULL iff kseq saw no quality string (ReadFiles.hpp:326-329)
+              rec.clear();
+              rec += fq ? '@' : '>';
+              rec.append(id, idn);
+              rec += '\n';
+              rec.append(ms, (size_t)so[i], sl);
+              rec += '\n';
+              if (fq) {
+                rec += "+\n";
+                rec.append(qs, (size_t)qo[i], ql);
+                rec += '\n';
+              }
+              gzwrite(readOut[cat][m], rec.data(), (unsigned)rec.size());
+            }
+          }
+        }
       }
       const bool last = bt->last;
       free_slots[bi].put(bt);
@@ -526,7 +582,14 @@ int main(int argc, char *argv[]) {
       b.seq2 = hasMate ? bt->seq2.data() : NULL;
       b.off2 = hasMate ? bt->off2.data() : NULL;
       // streaming form: this batch's upload overlaps the previous batches' kernels
-      st = cfr_submit_batch(h, &b, bt->results.data(), bt->assign.data(), NULL, &ticket);
+      if (keepReads) {
+        bt->masked1.resize(bt->seq1.size());
+        bt->masked2.resize(bt->seq2.size());
+        st = cfr_submit_batch_masked(h, &b, bt->results.data(), bt->assign.data(), &bt->masked1[0],
+                                     hasMate ? &bt->masked2[0] : NULL, NULL, &ticket);
+      } else {
+        st = cfr_submit_batch(h, &b, bt->results.data(), bt->assign.data(), NULL, &ticket);
+      }
       if (st != CFR_OK) {
         PrintLog("ERROR: %s", cfr_last_error());
         rc = EXIT_FAILURE;
@@ -542,6 +605,9 @@ int main(int argc, char *argv[]) {
   }
   ingest.join();
   output.join();
+  for (int cat = 0; cat < 2; ++cat)
+    for (int m = 0; m < 2; ++m)
+      if (readOut[cat][m]) gzclose(readOut[cat][m]);
   if (mate_mismatch) {
     PrintLog("ERROR: The two mate-pair read files have different number of reads.");  // CentrifugerClass.cpp:121-125
     return EXIT_FAILURE;

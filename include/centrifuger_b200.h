@@ -123,6 +123,14 @@ int cfr_submit_batch(cfr_handle *h, const cfr_read_batch *in, cfr_result *result
                      int *ticket);
 int cfr_wait_batch(cfr_handle *h, int ticket);
 
+/* cfr_submit_batch that also returns the reads as Classifier::Query saw them: the bytes of seq1 / seq2
+ * with the DUST-masked intervals replaced by 'N' (CentrifugerClass.cpp:276-316 masks the reads in
+ * place, and ResultWriter::Output writes those to the --un / --cl files, ResultWriter.hpp:244-262).
+ * masked1 / masked2 (host, as large as this batch's seq1 / seq2 bytes; masked2 may be NULL without
+ * mates) are filled when cfr_wait_batch(ticket) returns. */
+int cfr_submit_batch_masked(cfr_handle *h, const cfr_read_batch *in, cfr_result *results, uint64_t *ids,
+                            char *masked1, char *masked2, void *stream, int *ticket);
+
 /* Same work with the batch already resident in HBM (kernel-only timing;
  * multi-GPU shards).  upload = H2D + layout; classify_resident = kernels
  * only, asynchronous on `stream`; fetch = D2H + synchronize. */

@@ -274,6 +274,45 @@ def test_cli_binary_reproduces_reference_tsv(tiny_dir, manifest):
     assert r.stdout.decode().strip() == "Centrifuger v1.1.3-r347"
 
 
+def test_masked_reads_come_back(tiny_dir):
+    """cfr_submit_batch_masked returns the reads as Classifier::Query saw them = the oracle's DUST mask"""
+    idx = os.path.join(tiny_dir, "idx")
+    _, r1 = read_fastx(os.path.join(tiny_dir, "edge_1.fq"))
+    _, r2 = read_fastx(os.path.join(tiny_dir, "edge_2.fq"))
+    r1 = r1 + [b"A" * 100, b"AC" * 60, b"ACGTTGCA" * 12 + b"A" * 30]
+    r2 = r2 + [b"ACGTTGCA" * 12 + b"T" * 30, b"acgtNNNN" * 10, b"G" * 7]
+    g = cb.Classifier(idx, k=5)
+    res, ids, m1, m2 = g.classify_masked(r1, r2)
+    exp = g.classify(r1, r2)
+    assert np.array_equal(res, exp[0]) and np.array_equal(ids, exp[1])
+    assert m1 == [dust_mask(x) for x in r1] and m2 == [dust_mask(x) for x in r2]
+    g.close()
+    g = cb.Classifier(idx, dust=False)
+    _, _, m1, m2 = g.classify_masked(r1, r2)
+    assert m1 == list(r1) and m2 == list(r2)
+    g.close()
+
+
+def test_cli_un_cl_read_outputs(tiny_dir, manifest, tmp_path):
+    """--un / --cl: the files of unclassified / classified reads (DUST-masked as classified, FASTQ or
+    FASTA like the input, read ids as printed) decompress to what the reference binary writes"""
+    import gzip
+    import subprocess
+    exe = os.path.join(os.path.dirname(cb.LIB_PATH), "centrifuger-b200")
+    for name, m in manifest["reads_out"].items():
+        od = tmp_path / name
+        od.mkdir()
+        files = [golden_path("tiny", f) for f in m["files"]]
+        cmd = [exe, "-x", os.path.join(tiny_dir, "idx"), "--batch", "53"]
+        cmd += ["-u", files[0]] if len(files) == 1 else ["-1", files[0], "-2", files[1]]
+        cmd += m["args"] + ["--un", str(od / "un"), "--cl", str(od / "cl")]
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+        assert r.returncode == 0, r.stderr.decode()
+        assert hashlib.md5(r.stdout).hexdigest() == m["tsv_md5"], name
+        got = {f: hashlib.md5(gzip.open(str(od / f), "rb").read()).hexdigest() for f in sorted(os.listdir(str(od)))}
+        assert got == m["outputs"], name
+
+
 def test_kernel_variants_vs_oracle(small_dir, variant_env):
     """every kernel variant gives the oracle's answers and operation counts (occ-sector layout)"""
     idx = os.path.join(small_dir, "idx")
