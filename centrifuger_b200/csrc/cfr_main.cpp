@@ -44,6 +44,7 @@ static const char usage[] =
     "\t-k INT: report upto <int> distinct, primary assignments for each read pair [1]\n"
     "\t--un STR: output unclassified reads to files with the prefix of <str>\n"
     "\t--cl STR: output classified reads to files with the prefix of <str>\n"
+    "\t--merge-readpair: merge overlapped paired-end reads and trim adapters [no merge]\n"
     "\t--no-dust: do not DUST-mask low-complexity regions of reads [mask]\n"
     "\t--min-hitlen INT: minimum length of partial hits [auto]\n"
     "\t--hitk-factor INT: resolve at most <int>*k entries for each hit [40; use 0 for no restriction]\n"
@@ -56,7 +57,7 @@ static const char usage[] =
 
 enum {
   ARGV_NO_DUST = 256, ARGV_MIN_HITLEN, ARGV_HITK, ARGV_SECONDARY, ARGV_GPU, ARGV_BATCH, ARGV_LAYOUT,
-  ARGV_UNSUPPORTED, ARGV_DRY_RUN, ARGV_UN, ARGV_CL
+  ARGV_UNSUPPORTED, ARGV_DRY_RUN, ARGV_UN, ARGV_CL, ARGV_MERGE
 };
 
 static const char *short_options = "x:1:2:u:i:o:t:k:hv";
@@ -71,7 +72,7 @@ static struct option long_options[] = {
     {"dry-run", no_argument, 0, ARGV_DRY_RUN},
     {"un", required_argument, 0, ARGV_UN},
     {"cl", required_argument, 0, ARGV_CL},
-    {"merge-readpair", no_argument, 0, ARGV_UNSUPPORTED},
+    {"merge-readpair", no_argument, 0, ARGV_MERGE},
     {"expand-taxid", no_argument, 0, ARGV_UNSUPPORTED},
     {"read-format", required_argument, 0, ARGV_UNSUPPORTED},
     {"barcode", required_argument, 0, ARGV_UNSUPPORTED},
@@ -220,6 +221,111 @@ struct ReadSource {  // a list of files read back to back (ReadFiles::AddReadFil
   }
 };
 
+// ReadPairMerger (ReadPairMerger.hpp), host side: --merge-readpair merges or trims a pair before it is
+// classified (CentrifugerClass.cpp:271-272); a merged pair is classified as ONE read (Query(rm, NULL),
+// :323-333).  Literal port on (pointer, length) strings.
+struct PairMerger {
+  // IsMateOverlap (ReadPairMerger.hpp:14-84)
+  static int IsMateOverlap(const char *fr, int flen, const char *sr, int slen, int minOverlap, int &offset,
+                           int &bestMatchCnt, bool checkTandem) {
+    int i, j, k;
+    bestMatchCnt = -1;
+    int offsetCnt = 0;
+    int overlapSize = -1;
+    for (j = 0; j < flen - minOverlap; ++j) {  // the overlap start position in the first read
+      int matchCnt = 0;
+      bool flag = true;
+      double similarityThreshold = 0.95;
+      if (flen - j >= 100)
+        similarityThreshold = 0.85;
+      else if (flen - j >= 50)
+        similarityThreshold = 0.85 + (flen - j - 50) / 50.0 * 0.1;
+      for (k = 0; j + k < flen && k < slen; ++k) {
+        if (fr[j + k] == sr[k]) ++matchCnt;
+        if (matchCnt + (flen - (j + k) - 1) < int((flen - j) * similarityThreshold)) {
+          flag = false;
+          break;
+        }
+      }
+      if (flag) {
+        offset = j;
+        ++offsetCnt;
+        overlapSize = k;
+        bestMatchCnt = matchCnt;
+      }
+    }
+    if (offsetCnt != 1) return -1;
+    if (checkTandem && overlapSize <= minOverlap * 2) {  // a short overlap inside a tandem repeat is ambiguous
+      for (i = 1; i <= overlapSize / 2; ++i) {
+        bool tandem = true;
+        for (j = i; j + i - 1 < overlapSize; j += i) {
+          for (k = j; k <= j + i - 1; ++k)
+            if (sr[k - j] != sr[k]) break;
+          if (k <= j + i - 1) {
+            tandem = false;
+            break;
+          }
+        }
+        if (tandem) return -1;
+      }
+    }
+    return overlapSize;
+  }
+
+  static char Comp(char c) { return c == 'A' ? 'T' : c == 'C' ? 'G' : c == 'G' ? 'C' : c == 'T' ? 'A' : 'N'; }
+
+  // Merge (ReadPairMerger.hpp:132-235): 0 no merge, 1 overlap merge, 2 read-through trim; q1/q2 may be
+  // NULL (FASTA).  rm / qm receive the merged read and its qualities.
+  static int Merge(const char *r1, const char *q1, int len1, const char *r2, const char *q2, int len2, std::string &rm,
+                   std::string &qm) {
+    rm.clear();
+    qm.clear();
+    std::string rcr2(r2, (size_t)len2), rcq2;
+    std::reverse(rcr2.begin(), rcr2.end());
+    for (char &c : rcr2) c = Comp(c);
+    if (q2) {
+      rcq2.assign(q2, (size_t)len2);
+      std::reverse(rcq2.begin(), rcq2.end());
+    }
+    int minOverlap = (len1 + len2) / 10;
+    if (minOverlap > 31) minOverlap = 31;
+    const int minOverlap2 = minOverlap;
+    int offset = -1, bestMatchCnt = -1;
+    int overlapSize = IsMateOverlap(rcr2.data(), len2, r1, len1, minOverlap, offset, bestMatchCnt, false);  // read through
+    if (overlapSize >= 0) {
+      rm.assign(r1, (size_t)overlapSize);
+      if (q1) {
+        qm.assign(q1, (size_t)overlapSize);
+        for (int i = 0; i < overlapSize; ++i)
+          if (rcq2[(size_t)(i + offset)] > q1[i] || rm[(size_t)i] == 'N') {
+            rm[(size_t)i] = rcr2[(size_t)(i + offset)];
+            qm[(size_t)i] = rcq2[(size_t)(i + offset)];
+          }
+      }
+      return 2;
+    }
+    overlapSize = IsMateOverlap(r1, len1, rcr2.data(), len2, minOverlap2, offset, bestMatchCnt, true);  // simple overlap
+    if (overlapSize >= 0) {
+      const int len = offset + len2;  // (r2 may be a substring of r1)
+      rm.assign((size_t)std::max(len, len1 + len2 - overlapSize), 'N');
+      if (q2) qm.assign(rm.size(), '!');
+      for (int i = 0; i < len2; ++i) {
+        rm[(size_t)(offset + i)] = rcr2[(size_t)i];
+        if (q2) qm[(size_t)(offset + i)] = rcq2[(size_t)i];
+      }
+      for (int i = 0; i < len1 && i < len; ++i)
+        if (i < offset || (q1 != NULL && q1[i] >= qm[(size_t)i] - 14) || rm[(size_t)i] == 'N') {
+          rm[(size_t)i] = r1[i];
+          if (q1) qm[(size_t)i] = q1[i];
+        }
+      rm.resize((size_t)len);
+      if (q2) qm.resize((size_t)len);
+      return 1;
+    }
+    return 0;
+  }
+};
+
 // One batch travelling through the ingest -> classify -> output pipeline.
 struct Batch {
   std::string ids;              // read ids back to back
@@ -232,9 +338,17 @@ struct Batch {
   // (DUST intervals as 'N'), which is what the reference writes (ResultWriter.hpp:244-262)
   std::string qual1, qual2, masked1, masked2;
   std::vector<uint64_t> qoff1, qoff2;
+  // --merge-readpair: merged[i] != 0 when pair i is classified as one merged read (seq1 holds it, its
+  // mate-2 slot is empty); orig1 / orig2 keep the pairs as read, which is what --un / --cl write for them
+  std::vector<uint8_t> merged;
+  std::string orig1, orig2;
+  std::vector<uint64_t> ooff1, ooff2;
   size_t n = 0;
   bool last = false;
   void clear() {
+    merged.clear();
+    orig1.clear();
+    orig2.clear();
     qual1.clear();
     qual2.clear();
     qoff1.assign(1, 0);
@@ -299,6 +413,50 @@ static inline char *put_str(char *p, const char *s, size_t n) {
   return p + n;
 }
 
+// --merge-readpair over one parsed batch (host threads): pair i becomes (merged read, empty mate) when
+// ReadPairMerger::Merge succeeds.  The originals move to orig1 / orig2.
+static void MergeBatch(Batch &bt, bool haveQual, unsigned nthreads) {
+  const size_t n = bt.n;
+  std::vector<std::string> rms(n), qms(n);
+  bt.merged.assign(n, 0);
+  auto work = [&](size_t lo, size_t hi) {
+    for (size_t i = lo; i < hi; ++i) {
+      const int l1 = (int)(bt.off1[i + 1] - bt.off1[i]), l2 = (int)(bt.off2[i + 1] - bt.off2[i]);
+      const bool q = haveQual && bt.qoff1[i + 1] - bt.qoff1[i] == (uint64_t)l1 && bt.qoff2[i + 1] - bt.qoff2[i] == (uint64_t)l2 &&
+                     l1 > 0 && l2 > 0;
+      bt.merged[i] = (uint8_t)PairMerger::Merge(bt.seq1.data() + bt.off1[i], q ? bt.qual1.data() + bt.qoff1[i] : NULL, l1,
+                                                bt.seq2.data() + bt.off2[i], q ? bt.qual2.data() + bt.qoff2[i] : NULL, l2,
+                                                rms[i], qms[i]);
+    }
+  };
+  if (nthreads < 1) nthreads = 1;
+  std::vector<std::thread> pool;
+  const size_t per = (n + nthreads - 1) / nthreads;
+  for (unsigned t = 0; t < nthreads; ++t) {
+    const size_t lo = t * per, hi = std::min(n, lo + per);
+    if (lo < hi) pool.emplace_back(work, lo, hi);
+  }
+  for (auto &th : pool) th.join();
+  bt.orig1.swap(bt.seq1);
+  bt.orig2.swap(bt.seq2);
+  bt.ooff1.swap(bt.off1);
+  bt.ooff2.swap(bt.off2);
+  bt.seq1.clear();
+  bt.seq2.clear();
+  bt.off1.assign(1, 0);
+  bt.off2.assign(1, 0);
+  for (size_t i = 0; i < n; ++i) {
+    if (bt.merged[i]) {
+      bt.seq1 += rms[i];
+    } else {
+      bt.seq1.append(bt.orig1, (size_t)bt.ooff1[i], (size_t)(bt.ooff1[i + 1] - bt.ooff1[i]));
+      bt.seq2.append(bt.orig2, (size_t)bt.ooff2[i], (size_t)(bt.ooff2[i + 1] - bt.ooff2[i]));
+    }
+    bt.off1.push_back(bt.seq1.size());
+    bt.off2.push_back(bt.seq2.size());
+  }
+}
+
 int main(int argc, char *argv[]) {
   if (argc <= 1) {  // CentrifugerClass.cpp:347-351: usage on stderr, exit 0
     fprintf(stderr, "%s", usage);
@@ -312,6 +470,7 @@ int main(int argc, char *argv[]) {
   int device = 0;
   long batchReads = 1 << 20;
   const char *unPrefix = NULL, *clPrefix = NULL;  // --un / --cl
+  bool mergePairs = false;                        // --merge-readpair
   bool dryRun = false;  // diagnostics: parse the inputs and print id<TAB>mate1<TAB>mate2, no GPU work
   int c, option_index = 0;
   while ((c = getopt_long(argc, argv, short_options, long_options, &option_index)) != -1) {
@@ -344,6 +503,7 @@ int main(int argc, char *argv[]) {
       else if (!strcmp(optarg, "runblock")) params.layout = CFR_LAYOUT_RUNBLOCK;
       else params.layout = CFR_LAYOUT_AUTO;
     } else if (c == ARGV_DRY_RUN) dryRun = true;
+    else if (c == ARGV_MERGE) mergePairs = true;
     else if (c == ARGV_UN) unPrefix = optarg;
     else if (c == ARGV_CL) clPrefix = optarg;
     else if (c == ARGV_UNSUPPORTED) {
@@ -355,18 +515,28 @@ int main(int argc, char *argv[]) {
     }
   }
   if (dryRun) {
-    std::string name, name2, s1, s2;
+    std::string name, name2, s1, s2, q1, q2;
     for (;;) {
       name.clear();
       s1.clear();
       s2.clear();
-      if (!reads.next(name, s1)) break;
+      q1.clear();
+      q2.clear();
+      if (!reads.next(name, s1, &q1)) break;
       RemoveReadIdSuffix(name);
-      if (hasMate && !(interleaved ? reads.next(name2, s2) : mates.next(name2, s2))) {
+      if (hasMate && !(interleaved ? reads.next(name2, s2, &q2) : mates.next(name2, s2, &q2))) {
         PrintLog("ERROR: The two mate-pair read files have different number of reads.");
         return EXIT_FAILURE;
       }
-      printf("%s\t%s\t%s\n", name.c_str(), s1.c_str(), s2.c_str());
+      if (mergePairs && hasMate) {  // diagnostics for --merge-readpair: code, merged read, merged qualities
+        std::string rm, qm;
+        const bool q = q1.size() == s1.size() && q2.size() == s2.size() && !s1.empty() && !s2.empty();
+        const int code = PairMerger::Merge(s1.data(), q ? q1.data() : NULL, (int)s1.size(), s2.data(), q ? q2.data() : NULL,
+                                           (int)s2.size(), rm, qm);
+        printf("%d\t%s\t%s\n", code, rm.c_str(), qm.c_str());
+      } else {
+        printf("%s\t%s\t%s\n", name.c_str(), s1.c_str(), s2.c_str());
+      }
     }
     return 0;
   }
@@ -422,7 +592,8 @@ int main(int argc, char *argv[]) {
   bool mate_mismatch = false;
   // --un / --cl (ResultWriter::SetOutputReads, ResultWriter.hpp:118-172): <prefix>_1.fq.gz / _2.fq.gz with
   // mates, <prefix>.fq.gz without, gzip level 1
-  const bool keepReads = unPrefix != NULL || clPrefix != NULL;
+  const bool writeReads = unPrefix != NULL || clPrefix != NULL;
+  const bool keepReads = writeReads || mergePairs;  // qualities are parsed: --un / --cl print them, the merger reads them
   gzFile readOut[2][2] = {{NULL, NULL}, {NULL, NULL}};  // [0 = unclassified, 1 = classified][mate]
   for (int cat = 0; cat < 2; ++cat) {
     const char *prefix = cat ? clPrefix : unPrefix;
@@ -468,6 +639,7 @@ int main(int argc, char *argv[]) {
         if (mates.next(name2, tmp)) mate_mismatch = true;  // mate 1 ended first
       }
       bt->last = (long)bt->n < batchReads || mate_mismatch;
+      if (mergePairs && hasMate && bt->n) MergeBatch(*bt, true, std::thread::hardware_concurrency());
       to_gpu.put(bt);
       if (bt->last) break;
     }
@@ -521,12 +693,16 @@ int main(int argc, char *argv[]) {
           fwrite(out.data(), 1, out.size(), stdout);
           out.clear();
         }
-        if (keepReads) {  // ResultWriter::Output, ResultWriter.hpp:244-262
+        if (writeReads) {  // ResultWriter::Output, ResultWriter.hpp:244-262
           const int cat = r.n_assign > 0 ? 1 : 0;
           if (readOut[cat][0]) {
+            // a merged pair was masked and classified as the merged read: its two reads are written as read
+            const bool asRead = !bt->merged.empty() && bt->merged[i];
             for (int m = 0; m < (hasMate ? 2 : 1); ++m) {
-              const std::string &ms = m ? bt->masked2 : bt->masked1, &qs = m ? bt->qual2 : bt->qual1;
-              const std::vector<uint64_t> &so = m ? bt->off2 : bt->off1, &qo = m ? bt->qoff2 : bt->qoff1;
+              const std::string &ms = asRead ? (m ? bt->orig2 : bt->orig1) : (m ? bt->masked2 : bt->masked1);
+              const std::vector<uint64_t> &so = asRead ? (m ? bt->ooff2 : bt->ooff1) : (m ? bt->off2 : bt->off1);
+              const std::string &qs = m ? bt->qual2 : bt->qual1;
+              const std::vector<uint64_t> &qo = m ? bt->qoff2 : bt->qoff1;
               const size_t sl = (size_t)(so[i + 1] - so[i]), ql = (size_t)(qo[i + 1] - qo[i]);
               const bool fq = ql > 0;  // qual == NULL iff kseq saw no quality string (ReadFiles.hpp:326-329)
               rec.clear();
@@ -582,7 +758,7 @@ int main(int argc, char *argv[]) {
       b.seq2 = hasMate ? bt->seq2.data() : NULL;
       b.off2 = hasMate ? bt->off2.data() : NULL;
       // streaming form: this batch's upload overlaps the previous batches' kernels
-      if (keepReads) {
+      if (writeReads) {
         bt->masked1.resize(bt->seq1.size());
         bt->masked2.resize(bt->seq2.size());
         st = cfr_submit_batch_masked(h, &b, bt->results.data(), bt->assign.data(), &bt->masked1[0],

@@ -18,13 +18,50 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 REF = os.path.join(ROOT, "oracle", "_ref", "centrifuger")
 
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+
 CASES = {
     "pe_default": (["pe_100_1.fq", "pe_100_2.fq"], []),
     "edgepe_k5": (["edge_1.fq", "edge_2.fq"], ["-k", "5"]),
     "edge_se_default": (["edge.fq"], []),
     "edge_se_nodust": (["edge.fq"], ["--no-dust"]),
     "fasta_se_default": (["se_100.fa"], []),
+    # --merge-readpair (ReadPairMerger.hpp): pairs whose inserts are shorter than two reads
+    "overlap_merge": (["ov_1.fq", "ov_2.fq"], ["--merge-readpair"]),
+    "overlap_merge_k5_nodust": (["ov_1.fq", "ov_2.fq"], ["--merge-readpair", "-k", "5", "--no-dust"]),
+    "overlap_nomerge": (["ov_1.fq", "ov_2.fq"], []),
 }
+
+
+def write_overlapping_pairs(tg):
+    """200 pairs of 100-bp reads with inserts of 40..260 bp from the tiny collection (read-through, overlap,
+    no overlap), 1 % errors, mixed qualities, a few low-complexity fragments"""
+    import numpy as np
+    import gen_data
+    import make_data
+    genomes, _, _ = gen_data.make_genomes(seed=1, **make_data.DATASETS["tiny"]["genomes"])
+    rng = np.random.default_rng(77)
+    comp = {65: 84, 67: 71, 71: 67, 84: 65}
+    adapter = bytes(rng.choice(list(b"ACGT"), size=100).tolist())
+    with open(os.path.join(tg, "ov_1.fq"), "wb") as f1, open(os.path.join(tg, "ov_2.fq"), "wb") as f2:
+        for i in range(200):
+            g = gen_data.ACGT[genomes[int(rng.integers(len(genomes)))][2]].tobytes()
+            ins = int(rng.integers(40, 261))
+            p = int(rng.integers(0, len(g) - ins))
+            frag = g[p:p + ins]
+            if i % 23 == 0:
+                frag = (b"AC" * 200)[:ins]
+            rc = bytes(comp[c] for c in reversed(frag))
+            r = []
+            for s in ((frag + adapter)[:100], (rc + adapter)[:100]):
+                s = bytearray(s)
+                for q in range(100):
+                    if rng.random() < 0.01:
+                        s[q] = int(rng.choice(list(b"ACGTN")))
+                r.append(bytes(s))
+            qs = [bytes(rng.choice(list(b"#5?FI"), size=100).tolist()) for _ in range(2)]
+            f1.write(b"@ov%d/1\n%s\n+\n%s\n" % (i, r[0], qs[0]))
+            f2.write(b"@ov%d/2\n%s\n+\n%s\n" % (i, r[1], qs[1]))
 
 
 def unpack_index(dst):
@@ -51,6 +88,7 @@ def main():
         lines = fi.read().splitlines()
         for i in range(0, min(len(lines), 4 * 120), 4):
             fo.write(">" + lines[i][1:] + "\n" + lines[i + 1] + "\n")
+    write_overlapping_pairs(tg)
     manifest = json.load(open(os.path.join(HERE, "MANIFEST.json")))
     manifest["reads_out"] = {}
     d = tempfile.mkdtemp(prefix="cfr_golden_")

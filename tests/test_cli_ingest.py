@@ -61,7 +61,68 @@ def test_usage_and_version_and_rejections():
     r = subprocess.run([EXE], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
     assert r.returncode == 0 and b"-x FILE: index prefix" in r.stderr  # CentrifugerClass.cpp:347-351
     assert subprocess.run([EXE, "-v"], stdout=subprocess.PIPE).stdout.decode().strip() == "Centrifuger v1.1.3-r347"
-    r = subprocess.run([EXE, "-x", "nope", "-u", "x.fq", "--merge-readpair"], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    r = subprocess.run([EXE, "-x", "nope", "-u", "x.fq", "--expand-taxid"], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
     assert r.returncode != 0 and b"not supported" in r.stderr
     r = subprocess.run([EXE, "-u", "x.fq"], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
     assert r.returncode != 0 and b"Need to use -x" in r.stderr
+
+
+def _rc(s):
+    return bytes({65: 84, 67: 71, 71: 67, 84: 65}.get(c, 78) for c in reversed(s))
+
+
+def test_merge_readpair_port_matches_reference_merger(tmp_path):
+    """--merge-readpair: the CLI's port of ReadPairMerger::Merge against the UNMODIFIED reference header
+    (oracle/_ref/merge_ref, built by oracle/Makefile) on pairs with every kind of overlap: read-through
+    (insert shorter than the reads), plain overlaps with mismatches and quality conflicts, tandem
+    repeats near the minimum overlap, no overlap, Ns; FASTQ and FASTA."""
+    import random
+    ref = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "merge_ref")
+    if not os.path.exists(ref):
+        pytest.skip("oracle/_ref/merge_ref not built")
+    rng = random.Random(41)
+    pairs = []
+    for it in range(1500):
+        rl = rng.choice([50, 75, 100, 150])
+        mode = rng.random()
+        if mode < 0.25:
+            ins = rng.randint(20, rl)                       # read-through: adapters behind the insert
+        elif mode < 0.75:
+            ins = rng.randint(rl, 2 * rl + 10)              # overlap of 0..rl bases
+        else:
+            ins = rng.randint(2 * rl + 10, 3 * rl)          # no overlap
+        if rng.random() < 0.15:                             # tandem repeat fragment
+            unit = bytes(rng.choice(b"ACGT") for _ in range(rng.randint(1, 6)))
+            frag = (unit * (ins // len(unit) + 2))[:ins]
+        else:
+            frag = bytes(rng.choice(b"ACGT") for _ in range(ins))
+        adapter = bytes(rng.choice(b"ACGT") for _ in range(rl))
+        r1 = bytearray((frag + adapter)[:rl])
+        r2 = bytearray((_rc(frag) + adapter)[:rl])
+        for r in (r1, r2):
+            for p in range(len(r)):
+                x = rng.random()
+                if x < 0.02:
+                    r[p] = rng.choice(b"ACGT")
+                elif x < 0.025:
+                    r[p] = ord("N")
+        q1 = bytes(rng.choice(b"#5?FI") for _ in range(len(r1)))
+        q2 = bytes(rng.choice(b"#5?FI") for _ in range(len(r2)))
+        pairs.append((bytes(r1), q1, bytes(r2), q2))
+    for fastq in (True, False):
+        f1, f2 = tmp_path / ("m_1.f%s" % ("q" if fastq else "a")), tmp_path / ("m_2.f%s" % ("q" if fastq else "a"))
+        with open(f1, "wb") as a, open(f2, "wb") as b:
+            for i, (r1, q1, r2, q2) in enumerate(pairs):
+                if fastq:
+                    a.write(b"@p%d/1\n%s\n+\n%s\n" % (i, r1, q1))
+                    b.write(b"@p%d/2\n%s\n+\n%s\n" % (i, r2, q2))
+                else:
+                    a.write(b">p%d/1\n%s\n" % (i, r1))
+                    b.write(b">p%d/2\n%s\n" % (i, r2))
+        got = subprocess.run([EXE, "--dry-run", "--merge-readpair", "-1", str(f1), "-2", str(f2)], stdout=subprocess.PIPE,
+                             check=True).stdout
+        inp = b"".join(b"%s\t%s\t%s\t%s\n" % (r1, q1 if fastq else b"-", r2, q2 if fastq else b"-") for r1, q1, r2, q2 in pairs)
+        exp = subprocess.run([ref], input=inp, stdout=subprocess.PIPE, check=True).stdout
+        assert got == exp
+        codes = [l.split(b"\t")[0] for l in exp.splitlines()]
+        assert codes.count(b"1") > 100 and codes.count(b"2") > 100 and codes.count(b"0") > 100
