@@ -610,13 +610,19 @@ int main(int argc, char *argv[]) {
   std::thread ingest([&] {
     std::string name, name2, tmp;
     int bi = 0;
+    bool eof = false;
     for (;;) {
       Batch *bt = free_slots[bi].take();
       bi = (bi + 1) % NBATCH;
       bt->clear();
-      while ((long)bt->n < batchReads) {
+      // a batch ends after batchReads reads or 2^29 bases, whichever comes first (long reads: the device work
+      // areas grow with the bases and with the longest read of a batch)
+      while ((long)bt->n < batchReads && bt->seq1.size() + bt->seq2.size() < (512u << 20)) {
         name.clear();
-        if (!reads.next(name, bt->seq1, keepReads ? &bt->qual1 : nullptr)) break;
+        if (!reads.next(name, bt->seq1, keepReads ? &bt->qual1 : nullptr)) {
+          eof = true;
+          break;
+        }
         RemoveReadIdSuffix(name);
         bt->ids += name;
         bt->id_off.push_back((uint32_t)bt->ids.size());
@@ -634,11 +640,11 @@ int main(int argc, char *argv[]) {
         }
         ++bt->n;
       }
-      if (!mate_mismatch && hasMate && !interleaved && (long)bt->n < batchReads) {
+      if (!mate_mismatch && hasMate && !interleaved && eof) {
         tmp.clear();
         if (mates.next(name2, tmp)) mate_mismatch = true;  // mate 1 ended first
       }
-      bt->last = (long)bt->n < batchReads || mate_mismatch;
+      bt->last = eof || mate_mismatch;
       if (mergePairs && hasMate && bt->n) MergeBatch(*bt, true, std::thread::hardware_concurrency());
       to_gpu.put(bt);
       if (bt->last) break;
