@@ -46,7 +46,7 @@ WORKLOADS = {
     "small1m": dict(dataset="small", reads=1_000_000, rlen=100, paired=False, k=1,
                     desc="synthetic 10 Mbp / 100-sequence index (occ sectors 5 MB), 1M x 100 bp single-end reads"),
     "m700": dict(dataset="m700", reads=1_000_000, rlen=100, paired=False, k=1,
-                 desc="synthetic 700 Mbp / 175-taxa index (occ lines 350 MB > L2), 1M x 100 bp single-end reads"),
+                 desc="synthetic 700 Mbp / 175-taxa index (occ sectors 350 MB > L2), 1M x 100 bp single-end reads"),
     "m700pe": dict(dataset="m700", reads=500_000, rlen=150, paired=True, k=5,
                    desc="synthetic 700 Mbp / 175-taxa index, 500k x 2x150 bp pairs per step, -k 5"),
     "c3": dict(dataset="c3", reads=1_000_000, rlen=150, paired=True, k=5,
@@ -208,7 +208,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
-    ap.add_argument("--layout", type=int, default=0, help="0 auto, 1 run-block arrays, 2 occ lines")
+    ap.add_argument("--layout", type=int, default=0, help="0 auto, 1 run-block arrays, 2 occ sectors")
     ap.add_argument("--reads", type=int, default=0, help="override reads per step per GPU")
     ap.add_argument("--cpu-sample", type=int, default=0, help="reads in the CPU-baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

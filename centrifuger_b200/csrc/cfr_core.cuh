@@ -374,7 +374,7 @@ struct BwtRunBlock {
 };
 
 // ---------------------------------------------------------------------------
-// Layout 2: 64-byte occ lines (128 symbols + 4 absolute counters per line)
+// Layout 2: 32-byte occ sectors (64 symbols + the counts of A, C, G before them)
 // ---------------------------------------------------------------------------
 
 // occ(c, x) = # of symbol c in BWT[0..x), x in [0, n]: ONE 32-byte sector.

@@ -1,16 +1,19 @@
 // cfr_pipeline.cuh -- the stages of one classification pass over a read chunk.
 //
-// Stage          unit of work                 reference code it replaces
-//   dust_stage     one mate                     CentrifugerClass.cpp:276-316 (Dustmasker::MaskWithBuffer)
-//   search_stage   one (read, mate, strand)     Classifier::GetHitsFromRead              Classifier.hpp:274
-//   select_stage   one read                     AdjustHitBoundaryFromStrandHits + strand pick :303,:509
-//                                               + the row plan of GetClassificationFromHits :620-666
-//   locate_stage   one BWT row                  FMIndex::BackwardToSampledSA             FMIndex.hpp:514
-//   score_stage    one read                     GetClassificationFromHits :668-843 + Taxonomy::ReduceTaxIds
+// Stage              unit of work               reference code it replaces
+//   encode_stage       32 bases                   (layout: bytes -> 2-bit codes + N bits)
+//   dust_screen_stage  one mate                   proves "Dustmasker masks nothing" for most mates (cfr_core.cuh)
+//   dust_tasks         one mate the screen kept   CentrifugerClass.cpp:276-316 (Dustmasker::MaskWithBuffer)
+//   search_tasks       one (read, mate, strand)   Classifier::GetHitsFromRead              Classifier.hpp:274
+//   select_plan /      one read                   AdjustHitBoundaryFromStrandHits + strand pick :303,:509
+//   select_write_rows                             + the row plan of GetClassificationFromHits :620-666
+//                                                 (+ the rows themselves when the dense locate table covers every row)
+//   locate_rows        one BWT row                FMIndex::BackwardToSampledSA             FMIndex.hpp:514
+//   score_stage        one read                   GetClassificationFromHits :668-843 + Taxonomy::ReduceTaxIds
 //
-// Each stage is a plain per-task function (compiled for the device by nvcc and
-// for the host by the tests' simulation harness); cfr_kernels.cu wraps them in
-// grid-stride __global__ kernels.
+// Each stage is a plain function (compiled for the device by nvcc and for the host by the tests'
+// simulation harness, where a "warp" is one lane); cfr_kernels.cuh wraps them in __global__ kernels
+// that claim their work dynamically.
 #pragma once
 #include "cfr_core.cuh"
 

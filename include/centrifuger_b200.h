@@ -41,7 +41,7 @@ typedef enum {
 typedef enum {
   CFR_LAYOUT_AUTO = 0,
   CFR_LAYOUT_RUNBLOCK = 1, /* the run-block arrays exactly as stored (rank9 + wavelet trees) */
-  CFR_LAYOUT_OCCLINE = 2   /* transcoded on the GPU at load into 64-byte occ lines */
+  CFR_LAYOUT_OCCLINE = 2   /* transcoded on the GPU at load into 32-byte occ sectors (64 BWT rows each) */
 } cfr_layout;
 
 /* replaces _classifierParam (Classifier.hpp:17-38) + the --no-dust switch
