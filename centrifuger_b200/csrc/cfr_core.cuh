@@ -1447,8 +1447,12 @@ CFR_HD bool dust_step(DustIn &in, const DustOut &out, int seg_off, int wfinish, 
 // the suffix no longer satisfies max c(v) <= 2T: drop its head up to the first t (:127-134)
 template <int SW>
 CFR_HD void dust_shrink(DustStateT<SW> &d, int t) {
+  // (the window entry of the next turn is fetched before the counter update of this one: the loop is a
+  // chain of dependent shared-memory accesses and this takes one of them off it)
+  int s_next = dust_win_at(d, d.size - d.lv);
   for (;;) {
-    const int s = dust_win_at(d, d.size - d.lv);
+    const int s = s_next;
+    if (d.lv > 1) s_next = dust_win_at(d, d.size - d.lv + 1);
     unsigned short &es = d.cc[s];
     const int e = (int)es - 0x100;  // --cv[s]
     es = (unsigned short)e;
@@ -1472,13 +1476,15 @@ CFR_HD void dust_find_perfect(int wfinish, DustStateT<SW> &d) {
   int folded = wstart + d.size;  // starts >= folded have been folded into (max_score, max_cnt)
   const int first = d.size - d.lv - 1;
   int i = first;
+  int tt_next = first >= 0 ? dust_win_at(d, first) : 0;
   for (; i >= 0; --i) {
     const int span = d.size - i - 1;
     // A candidate needs rv * 10 > T * span.  rv counts pairs inside a part of the window, so it
     // never exceeds rw (the pairs of the whole window), and span only grows from here: once
     // T * span >= rw * 10 no candidate is left and the rest of the scan cannot change anything.
     if (d.rw * 10 <= T * span) break;
-    const int tt = dust_win_at(d, i);
+    const int tt = tt_next;
+    if (i > 0) tt_next = dust_win_at(d, i - 1);  // next turn's window entry, off the dependent chain
     unsigned short &ett = d.cc[tt];
     rv += ett >> 8;
     ett = (unsigned short)(ett + 0x100);  // ++cv[tt]
