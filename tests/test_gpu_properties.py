@@ -127,3 +127,33 @@ def test_error_free_reads_hit_their_source(c2):
             bad += 0 if ok else 1
     assert bad == 0
     g.close()
+
+
+def test_load_time_tables_change_nothing_at_scale(c2, monkeypatch):
+    """the literal path (every LF step and BackwardExtend of the reference) and the default path (dense
+    locate table; wide lookup table forced on) give identical records for 200k single reads and 60k
+    pairs, while running fewer steps"""
+    import gen_data
+    idx, genomes, cat = c2
+    s1, o1 = _pack(gen_data.make_reads_se_fast(genomes, 200_000, 100, seed=31, cat=cat))
+    r1, r2 = gen_data.make_reads_pe_fast(genomes, 60_000, 150, seed=33, cat=cat)
+    p1, q1 = _pack(r1)
+    p2, q2 = _pack(r2)
+    out = {}
+    for name, env in (("literal", {"CFR_B200_DENSE_LOCATE": "-1", "CFR_B200_WIDE_LOOKUP": "0"}),
+                      ("tables", {"CFR_B200_WIDE_LOOKUP": "12"}),
+                      ("tables_pos64", {"CFR_B200_WIDE_LOOKUP": "11", "CFR_B200_DENSE_LOCATE": "2", "CFR_B200_POS64": "1"})):
+        for k in ("CFR_B200_DENSE_LOCATE", "CFR_B200_WIDE_LOOKUP", "CFR_B200_POS64"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        g = cb.Classifier(idx, k=5)
+        g.reset_counters()
+        a = g.classify_packed(s1, o1)
+        b = g.classify_packed(p1, q1, p2, q2)
+        out[name] = (a, b, g.counters())
+        g.close()
+    for name in ("tables", "tables_pos64"):
+        assert _eq(out["literal"][0], out[name][0]) and _eq(out["literal"][1], out[name][1]), name
+        assert out[name][2]["n_lf"] < out["literal"][2]["n_lf"] and out[name][2]["n_extend"] < out["literal"][2]["n_extend"]
+        assert out[name][2]["n_locate"] == out["literal"][2]["n_locate"] and out[name][2]["n_search"] == out["literal"][2]["n_search"]
