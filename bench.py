@@ -372,10 +372,12 @@ def main():
     run_e2e(a.warmup)
     sync_all()
     clf.reset_counters()
+    link0 = (clf.info(13), clf.info(14))  # bytes the library has moved over the host link so far
     t0 = time.perf_counter()
     run_e2e(a.steps)
     sync_all()
     e2e_s = time.perf_counter() - t0
+    link1 = (clf.info(13), clf.info(14))
     # single-call latency form (cfr_classify_batch: chunked copy/compute overlap inside one call)
     step_e2e()
     sync_all()
@@ -448,8 +450,10 @@ def main():
                 "l2": "256 MiB device write between timed iterations (L2 flush)",
                 "index_hbm_bytes": clf.hbm_bytes, "min_hit_len": clf.min_hit_len}),
             "e2e": {"value": e2e_value, "unit": unit,
-                    "h2d_bytes_per_step": int(bases + (n + 1) * 8 * (2 if seq2 is not None else 1)),
-                    "d2h_bytes_per_step": int(n * 32 + n * w["k"] * 8),
+                    # counted by the library from the copies it issues (reads of one length: the offsets
+                    # are generated on the device and do not cross the link)
+                    "h2d_bytes_per_step": int((link1[0] - link0[0]) // a.steps),
+                    "d2h_bytes_per_step": int((link1[1] - link0[1]) // a.steps),
                     "api": "cfr_submit_batch / cfr_wait_batch, three steps in flight, pinned host buffers",
                     "single_call_value": n * world / e2e_single_s,
                     "host_link_h2d_gbs": h2d_gbs},

@@ -99,6 +99,7 @@ struct cfr_handle {
   DevCounters *d_counters = nullptr;
   u64 launches = 0;
   u64 host_bases = 0;
+  u64 h2d_bytes = 0, d2h_bytes = 0;  // bytes the batch paths really moved over the host link
   // cfr_classify_batch pipeline: two chunk slots, H2D / compute / D2H on three streams
   // NSLOT batches can be in flight in the streaming form (upload of batch i+2 next to the kernels of
   // i+1 and the download of i); cfr_classify_batch's chunk pipeline uses the first two
@@ -383,16 +384,22 @@ int upload_chunk(cfr_handle *h, const cfr_read_batch *in, u64 r0, u64 r1, cfr_de
   b->off_bias[0] = s1;
   b->off_bias[1] = s2 - pos2;  // wraps modulo 2^64 by design; positions are computed as off - bias
   int max_len = 0;
+  // uniform[m]: every read of mate m has the same length (the usual case for short-read data): the
+  // offsets are then an arithmetic progression written on the device instead of crossing PCIe
+  bool uniform[2] = {n > 0, n > 0 && mates == 2};
+  const u64 ulen[2] = {n ? in->off1[r0 + 1] - in->off1[r0] : 0, (n && mates == 2) ? in->off2[r0 + 1] - in->off2[r0] : 0};
   for (u64 i = r0; i < r1; ++i) {
     const u64 l = in->off1[i + 1] - in->off1[i];
     if (l > 0x3fffffffull) return fail(CFR_ERR_ARG, "read longer than 2^30");
     if ((int)l > max_len) max_len = (int)l;
+    uniform[0] = uniform[0] && l == ulen[0];
   }
   if (mates == 2)
     for (u64 i = r0; i < r1; ++i) {
       const u64 l = in->off2[i + 1] - in->off2[i];
       if (l > 0x3fffffffull) return fail(CFR_ERR_ARG, "read longer than 2^30");
       if ((int)l > max_len) max_len = (int)l;
+      uniform[1] = uniform[1] && l == ulen[1];
     }
   b->cap_h = std::max(1, max_hits_for_len(max_len, h->P.min_hit_len));
   const u64 S = 2 * (u64)mates;
@@ -427,9 +434,19 @@ int upload_chunk(cfr_handle *h, const cfr_read_batch *in, u64 r0, u64 r1, cfr_de
   // H2D
   if (len1) CUDA_TRY(cudaMemcpyAsync(b->seq_raw.p, in->seq1 + s1, len1, cudaMemcpyHostToDevice, s));
   if (len2) CUDA_TRY(cudaMemcpyAsync((char *)b->seq_raw.p + pos2, in->seq2 + s2, len2, cudaMemcpyHostToDevice, s));
-  CUDA_TRY(cudaMemcpyAsync(b->off.p, in->off1 + r0, (n + 1) * 8, cudaMemcpyHostToDevice, s));
-  if (mates == 2)
-    CUDA_TRY(cudaMemcpyAsync((u64 *)b->off.p + (n + 1), in->off2 + r0, (n + 1) * 8, cudaMemcpyHostToDevice, s));
+  h->h2d_bytes += len1 + len2;
+  for (int m = 0; m < mates; ++m) {
+    u64 *dst = (u64 *)b->off.p + (m ? n + 1 : 0);
+    const uint64_t *src = (m ? in->off2 : in->off1) + r0;
+    if (uniform[m]) {
+      k_fill_offsets<<<grid_for(h, n + 1, 256, 8), 256, 0, s>>>(dst, n + 1, src[0], ulen[m]);
+      ++h->launches;
+    } else {
+      CUDA_TRY(cudaMemcpyAsync(dst, src, (n + 1) * 8, cudaMemcpyHostToDevice, s));
+      h->h2d_bytes += (n + 1) * 8;
+    }
+  }
+  CUDA_TRY(cudaGetLastError());
   return CFR_OK;
 }
 
@@ -752,6 +769,8 @@ uint64_t cfr_index_info(const cfr_handle *h, int which) {
     case 10: return (uint64_t)h->ix.sample_rate;
     case 11: return (uint64_t)h->ix.pre_width;
     case 12: return (uint64_t)h->P.max_result;
+    case 13: return (uint64_t)h->h2d_bytes;
+    case 14: return (uint64_t)h->d2h_bytes;
     default: return 0;
   }
 }
@@ -804,6 +823,7 @@ int cfr_batch_fetch(cfr_handle *h, cfr_device_batch *b, cfr_result *results, uin
   if (b->n_reads) {
     CUDA_TRY(cudaMemcpyAsync(results, b->results.p, b->n_reads * sizeof(DevResult), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaMemcpyAsync(ids, b->out_ids.p, b->n_reads * (u64)h->P.max_result * 8, cudaMemcpyDeviceToHost, s));
+    h->d2h_bytes += b->n_reads * (sizeof(DevResult) + (u64)h->P.max_result * 8);
   }
   return check_device_errors(h, s);
 }
@@ -921,6 +941,7 @@ int cfr_classify_batch(cfr_handle *h, const cfr_read_batch *in, cfr_result *resu
     CUDA_TRY(cudaStreamWaitEvent(h->s_out, h->ev_comp[slot], 0));
     CUDA_TRY(cudaMemcpyAsync(results + r0, b->results.p, (r1 - r0) * sizeof(DevResult), cudaMemcpyDeviceToHost, h->s_out));
     CUDA_TRY(cudaMemcpyAsync(ids + r0 * k, b->out_ids.p, (r1 - r0) * k * 8, cudaMemcpyDeviceToHost, h->s_out));
+    h->d2h_bytes += (r1 - r0) * (sizeof(DevResult) + k * 8);
     CUDA_TRY(cudaMemcpyAsync(&h->pinned_scalars[slot], b->scalars.p, 16, cudaMemcpyDeviceToHost, h->s_out));
     CUDA_TRY(cudaEventRecord(h->ev_d2h[slot], h->s_out));
     // the next upload into the OTHER slot may start at once; an upload into THIS slot (chunk c+2)
@@ -983,10 +1004,12 @@ int cfr_submit_batch_masked(cfr_handle *h, const cfr_read_batch *in, cfr_result 
   if (in->n_reads) {
     CUDA_TRY(cudaMemcpyAsync(results, b->results.p, in->n_reads * sizeof(DevResult), cudaMemcpyDeviceToHost, h->s_out));
     CUDA_TRY(cudaMemcpyAsync(ids, b->out_ids.p, in->n_reads * k * 8, cudaMemcpyDeviceToHost, h->s_out));
+    h->d2h_bytes += in->n_reads * (sizeof(DevResult) + k * 8);
   }
   if (b->want_masked && in->n_reads) {
     const u64 len1 = in->off1[in->n_reads] - in->off1[0];
     const u64 len2 = in->seq2 ? in->off2[in->n_reads] - in->off2[0] : 0;
+    h->d2h_bytes += len1 + (masked2 ? len2 : 0);
     if (len1) CUDA_TRY(cudaMemcpyAsync(masked1, b->masked.p, len1, cudaMemcpyDeviceToHost, h->s_out));
     if (len2 && masked2)
       CUDA_TRY(cudaMemcpyAsync(masked2, (char *)b->masked.p + ((len1 + 31) & ~31ull), len2, cudaMemcpyDeviceToHost, h->s_out));

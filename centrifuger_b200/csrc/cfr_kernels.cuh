@@ -30,6 +30,12 @@ __global__ void __launch_bounds__(256) k_encode(const __grid_constant__ ChunkDev
   for (u64 w = (u64)blockIdx.x * blockDim.x + threadIdx.x; w < B.n_words; w += stride) encode_stage(B, w, total_bytes);
 }
 
+// read offsets of a batch whose reads all have one length: off[i] = first + i * len
+__global__ void k_fill_offsets(u64 *off, u64 n, u64 first, u64 len) {
+  const u64 stride = (u64)gridDim.x * blockDim.x;
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) off[i] = first + i * len;
+}
+
 // diagnostics: the uploaded bytes with the DUST intervals replaced by 'N'
 __global__ void k_apply_dust(const __grid_constant__ ChunkDev B, unsigned char *out, const u64 total_bytes) {
   const u64 stride = (u64)gridDim.x * blockDim.x;

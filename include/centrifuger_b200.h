@@ -146,7 +146,8 @@ void cfr_host_free(void *p);
 
 /* index facts: 0 n, 1 b, 2 blockCnt, 3 firstISA, 4 min_hit_len in effect,
  * 5 nodeCnt, 6 seqCnt(+extra), 7 root ctid, 8 layout in use, 9 HBM bytes held,
- * 10 sampleRate, 11 precomputeWidth, 12 max_result */
+ * 10 sampleRate, 11 precomputeWidth, 12 max_result,
+ * 13 / 14 bytes the batch calls have moved host->device / device->host so far */
 uint64_t cfr_index_info(const cfr_handle *h, int which);
 
 /* Taxonomy look-ups used by ResultWriter (host tables) */
