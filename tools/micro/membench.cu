@@ -30,6 +30,42 @@ __global__ void __launch_bounds__(128) k_read(const u64 *a, u64 n_units, int ite
   if (acc == 0x1234567) out[0] = acc;
 }
 
+// G adjacent lanes fetch ONE random 32*G-byte unit together (lane g its g-th sector): a single
+// coalesced request per unit instead of G separate ones
+template <int G>
+__global__ void __launch_bounds__(128) k_read_coop(const u64 *a, u64 n_units, int iters, u64 seed, u64 *out) {
+  u64 acc = 0;
+  const int g = threadIdx.x % G;
+  u64 r = mix(seed + blockIdx.x * 1315423911ull + threadIdx.x / G);
+  for (int it = 0; it < iters; ++it) {
+    r = mix(r + it);
+    const u64 unit = r % n_units;
+    const u64 *p = a + unit * (4 * G) + 4 * g;
+    u64 x0, x1, x2, x3;
+    asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(x0), "=l"(x1), "=l"(x2), "=l"(x3) : "l"(p));
+    acc += x0 ^ x1 ^ x2 ^ x3;
+  }
+  if (acc == 0x1234567) out[0] = acc;
+}
+
+template <int G>
+void run_coop(const u64 *a, size_t bytes, u64 *out, int blocks_per_sm) {
+  const u64 n_units = bytes / (32 * G);
+  const int iters = 2000;
+  const int grid = 148 * blocks_per_sm;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  k_read_coop<G><<<grid, 128>>>(a, n_units, 200, 1, out);
+  cudaEventRecord(e0);
+  k_read_coop<G><<<grid, 128>>>(a, n_units, iters, 7, out);
+  cudaEventRecord(e1);
+  cudaEventSynchronize(e1);
+  float ms; cudaEventElapsedTime(&ms, e0, e1);
+  const double units = (double)grid * 128 / G * iters;
+  printf("array %6.0f MB  %d lanes share one %3d-B unit  blocks/SM %2d : %7.2f G units/s  %7.1f GB/s useful  (%.2f ms)\n",
+         bytes / 1e6, G, 32 * G, blocks_per_sm, units / ms / 1e6, units * 32 * G / ms / 1e6, ms);
+}
+
 template <int S, int DEP>
 void run(const u64 *a, size_t bytes, u64 *out, int blocks_per_sm) {
   const u64 n_units = bytes / S;
@@ -70,6 +106,8 @@ int main(int argc, char **argv) {
     run<32, 1>(a, bytes, out, 10);
     run<64, 1>(a, bytes, out, 10);
     run<32, 1>(a, bytes, out, 16);
+    run_coop<2>(a, bytes, out, 16);
+    run_coop<4>(a, bytes, out, 16);
     cudaFree(a);
   }
   return 0;
