@@ -14,6 +14,7 @@
 #include <zlib.h>
 
 #include <algorithm>
+#include <atomic>
 #include <condition_variable>
 #include <cstdarg>
 #include <cstdio>
@@ -58,7 +59,7 @@ static const char usage[] =
 
 enum {
   ARGV_NO_DUST = 256, ARGV_MIN_HITLEN, ARGV_HITK, ARGV_SECONDARY, ARGV_GPU, ARGV_BATCH, ARGV_LAYOUT,
-  ARGV_UNSUPPORTED, ARGV_DRY_RUN, ARGV_UN, ARGV_CL, ARGV_MERGE
+  ARGV_UNSUPPORTED, ARGV_DRY_RUN, ARGV_DRY_PIPE, ARGV_UN, ARGV_CL, ARGV_MERGE
 };
 
 static const char *short_options = "x:1:2:u:i:o:t:k:hv";
@@ -71,6 +72,7 @@ static struct option long_options[] = {
     {"batch", required_argument, 0, ARGV_BATCH},
     {"layout", required_argument, 0, ARGV_LAYOUT},
     {"dry-run", no_argument, 0, ARGV_DRY_RUN},
+    {"dry-run-pipeline", no_argument, 0, ARGV_DRY_PIPE},
     {"un", required_argument, 0, ARGV_UN},
     {"cl", required_argument, 0, ARGV_CL},
     {"merge-readpair", no_argument, 0, ARGV_MERGE},
@@ -478,6 +480,7 @@ int main(int argc, char *argv[]) {
   long batchReads = 1 << 20;
   const char *unPrefix = NULL, *clPrefix = NULL;  // --un / --cl
   bool mergePairs = false;                        // --merge-readpair
+  bool dryPipe = false;  // diagnostics: the batches the threaded ingest stage hands to the GPU stage, no GPU work
   bool dryRun = false;  // diagnostics: parse the inputs and print id<TAB>mate1<TAB>mate2, no GPU work
   int c, option_index = 0;
   while ((c = getopt_long(argc, argv, short_options, long_options, &option_index)) != -1) {
@@ -510,6 +513,7 @@ int main(int argc, char *argv[]) {
       else if (!strcmp(optarg, "runblock")) params.layout = CFR_LAYOUT_RUNBLOCK;
       else params.layout = CFR_LAYOUT_AUTO;
     } else if (c == ARGV_DRY_RUN) dryRun = true;
+    else if (c == ARGV_DRY_PIPE) dryPipe = true;
     else if (c == ARGV_MERGE) mergePairs = true;
     else if (c == ARGV_UN) unPrefix = optarg;
     else if (c == ARGV_CL) clPrefix = optarg;
@@ -547,8 +551,8 @@ int main(int argc, char *argv[]) {
     }
     return 0;
   }
-  PrintLog("Centrifuger v" CENTRIFUGER_VERSION " starts.");
-  if (idxPrefix == NULL) {
+  if (!dryPipe) PrintLog("Centrifuger v" CENTRIFUGER_VERSION " starts.");
+  if (idxPrefix == NULL && !dryPipe) {
     PrintLog("Need to use -x to specify index prefix.");
     return EXIT_FAILURE;
   }
@@ -578,13 +582,16 @@ int main(int argc, char *argv[]) {
     }
   }
   cfr_handle *h = NULL;
-  int st = cfr_open(idxPrefix, &params, device, &h);
-  if (st != CFR_OK) {
-    PrintLog("ERROR: %s", cfr_last_error());
-    return EXIT_FAILURE;
+  int st = CFR_OK;
+  if (!dryPipe) {
+    st = cfr_open(idxPrefix, &params, device, &h);
+    if (st != CFR_OK) {
+      PrintLog("ERROR: %s", cfr_last_error());
+      return EXIT_FAILURE;
+    }
+    PrintLog("Finishes loading index.");
+    if (params.min_hit_len <= 0) PrintLog("Inferred --min-hitlen: %d", (int)cfr_index_info(h, 4));
   }
-  PrintLog("Finishes loading index.");
-  if (params.min_hit_len <= 0) PrintLog("Inferred --min-hitlen: %d", (int)cfr_index_info(h, 4));
 
   // Three-stage pipeline over three rotating batches: the ingest thread parses batch i+1 while
   // the GPU classifies batch i and the output thread formats batch i-1 (ResultWriter::Output,
@@ -618,13 +625,35 @@ int main(int argc, char *argv[]) {
     std::string name, name2, tmp;
     int bi = 0;
     bool eof = false;
+    const bool twoFiles = hasMate && !interleaved;
     for (;;) {
       Batch *bt = free_slots[bi].take();
       bi = (bi + 1) % NBATCH;
       bt->clear();
-      // a batch ends after batchReads reads or 2^29 bases, whichever comes first (long reads: the device work
-      // areas grow with the bases and with the longest read of a batch)
-      while ((long)bt->n < batchReads && bt->seq1.size() + bt->seq2.size() < (512u << 20)) {
+      // a batch ends after batchReads reads or 2^28 bases per mate, whichever comes first (long reads: the
+      // device work areas grow with the bases and with the longest read of a batch)
+      const size_t maxBases = 256u << 20;
+      // mate 2 of separate files is parsed by a second thread that trails this one: it reads record j only
+      // after mate 1's record j exists, so the two files advance by the same number of records per batch
+      std::atomic<long> n1(0);       // mate-1 records parsed so far in this batch
+      std::atomic<bool> done1(false);
+      long n2 = 0;
+      std::thread mate2;
+      if (twoFiles) {
+        mate2 = std::thread([&] {
+          std::string nm;
+          std::string *q2 = keepReads ? &bt->qual2 : nullptr;
+          for (;;) {
+            while (n2 >= n1.load(std::memory_order_acquire) && !done1.load(std::memory_order_acquire)) std::this_thread::yield();
+            if (n2 >= n1.load(std::memory_order_acquire)) break;  // mate 1 is done and mate 2 has caught up
+            if (!mates.next(nm, bt->seq2, q2)) break;             // mate 2 ended first
+            bt->off2.push_back(bt->seq2.size());
+            if (keepReads) bt->qoff2.push_back(bt->qual2.size());
+            ++n2;
+          }
+        });
+      }
+      while ((long)bt->n < batchReads && bt->seq1.size() < maxBases) {
         name.clear();
         if (!reads.next(name, bt->seq1, keepReads ? &bt->qual1 : nullptr)) {
           eof = true;
@@ -635,10 +664,9 @@ int main(int argc, char *argv[]) {
         bt->id_off.push_back((uint32_t)bt->ids.size());
         bt->off1.push_back(bt->seq1.size());
         if (keepReads) bt->qoff1.push_back(bt->qual1.size());
-        if (hasMate) {
+        if (interleaved) {
           std::string *q2 = keepReads ? &bt->qual2 : nullptr;
-          const bool ok = interleaved ? reads.next(name2, bt->seq2, q2) : mates.next(name2, bt->seq2, q2);
-          if (!ok) {
+          if (!reads.next(name2, bt->seq2, q2)) {
             mate_mismatch = true;
             break;
           }
@@ -646,10 +674,21 @@ int main(int argc, char *argv[]) {
           if (keepReads) bt->qoff2.push_back(bt->qual2.size());
         }
         ++bt->n;
+        n1.store((long)bt->n, std::memory_order_release);
       }
-      if (!mate_mismatch && hasMate && !interleaved && eof) {
-        tmp.clear();
-        if (mates.next(name2, tmp)) mate_mismatch = true;  // mate 1 ended first
+      if (twoFiles) {
+        done1.store(true, std::memory_order_release);
+        mate2.join();
+        if (n2 < (long)bt->n) mate_mismatch = true;  // mate 2 ended first
+        if (!mate_mismatch && eof) {
+          tmp.clear();
+          if (mates.next(name2, tmp)) mate_mismatch = true;  // mate 1 ended first
+        }
+        if (mate_mismatch && n2 < (long)bt->n) {  // keep the batch consistent for the stages behind
+          bt->n = (size_t)n2;
+          bt->off1.resize(bt->n + 1);
+          bt->id_off.resize(bt->n + 1);
+        }
       }
       bt->last = eof || mate_mismatch;
       if (mergePairs && hasMate && bt->n) MergeBatch(*bt, true, std::thread::hardware_concurrency());
@@ -657,6 +696,31 @@ int main(int argc, char *argv[]) {
       if (bt->last) break;
     }
   });
+
+  for (int i = 0; i < NBATCH; ++i) free_slots[i].put(&batches[i]);
+  if (dryPipe) {  // what the GPU stage would receive: id, mate 1, mate 2 (merged pairs: the merged read, empty mate)
+    for (;;) {
+      Batch *bt = to_gpu.take();
+      for (size_t i = 0; i < bt->n; ++i) {
+        fwrite(bt->ids.data() + bt->id_off[i], 1, bt->id_off[i + 1] - bt->id_off[i], stdout);
+        fputc('\t', stdout);
+        fwrite(bt->seq1.data() + bt->off1[i], 1, (size_t)(bt->off1[i + 1] - bt->off1[i]), stdout);
+        fputc('\t', stdout);
+        if (hasMate) fwrite(bt->seq2.data() + bt->off2[i], 1, (size_t)(bt->off2[i + 1] - bt->off2[i]), stdout);
+        fputc('\n', stdout);
+      }
+      const bool last = bt->last;
+      for (int q = 0; q < NBATCH; ++q)
+        if (&batches[q] == bt) free_slots[q].put(bt);
+      if (last) break;
+    }
+    ingest.join();
+    if (mate_mismatch) {
+      PrintLog("ERROR: The two mate-pair read files have different number of reads.");
+      return EXIT_FAILURE;
+    }
+    return 0;
+  }
 
   std::thread output([&] {
     std::string out, rec;
@@ -743,7 +807,6 @@ int main(int argc, char *argv[]) {
     fflush(stdout);
   });
 
-  for (int i = 0; i < NBATCH; ++i) free_slots[i].put(&batches[i]);
   int rc = 0;
   // submitted, not yet waited for: up to two stay behind the batch just submitted (three in flight)
   std::deque<std::pair<Batch *, int>> pending;

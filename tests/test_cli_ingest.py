@@ -126,3 +126,52 @@ def test_merge_readpair_port_matches_reference_merger(tmp_path):
         assert got == exp
         codes = [l.split(b"\t")[0] for l in exp.splitlines()]
         assert codes.count(b"1") > 100 and codes.count(b"2") > 100 and codes.count(b"0") > 100
+
+
+def _pipe(args):
+    r = subprocess.run([EXE, "--dry-run-pipeline"] + args, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=120)
+    return r.returncode, [tuple(l.split("\t")) for l in r.stdout.decode().split("\n") if l], r.stderr.decode()
+
+
+def test_threaded_ingest_stage_matches_serial_parse(tiny_dir, tmp_path):
+    """the batches the ingest stage hands to the GPU stage (mate 2 parsed by a trailing second thread,
+    batches cut at --batch reads) hold exactly the records of the serial parse, in order"""
+    f1, f2 = os.path.join(tiny_dir, "pe_100_1.fq"), os.path.join(tiny_dir, "pe_100_2.fq")
+    ref = _dry(["-1", f1, "-2", f2])
+    for batch in ("1", "7", "64", "300", "1048576"):
+        rc, got, _ = _pipe(["--batch", batch, "-1", f1, "-2", f2])
+        assert rc == 0 and got == ref, batch
+    se = os.path.join(tiny_dir, "edge.fq")
+    rc, got, _ = _pipe(["--batch", "5", "-u", se])
+    assert rc == 0 and got == [(a, b, "") for a, b, _ in _dry(["-u", se])]
+    # interleaved input and gz input
+    il = tmp_path / "il.fq.gz"
+    with gzip.open(il, "wb") as f:
+        for (i, a, b) in ref[:50]:
+            f.write(("@%s/1\n%s\n+\n%s\n@%s/2\n%s\n+\n%s\n" % (i, a, "I" * len(a), i, b, "I" * len(b))).encode())
+    rc, got, _ = _pipe(["--batch", "9", "-i", str(il)])
+    assert rc == 0 and got == ref[:50]
+    # mate files of different length: an error, whichever file is the short one
+    short = tmp_path / "short.fq"
+    short.write_bytes(b"".join(b"@%s\n%s\n+\n%s\n" % (i.encode(), b.encode(), b"I" * len(b)) for i, _, b in ref[:120]))
+    rc, _, err = _pipe(["--batch", "50", "-1", f1, "-2", str(short)])
+    assert rc != 0 and "different number of reads" in err
+    rc, _, err = _pipe(["--batch", "50", "-1", str(short), "-2", f2])
+    assert rc != 0 and "different number of reads" in err
+
+
+def test_merge_readpair_in_the_ingest_stage(tiny_dir):
+    """--merge-readpair inside the pipeline: a merged pair reaches the GPU stage as (merged read, empty mate)"""
+    f1, f2 = os.path.join(tiny_dir, "ov_1.fq"), os.path.join(tiny_dir, "ov_2.fq")
+    codes = _dry(["--merge-readpair", "-1", f1, "-2", f2])   # (code, merged read, merged qualities)
+    plain = _dry(["-1", f1, "-2", f2])
+    rc, got, _ = _pipe(["--merge-readpair", "--batch", "33", "-1", f1, "-2", f2])
+    assert rc == 0 and len(got) == len(plain)
+    merged = 0
+    for c, p, g in zip(codes, plain, got):
+        if c[0] != "0":
+            assert g == (p[0], c[1], ""), p[0]
+            merged += 1
+        else:
+            assert g == p
+    assert merged > 50
