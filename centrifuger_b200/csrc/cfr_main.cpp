@@ -1,14 +1,16 @@
 // cfr_main.cpp -- `centrifuger-b200`: drop-in for the reference's classification
 // binary (CentrifugerClass.cpp) on the paths this repo covers: same -x/-1/-2/-u/-i/
-// -t/-k/--min-hitlen/--hitk-factor/--no-dust/--consider-secondary/-h/-v options, the
-// reference's own *.cfr index files, the identical TSV on stdout and the same log
-// lines on stderr.  All classification work is done by libcfrb200.so on the GPU
-// (include/centrifuger_b200.h); this file is host I/O only: gz FASTA/FASTQ parsing
-// (ReadFiles.hpp + kseq.h behaviour), batching and ResultWriter-style output.
+// -t/-k/--min-hitlen/--hitk-factor/--no-dust/--consider-secondary/--un/--cl/
+// --merge-readpair/-h/-v options, the reference's own *.cfr index files, the identical
+// TSV on stdout and the same log lines on stderr.  All classification work is done by
+// libcfrb200.so on the GPU (include/centrifuger_b200.h); this file is host I/O only:
+// gz FASTA/FASTQ parsing (ReadFiles.hpp + kseq.h behaviour) on an ingest thread (mate 2
+// on a second one), batching, the read-pair merger (ReadPairMerger.hpp behaviour) and
+// ResultWriter-style output on an output thread.
 //
-// Not supported (the reference's single-cell / output-side extras, SURVEY.md 8 "out
-// of scope"): --un/--cl, --merge-readpair, --expand-taxid, barcode/UMI/read-format
-// options, --sample-sheet.  They are rejected with a log line and EXIT_FAILURE.
+// Not supported (the reference's single-cell extras, SURVEY.md 8 "out of scope"):
+// --expand-taxid, barcode/UMI/read-format options, --sample-sheet.  They are rejected
+// with a log line and EXIT_FAILURE.
 #include <getopt.h>
 #include <sys/stat.h>
 #include <zlib.h>

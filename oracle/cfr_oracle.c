@@ -496,9 +496,13 @@ static int u64set_insert(u64set *s, uint64_t x) { /* returns 1 if newly inserted
   return 1;
 }
 
-/* Taxonomy.hpp:733-836 (lcaChildTaxIds == NULL branch only) */
-static uint64_t tax_lca(const taxonomy_t *t, const uint64_t *tax_ids, int tax_cnt) {
+/* Taxonomy.hpp:733-836.  `children` (may be NULL) is lcaChildTaxIds: when the answer is a backbone
+ * node it receives, ascending, the distinct nodes directly below the answer where the inputs'
+ * lineages leave it (:767-773, :811-812, :825-831); it is left untouched when the answer is the
+ * root by default (all-root input :756, no shared backbone node :819) */
+static uint64_t tax_lca(const taxonomy_t *t, const uint64_t *tax_ids, int tax_cnt, u64set *children) {
   int i, j, k;
+  u64set *below = NULL; /* backboneChildTaxIds */
   uint64_t cur;
   uint64_t *path = NULL, *tmp = NULL;
   int *path_cnt = NULL;
@@ -528,6 +532,10 @@ static uint64_t tax_lca(const taxonomy_t *t, const uint64_t *tax_ids, int tax_cn
   }
   path[path_len] = t->root;
   path_cnt[path_len++] = 1;
+  if (children) { /* :767-773 */
+    below = (u64set *)calloc((size_t)path_len, sizeof(u64set));
+    for (j = 1; j < path_len; ++j) u64set_insert(&below[j], path[j - 1]);
+  }
 
   for (i = 0; i < tax_cnt; ++i) {
     int ib, it;
@@ -551,23 +559,48 @@ static uint64_t tax_lca(const taxonomy_t *t, const uint64_t *tax_ids, int tax_cn
       if (tmp[it] != path[ib]) break;
       path_cnt[ib] += 1;
     }
+    if (children && it >= 0 && ib + 1 < path_len) u64set_insert(&below[ib + 1], tmp[it]); /* :811-812 */
   }
   for (j = 0; j < path_len; ++j)
     if (path_cnt[j] == tax_cnt - root_count) break;
   ret = (j >= path_len) ? t->root : path[j];
+  if (children) {
+    if (j < path_len) { /* :825-831 */
+      children->n = 0;
+      for (i = 0; i < below[j].n; ++i) u64set_insert(children, below[j].a[i]);
+    }
+    for (j = 0; j < path_len; ++j) free(below[j].a);
+    free(below);
+  }
   free(path);
   free(path_cnt);
   free(tmp);
   return ret;
 }
 
-/* Taxonomy.hpp:839-973 (promotedChildTaxIds == NULL) */
+/* plain append (the lists of promotedChildTaxIds are vectors: order kept, duplicates allowed) */
+static void u64vec_push(u64set *v, uint64_t x) {
+  if (v->n == v->cap) {
+    v->cap = v->cap ? v->cap * 2 : 8;
+    v->a = (uint64_t *)realloc(v->a, sizeof(uint64_t) * (size_t)v->cap);
+    if (!v->a) die("out of memory");
+  }
+  v->a[v->n++] = x;
+}
+
+/* Taxonomy.hpp:839-973.  `lists`/`n_lists` (may be NULL) are promotedChildTaxIds: *n_lists vectors,
+ * allocated here (caller frees each .a and the array); the caller prints them only when
+ * *n_lists equals the number of ids returned (Classifier.hpp:823) */
 static int tax_reduce(const taxonomy_t *t, const uint64_t *tax_ids, int tax_cnt, int k,
-                      uint64_t *out, int cap) {
+                      uint64_t *out, int cap, u64set **lists, int *n_lists) {
   int i, n_out = 0;
   u64set level[RANK_MAX];
   uint8_t ri;
 #define PUSH(x) do { if (n_out < cap) out[n_out] = (x); ++n_out; } while (0)
+  if (lists) {
+    *lists = NULL;
+    *n_lists = 0;
+  }
   if (tax_cnt <= k) { /* :847-851 */
     for (i = 0; i < tax_cnt; ++i) PUSH(tax_ids[i]);
     return n_out;
@@ -575,10 +608,22 @@ static int tax_reduce(const taxonomy_t *t, const uint64_t *tax_ids, int tax_cnt,
   for (i = 0; i < tax_cnt; ++i) /* :855-882 */
     if (tax_ids[i] >= t->node_cnt) {
       PUSH(t->node_cnt);
+      if (lists) { /* :871-878: one list holding every input id as given */
+        int j;
+        *lists = (u64set *)calloc(1, sizeof(u64set));
+        *n_lists = 1;
+        for (j = 0; j < tax_cnt; ++j) u64vec_push(&(*lists)[0], tax_ids[j]);
+      }
       return n_out;
     }
   if (k == 1) { /* :884-901 */
-    PUSH(tax_lca(t, tax_ids, tax_cnt));
+    if (lists) {
+      *lists = (u64set *)calloc(1, sizeof(u64set));
+      *n_lists = 1;
+      PUSH(tax_lca(t, tax_ids, tax_cnt, &(*lists)[0]));
+    } else {
+      PUSH(tax_lca(t, tax_ids, tax_cnt, NULL));
+    }
     return n_out;
   }
   memset(level, 0, sizeof(level));
@@ -603,7 +648,26 @@ static int tax_reduce(const taxonomy_t *t, const uint64_t *tax_ids, int tax_cnt,
   for (ri = 0; ri < t->rank_num[RANK_UNKNOWN]; ++ri) /* :933-936 */
     if (level[ri].n <= k) break;
   for (i = 0; i < level[ri].n; ++i) PUSH(level[ri].a[i]);
-  if (n_out == 0) PUSH(t->root);
+  if (n_out == 0) {
+    PUSH(t->root);
+  } else if (lists && ri > 0) { /* :941-971: the level below, grouped by the promoted node above it */
+    *lists = (u64set *)calloc((size_t)level[ri].n, sizeof(u64set));
+    *n_lists = level[ri].n;
+    for (i = 0; i < level[ri - 1].n; ++i) {
+      uint64_t cur = level[ri - 1].a[i];
+      while (cur != t->tree[cur].parent) {
+        uint8_t rank_num;
+        cur = t->tree[cur].parent;
+        rank_num = t->rank_num[t->tree[cur].rank];
+        if (rank_num > ri) break;
+        if (rank_num == ri) {
+          int pos;
+          if (u64set_find(&level[ri], cur, &pos)) u64vec_push(&(*lists)[pos], level[ri - 1].a[i]);
+          break;
+        }
+      }
+    }
+  }
   for (i = 0; i < RANK_MAX; ++i) free(level[i].a);
 #undef PUSH
   return n_out;
@@ -1222,9 +1286,17 @@ static seq_rec *recmap_get(recmap *m, uint64_t seq_id) {
   return &m->a[pos];
 }
 
+/* the child lists of one result (Classifier.hpp:807-838, outputExpandedResult) */
+typedef struct {
+  uint64_t *child; /* compact tax ids, list after list */
+  int child_cap;
+  int32_t *cnt;    /* entries per reported id (64 slots) */
+  int total;
+} expand_out;
+
 /* Classifier.hpp:585-843 */
 static void classification_from_hits(cfr_oracle *o, const cfr_oracle_param *p, int min_hit_len,
-                                     const hitvec *hv, cfr_oracle_result *res) {
+                                     const hitvec *hv, cfr_oracle_result *res, expand_out *ex) {
   int i, k;
   uint64_t j;
   const cfr_oracle_hit *hits = hv->a;
@@ -1355,7 +1427,24 @@ static void classification_from_hits(cfr_oracle *o, const cfr_oracle_param *p, i
     uint64_t *red = (uint64_t *)xmalloc(8 * (size_t)(best_n + 1));
     int nred;
     for (i = 0; i < best_n; ++i) tids[i] = tax_seq_to_tax(&o->tax, best_ids[i]);
-    nred = tax_reduce(&o->tax, tids, best_n, p->max_result, red, best_n + 1);
+    if (ex) { /* :807-838 */
+      u64set *lists = NULL;
+      int n_lists = 0, q;
+      nred = tax_reduce(&o->tax, tids, best_n, p->max_result, red, best_n + 1, &lists, &n_lists);
+      for (i = 0; i < n_lists; ++i) {
+        if (n_lists == nred && i < 64) { /* :823 */
+          ex->cnt[i] = lists[i].n;
+          for (q = 0; q < lists[i].n; ++q) {
+            if (ex->total < ex->child_cap) ex->child[ex->total] = lists[i].a[q];
+            ++ex->total;
+          }
+        }
+        free(lists[i].a);
+      }
+      free(lists);
+    } else {
+      nred = tax_reduce(&o->tax, tids, best_n, p->max_result, red, best_n + 1, NULL, NULL);
+    }
     for (i = 0; i < nred && i < 64; ++i) {
       res->ids[i] = red[i];
       res->tax_ids[i] = tax_orig_id(&o->tax, red[i]);
@@ -1378,10 +1467,30 @@ void cfr_oracle_query(cfr_oracle *o, const cfr_oracle_param *p, const char *r1, 
   int mhl = eff_min_hit_len(o, p);
   memset(res, 0, sizeof(*res));
   search_forward_and_reverse(o, mhl, r1, r2, &hits);
-  classification_from_hits(o, p, mhl, &hits, res);
+  classification_from_hits(o, p, mhl, &hits, res, NULL);
   res->query_length = (int32_t)strlen(r1);
   if (r2) res->query_length += (int32_t)strlen(r2);
   free(hits.a);
+}
+
+/* Query with _classifierParam.outputExpandedResult (Classifier.hpp:22, :792-838) */
+int cfr_oracle_query_expanded(cfr_oracle *o, const cfr_oracle_param *p, const char *r1, const char *r2,
+                              cfr_oracle_result *res, uint64_t *child, int child_cap, int32_t *child_cnt) {
+  hitvec hits = {0, 0, 0};
+  expand_out ex;
+  int mhl = eff_min_hit_len(o, p);
+  memset(res, 0, sizeof(*res));
+  memset(child_cnt, 0, 64 * sizeof(int32_t));
+  ex.child = child;
+  ex.child_cap = child_cap;
+  ex.cnt = child_cnt;
+  ex.total = 0;
+  search_forward_and_reverse(o, mhl, r1, r2, &hits);
+  classification_from_hits(o, p, mhl, &hits, res, &ex);
+  res->query_length = (int32_t)strlen(r1);
+  if (r2) res->query_length += (int32_t)strlen(r2);
+  free(hits.a);
+  return ex.total;
 }
 
 uint64_t cfr_oracle_seqid_to_taxid(const cfr_oracle *o, uint64_t s) { return tax_seq_to_tax(&o->tax, s); }
@@ -1395,7 +1504,24 @@ const char *cfr_oracle_rank_name(const cfr_oracle *o, uint64_t c) {
 }
 int cfr_oracle_reduce_taxids(const cfr_oracle *o, const uint64_t *t, int n, int k, uint64_t *out,
                              int cap) {
-  return tax_reduce(&o->tax, t, n, k, out, cap);
+  return tax_reduce(&o->tax, t, n, k, out, cap, NULL, NULL);
+}
+int cfr_oracle_reduce_taxids_expanded(const cfr_oracle *o, const uint64_t *t, int n, int k, uint64_t *out,
+                                      int cap, uint64_t *child, int child_cap, int32_t *child_cnt,
+                                      int *n_lists) {
+  u64set *lists = NULL;
+  int i, q, total = 0;
+  int nred = tax_reduce(&o->tax, t, n, k, out, cap, &lists, n_lists);
+  for (i = 0; i < *n_lists; ++i) {
+    child_cnt[i] = lists[i].n;
+    for (q = 0; q < lists[i].n; ++q) {
+      if (total < child_cap) child[total] = lists[i].a[q];
+      ++total;
+    }
+    free(lists[i].a);
+  }
+  free(lists);
+  return nred;
 }
 
 /* ResultWriter.hpp:199-236 */
@@ -1414,6 +1540,37 @@ int cfr_oracle_format_tsv(const cfr_oracle *o, const char *read_id, const cfr_or
     }
   } else {
     w = snprintf(buf + off, cap - off, "%s\tunclassified\t0\t0\t0\t0\t%d\t1\n", read_id, r->query_length);
+    if (w < 0 || (size_t)w >= cap - off) return -1;
+    off += (size_t)w;
+  }
+  return (int)off;
+}
+
+/* ResultWriter.hpp:186-241 with _outputExpandedTaxIds: one more column, the original ids of the
+ * child list joined by ',' (Classifier.hpp:826-835); empty for unclassified reads */
+int cfr_oracle_format_tsv_expanded(const cfr_oracle *o, const char *read_id, const cfr_oracle_result *r,
+                                   const uint64_t *child, const int32_t *child_cnt, char *buf, size_t cap) {
+  size_t off = 0;
+  int i, q, w, at = 0;
+  if (r->n > 0) {
+    for (i = 0; i < r->n && i < 64; ++i) {
+      const char *name = r->by_rank ? cfr_oracle_rank_name(o, r->ids[i]) : cfr_oracle_seq_name(o, r->ids[i]);
+      w = snprintf(buf + off, cap - off, "%s\t%s\t%lu\t%lu\t%lu\t%d\t%d\t%d\t", read_id, name,
+                   (unsigned long)r->tax_ids[i], (unsigned long)r->score,
+                   (unsigned long)r->secondary_score, r->hit_length, r->query_length, r->n);
+      if (w < 0 || (size_t)w >= cap - off) return -1;
+      off += (size_t)w;
+      for (q = 0; q < child_cnt[i]; ++q, ++at) {
+        w = snprintf(buf + off, cap - off, "%s%lu", q ? "," : "", (unsigned long)tax_orig_id(&o->tax, child[at]));
+        if (w < 0 || (size_t)w >= cap - off) return -1;
+        off += (size_t)w;
+      }
+      if (cap - off < 2) return -1;
+      buf[off++] = '\n';
+      buf[off] = 0;
+    }
+  } else {
+    w = snprintf(buf + off, cap - off, "%s\tunclassified\t0\t0\t0\t0\t%d\t1\t\n", read_id, r->query_length);
     if (w < 0 || (size_t)w >= cap - off) return -1;
     off += (size_t)w;
   }

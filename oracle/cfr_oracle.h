@@ -106,6 +106,18 @@ const char *cfr_oracle_rank_name(const cfr_oracle *o, uint64_t ctid);
 int cfr_oracle_reduce_taxids(const cfr_oracle *o, const uint64_t *tax_ids,
                              int n, int k, uint64_t *out, int cap);
 
+/* the same with promotedChildTaxIds: *n_lists lists (child_cnt[i] entries each, concatenated in
+ * child); the classifier prints them only when *n_lists equals the returned count */
+int cfr_oracle_reduce_taxids_expanded(const cfr_oracle *o, const uint64_t *tax_ids, int n, int k,
+                                      uint64_t *out, int cap, uint64_t *child, int child_cap,
+                                      int32_t *child_cnt, int *n_lists);
+/* Query with outputExpandedResult (--expand-taxid, Classifier.hpp:22, :792-838): child_cnt[64]
+ * = entries per reported id, child = the compact tax ids list after list; returns their total */
+int cfr_oracle_query_expanded(cfr_oracle *o, const cfr_oracle_param *p, const char *r1, const char *r2,
+                              cfr_oracle_result *res, uint64_t *child, int child_cap, int32_t *child_cnt);
+int cfr_oracle_format_tsv_expanded(const cfr_oracle *o, const char *read_id, const cfr_oracle_result *res,
+                                   const uint64_t *child, const int32_t *child_cnt, char *buf, size_t cap);
+
 /* SDUST masker (Dustmasker.hpp:357-421 + CentrifugerClass.cpp:276-316):
  * masks seq[0..n) in place with 'N'; returns the number of masked intervals */
 int cfr_oracle_dust_mask(char *seq, size_t n);
