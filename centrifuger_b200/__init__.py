@@ -31,7 +31,7 @@ class Params(C.Structure):
                 ("consider_secondary_hit_len", C.c_uint64),
                 ("consider_secondary_score_factor", C.c_double),
                 ("layout", C.c_int32), ("max_batch_reads", C.c_int32),
-                ("arena_rows", C.c_uint64)]
+                ("arena_rows", C.c_uint64), ("expand_taxid", C.c_int32), ("reserved_", C.c_int32)]
 
 
 class ReadBatch(C.Structure):
@@ -58,6 +58,7 @@ RESULT_DTYPE = np.dtype([("score", "<u8"), ("secondary_score", "<u8"), ("hit_len
 ABI_SYMBOLS = [
     "cfr_default_params", "cfr_open", "cfr_close", "cfr_last_error", "cfr_classify_batch",
     "cfr_submit_batch", "cfr_submit_batch_masked", "cfr_wait_batch", "cfr_batch_upload", "cfr_classify_resident", "cfr_batch_fetch", "cfr_batch_free",
+    "cfr_fetch_expanded", "cfr_batch_fetch_expanded",
     "cfr_host_alloc", "cfr_host_free", "cfr_index_info", "cfr_seq_name", "cfr_rank_name", "cfr_orig_taxid", "cfr_seq_taxid",
     "cfr_format_tsv", "cfr_taxon_counts_device", "cfr_taxon_counts_read", "cfr_taxon_counts_reset",
     "cfr_get_counters", "cfr_reset_counters", "cfr_set_profiling", "cfr_get_stage_times",
@@ -91,6 +92,8 @@ def load_library():
     L.cfr_batch_upload.argtypes = [vp, C.POINTER(ReadBatch), vp, C.POINTER(vp)]
     L.cfr_classify_resident.argtypes = [vp, vp, vp]
     L.cfr_batch_fetch.argtypes = [vp, vp, vp, vp, vp]
+    L.cfr_fetch_expanded.argtypes = [vp, C.c_int, vp, vp, vp, u64, C.POINTER(u64)]
+    L.cfr_batch_fetch_expanded.argtypes = [vp, vp, vp, vp, vp, u64, C.POINTER(u64), vp]
     L.cfr_batch_free.argtypes = [vp, vp]
     L.cfr_batch_free.restype = None
     L.cfr_host_alloc.argtypes = [C.c_size_t]
@@ -180,7 +183,7 @@ class Classifier:
 
     def __init__(self, idx_prefix, k=1, min_hit_len=0, hitk_factor=40, dust=True,
                  secondary_len=2000, secondary_factor=0.995, layout=LAYOUT_AUTO,
-                 device=0, max_batch_reads=0, arena_rows=0):
+                 device=0, max_batch_reads=0, arena_rows=0, expand_taxid=False):
         self.L = load_library()
         p = Params()
         self.L.cfr_default_params(C.byref(p))
@@ -189,6 +192,7 @@ class Classifier:
         p.consider_secondary_hit_len = secondary_len
         p.consider_secondary_score_factor = secondary_factor
         p.layout, p.max_batch_reads, p.arena_rows = layout, max_batch_reads, arena_rows
+        p.expand_taxid = 1 if expand_taxid else 0
         self.params = p
         self.k = k
         self.h = C.c_void_p()
@@ -296,6 +300,45 @@ class Classifier:
         self.wait(t.value)
         split = lambda m, o: [bytes(m[int(o[i]):int(o[i + 1])]) for i in range(n)]
         return res, ids.reshape(n, self.k), split(m1, o1), (split(m2, o2) if m2 is not None else None)
+
+    def _expansion_lists(self, res, fetch):
+        """fetch(exp_cnt, exp_off, exp_ids, cap, &n) -> per read, one list of compact tax ids per reported id"""
+        n = len(res)
+        cnt = np.zeros(max(1, n * self.k), dtype=np.uint32)
+        off = np.zeros(max(1, n), dtype=np.uint64)
+        need = C.c_uint64(0)
+        ids = np.zeros(1024, dtype=np.uint64)
+        st = fetch(_ptr(cnt), _ptr(off), _ptr(ids), len(ids), C.byref(need))
+        if st != 0 and need.value > len(ids):  # sized on the second try
+            ids = np.zeros(need.value, dtype=np.uint64)
+            st = fetch(_ptr(cnt), _ptr(off), _ptr(ids), len(ids), C.byref(need))
+        self._check(st)
+        out = []
+        for i in range(n):
+            at = int(off[i])
+            lists = []
+            for j in range(min(int(res["n_assign"][i]), self.k)):
+                c = int(cnt[i * self.k + j])
+                lists.append([int(x) for x in ids[at:at + c]])
+                at += c
+            out.append(lists)
+        return out
+
+    def classify_expanded(self, reads1, reads2=None):
+        """One batch with --expand-taxid (handle opened with expand_taxid=True): (results, ids, lists) where
+        lists[i][j] are the compact tax ids promoted into assignment j of read i (Classifier.hpp:807-838)."""
+        s1, o1 = pack_reads(reads1)
+        s2, o2 = pack_reads(reads2) if reads2 is not None else (None, None)
+        t, res, ids, keep = self.submit(s1, o1, s2, o2)
+        self.wait(t)
+        lists = self._expansion_lists(
+            res, lambda c, o, i, cap, n: self.L.cfr_fetch_expanded(self.h, t, c, o, i, cap, n))
+        return res, ids.reshape(-1, self.k) if len(reads1) else ids, lists
+
+    def fetch_expanded(self, batch, res, stream=None):
+        """the lists of a resident batch, after fetch()"""
+        return self._expansion_lists(
+            res, lambda c, o, i, cap, n: self.L.cfr_batch_fetch_expanded(self.h, batch.h, c, o, i, cap, n, stream))
 
     def upload(self, seq1, off1, seq2=None, off2=None, stream=None):
         n = len(off1) - 1

@@ -69,11 +69,14 @@ struct cfr_device_batch {
   DevBuf seq_raw, codes, mask_raw, mask, off, strand_hits, strand_nhits, fhits, work, rows, seq_ids, rec0, rec1, best, tmp,
       results, out_ids, deferred, dust_list, scalars;  // scalars: {u64 arena_used, u32 n_deferred, pad}
   DevBuf dust_bits, masked;  // only when the caller wants the masked reads back (cfr_submit_batch_masked)
+  DevBuf exp_cnt, exp_off, exp_ids;  // only with cfr_params.expand_taxid
+  int ticket = -1;                   // streaming ticket this slot last served
   bool want_masked = false;
   bool classified = false;
   void release() {
     DevBuf *all[] = {&seq_raw, &codes, &mask_raw, &mask, &off, &strand_hits, &strand_nhits, &fhits, &work, &rows, &seq_ids,
-                     &rec0, &rec1, &best, &tmp, &results, &out_ids, &deferred, &dust_list, &scalars, &dust_bits, &masked};
+                     &rec0, &rec1, &best, &tmp, &results, &out_ids, &deferred, &dust_list, &scalars, &dust_bits, &masked,
+                     &exp_cnt, &exp_off, &exp_ids};
     for (DevBuf *b : all) b->release();
   }
 };
@@ -431,6 +434,11 @@ int upload_chunk(cfr_handle *h, const cfr_read_batch *in, u64 r0, u64 r1, cfr_de
     if ((st = b->dust_bits.ensure(n_words * 4))) return st;
     if ((st = b->masked.ensure(b->seq_bytes + 64))) return st;
   }
+  if (h->params.expand_taxid) {  // a read's lists hold at most as many ids as it has arena rows
+    if ((st = b->exp_cnt.ensure(n * (u64)h->P.max_result * 4))) return st;
+    if ((st = b->exp_off.ensure(n * 8))) return st;
+    if ((st = b->exp_ids.ensure(arena * 8))) return st;
+  }
   // H2D
   if (len1) CUDA_TRY(cudaMemcpyAsync(b->seq_raw.p, in->seq1 + s1, len1, cudaMemcpyHostToDevice, s));
   if (len2) CUDA_TRY(cudaMemcpyAsync((char *)b->seq_raw.p + pos2, in->seq2 + s2, len2, cudaMemcpyHostToDevice, s));
@@ -489,6 +497,13 @@ void fill_chunk(cfr_handle *h, cfr_device_batch *b, ChunkDev &B) {
   B.taxon_counts = h->d_taxon;
   B.counters = h->d_counters;
   B.deferred = (u32 *)b->deferred.p;
+  if (h->params.expand_taxid) {
+    B.exp_cnt = (u32 *)b->exp_cnt.p;
+    B.exp_off = (u64 *)b->exp_off.p;
+    B.exp_ids = (u64 *)b->exp_ids.p;
+    B.exp_cap = b->arena_cap;
+    B.exp_used = (u64 *)((char *)b->scalars.p + 56);
+  }
   B.read_list = nullptr;
   B.n_list = b->n_reads;
 }
@@ -589,6 +604,28 @@ int check_device_errors(cfr_handle *h, cudaStream_t s) {
   CUDA_TRY(cudaMemcpyAsync(&flags, &h->d_counters[CFR_STAGE_SCORE].error_flags, 8, cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaStreamSynchronize(s));
   if (flags & 1ull) return fail(CFR_ERR_OVERFLOW, "taxonomy lineage deeper than the device path capacity");
+  if (flags & 2ull) return fail(CFR_ERR_OVERFLOW, "expanded tax id lists exceed the batch's list area; raise cfr_params.arena_rows");
+  return CFR_OK;
+}
+
+// D2H of the --expand-taxid lists of a finished batch
+int fetch_expanded(cfr_handle *h, cfr_device_batch *b, uint32_t *exp_cnt, uint64_t *exp_off, uint64_t *exp_ids,
+                   uint64_t exp_cap, uint64_t *exp_n, cudaStream_t s) {
+  if (!exp_cnt || !exp_off || !exp_n || (exp_cap && !exp_ids)) return fail(CFR_ERR_ARG, "null argument");
+  if (!h->params.expand_taxid) return fail(CFR_ERR_ARG, "the handle was opened without cfr_params.expand_taxid");
+  *exp_n = 0;
+  if (b->n_reads == 0) return CFR_OK;
+  u64 used = 0;
+  CUDA_TRY(cudaMemcpyAsync(&used, (char *)b->scalars.p + 56, 8, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  *exp_n = used;
+  if (used > exp_cap) return fail(CFR_ERR_OVERFLOW, "exp_ids is too small for this batch (see *exp_n)");
+  const u64 k = (u64)h->P.max_result;
+  CUDA_TRY(cudaMemcpyAsync(exp_cnt, b->exp_cnt.p, b->n_reads * k * 4, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaMemcpyAsync(exp_off, b->exp_off.p, b->n_reads * 8, cudaMemcpyDeviceToHost, s));
+  if (used) CUDA_TRY(cudaMemcpyAsync(exp_ids, b->exp_ids.p, used * 8, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  h->d2h_bytes += b->n_reads * (k * 4 + 8) + used * 8 + 8;
   return CFR_OK;
 }
 
@@ -610,6 +647,7 @@ void cfr_default_params(cfr_params *p) {
   p->layout = CFR_LAYOUT_AUTO;
   p->max_batch_reads = 0;
   p->arena_rows = 0;
+  p->expand_taxid = 0;
 }
 
 const char *cfr_last_error(void) { return g_err.c_str(); }
@@ -828,6 +866,14 @@ int cfr_batch_fetch(cfr_handle *h, cfr_device_batch *b, cfr_result *results, uin
   return check_device_errors(h, s);
 }
 
+int cfr_batch_fetch_expanded(cfr_handle *h, cfr_device_batch *b, uint32_t *exp_cnt, uint64_t *exp_off,
+                             uint64_t *exp_ids, uint64_t exp_cap, uint64_t *exp_n, void *stream) {
+  if (!h || !b) return fail(CFR_ERR_ARG, "null argument");
+  if (!b->classified) return fail(CFR_ERR_ARG, "batch was not classified");
+  CUDA_TRY(cudaSetDevice(h->device));
+  return fetch_expanded(h, b, exp_cnt, exp_off, exp_ids, exp_cap, exp_n, pick_stream(h, stream));
+}
+
 void cfr_batch_free(cfr_handle *h, cfr_device_batch *b) {
   if (!b) return;
   if (h) cudaSetDevice(h->device);
@@ -933,6 +979,7 @@ int cfr_classify_batch(cfr_handle *h, const cfr_read_batch *in, cfr_result *resu
     }
     starts[slot] = r0;
     b->want_masked = false;
+    b->ticket = -1;  // the slot no longer holds a streaming batch
     if ((st = upload_chunk(h, in, r0, r1, b, h->s_in))) return st;
     CUDA_TRY(cudaEventRecord(h->ev_h2d[slot], h->s_in));
     CUDA_TRY(cudaStreamWaitEvent(h->s_comp[slot], h->ev_h2d[slot], 0));
@@ -1017,6 +1064,7 @@ int cfr_submit_batch_masked(cfr_handle *h, const cfr_read_batch *in, cfr_result 
   CUDA_TRY(cudaMemcpyAsync(&h->pinned_scalars[slot], b->scalars.p, 16, cudaMemcpyDeviceToHost, h->s_out));
   CUDA_TRY(cudaEventRecord(h->ev_d2h[slot], h->s_out));
   if (h->trace) cudaEventRecord(h->tr_ev[slot][3], h->s_out);
+  b->ticket = h->next_ticket;
   h->jobs[slot].ticket = h->next_ticket;
   h->jobs[slot].results = results;
   h->jobs[slot].ids = ids;
@@ -1040,6 +1088,19 @@ int cfr_wait_batch(cfr_handle *h, int ticket) {
             t[0], t[1], t[2], t[3], h->tr_host_submit[slot]);
   }
   return rc;
+}
+
+int cfr_fetch_expanded(cfr_handle *h, int ticket, uint32_t *exp_cnt, uint64_t *exp_off, uint64_t *exp_ids,
+                       uint64_t exp_cap, uint64_t *exp_n) {
+  if (!h || ticket < 0) return fail(CFR_ERR_ARG, "bad ticket");
+  CUDA_TRY(cudaSetDevice(h->device));
+  const int slot = ticket % cfr_handle::NSLOT;
+  if (h->slots[slot].ticket != ticket) return fail(CFR_ERR_ARG, "the batch of this ticket has left the device (fetch before submitting three more)");
+  if (h->jobs[slot].ticket == ticket) {  // not waited for yet
+    const int st = job_finish(h, slot);
+    if (st) return st;
+  }
+  return fetch_expanded(h, &h->slots[slot], exp_cnt, exp_off, exp_ids, exp_cap, exp_n, h->s_comp[slot]);
 }
 
 const char *cfr_seq_name(const cfr_handle *h, uint64_t seq_id) {

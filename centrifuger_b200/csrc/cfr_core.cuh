@@ -1068,6 +1068,148 @@ CFR_HD int tax_reduce(const DevIndex &ix, const u64 *tax_ids, int cnt, int k, u6
   return 1;
 }
 
+// Where the lineage of `x` leaves the backbone `path` (Taxonomy::LCA, Taxonomy.hpp:775-813): both root
+// paths are aligned at their root ends and compared from the top; returns the highest aligned index
+// that differs (plen - tlen - 1 ... when the whole aligned window agrees) and, in `node`, x's lineage
+// node at that index (~0u when x's path does not reach down to it).  x is not a root-level node.
+CFR_HD int tax_divergence(const DevIndex &ix, const u32 *path, int plen, u32 x, u32 &node) {
+  const u32 root = (u32)ix.root;
+  int tlen = 0;
+  u32 t = x;
+  do {
+    ++tlen;
+    t = tax_parent(ix, t);
+  } while (t != tax_parent(ix, t));
+  ++tlen;  // the pushed root
+  int ib, it;
+  if (tlen >= plen) {
+    it = tlen - plen;
+    ib = 0;
+  } else {
+    it = 0;
+    ib = plen - tlen;
+  }
+  t = x;
+  u32 above = ~0u;  // x's lineage node one step below the aligned window (index ib - 1), if it has one
+  for (int s = 0; s < it; ++s) {
+    above = t;
+    t = tax_parent(ix, t);
+  }
+  int last_mismatch = ib - 1;
+  node = above;
+  for (int q = ib; q < plen; ++q, ++it) {
+    const u32 here = (it == tlen - 1) ? root : t;
+    if (here != path[q]) {
+      last_mismatch = q;
+      node = here;
+    }
+    if (it < tlen - 1) t = tax_parent(ix, t);
+  }
+  return last_mismatch;
+}
+
+// The child lists of Taxonomy::ReduceTaxIds / LCA (promotedChildTaxIds / lcaChildTaxIds, used by
+// --expand-taxid: Taxonomy.hpp:767-773, :811-812, :825-831, :871-878, :938-971), computed after
+// tax_reduce() on the same ids.  promoted[0..np) is what tax_reduce returned.  Writes list after
+// list to `child` (room for cnt ids; child_cnt[i] = length of list i) and returns the total; lists
+// the classifier would not print (Classifier.hpp:823) have length 0.  `scratch` has room for cnt ids.
+CFR_HD int tax_expand(const DevIndex &ix, const u64 *tax_ids, int cnt, int k, const u64 *promoted, int np,
+                      u64 *scratch, u64 *child, u32 *child_cnt, u64 *err_flags) {
+  for (int i = 0; i < np; ++i) child_cnt[i] = 0;
+  for (int i = 0; i < cnt; ++i)
+    if (tax_ids[i] >= ix.node_cnt) {  // :871-878: every input id, as given
+      for (int j = 0; j < cnt; ++j) child[j] = tax_ids[j];
+      child_cnt[0] = (u32)cnt;
+      return cnt;
+    }
+  if (k == 1) {
+    const u32 root = (u32)ix.root;
+    int kk = 0;
+    while (kk < cnt && (u32)tax_ids[kk] == root) ++kk;
+    if (kk >= cnt) return 0;  // all root: the list stays empty (:756)
+    u32 path[CFR_TAX_PATH_CAP];
+    int plen = 0;
+    u32 t = (u32)tax_ids[kk];
+    do {
+      if (plen >= CFR_TAX_PATH_CAP - 1) {
+        *err_flags |= 1ull;
+        return 0;
+      }
+      path[plen++] = t;
+      t = tax_parent(ix, t);
+    } while (t != tax_parent(ix, t));
+    path[plen++] = root;
+    // the answer is the backbone node just above the highest divergence; the list holds the backbone
+    // node below it and the nodes where the other lineages leave the backbone right there
+    int j = 0;
+    for (int i = 0; i < cnt; ++i) {
+      const u32 x = (u32)tax_ids[i];
+      if (i == kk || x == tax_parent(ix, x)) continue;
+      u32 node;
+      const int m = tax_divergence(ix, path, plen, x, node);
+      if (m + 1 > j) j = m + 1;
+    }
+    int nc = 0;
+    if (j >= 1) scratch[nc++] = path[j - 1];
+    for (int i = 0; i < cnt; ++i) {
+      const u32 x = (u32)tax_ids[i];
+      if (i == kk || x == tax_parent(ix, x)) continue;
+      u32 node;
+      const int m = tax_divergence(ix, path, plen, x, node);
+      if (m + 1 == j && node != ~0u) scratch[nc++] = node;
+    }
+    sort_u64(scratch, nc);
+    nc = unique_u64(scratch, nc);
+    for (int i = 0; i < nc; ++i) child[i] = scratch[i];
+    child_cnt[0] = (u32)nc;
+    return nc;
+  }
+  // rank promotion: find the level tax_reduce stopped at, then group the level below by promoted node
+  const int unknown = ix.rank_num[0];
+  int ri = 0, m = 0;
+  for (; ri < unknown; ++ri) {
+    m = 0;
+    for (int i = 0; i < cnt; ++i) {
+      const u32 node = tax_node_at_level(ix, (u32)tax_ids[i], ri);
+      if (node != ~0u) scratch[m++] = node;
+    }
+    sort_u64(scratch, m);
+    m = unique_u64(scratch, m);
+    if (m <= k) break;
+  }
+  if (ri >= unknown || m == 0 || ri == 0) return 0;  // root by default (:939-940) or nothing promoted (:941)
+  m = 0;
+  for (int i = 0; i < cnt; ++i) {
+    const u32 node = tax_node_at_level(ix, (u32)tax_ids[i], ri - 1);
+    if (node != ~0u) scratch[m++] = node;
+  }
+  sort_u64(scratch, m);
+  m = unique_u64(scratch, m);
+  int total = 0;
+  for (int q = 0; q < m; ++q) {  // :953-970
+    const u32 c = (u32)scratch[q];
+    u32 t = c;
+    int owner = -1;
+    while (t != tax_parent(ix, t)) {
+      t = tax_parent(ix, t);
+      const int rn = tax_level_of(ix, t);
+      if (rn > ri) break;
+      if (rn == ri) {
+        for (int i = 0; i < np; ++i)
+          if ((u32)promoted[i] == t) owner = i;
+        break;
+      }
+    }
+    if (owner >= 0) child[total++] = ((u64)owner << 32) | c;
+  }
+  sort_u64(child, total);  // by promoted node, ascending ids inside (the order of the reference's map walk)
+  for (int q = 0; q < total; ++q) {
+    ++child_cnt[child[q] >> 32];
+    child[q] &= 0xffffffffull;
+  }
+  return total;
+}
+
 // ---------------------------------------------------------------------------
 // Classifier: scoring (GetClassificationFromHits after the locate walks)
 // ---------------------------------------------------------------------------
@@ -1109,7 +1251,7 @@ CFR_HD SeqRec *rec_get(RecTable &t, u32 seq_id, bool &created) {
 // capacity each (a hit contributes at most row_cnt distinct ids).
 CFR_HD void score_read(const DevIndex &ix, const DevParams &p, const FinalHit *hits, int hit_cnt, u32 *seq_ids,
                        SeqRec *rec0, SeqRec *rec1, u64 *best, u64 *tmp, DevResult &res, u64 *out_ids,
-                       u64 *err_flags) {
+                       u64 *err_flags, int *nb_out = nullptr) {
   const int mhl = p.min_hit_len;
   RecTable rec[2] = {{rec0, 0}, {rec1, 0}};
   u32 prev_seq = 0;
@@ -1259,6 +1401,7 @@ CFR_HD void score_read(const DevIndex &ix, const DevParams &p, const FinalHit *h
     res.n_assign = tax_reduce(ix, best, nb, p.max_result, tmp, out_ids, err_flags);
     res.by_rank = 1;
   }
+  if (nb_out) *nb_out = nb;  // best[0..nb) now holds the compact tax ids that were reduced (by_rank) or the seq ids
 }
 
 // ---------------------------------------------------------------------------

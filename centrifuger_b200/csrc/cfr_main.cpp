@@ -1,7 +1,7 @@
 // cfr_main.cpp -- `centrifuger-b200`: drop-in for the reference's classification
 // binary (CentrifugerClass.cpp) on the paths this repo covers: same -x/-1/-2/-u/-i/
 // -t/-k/--min-hitlen/--hitk-factor/--no-dust/--consider-secondary/--un/--cl/
-// --merge-readpair/-h/-v options, the reference's own *.cfr index files, the identical
+// --merge-readpair/--expand-taxid/-h/-v options, the reference's own *.cfr index files, the identical
 // TSV on stdout and the same log lines on stderr.  All classification work is done by
 // libcfrb200.so on the GPU (include/centrifuger_b200.h); this file is host I/O only:
 // gz FASTA/FASTQ parsing (ReadFiles.hpp + kseq.h behaviour) on an ingest thread (mate 2
@@ -9,7 +9,7 @@
 // ResultWriter-style output on an output thread.
 //
 // Not supported (the reference's single-cell extras, SURVEY.md 8 "out of scope"):
-// --expand-taxid, barcode/UMI/read-format options, --sample-sheet.  They are rejected
+// barcode/UMI/read-format options, --sample-sheet.  They are rejected
 // with a log line and EXIT_FAILURE.
 #include <getopt.h>
 #include <sys/stat.h>
@@ -49,6 +49,7 @@ static const char usage[] =
     "\t--un STR: output unclassified reads to files with the prefix of <str>\n"
     "\t--cl STR: output classified reads to files with the prefix of <str>\n"
     "\t--merge-readpair: merge overlapped paired-end reads and trim adapters [no merge]\n"
+    "\t--expand-taxid: output the tax IDs that are promoted to the final report tax ID [no]\n"
     "\t--no-dust: do not DUST-mask low-complexity regions of reads [mask]\n"
     "\t--min-hitlen INT: minimum length of partial hits [auto]\n"
     "\t--hitk-factor INT: resolve at most <int>*k entries for each hit [40; use 0 for no restriction]\n"
@@ -61,7 +62,7 @@ static const char usage[] =
 
 enum {
   ARGV_NO_DUST = 256, ARGV_MIN_HITLEN, ARGV_HITK, ARGV_SECONDARY, ARGV_GPU, ARGV_BATCH, ARGV_LAYOUT,
-  ARGV_UNSUPPORTED, ARGV_DRY_RUN, ARGV_DRY_PIPE, ARGV_UN, ARGV_CL, ARGV_MERGE
+  ARGV_UNSUPPORTED, ARGV_DRY_RUN, ARGV_DRY_PIPE, ARGV_UN, ARGV_CL, ARGV_MERGE, ARGV_EXPAND
 };
 
 static const char *short_options = "x:1:2:u:i:o:t:k:hv";
@@ -78,7 +79,7 @@ static struct option long_options[] = {
     {"un", required_argument, 0, ARGV_UN},
     {"cl", required_argument, 0, ARGV_CL},
     {"merge-readpair", no_argument, 0, ARGV_MERGE},
-    {"expand-taxid", no_argument, 0, ARGV_UNSUPPORTED},
+    {"expand-taxid", no_argument, 0, ARGV_EXPAND},
     {"read-format", required_argument, 0, ARGV_UNSUPPORTED},
     {"barcode", required_argument, 0, ARGV_UNSUPPORTED},
     {"UMI", required_argument, 0, ARGV_UNSUPPORTED},
@@ -345,6 +346,9 @@ struct Batch {
   std::vector<uint64_t> off1, off2;
   std::vector<cfr_result> results;
   std::vector<uint64_t> assign;
+  // --expand-taxid only: the ids promoted into each assignment (cfr_fetch_expanded layout)
+  std::vector<uint32_t> exp_cnt;
+  std::vector<uint64_t> exp_off, exp_ids;
   // --un / --cl only: quality strings (empty for a FASTA record) and the reads as classified
   // (DUST intervals as 'N'), which is what the reference writes (ResultWriter.hpp:244-262)
   std::string qual1, qual2, masked1, masked2;
@@ -517,6 +521,7 @@ int main(int argc, char *argv[]) {
     } else if (c == ARGV_DRY_RUN) dryRun = true;
     else if (c == ARGV_DRY_PIPE) dryPipe = true;
     else if (c == ARGV_MERGE) mergePairs = true;
+    else if (c == ARGV_EXPAND) params.expand_taxid = 1;  // classifierParam.outputExpandedResult, CentrifugerClass.cpp:453-456
     else if (c == ARGV_UN) unPrefix = optarg;
     else if (c == ARGV_CL) clPrefix = optarg;
     else if (c == ARGV_UNSUPPORTED) {
@@ -599,6 +604,7 @@ int main(int argc, char *argv[]) {
   // the GPU classifies batch i and the output thread formats batch i-1 (ResultWriter::Output,
   // ResultWriter.hpp:199-236; rows in input order as in CentrifugerClass.cpp:690).
   const int k = params.max_result;
+  const bool expandTaxid = params.expand_taxid != 0;  // --expand-taxid: one more TSV column
   enum { NBATCH = 5 };  // ingest (1) + in flight on the GPU (3) + output (1)
   Batch batches[NBATCH];
   Slot<Batch *> free_slots[NBATCH];
@@ -728,7 +734,9 @@ int main(int argc, char *argv[]) {
     std::string out, rec;
     out.reserve(64 << 20);
     // ResultWriter::OutputHeader (ResultWriter.hpp:186-197)
-    out += "readID\tseqID\ttaxID\tscore\t2ndBestScore\thitLength\tqueryLength\tnumMatches\n";
+    out += "readID\tseqID\ttaxID\tscore\t2ndBestScore\thitLength\tqueryLength\tnumMatches";
+    if (expandTaxid) out += "\texpandedTaxIDs";
+    out += '\n';
     int bi = 0;
     for (;;) {
       Batch *bt = to_out.take();
@@ -741,6 +749,7 @@ int main(int argc, char *argv[]) {
         if (r.n_assign > 0) {
           ++classifiedCnt;
           const int m = r.n_assign < k ? r.n_assign : k;
+          uint64_t ex_at = expandTaxid ? bt->exp_off[i] : 0;
           for (int j = 0; j < m; ++j) {
             const uint64_t a = bt->assign[i * (size_t)k + j];
             const char *nm = r.by_rank ? cfr_rank_name(h, a) : cfr_seq_name(h, a);
@@ -756,7 +765,20 @@ int main(int argc, char *argv[]) {
             p = put_u64(p, r.secondary_score); *p++ = '\t';
             p = put_i32(p, r.hit_length); *p++ = '\t';
             p = put_i32(p, r.query_length); *p++ = '\t';
-            p = put_i32(p, r.n_assign); *p++ = '\n';
+            p = put_i32(p, r.n_assign);
+            if (expandTaxid) {  // ResultWriter.hpp:226-227: the original ids of the promoted nodes, comma separated
+              *p++ = '\t';
+              const uint32_t cnt = bt->exp_cnt[i * (size_t)k + j];
+              const size_t used = (size_t)(p - out.data());
+              out.resize(used + (size_t)cnt * 21 + 8);
+              p = &out[used];
+              for (uint32_t q = 0; q < cnt; ++q) {
+                if (q) *p++ = ',';
+                p = put_u64(p, cfr_orig_taxid(h, bt->exp_ids[ex_at + q]));
+              }
+              ex_at += cnt;
+            }
+            *p++ = '\n';
             out.resize((size_t)(p - out.data()));
           }
         } else {
@@ -765,7 +787,9 @@ int main(int argc, char *argv[]) {
           p = put_str(p, id, idn);
           p = put_str(p, "\tunclassified\t0\t0\t0\t0\t", 22);
           p = put_i32(p, r.query_length);
-          p = put_str(p, "\t1\n", 3);
+          p = put_str(p, "\t1", 2);
+          if (expandTaxid) *p++ = '\t';  // PrintExtraCol(""), ResultWriter.hpp:239-240
+          *p++ = '\n';
           out.resize((size_t)(p - out.data()));
         }
         if (out.size() > (48u << 20)) {
@@ -820,6 +844,22 @@ int main(int argc, char *argv[]) {
       PrintLog("ERROR: %s", cfr_last_error());
       rc = EXIT_FAILURE;
       pb->n = 0;
+    }
+    if (expandTaxid && tk >= 0 && pb->n > 0) {  // the lists leave the device before this slot's next batch
+      pb->exp_cnt.resize(pb->n * (size_t)k);
+      pb->exp_off.resize(pb->n);
+      if (pb->exp_ids.size() < 4096) pb->exp_ids.resize(4096);
+      uint64_t need = 0;
+      int est = cfr_fetch_expanded(h, tk, pb->exp_cnt.data(), pb->exp_off.data(), pb->exp_ids.data(), pb->exp_ids.size(), &need);
+      if (est != CFR_OK && need > pb->exp_ids.size()) {
+        pb->exp_ids.resize(need);
+        est = cfr_fetch_expanded(h, tk, pb->exp_cnt.data(), pb->exp_off.data(), pb->exp_ids.data(), pb->exp_ids.size(), &need);
+      }
+      if (est != CFR_OK) {
+        PrintLog("ERROR: %s", cfr_last_error());
+        rc = EXIT_FAILURE;
+        pb->n = 0;
+      }
     }
     to_out.put(pb);
   };

@@ -55,6 +55,12 @@ struct ChunkDev {
   u64 *out_ids;        // [n_reads * max_result]
   u64 *taxon_counts;   // [node_cnt + 3]
   DevCounters *counters;
+  // optional (--expand-taxid): the ids promoted into each reported id, Classifier.hpp:807-838
+  u32 *exp_cnt;   // [n_reads * max_result] list lengths (nullptr = not requested)
+  u64 *exp_off;   // [n_reads] start of the read's lists in exp_ids
+  u64 *exp_ids;   // compact tax ids, list after list
+  u64 exp_cap;
+  u64 *exp_used;  // next free entry of exp_ids
   // reads that did not fit the arena in this pass
   u32 *deferred;
   u32 *n_deferred;
@@ -99,6 +105,17 @@ CFR_HD u64 warp_claim(u64 *counter, bool want) {
 #endif
 }
 
+
+// n consecutive entries of a shared output area
+CFR_HD u64 claim_entries(u64 *counter, u64 n) {
+#if defined(__CUDA_ARCH__)
+  return atomicAdd(counter, n);
+#else
+  const u64 at = *counter;
+  *counter += n;
+  return at;
+#endif
+}
 
 // ------------------------------------------------------------------ encode
 // word w of the batch buffer: 32 uploaded bytes -> 2-bit codes + N bits
@@ -616,9 +633,28 @@ CFR_HD int score_stage(const DevIndex &ix, const DevParams &P, const ChunkDev &B
   res.by_rank = 0;
   u64 *out = B.out_ids + read * (u64)P.max_result;
   const u64 a = w.arena_base;
+  int nb = 0;
   score_read(ix, P, fh, (int)w.n_hits, B.seq_ids + a, B.rec0 + a, B.rec1 + a, B.best + a, B.tmp + a, res, out,
-             err_flags);
+             err_flags, &nb);
   for (int i = res.n_assign; i < P.max_result; ++i) out[i] = 0;  // unused id slots read as 0
+  if (B.exp_cnt) {
+    u32 *cc = B.exp_cnt + read * (u64)P.max_result;
+    for (int i = 0; i < P.max_result; ++i) cc[i] = 0;
+    B.exp_off[read] = 0;
+    if (res.by_rank) {  // the scoring records are done with: their space holds the lists until they are copied out
+      u64 *lists = reinterpret_cast<u64 *>(B.rec0 + a);
+      const int total = tax_expand(ix, B.best + a, nb, P.max_result, out, res.n_assign, B.tmp + a, lists, cc, err_flags);
+      if (total > 0) {
+        const u64 at = claim_entries(B.exp_used, (u64)total);
+        if (at + (u64)total <= B.exp_cap) {
+          for (int i = 0; i < total; ++i) B.exp_ids[at + i] = lists[i];
+          B.exp_off[read] = at;
+        } else {
+          *err_flags |= 2ull;
+        }
+      }
+    }
+  }
   B.results[read] = res;
   return res.n_assign;
 }

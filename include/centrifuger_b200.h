@@ -56,6 +56,10 @@ typedef struct {
   int32_t layout;                    /* cfr_layout */
   int32_t max_batch_reads;           /* device chunk size, 0 = default */
   uint64_t arena_rows;               /* locate work-area rows per chunk, 0 = default */
+  int32_t expand_taxid;              /* --expand-taxid (_classifierParam.outputExpandedResult, Classifier.hpp:22):
+                                        keep the ids that were promoted into each reported id; read them
+                                        with cfr_fetch_expanded / cfr_batch_fetch_expanded  [0] */
+  int32_t reserved_;
 } cfr_params;
 
 /* One batch of reads, structure-of-arrays, HOST memory (pinned recommended).
@@ -131,12 +135,27 @@ int cfr_wait_batch(cfr_handle *h, int ticket);
 int cfr_submit_batch_masked(cfr_handle *h, const cfr_read_batch *in, cfr_result *results, uint64_t *ids,
                             char *masked1, char *masked2, void *stream, int *ticket);
 
+/* The expandedTaxIDs column of --expand-taxid (Classifier.hpp:807-838 fills
+ * _classifierResult::expandedTaxIdStrings from the child lists of Taxonomy::ReduceTaxIds / LCA,
+ * Taxonomy.hpp:767-831, :871-878, :938-971).  For a handle opened with cfr_params.expand_taxid, after
+ * cfr_wait_batch(ticket) and before three more batches are submitted:
+ *   exp_cnt[i*max_result + j] = number of ids promoted into assignment j of read i (0 when the read was
+ *                               not reduced by rank, or the reference prints an empty string);
+ *   exp_off[i]                = where read i's lists start in exp_ids (list j follows list j-1);
+ *   exp_ids                   = compact taxonomy ids (print with cfr_orig_taxid), *exp_n of them.
+ * exp_cap = entries exp_ids can hold; CFR_ERR_OVERFLOW (and *exp_n = the number needed) if too small. */
+int cfr_fetch_expanded(cfr_handle *h, int ticket, uint32_t *exp_cnt, uint64_t *exp_off, uint64_t *exp_ids,
+                       uint64_t exp_cap, uint64_t *exp_n);
+
 /* Same work with the batch already resident in HBM (kernel-only timing;
  * multi-GPU shards).  upload = H2D + layout; classify_resident = kernels
  * only, asynchronous on `stream`; fetch = D2H + synchronize. */
 int cfr_batch_upload(cfr_handle *h, const cfr_read_batch *in, void *stream, cfr_device_batch **out);
 int cfr_classify_resident(cfr_handle *h, cfr_device_batch *b, void *stream);
 int cfr_batch_fetch(cfr_handle *h, cfr_device_batch *b, cfr_result *results, uint64_t *ids, void *stream);
+/* cfr_fetch_expanded for a resident batch, after cfr_batch_fetch */
+int cfr_batch_fetch_expanded(cfr_handle *h, cfr_device_batch *b, uint32_t *exp_cnt, uint64_t *exp_off,
+                             uint64_t *exp_ids, uint64_t exp_cap, uint64_t *exp_n, void *stream);
 void cfr_batch_free(cfr_handle *h, cfr_device_batch *b);
 
 /* Page-locked host memory for read / result buffers (cudaHostAlloc), so callers that do

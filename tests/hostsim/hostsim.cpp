@@ -199,6 +199,18 @@ int hostsim_reduce_taxids(void *hh, const uint64_t *tax_ids, int cnt, int k, uin
   return n;
 }
 
+// the child lists (tax_expand) for the same ids; child_cnt has max(k,1) slots; returns the total
+int hostsim_expand_taxids(void *hh, const uint64_t *tax_ids, int cnt, int k, uint64_t *child, uint32_t *child_cnt) {
+  HostIndex *h = (HostIndex *)hh;
+  std::vector<u64> scratch(cnt + 1), o(cnt + 1 + (k > 0 ? k : 1)), c(cnt + 1);
+  u64 err = 0;
+  const int n = tax_reduce(h->ix, (const u64 *)tax_ids, cnt, k, scratch.data(), o.data(), &err);
+  const int total = tax_expand(h->ix, (const u64 *)tax_ids, cnt, k, o.data(), n, scratch.data(), c.data(), child_cnt, &err);
+  if (err) return -1;
+  for (int i = 0; i < total; ++i) child[i] = c[i];
+  return total;
+}
+
 void hostsim_dust(const char *in, int n, char *out) {
   static DustState d;
   memcpy(out, in, (size_t)n);
@@ -243,9 +255,11 @@ int hostsim_dust_screen(const char *in, int n) {
   return dust_screen_stage(B, 0) ? 1 : 0;
 }
 
-// the whole pipeline for one batch; arena_rows small values exercise the deferral loop
-int hostsim_classify(void *hh, int dust, uint64_t arena_rows, const cfr_read_batch *in, cfr_result *results,
-                     uint64_t *ids, cfr_counters *counters) {
+// the whole pipeline for one batch; arena_rows small values exercise the deferral loop.
+// exp_cnt != NULL asks for the --expand-taxid lists (exp_cnt[n*k], exp_off[n], exp_ids[exp_cap]).
+int hostsim_classify_expanded(void *hh, int dust, uint64_t arena_rows, const cfr_read_batch *in, cfr_result *results,
+                              uint64_t *ids, cfr_counters *counters, uint32_t *exp_cnt, uint64_t *exp_off,
+                              uint64_t *exp_ids, uint64_t exp_cap, uint64_t *exp_n) {
   HostIndex *h = (HostIndex *)hh;
   const DevIndex &ix = h->ix;
   const DevParams &P = h->P;
@@ -314,6 +328,14 @@ int hostsim_classify(void *hh, int dust, uint64_t arena_rows, const cfr_read_bat
   B.counters = &cnt;
   B.deferred = deferred.data();
   B.n_deferred = &n_deferred;
+  u64 exp_used = 0;
+  if (exp_cnt) {
+    B.exp_cnt = exp_cnt;
+    B.exp_off = (u64 *)exp_off;
+    B.exp_ids = (u64 *)exp_ids;
+    B.exp_cap = exp_cap;
+    B.exp_used = &exp_used;
+  }
   OpCount oc{};
   static DustState ds;
   for (u64 w = 0; w < n_words; ++w) encode_stage(B, w, len1 + len2);
@@ -378,6 +400,7 @@ int hostsim_classify(void *hh, int dust, uint64_t arena_rows, const cfr_read_bat
     first = false;
   }
   if (err_flags) return CFR_ERR_OVERFLOW;
+  if (exp_n) *exp_n = exp_used;
   for (u64 i = 0; i < n; ++i) {
     results[i].score = res[i].score;
     results[i].secondary_score = res[i].secondary_score;
@@ -399,6 +422,11 @@ int hostsim_classify(void *hh, int dust, uint64_t arena_rows, const cfr_read_bat
     counters->n_reads = n;
   }
   return 0;
+}
+
+int hostsim_classify(void *hh, int dust, uint64_t arena_rows, const cfr_read_batch *in, cfr_result *results,
+                     uint64_t *ids, cfr_counters *counters) {
+  return hostsim_classify_expanded(hh, dust, arena_rows, in, results, ids, counters, nullptr, nullptr, nullptr, 0, nullptr);
 }
 
 }  // extern "C"

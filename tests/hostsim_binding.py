@@ -23,7 +23,7 @@ class Params(C.Structure):
                 ("consider_secondary_hit_len", C.c_uint64),
                 ("consider_secondary_score_factor", C.c_double),
                 ("layout", C.c_int32), ("max_batch_reads", C.c_int32),
-                ("arena_rows", C.c_uint64)]
+                ("arena_rows", C.c_uint64), ("expand_taxid", C.c_int32), ("reserved_", C.c_int32)]
 
 
 class ReadBatch(C.Structure):
@@ -100,6 +100,12 @@ def lib():
         L.hostsim_locate.argtypes = [C.c_void_p, C.c_uint64]
         L.hostsim_reduce_taxids.restype = C.c_int
         L.hostsim_reduce_taxids.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.c_int, C.c_int, C.POINTER(C.c_uint64)]
+        L.hostsim_expand_taxids.restype = C.c_int
+        L.hostsim_expand_taxids.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.c_int, C.c_int, C.POINTER(C.c_uint64),
+                                            C.POINTER(C.c_uint32)]
+        L.hostsim_classify_expanded.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.POINTER(ReadBatch), C.c_void_p,
+                                                C.c_void_p, C.POINTER(Counters), C.c_void_p, C.c_void_p, C.c_void_p,
+                                                C.c_uint64, C.POINTER(C.c_uint64)]
         L.hostsim_dust.argtypes = [C.c_char_p, C.c_int, C.c_char_p]
         L.hostsim_dust_screen.argtypes = [C.c_char_p, C.c_int]
         L.hostsim_dust_screen.restype = C.c_int
@@ -161,6 +167,39 @@ class HostSim:
         n = self.L.hostsim_reduce_taxids(self.h, arr, len(tax_ids), k, out)
         return [int(out[i]) for i in range(n)]
 
+    def expand_taxids(self, tax_ids, k):
+        """(promoted ids, child lists) of the scoring stage's tax_reduce + tax_expand"""
+        ids = self.reduce_taxids(tax_ids, k)
+        arr = (C.c_uint64 * len(tax_ids))(*tax_ids)
+        child = (C.c_uint64 * (len(tax_ids) + 1))()
+        cnt = (C.c_uint32 * (max(k, 1) + 1))()
+        total = self.L.hostsim_expand_taxids(self.h, arr, len(tax_ids), k, child, cnt)
+        assert total >= 0
+        lists, at = [], 0
+        for i in range(len(ids)):
+            lists.append([int(x) for x in child[at:at + cnt[i]]])
+            at += cnt[i]
+        assert at == total
+        return ids, lists
+
+    def classify_expanded(self, reads1, reads2=None, arena_rows=0):
+        """classify() plus, per read, the list of child-id lists (one per reported id)"""
+        b, keep = make_batch(reads1, reads2)
+        n, k = len(reads1), self.p.max_result
+        res = np.zeros(n, dtype=RESULT_DTYPE)
+        ids = np.zeros(max(1, n * k), dtype=np.uint64)
+        exp_cnt = np.zeros(max(1, n * k), dtype=np.uint32)
+        exp_off = np.zeros(max(1, n), dtype=np.uint64)
+        cap = 64 * n + 1024
+        exp_ids = np.zeros(cap, dtype=np.uint64)
+        exp_n = C.c_uint64(0)
+        st = self.L.hostsim_classify_expanded(self.h, self.p.dust, arena_rows, C.byref(b), res.ctypes.data,
+                                              ids.ctypes.data, None, exp_cnt.ctypes.data, exp_off.ctypes.data,
+                                              exp_ids.ctypes.data, cap, C.byref(exp_n))
+        if st != 0:
+            raise RuntimeError("hostsim_classify_expanded status %d" % st)
+        return res, ids.reshape(-1, k) if n else ids, expansion_lists(res, exp_cnt, exp_off, exp_ids, k)
+
     def classify(self, reads1, reads2=None, arena_rows=0):
         b, keep = make_batch(reads1, reads2)
         n = len(reads1)
@@ -184,4 +223,18 @@ def result_tuples(res, ids, k):
         out.append((int(res["score"][i]), int(res["secondary_score"][i]), int(res["hit_length"][i]),
                     int(res["query_length"][i]), n, int(res["by_rank"][i]),
                     tuple(int(x) for x in ids[i][:m])))
+    return out
+
+
+def expansion_lists(res, exp_cnt, exp_off, exp_ids, k):
+    """per read: one list of compact tax ids per reported id (cfr_fetch_expanded layout)"""
+    out = []
+    for i in range(len(res)):
+        at = int(exp_off[i])
+        lists = []
+        for j in range(min(int(res["n_assign"][i]), k)):
+            c = int(exp_cnt[i * k + j])
+            lists.append([int(x) for x in exp_ids[at:at + c]])
+            at += c
+        out.append(lists)
     return out

@@ -89,6 +89,18 @@ def lib():
         L.cfr_oracle_reduce_taxids.restype = C.c_int
         L.cfr_oracle_reduce_taxids.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.c_int, C.c_int,
                                                C.POINTER(C.c_uint64), C.c_int]
+        L.cfr_oracle_reduce_taxids_expanded.restype = C.c_int
+        L.cfr_oracle_reduce_taxids_expanded.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.c_int, C.c_int,
+                                                        C.POINTER(C.c_uint64), C.c_int, C.POINTER(C.c_uint64),
+                                                        C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int)]
+        L.cfr_oracle_query_expanded.restype = C.c_int
+        L.cfr_oracle_query_expanded.argtypes = [C.c_void_p, C.POINTER(Param), C.c_char_p, C.c_char_p,
+                                                C.POINTER(Result), C.POINTER(C.c_uint64), C.c_int,
+                                                C.POINTER(C.c_int32)]
+        L.cfr_oracle_format_tsv_expanded.restype = C.c_int
+        L.cfr_oracle_format_tsv_expanded.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(Result),
+                                                     C.POINTER(C.c_uint64), C.POINTER(C.c_int32), C.c_char_p,
+                                                     C.c_size_t]
         L.cfr_oracle_dust_mask.restype = C.c_int
         L.cfr_oracle_dust_mask.argtypes = [C.c_char_p, C.c_size_t]
         L.cfr_oracle_format_tsv.restype = C.c_int
@@ -206,6 +218,42 @@ class Oracle:
         out = (C.c_uint64 * (len(tax_ids) + 1))()
         n = self.L.cfr_oracle_reduce_taxids(self.h, arr, len(tax_ids), k, out, len(tax_ids) + 1)
         return list(out[:n])
+
+    def reduce_taxids_expanded(self, tax_ids, k):
+        """(promoted ids, child lists) -- the lists are [] when the classifier would print none"""
+        n = len(tax_ids)
+        arr = (C.c_uint64 * n)(*tax_ids)
+        out = (C.c_uint64 * (n + 1))()
+        child = (C.c_uint64 * (n + 1))()
+        cnt = (C.c_int32 * (n + 1))()
+        n_lists = C.c_int(0)
+        m = self.L.cfr_oracle_reduce_taxids_expanded(self.h, arr, n, k, out, n + 1, child, n + 1, cnt,
+                                                     C.byref(n_lists))
+        lists, at = [], 0
+        for i in range(n_lists.value):
+            lists.append(list(child[at:at + cnt[i]]))
+            at += cnt[i]
+        return list(out[:m]), (lists if n_lists.value == m else [])
+
+    def query_expanded(self, r1: bytes, r2: bytes = None, cap=4096):
+        """(Result, child lists per reported id) with outputExpandedResult set"""
+        res = Result()
+        child = (C.c_uint64 * cap)()
+        cnt = (C.c_int32 * 64)()
+        tot = self.L.cfr_oracle_query_expanded(self.h, C.byref(self.p), self._mask(r1), self._mask(r2),
+                                               C.byref(res), child, cap, cnt)
+        assert tot <= cap
+        return res, child, cnt
+
+    def classify_tsv_expanded(self, ids, reads1, reads2=None) -> str:
+        out = [TSV_HEADER[:-1] + "\texpandedTaxIDs\n"]
+        buf = C.create_string_buffer(1 << 18)
+        for i, rid in enumerate(ids):
+            res, child, cnt = self.query_expanded(reads1[i], reads2[i] if reads2 is not None else None)
+            w = self.L.cfr_oracle_format_tsv_expanded(self.h, rid.encode(), C.byref(res), child, cnt, buf, len(buf))
+            assert w >= 0
+            out.append(buf.raw[:w].decode())
+        return "".join(out)
 
     def counters(self):
         c = Counters()

@@ -61,7 +61,7 @@ def test_usage_and_version_and_rejections():
     r = subprocess.run([EXE], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
     assert r.returncode == 0 and b"-x FILE: index prefix" in r.stderr  # CentrifugerClass.cpp:347-351
     assert subprocess.run([EXE, "-v"], stdout=subprocess.PIPE).stdout.decode().strip() == "Centrifuger v1.1.3-r347"
-    r = subprocess.run([EXE, "-x", "nope", "-u", "x.fq", "--expand-taxid"], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    r = subprocess.run([EXE, "-x", "nope", "-u", "x.fq", "--sample-sheet", "s.tsv"], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
     assert r.returncode != 0 and b"not supported" in r.stderr
     r = subprocess.run([EXE, "-u", "x.fq"], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
     assert r.returncode != 0 and b"Need to use -x" in r.stderr

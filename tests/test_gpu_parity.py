@@ -360,3 +360,67 @@ def test_streaming_submit_wait(small_dir):
         g.wait(tk)
         assert np.array_equal(res, eres) and np.array_equal(ids.reshape(-1, 5), eids)
     g.close()
+
+
+def _oracle_expansion(o, r1, r2, k):
+    tup, lists = [], []
+    for i in range(len(r1)):
+        res, child, cnt = o.query_expanded(r1[i], r2[i] if r2 else None)
+        tup.append(o.result_tuple(res)[:7])
+        row, at = [], 0
+        for j in range(min(res.n, k)):
+            row.append([int(x) for x in child[at:at + cnt[j]]])
+            at += cnt[j]
+        lists.append(row)
+    return tup, lists
+
+
+@pytest.mark.parametrize("layout", LAYOUTS)
+def test_expand_taxid_lists(tiny_dir, small_dir, layout):
+    """_classifierParam.outputExpandedResult (--expand-taxid): the ids promoted into each reported id,
+    streaming and resident forms, also with a locate arena small enough to need several passes"""
+    cases = [(os.path.join(tiny_dir, "idx"), os.path.join(tiny_dir, "pe_100_1.fq"), os.path.join(tiny_dir, "pe_100_2.fq"), 10**9),
+             (os.path.join(tiny_dir, "idx"), os.path.join(tiny_dir, "se_100.fq"), None, 10**9),
+             (os.path.join(small_dir, "idx"), os.path.join(small_dir, "pe_150_1.fq"), os.path.join(small_dir, "pe_150_2.fq"), 3000)]
+    for idx, f1, f2, limit in cases:
+        _, r1 = read_fastx(f1)
+        r2 = read_fastx(f2)[1][:limit] if f2 else None
+        r1 = r1[:limit]
+        for kw, arena in ((dict(), 0), (dict(k=2), 0), (dict(k=3), 1200), (dict(k=4, hitk_factor=0), 0)):
+            o = Oracle(idx, **kw)
+            exp_t, exp_l = _oracle_expansion(o, r1, r2, kw.get("k", 1))
+            o.close()
+            assert sum(1 for row in exp_l if any(row)) > 0
+            g = cb.Classifier(idx, layout=layout, expand_taxid=True, arena_rows=arena, **kw)
+            res, ids, lists = g.classify_expanded(r1, r2)
+            assert _tuples(res, ids, g.k) == exp_t, (idx, kw)
+            assert lists == exp_l, (idx, kw)
+            # resident form
+            s1, o1 = cb.pack_reads(r1)
+            s2, o2 = cb.pack_reads(r2) if r2 else (None, None)
+            b = g.upload(s1, o1, s2, o2)
+            g.classify_resident(b)
+            res, ids = g.fetch(b)
+            assert g.fetch_expanded(b, res) == exp_l, (idx, kw)
+            b.free()
+            g.close()
+    # a handle opened without the flag refuses the fetch
+    g = cb.Classifier(os.path.join(tiny_dir, "idx"))
+    with pytest.raises(cb.CfrError):
+        g.classify_expanded([b"ACGT" * 30])
+    g.close()
+
+
+def test_cli_expand_taxid(tiny_dir, manifest):
+    """--expand-taxid: the TSV with its expandedTaxIDs column, byte for byte what the reference binary prints"""
+    import subprocess
+    exe = os.path.join(os.path.dirname(cb.LIB_PATH), "centrifuger-b200")
+    for name, m in sorted(manifest["expanded"].items()):
+        files = [golden_path("tiny", f) for f in m["files"]]
+        for batch in ("47", "1048576"):
+            cmd = [exe, "-x", os.path.join(tiny_dir, "idx"), "--expand-taxid", "--batch", batch] + m["args"]
+            cmd += ["-u", files[0]] if len(files) == 1 else ["-1", files[0], "-2", files[1]]
+            r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+            assert r.returncode == 0, r.stderr.decode()
+            assert r.stdout.decode() == open(golden_path("tiny", "expanded", name + ".tsv")).read(), (name, batch)
+            assert hashlib.md5(r.stdout).hexdigest() == m["md5"], name

@@ -112,6 +112,67 @@ def test_reduce_taxids_fuzz(tiny_dir, example_idx):
         o.close()
 
 
+def test_expand_taxids_fuzz(tiny_dir, example_idx):
+    """the child lists of ReduceTaxIds / LCA (--expand-taxid) on random id sets against the oracle"""
+    rng = random.Random(31)
+    for idx in (os.path.join(tiny_dir, "idx"), example_idx):
+        o = Oracle(idx)
+        hs = HostSim(idx)
+        nodes = o.scalar(10)
+        non_empty = 0
+        for it in range(3000):
+            cnt = rng.randint(2, 9)
+            mode = rng.random()
+            if mode < 0.5:
+                ids = [rng.randrange(nodes) for _ in range(cnt)]
+            elif mode < 0.8:
+                pool = [rng.randrange(nodes) for _ in range(3)]
+                ids = [rng.choice(pool) for _ in range(cnt)]
+            else:
+                ids = [rng.randrange(nodes + 2) for _ in range(cnt)]
+            for k in (1, 2, 3, 5):
+                if cnt <= k:
+                    continue
+                exp_ids, exp_lists = o.reduce_taxids_expanded(ids, k)
+                got_ids, got_lists = hs.expand_taxids(ids, k)
+                assert got_ids == exp_ids, (ids, k)
+                # lists the classifier would not print count as empty on both sides
+                assert got_lists == (exp_lists if exp_lists else [[] for _ in exp_ids]), (ids, k)
+                non_empty += any(len(l) for l in got_lists)
+        assert non_empty > 1000
+        hs.close()
+        o.close()
+
+
+@pytest.mark.parametrize("layout", [1, 2])
+def test_expand_taxid_pipeline(tiny_dir, layout):
+    """--expand-taxid through the whole pipeline: results unchanged, child lists equal to the oracle's"""
+    idx = os.path.join(tiny_dir, "idx")
+    for files in (["se_100.fq"], ["pe_100_1.fq", "pe_100_2.fq"], ["edge_1.fq", "edge_2.fq"]):
+        fs = [os.path.join(tiny_dir, f) for f in files]
+        _, r1 = read_fastx(fs[0])
+        r2 = read_fastx(fs[1])[1] if len(fs) == 2 else None
+        for kw, arena in ((dict(), 0), (dict(k=2), 0), (dict(k=3), 300), (dict(k=4, hitk_factor=0), 0)):
+            o = Oracle(idx, **kw)
+            hs = HostSim(idx, layout=layout, **kw)
+            k = hs.p.max_result
+            res, ids, lists = hs.classify_expanded(r1, r2, arena_rows=arena)
+            got = result_tuples(res, ids, k)
+            seen = 0
+            for i in range(len(r1)):
+                ores, child, cnt = o.query_expanded(r1[i], r2[i] if r2 else None)
+                assert got[i] == o.result_tuple(ores)[:7]
+                exp, at = [], 0
+                for j in range(min(ores.n, k)):
+                    exp.append([int(x) for x in child[at:at + cnt[j]]])
+                    at += cnt[j]
+                assert lists[i] == exp, (files, kw, i)
+                seen += any(len(l) for l in exp)
+            assert seen > 0
+            hs.close()
+            o.close()
+
+
 def test_example(example_idx):
     from conftest import golden_path
     fs = [golden_path("example", "example_1.fq"), golden_path("example", "example_2.fq")]

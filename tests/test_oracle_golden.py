@@ -67,6 +67,24 @@ def test_tiny_reference_outputs(tiny_dir, manifest):
         assert hashlib.md5(got.encode()).hexdigest() == m["md5"], name
 
 
+def test_tiny_expand_taxid_outputs(tiny_dir, manifest):
+    """--expand-taxid (the expandedTaxIDs column) as written by the reference binary, -k 1..5"""
+    assert len(manifest["expanded"]) >= 18
+    with_lists = 0
+    for name, m in sorted(manifest["expanded"].items()):
+        files = [os.path.join(tiny_dir, f) for f in m["files"]]
+        ids, r1 = read_fastx(files[0])
+        r2 = read_fastx(files[1])[1] if len(files) == 2 else None
+        o = Oracle(os.path.join(tiny_dir, "idx"), **_args_to_kw(m["args"]))
+        got = o.classify_tsv_expanded(ids, r1, r2)
+        o.close()
+        exp = open(golden_path("tiny", "expanded", name + ".tsv")).read()
+        assert got == exp, name
+        assert hashlib.md5(got.encode()).hexdigest() == m["md5"], name
+        with_lists += m["rows_with_lists"]
+    assert with_lists > 400
+
+
 def test_index_header_facts(example_idx):
     """the example index header as parsed."""
     o = Oracle(example_idx)
