@@ -85,6 +85,51 @@ def test_tiny_expand_taxid_outputs(tiny_dir, manifest):
     assert with_lists > 400
 
 
+def test_reduce_taxids_against_reference_header(tiny_dir):
+    """Taxonomy::ReduceTaxIds with its child lists: the oracle against the UNMODIFIED reference header
+    (oracle/_ref/taxonomy_ref, built from /root/reference/Taxonomy.hpp) on 6000 random id sets"""
+    import random
+    import subprocess
+    from oracle_binding import REF_DIR
+    exe = os.path.join(REF_DIR, "taxonomy_ref")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/taxonomy_ref not built")
+    rng = random.Random(41)
+    o = Oracle(os.path.join(tiny_dir, "idx"))
+    nodes = o.scalar(10)
+    queries = []
+    for it in range(6000):
+        cnt = rng.randint(1, 10)
+        mode = rng.random()
+        if mode < 0.5:
+            ids = [rng.randrange(nodes) for _ in range(cnt)]
+        elif mode < 0.8:
+            pool = [rng.randrange(nodes) for _ in range(3)]
+            ids = [rng.choice(pool) for _ in range(cnt)]
+        else:
+            ids = [rng.randrange(nodes + 2) for _ in range(cnt)]
+        queries.append((rng.choice([1, 1, 2, 3, 5]), ids))
+    text = "".join("%d %s\n" % (k, " ".join(map(str, ids))) for k, ids in queries)
+    r = subprocess.run([exe, os.path.join(tiny_dir, "idx.2.cfr")], input=text.encode(), stdout=subprocess.PIPE, check=True)
+    lines = r.stdout.decode().split("\n")
+    with_lists = 0
+    for (k, ids), line in zip(queries, lines):
+        left, right = line.split("|")
+        ref_ids = [int(x) for x in left.split()]
+        ref_lists = [[int(x) for x in l.split(",") if x] for l in right.split(";")] if right or len(ref_ids) == 0 else []
+        if right == "":
+            ref_lists = []  # no list at all, or one empty list: both print as an empty column
+        got_ids, got_lists = o.reduce_taxids_expanded(ids, k)
+        assert got_ids == ref_ids, (k, ids)
+        if len(ref_lists) != len(ref_ids):
+            ref_lists = []  # Classifier.hpp:823 prints nothing then
+        norm = lambda ls: ls if any(ls) else []
+        assert norm(got_lists) == norm(ref_lists), (k, ids, line)
+        with_lists += bool(norm(ref_lists))
+    assert with_lists > 1500
+    o.close()
+
+
 def test_index_header_facts(example_idx):
     """the example index header as parsed."""
     o = Oracle(example_idx)
