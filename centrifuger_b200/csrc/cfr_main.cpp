@@ -641,6 +641,11 @@ int main(int argc, char *argv[]) {
       // a batch ends after batchReads reads or 2^28 bases per mate, whichever comes first (long reads: the
       // device work areas grow with the bases and with the longest read of a batch)
       const size_t maxBases = 256u << 20;
+      // the device hit tables hold (longest read / (minHitLen + 1)) slots for every read of a batch, so one
+      // very long read among short ones must not share a batch with a million of them: a batch also ends
+      // when reads x (longest / 24 + 1) would pass 2^26 slots (CFR_B200_SLOT_BUDGET overrides, for tests)
+      static const size_t slotBudget = getenv("CFR_B200_SLOT_BUDGET") ? (size_t)atoll(getenv("CFR_B200_SLOT_BUDGET")) : (64u << 20);
+      size_t maxLen = 0;
       // mate 2 of separate files is parsed by a second thread that trails this one: it reads record j only
       // after mate 1's record j exists, so the two files advance by the same number of records per batch
       std::atomic<long> n1(0);       // mate-1 records parsed so far in this batch
@@ -661,7 +666,8 @@ int main(int argc, char *argv[]) {
           }
         });
       }
-      while ((long)bt->n < batchReads && bt->seq1.size() < maxBases) {
+      while ((long)bt->n < batchReads && bt->seq1.size() < maxBases &&
+             (bt->n == 0 || (bt->n + 1) * (maxLen / 24 + 1) <= slotBudget)) {
         name.clear();
         if (!reads.next(name, bt->seq1, keepReads ? &bt->qual1 : nullptr)) {
           eof = true;
@@ -671,6 +677,7 @@ int main(int argc, char *argv[]) {
         bt->ids += name;
         bt->id_off.push_back((uint32_t)bt->ids.size());
         bt->off1.push_back(bt->seq1.size());
+        maxLen = std::max(maxLen, (size_t)(bt->off1[bt->n + 1] - bt->off1[bt->n]));
         if (keepReads) bt->qoff1.push_back(bt->qual1.size());
         if (interleaved) {
           std::string *q2 = keepReads ? &bt->qual2 : nullptr;
@@ -679,6 +686,7 @@ int main(int argc, char *argv[]) {
             break;
           }
           bt->off2.push_back(bt->seq2.size());
+          maxLen = std::max(maxLen, (size_t)(bt->off2[bt->n + 1] - bt->off2[bt->n]));
           if (keepReads) bt->qoff2.push_back(bt->qual2.size());
         }
         ++bt->n;

@@ -175,3 +175,23 @@ def test_merge_readpair_in_the_ingest_stage(tiny_dir):
         else:
             assert g == p
     assert merged > 50
+
+
+def test_batches_end_early_when_a_long_read_arrives(tiny_dir, tmp_path):
+    """hit-table budget: reads x (longest read / 24 + 1) per batch is bounded, so a long read among short
+    ones cuts the batch; the records and their order do not change"""
+    from conftest import golden_path
+    _, short = read_fastx(os.path.join(tiny_dir, "se_100.fq"))
+    _, long_ = read_fastx(golden_path("tiny", "long.fa"))
+    mixed = tmp_path / "mixed.fa"
+    with open(mixed, "wb") as f:
+        for i, s in enumerate(short[:60] + long_[:3] + short[60:120] + long_[3:5] + short[120:]):
+            f.write(b">m%d\n%s\n" % (i, s))
+    ref = _dry(["-u", str(mixed)])
+    assert len(ref) == len(short) + 5
+    for budget in ("1", "200", "5000", "100000"):
+        env = dict(os.environ, CFR_B200_SLOT_BUDGET=budget)
+        r = subprocess.run([EXE, "--dry-run-pipeline", "-u", str(mixed)], stdout=subprocess.PIPE, stderr=subprocess.PIPE,
+                           timeout=120, env=env)
+        got = [tuple(l.split("\t")) for l in r.stdout.decode().split("\n") if l]
+        assert r.returncode == 0 and got == [(a, b, "") for a, b, _ in ref], budget

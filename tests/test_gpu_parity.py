@@ -426,3 +426,34 @@ def test_cli_expand_taxid(tiny_dir, manifest):
             assert r.returncode == 0, r.stderr.decode()
             assert r.stdout.decode() == open(golden_path("tiny", "expanded", name + ".tsv")).read(), (name, batch)
             assert hashlib.md5(r.stdout).hexdigest() == m["md5"], name
+
+
+def test_cli_long_reads_and_consider_secondary(tiny_dir, manifest):
+    """reads of 2 - 9 kbp and the near-tie rule of --consider-secondary (Classifier.hpp:763-781; bars lowered
+    so short reads reach it): the CLI's TSV is byte for byte the reference binary's"""
+    import subprocess
+    exe = os.path.join(os.path.dirname(cb.LIB_PATH), "centrifuger-b200")
+    for name, m in sorted(manifest["long"].items()):
+        files = [golden_path("tiny", f) for f in m["files"]]
+        for extra in ([], ["--batch", "13"]):
+            cmd = [exe, "-x", os.path.join(tiny_dir, "idx")] + m["args"] + extra
+            cmd += ["-u", files[0]] if len(files) == 1 else ["-1", files[0], "-2", files[1]]
+            r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+            assert r.returncode == 0, r.stderr.decode()
+            assert r.stdout.decode() == open(golden_path("tiny", "long", name + ".tsv")).read(), (name, extra)
+            assert hashlib.md5(r.stdout).hexdigest() == m["md5"], name
+
+
+@pytest.mark.parametrize("layout", LAYOUTS)
+def test_long_reads_vs_oracle(tiny_dir, layout):
+    """long reads through the C ABI with operation counts, also with an arena that needs several passes"""
+    idx = os.path.join(tiny_dir, "idx")
+    _, r1 = read_fastx(golden_path("tiny", "long.fa"))
+    for kw, arena in ((dict(), 0), (dict(k=2, secondary_len=1000, secondary_factor=0.1), 700), (dict(k=5, dust=False), 0)):
+        o = Oracle(idx, **kw)
+        exp = _oracle_tuples(o, r1, None)
+        o.close()
+        g = cb.Classifier(idx, layout=layout, arena_rows=arena, **kw)
+        res, ids = g.classify(r1)
+        assert _tuples(res, ids, g.k) == exp, kw
+        g.close()

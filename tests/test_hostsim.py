@@ -173,6 +173,25 @@ def test_expand_taxid_pipeline(tiny_dir, layout):
             o.close()
 
 
+@pytest.mark.parametrize("layout", [1, 2, 3])
+def test_long_reads_and_consider_secondary(tiny_dir, layout):
+    """2 - 9 kbp reads (hundreds of hits per strand, hit lengths past the 2000-base bar) and the
+    near-tie rule with lowered bars on the short read sets"""
+    from conftest import golden_path
+    long_fa = [golden_path("tiny", "long.fa")]
+    idx = os.path.join(tiny_dir, "idx")
+    for kw in (dict(), dict(k=5), dict(k=2, secondary_len=1000, secondary_factor=0.1),
+               dict(dust=False, secondary_len=3000, secondary_factor=0.05)):
+        _compare(idx, long_fa, layout, **kw)
+    _compare(idx, long_fa, layout, arena_rows=700, k=2, secondary_len=1000, secondary_factor=0.1)
+    for files, kw in ((["se_100.fq"], dict(secondary_len=50, secondary_factor=0.9)),
+                      (["se_100.fq"], dict(k=3, secondary_len=60, secondary_factor=0.8)),
+                      (["pe_100_1.fq", "pe_100_2.fq"], dict(secondary_len=100, secondary_factor=0.9)),
+                      (["pe_100_1.fq", "pe_100_2.fq"], dict(k=5, secondary_len=50, secondary_factor=0.5)),
+                      (["edge_1.fq", "edge_2.fq"], dict(k=2, secondary_len=30, secondary_factor=0.7))):
+        _compare(idx, [os.path.join(tiny_dir, f) for f in files], layout, **kw)
+
+
 def test_example(example_idx):
     from conftest import golden_path
     fs = [golden_path("example", "example_1.fq"), golden_path("example", "example_2.fq")]

@@ -25,6 +25,9 @@ def _args_to_kw(args):
             kw["hitk_factor"] = int(next(it))
         elif a == "--min-hitlen":
             kw["min_hit_len"] = int(next(it))
+        elif a == "--consider-secondary":
+            ln, fac = next(it).split(",")
+            kw["secondary_len"], kw["secondary_factor"] = int(ln), float(fac)
     return kw
 
 
@@ -83,6 +86,21 @@ def test_tiny_expand_taxid_outputs(tiny_dir, manifest):
         assert hashlib.md5(got.encode()).hexdigest() == m["md5"], name
         with_lists += m["rows_with_lists"]
     assert with_lists > 400
+
+
+def test_long_reads_and_consider_secondary(tiny_dir, manifest):
+    """reads of 2 - 9 kbp, and the near-tie rule (Classifier.hpp:763-781, `2nd >= (size_t)(factor * best)`
+    once the second hit length passes the bar) with the bar lowered so that short reads reach it"""
+    for name, m in sorted(manifest["long"].items()):
+        files = [golden_path("tiny", f) for f in m["files"]]
+        args = [a for a in m["args"] if a != "--expand-taxid"]
+        ids, r1 = read_fastx(files[0])
+        r2 = read_fastx(files[1])[1] if len(files) == 2 else None
+        o = Oracle(os.path.join(tiny_dir, "idx"), **_args_to_kw(args))
+        got = o.classify_tsv_expanded(ids, r1, r2) if "--expand-taxid" in m["args"] else o.classify_tsv(ids, r1, r2)
+        o.close()
+        assert got == open(golden_path("tiny", "long", name + ".tsv")).read(), name
+        assert hashlib.md5(got.encode()).hexdigest() == m["md5"], name
 
 
 def test_reduce_taxids_against_reference_header(tiny_dir):
