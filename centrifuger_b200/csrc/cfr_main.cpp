@@ -1,7 +1,7 @@
 // cfr_main.cpp -- `centrifuger-b200`: drop-in for the reference's classification
 // binary (CentrifugerClass.cpp) on the paths this repo covers: same -x/-1/-2/-u/-i/
 // -t/-k/--min-hitlen/--hitk-factor/--no-dust/--consider-secondary/--un/--cl/
-// --merge-readpair/--expand-taxid/-h/-v options, the reference's own *.cfr index files, the identical
+// --merge-readpair/--expand-taxid/--sample-sheet/-h/-v options, the reference's own *.cfr index files, the identical
 // TSV on stdout and the same log lines on stderr.  All classification work is done by
 // libcfrb200.so on the GPU (include/centrifuger_b200.h); this file is host I/O only:
 // gz FASTA/FASTQ parsing (ReadFiles.hpp + kseq.h behaviour) on an ingest thread (mate 2
@@ -9,9 +9,10 @@
 // ResultWriter-style output on an output thread.
 //
 // Not supported (the reference's single-cell extras, SURVEY.md 8 "out of scope"):
-// barcode/UMI/read-format options, --sample-sheet.  They are rejected
+// barcode/UMI/read-format options (also as sample-sheet columns).  They are rejected
 // with a log line and EXIT_FAILURE.
 #include <getopt.h>
+#include <glob.h>
 #include <sys/stat.h>
 #include <zlib.h>
 
@@ -43,6 +44,8 @@ static const char usage[] =
     "\t-u FILE: single-end read\n"
     "\t\tor\n"
     "\t-i FILE: interleaved read file\n"
+    "\t\tor\n"
+    "\t--sample-sheet FILE: list of sample files, each row: \"read1 read2 barcode UMI output\". Use dot(.) to represent no such file\n"
     "Optional:\n"
     "\t-t INT: number of threads [1] (accepted for compatibility; the work runs on the GPU)\n"
     "\t-k INT: report upto <int> distinct, primary assignments for each read pair [1]\n"
@@ -62,7 +65,7 @@ static const char usage[] =
 
 enum {
   ARGV_NO_DUST = 256, ARGV_MIN_HITLEN, ARGV_HITK, ARGV_SECONDARY, ARGV_GPU, ARGV_BATCH, ARGV_LAYOUT,
-  ARGV_UNSUPPORTED, ARGV_DRY_RUN, ARGV_DRY_PIPE, ARGV_UN, ARGV_CL, ARGV_MERGE, ARGV_EXPAND
+  ARGV_UNSUPPORTED, ARGV_DRY_RUN, ARGV_DRY_PIPE, ARGV_UN, ARGV_CL, ARGV_MERGE, ARGV_EXPAND, ARGV_SAMPLE_SHEET, ARGV_DRY_OUT
 };
 
 static const char *short_options = "x:1:2:u:i:o:t:k:hv";
@@ -76,6 +79,7 @@ static struct option long_options[] = {
     {"layout", required_argument, 0, ARGV_LAYOUT},
     {"dry-run", no_argument, 0, ARGV_DRY_RUN},
     {"dry-run-pipeline", no_argument, 0, ARGV_DRY_PIPE},
+    {"dry-run-output", no_argument, 0, ARGV_DRY_OUT},
     {"un", required_argument, 0, ARGV_UN},
     {"cl", required_argument, 0, ARGV_CL},
     {"merge-readpair", no_argument, 0, ARGV_MERGE},
@@ -85,7 +89,7 @@ static struct option long_options[] = {
     {"UMI", required_argument, 0, ARGV_UNSUPPORTED},
     {"barcode-whitelist", required_argument, 0, ARGV_UNSUPPORTED},
     {"barcode-translate", required_argument, 0, ARGV_UNSUPPORTED},
-    {"sample-sheet", required_argument, 0, ARGV_UNSUPPORTED},
+    {"sample-sheet", required_argument, 0, ARGV_SAMPLE_SHEET},
     {(char *)0, 0, 0, 0}};
 
 // Utils::PrintLog (compactds/Utils.hpp:369-381)
@@ -208,22 +212,45 @@ struct ReadSource {  // a list of files read back to back (ReadFiles::AddReadFil
   std::vector<std::string> files;
   size_t cur = 0;
   bool opened = false;
+  bool markFileEnds = false;  // --sample-sheet: every file end is reported (ReadFiles::SetSpecialReadToMarkFileEnd)
   SeqReader rd;
-  bool next(std::string &name, std::string &seq, std::string *qual = nullptr) {
+  // a name with '*' stands for the files it matches, in glob(3) order (ReadFiles.hpp:135-172)
+  void add(const char *file) {
+    if (!strchr(file, '*')) {
+      files.push_back(file);
+      return;
+    }
+    glob_t g;
+    memset(&g, 0, sizeof(g));
+    const int rc = glob(file, GLOB_TILDE, NULL, &g);
+    if (rc != 0) fprintf(stderr, "glob() failed with return value %d.\n", rc);
+    for (size_t i = 0; rc == 0 && i < g.gl_pathc; ++i) files.push_back(g.gl_pathv[i]);
+    globfree(&g);
+  }
+  enum { END = 0, RECORD = 1, FILE_END = 2 };
+  // RECORD, END (no file left) or -- with markFileEnds -- FILE_END once per file, the last one included
+  int step(std::string &name, std::string &seq, std::string *qual = nullptr) {
     for (;;) {
       if (!opened) {
-        if (cur >= files.size()) return false;
+        if (cur >= files.size()) return END;
         if (!rd.open(files[cur])) {
           PrintLog("ERROR: cannot open read file %s", files[cur].c_str());
           exit(EXIT_FAILURE);
         }
         opened = true;
       }
-      if (rd.next(name, seq, qual)) return true;
+      if (rd.next(name, seq, qual)) return RECORD;
       rd.close();
       opened = false;
       ++cur;
+      if (markFileEnds) return FILE_END;
     }
+  }
+  bool next(std::string &name, std::string &seq, std::string *qual = nullptr) {
+    int r;
+    while ((r = step(name, seq, qual)) == FILE_END) {
+    }
+    return r == RECORD;
   }
 };
 
@@ -360,7 +387,9 @@ struct Batch {
   std::vector<uint64_t> ooff1, ooff2;
   size_t n = 0;
   bool last = false;
+  bool fileEnd = false;  // --sample-sheet: an input file ended with this batch, the TSV moves to the next output
   void clear() {
+    fileEnd = false;
     merged.clear();
     orig1.clear();
     orig2.clear();
@@ -486,15 +515,52 @@ int main(int argc, char *argv[]) {
   long batchReads = 1 << 20;
   const char *unPrefix = NULL, *clPrefix = NULL;  // --un / --cl
   bool mergePairs = false;                        // --merge-readpair
+  bool useSheet = false;                          // --sample-sheet
+  std::vector<std::string> sheetOutputs;          // TSV file of every input file, in input order
   bool dryPipe = false;  // diagnostics: the batches the threaded ingest stage hands to the GPU stage, no GPU work
+  bool dryOut = false;  // diagnostics: ingest and output stages as in a real run, every read reported unclassified, no GPU work
   bool dryRun = false;  // diagnostics: parse the inputs and print id<TAB>mate1<TAB>mate2, no GPU work
   int c, option_index = 0;
   while ((c = getopt_long(argc, argv, short_options, long_options, &option_index)) != -1) {
     if (c == 'x') idxPrefix = optarg;
-    else if (c == 'u') reads.files.push_back(optarg);
-    else if (c == '1') { reads.files.push_back(optarg); hasMate = true; }
-    else if (c == '2') { mates.files.push_back(optarg); hasMate = true; }
-    else if (c == 'i') { reads.files.push_back(optarg); hasMate = true; interleaved = true; }
+    else if (c == 'u') reads.add(optarg);
+    else if (c == '1') { reads.add(optarg); hasMate = true; }
+    else if (c == '2') { mates.add(optarg); hasMate = true; }
+    else if (c == 'i') { reads.add(optarg); hasMate = true; interleaved = true; }
+    else if (c == ARGV_SAMPLE_SHEET) {
+      // rows "read1 read2 barcode UMI output", '.' = none (CentrifugerClass.cpp:467-516); every file end
+      // moves the TSV to the next row's output file (ResultWriter.hpp:75-107)
+      FILE *fs = fopen(optarg, "r");
+      if (!fs) {
+        PrintLog("Cannot open the sample sheet %s", optarg);
+        return EXIT_FAILURE;
+      }
+      char line[8192], f1[2048], f2[2048], bc[2048], um[2048], of[2048];
+      while (fgets(line, sizeof(line), fs)) {
+        f1[0] = f2[0] = bc[0] = um[0] = of[0] = 0;
+        if (sscanf(line, "%2047s %2047s %2047s %2047s %2047s", f1, f2, bc, um, of) < 1) continue;
+        if (strcmp(bc, ".") || strcmp(um, ".")) {
+          PrintLog("ERROR: barcode / UMI files in the sample sheet are not supported by centrifuger-b200.");
+          return EXIT_FAILURE;
+        }
+        const bool paired = strcmp(f2, ".") != 0;
+        if (!sheetOutputs.empty() && paired != hasMate) {
+          PrintLog("ERROR: a sample sheet mixing single-end and paired-end rows is not supported by centrifuger-b200.");
+          return EXIT_FAILURE;
+        }
+        const size_t before = reads.files.size();
+        reads.add(f1);
+        if (paired) {
+          mates.add(f2);
+          hasMate = true;
+        }
+        // one output entry per input FILE (a row whose name globs to several files moves on at each of
+        // them, as the reference's per-file end marker does)
+        for (size_t q = before; q < reads.files.size(); ++q) sheetOutputs.push_back(of);
+      }
+      fclose(fs);
+      useSheet = true;
+    }
     else if (c == 'o') { /* parsed but unused by the reference as well (CentrifugerClass.cpp:416) */ }
     else if (c == 't') { /* host thread count of the reference; nothing to do */ }
     else if (c == 'k') params.max_result = atoi(optarg);
@@ -520,6 +586,7 @@ int main(int argc, char *argv[]) {
       else params.layout = CFR_LAYOUT_AUTO;
     } else if (c == ARGV_DRY_RUN) dryRun = true;
     else if (c == ARGV_DRY_PIPE) dryPipe = true;
+    else if (c == ARGV_DRY_OUT) dryOut = true;
     else if (c == ARGV_MERGE) mergePairs = true;
     else if (c == ARGV_EXPAND) params.expand_taxid = 1;  // classifierParam.outputExpandedResult, CentrifugerClass.cpp:453-456
     else if (c == ARGV_UN) unPrefix = optarg;
@@ -531,6 +598,13 @@ int main(int argc, char *argv[]) {
       fprintf(stderr, "%s", usage);
       return EXIT_FAILURE;
     }
+  }
+  if (useSheet) {
+    if (sheetOutputs.empty()) {
+      PrintLog("ERROR: the sample sheet lists no files.");
+      return EXIT_FAILURE;
+    }
+    reads.markFileEnds = mates.markFileEnds = true;
   }
   if (dryRun) {
     std::string name, name2, s1, s2, q1, q2;
@@ -559,7 +633,7 @@ int main(int argc, char *argv[]) {
     return 0;
   }
   if (!dryPipe) PrintLog("Centrifuger v" CENTRIFUGER_VERSION " starts.");
-  if (idxPrefix == NULL && !dryPipe) {
+  if (idxPrefix == NULL && !dryPipe && !dryOut) {
     PrintLog("Need to use -x to specify index prefix.");
     return EXIT_FAILURE;
   }
@@ -590,7 +664,7 @@ int main(int argc, char *argv[]) {
   }
   cfr_handle *h = NULL;
   int st = CFR_OK;
-  if (!dryPipe) {
+  if (!dryPipe && !dryOut) {
     st = cfr_open(idxPrefix, &params, device, &h);
     if (st != CFR_OK) {
       PrintLog("ERROR: %s", cfr_last_error());
@@ -659,7 +733,7 @@ int main(int argc, char *argv[]) {
           for (;;) {
             while (n2 >= n1.load(std::memory_order_acquire) && !done1.load(std::memory_order_acquire)) std::this_thread::yield();
             if (n2 >= n1.load(std::memory_order_acquire)) break;  // mate 1 is done and mate 2 has caught up
-            if (!mates.next(nm, bt->seq2, q2)) break;             // mate 2 ended first
+            if (mates.step(nm, bt->seq2, q2) != ReadSource::RECORD) break;  // mate 2 (or, with a sample sheet, its file) ended first
             bt->off2.push_back(bt->seq2.size());
             if (keepReads) bt->qoff2.push_back(bt->qual2.size());
             ++n2;
@@ -669,7 +743,12 @@ int main(int argc, char *argv[]) {
       while ((long)bt->n < batchReads && bt->seq1.size() < maxBases &&
              (bt->n == 0 || (bt->n + 1) * (maxLen / 24 + 1) <= slotBudget)) {
         name.clear();
-        if (!reads.next(name, bt->seq1, keepReads ? &bt->qual1 : nullptr)) {
+        const int got = reads.step(name, bt->seq1, keepReads ? &bt->qual1 : nullptr);
+        if (got == ReadSource::FILE_END) {  // sample sheet: the batch ends with the file
+          bt->fileEnd = true;
+          break;
+        }
+        if (got == ReadSource::END) {
           eof = true;
           break;
         }
@@ -696,9 +775,10 @@ int main(int argc, char *argv[]) {
         done1.store(true, std::memory_order_release);
         mate2.join();
         if (n2 < (long)bt->n) mate_mismatch = true;  // mate 2 ended first
-        if (!mate_mismatch && eof) {
+        if (!mate_mismatch && (eof || bt->fileEnd)) {  // mate 1 (its file) ended: mate 2 must end here too
           tmp.clear();
-          if (mates.next(name2, tmp)) mate_mismatch = true;  // mate 1 ended first
+          const int got2 = mates.step(name2, tmp);
+          if (got2 == ReadSource::RECORD || (bt->fileEnd && got2 != ReadSource::FILE_END)) mate_mismatch = true;
         }
         if (mate_mismatch && n2 < (long)bt->n) {  // keep the batch consistent for the stages behind
           bt->n = (size_t)n2;
@@ -738,13 +818,24 @@ int main(int argc, char *argv[]) {
     return 0;
   }
 
+  FILE *fpOut = stdout;
+  if (useSheet) {  // ResultWriter::SetMultiOutputFileList: the first row's file, header included, instead of stdout
+    fpOut = fopen(sheetOutputs[0].c_str(), "w");
+    if (!fpOut) {
+      PrintLog("ERROR: cannot open output file %s", sheetOutputs[0].c_str());
+      return EXIT_FAILURE;
+    }
+  }
   std::thread output([&] {
     std::string out, rec;
     out.reserve(64 << 20);
     // ResultWriter::OutputHeader (ResultWriter.hpp:186-197)
-    out += "readID\tseqID\ttaxID\tscore\t2ndBestScore\thitLength\tqueryLength\tnumMatches";
-    if (expandTaxid) out += "\texpandedTaxIDs";
-    out += '\n';
+    const std::string header = std::string("readID\tseqID\ttaxID\tscore\t2ndBestScore\thitLength\tqueryLength\tnumMatches") +
+                               (expandTaxid ? "\texpandedTaxIDs" : "") + "\n";
+    out += header;
+    size_t sheetAt = 0;  // --sample-sheet: index of the input file being written (ResultWriter.hpp:75-107)
+    std::vector<std::string> sheetSeen;
+    if (useSheet) sheetSeen.push_back(sheetOutputs[0]);
     int bi = 0;
     for (;;) {
       Batch *bt = to_out.take();
@@ -801,7 +892,7 @@ int main(int argc, char *argv[]) {
           out.resize((size_t)(p - out.data()));
         }
         if (out.size() > (48u << 20)) {
-          fwrite(out.data(), 1, out.size(), stdout);
+          fwrite(out.data(), 1, out.size(), fpOut);
           out.clear();
         }
         if (writeReads) {  // ResultWriter::Output, ResultWriter.hpp:244-262
@@ -832,13 +923,37 @@ int main(int argc, char *argv[]) {
           }
         }
       }
+      if (useSheet && bt->fileEnd) {  // ResultWriter::NextMultiOutputFile: a file seen before is appended to, without a header
+        if (fpOut) {
+          fwrite(out.data(), 1, out.size(), fpOut);
+          fclose(fpOut);
+          fpOut = NULL;
+        }
+        out.clear();
+        if (++sheetAt < sheetOutputs.size()) {
+          const std::string &nm = sheetOutputs[sheetAt];
+          const bool seen = std::find(sheetSeen.begin(), sheetSeen.end(), nm) != sheetSeen.end();
+          fpOut = fopen(nm.c_str(), seen ? "a" : "w");
+          if (!fpOut) {
+            PrintLog("ERROR: cannot open output file %s", nm.c_str());
+            exit(EXIT_FAILURE);
+          }
+          if (!seen) {
+            sheetSeen.push_back(nm);
+            out += header;
+          }
+        }
+      }
       const bool last = bt->last;
       free_slots[bi].put(bt);
       bi = (bi + 1) % NBATCH;
       if (last) break;
     }
-    fwrite(out.data(), 1, out.size(), stdout);
-    fflush(stdout);
+    if (fpOut) {
+      fwrite(out.data(), 1, out.size(), fpOut);
+      fflush(fpOut);
+      if (fpOut != stdout) fclose(fpOut);
+    }
   });
 
   int rc = 0;
@@ -874,7 +989,14 @@ int main(int argc, char *argv[]) {
   for (;;) {
     Batch *bt = to_gpu.take();
     int ticket = -1;
-    if (rc == 0 && bt->n > 0) {
+    if (dryOut) {  // no device: the output stage sees every read as unclassified
+      bt->results.assign(bt->n, cfr_result());
+      bt->assign.assign(bt->n * (size_t)k, 0);
+      for (size_t i = 0; i < bt->n; ++i)
+        bt->results[i].query_length = (int32_t)(bt->off1[i + 1] - bt->off1[i] + (hasMate ? bt->off2[i + 1] - bt->off2[i] : 0));
+      bt->masked1 = bt->seq1;
+      bt->masked2 = bt->seq2;
+    } else if (rc == 0 && bt->n > 0) {
       bt->results.resize(bt->n);
       bt->assign.resize(bt->n * (size_t)k);
       cfr_read_batch b;
@@ -918,7 +1040,7 @@ int main(int argc, char *argv[]) {
   // ResultWriter::Finalize (ResultWriter.hpp:279-283)
   PrintLog("Processed %lu read fragments, and %lu (%.2lf%%) can be classified.", totalCnt, classifiedCnt,
            (double)classifiedCnt / (double)totalCnt * 100.0);
-  cfr_close(h);
+  if (h) cfr_close(h);
   PrintLog("Centrifuger finishes.");
   return 0;
 }

@@ -61,7 +61,7 @@ def test_usage_and_version_and_rejections():
     r = subprocess.run([EXE], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
     assert r.returncode == 0 and b"-x FILE: index prefix" in r.stderr  # CentrifugerClass.cpp:347-351
     assert subprocess.run([EXE, "-v"], stdout=subprocess.PIPE).stdout.decode().strip() == "Centrifuger v1.1.3-r347"
-    r = subprocess.run([EXE, "-x", "nope", "-u", "x.fq", "--sample-sheet", "s.tsv"], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    r = subprocess.run([EXE, "-x", "nope", "-u", "x.fq", "--barcode", "b.fq"], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
     assert r.returncode != 0 and b"not supported" in r.stderr
     r = subprocess.run([EXE, "-u", "x.fq"], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
     assert r.returncode != 0 and b"Need to use -x" in r.stderr
@@ -195,3 +195,54 @@ def test_batches_end_early_when_a_long_read_arrives(tiny_dir, tmp_path):
                            timeout=120, env=env)
         got = [tuple(l.split("\t")) for l in r.stdout.decode().split("\n") if l]
         assert r.returncode == 0 and got == [(a, b, "") for a, b, _ in ref], budget
+
+
+def _write_sheet(path, rows, outdir):
+    from conftest import golden_path
+    with open(path, "w") as f:
+        for r1, r2, o in rows:
+            f.write("%s %s . . %s\n" % (golden_path("tiny", r1), r2 if r2 == "." else golden_path("tiny", r2),
+                                        os.path.join(str(outdir), o + ".tsv")))
+
+
+def test_sample_sheet_routes_reads_to_their_output_files(manifest, tmp_path):
+    """--sample-sheet on the ingest and output stages (no GPU: every read is printed as unclassified): each
+    input file's rows land in its row's output file, a file named twice is appended to without a second
+    header, nothing goes to stdout -- the read ids per file are those of the reference binary's outputs"""
+    from conftest import golden_path
+    for case, m in manifest["sample_sheet"].items():
+        od = tmp_path / case
+        od.mkdir()
+        sheet = tmp_path / (case + ".sheet")
+        _write_sheet(sheet, m["rows"], od)
+        for batch in ("1048576", "37"):
+            for f in os.listdir(str(od)):
+                os.remove(str(od / f))
+            r = subprocess.run([EXE, "--dry-run-output", "--batch", batch, "--sample-sheet", str(sheet)] + m["args"],
+                               stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=120)
+            assert r.returncode == 0 and r.stdout == b"", r.stderr.decode()
+            assert sorted(os.listdir(str(od))) == sorted(m["outputs"])
+            for o in m["outputs"]:
+                exp = open(golden_path("tiny", "sheet", "%s__%s" % (case, o))).read().split("\n")
+                got = open(str(od / o)).read().split("\n")
+                assert got[0] == exp[0] and sum(1 for l in got if l.startswith("readID")) == 1
+                exp_reads = []
+                for l in exp[1:]:
+                    if l and (not exp_reads or exp_reads[-1][0] != l.split("\t")[0]):  # -k > 1: several rows per read
+                        exp_reads.append((l.split("\t")[0], l.split("\t")[6]))
+                assert [(l.split("\t")[0], l.split("\t")[6]) for l in got[1:] if l] == exp_reads, (case, o, batch)
+    # rows that ask for what this build does not do are refused
+    bad = tmp_path / "bad.sheet"
+    bad.write_text("%s . %s . %s\n" % (golden_path("tiny", "se_100.fq"), golden_path("tiny", "se_100.fq"), tmp_path / "x.tsv"))
+    r = subprocess.run([EXE, "--dry-run-output", "--sample-sheet", str(bad)], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert r.returncode != 0 and b"not supported" in r.stderr
+    r = subprocess.run([EXE, "--dry-run-output", "--sample-sheet", str(tmp_path / "missing.sheet")], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert r.returncode != 0 and b"Cannot open the sample sheet" in r.stderr
+
+
+def test_glob_in_file_names(tiny_dir):
+    """a '*' in a read file name stands for the matching files in glob order (ReadFiles.hpp:135-172)"""
+    ref = _dry(["-1", os.path.join(tiny_dir, "edge_1.fq"), "-1", os.path.join(tiny_dir, "pe_100_1.fq"),
+                "-2", os.path.join(tiny_dir, "edge_2.fq"), "-2", os.path.join(tiny_dir, "pe_100_2.fq")])
+    got = _dry(["-1", os.path.join(tiny_dir, "*e*_1.fq"), "-2", os.path.join(tiny_dir, "*e*_2.fq")])
+    assert got == ref and len(ref) > 300

@@ -457,3 +457,23 @@ def test_long_reads_vs_oracle(tiny_dir, layout):
         res, ids = g.classify(r1)
         assert _tuples(res, ids, g.k) == exp, kw
         g.close()
+
+
+def test_cli_sample_sheet(tiny_dir, manifest, tmp_path):
+    """--sample-sheet: every output file byte for byte what the reference binary writes (a file named by two
+    rows is appended to), nothing on stdout"""
+    import subprocess
+    exe = os.path.join(os.path.dirname(cb.LIB_PATH), "centrifuger-b200")
+    for case, m in manifest["sample_sheet"].items():
+        od = tmp_path / case
+        od.mkdir()
+        sheet = tmp_path / (case + ".sheet")
+        with open(str(sheet), "w") as f:
+            for r1, r2, o in m["rows"]:
+                f.write("%s %s . . %s\n" % (golden_path("tiny", r1), r2 if r2 == "." else golden_path("tiny", r2),
+                                            str(od / (o + ".tsv"))))
+        r = subprocess.run([exe, "-x", os.path.join(tiny_dir, "idx"), "--batch", "41", "--sample-sheet", str(sheet)] + m["args"],
+                           stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+        assert r.returncode == 0 and r.stdout == b"", r.stderr.decode()
+        got = {o: hashlib.md5(open(str(od / o), "rb").read()).hexdigest() for o in sorted(os.listdir(str(od)))}
+        assert got == m["outputs"], case
