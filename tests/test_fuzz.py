@@ -1,0 +1,28 @@
+"""A few rounds of the two differential fuzzers (tools/fuzz_hostsim.py, tools/fuzz_oracle_vs_reference.py):
+generated reads with substitutions, indels, N runs, low-complexity inserts, chimeras, lowercase and
+random options.  The long runs are done by hand (DESIGN.md section 1c records them)."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+from oracle_binding import REF_DIR
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(script, rounds, seed):
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", script), str(rounds), str(seed)],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=600)
+    assert r.returncode == 0 and b"ok:" in r.stdout, r.stdout.decode()[-2000:]
+
+
+def test_product_stage_functions_against_oracle():
+    _run("fuzz_hostsim.py", 8, 101)
+
+
+def test_oracle_against_reference_binary():
+    if not os.path.exists(os.path.join(REF_DIR, "centrifuger")):
+        pytest.skip("oracle/_ref/centrifuger not built")
+    _run("fuzz_oracle_vs_reference.py", 8, 202)
