@@ -1,7 +1,7 @@
 // cfr_main.cpp -- `centrifuger-b200`: drop-in for the reference's classification
 // binary (CentrifugerClass.cpp) on the paths this repo covers: same -x/-1/-2/-u/-i/
 // -t/-k/--min-hitlen/--hitk-factor/--no-dust/--consider-secondary/--un/--cl/
-// --merge-readpair/--expand-taxid/--sample-sheet/-h/-v options, the reference's own *.cfr index files, the identical
+// --merge-readpair/--expand-taxid/--sample-sheet/--read-format/--barcode/--UMI/-h/-v options, the reference's own *.cfr index files, the identical
 // TSV on stdout and the same log lines on stderr.  All classification work is done by
 // libcfrb200.so on the GPU (include/centrifuger_b200.h); this file is host I/O only:
 // gz FASTA/FASTQ parsing (ReadFiles.hpp + kseq.h behaviour) on an ingest thread (mate 2
@@ -9,7 +9,7 @@
 // ResultWriter-style output on an output thread.
 //
 // Not supported (the reference's single-cell extras, SURVEY.md 8 "out of scope"):
-// barcode/UMI/read-format options (also as sample-sheet columns).  They are rejected
+// --barcode-whitelist / --barcode-translate, barcode / UMI columns of a sample sheet.  They are rejected
 // with a log line and EXIT_FAILURE.
 #include <getopt.h>
 #include <glob.h>
@@ -52,6 +52,9 @@ static const char usage[] =
     "\t--un STR: output unclassified reads to files with the prefix of <str>\n"
     "\t--cl STR: output classified reads to files with the prefix of <str>\n"
     "\t--merge-readpair: merge overlapped paired-end reads and trim adapters [no merge]\n"
+    "\t--barcode STR: path to the barcode file\n"
+    "\t--UMI STR: path to the UMI file\n"
+    "\t--read-format STR: format for read, barcode and UMI files, e.g. r1:0:-1,r2:0:-1,bc:0:15,um:16:-1 for paired-end files with barcode and UMI\n"
     "\t--expand-taxid: output the tax IDs that are promoted to the final report tax ID [no]\n"
     "\t--no-dust: do not DUST-mask low-complexity regions of reads [mask]\n"
     "\t--min-hitlen INT: minimum length of partial hits [auto]\n"
@@ -65,7 +68,7 @@ static const char usage[] =
 
 enum {
   ARGV_NO_DUST = 256, ARGV_MIN_HITLEN, ARGV_HITK, ARGV_SECONDARY, ARGV_GPU, ARGV_BATCH, ARGV_LAYOUT,
-  ARGV_UNSUPPORTED, ARGV_DRY_RUN, ARGV_DRY_PIPE, ARGV_UN, ARGV_CL, ARGV_MERGE, ARGV_EXPAND, ARGV_SAMPLE_SHEET, ARGV_DRY_OUT
+  ARGV_UNSUPPORTED, ARGV_DRY_RUN, ARGV_DRY_PIPE, ARGV_UN, ARGV_CL, ARGV_MERGE, ARGV_EXPAND, ARGV_SAMPLE_SHEET, ARGV_DRY_OUT, ARGV_READ_FORMAT, ARGV_BARCODE, ARGV_UMI
 };
 
 static const char *short_options = "x:1:2:u:i:o:t:k:hv";
@@ -84,9 +87,9 @@ static struct option long_options[] = {
     {"cl", required_argument, 0, ARGV_CL},
     {"merge-readpair", no_argument, 0, ARGV_MERGE},
     {"expand-taxid", no_argument, 0, ARGV_EXPAND},
-    {"read-format", required_argument, 0, ARGV_UNSUPPORTED},
-    {"barcode", required_argument, 0, ARGV_UNSUPPORTED},
-    {"UMI", required_argument, 0, ARGV_UNSUPPORTED},
+    {"read-format", required_argument, 0, ARGV_READ_FORMAT},
+    {"barcode", required_argument, 0, ARGV_BARCODE},
+    {"UMI", required_argument, 0, ARGV_UMI},
     {"barcode-whitelist", required_argument, 0, ARGV_UNSUPPORTED},
     {"barcode-translate", required_argument, 0, ARGV_UNSUPPORTED},
     {"sample-sheet", required_argument, 0, ARGV_SAMPLE_SHEET},
@@ -126,7 +129,7 @@ class SeqReader {
   }
   // appends the record's sequence to `seq` (and, for FASTQ records, its quality string to `qual` when
   // given: a FASTA record appends nothing there); returns false at end of file
-  bool next(std::string &name, std::string &seq, std::string *qual = nullptr) {
+  bool next(std::string &name, std::string &seq, std::string *qual = nullptr, std::string *comment = nullptr) {
     const char *ln;
     size_t n;
     // header line
@@ -138,6 +141,7 @@ class SeqReader {
     size_t e = 1;
     while (e < n && ln[e] != ' ' && ln[e] != '\t') ++e;
     name.assign(ln + 1, e - 1);
+    if (comment) comment->assign(e < n ? ln + e + 1 : ln + n, e < n ? n - e - 1 : 0);  // kseq: the rest of the line
     // sequence lines: until a line starting with '+' (FASTQ), '>' or '@' (next record)
     const size_t start = seq.size();
     for (;;) {
@@ -229,7 +233,7 @@ struct ReadSource {  // a list of files read back to back (ReadFiles::AddReadFil
   }
   enum { END = 0, RECORD = 1, FILE_END = 2 };
   // RECORD, END (no file left) or -- with markFileEnds -- FILE_END once per file, the last one included
-  int step(std::string &name, std::string &seq, std::string *qual = nullptr) {
+  int step(std::string &name, std::string &seq, std::string *qual = nullptr, std::string *comment = nullptr) {
     for (;;) {
       if (!opened) {
         if (cur >= files.size()) return END;
@@ -239,18 +243,170 @@ struct ReadSource {  // a list of files read back to back (ReadFiles::AddReadFil
         }
         opened = true;
       }
-      if (rd.next(name, seq, qual)) return RECORD;
+      if (rd.next(name, seq, qual, comment)) return RECORD;
       rd.close();
       opened = false;
       ++cur;
       if (markFileEnds) return FILE_END;
     }
   }
-  bool next(std::string &name, std::string &seq, std::string *qual = nullptr) {
+  bool next(std::string &name, std::string &seq, std::string *qual = nullptr, std::string *comment = nullptr) {
     int r;
-    while ((r = step(name, seq, qual)) == FILE_END) {
+    while ((r = step(name, seq, qual, comment)) == FILE_END) {
     }
     return r == RECORD;
+  }
+};
+
+// --read-format (ReadFormatter.hpp): which stretches of read 1 / read 2 / the barcode record / the UMI
+// record are used.  A description is a ',' or ';' separated list of  <r1|r2|bc|um>:START:END[:STRAND]
+// (0-based, END inclusive, negative = counted from the end, STRAND '-' reverse-complements the
+// assembled stretch) or  <bc|um>:hd:FIELD:START:END[:STRAND]  for a stretch of the header comment
+// (FIELD = number of the whitespace separated field, or a prefix to search for).  Stretches of one
+// category are concatenated in the order given (ReadFormatter.hpp:275-391).
+struct ReadFormat {
+  enum { R1 = 0, R2 = 1, BARCODE = 2, UMI = 3, NCAT = 4 };
+  struct Seg {
+    int start = 0, end = -1, strand = 1;
+    bool inComment = false;
+    int field = -1;
+    std::string prefix;
+  };
+  std::vector<Seg> segs[NCAT];
+
+  // one item of the description (ReadFormatter.hpp:50-139)
+  bool ParseItem(const char *s, int len) {
+    if (len < 3 || s[2] != ':') return false;
+    int cat;
+    if (s[0] == 'r' && s[1] == '1') cat = R1;
+    else if (s[0] == 'r' && s[1] == '2') cat = R2;
+    else if (s[0] == 'b' && s[1] == 'c') cat = BARCODE;
+    else if (s[0] == 'u' && s[1] == 'm') cat = UMI;
+    else return false;
+    Seg seg;
+    int at = 3;
+    if (len >= 6 && s[3] == 'h' && s[4] == 'd' && s[5] == ':') {
+      seg.inComment = true;
+      int e = 6;
+      while (e < len && s[e] != ':') ++e;
+      const std::string tok(s + 6, (size_t)(e - 6));
+      const bool digits = tok.find_first_not_of("0123456789") == std::string::npos;
+      if (digits) seg.field = atoi(tok.c_str());
+      else seg.prefix = tok;
+      at = e + 1;
+    }
+    int part = 0;
+    std::string tok;
+    for (int i = at; i <= len; ++i) {
+      if (i >= len || s[i] == ':') {
+        if (part == 0) seg.start = atoi(tok.c_str());
+        else if (part == 1) seg.end = atoi(tok.c_str());
+        else seg.strand = (!tok.empty() && tok[0] == '+') ? 1 : -1;
+        tok.clear();
+        if (i < len && s[i] == ':') ++part;
+      } else {
+        tok += s[i];
+      }
+    }
+    if (part >= 3 || part < 1) return false;
+    segs[cat].push_back(seg);
+    return true;
+  }
+  void Init(const char *desc) {  // ReadFormatter.hpp:198-225
+    for (int i = 0; desc[i];) {
+      int j = i;
+      while (desc[j] && desc[j] != ';' && desc[j] != ',') ++j;
+      if (!ParseItem(desc + i, j - i)) {
+        fprintf(stderr, "Format description error in %s\n", desc);
+        exit(1);
+      }
+      i = desc[j] ? j + 1 : j;
+    }
+    for (int c = 0; c < NCAT; ++c) {  // ReadFormatter::AreSegmentsSorted (:140-149); an END of -1 always passes
+      inOrder[c] = true;
+      for (size_t q = 1; q < segs[c].size(); ++q)
+        if (segs[c][q].start <= segs[c][q - 1].end) inOrder[c] = false;
+    }
+  }
+  bool inOrder[NCAT] = {true, true, true, true};
+  bool InComment(int cat) const { return !segs[cat].empty() && segs[cat][0].inComment; }
+  bool NeedExtract(int cat) const {  // ReadFormatter.hpp:259-273
+    if (segs[cat].empty()) return false;
+    if (segs[cat].size() == 1) {
+      const Seg &g = segs[cat][0];
+      if (g.start == 0 && g.end == -1 && g.strand == 1 && !g.inComment) return false;
+    }
+    return true;
+  }
+  // the stretches of `in` (a sequence, a quality string or a header comment); complement = false for qualities.
+  // overwrite = true restates ReadFormatter::InplaceExtractSeqAndQual for stretches it considers in order:
+  // the reference then assembles the result inside the record itself, so a stretch that lies in front of an
+  // earlier one (possible when the earlier one ends at -1) is read after it was overwritten.
+  std::string Extract(const std::string &given, int cat, bool complement, bool overwrite = false) const {
+    if (!NeedExtract(cat)) return given;
+    const int len = (int)given.size();
+    std::string in = given, out;
+    int strand = 1;
+    for (const Seg &g : segs[cat]) {
+      int start = g.start, end = g.end, lenk = len;
+      if (InComment(cat)) {  // find the field, then count inside it (ReadFormatter.hpp:318-366)
+        int fstart = 0, fend = 0;
+        if (g.field >= 0) {
+          int f = 0;
+          for (int j = 0; j <= len; ++j) {
+            const char ch = j < len ? in[j] : '\0';
+            if (ch == ' ' || ch == '\t' || ch == '\0') {
+              ++f;
+              if (f == g.field) fstart = j + 1;
+              else if (f == g.field + 1) {
+                fend = j - 1;
+                break;
+              }
+            }
+          }
+          if (f <= g.field) {
+            fstart = len;
+            fend = len - 1;
+          }
+        } else {
+          const size_t p = in.find(g.prefix);
+          if (p != std::string::npos) {
+            fstart = (int)p;
+            size_t q = p;
+            while (q < in.size() && in[q] != ' ' && in[q] != '\t') ++q;
+            fend = (int)q - 1;
+          } else {
+            fstart = len;
+            fend = len - 1;
+          }
+        }
+        if (start >= 0) start += fstart;
+        if (end >= 0) end += fstart;
+        lenk = fend + 1;
+      }
+      if (start < 0) start = lenk + start;
+      if (end >= lenk) end = lenk - 1;
+      else if (end < 0) end = lenk + end;
+      if (start < 0) start = 0;  // the reference would read in front of its buffer here
+      for (int j = start; j <= end && j < len; ++j) {
+        out += in[j];
+        if (overwrite && out.size() <= in.size()) in[out.size() - 1] = in[j];
+      }
+      if (g.strand == -1) strand = -1;
+    }
+    if (strand == -1) {
+      std::reverse(out.begin(), out.end());
+      if (complement)
+        for (char &c : out) c = c == 'A' ? 'T' : c == 'C' ? 'G' : c == 'G' ? 'C' : c == 'T' ? 'A' : 'N';
+    }
+    return out;
+  }
+  // replaces the record just appended to `buf` (from `from` on) by its stretches
+  void ExtractTail(std::string &buf, size_t from, int cat, bool complement) const {
+    if (!NeedExtract(cat)) return;
+    const std::string rec = buf.substr(from);
+    buf.resize(from);
+    buf += Extract(rec, cat, complement, inOrder[cat]);
   }
 };
 
@@ -373,6 +529,9 @@ struct Batch {
   std::vector<uint64_t> off1, off2;
   std::vector<cfr_result> results;
   std::vector<uint64_t> assign;
+  // --barcode / --UMI / bc,um stretches of --read-format: the strings printed for each read
+  std::string bc, um;
+  std::vector<uint32_t> bc_off, um_off;
   // --expand-taxid only: the ids promoted into each assignment (cfr_fetch_expanded layout)
   std::vector<uint32_t> exp_cnt;
   std::vector<uint64_t> exp_off, exp_ids;
@@ -390,6 +549,10 @@ struct Batch {
   bool fileEnd = false;  // --sample-sheet: an input file ended with this batch, the TSV moves to the next output
   void clear() {
     fileEnd = false;
+    bc.clear();
+    um.clear();
+    bc_off.assign(1, 0);
+    um_off.assign(1, 0);
     merged.clear();
     orig1.clear();
     orig2.clear();
@@ -509,7 +672,9 @@ int main(int argc, char *argv[]) {
   cfr_params params;
   cfr_default_params(&params);
   const char *idxPrefix = NULL;
-  ReadSource reads, mates;
+  ReadSource reads, mates, barcodes, umis;  // --barcode / --UMI: one record per read, in step with the read files
+  ReadFormat fmt;                            // --read-format
+  bool hasBarcode = false, hasUmi = false;
   bool hasMate = false, interleaved = false;
   int device = 0;
   long batchReads = 1 << 20;
@@ -585,6 +750,9 @@ int main(int argc, char *argv[]) {
       else if (!strcmp(optarg, "runblock")) params.layout = CFR_LAYOUT_RUNBLOCK;
       else params.layout = CFR_LAYOUT_AUTO;
     } else if (c == ARGV_DRY_RUN) dryRun = true;
+    else if (c == ARGV_READ_FORMAT) fmt.Init(optarg);
+    else if (c == ARGV_BARCODE) { barcodes.add(optarg); hasBarcode = true; }
+    else if (c == ARGV_UMI) { umis.add(optarg); hasUmi = true; }
     else if (c == ARGV_DRY_PIPE) dryPipe = true;
     else if (c == ARGV_DRY_OUT) dryOut = true;
     else if (c == ARGV_MERGE) mergePairs = true;
@@ -599,6 +767,10 @@ int main(int argc, char *argv[]) {
       return EXIT_FAILURE;
     }
   }
+  // a barcode / UMI stretch in the description without a file of its own is cut out of read 1
+  // (CentrifugerClass.cpp:560-563, :141-146)
+  if (fmt.segs[ReadFormat::BARCODE].size() > 0) hasBarcode = true;
+  if (fmt.segs[ReadFormat::UMI].size() > 0) hasUmi = true;
   if (useSheet) {
     if (sheetOutputs.empty()) {
       PrintLog("ERROR: the sample sheet lists no files.");
@@ -690,21 +862,23 @@ int main(int argc, char *argv[]) {
   // mates, <prefix>.fq.gz without, gzip level 1
   const bool writeReads = unPrefix != NULL || clPrefix != NULL;
   const bool keepReads = writeReads || mergePairs;  // qualities are parsed: --un / --cl print them, the merger reads them
-  gzFile readOut[2][2] = {{NULL, NULL}, {NULL, NULL}};  // [0 = unclassified, 1 = classified][mate]
+  gzFile readOut[2][4] = {{NULL, NULL, NULL, NULL}, {NULL, NULL, NULL, NULL}};  // [0 = unclassified, 1 = classified][mate 1, mate 2, barcode, UMI]
   for (int cat = 0; cat < 2; ++cat) {
     const char *prefix = cat ? clPrefix : unPrefix;
     if (!prefix) continue;
     const std::string p(prefix);
     readOut[cat][0] = gzopen((hasMate ? p + "_1.fq.gz" : p + ".fq.gz").c_str(), "w1");
     if (hasMate) readOut[cat][1] = gzopen((p + "_2.fq.gz").c_str(), "w1");
-    if (!readOut[cat][0] || (hasMate && !readOut[cat][1])) {
+    if (hasBarcode) readOut[cat][2] = gzopen((p + "_bc.fa.gz").c_str(), "w1");  // ResultWriter.hpp:158-168
+    if (hasUmi) readOut[cat][3] = gzopen((p + "_um.fa.gz").c_str(), "w1");
+    if (!readOut[cat][0] || (hasMate && !readOut[cat][1]) || (hasBarcode && !readOut[cat][2]) || (hasUmi && !readOut[cat][3])) {
       PrintLog("ERROR: cannot open the read output files with prefix %s", prefix);
       return EXIT_FAILURE;
     }
   }
 
   std::thread ingest([&] {
-    std::string name, name2, tmp;
+    std::string name, name2, tmp, comment1;
     int bi = 0;
     bool eof = false;
     const bool twoFiles = hasMate && !interleaved;
@@ -734,6 +908,8 @@ int main(int argc, char *argv[]) {
             while (n2 >= n1.load(std::memory_order_acquire) && !done1.load(std::memory_order_acquire)) std::this_thread::yield();
             if (n2 >= n1.load(std::memory_order_acquire)) break;  // mate 1 is done and mate 2 has caught up
             if (mates.step(nm, bt->seq2, q2) != ReadSource::RECORD) break;  // mate 2 (or, with a sample sheet, its file) ended first
+            fmt.ExtractTail(bt->seq2, (size_t)bt->off2.back(), ReadFormat::R2, true);
+            if (keepReads && bt->qual2.size() > bt->qoff2.back()) fmt.ExtractTail(bt->qual2, (size_t)bt->qoff2.back(), ReadFormat::R2, false);
             bt->off2.push_back(bt->seq2.size());
             if (keepReads) bt->qoff2.push_back(bt->qual2.size());
             ++n2;
@@ -743,7 +919,7 @@ int main(int argc, char *argv[]) {
       while ((long)bt->n < batchReads && bt->seq1.size() < maxBases &&
              (bt->n == 0 || (bt->n + 1) * (maxLen / 24 + 1) <= slotBudget)) {
         name.clear();
-        const int got = reads.step(name, bt->seq1, keepReads ? &bt->qual1 : nullptr);
+        const int got = reads.step(name, bt->seq1, keepReads ? &bt->qual1 : nullptr, &comment1);
         if (got == ReadSource::FILE_END) {  // sample sheet: the batch ends with the file
           bt->fileEnd = true;
           break;
@@ -755,6 +931,32 @@ int main(int argc, char *argv[]) {
         RemoveReadIdSuffix(name);
         bt->ids += name;
         bt->id_off.push_back((uint32_t)bt->ids.size());
+        if (hasBarcode || hasUmi) {  // GetReadBatch, CentrifugerClass.cpp:128-227
+          // each comes from its own file, or is a copy of read 1 as read (before read 1 is cut itself)
+          const std::string raw1 = bt->seq1.substr((size_t)bt->off1.back());
+          for (int which = 0; which < 2; ++which) {
+            if (!(which ? hasUmi : hasBarcode)) continue;
+            ReadSource &src = which ? umis : barcodes;
+            const int cat = which ? ReadFormat::UMI : ReadFormat::BARCODE;
+            std::string rec, com, nm;
+            if (!src.files.empty()) {
+              if (!src.next(nm, rec, nullptr, &com)) {
+                PrintLog(which ? "ERROR: The UMI file and read file have different number of reads."
+                               : "ERROR: The barcode file and read file have different number of reads.");
+                exit(EXIT_FAILURE);
+              }
+            } else {
+              rec = raw1;
+              com = comment1;
+            }
+            const std::string val = fmt.InComment(cat) ? fmt.Extract(com, cat, true) : fmt.Extract(rec, cat, true, fmt.inOrder[cat]);
+            std::string &dst = which ? bt->um : bt->bc;
+            dst += val;
+            (which ? bt->um_off : bt->bc_off).push_back((uint32_t)dst.size());
+          }
+        }
+        fmt.ExtractTail(bt->seq1, (size_t)bt->off1.back(), ReadFormat::R1, true);
+        if (keepReads && bt->qual1.size() > bt->qoff1.back()) fmt.ExtractTail(bt->qual1, (size_t)bt->qoff1.back(), ReadFormat::R1, false);
         bt->off1.push_back(bt->seq1.size());
         maxLen = std::max(maxLen, (size_t)(bt->off1[bt->n + 1] - bt->off1[bt->n]));
         if (keepReads) bt->qoff1.push_back(bt->qual1.size());
@@ -764,6 +966,8 @@ int main(int argc, char *argv[]) {
             mate_mismatch = true;
             break;
           }
+          fmt.ExtractTail(bt->seq2, (size_t)bt->off2.back(), ReadFormat::R2, true);
+          if (keepReads && bt->qual2.size() > bt->qoff2.back()) fmt.ExtractTail(bt->qual2, (size_t)bt->qoff2.back(), ReadFormat::R2, false);
           bt->off2.push_back(bt->seq2.size());
           maxLen = std::max(maxLen, (size_t)(bt->off2[bt->n + 1] - bt->off2[bt->n]));
           if (keepReads) bt->qoff2.push_back(bt->qual2.size());
@@ -831,7 +1035,19 @@ int main(int argc, char *argv[]) {
     out.reserve(64 << 20);
     // ResultWriter::OutputHeader (ResultWriter.hpp:186-197)
     const std::string header = std::string("readID\tseqID\ttaxID\tscore\t2ndBestScore\thitLength\tqueryLength\tnumMatches") +
+                               (hasBarcode ? "\tbarcode" : "") + (hasUmi ? "\tUMI" : "") +
                                (expandTaxid ? "\texpandedTaxIDs" : "") + "\n";
+    // the barcode / UMI columns of read i (ResultWriter.hpp:222-225, :235-238)
+    auto put_extra = [&](const Batch *bt, size_t i) {
+      if (hasBarcode) {
+        out += '\t';
+        out.append(bt->bc, bt->bc_off[i], bt->bc_off[i + 1] - bt->bc_off[i]);
+      }
+      if (hasUmi) {
+        out += '\t';
+        out.append(bt->um, bt->um_off[i], bt->um_off[i + 1] - bt->um_off[i]);
+      }
+    };
     out += header;
     size_t sheetAt = 0;  // --sample-sheet: index of the input file being written (ResultWriter.hpp:75-107)
     std::vector<std::string> sheetSeen;
@@ -865,6 +1081,13 @@ int main(int argc, char *argv[]) {
             p = put_i32(p, r.hit_length); *p++ = '\t';
             p = put_i32(p, r.query_length); *p++ = '\t';
             p = put_i32(p, r.n_assign);
+            if (hasBarcode || hasUmi) {
+              out.resize((size_t)(p - out.data()));
+              put_extra(bt, i);
+              const size_t used = out.size();
+              out.resize(used + 8);
+              p = &out[used];
+            }
             if (expandTaxid) {  // ResultWriter.hpp:226-227: the original ids of the promoted nodes, comma separated
               *p++ = '\t';
               const uint32_t cnt = bt->exp_cnt[i * (size_t)k + j];
@@ -887,6 +1110,13 @@ int main(int argc, char *argv[]) {
           p = put_str(p, "\tunclassified\t0\t0\t0\t0\t", 22);
           p = put_i32(p, r.query_length);
           p = put_str(p, "\t1", 2);
+          if (hasBarcode || hasUmi) {
+            out.resize((size_t)(p - out.data()));
+            put_extra(bt, i);
+            const size_t used = out.size();
+            out.resize(used + 8);
+            p = &out[used];
+          }
           if (expandTaxid) *p++ = '\t';  // PrintExtraCol(""), ResultWriter.hpp:239-240
           *p++ = '\n';
           out.resize((size_t)(p - out.data()));
@@ -919,6 +1149,18 @@ int main(int argc, char *argv[]) {
                 rec += '\n';
               }
               gzwrite(readOut[cat][m], rec.data(), (unsigned)rec.size());
+            }
+            for (int w = 0; w < 2; ++w) {  // ResultWriter.hpp:265-273: ">id\n<barcode>\n", ">id\n<UMI>\n"
+              if (!readOut[cat][2 + w]) continue;
+              const std::string &vs = w ? bt->um : bt->bc;
+              const std::vector<uint32_t> &vo = w ? bt->um_off : bt->bc_off;
+              rec.clear();
+              rec += '>';
+              rec.append(id, idn);
+              rec += '\n';
+              rec.append(vs, vo[i], vo[i + 1] - vo[i]);
+              rec += '\n';
+              gzwrite(readOut[cat][2 + w], rec.data(), (unsigned)rec.size());
             }
           }
         }
@@ -1030,7 +1272,7 @@ int main(int argc, char *argv[]) {
   ingest.join();
   output.join();
   for (int cat = 0; cat < 2; ++cat)
-    for (int m = 0; m < 2; ++m)
+    for (int m = 0; m < 4; ++m)
       if (readOut[cat][m]) gzclose(readOut[cat][m]);
   if (mate_mismatch) {
     PrintLog("ERROR: The two mate-pair read files have different number of reads.");  // CentrifugerClass.cpp:121-125

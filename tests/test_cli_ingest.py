@@ -61,7 +61,7 @@ def test_usage_and_version_and_rejections():
     r = subprocess.run([EXE], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
     assert r.returncode == 0 and b"-x FILE: index prefix" in r.stderr  # CentrifugerClass.cpp:347-351
     assert subprocess.run([EXE, "-v"], stdout=subprocess.PIPE).stdout.decode().strip() == "Centrifuger v1.1.3-r347"
-    r = subprocess.run([EXE, "-x", "nope", "-u", "x.fq", "--barcode", "b.fq"], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    r = subprocess.run([EXE, "-x", "nope", "-u", "x.fq", "--barcode-whitelist", "w.txt"], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
     assert r.returncode != 0 and b"not supported" in r.stderr
     r = subprocess.run([EXE, "-u", "x.fq"], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
     assert r.returncode != 0 and b"Need to use -x" in r.stderr
@@ -246,3 +246,33 @@ def test_glob_in_file_names(tiny_dir):
                 "-2", os.path.join(tiny_dir, "edge_2.fq"), "-2", os.path.join(tiny_dir, "pe_100_2.fq")])
     got = _dry(["-1", os.path.join(tiny_dir, "*e*_1.fq"), "-2", os.path.join(tiny_dir, "*e*_2.fq")])
     assert got == ref and len(ref) > 300
+
+
+def test_read_format_barcode_umi_plumbing(manifest, tmp_path):
+    """--read-format / --barcode / --UMI on the ingest and output stages: with every read unclassified the TSV
+    (barcode / UMI columns, query lengths after the read stretches are cut) and the --un files (reads and
+    qualities as cut, _bc / _um FASTA files) are byte for byte the reference binary's"""
+    import hashlib
+    from conftest import golden_path
+    for name, m in sorted(manifest["barcode"].items()):
+        files = [golden_path("tiny", f) for f in m["files"]]
+        args = [golden_path("tiny", o[1:]) if o.startswith("@") else o for o in m["args"]]
+        for batch in ("1048576", "29"):
+            od = tmp_path / (name + "_" + batch)
+            od.mkdir()
+            cmd = [EXE, "--dry-run-output", "--batch", batch] + args
+            cmd += ["-u", files[0]] if len(files) == 1 else ["-1", files[0], "-2", files[1]]
+            cmd += ["--un", str(od / "un"), "--cl", str(od / "cl")]
+            r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=120)
+            assert r.returncode == 0, r.stderr.decode()
+            exp = open(golden_path("tiny", "barcode", name + "__unclassified.tsv")).read()
+            assert r.stdout.decode() == exp, (name, batch)
+            got = {f: hashlib.md5(gzip.open(str(od / f), "rb").read()).hexdigest() for f in sorted(os.listdir(str(od)))}
+            assert got == m["unclassified"]["outputs"], (name, batch)
+    r = subprocess.run([EXE, "--dry-run-output", "-u", "x.fq", "--read-format", "r3:0:1"], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert r.returncode == 1 and b"Format description error in r3:0:1" in r.stderr  # ReadFormatter.hpp:207-211
+    short = tmp_path / "short_bc.fq"
+    short.write_text("@a\nACGT\n+\nIIII\n")
+    r = subprocess.run([EXE, "--dry-run-output", "-u", golden_path("tiny", "se_100.fq"), "--barcode", str(short)],
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert r.returncode != 0 and b"barcode file and read file have different number of reads" in r.stderr

@@ -487,3 +487,24 @@ def test_gpu_fuzz_rounds():
     r = subprocess.run([sys.executable, os.path.join(root, "tools", "fuzz_gpu.py"), "6", "303"],
                        stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=600)
     assert r.returncode == 0 and b"ok:" in r.stdout, r.stdout.decode()[-3000:]
+
+
+def test_cli_read_format_barcode_umi(tiny_dir, manifest, tmp_path):
+    """--read-format / --barcode / --UMI with real classification: TSV (barcode / UMI columns) and the
+    --un / --cl files (reads as cut and masked, _bc / _um files) are the reference binary's"""
+    import gzip
+    import subprocess
+    exe = os.path.join(os.path.dirname(cb.LIB_PATH), "centrifuger-b200")
+    for name, m in sorted(manifest["barcode"].items()):
+        files = [golden_path("tiny", f) for f in m["files"]]
+        args = [golden_path("tiny", o[1:]) if o.startswith("@") else o for o in m["args"]]
+        od = tmp_path / name
+        od.mkdir()
+        cmd = [exe, "-x", os.path.join(tiny_dir, "idx"), "--batch", "61"] + args
+        cmd += ["-u", files[0]] if len(files) == 1 else ["-1", files[0], "-2", files[1]]
+        cmd += ["--un", str(od / "un"), "--cl", str(od / "cl")]
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+        assert r.returncode == 0, r.stderr.decode()
+        assert r.stdout.decode() == open(golden_path("tiny", "barcode", name + "__real.tsv")).read(), name
+        got = {f: hashlib.md5(gzip.open(str(od / f), "rb").read()).hexdigest() for f in sorted(os.listdir(str(od)))}
+        assert got == m["real"]["outputs"], name
