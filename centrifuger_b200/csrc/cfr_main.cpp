@@ -9,7 +9,7 @@
 // ResultWriter-style output on an output thread.
 //
 // Not supported (the reference's single-cell extras, SURVEY.md 8 "out of scope"):
-// --barcode-whitelist / --barcode-translate, barcode / UMI columns of a sample sheet.  They are rejected
+// --barcode-whitelist / --barcode-translate.  They are rejected
 // with a log line and EXIT_FAILURE.
 #include <getopt.h>
 #include <glob.h>
@@ -704,9 +704,13 @@ int main(int argc, char *argv[]) {
       while (fgets(line, sizeof(line), fs)) {
         f1[0] = f2[0] = bc[0] = um[0] = of[0] = 0;
         if (sscanf(line, "%2047s %2047s %2047s %2047s %2047s", f1, f2, bc, um, of) < 1) continue;
-        if (strcmp(bc, ".") || strcmp(um, ".")) {
-          PrintLog("ERROR: barcode / UMI files in the sample sheet are not supported by centrifuger-b200.");
-          return EXIT_FAILURE;
+        if (strcmp(bc, ".")) {  // CentrifugerClass.cpp:495-505
+          barcodes.add(bc);
+          hasBarcode = true;
+        }
+        if (strcmp(um, ".")) {
+          umis.add(um);
+          hasUmi = true;
         }
         const bool paired = strcmp(f2, ".") != 0;
         if (!sheetOutputs.empty() && paired != hasMate) {

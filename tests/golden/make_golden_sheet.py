@@ -22,14 +22,20 @@ REF = os.path.join(ROOT, "oracle", "_ref", "centrifuger")
 SHEETS = {
     "pe": ([("pe_100_1.fq", "pe_100_2.fq", "a"), ("edge_1.fq", "edge_2.fq", "b"), ("ov_1.fq", "ov_2.fq", "a")], []),
     "se_k3": ([("se_100.fq", ".", "a"), ("edge.fq", ".", "b"), ("se_100.fa", ".", "c")], ["-k", "3"]),
+    # rows with barcode and UMI files (4th and 5th element; the technical reads of bc.fq serve both)
+    "se_bc": ([("se_100.fq", ".", "a", "bc.fq", "bc.fq"), ("se_com.fq", ".", "b", "bc.fq", "bc.fq")],
+              ["--read-format", "bc:0:15,um:16:25"]),
 }
 
 
 def write_sheet(path, rows, src, outdir):
     with open(path, "w") as f:
-        for r1, r2, o in rows:
-            f.write("%s %s . . %s\n" % (os.path.join(src, r1), r2 if r2 == "." else os.path.join(src, r2),
-                                        os.path.join(outdir, o + ".tsv")))
+        for row in rows:
+            r1, r2, o = row[:3]
+            bc, um = (row[3], row[4]) if len(row) > 3 else (".", ".")
+            f.write("%s %s %s %s %s\n" % (os.path.join(src, r1), r2 if r2 == "." else os.path.join(src, r2),
+                                          bc if bc == "." else os.path.join(src, bc), um if um == "." else os.path.join(src, um),
+                                          os.path.join(outdir, o + ".tsv")))
 
 
 def main():

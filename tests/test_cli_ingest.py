@@ -200,9 +200,12 @@ def test_batches_end_early_when_a_long_read_arrives(tiny_dir, tmp_path):
 def _write_sheet(path, rows, outdir):
     from conftest import golden_path
     with open(path, "w") as f:
-        for r1, r2, o in rows:
-            f.write("%s %s . . %s\n" % (golden_path("tiny", r1), r2 if r2 == "." else golden_path("tiny", r2),
-                                        os.path.join(str(outdir), o + ".tsv")))
+        for row in rows:
+            r1, r2, o = row[:3]
+            bc, um = (row[3], row[4]) if len(row) > 3 else (".", ".")
+            f.write("%s %s %s %s %s\n" % (golden_path("tiny", r1), r2 if r2 == "." else golden_path("tiny", r2),
+                                          bc if bc == "." else golden_path("tiny", bc), um if um == "." else golden_path("tiny", um),
+                                          os.path.join(str(outdir), o + ".tsv")))
 
 
 def test_sample_sheet_routes_reads_to_their_output_files(manifest, tmp_path):
@@ -231,9 +234,13 @@ def test_sample_sheet_routes_reads_to_their_output_files(manifest, tmp_path):
                     if l and (not exp_reads or exp_reads[-1][0] != l.split("\t")[0]):  # -k > 1: several rows per read
                         exp_reads.append((l.split("\t")[0], l.split("\t")[6]))
                 assert [(l.split("\t")[0], l.split("\t")[6]) for l in got[1:] if l] == exp_reads, (case, o, batch)
+                if "barcode" in exp[0]:  # the barcode / UMI columns of every read
+                    cols = lambda ls: sorted(set((l.split("\t")[0],) + tuple(l.split("\t")[8:10]) for l in ls[1:] if l))
+                    assert cols(got) == cols(exp), (case, o)
     # rows that ask for what this build does not do are refused
     bad = tmp_path / "bad.sheet"
-    bad.write_text("%s . %s . %s\n" % (golden_path("tiny", "se_100.fq"), golden_path("tiny", "se_100.fq"), tmp_path / "x.tsv"))
+    bad.write_text("%s . . . %s\n%s %s . . %s\n" % (golden_path("tiny", "se_100.fq"), tmp_path / "x.tsv", golden_path("tiny", "pe_100_1.fq"),
+                                                   golden_path("tiny", "pe_100_2.fq"), tmp_path / "y.tsv"))
     r = subprocess.run([EXE, "--dry-run-output", "--sample-sheet", str(bad)], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
     assert r.returncode != 0 and b"not supported" in r.stderr
     r = subprocess.run([EXE, "--dry-run-output", "--sample-sheet", str(tmp_path / "missing.sheet")], stdout=subprocess.PIPE, stderr=subprocess.PIPE)

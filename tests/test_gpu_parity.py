@@ -469,9 +469,12 @@ def test_cli_sample_sheet(tiny_dir, manifest, tmp_path):
         od.mkdir()
         sheet = tmp_path / (case + ".sheet")
         with open(str(sheet), "w") as f:
-            for r1, r2, o in m["rows"]:
-                f.write("%s %s . . %s\n" % (golden_path("tiny", r1), r2 if r2 == "." else golden_path("tiny", r2),
-                                            str(od / (o + ".tsv"))))
+            for row in m["rows"]:
+                r1, r2, o = row[:3]
+                bc, um = (row[3], row[4]) if len(row) > 3 else (".", ".")
+                f.write("%s %s %s %s %s\n" % (golden_path("tiny", r1), r2 if r2 == "." else golden_path("tiny", r2),
+                                              bc if bc == "." else golden_path("tiny", bc), um if um == "." else golden_path("tiny", um),
+                                              str(od / (o + ".tsv"))))
         r = subprocess.run([exe, "-x", os.path.join(tiny_dir, "idx"), "--batch", "41", "--sample-sheet", str(sheet)] + m["args"],
                            stdout=subprocess.PIPE, stderr=subprocess.PIPE)
         assert r.returncode == 0 and r.stdout == b"", r.stderr.decode()
