@@ -1,16 +1,13 @@
 // cfr_main.cpp -- `centrifuger-b200`: drop-in for the reference's classification
-// binary (CentrifugerClass.cpp) on the paths this repo covers: same -x/-1/-2/-u/-i/
-// -t/-k/--min-hitlen/--hitk-factor/--no-dust/--consider-secondary/--un/--cl/
-// --merge-readpair/--expand-taxid/--sample-sheet/--read-format/--barcode/--UMI/-h/-v options, the reference's own *.cfr index files, the identical
-// TSV on stdout and the same log lines on stderr.  All classification work is done by
-// libcfrb200.so on the GPU (include/centrifuger_b200.h); this file is host I/O only:
-// gz FASTA/FASTQ parsing (ReadFiles.hpp + kseq.h behaviour) on an ingest thread (mate 2
-// on a second one), batching, the read-pair merger (ReadPairMerger.hpp behaviour) and
-// ResultWriter-style output on an output thread.
-//
-// Not supported (the reference's single-cell extras, SURVEY.md 8 "out of scope"):
-// --barcode-whitelist / --barcode-translate.  They are rejected
-// with a log line and EXIT_FAILURE.
+// binary (CentrifugerClass.cpp): the same options (-x/-1/-2/-u/-i/--sample-sheet/-t/-k/--min-hitlen/
+// --hitk-factor/--no-dust/--consider-secondary/--un/--cl/--merge-readpair/--expand-taxid/--read-format/
+// --barcode/--UMI/--barcode-whitelist/--barcode-translate/-h/-v), the reference's own *.cfr index files,
+// the identical TSV on stdout and the same log lines on stderr.  All classification work is done by
+// libcfrb200.so on the GPU (include/centrifuger_b200.h); this file is host I/O only: gz FASTA/FASTQ
+// parsing (ReadFiles.hpp + kseq.h behaviour) on an ingest thread (mate 2 on a second one), batching, read
+// stretches / barcodes / UMIs (ReadFormatter.hpp, BarcodeCorrector.hpp, BarcodeTranslator.hpp behaviour),
+// the read-pair merger (ReadPairMerger.hpp behaviour) and ResultWriter-style output on an output thread.
+// Protein indexes are refused by the library at load.
 #include <getopt.h>
 #include <glob.h>
 #include <sys/stat.h>
@@ -27,6 +24,7 @@
 #include <mutex>
 #include <string>
 #include <thread>
+#include <unordered_map>
 #include <deque>
 #include <iterator>
 #include <vector>
@@ -55,6 +53,8 @@ static const char usage[] =
     "\t--barcode STR: path to the barcode file\n"
     "\t--UMI STR: path to the UMI file\n"
     "\t--read-format STR: format for read, barcode and UMI files, e.g. r1:0:-1,r2:0:-1,bc:0:15,um:16:-1 for paired-end files with barcode and UMI\n"
+    "\t--barcode-whitelist STR: path to the barcode whitelist file\n"
+    "\t--barcode-translate STR: path to the barcode translation file\n"
     "\t--expand-taxid: output the tax IDs that are promoted to the final report tax ID [no]\n"
     "\t--no-dust: do not DUST-mask low-complexity regions of reads [mask]\n"
     "\t--min-hitlen INT: minimum length of partial hits [auto]\n"
@@ -68,7 +68,7 @@ static const char usage[] =
 
 enum {
   ARGV_NO_DUST = 256, ARGV_MIN_HITLEN, ARGV_HITK, ARGV_SECONDARY, ARGV_GPU, ARGV_BATCH, ARGV_LAYOUT,
-  ARGV_UNSUPPORTED, ARGV_DRY_RUN, ARGV_DRY_PIPE, ARGV_UN, ARGV_CL, ARGV_MERGE, ARGV_EXPAND, ARGV_SAMPLE_SHEET, ARGV_DRY_OUT, ARGV_READ_FORMAT, ARGV_BARCODE, ARGV_UMI
+  ARGV_UNSUPPORTED, ARGV_DRY_RUN, ARGV_DRY_PIPE, ARGV_UN, ARGV_CL, ARGV_MERGE, ARGV_EXPAND, ARGV_SAMPLE_SHEET, ARGV_DRY_OUT, ARGV_READ_FORMAT, ARGV_BARCODE, ARGV_UMI, ARGV_BC_WHITELIST, ARGV_BC_TRANSLATE
 };
 
 static const char *short_options = "x:1:2:u:i:o:t:k:hv";
@@ -90,8 +90,8 @@ static struct option long_options[] = {
     {"read-format", required_argument, 0, ARGV_READ_FORMAT},
     {"barcode", required_argument, 0, ARGV_BARCODE},
     {"UMI", required_argument, 0, ARGV_UMI},
-    {"barcode-whitelist", required_argument, 0, ARGV_UNSUPPORTED},
-    {"barcode-translate", required_argument, 0, ARGV_UNSUPPORTED},
+    {"barcode-whitelist", required_argument, 0, ARGV_BC_WHITELIST},
+    {"barcode-translate", required_argument, 0, ARGV_BC_TRANSLATE},
     {"sample-sheet", required_argument, 0, ARGV_SAMPLE_SHEET},
     {(char *)0, 0, 0, 0}};
 
@@ -410,6 +410,130 @@ struct ReadFormat {
   }
 };
 
+// --barcode-whitelist (BarcodeCorrector.hpp): a barcode that is not on the list is replaced by the listed
+// barcode one substitution away that was seen most often among the first two million barcodes (ties: the
+// one whose changed base has the lowest quality, then the first in position / base order); none -> "N".
+// The list lives in a 4-ary trie like the reference's, because its look-up also "finds" a proper prefix
+// of a listed barcode (with whatever count that inner node has), and that decides what gets corrected.
+struct BarcodeWhitelist {
+  struct Node {
+    int next[4] = {-1, -1, -1, -1};
+    int count = 0;
+  };
+  std::vector<Node> nodes;
+  int listed = 0;
+  BarcodeWhitelist() : nodes(1) {}
+  static int Code(char c) { return c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : -1; }
+  void Insert(const std::string &s, int weight) {  // Trie::Insert (:69-94)
+    for (char c : s)
+      if (Code(c) < 0) return;
+    int p = 0;
+    bool grew = false;
+    for (char c : s) {
+      const int t = Code(c);
+      if (nodes[p].next[t] < 0) {
+        nodes[p].next[t] = (int)nodes.size();
+        nodes.push_back(Node());
+        grew = true;
+      }
+      p = nodes[p].next[t];
+    }
+    nodes[p].count += weight;
+    if (grew) ++listed;
+  }
+  int Find(const std::string &s, int weight) {  // Trie::SearchAndUpdate (:96-113): count after the update, -1 = absent
+    for (char c : s)
+      if (Code(c) < 0) return -1;
+    int p = 0;
+    for (char c : s) {
+      p = nodes[p].next[Code(c)];
+      if (p < 0) return -1;
+    }
+    nodes[p].count += weight;
+    return nodes[p].count;
+  }
+  bool Load(const char *file) {  // SetWhitelist (:123-143)
+    gzFile fp = gzopen(file, "r");
+    if (!fp) return false;
+    char buffer[256];
+    while (gzgets(fp, buffer, sizeof(buffer)) != NULL) {
+      size_t len = strlen(buffer);
+      if (len && buffer[len - 1] == '\n') buffer[--len] = 0;
+      Insert(buffer, 1);
+    }
+    gzclose(fp);
+    return true;
+  }
+  // Correct (:164-233): -1 could not correct, 0 listed, 1 corrected in place; qual may be empty
+  int Correct(std::string &bc, const std::string &qual) {
+    if (Find(bc, 0) != -1) return 0;
+    int bestCnt = -1, bestPos = -1, bestBase = -1, bestLowQual = 255;
+    std::string probe = bc;
+    for (size_t i = 0; i < bc.size(); ++i)
+      for (int j = 0; j < 4; ++j) {
+        if ("ACGT"[j] == bc[i]) continue;
+        probe[i] = "ACGT"[j];
+        const int cnt = Find(probe, 0);
+        probe[i] = bc[i];
+        if (cnt == -1) continue;
+        const bool haveQual = i < qual.size();
+        if (cnt > bestCnt) {
+          bestCnt = cnt;
+          bestPos = (int)i;
+          bestBase = j;
+          if (!qual.empty()) bestLowQual = haveQual ? qual[i] : 0;
+        } else if (cnt == bestCnt && !qual.empty() && (haveQual ? qual[i] : 0) < bestLowQual) {
+          bestLowQual = haveQual ? qual[i] : 0;
+          bestPos = (int)i;
+          bestBase = j;
+        }
+      }
+    if (bestPos < 0) return -1;
+    bc[(size_t)bestPos] = "ACGT"[bestBase];
+    return 1;
+  }
+};
+
+// --barcode-translate (BarcodeTranslator.hpp): lines "<to><sep><from>"; a barcode is cut into pieces as long
+// as the last line's <from>, each piece is replaced, the results are joined with '-'
+struct BarcodeTranslation {
+  std::unordered_map<std::string, std::string> table;  // from -> to, a later line replaces an earlier one
+  int fromLen = -1;
+  bool set = false;
+  bool Load(const char *file) {
+    gzFile fp = gzopen(file, "r");
+    if (!fp) return false;
+    set = true;
+    char line[512];
+    while (gzgets(fp, line, sizeof(line)) != NULL) {
+      size_t len = strlen(line);
+      if (len && line[len - 1] == '\n') line[--len] = 0;
+      size_t i = 0;
+      while (i < len && line[i] != ',' && line[i] != '\t' && line[i] != ' ') ++i;
+      const std::string to(line, i), from(i < len ? line + i + 1 : "");
+      fromLen = i < len ? (int)(len - i - 1) : -1;
+      table[from] = to;
+    }
+    gzclose(fp);
+    return true;
+  }
+  std::string Translate(const std::string &bc) const {
+    std::string ret;
+    if (fromLen <= 0) return ret;
+    for (size_t i = 0; i < bc.size() / (size_t)fromLen; ++i) {
+      const std::string piece = bc.substr(i * (size_t)fromLen, (size_t)fromLen);
+      const auto hit = table.find(piece);
+      const std::string *to = hit == table.end() ? nullptr : &hit->second;
+      if (!to) {
+        fprintf(stderr, "Barcode %s does not exist in the translation table.\n", piece.c_str());
+        exit(-1);
+      }
+      ret += i ? "-" + *to : *to;
+    }
+    return ret;
+  }
+};
+
 // --merge-readpair (ReadPairMerger.hpp; applied in CentrifugerClass.cpp:271-272): before a pair is
 // classified, mate 2 is reverse-complemented and laid over mate 1.  If the fragment was shorter than a
 // read ("read-through": mate 1 starts inside rc(mate 2)) the pair is trimmed to the fragment; if the
@@ -675,6 +799,9 @@ int main(int argc, char *argv[]) {
   ReadSource reads, mates, barcodes, umis;  // --barcode / --UMI: one record per read, in step with the read files
   ReadFormat fmt;                            // --read-format
   bool hasBarcode = false, hasUmi = false;
+  BarcodeWhitelist whitelist;      // --barcode-whitelist
+  BarcodeTranslation translation;  // --barcode-translate
+  bool hasWhitelist = false;
   bool hasMate = false, interleaved = false;
   int device = 0;
   long batchReads = 1 << 20;
@@ -757,6 +884,18 @@ int main(int argc, char *argv[]) {
     else if (c == ARGV_READ_FORMAT) fmt.Init(optarg);
     else if (c == ARGV_BARCODE) { barcodes.add(optarg); hasBarcode = true; }
     else if (c == ARGV_UMI) { umis.add(optarg); hasUmi = true; }
+    else if (c == ARGV_BC_WHITELIST) {
+      if (!whitelist.Load(optarg)) {
+        PrintLog("ERROR: cannot open the barcode whitelist %s", optarg);
+        return EXIT_FAILURE;
+      }
+      hasWhitelist = true;
+    } else if (c == ARGV_BC_TRANSLATE) {
+      if (!translation.Load(optarg)) {
+        PrintLog("ERROR: cannot open the barcode translation table %s", optarg);
+        return EXIT_FAILURE;
+      }
+    }
     else if (c == ARGV_DRY_PIPE) dryPipe = true;
     else if (c == ARGV_DRY_OUT) dryOut = true;
     else if (c == ARGV_MERGE) mergePairs = true;
@@ -775,6 +914,23 @@ int main(int argc, char *argv[]) {
   // (CentrifugerClass.cpp:560-563, :141-146)
   if (fmt.segs[ReadFormat::BARCODE].size() > 0) hasBarcode = true;
   if (fmt.segs[ReadFormat::UMI].size() > 0) hasUmi = true;
+  if (hasBarcode && hasWhitelist) {  // CentrifugerClass.cpp:565-574
+    if (barcodes.files.empty()) {
+      PrintLog("Barcode whitelist has to be used with --barcode option, so cases like piping input is not supported.");
+      return EXIT_FAILURE;
+    }
+    // BarcodeCorrector::CollectBackgroundDistribution: how often each listed barcode occurs among the first
+    // two million records, then the barcode files are read again from the start
+    std::string nm, rec;
+    for (int seen = 0; seen < 2000000; ++seen) {
+      rec.clear();
+      if (!barcodes.next(nm, rec)) break;
+      whitelist.Find(fmt.Extract(rec, ReadFormat::BARCODE, true), 1);
+    }
+    if (barcodes.opened) barcodes.rd.close();
+    barcodes.opened = false;
+    barcodes.cur = 0;
+  }
   if (useSheet) {
     if (sheetOutputs.empty()) {
       PrintLog("ERROR: the sample sheet lists no files.");
@@ -942,9 +1098,9 @@ int main(int argc, char *argv[]) {
             if (!(which ? hasUmi : hasBarcode)) continue;
             ReadSource &src = which ? umis : barcodes;
             const int cat = which ? ReadFormat::UMI : ReadFormat::BARCODE;
-            std::string rec, com, nm;
+            std::string rec, com, nm, rq;
             if (!src.files.empty()) {
-              if (!src.next(nm, rec, nullptr, &com)) {
+              if (!src.next(nm, rec, &rq, &com)) {
                 PrintLog(which ? "ERROR: The UMI file and read file have different number of reads."
                                : "ERROR: The barcode file and read file have different number of reads.");
                 exit(EXIT_FAILURE);
@@ -953,7 +1109,16 @@ int main(int argc, char *argv[]) {
               rec = raw1;
               com = comment1;
             }
-            const std::string val = fmt.InComment(cat) ? fmt.Extract(com, cat, true) : fmt.Extract(rec, cat, true, fmt.inOrder[cat]);
+            std::string val = fmt.InComment(cat) ? fmt.Extract(com, cat, true) : fmt.Extract(rec, cat, true, fmt.inOrder[cat]);
+            if (which == 0) {  // CentrifugerClass.cpp:186-206: whitelist correction, then translation; "N" when neither listed nor correctable
+              int verdict = 0;
+              if (whitelist.listed > 0) {
+                const std::string qv = (!fmt.InComment(cat) && !rq.empty()) ? fmt.Extract(rq, cat, false, fmt.inOrder[cat]) : std::string();
+                verdict = whitelist.Correct(val, qv);
+              }
+              if (verdict < 0) val = "N";
+              else if (translation.set) val = translation.Translate(val);
+            }
             std::string &dst = which ? bt->um : bt->bc;
             dst += val;
             (which ? bt->um_off : bt->bc_off).push_back((uint32_t)dst.size());

@@ -33,6 +33,12 @@ CASES = {
     "se_um_only": (["se_100.fq"], ["--UMI", "@bc.fq", "--read-format", "um:-12:-3;r1:5:80:+"]),
     "fa_inline_um": (["se_100.fa"], ["--read-format", "r1:5:80:+,um:0:4"]),
     "pe_unsorted_segments": (["pe_100_1.fq", "pe_100_2.fq"], ["--read-format", "r1:50:-1,r1:0:30,r2:20:90,bc:hd:1:0:-1"]),
+    # BarcodeCorrector / BarcodeTranslator: bc_whitelist.txt lacks one of the seven barcodes (-> "N") and holds
+    # close variants of another (several one-substitution candidates: counts, then base qualities decide)
+    "se_whitelist": (["se_100.fq"], ["--barcode", "@bc.fq", "--read-format", "bc:0:15", "--barcode-whitelist", "@bc_whitelist.txt"]),
+    "se_whitelist_translate": (["se_100.fq"], ["--barcode", "@bc.fq", "--UMI", "@bc.fq", "--read-format", "bc:0:15,um:16:25",
+                                               "--barcode-whitelist", "@bc_whitelist.txt", "--barcode-translate", "@bc_translate.tsv"]),
+    "se_translate_only": (["se_100.fq"], ["--barcode", "@bc.fq", "--read-format", "bc:0:15", "--barcode-translate", "@bc_translate_all.tsv"]),
 }
 
 
@@ -41,6 +47,7 @@ def write_inputs(tg):
     recs = open(os.path.join(tg, "se_100.fq")).read().split("\n")
     with open(os.path.join(tg, "bc.fq"), "w") as fb, open(os.path.join(tg, "se_com.fq"), "w") as fc:
         pool = ["".join(rng.choice(list("ACGT"), size=16)) for _ in range(7)]
+        seen = set()
         for i in range(len(recs) // 4):
             name = recs[4 * i][1:].split()[0]
             bc = pool[int(rng.integers(len(pool)))]
@@ -48,9 +55,22 @@ def write_inputs(tg):
                 bc = bc[:5] + "N" + bc[6:]
             umi = "".join(rng.choice(list("ACGT"), size=10))
             q = "".join(rng.choice(list("#5?FI"), size=28))
+            seen.add(bc)
             fb.write("@%s\n%s%sTT\n+\n%s\n" % (name, bc, umi, q))
             comment = "CB:Z:%s\tUB:Z:%s" % (bc, umi) if i % 13 else ("UB:Z:%s" % umi if i % 2 else "")
             fc.write("@%s%s\n%s\n+\n%s\n" % (name, (" " + comment) if comment else "", recs[4 * i + 1], recs[4 * i + 3]))
+    listed = pool[:6]  # pool[6] is not on the list
+    for b in "ACGT":   # close variants of pool[0] at the position where every 11th barcode carries an N
+        v = pool[0][:5] + b + pool[0][6:]
+        if v not in listed:
+            listed.append(v)
+    listed.append(pool[1][:9] + ("A" if pool[1][9] != "A" else "C") + pool[1][10:])
+    with open(os.path.join(tg, "bc_whitelist.txt"), "w") as f:
+        f.write("".join(b + "\n" for b in listed))
+    with open(os.path.join(tg, "bc_translate.tsv"), "w") as f:
+        f.write("".join("CELL%03d\t%s\n" % (i, b) for i, b in enumerate(listed)))
+    with open(os.path.join(tg, "bc_translate_all.tsv"), "w") as f:  # without a whitelist every barcode as read must be listed
+        f.write("".join("RAW%03d,%s\n" % (i, b) for i, b in enumerate(sorted(seen))))
 
 
 def main():

@@ -61,8 +61,8 @@ def test_usage_and_version_and_rejections():
     r = subprocess.run([EXE], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
     assert r.returncode == 0 and b"-x FILE: index prefix" in r.stderr  # CentrifugerClass.cpp:347-351
     assert subprocess.run([EXE, "-v"], stdout=subprocess.PIPE).stdout.decode().strip() == "Centrifuger v1.1.3-r347"
-    r = subprocess.run([EXE, "-x", "nope", "-u", "x.fq", "--barcode-whitelist", "w.txt"], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
-    assert r.returncode != 0 and b"not supported" in r.stderr
+    r = subprocess.run([EXE, "-x", "nope", "-u", "x.fq", "--no-such-option"], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert r.returncode != 0 and b"-x FILE: index prefix" in r.stderr  # unknown option: usage, failure (CentrifugerClass.cpp:541-545)
     r = subprocess.run([EXE, "-u", "x.fq"], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
     assert r.returncode != 0 and b"Need to use -x" in r.stderr
 
@@ -283,3 +283,16 @@ def test_read_format_barcode_umi_plumbing(manifest, tmp_path):
     r = subprocess.run([EXE, "--dry-run-output", "-u", golden_path("tiny", "se_100.fq"), "--barcode", str(short)],
                        stdout=subprocess.PIPE, stderr=subprocess.PIPE)
     assert r.returncode != 0 and b"barcode file and read file have different number of reads" in r.stderr
+
+
+def test_barcode_whitelist_and_translate_refusals(tmp_path):
+    from conftest import golden_path
+    se, wl = golden_path("tiny", "se_100.fq"), golden_path("tiny", "bc_whitelist.txt")
+    # a whitelist needs a barcode file to learn the barcode frequencies from (CentrifugerClass.cpp:565-574)
+    r = subprocess.run([EXE, "--dry-run-output", "-u", se, "--read-format", "bc:0:15", "--barcode-whitelist", wl],
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert r.returncode != 0 and b"Barcode whitelist has to be used with --barcode option" in r.stderr
+    # a barcode the translation table does not know ends the run (BarcodeTranslator.hpp:66-72)
+    r = subprocess.run([EXE, "--dry-run-output", "-u", se, "--barcode", golden_path("tiny", "bc.fq"), "--read-format", "bc:0:15",
+                        "--barcode-translate", golden_path("tiny", "bc_translate.tsv")], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert r.returncode != 0 and b"does not exist in the translation table." in r.stderr
