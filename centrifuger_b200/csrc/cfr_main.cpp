@@ -121,6 +121,7 @@ class SeqReader {
     buf_.resize(4 << 20);
     len_ = pos_ = 0;
     eof_ = false;
+    dead_ = false;
     return true;
   }
   void close() {
@@ -132,6 +133,7 @@ class SeqReader {
   bool next(std::string &name, std::string &seq, std::string *qual = nullptr, std::string *comment = nullptr) {
     const char *ln;
     size_t n;
+    if (dead_) return false;
     // header line
     for (;;) {
       if (!line(ln, n)) return false;
@@ -148,17 +150,37 @@ class SeqReader {
       if (!peek_line(ln, n)) return true;  // EOF ends the record
       if (n > 0 && (ln[0] == '+' || ln[0] == '>' || ln[0] == '@')) break;
       seq.append(ln, n);
+      // kseq drops a line's trailing '\r' only once the record holds more than one character: an otherwise
+      // empty CRLF line at the start of a record leaves a one-character sequence "\r" (kseq.h:146)
+      if (n == 0 && cr_ && seq.size() == start) seq += '\r';
       consume();
     }
     if (ln[0] != '+') return true;  // FASTA: next header stays in the buffer
     (void)fastq;
     consume();  // the '+' line
     size_t q = 0;
-    const size_t want = seq.size() - start;
-    while (q < want) {  // quality lines (may start with '@' or '+'): by length
-      if (!line(ln, n)) return true;
+    const size_t want = seq.size() - start, qstart = qual ? qual->size() : 0;
+    // kseq_read returns an error -- which ends the FILE for ReadFiles::Next -- when the stream stops inside
+    // the '+' line, when the quality string is cut short, or when it comes out longer than the sequence
+    // (kseq.h:212-218); the record is dropped in all three cases
+    bool broken = !nl_;
+    while (!broken && q < want) {  // quality lines (may start with '@' or '+'): by length
+      if (!line(ln, n)) {
+        broken = true;
+        break;
+      }
       if (qual) qual->append(ln, n);
       q += n;
+      if (n == 0 && cr_ && q == 0) {  // the same rule for the quality string
+        if (qual) *qual += '\r';
+        ++q;
+      }
+    }
+    if (broken || q != want) {
+      seq.resize(start);
+      if (qual) qual->resize(qstart);
+      dead_ = true;
+      return false;
     }
     return true;
   }
@@ -177,7 +199,9 @@ class SeqReader {
         p = buf_.data() + pos_;
         n = (size_t)(nl - p);
         next_ = pos_ + n + 1;
-        if (n > 0 && p[n - 1] == '\r') --n;
+        nl_ = true;
+        cr_ = n > 0 && p[n - 1] == '\r';
+        if (cr_) --n;
         return true;
       }
       if (eof_) {
@@ -185,7 +209,9 @@ class SeqReader {
         p = buf_.data() + pos_;  // last line without '\n'
         n = len_ - pos_;
         next_ = len_;
-        if (n > 0 && p[n - 1] == '\r') --n;
+        nl_ = false;
+        cr_ = n > 0 && p[n - 1] == '\r';
+        if (cr_) --n;
         return true;
       }
       // refill: keep the partial line at the front
@@ -204,6 +230,9 @@ class SeqReader {
   std::string buf_;
   size_t len_ = 0, pos_ = 0, next_ = 0;
   bool eof_ = false;
+  bool cr_ = false;  // the line peek_line() returned last ended in "\r\n"
+  bool nl_ = true;   // ... and had a line terminator at all (false: the stream ended inside it)
+  bool dead_ = false;  // a broken FASTQ record ended this file
 };
 
 // ReadFiles::RemoveReadIdSuffix (ReadFiles.hpp:82-90)
@@ -1079,7 +1108,7 @@ int main(int argc, char *argv[]) {
       while ((long)bt->n < batchReads && bt->seq1.size() < maxBases &&
              (bt->n == 0 || (bt->n + 1) * (maxLen / 24 + 1) <= slotBudget)) {
         name.clear();
-        const int got = reads.step(name, bt->seq1, keepReads ? &bt->qual1 : nullptr, &comment1);
+        const int got = reads.step(name, bt->seq1, keepReads ? &bt->qual1 : nullptr, (hasBarcode || hasUmi) ? &comment1 : nullptr);
         if (got == ReadSource::FILE_END) {  // sample sheet: the batch ends with the file
           bt->fileEnd = true;
           break;

@@ -1,4 +1,4 @@
-"""A few rounds of the two differential fuzzers (tools/fuzz_hostsim.py, tools/fuzz_oracle_vs_reference.py):
+"""A few rounds of the differential fuzzers (tools/fuzz_hostsim.py, tools/fuzz_oracle_vs_reference.py, tools/fuzz_cli_parser.py):
 generated reads with substitutions, indels, N runs, low-complexity inserts, chimeras, lowercase and
 random options.  The long runs are done by hand (DESIGN.md section 1c records them)."""
 import os
@@ -26,3 +26,9 @@ def test_oracle_against_reference_binary():
     if not os.path.exists(os.path.join(REF_DIR, "centrifuger")):
         pytest.skip("oracle/_ref/centrifuger not built")
     _run("fuzz_oracle_vs_reference.py", 8, 202)
+
+
+def test_cli_parser_against_reference_binary():
+    if not os.path.exists(os.path.join(REF_DIR, "centrifuger")):
+        pytest.skip("oracle/_ref/centrifuger not built")
+    _run("fuzz_cli_parser.py", 25, 404)
