@@ -32,3 +32,9 @@ def test_cli_parser_against_reference_binary():
     if not os.path.exists(os.path.join(REF_DIR, "centrifuger")):
         pytest.skip("oracle/_ref/centrifuger not built")
     _run("fuzz_cli_parser.py", 25, 404)
+
+
+def test_read_format_and_barcodes_against_reference_binary():
+    if not os.path.exists(os.path.join(REF_DIR, "centrifuger")):
+        pytest.skip("oracle/_ref/centrifuger not built")
+    _run("fuzz_read_format.py", 20, 505)
