@@ -143,7 +143,9 @@ int cfr_submit_batch_masked(cfr_handle *h, const cfr_read_batch *in, cfr_result 
  *                               not reduced by rank, or the reference prints an empty string);
  *   exp_off[i]                = where read i's lists start in exp_ids (list j follows list j-1);
  *   exp_ids                   = compact taxonomy ids (print with cfr_orig_taxid), *exp_n of them.
- * exp_cap = entries exp_ids can hold; CFR_ERR_OVERFLOW (and *exp_n = the number needed) if too small. */
+ * exp_cap = entries exp_ids can hold; CFR_ERR_OVERFLOW (and *exp_n = the number needed) if too small.
+ * cfr_classify_batch cuts its input into chunks that share device slots and keeps no lists: use the
+ * streaming form or the resident form (cfr_batch_fetch_expanded) when the lists are wanted. */
 int cfr_fetch_expanded(cfr_handle *h, int ticket, uint32_t *exp_cnt, uint64_t *exp_off, uint64_t *exp_ids,
                        uint64_t exp_cap, uint64_t *exp_n);
 
