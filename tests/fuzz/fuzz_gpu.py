@@ -10,9 +10,10 @@ import shutil
 import sys
 import tempfile
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.join(ROOT, "tests", "fuzz"))
 sys.path.insert(0, os.path.join(ROOT, "tools"))
 import centrifuger_b200 as cb  # noqa: E402
 from fuzz_hostsim import make_read  # noqa: E402

@@ -11,8 +11,9 @@ import shutil
 import sys
 import tempfile
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.join(ROOT, "tests", "fuzz"))
 sys.path.insert(0, os.path.join(ROOT, "tools"))
 from hostsim_binding import HostSim, result_tuples  # noqa: E402
 from oracle_binding import Oracle  # noqa: E402

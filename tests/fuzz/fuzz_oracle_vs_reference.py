@@ -12,8 +12,9 @@ import subprocess
 import sys
 import tempfile
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.join(ROOT, "tests", "fuzz"))
 sys.path.insert(0, os.path.join(ROOT, "tools"))
 from fuzz_hostsim import make_read  # noqa: E402
 from oracle_binding import Oracle  # noqa: E402

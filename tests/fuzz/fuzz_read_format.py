@@ -14,7 +14,7 @@ import subprocess
 import sys
 import tempfile
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 REF = os.path.join(ROOT, "oracle", "_ref", "centrifuger")
 EXE = os.path.join(ROOT, "centrifuger_b200", "centrifuger-b200")
 TG = os.path.join(ROOT, "tests", "golden", "tiny")

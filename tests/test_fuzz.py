@@ -1,4 +1,4 @@
-"""A few rounds of the differential fuzzers (tools/fuzz_hostsim.py, tools/fuzz_oracle_vs_reference.py, tools/fuzz_cli_parser.py):
+"""A few rounds of the differential fuzzers (tests/fuzz/fuzz_hostsim.py, tests/fuzz/fuzz_oracle_vs_reference.py, tests/fuzz/fuzz_cli_parser.py):
 generated reads with substitutions, indels, N runs, low-complexity inserts, chimeras, lowercase and
 random options.  The long runs are done by hand (DESIGN.md section 1c records them)."""
 import os
@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _run(script, rounds, seed):
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", script), str(rounds), str(seed)],
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "fuzz", script), str(rounds), str(seed)],
                        stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=600)
     assert r.returncode == 0 and b"ok:" in r.stdout, r.stdout.decode()[-2000:]
 

@@ -483,11 +483,11 @@ def test_cli_sample_sheet(tiny_dir, manifest, tmp_path):
 
 
 def test_gpu_fuzz_rounds():
-    """a few rounds of tools/fuzz_gpu.py: generated reads, random options, kernel variants, arena and chunk sizes"""
+    """a few rounds of tests/fuzz/fuzz_gpu.py: generated reads, random options, kernel variants, arena and chunk sizes"""
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    r = subprocess.run([sys.executable, os.path.join(root, "tools", "fuzz_gpu.py"), "6", "303"],
+    r = subprocess.run([sys.executable, os.path.join(root, "tests", "fuzz", "fuzz_gpu.py"), "6", "303"],
                        stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=600)
     assert r.returncode == 0 and b"ok:" in r.stdout, r.stdout.decode()[-3000:]
 

@@ -12,6 +12,6 @@ grep -E "passed|failed|rror" gpurun_out/pytest_gpu.log | tail -2
 wait $PID
 for spec in "c2 ${1:-1000000}" "m700pe ${2:-500000}"; do
   F=gpurun_out/cli_$(echo $spec | tr ' ' '_')
-  timeout 900 python tools/cli_bench.py $spec > $F.json 2> $F.err
+  timeout 900 python tests/cli_bench.py $spec > $F.json 2> $F.err
   cat $F.json
 done

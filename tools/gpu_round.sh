@@ -51,10 +51,10 @@ if [ "$1" = "c3" ]; then
 fi
 # ---- drop-in CLI: FASTQ -> TSV wall time and byte equality with the reference binary at scale
 for spec in "c2 500000" "m700pe 100000"; do
-  timeout 900 python tools/cli_bench.py $spec > gpurun_out/cli_$(echo $spec | tr ' ' '_').json 2> gpurun_out/cli_$(echo $spec | tr ' ' '_').err
+  timeout 900 python tests/cli_bench.py $spec > gpurun_out/cli_$(echo $spec | tr ' ' '_').json 2> gpurun_out/cli_$(echo $spec | tr ' ' '_').err
   cat gpurun_out/cli_$(echo $spec | tr ' ' '_').json
 done
 if [ "$1" = "c3" ]; then
-  timeout 1200 python tools/cli_bench.py c3 100000 > gpurun_out/cli_c3_100000.json 2> gpurun_out/cli_c3_100000.err
+  timeout 1200 python tests/cli_bench.py c3 100000 > gpurun_out/cli_c3_100000.json 2> gpurun_out/cli_c3_100000.err
   cat gpurun_out/cli_c3_100000.json
 fi
