@@ -94,585 +94,9 @@ static struct option long_options[] = {
     {"barcode-translate", required_argument, 0, ARGV_BC_TRANSLATE},
     {"sample-sheet", required_argument, 0, ARGV_SAMPLE_SHEET},
     {(char *)0, 0, 0, 0}};
-
-// Utils::PrintLog (compactds/Utils.hpp:369-381)
-static void PrintLog(const char *fmt, ...) {
-  va_list args;
-  va_start(args, fmt);
-  char buffer[1000];
-  vsnprintf(buffer, sizeof(buffer), fmt, args);
-  va_end(args);
-  time_t mytime = time(NULL);
-  struct tm *localT = localtime(&mytime);
-  char stime[500];
-  strftime(stime, sizeof(stime), "%c", localT);
-  fprintf(stderr, "[%s] %s\n", stime, buffer);
-}
-
-// FASTA/FASTQ reader with kseq.h semantics (name = first token after '>'/'@', sequence
-// lines concatenated, FASTQ quality skipped by length; '-' = stdin; gz ok), block-buffered
-// with memchr line splitting.
-class SeqReader {
- public:
-  bool open(const std::string &path) {
-    fp_ = path == "-" ? gzdopen(fileno(stdin), "r") : gzopen(path.c_str(), "r");
-    if (!fp_) return false;
-    gzbuffer(fp_, 1 << 20);
-    buf_.resize(4 << 20);
-    len_ = pos_ = 0;
-    eof_ = false;
-    dead_ = false;
-    return true;
-  }
-  void close() {
-    if (fp_) gzclose(fp_);
-    fp_ = nullptr;
-  }
-  // appends the record's sequence to `seq` (and, for FASTQ records, its quality string to `qual` when
-  // given: a FASTA record appends nothing there); returns false at end of file
-  bool next(std::string &name, std::string &seq, std::string *qual = nullptr, std::string *comment = nullptr) {
-    const char *ln;
-    size_t n;
-    if (dead_) return false;
-    // header line
-    for (;;) {
-      if (!line(ln, n)) return false;
-      if (n > 0 && (ln[0] == '>' || ln[0] == '@')) break;
-    }
-    const bool fastq = ln[0] == '@';
-    size_t e = 1;
-    while (e < n && ln[e] != ' ' && ln[e] != '\t') ++e;
-    name.assign(ln + 1, e - 1);
-    if (comment) comment->assign(e < n ? ln + e + 1 : ln + n, e < n ? n - e - 1 : 0);  // kseq: the rest of the line
-    // sequence lines: until a line starting with '+' (FASTQ), '>' or '@' (next record)
-    const size_t start = seq.size();
-    for (;;) {
-      if (!peek_line(ln, n)) return true;  // EOF ends the record
-      if (n > 0 && (ln[0] == '+' || ln[0] == '>' || ln[0] == '@')) break;
-      seq.append(ln, n);
-      // kseq drops a line's trailing '\r' only once the record holds more than one character: an otherwise
-      // empty CRLF line at the start of a record leaves a one-character sequence "\r" (kseq.h:146)
-      if (n == 0 && cr_ && seq.size() == start) seq += '\r';
-      consume();
-    }
-    if (ln[0] != '+') return true;  // FASTA: next header stays in the buffer
-    (void)fastq;
-    consume();  // the '+' line
-    size_t q = 0;
-    const size_t want = seq.size() - start, qstart = qual ? qual->size() : 0;
-    // kseq_read returns an error -- which ends the FILE for ReadFiles::Next -- when the stream stops inside
-    // the '+' line, when the quality string is cut short, or when it comes out longer than the sequence
-    // (kseq.h:212-218); the record is dropped in all three cases
-    bool broken = !nl_;
-    while (!broken && q < want) {  // quality lines (may start with '@' or '+'): by length
-      if (!line(ln, n)) {
-        broken = true;
-        break;
-      }
-      if (qual) qual->append(ln, n);
-      q += n;
-      if (n == 0 && cr_ && q == 0) {  // the same rule for the quality string
-        if (qual) *qual += '\r';
-        ++q;
-      }
-    }
-    if (broken || q != want) {
-      seq.resize(start);
-      if (qual) qual->resize(qstart);
-      dead_ = true;
-      return false;
-    }
-    return true;
-  }
-
- private:
-  // returns the next line without its terminator ('\r' stripped) and consumes it
-  bool line(const char *&p, size_t &n) {
-    if (!peek_line(p, n)) return false;
-    consume();
-    return true;
-  }
-  bool peek_line(const char *&p, size_t &n) {
-    for (;;) {
-      const char *nl = (const char *)memchr(buf_.data() + pos_, '\n', len_ - pos_);
-      if (nl) {
-        p = buf_.data() + pos_;
-        n = (size_t)(nl - p);
-        next_ = pos_ + n + 1;
-        nl_ = true;
-        cr_ = n > 0 && p[n - 1] == '\r';
-        if (cr_) --n;
-        return true;
-      }
-      if (eof_) {
-        if (pos_ >= len_) return false;
-        p = buf_.data() + pos_;  // last line without '\n'
-        n = len_ - pos_;
-        next_ = len_;
-        nl_ = false;
-        cr_ = n > 0 && p[n - 1] == '\r';
-        if (cr_) --n;
-        return true;
-      }
-      // refill: keep the partial line at the front
-      if (pos_ > 0) {
-        memmove(&buf_[0], buf_.data() + pos_, len_ - pos_);
-        len_ -= pos_;
-        pos_ = 0;
-      }
-      if (len_ == buf_.size()) buf_.resize(buf_.size() * 2);
-      const int got = gzread(fp_, &buf_[len_], (unsigned)std::min<size_t>(buf_.size() - len_, 1u << 30));
-      if (got <= 0) eof_ = true; else len_ += (size_t)got;
-    }
-  }
-  void consume() { pos_ = next_; }
-  gzFile fp_ = nullptr;
-  std::string buf_;
-  size_t len_ = 0, pos_ = 0, next_ = 0;
-  bool eof_ = false;
-  bool cr_ = false;  // the line peek_line() returned last ended in "\r\n"
-  bool nl_ = true;   // ... and had a line terminator at all (false: the stream ended inside it)
-  bool dead_ = false;  // a broken FASTQ record ended this file
-};
-
-// ReadFiles::RemoveReadIdSuffix (ReadFiles.hpp:82-90)
-static void RemoveReadIdSuffix(std::string &id) {
-  const size_t len = id.size();
-  if (len >= 2 && (id[len - 1] == '1' || id[len - 1] == '2') && id[len - 2] == '/') id.resize(len - 2);
-}
-
-struct ReadSource {  // a list of files read back to back (ReadFiles::AddReadFile)
-  std::vector<std::string> files;
-  size_t cur = 0;
-  bool opened = false;
-  bool markFileEnds = false;  // --sample-sheet: every file end is reported (ReadFiles::SetSpecialReadToMarkFileEnd)
-  SeqReader rd;
-  // a name with '*' stands for the files it matches, in glob(3) order (ReadFiles.hpp:135-172)
-  void add(const char *file) {
-    if (!strchr(file, '*')) {
-      files.push_back(file);
-      return;
-    }
-    glob_t g;
-    memset(&g, 0, sizeof(g));
-    const int rc = glob(file, GLOB_TILDE, NULL, &g);
-    if (rc != 0) fprintf(stderr, "glob() failed with return value %d.\n", rc);
-    for (size_t i = 0; rc == 0 && i < g.gl_pathc; ++i) files.push_back(g.gl_pathv[i]);
-    globfree(&g);
-  }
-  enum { END = 0, RECORD = 1, FILE_END = 2 };
-  // RECORD, END (no file left) or -- with markFileEnds -- FILE_END once per file, the last one included
-  int step(std::string &name, std::string &seq, std::string *qual = nullptr, std::string *comment = nullptr) {
-    for (;;) {
-      if (!opened) {
-        if (cur >= files.size()) return END;
-        if (!rd.open(files[cur])) {
-          PrintLog("ERROR: cannot open read file %s", files[cur].c_str());
-          exit(EXIT_FAILURE);
-        }
-        opened = true;
-      }
-      if (rd.next(name, seq, qual, comment)) return RECORD;
-      rd.close();
-      opened = false;
-      ++cur;
-      if (markFileEnds) return FILE_END;
-    }
-  }
-  bool next(std::string &name, std::string &seq, std::string *qual = nullptr, std::string *comment = nullptr) {
-    int r;
-    while ((r = step(name, seq, qual, comment)) == FILE_END) {
-    }
-    return r == RECORD;
-  }
-};
-
-// --read-format (ReadFormatter.hpp): which stretches of read 1 / read 2 / the barcode record / the UMI
-// record are used.  A description is a ',' or ';' separated list of  <r1|r2|bc|um>:START:END[:STRAND]
-// (0-based, END inclusive, negative = counted from the end, STRAND '-' reverse-complements the
-// assembled stretch) or  <bc|um>:hd:FIELD:START:END[:STRAND]  for a stretch of the header comment
-// (FIELD = number of the whitespace separated field, or a prefix to search for).  Stretches of one
-// category are concatenated in the order given (ReadFormatter.hpp:275-391).
-struct ReadFormat {
-  enum { R1 = 0, R2 = 1, BARCODE = 2, UMI = 3, NCAT = 4 };
-  struct Seg {
-    int start = 0, end = -1, strand = 1;
-    bool inComment = false;
-    int field = -1;
-    std::string prefix;
-  };
-  std::vector<Seg> segs[NCAT];
-
-  // one item of the description (ReadFormatter.hpp:50-139)
-  bool ParseItem(const char *s, int len) {
-    if (len < 3 || s[2] != ':') return false;
-    int cat;
-    if (s[0] == 'r' && s[1] == '1') cat = R1;
-    else if (s[0] == 'r' && s[1] == '2') cat = R2;
-    else if (s[0] == 'b' && s[1] == 'c') cat = BARCODE;
-    else if (s[0] == 'u' && s[1] == 'm') cat = UMI;
-    else return false;
-    Seg seg;
-    int at = 3;
-    if (len >= 6 && s[3] == 'h' && s[4] == 'd' && s[5] == ':') {
-      seg.inComment = true;
-      int e = 6;
-      while (e < len && s[e] != ':') ++e;
-      const std::string tok(s + 6, (size_t)(e - 6));
-      const bool digits = tok.find_first_not_of("0123456789") == std::string::npos;
-      if (digits) seg.field = atoi(tok.c_str());
-      else seg.prefix = tok;
-      at = e + 1;
-    }
-    int part = 0;
-    std::string tok;
-    for (int i = at; i <= len; ++i) {
-      if (i >= len || s[i] == ':') {
-        if (part == 0) seg.start = atoi(tok.c_str());
-        else if (part == 1) seg.end = atoi(tok.c_str());
-        else seg.strand = (!tok.empty() && tok[0] == '+') ? 1 : -1;
-        tok.clear();
-        if (i < len && s[i] == ':') ++part;
-      } else {
-        tok += s[i];
-      }
-    }
-    if (part >= 3 || part < 1) return false;
-    segs[cat].push_back(seg);
-    return true;
-  }
-  void Init(const char *desc) {  // ReadFormatter.hpp:198-225
-    for (int i = 0; desc[i];) {
-      int j = i;
-      while (desc[j] && desc[j] != ';' && desc[j] != ',') ++j;
-      if (!ParseItem(desc + i, j - i)) {
-        fprintf(stderr, "Format description error in %s\n", desc);
-        exit(1);
-      }
-      i = desc[j] ? j + 1 : j;
-    }
-    for (int c = 0; c < NCAT; ++c) {  // ReadFormatter::AreSegmentsSorted (:140-149); an END of -1 always passes
-      inOrder[c] = true;
-      for (size_t q = 1; q < segs[c].size(); ++q)
-        if (segs[c][q].start <= segs[c][q - 1].end) inOrder[c] = false;
-    }
-  }
-  bool inOrder[NCAT] = {true, true, true, true};
-  bool InComment(int cat) const { return !segs[cat].empty() && segs[cat][0].inComment; }
-  bool NeedExtract(int cat) const {  // ReadFormatter.hpp:259-273
-    if (segs[cat].empty()) return false;
-    if (segs[cat].size() == 1) {
-      const Seg &g = segs[cat][0];
-      if (g.start == 0 && g.end == -1 && g.strand == 1 && !g.inComment) return false;
-    }
-    return true;
-  }
-  // the stretches of `in` (a sequence, a quality string or a header comment); complement = false for qualities.
-  // overwrite = true restates ReadFormatter::InplaceExtractSeqAndQual for stretches it considers in order:
-  // the reference then assembles the result inside the record itself, so a stretch that lies in front of an
-  // earlier one (possible when the earlier one ends at -1) is read after it was overwritten.
-  std::string Extract(const std::string &given, int cat, bool complement, bool overwrite = false) const {
-    if (!NeedExtract(cat)) return given;
-    const int len = (int)given.size();
-    std::string in = given, out;
-    int strand = 1;
-    for (const Seg &g : segs[cat]) {
-      int start = g.start, end = g.end, lenk = len;
-      if (InComment(cat)) {  // find the field, then count inside it (ReadFormatter.hpp:318-366)
-        int fstart = 0, fend = 0;
-        if (g.field >= 0) {
-          int f = 0;
-          for (int j = 0; j <= len; ++j) {
-            const char ch = j < len ? in[j] : '\0';
-            if (ch == ' ' || ch == '\t' || ch == '\0') {
-              ++f;
-              if (f == g.field) fstart = j + 1;
-              else if (f == g.field + 1) {
-                fend = j - 1;
-                break;
-              }
-            }
-          }
-          if (f <= g.field) {
-            fstart = len;
-            fend = len - 1;
-          }
-        } else {
-          const size_t p = in.find(g.prefix);
-          if (p != std::string::npos) {
-            fstart = (int)p;
-            size_t q = p;
-            while (q < in.size() && in[q] != ' ' && in[q] != '\t') ++q;
-            fend = (int)q - 1;
-          } else {
-            fstart = len;
-            fend = len - 1;
-          }
-        }
-        if (start >= 0) start += fstart;
-        if (end >= 0) end += fstart;
-        lenk = fend + 1;
-      }
-      if (start < 0) start = lenk + start;
-      if (end >= lenk) end = lenk - 1;
-      else if (end < 0) end = lenk + end;
-      if (start < 0) start = 0;  // the reference would read in front of its buffer here
-      for (int j = start; j <= end && j < len; ++j) {
-        out += in[j];
-        if (overwrite && out.size() <= in.size()) in[out.size() - 1] = in[j];
-      }
-      if (g.strand == -1) strand = -1;
-    }
-    if (strand == -1) {
-      std::reverse(out.begin(), out.end());
-      if (complement)
-        for (char &c : out) c = c == 'A' ? 'T' : c == 'C' ? 'G' : c == 'G' ? 'C' : c == 'T' ? 'A' : 'N';
-    }
-    return out;
-  }
-  // replaces the record just appended to `buf` (from `from` on) by its stretches
-  void ExtractTail(std::string &buf, size_t from, int cat, bool complement) const {
-    if (!NeedExtract(cat)) return;
-    const std::string rec = buf.substr(from);
-    buf.resize(from);
-    buf += Extract(rec, cat, complement, inOrder[cat]);
-  }
-};
-
-// --barcode-whitelist (BarcodeCorrector.hpp): a barcode that is not on the list is replaced by the listed
-// barcode one substitution away that was seen most often among the first two million barcodes (ties: the
-// one whose changed base has the lowest quality, then the first in position / base order); none -> "N".
-// The list lives in a 4-ary trie like the reference's, because its look-up also "finds" a proper prefix
-// of a listed barcode (with whatever count that inner node has), and that decides what gets corrected.
-struct BarcodeWhitelist {
-  struct Node {
-    int next[4] = {-1, -1, -1, -1};
-    int count = 0;
-  };
-  std::vector<Node> nodes;
-  int listed = 0;
-  BarcodeWhitelist() : nodes(1) {}
-  static int Code(char c) { return c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : -1; }
-  void Insert(const std::string &s, int weight) {  // Trie::Insert (:69-94)
-    for (char c : s)
-      if (Code(c) < 0) return;
-    int p = 0;
-    bool grew = false;
-    for (char c : s) {
-      const int t = Code(c);
-      if (nodes[p].next[t] < 0) {
-        nodes[p].next[t] = (int)nodes.size();
-        nodes.push_back(Node());
-        grew = true;
-      }
-      p = nodes[p].next[t];
-    }
-    nodes[p].count += weight;
-    if (grew) ++listed;
-  }
-  int Find(const std::string &s, int weight) {  // Trie::SearchAndUpdate (:96-113): count after the update, -1 = absent
-    for (char c : s)
-      if (Code(c) < 0) return -1;
-    int p = 0;
-    for (char c : s) {
-      p = nodes[p].next[Code(c)];
-      if (p < 0) return -1;
-    }
-    nodes[p].count += weight;
-    return nodes[p].count;
-  }
-  bool Load(const char *file) {  // SetWhitelist (:123-143)
-    gzFile fp = gzopen(file, "r");
-    if (!fp) return false;
-    char buffer[256];
-    while (gzgets(fp, buffer, sizeof(buffer)) != NULL) {
-      size_t len = strlen(buffer);
-      if (len && buffer[len - 1] == '\n') buffer[--len] = 0;
-      Insert(buffer, 1);
-    }
-    gzclose(fp);
-    return true;
-  }
-  // Correct (:164-233): -1 could not correct, 0 listed, 1 corrected in place; qual may be empty
-  int Correct(std::string &bc, const std::string &qual) {
-    if (Find(bc, 0) != -1) return 0;
-    int bestCnt = -1, bestPos = -1, bestBase = -1, bestLowQual = 255;
-    std::string probe = bc;
-    for (size_t i = 0; i < bc.size(); ++i)
-      for (int j = 0; j < 4; ++j) {
-        if ("ACGT"[j] == bc[i]) continue;
-        probe[i] = "ACGT"[j];
-        const int cnt = Find(probe, 0);
-        probe[i] = bc[i];
-        if (cnt == -1) continue;
-        const bool haveQual = i < qual.size();
-        if (cnt > bestCnt) {
-          bestCnt = cnt;
-          bestPos = (int)i;
-          bestBase = j;
-          if (!qual.empty()) bestLowQual = haveQual ? qual[i] : 0;
-        } else if (cnt == bestCnt && !qual.empty() && (haveQual ? qual[i] : 0) < bestLowQual) {
-          bestLowQual = haveQual ? qual[i] : 0;
-          bestPos = (int)i;
-          bestBase = j;
-        }
-      }
-    if (bestPos < 0) return -1;
-    bc[(size_t)bestPos] = "ACGT"[bestBase];
-    return 1;
-  }
-};
-
-// --barcode-translate (BarcodeTranslator.hpp): lines "<to><sep><from>"; a barcode is cut into pieces as long
-// as the last line's <from>, each piece is replaced, the results are joined with '-'
-struct BarcodeTranslation {
-  std::unordered_map<std::string, std::string> table;  // from -> to, a later line replaces an earlier one
-  int fromLen = -1;
-  bool set = false;
-  bool Load(const char *file) {
-    gzFile fp = gzopen(file, "r");
-    if (!fp) return false;
-    set = true;
-    char line[512];
-    while (gzgets(fp, line, sizeof(line)) != NULL) {
-      size_t len = strlen(line);
-      if (len && line[len - 1] == '\n') line[--len] = 0;
-      size_t i = 0;
-      while (i < len && line[i] != ',' && line[i] != '\t' && line[i] != ' ') ++i;
-      const std::string to(line, i), from(i < len ? line + i + 1 : "");
-      fromLen = i < len ? (int)(len - i - 1) : -1;
-      table[from] = to;
-    }
-    gzclose(fp);
-    return true;
-  }
-  std::string Translate(const std::string &bc) const {
-    std::string ret;
-    if (fromLen <= 0) return ret;
-    for (size_t i = 0; i < bc.size() / (size_t)fromLen; ++i) {
-      const std::string piece = bc.substr(i * (size_t)fromLen, (size_t)fromLen);
-      const auto hit = table.find(piece);
-      const std::string *to = hit == table.end() ? nullptr : &hit->second;
-      if (!to) {
-        fprintf(stderr, "Barcode %s does not exist in the translation table.\n", piece.c_str());
-        exit(-1);
-      }
-      ret += i ? "-" + *to : *to;
-    }
-    return ret;
-  }
-};
-
-// --merge-readpair (ReadPairMerger.hpp; applied in CentrifugerClass.cpp:271-272): before a pair is
-// classified, mate 2 is reverse-complemented and laid over mate 1.  If the fragment was shorter than a
-// read ("read-through": mate 1 starts inside rc(mate 2)) the pair is trimmed to the fragment; if the
-// mates overlap at their ends they are joined; either way the result is classified as ONE read
-// (Query(rm, NULL), :323-333).  Same decisions as the reference, bit for bit (tests/test_cli_ingest.py
-// runs this against the unmodified reference header):
-//   * placing `b` at offset j of `a` is accepted when the matches can still reach
-//     int((|a| - j) * t), t = 0.95 below 50 overlapping bases, rising linearly to 0.85 at 100 and above;
-//   * exactly one offset j < |a| - minOverlap may be accepted, minOverlap = min(31, (|a| + |b|) / 10);
-//   * an end overlap of at most 2 * minOverlap bases is refused when `b` starts with a tandem repeat
-//     of period <= overlap / 2 (every complete repeat unit inside the overlap equals the first).
-struct PairMerger {
-  struct Placement {
-    int offset = -1, length = -1;  // where b sits on a, and how many bases were compared
-  };
-
-  static double RequiredIdentity(int span) {
-    if (span >= 100) return 0.85;
-    if (span >= 50) return 0.85 + (span - 50) / 50.0 * 0.1;
-    return 0.95;
-  }
-
-  // true when b laid at a[j..] stays above the identity bound; `compared` = bases looked at
-  static bool Fits(const char *a, int alen, const char *b, int blen, int j, int &compared) {
-    const int span = alen - j;
-    const int need = int(span * RequiredIdentity(span));
-    int same = 0, k = 0;
-    for (; j + k < alen && k < blen; ++k) {
-      same += a[j + k] == b[k];
-      if (same + (span - k - 1) < need) return false;  // even a perfect rest cannot reach the bound
-    }
-    compared = k;
-    return true;
-  }
-
-  static bool StartsWithTandem(const char *b, int n) {
-    for (int period = 1; period <= n / 2; ++period) {
-      const int whole = (n / period) * period;  // only complete repeat units are compared
-      int k = period;
-      while (k < whole && b[k] == b[k % period]) ++k;
-      if (k == whole) return true;
-    }
-    return false;
-  }
-
-  static Placement UniquePlacement(const char *a, int alen, const char *b, int blen, int minOverlap, bool refuseTandem) {
-    Placement found;
-    int accepted = 0;
-    for (int j = 0; j < alen - minOverlap; ++j) {
-      int compared;
-      if (Fits(a, alen, b, blen, j, compared)) {
-        ++accepted;
-        found.offset = j;
-        found.length = compared;
-      }
-    }
-    if (accepted != 1) return Placement();
-    if (refuseTandem && found.length <= 2 * minOverlap && StartsWithTandem(b, found.length)) return Placement();
-    return found;
-  }
-
-  static char Complement(char c) { return c == 'A' ? 'T' : c == 'C' ? 'G' : c == 'G' ? 'C' : c == 'T' ? 'A' : 'N'; }
-
-  // 0 = left as a pair, 1 = joined at an end overlap, 2 = trimmed to a read-through fragment.
-  // q1 / q2 may be NULL (FASTA input); rm / qm receive the single read and its qualities.
-  static int Merge(const char *r1, const char *q1, int len1, const char *r2, const char *q2, int len2, std::string &rm,
-                   std::string &qm) {
-    rm.clear();
-    qm.clear();
-    std::string m2(len2, 'N'), m2q;  // mate 2 on mate 1's strand
-    for (int i = 0; i < len2; ++i) m2[i] = Complement(r2[len2 - 1 - i]);
-    if (q2) m2q.assign(std::reverse_iterator<const char *>(q2 + len2), std::reverse_iterator<const char *>(q2));
-    const int minOverlap = std::min(31, (len1 + len2) / 10);
-
-    // read-through: mate 1 begins somewhere inside m2; the fragment is what they share
-    Placement p = UniquePlacement(m2.data(), len2, r1, len1, minOverlap, false);
-    if (p.length >= 0) {
-      rm.assign(r1, p.length);
-      if (q1) {
-        qm.assign(q1, p.length);
-        for (int i = 0; i < p.length; ++i)
-          if (m2q[i + p.offset] > q1[i] || rm[i] == 'N') {  // the better-called base wins
-            rm[i] = m2[i + p.offset];
-            qm[i] = m2q[i + p.offset];
-          }
-      }
-      return 2;
-    }
-
-    // end overlap: m2 begins inside mate 1
-    p = UniquePlacement(r1, len1, m2.data(), len2, minOverlap, true);
-    if (p.length < 0) return 0;
-    const int total = p.offset + len2;  // (mate 2 may end before mate 1 does)
-    rm.assign(total, 'N');
-    rm.replace(p.offset, len2, m2);
-    if (q2) {
-      qm.assign(total, '!');
-      qm.replace(p.offset, len2, m2q);
-    }
-    for (int i = 0; i < std::min(len1, total); ++i) {
-      // mate 1 keeps its bases in front of the overlap, where its call is at most 14 below mate 2's, and
-      // where mate 2 has no call
-      if (i < p.offset || (q1 != NULL && q2 != NULL && q1[i] >= qm[i] - 14) || rm[i] == 'N') {
-        rm[i] = r1[i];
-        if (q1) qm[i] = q1[i];
-      }
-    }
-    return 1;
-  }
-};
+#include "cfr_cli_reads.hpp"   // PrintLog, SeqReader, ReadSource: FASTA/FASTQ ingest
+#include "cfr_cli_format.hpp"  // ReadFormat, BarcodeWhitelist, BarcodeTranslation
+#include "cfr_cli_merge.hpp"   // PairMerger
 
 // One batch travelling through the ingest -> classify -> output pipeline.
 struct Batch {
