@@ -276,3 +276,21 @@ def test_rank_access_locate_primitives(tiny_dir, layout):
             assert hs.locate(p) == o.locate(p)[0]
         hs.close()
         o.close()
+
+
+def test_truncated_index_files_are_refused(tiny_dir, tmp_path):
+    """the product's .cfr parser (cfr_format.cpp, shared with the library) refuses cut-off files instead of
+    reading past their end"""
+    import shutil
+    rng = random.Random(3)
+    for which in (".1.cfr", ".2.cfr"):
+        size = os.path.getsize(os.path.join(tiny_dir, "idx" + which))
+        # (the last byte of .1.cfr alone may be missing: indexes written before the end-marker flag existed, FMIndex.hpp:178-181)
+        for cut in [0, 7, 40, size - 9] + [rng.randrange(1, size - 1) for _ in range(8)]:
+            for ext in (".1.cfr", ".2.cfr", ".3.cfr", ".4.cfr"):
+                shutil.copyfile(os.path.join(tiny_dir, "idx" + ext), str(tmp_path / ("t" + ext)))
+            with open(str(tmp_path / ("t" + which)), "r+b") as f:
+                f.truncate(cut)
+            with pytest.raises(RuntimeError):
+                HostSim(str(tmp_path / "t"))
+    HostSim(os.path.join(tiny_dir, "idx")).close()
