@@ -122,7 +122,10 @@ int cfr_classify_batch(cfr_handle *h, const cfr_read_batch *in, cfr_result *resu
  * batch i+1 overlaps the kernels of batch i and the download of batch i-1.  At most three batches are
  * in flight; submitting a fourth first completes the oldest one.  `in`, `results` and `ids` must stay
  * valid (and should be pinned) until cfr_wait_batch(ticket) returns.  n_reads must not exceed
- * cfr_params.max_batch_reads (default 2^20). */
+ * cfr_params.max_batch_reads (default 2^20).  The device hit tables of a batch hold
+ * n_reads x (longest read / (min_hit_len + 1)) entries per strand, so a caller whose reads differ wildly in
+ * length should cut batches by bases and keep very long reads apart (the CLI does: cfr_main.cpp, slot
+ * budget); a batch that does not fit returns CFR_ERR_NOMEM. */
 int cfr_submit_batch(cfr_handle *h, const cfr_read_batch *in, cfr_result *results, uint64_t *ids, void *stream,
                      int *ticket);
 int cfr_wait_batch(cfr_handle *h, int ticket);
