@@ -3,7 +3,7 @@
 against the oracle on generated reads over the tiny golden index -- genome fragments with
 substitutions / indels / N runs / low-complexity inserts / chimeras / lowercase, random lengths, random
 options (k, hitk, min-hitlen, dust, consider-secondary, arena size, layout, expand-taxid).
-Test infrastructure only.   usage: fuzz_hostsim.py [rounds] [seed]"""
+Test infrastructure only.   usage: fuzz_hostsim.py [rounds] [seed] [tiny|small]"""
 import gzip
 import os
 import random
@@ -63,7 +63,8 @@ def main():
     rng = random.Random(seed)
     import gen_data
     import make_data
-    gs, _, _ = gen_data.make_genomes(seed=1, **make_data.DATASETS["tiny"]["genomes"])
+    dataset = sys.argv[3] if len(sys.argv) > 3 else "tiny"  # "small": data/small (10 Mbp, 100 sequences; make_data builds it)
+    gs, _, _ = gen_data.make_genomes(seed=1, **make_data.DATASETS[dataset]["genomes"])
     genomes = [gen_data.ACGT[g[2]].tobytes() for g in gs]
     d = tempfile.mkdtemp(prefix="cfr_fuzz_")
     tg = os.path.join(ROOT, "tests", "golden", "tiny")
@@ -71,9 +72,12 @@ def main():
         if f.endswith(".cfr.gz"):
             with gzip.open(os.path.join(tg, f), "rb") as fi, open(os.path.join(d, f[:-3]), "wb") as fo:
                 shutil.copyfileobj(fi, fo)
+    if dataset != "tiny":
+        big = make_data.ensure(dataset, log=lambda *a: None)
+        assert big, "data/%s is not available" % dataset
     total = 0
     for it in range(rounds):
-        variant = rng.choice(["idx", "idx", "idx_b1", "idx_b8", "idx_off3"])
+        variant = rng.choice(["idx", "idx", "idx_b1", "idx_b8", "idx_off3"]) if dataset == "tiny" else "idx"
         kw = dict(k=rng.choice([1, 1, 2, 3, 5]), hitk_factor=rng.choice([40, 40, 2, 0, 1]),
                   min_hit_len=rng.choice([0, 0, 16, 20, 30]), dust=rng.random() < 0.7)
         if rng.random() < 0.4:
@@ -88,7 +92,7 @@ def main():
         if rng.random() < 0.2:
             r1[rng.randrange(n)] = b""
         arena = rng.choice([0, 0, 0, 500, 2000])
-        idx = os.path.join(d, variant)
+        idx = os.path.join(d if dataset == "tiny" else big, variant)
         # the load-time tables and the SDUST screen of the product, as hostsim exposes them
         for key, choices in (("HOSTSIM_WIDE_LOOKUP", [None, None, "7", "9"]), ("HOSTSIM_DENSE_LOCATE", [None, "0", "1", "2", "3"]),
                              ("HOSTSIM_NO_DUST_SCREEN", [None, None, "1"])):

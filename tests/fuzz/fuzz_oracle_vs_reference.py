@@ -3,7 +3,7 @@
 the UNMODIFIED reference binary (oracle/_ref/centrifuger) and by the oracle with the same random
 options (-k, --hitk-factor, --min-hitlen, --no-dust, --consider-secondary, --expand-taxid); the two
 TSVs must be byte-identical.  Build container only (needs oracle/_ref).  Test infrastructure only.
-usage: fuzz_oracle_vs_reference.py [rounds] [seed]"""
+usage: fuzz_oracle_vs_reference.py [rounds] [seed] [tiny|small]"""
 import gzip
 import os
 import random
@@ -28,7 +28,8 @@ def main():
     rng = random.Random(seed)
     import gen_data
     import make_data
-    gs, _, _ = gen_data.make_genomes(seed=1, **make_data.DATASETS["tiny"]["genomes"])
+    dataset = sys.argv[3] if len(sys.argv) > 3 else "tiny"  # "small": data/small (10 Mbp, 100 sequences; make_data builds it)
+    gs, _, _ = gen_data.make_genomes(seed=1, **make_data.DATASETS[dataset]["genomes"])
     genomes = [gen_data.ACGT[g[2]].tobytes() for g in gs]
     d = tempfile.mkdtemp(prefix="cfr_fuzz_ref_")
     tg = os.path.join(ROOT, "tests", "golden", "tiny")
@@ -36,9 +37,12 @@ def main():
         if f.endswith(".cfr.gz"):
             with gzip.open(os.path.join(tg, f), "rb") as fi, open(os.path.join(d, f[:-3]), "wb") as fo:
                 shutil.copyfileobj(fi, fo)
+    if dataset != "tiny":
+        big = make_data.ensure(dataset, log=lambda *a: None)
+        assert big, "data/%s is not available" % dataset
     total = 0
     for it in range(rounds):
-        variant = rng.choice(["idx", "idx", "idx_b1", "idx_b8", "idx_off3"])
+        variant = rng.choice(["idx", "idx", "idx_b1", "idx_b8", "idx_off3"]) if dataset == "tiny" else "idx"
         kw = dict(k=rng.choice([1, 1, 2, 3, 5]), hitk_factor=rng.choice([40, 40, 2, 0, 1]),
                   min_hit_len=rng.choice([0, 0, 16, 20, 30]), dust=rng.random() < 0.7)
         args = ["-k", str(kw["k"]), "--hitk-factor", str(kw["hitk_factor"])]
@@ -63,10 +67,10 @@ def main():
             with open(os.path.join(d, "r_%d.fa" % m), "wb") as f:
                 for i, s in zip(ids, reads):
                     f.write(b">%s\n%s\n" % (i.encode(), s))
-        cmd = [REF, "-x", os.path.join(d, variant), "-t", "1"] + args + (["--expand-taxid"] if expand else [])
+        cmd = [REF, "-x", os.path.join(d if dataset == "tiny" else big, variant), "-t", "1"] + args + (["--expand-taxid"] if expand else [])
         cmd += ["-1", os.path.join(d, "r_1.fa"), "-2", os.path.join(d, "r_2.fa")] if paired else ["-u", os.path.join(d, "r_1.fa")]
         exp = subprocess.run(cmd, check=True, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL).stdout.decode()
-        o = Oracle(os.path.join(d, variant), **kw)
+        o = Oracle(os.path.join(d if dataset == "tiny" else big, variant), **kw)
         got = o.classify_tsv_expanded(ids, r1, r2) if expand else o.classify_tsv(ids, r1, r2)
         o.close()
         if got != exp:
