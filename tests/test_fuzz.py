@@ -38,3 +38,9 @@ def test_read_format_and_barcodes_against_reference_binary():
     if not os.path.exists(os.path.join(REF_DIR, "centrifuger")):
         pytest.skip("oracle/_ref/centrifuger not built")
     _run("fuzz_read_format.py", 20, 505)
+
+
+def test_merge_readpair_cli_against_reference_binary():
+    if not os.path.exists(os.path.join(REF_DIR, "centrifuger")):
+        pytest.skip("oracle/_ref/centrifuger not built")
+    _run("fuzz_merge_cli.py", 15, 606)
