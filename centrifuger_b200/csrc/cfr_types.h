@@ -139,6 +139,7 @@ struct DevResult {  // mirrors cfr_result
 struct DevCounters {
   u64 n_rank, n_access, n_search, n_locate, n_lf, n_extend, n_bases, n_reads;
   u64 error_flags;  // bit 0: taxonomy path deeper than the device cap; bit 1: --expand-taxid lists exceed the batch's list area
+                    // (sticky until cfr_reset_counters: batches overlap on the device, so a flag cannot be attributed and cleared per batch); bit 1: --expand-taxid lists exceed the batch's list area
 };
 
 enum { CFR_TAX_PATH_CAP = 128 };

@@ -34,7 +34,8 @@ typedef enum {
   CFR_ERR_UNSUPPORTED = -4,  /* protein index, non-ACGT alphabet, k <= 0 ... */
   CFR_ERR_CUDA = -5,         /* no device / CUDA runtime error */
   CFR_ERR_NOMEM = -6,
-  CFR_ERR_OVERFLOW = -7      /* a per-read device work area was exceeded */
+  CFR_ERR_OVERFLOW = -7      /* a per-read device work area was exceeded; the condition stays raised on the
+                                handle (later batches report it too) until cfr_reset_counters() */
 } cfr_status;
 
 /* In-HBM layout of the BWT.  The *.cfr files are always read unchanged. */
