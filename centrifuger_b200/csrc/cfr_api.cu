@@ -603,10 +603,6 @@ int check_device_errors(cfr_handle *h, cudaStream_t s) {
   u64 flags = 0;
   CUDA_TRY(cudaMemcpyAsync(&flags, &h->d_counters[CFR_STAGE_SCORE].error_flags, 8, cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaStreamSynchronize(s));
-  if (flags) {  // reported once, for the batch that raised it
-    CUDA_TRY(cudaMemsetAsync(&h->d_counters[CFR_STAGE_SCORE].error_flags, 0, 8, s));
-    CUDA_TRY(cudaStreamSynchronize(s));
-  }
   if (flags & 1ull) return fail(CFR_ERR_OVERFLOW, "taxonomy lineage deeper than the device path capacity");
   if (flags & 2ull) return fail(CFR_ERR_OVERFLOW, "expanded tax id lists exceed the batch's list area; raise cfr_params.arena_rows");
   return CFR_OK;
