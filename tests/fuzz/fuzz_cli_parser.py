@@ -67,6 +67,12 @@ def main():
                 f.write(text.encode())
             files.append(path)
         inputs = ["-1", files[0], "-2", files[1]] if paired else ["-u", files[0]]
+        if paired and rng.random() < 0.3:  # the same pairs as one interleaved file
+            recs = [[record(rng, i, fastq, "/%d" % (m + 1)) for m in range(2)] for i in range(n)]
+            path = os.path.join(d, "r%d_il.fq" % it)
+            with open(path, "wb") as f:
+                f.write("".join(a + b for a, b in recs).encode())
+            inputs = ["-i", path]
         outs = []
         for who, cmd in (("ref", [REF, "-x", os.path.join(d, "idx"), "-t", "1", "--min-hitlen", "5000", "--no-dust"]),
                          ("our", [EXE, "--dry-run-output", "--batch", str(rng.choice([1, 7, 1 << 20]))])):
