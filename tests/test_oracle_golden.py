@@ -148,6 +148,48 @@ def test_reduce_taxids_against_reference_header(tiny_dir):
     o.close()
 
 
+def test_dust_mask_against_reference_header():
+    """SDUST (Dustmasker.hpp) as ClassifyReads_Thread applies it: the oracle's masker against the UNMODIFIED
+    reference header (oracle/_ref/dust_ref) on 12000 generated reads rich in low-complexity stretches, N runs
+    longer than the window, lowercase and non-ACGT bytes"""
+    import random
+    import subprocess
+    from oracle_binding import REF_DIR
+    exe = os.path.join(REF_DIR, "dust_ref")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/dust_ref not built")
+    rng = random.Random(53)
+    reads = [b"", b"A", b"AC", b"ACG", b"A" * 300, b"N" * 200, b"ACGT" * 80, b"A" * 70 + b"N" * 70 + b"C" * 70]
+    for it in range(12000):
+        L = rng.choice([3, 7, 30, 63, 64, 65, 100, 128, 150, 151, 250, 300, 700, 2000]) if rng.random() < 0.8 else rng.randrange(1, 400)
+        mode = rng.random()
+        if mode < 0.25:
+            s = bytearray(rng.choice(b"ACGT") for _ in range(L))
+        elif mode < 0.6:
+            per = rng.randint(1, 12)
+            unit = bytes(rng.choice(b"ACGT") for _ in range(per))
+            noise = rng.choice([0, 0.02, 0.05, 0.15])
+            s = bytearray(unit[i % per] if rng.random() >= noise else rng.choice(b"ACGTN") for i in range(L))
+        elif mode < 0.8:  # random with planted repeats and N runs
+            s = bytearray(rng.choice(b"ACGT") for _ in range(L))
+            for _ in range(rng.randint(1, 4)):
+                a = rng.randrange(L)
+                n = rng.randint(3, 90)
+                unit = bytes(rng.choice(b"ACGTN") for _ in range(rng.randint(1, 4))) if rng.random() < 0.7 else b"N"
+                s[a:a + n] = (unit * 90)[:n]
+            s = s[:L]
+        else:
+            s = bytearray(rng.choice(b"AAAAACGTNacgtXR-") for _ in range(L))
+        reads.append(bytes(s))
+    text = b"".join(r + b"\n" for r in reads)
+    out = subprocess.run([exe], input=text, stdout=subprocess.PIPE, check=True).stdout.split(b"\n")
+    masked = 0
+    for r, exp in zip(reads, out):
+        assert dust_mask(r) == exp, r
+        masked += exp != r
+    assert masked > 4000
+
+
 def test_index_header_facts(example_idx):
     """the example index header as parsed."""
     o = Oracle(example_idx)
