@@ -190,6 +190,53 @@ def test_dust_mask_against_reference_header():
     assert masked > 4000
 
 
+@pytest.mark.parametrize("variant", ["idx", "idx_b1", "idx_b8", "idx_off3"])
+def test_fm_index_against_reference_headers(tiny_dir, variant):
+    """rank / access / FM rank / backward search / locate walk: the oracle against the UNMODIFIED
+    compactds headers (oracle/_ref/fm_ref loads the same .1.cfr) on random queries"""
+    import random
+    import subprocess
+    from oracle_binding import REF_DIR
+    exe = os.path.join(REF_DIR, "fm_ref")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/fm_ref not built")
+    rng = random.Random(61)
+    o = Oracle(os.path.join(tiny_dir, variant))
+    n = o.n
+    _, reads = read_fastx(os.path.join(tiny_dir, "se_100.fq"))
+    queries = []
+    for p in [0, 1, n - 2, n - 1] + [rng.randrange(n) for _ in range(1500)]:
+        c = rng.choice("ACGT")
+        incl = rng.randrange(2)
+        queries += [("R", c, p, incl), ("A", p), ("F", c, p, incl)]
+    for _ in range(1200):
+        queries.append(("L", rng.randrange(n)))
+    for _ in range(1500):
+        r = rng.choice(reads)
+        a = rng.randrange(len(r) - 12)
+        s = bytearray(r[a:a + rng.randrange(11, len(r) - a + 1)])
+        if rng.random() < 0.3:
+            s[rng.randrange(len(s))] = rng.choice(b"ACGTN")
+        if rng.random() < 0.1:
+            s = bytearray(rng.choice(b"ACGT") for _ in range(rng.randrange(10, 40)))
+        queries.append(("S", bytes(s).decode()))
+    text = "".join(" ".join(map(str, q)) + "\n" for q in queries)
+    out = subprocess.run([exe, os.path.join(tiny_dir, variant + ".1.cfr")], input=text.encode(), stdout=subprocess.PIPE,
+                         check=True).stdout.decode().split("\n")
+    for q, line in zip(queries, out):
+        if q[0] == "R":
+            assert o.bwt_rank(q[1], q[2], q[3]) == int(line), q
+        elif q[0] == "A":
+            assert o.bwt_access(q[1]) == line, q
+        elif q[0] == "F":
+            assert o.fm_rank(q[1], q[2], q[3]) == int(line), q
+        elif q[0] == "L":
+            assert list(o.locate(q[1])) == [int(x) for x in line.split()], q
+        else:
+            assert list(o.backward_search(q[1].encode())) == [int(x) for x in line.split()], q
+    o.close()
+
+
 def test_index_header_facts(example_idx):
     """the example index header as parsed."""
     o = Oracle(example_idx)
