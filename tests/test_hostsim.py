@@ -294,3 +294,42 @@ def test_truncated_index_files_are_refused(tiny_dir, tmp_path):
             with pytest.raises(RuntimeError):
                 HostSim(str(tmp_path / "t"))
     HostSim(os.path.join(tiny_dir, "idx")).close()
+
+
+def test_device_sdust_against_reference_header():
+    """the product's SDUST (64-slot interval table, register-only screen in front) against the UNMODIFIED
+    Dustmasker.hpp (oracle/_ref/dust_ref) on generated reads -- no oracle in between"""
+    import subprocess
+    from oracle_binding import REF_DIR
+    exe = os.path.join(REF_DIR, "dust_ref")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/dust_ref not built")
+    rng = random.Random(71)
+    reads = [b"ACG", b"A" * 300, b"ACGT" * 80, b"A" * 70 + b"N" * 70 + b"C" * 70]
+    for it in range(5000):
+        L = rng.choice([3, 30, 63, 64, 65, 100, 150, 151, 300, 700, 1500])
+        mode = rng.random()
+        if mode < 0.3:
+            s = bytearray(rng.choice(b"ACGT") for _ in range(L))
+        elif mode < 0.7:
+            per = rng.randint(1, 12)
+            unit = bytes(rng.choice(b"ACGT") for _ in range(per))
+            noise = rng.choice([0, 0.02, 0.05, 0.15])
+            s = bytearray(unit[i % per] if rng.random() >= noise else rng.choice(b"ACGTN") for i in range(L))
+        else:
+            s = bytearray(rng.choice(b"ACGT") for _ in range(L))
+            for _ in range(rng.randint(1, 4)):
+                a = rng.randrange(L)
+                n = rng.randint(3, 90)
+                unit = bytes(rng.choice(b"ACGTN") for _ in range(rng.randint(1, 4))) if rng.random() < 0.7 else b"N"
+                s[a:a + n] = (unit * 90)[:n]
+            s = s[:L]
+        reads.append(bytes(s))
+    out = subprocess.run([exe], input=b"".join(r + b"\n" for r in reads), stdout=subprocess.PIPE, check=True).stdout.split(b"\n")
+    masked = 0
+    for r, exp in zip(reads, out):
+        assert hostsim_dust(r) == exp, r
+        if not hostsim_dust_screen(r):
+            assert exp == r, r  # a read the screen clears is one the reference leaves alone
+        masked += exp != r
+    assert masked > 1500
