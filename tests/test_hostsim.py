@@ -333,3 +333,45 @@ def test_device_sdust_against_reference_header():
             assert exp == r, r  # a read the screen clears is one the reference leaves alone
         masked += exp != r
     assert masked > 1500
+
+
+def test_device_taxonomy_reduction_against_reference_header(tiny_dir):
+    """tax_reduce / tax_lca / tax_expand (what the scoring kernel runs) directly against the UNMODIFIED
+    Taxonomy.hpp (oracle/_ref/taxonomy_ref): promoted ids and child lists on 5000 random id sets"""
+    import subprocess
+    from oracle_binding import REF_DIR
+    exe = os.path.join(REF_DIR, "taxonomy_ref")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/taxonomy_ref not built")
+    rng = random.Random(83)
+    hs = HostSim(os.path.join(tiny_dir, "idx"))
+    o = Oracle(os.path.join(tiny_dir, "idx"))
+    nodes = o.scalar(10)
+    o.close()
+    queries = []
+    for it in range(5000):
+        cnt = rng.randint(2, 10)
+        mode = rng.random()
+        if mode < 0.5:
+            ids = [rng.randrange(nodes) for _ in range(cnt)]
+        elif mode < 0.8:
+            pool = [rng.randrange(nodes) for _ in range(3)]
+            ids = [rng.choice(pool) for _ in range(cnt)]
+        else:
+            ids = [rng.randrange(nodes + 2) for _ in range(cnt)]
+        k = rng.choice([1, 1, 2, 3, 5])
+        if cnt > k:  # the kernel reduces only when there are more candidates than -k
+            queries.append((k, ids))
+    text = "".join("%d %s\n" % (k, " ".join(map(str, ids))) for k, ids in queries)
+    lines = subprocess.run([exe, os.path.join(tiny_dir, "idx.2.cfr")], input=text.encode(), stdout=subprocess.PIPE,
+                           check=True).stdout.decode().split("\n")
+    for (k, ids), line in zip(queries, lines):
+        left, right = line.split("|")
+        ref_ids = [int(x) for x in left.split()]
+        ref_lists = [[int(x) for x in l.split(",") if x] for l in right.split(";")] if right else []
+        if len(ref_lists) != len(ref_ids):
+            ref_lists = []  # Classifier.hpp:823: nothing is printed then
+        got_ids, got_lists = hs.expand_taxids(ids, k)
+        assert got_ids == ref_ids, (k, ids)
+        assert got_lists == (ref_lists if ref_lists else [[] for _ in ref_ids]), (k, ids, line)
+    hs.close()
