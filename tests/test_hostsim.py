@@ -375,3 +375,35 @@ def test_device_taxonomy_reduction_against_reference_header(tiny_dir):
         assert got_ids == ref_ids, (k, ids)
         assert got_lists == (ref_lists if ref_lists else [[] for _ in ref_ids]), (k, ids, line)
     hs.close()
+
+
+@pytest.mark.parametrize("layout", [1, 2])
+def test_device_fm_primitives_against_reference_headers(tiny_dir, layout):
+    """rank / access / locate of the product's BWT layouts (run-block as stored, and the occ sectors it is
+    transcoded into) directly against the UNMODIFIED compactds headers (oracle/_ref/fm_ref)"""
+    import subprocess
+    from oracle_binding import REF_DIR
+    exe = os.path.join(REF_DIR, "fm_ref")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/fm_ref not built")
+    rng = random.Random(97)
+    for variant in ("idx", "idx_b1", "idx_b8", "idx_off3"):
+        hs = HostSim(os.path.join(tiny_dir, variant), layout=layout)
+        o = Oracle(os.path.join(tiny_dir, variant))
+        n = o.n
+        o.close()
+        queries = []
+        for p in [0, 1, n - 2, n - 1] + [rng.randrange(n) for _ in range(800)]:
+            queries += [("R", rng.choice("ACGT"), p, rng.randrange(2)), ("A", p)]
+        queries += [("L", rng.randrange(n)) for _ in range(600)]
+        text = "".join(" ".join(map(str, q)) + "\n" for q in queries)
+        out = subprocess.run([exe, os.path.join(tiny_dir, variant + ".1.cfr")], input=text.encode(), stdout=subprocess.PIPE,
+                             check=True).stdout.decode().split("\n")
+        for q, line in zip(queries, out):
+            if q[0] == "R":
+                assert hs.bwt_rank(q[1], q[2], q[3]) == int(line), (variant, q)
+            elif q[0] == "A":
+                assert hs.bwt_access(q[1]) == line, (variant, q)
+            else:
+                assert hs.locate(q[1]) == int(line.split()[0]), (variant, q)
+        hs.close()
