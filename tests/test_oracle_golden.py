@@ -237,6 +237,48 @@ def test_fm_index_against_reference_headers(tiny_dir, variant):
     o.close()
 
 
+@pytest.mark.parametrize("variant,mhl", [("idx", 0), ("idx_b8", 16), ("idx_off3", 30)])
+def test_search_stage_against_reference_header(tiny_dir, variant, mhl):
+    """GetHitsFromRead / AdjustHitBoundaryFromStrandHits / SearchForwardAndReverse (Classifier.hpp:274-583):
+    the oracle's hit lists (sp, ep, length, offset, strand) against the UNMODIFIED Classifier.hpp
+    (oracle/_ref/classifier_ref) on the golden read sets plus generated reads, single and paired"""
+    import random
+    import subprocess
+    import sys
+    from oracle_binding import REF_DIR
+    exe = os.path.join(REF_DIR, "classifier_ref")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/classifier_ref not built")
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "fuzz"))
+    from fuzz_hostsim import make_read
+    rng = random.Random(89)
+    _, se = read_fastx(os.path.join(tiny_dir, "se_100.fq"))
+    _, p1 = read_fastx(os.path.join(tiny_dir, "pe_100_1.fq"))
+    _, p2 = read_fastx(os.path.join(tiny_dir, "pe_100_2.fq"))
+    _, e1 = read_fastx(os.path.join(tiny_dir, "edge_1.fq"))
+    _, e2 = read_fastx(os.path.join(tiny_dir, "edge_2.fq"))
+    genomes = [b"".join(se[i:i + 40]) for i in range(0, 240, 40)]  # stitched reads: chimeric "genomes" to cut fuzz reads from
+    pairs = [(r, None) for r in se] + list(zip(p1, p2)) + list(zip(e1, e2))
+    for _ in range(600):
+        L = rng.choice([rng.randrange(24, 160), 100, 150, rng.randrange(300, 1500)])
+        r1 = make_read(rng, genomes, L)
+        r2 = make_read(rng, genomes, max(24, L + rng.randrange(-20, 20))) if rng.random() < 0.5 else None
+        pairs.append((r1, r2))
+    pairs = [(a, b) for a, b in pairs if a and b != b"" and b"\t" not in a]
+    text = b"".join(a + b"\t" + (b if b else b"-") + b"\n" for a, b in pairs)
+    args = [exe, os.path.join(tiny_dir, variant)] + ([str(mhl)] if mhl else [])
+    out = subprocess.run(args, input=text, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, check=True).stdout.decode().split("\n")
+    o = Oracle(os.path.join(tiny_dir, variant), min_hit_len=mhl, dust=False)
+    with_hits = 0
+    for (a, b), line in zip(pairs, out):
+        exp = [tuple(int(x) for x in h.split(",")) for h in line.split(";") if h]
+        got = [(sp, ep, l, off, strand) for sp, ep, l, off, strand in o.search(a, b, cap=4096)]
+        assert got == exp, (a, b)
+        with_hits += bool(exp)
+    assert with_hits > 500
+    o.close()
+
+
 def test_index_header_facts(example_idx):
     """the example index header as parsed."""
     o = Oracle(example_idx)
