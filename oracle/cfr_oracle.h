@@ -11,9 +11,14 @@
  * this library, and only as the checker.  The product (centrifuger_b200/) never
  * links, loads or calls it.
  *
- * Pinning: checked against (1) /root/reference/example/example_class.out and
- * (2) outputs of the unmodified reference binary built into oracle/_ref/ (see
- * tests/test_oracle_golden.py, tests/golden/).
+ * Pinning (tests/test_oracle_golden.py, tests/golden/, tests/fuzz/): checked against
+ * (1) /root/reference/example/example_class.out, (2) ~100 committed outputs of the
+ * unmodified reference binary built into oracle/_ref/ (option grid, --expand-taxid,
+ * long reads, --consider-secondary), (3) the reference's own headers compiled into
+ * small drivers under oracle/_ref/ and queried at random: fm_ref (rank, access,
+ * FM rank, backward search, locate walk), classifier_ref (hit lists of the search
+ * stage), taxonomy_ref (ReduceTaxIds with its child lists), dust_ref (SDUST), and
+ * (4) a differential fuzzer against the reference binary on generated reads.
  */
 #ifndef CFR_ORACLE_H
 #define CFR_ORACLE_H
