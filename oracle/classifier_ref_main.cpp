@@ -1,8 +1,9 @@
 // Test infrastructure ONLY: a driver around the UNMODIFIED reference header Classifier.hpp (included from
 // the read-only reference tree at build time, never copied; its private search stage is reached by
 // redefining `private` for this translation unit only).  Built into oracle/_ref/classifier_ref.
-// argv: <index prefix> [minHitLen].  stdin: "r1<TAB>r2" per line ("-" = no mate); stdout: the hits of
-// Classifier::SearchForwardAndReverse as "sp,ep,l,offset,strand" separated by ';'.
+// argv: <index prefix> [minHitLen [k]].  stdin: "r1<TAB>r2" per line ("-" = no mate); stdout: the hits of
+// Classifier::SearchForwardAndReverse as "sp,ep,l,offset,strand" separated by ';' -- or, when k is given,
+// the result of Classifier::Query (no DUST): "score 2ndBest hitLength queryLength n name:taxID;...".
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -37,6 +38,8 @@ int main(int argc, char *argv[]) {
   if (argc < 2) return 2;
   struct _classifierParam param;
   if (argc > 2) param.minHitLen = atoi(argv[2]);
+  const bool query = argc > 3;
+  if (query) param.maxResult = atoi(argv[3]);
   Classifier<Sequence_RunBlock> classifier;
   classifier.Init(argv[1], param);
   static char line[1 << 20];
@@ -48,6 +51,16 @@ int main(int argc, char *argv[]) {
       continue;
     }
     if (r2 && !strcmp(r2, "-")) r2 = NULL;
+    if (query) {
+      struct _classifierResult res;
+      classifier.Query(r1, r2, res);
+      printf("%lu %lu %d %d %d ", (unsigned long)res.score, (unsigned long)res.secondaryScore, res.hitLength,
+             res.queryLength, (int)res.taxIds.size());
+      for (size_t i = 0; i < res.taxIds.size(); ++i)
+        printf("%s%s:%lu", i ? ";" : "", res.seqStrNames[i].c_str(), (unsigned long)res.taxIds[i]);
+      printf("\n");
+      continue;
+    }
     SimpleVector<struct _BWTHit> hits;
     classifier.SearchForwardAndReverse(r1, r2, hits);
     for (int i = 0; i < (int)hits.Size(); ++i)

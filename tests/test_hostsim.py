@@ -407,3 +407,59 @@ def test_device_fm_primitives_against_reference_headers(tiny_dir, layout):
             else:
                 assert hs.locate(q[1]) == int(line.split()[0]), (variant, q)
         hs.close()
+
+
+@pytest.mark.parametrize("layout,k", [(1, 1), (2, 1), (2, 3), (3, 5)])
+def test_device_pipeline_against_reference_header(tiny_dir, layout, k):
+    """the whole per-read path of the product (search, row plan, locate, scoring, reduction) directly against
+    Classifier::Query of the UNMODIFIED Classifier.hpp (oracle/_ref/classifier_ref), DUST off: golden read
+    sets plus generated reads, single and paired.  The oracle library only translates ids to names here."""
+    import subprocess
+    import sys
+    from oracle_binding import REF_DIR
+    exe = os.path.join(REF_DIR, "classifier_ref")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/classifier_ref not built")
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "fuzz"))
+    from fuzz_hostsim import make_read
+    rng = random.Random(101 + k)
+    idx = os.path.join(tiny_dir, "idx")
+    _, se = read_fastx(os.path.join(tiny_dir, "se_100.fq"))
+    _, p1 = read_fastx(os.path.join(tiny_dir, "pe_100_1.fq"))
+    _, p2 = read_fastx(os.path.join(tiny_dir, "pe_100_2.fq"))
+    genomes = [b"".join(se[i:i + 40]) for i in range(0, 240, 40)]
+    for paired in (False, True):
+        r1 = list(se) if not paired else list(p1)
+        r2 = None if not paired else list(p2)
+        for _ in range(400):
+            L = rng.choice([rng.randrange(24, 160), 100, 150, rng.randrange(300, 1200)])
+            r1.append(make_read(rng, genomes, L))
+            if paired:
+                r2.append(make_read(rng, genomes, max(24, L + rng.randrange(-20, 20))))
+        keep = [i for i in range(len(r1)) if r1[i] and (not paired or r2[i])]
+        r1 = [r1[i] for i in keep]
+        r2 = [r2[i] for i in keep] if paired else None
+        text = b"".join(r1[i] + b"\t" + (r2[i] if paired else b"-") + b"\n" for i in range(len(r1)))
+        out = subprocess.run([exe, idx, "0", str(k)], input=text, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
+                             check=True).stdout.decode().split("\n")
+        hs = HostSim(idx, layout=layout, k=k, dust=False)
+        names = Oracle(idx, k=k, dust=False)
+        res, ids, _ = hs.classify(r1, r2)
+        classified = 0
+        for i in range(len(r1)):
+            n = int(res["n_assign"][i])
+            parts = []
+            for j in range(min(n, k)):
+                a = int(ids[i][j])
+                if int(res["by_rank"][i]):
+                    parts.append("%s:%d" % (names.L.cfr_oracle_rank_name(names.h, a).decode(), names.L.cfr_oracle_orig_taxid(names.h, a)))
+                else:
+                    parts.append("%s:%d" % (names.L.cfr_oracle_seq_name(names.h, a).decode(),
+                                            names.L.cfr_oracle_orig_taxid(names.h, names.L.cfr_oracle_seqid_to_taxid(names.h, a))))
+            got = "%d %d %d %d %d %s" % (int(res["score"][i]), int(res["secondary_score"][i]), int(res["hit_length"][i]),
+                                         int(res["query_length"][i]), n, ";".join(parts))
+            assert got == out[i], (paired, i, r1[i])
+            classified += n > 0
+        assert classified > 300
+        hs.close()
+        names.close()
