@@ -1,7 +1,7 @@
 // Test infrastructure ONLY: a driver around the UNMODIFIED reference header Classifier.hpp (included from
 // the read-only reference tree at build time, never copied; its private search stage is reached by
 // redefining `private` for this translation unit only).  Built into oracle/_ref/classifier_ref.
-// argv: <index prefix> [minHitLen [k]].  stdin: "r1<TAB>r2" per line ("-" = no mate); stdout: the hits of
+// argv: <index prefix> [minHitLen [k [hitkFactor [secondaryHitLen secondaryScoreFactor]]]].  stdin: "r1<TAB>r2" per line ("-" = no mate); stdout: the hits of
 // Classifier::SearchForwardAndReverse as "sp,ep,l,offset,strand" separated by ';' -- or, when k is given,
 // the result of Classifier::Query (no DUST): "score 2ndBest hitLength queryLength n name:taxID;...".
 #include <stdio.h>
@@ -40,6 +40,11 @@ int main(int argc, char *argv[]) {
   if (argc > 2) param.minHitLen = atoi(argv[2]);
   const bool query = argc > 3;
   if (query) param.maxResult = atoi(argv[3]);
+  if (argc > 4) param.maxResultPerHitFactor = atoi(argv[4]);
+  if (argc > 6) {
+    param.considerSecondaryHitLen = (size_t)atol(argv[5]);
+    param.considerSecondaryScoreFactor = atof(argv[6]);
+  }
   Classifier<Sequence_RunBlock> classifier;
   classifier.Init(argv[1], param);
   static char line[1 << 20];

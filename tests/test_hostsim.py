@@ -409,8 +409,9 @@ def test_device_fm_primitives_against_reference_headers(tiny_dir, layout):
         hs.close()
 
 
-@pytest.mark.parametrize("layout,k", [(1, 1), (2, 1), (2, 3), (3, 5)])
-def test_device_pipeline_against_reference_header(tiny_dir, layout, k):
+@pytest.mark.parametrize("layout,k,hitk,sec", [(1, 1, 40, None), (2, 1, 40, None), (2, 3, 2, None), (3, 5, 0, None),
+                                               (2, 1, 40, (50, 0.9)), (1, 2, 1, (100, 0.5))])
+def test_device_pipeline_against_reference_header(tiny_dir, layout, k, hitk, sec):
     """the whole per-read path of the product (search, row plan, locate, scoring, reduction) directly against
     Classifier::Query of the UNMODIFIED Classifier.hpp (oracle/_ref/classifier_ref), DUST off: golden read
     sets plus generated reads, single and paired.  The oracle library only translates ids to names here."""
@@ -440,9 +441,13 @@ def test_device_pipeline_against_reference_header(tiny_dir, layout, k):
         r1 = [r1[i] for i in keep]
         r2 = [r2[i] for i in keep] if paired else None
         text = b"".join(r1[i] + b"\t" + (r2[i] if paired else b"-") + b"\n" for i in range(len(r1)))
-        out = subprocess.run([exe, idx, "0", str(k)], input=text, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
+        extra = [str(hitk)] + ([str(sec[0]), str(sec[1])] if sec else [])
+        kw = dict(hitk_factor=hitk)
+        if sec:
+            kw.update(secondary_len=sec[0], secondary_factor=sec[1])
+        out = subprocess.run([exe, idx, "0", str(k)] + extra, input=text, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
                              check=True).stdout.decode().split("\n")
-        hs = HostSim(idx, layout=layout, k=k, dust=False)
+        hs = HostSim(idx, layout=layout, k=k, dust=False, **kw)
         names = Oracle(idx, k=k, dust=False)
         res, ids, _ = hs.classify(r1, r2)
         classified = 0
