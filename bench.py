@@ -1,25 +1,29 @@
 #!/usr/bin/env python
-"""bench.py -- reads/s of the classification hot path on B200 (BASELINE.json metric).
+"""bench.py -- read pairs/s of the classification hot path on B200 (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|small|c3]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c3|c2|...]
 
-One "step" = one pass of the hot path over one batch of synthetic reads.
-Workload (N=1): BASELINE.json configs[1] -- synthetic 100 Mbp / 50-taxa index,
-1M x 100 bp single-end reads (seeded generator, tools/gen_data.py; the index is
-built by the unmodified reference builder, tools/make_data.py).
+One "step" = one pass of the hot path over the workload's reads.  Default workload (every N):
+BASELINE.json configs[2] -- synthetic 2 Gbp / 500-taxa index (HBM-resident: 1 GB of occ sectors,
+larger than the 126 MB L2), 10 M x 2x150 bp read pairs per step per GPU as ten distinct 1 M-pair
+device batches, -k 5.  Reads come from the seeded generator (tools/gen_data.py); the index is
+built by the unmodified reference builder (tools/make_data.py) and loaded unchanged.
 
 Numbers on the JSON line:
-  value     reads/s with the batch resident in HBM (cfr_classify_resident), device time
-  e2e       reads/s through cfr_classify_batch with pinned HOST buffers: H2D of the reads,
-            all kernels, D2H of the results, per step
-  roofline  dominant kernel (search): algorithmic index bytes (120 B per
-            run-block rank, 72 B per access, 16 B per lookup probe, counted in-kernel)
-            / its CUDA-event time, vs the measured HBM copy peak
+  value     pairs/s with the batches resident in HBM (cfr_classify_resident), CUDA-event time
+  e2e       pairs/s through cfr_submit_batch / cfr_wait_batch with pinned HOST buffers: H2D of the
+            reads, all kernels, D2H of the results, every step
+  roofline  dominant kernel (k_search).  `achieved` = its ALGORITHMIC bytes in this library's HBM
+            layout (32 B occ sector per rank, 16 B per lookup probe, 2.25 bits per read base; the
+            operations are counted in-kernel) / its CUDA-event time.  `achieved_dram` = the DRAM
+            bytes ncu measured for the same launch (profiles/traffic.json) / the same time.  `bound`
+            says "hbm" only when the sector array is larger than L2.
   cpu_baseline  the reference binary (oracle/_ref/centrifuger -t <cores>) on a bounded
             sample of the same reads, same box
 
-Multi-GPU (torchrun, one rank per GPU): reads shard across ranks, the index is replicated
-per GPU, NCCL all-reduces the per-taxon counters at the end of every step; weak scaling.
+Multi-GPU (torchrun, one rank per GPU): reads shard across ranks, the index is replicated per
+GPU, no data-path collective; NCCL all-reduces the per-taxon counters ONCE, after the last step
+(inside the timed region); weak scaling.
 """
 import argparse
 import json
@@ -38,20 +42,22 @@ sys.path.insert(0, os.path.join(ROOT, "tools"))
 import numpy as np  # noqa: E402
 
 WORKLOADS = {
-    # name: dataset, reads per step per GPU, read length, paired, -k
-    "c2": dict(dataset="c2", reads=1_000_000, rlen=100, paired=False, k=1,
+    # name: dataset, reads per step per GPU, reads per device batch, read length, paired, -k
+    "c2": dict(dataset="c2", reads=1_000_000, batch=1_000_000, rlen=100, paired=False, k=1,
                desc="synthetic 100 Mbp / 50-taxa index, 1M x 100 bp single-end reads (BASELINE configs[1])"),
-    "small": dict(dataset="small", reads=200_000, rlen=100, paired=False, k=1,
+    "small": dict(dataset="small", reads=200_000, batch=200_000, rlen=100, paired=False, k=1,
                   desc="synthetic 10 Mbp / 100-sequence index, 200k x 100 bp single-end reads"),
-    "small1m": dict(dataset="small", reads=1_000_000, rlen=100, paired=False, k=1,
-                    desc="synthetic 10 Mbp / 100-sequence index (occ sectors 5 MB), 1M x 100 bp single-end reads"),
-    "m700": dict(dataset="m700", reads=1_000_000, rlen=100, paired=False, k=1,
+    "m700": dict(dataset="m700", reads=1_000_000, batch=1_000_000, rlen=100, paired=False, k=1,
                  desc="synthetic 700 Mbp / 175-taxa index (occ sectors 350 MB > L2), 1M x 100 bp single-end reads"),
-    "m700pe": dict(dataset="m700", reads=500_000, rlen=150, paired=True, k=5,
-                   desc="synthetic 700 Mbp / 175-taxa index, 500k x 2x150 bp pairs per step, -k 5"),
-    "c3": dict(dataset="c3", reads=1_000_000, rlen=150, paired=True, k=5,
-               desc="synthetic 2 Gbp / 500-taxa index, 1M x 2x150 bp pairs per step, -k 5 (BASELINE configs[2])"),
+    "m700pe": dict(dataset="m700", reads=1_000_000, batch=500_000, rlen=150, paired=True, k=5,
+                   desc="synthetic 700 Mbp / 175-taxa index, 1M x 2x150 bp pairs per step, -k 5"),
+    "c3": dict(dataset="c3", reads=10_000_000, batch=1_000_000, rlen=150, paired=True, k=5,
+               desc="synthetic 2 Gbp / 500-taxa index, 10M x 2x150 bp read pairs, -k 5 (BASELINE configs[2])"),
+    "c3s": dict(dataset="c3", reads=1_000_000, batch=1_000_000, rlen=150, paired=True, k=5,
+                desc="synthetic 2 Gbp / 500-taxa index, 1M x 2x150 bp read pairs, -k 5 (one batch of BASELINE configs[2])"),
 }
+DEFAULT_WORKLOAD = "c3"
+L2_BYTES = 126 << 20
 
 
 def algorithmic_bytes(c, n_reads, bases):
@@ -133,39 +139,62 @@ class ClockSampler(threading.Thread):
                 "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
+def log(*a):
+    print("[bench]", *a, file=sys.stderr, flush=True)
+
+
 def ensure_dataset(name):
     import make_data
-    d = make_data.ensure(name, log=lambda *a: print("[bench]", *a, file=sys.stderr))
+    d = make_data.ensure(name, log=log)
     if d is None:
         raise SystemExit("dataset %s is missing and cannot be built (needs oracle/_ref/centrifuger-build)" % name)
     return os.path.join(d, "idx")
 
 
-def make_reads(w, seed):
-    import gen_data
-    import make_data
-    genomes = make_data.genomes_of(w["dataset"])
-    cat = gen_data.concat_genomes(genomes)
-    n, rl = w["reads"], w["rlen"]
-    off = (np.arange(n + 1, dtype=np.uint64) * np.uint64(rl))
-    if w["paired"]:
-        r1, r2 = gen_data.make_reads_pe_fast(genomes, n, rl, seed=seed, cat=cat)
-        return np.ascontiguousarray(r1).reshape(-1), off, np.ascontiguousarray(r2).reshape(-1), off.copy()
-    r1 = gen_data.make_reads_se_fast(genomes, n, rl, seed=seed, cat=cat)
-    return np.ascontiguousarray(r1).reshape(-1), off, None, None
+class ReadSource:
+    """Seeded synthetic reads of one workload: batch j of rank r is always the same reads."""
+
+    def __init__(self, w):
+        import gen_data
+        import make_data
+        self.w, self.gd = w, gen_data
+        self.genomes = make_data.genomes_of(w["dataset"])
+        self.cat = gen_data.concat_genomes(self.genomes)
+
+    def batch(self, n, seed):
+        """-> (seq1 bytes, off1, seq2 bytes | None, off2 | None), numpy arrays"""
+        w, rl = self.w, self.w["rlen"]
+        off = (np.arange(n + 1, dtype=np.uint64) * np.uint64(rl))
+        if w["paired"]:
+            r1, r2 = self.gd.make_reads_pe_fast(self.genomes, n, rl, seed=seed, cat=self.cat)
+            return np.ascontiguousarray(r1).reshape(-1), off, np.ascontiguousarray(r2).reshape(-1), off.copy()
+        r1 = self.gd.make_reads_se_fast(self.genomes, n, rl, seed=seed, cat=self.cat)
+        return np.ascontiguousarray(r1).reshape(-1), off, None, None
 
 
 def write_fastq_sample(seq, off, n, path, suffix=""):
+    rl = int(off[1] - off[0]) if n > 0 else 0
+    same = n > 0 and int(off[n]) == n * rl
     with open(path, "wb") as f:
-        for i in range(n):
-            s = seq[int(off[i]):int(off[i + 1])].tobytes()
-            f.write(b"@r%d%s\n%s\n+\n%s\n" % (i, suffix.encode(), s, b"I" * len(s)))
+        if same:  # one read length: build the file with numpy instead of a Python loop
+            ids = np.char.add(np.char.add("@r", np.arange(n).astype(str)), suffix).astype("S")
+            body = np.asarray(seq[:n * rl]).reshape(n, rl)
+            qual = b"I" * rl
+            out = bytearray()
+            for i in range(n):
+                out += ids[i] + b"\n" + body[i].tobytes() + b"\n+\n" + qual + b"\n"
+            f.write(out)
+        else:
+            for i in range(n):
+                s = seq[int(off[i]):int(off[i + 1])].tobytes()
+                f.write(b"@r%d%s\n%s\n+\n%s\n" % (i, suffix.encode(), s, b"I" * len(s)))
 
 
-def run_reference_cpu(idx, w, seq1, off1, seq2, off2, n_sample, threads, repeat=1):
-    """Time oracle/_ref/centrifuger (the unmodified reference) on the first n_sample reads of the
-    step batch, taken `repeat` times over (one process, `repeat` x n_sample reads).
-    Returns (reads/s, seconds, cores).  Index load time is measured with a 1-read run and subtracted."""
+def run_reference_cpu(idx, w, seq1, off1, seq2, off2, n_sample, threads, repeat=1, t_load=None):
+    """Time oracle/_ref/centrifuger (the unmodified reference) on the first n_sample reads of a
+    batch, taken `repeat` times over (one process, `repeat` x n_sample reads).
+    Returns (reads/s, seconds, cores, load seconds).  Index load time is measured with a 1-read run
+    and subtracted."""
     exe = os.path.join(ROOT, "oracle", "_ref", "centrifuger")
     if not os.path.exists(exe):
         return None
@@ -191,23 +220,31 @@ def run_reference_cpu(idx, w, seq1, off1, seq2, off2, n_sample, threads, repeat=
                 subprocess.run(base + args, check=True, stdout=dn, stderr=dn)
             return time.perf_counter() - t
 
-        timed(tiny)  # page the index in
-        t_load = min(timed(tiny), timed(tiny))
+        if t_load is None:
+            timed(tiny)  # page the index in
+            t_load = min(timed(tiny), timed(tiny))
         t_run = timed(files)
         secs = max(t_run - t_load, 1e-6)
-        return n_sample * repeat / secs, secs, threads
+        return n_sample * repeat / secs, secs, threads, t_load
     finally:
         import shutil
         shutil.rmtree(d, ignore_errors=True)
+
+
+def base_config(w, a, world):
+    """The part of `config` both arms print identically."""
+    return {"workload": w["desc"], "index": "data/%s/idx" % w["dataset"], "reads_per_step_per_gpu": w["reads"],
+            "read_length": w["rlen"], "paired": w["paired"], "k": w["k"], "dust": not a.no_dust,
+            "parallelism": "reads sharded over %d GPU(s), index replicated" % max(world, a.gpus)}
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default=os.environ.get("CFR_BENCH_WORKLOAD", DEFAULT_WORKLOAD), choices=sorted(WORKLOADS))
     ap.add_argument("--layout", type=int, default=0, help="0 auto, 1 run-block arrays, 2 occ sectors")
     ap.add_argument("--reads", type=int, default=0, help="override reads per step per GPU")
     ap.add_argument("--cpu-sample", type=int, default=0, help="reads in the CPU-baseline sample (0 = auto)")
@@ -219,29 +256,34 @@ def main():
     w = dict(WORKLOADS[a.workload])
     if a.reads:
         w["reads"] = a.reads
+        w["batch"] = min(w["batch"], a.reads)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     metric = "read pairs classified per second" if w["paired"] else "reads classified per second"
     unit = "pairs/s" if w["paired"] else "reads/s"
-    config = {"workload": w["desc"], "index": "data/%s/idx" % w["dataset"], "reads_per_step_per_gpu": w["reads"],
-              "read_length": w["rlen"], "paired": w["paired"], "k": w["k"], "dust": not a.no_dust,
-              "parallelism": "reads sharded over %d GPU(s), index replicated" % max(world, a.gpus)}
+    config = base_config(w, a, world)
+    nb = max(1, w["reads"] // w["batch"])      # device batches per step
+    bn = w["batch"]
+    n = nb * bn                                # reads per step per GPU
 
     # ------------------------------------------------------------------ reference arm
     if a.impl == "reference":
         if rank != 0:
             return 0
         idx = ensure_dataset(w["dataset"])
-        seq1, off1, seq2, off2 = make_reads(w, 7)
+        src = ReadSource(w)
         cores = os.cpu_count() or 1
-        n_sample = a.cpu_sample or min(w["reads"], (250_000 if not w["paired"] else 100_000) * max(1, cores // 8))
-        vals = []
+        # each step = a bounded sample of the workload: the first n_sample reads of the step's first batch
+        n_sample = a.cpu_sample or min(bn, (250_000 if not w["paired"] else 100_000) * max(1, cores // 8))
+        seq1, off1, seq2, off2 = src.batch(bn, 7)
+        vals, t_load = [], None
         for i in range(a.warmup + a.steps):
-            r = run_reference_cpu(idx, w, seq1, off1, seq2, off2, n_sample, cores)
+            r = run_reference_cpu(idx, w, seq1, off1, seq2, off2, n_sample, cores, t_load=t_load)
             if r is None:
                 print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/centrifuger not built"}))
                 return 0
+            t_load = r[3]
             if i >= a.warmup:
                 vals.append(r)
         secs = sum(v[1] for v in vals)
@@ -251,7 +293,8 @@ def main():
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64",
                 "data": "synthetic", "config": config,
                 "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": "reference",
-                                 "sample": "first %d reads of the step batch per step, centrifuger -t %d, index-load time subtracted" % (n_sample, cores)},
+                                 "sample": "first %d reads of the step's first batch per step, centrifuger -t %d, "
+                                           "FASTQ in / TSV to /dev/null, index-load time (%.2f s) subtracted" % (n_sample, cores, t_load)},
                 "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
         print(json.dumps(line))
@@ -275,12 +318,15 @@ def main():
         dist.barrier()
         if idx is None:
             idx = ensure_dataset(w["dataset"])
-    seq1, off1, seq2, off2 = make_reads(w, 7 + 1000 * rank)
-    n = w["reads"]
-    bases = int(seq1.size + (seq2.size if seq2 is not None else 0))
+    t0 = time.perf_counter()
+    src = ReadSource(w)
+    host = [src.batch(bn, 7 + 1000 * rank + 100003 * j) for j in range(nb)]
+    log("rank %d: %d batches of %d reads generated in %.1f s" % (rank, nb, bn, time.perf_counter() - t0))
+    bases = int(sum(b[0].size + (b[2].size if b[2] is not None else 0) for b in host))
 
     clf = cb.Classifier(idx, k=w["k"], dust=not a.no_dust, layout=a.layout, device=local_rank,
                         max_batch_reads=a.chunk)
+    log("rank %d: index open in %.2f s, %.2f GB of HBM" % (rank, clf.info(18) / 1e6, clf.hbm_bytes / 1e9))
     # a dedicated (non-default) torch stream: its handle is passed through the C ABI so the
     # library's kernels and torch's CUDA events are on the same stream
     stream = torch.cuda.Stream()
@@ -289,35 +335,31 @@ def main():
     assert sptr != 0
     # pinned host staging (torch supplies pinned memory and events; the work is in libcfrb200.so)
     pin = lambda arr: torch.from_numpy(arr).pin_memory() if arr is not None else None
-    p_seq1, p_off1, p_seq2, p_off2 = pin(seq1), pin(off1), pin(seq2), pin(off2)
-    res_host = torch.empty(n * 32, dtype=torch.uint8).pin_memory()
-    ids_host = torch.empty(max(1, n * w["k"]), dtype=torch.int64).pin_memory()
-    res_host2 = torch.empty(n * 32, dtype=torch.uint8).pin_memory()  # more sets for the streaming e2e loop
-    ids_host2 = torch.empty(max(1, n * w["k"]), dtype=torch.int64).pin_memory()
-    res_host3 = torch.empty(n * 32, dtype=torch.uint8).pin_memory()
-    ids_host3 = torch.empty(max(1, n * w["k"]), dtype=torch.int64).pin_memory()
+    pinned = [tuple(pin(x) for x in b) for b in host]
+    del host
+    NOUT = 3  # result buffers of the streaming loop (three batches in flight)
+    outs = [(torch.empty(bn * 32, dtype=torch.uint8).pin_memory(),
+             torch.empty(max(1, bn * w["k"]), dtype=torch.int64).pin_memory()) for _ in range(NOUT)]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
 
     from centrifuger_b200 import distributed as cdist
-    # the library's per-taxon counter vector in HBM, aliased as a torch tensor for the NCCL all-reduce
-    tax_tensor = cdist.device_counts_tensor(clf) if world > 1 else None
 
-    batch = clf.upload(p_seq1, p_off1, p_seq2, p_off2, stream=sptr)
+    batches = [clf.upload(*p, stream=sptr) for p in pinned]
+    reduced = [None]
 
-    def step_resident():
-        clf.classify_resident(batch, stream=sptr)
+    def final_reduce():
+        # the ONE collective of the path: per-taxon assignment counters, after the last step
         if world > 1:
-            cdist.allreduce_counts(tax_tensor)
-
-    def step_e2e():
-        clf.classify_packed(p_seq1, p_off1, p_seq2, p_off2, stream=sptr, out=(res_host, ids_host))
-        if world > 1:
-            cdist.allreduce_counts(tax_tensor)
+            reduced[0] = cdist.final_counts(clf)
 
     def sync_all():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def step_resident():
+        for b in batches:
+            clf.classify_resident(b, stream=sptr)
 
     # ---- kernel-resident timing ----
     for _ in range(a.warmup):
@@ -325,51 +367,49 @@ def main():
         step_resident()
     sync_all()
     clf.reset_counters()
+    clf.taxon_counts_reset()
     clf.stage_times(reset=True)
     clf.set_profiling(True)
     sampler = ClockSampler(local_rank)
     sampler.start()
-    evs = []
     t_wall0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
     for _ in range(a.steps):
-        flush.zero_()  # L2 flush between timed iterations (outside the per-step events)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        step_resident()
-        e1.record(stream)
-        evs.append((e0, e1))
+        step_resident()  # no L2 flush needed: index and the step's distinct batches are each larger than L2
+    final_reduce()
+    e1.record(stream)
     sync_all()
     t_wall = time.perf_counter() - t_wall0
-    dev_ms = sum(e0.elapsed_time(e1) for e0, e1 in evs)
+    dev_ms = e0.elapsed_time(e1)
     stage = clf.stage_times(reset=True)
     clf.set_profiling(False)
     counters = clf.counters()
     search_c = clf.stage_counters("search")
     # results must be complete (no reads left deferred) -- fetch also checks device error flags
-    clf.fetch(batch, stream=sptr, out=(res_host, ids_host))
+    clf.fetch(batches[0], stream=sptr, out=outs[0])
     launches_resident = counters["n_launches"]
+    tax_total = int(clf.taxon_counts()[clf.node_cnt + 1]) if world == 1 else int(reduced[0][clf.node_cnt + 1])
 
     # ---- end-to-end timing (pinned host buffers in, host results out) ----
     # The streaming form of the C ABI (cfr_submit_batch / cfr_wait_batch, what the CLI uses): every step
-    # uploads its reads from pinned host memory, runs all kernels and downloads its results; three steps
-    # are in flight so the copies of one overlap the kernels of the others.  All K steps' copies and
-    # kernels are inside the timed region.
-    outs = [(res_host, ids_host), (res_host2, ids_host2), (res_host3, ids_host3)]
-
+    # uploads its reads from pinned host memory, runs all kernels and downloads its results; three
+    # batches are in flight so the copies of one overlap the kernels of the others.  All K steps' copies
+    # and kernels are inside the timed region.
     def run_e2e(k_steps):
         inflight = []
-        for i in range(k_steps):
-            inflight.append(clf.submit(p_seq1, p_off1, p_seq2, p_off2, stream=sptr, out=outs[i % 3]))
-            if len(inflight) == 3:
-                clf.wait(inflight.pop(0)[0])
-                if world > 1:
-                    cdist.allreduce_counts(tax_tensor)
+        i = 0
+        for _ in range(k_steps):
+            for p in pinned:
+                inflight.append(clf.submit(*p, stream=sptr, out=outs[i % NOUT]))
+                i += 1
+                if len(inflight) == NOUT:
+                    clf.wait(inflight.pop(0)[0])
         while inflight:
             clf.wait(inflight.pop(0)[0])
-            if world > 1:
-                cdist.allreduce_counts(tax_tensor)
+        final_reduce()
 
-    run_e2e(a.warmup)
+    run_e2e(min(a.warmup, 2))
     sync_all()
     clf.reset_counters()
     link0 = (clf.info(13), clf.info(14))  # bytes the library has moved over the host link so far
@@ -379,14 +419,15 @@ def main():
     e2e_s = time.perf_counter() - t0
     link1 = (clf.info(13), clf.info(14))
     # single-call latency form (cfr_classify_batch: chunked copy/compute overlap inside one call)
-    step_e2e()
+    clf.classify_packed(*pinned[0], stream=sptr, out=outs[0])
     sync_all()
     t1 = time.perf_counter()
-    for _ in range(min(a.steps, 5)):
-        step_e2e()
+    for _ in range(3):
+        clf.classify_packed(*pinned[0], stream=sptr, out=outs[0])
     sync_all()
-    e2e_single_s = (time.perf_counter() - t1) / min(a.steps, 5)
-    # diagnostic: what the host link delivers for a plain pinned copy of the step's read bytes
+    e2e_single_s = (time.perf_counter() - t1) / 3
+    # diagnostic: what the host link delivers for a plain pinned copy of one batch's read bytes
+    p_seq1 = pinned[0][0]
     hb = torch.empty(int(p_seq1.numel()), dtype=torch.uint8, device="cuda")
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     hb.copy_(p_seq1, non_blocking=True)
@@ -400,13 +441,6 @@ def main():
     sampler.stop_flag = True
     sampler.join(timeout=2)
     launches_e2e = clf.counters()["n_launches"]
-    # diagnostic (untimed): per-stage kernel time of one end-to-end step (chunked launches)
-    clf.stage_times(reset=True)
-    clf.set_profiling(True)
-    step_e2e()
-    sync_all()
-    e2e_stage = clf.stage_times(reset=True)
-    clf.set_profiling(False)
 
     # ---- reduce over ranks (max time) ----
     t = torch.tensor([dev_ms, e2e_s * 1000.0, t_wall * 1000.0], dtype=torch.float64, device="cuda")
@@ -434,59 +468,85 @@ def main():
         per_launch_s = (s_ms / max(s_launch, 1)) / 1000.0
         achieved = (s_bytes / max(s_launch, 1)) / per_launch_s / 1e9 if s_ms > 0 else 0.0
         achieved_ref = (s_bytes_ref / max(s_launch, 1)) / per_launch_s / 1e9 if s_ms > 0 else 0.0
-        traffic = None
+        # DRAM bytes of one k_search launch over one device batch, from the committed ncu --set full
+        # capture of this workload (profiles/traffic.json; null if this workload has none)
+        traffic, traffic_src = None, None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
             try:
-                traffic = json.load(open(tp)).get(a.workload, {}).get("k_search_dram_bytes_per_launch")
+                tj = json.load(open(tp)).get(w["dataset"] + ("pe" if w["paired"] and w["dataset"] == "m700" else ""), {})
+                if tj.get("reads_per_launch") == bn:
+                    traffic, traffic_src = tj.get("k_search_dram_bytes_per_launch"), tj.get("source")
             except Exception:
                 traffic = None
+        index_bytes = clf.info(15) if occ else clf.info(19) or clf.hbm_bytes
+        hbm_resident = index_bytes > L2_BYTES
+        achieved_dram = (traffic / per_launch_s / 1e9) if (traffic and s_ms > 0) else None
         total_alg = algorithmic_bytes(counters, n * a.steps, bases * a.steps)
         line = {
             "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": dev_ms_max / a.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "int64", "data": "synthetic", "config": dict(config, **{
+            "vs_baseline": None, "dtype": "int64", "data": "synthetic", "config": config,
+            "details": {
                 "layout": {1: "run-block arrays as stored", 2: "32-byte occ sectors (transcoded on the GPU at load)"}[clf.layout],
-                "l2": "256 MiB device write between timed iterations (L2 flush)",
-                "index_hbm_bytes": clf.hbm_bytes, "min_hit_len": clf.min_hit_len}),
+                "l2": "no flush inside the timed region: the occ sectors (%.0f MB) and each step's %d distinct device batches "
+                      "(%.0f MB of reads) are larger than the 126 MB L2" % (clf.info(15) / 1e6, nb, bases / 1e6)
+                      if hbm_resident and bases > L2_BYTES else
+                      "index or step input smaller than L2: L2-resident numbers (256 MiB device write before each warm-up step only)",
+                "device_batches_per_step": nb, "reads_per_device_batch": bn,
+                "index_hbm_bytes": clf.hbm_bytes, "occ_sector_bytes": clf.info(15), "wide_lookup_bytes": clf.info(16),
+                "dense_locate_bytes": clf.info(17), "runblock_bytes_released": clf.info(19),
+                "dense_locate_shift": clf.info(20), "wide_lookup_width": clf.info(21), "position_bits": clf.info(22),
+                "cfr_open_seconds": clf.info(18) / 1e6, "min_hit_len": clf.min_hit_len, "index_rows": clf.n,
+                "reads_counted_by_final_reduce": tax_total},
             "e2e": {"value": e2e_value, "unit": unit,
                     # counted by the library from the copies it issues (reads of one length: the offsets
                     # are generated on the device and do not cross the link)
                     "h2d_bytes_per_step": int((link1[0] - link0[0]) // a.steps),
                     "d2h_bytes_per_step": int((link1[1] - link0[1]) // a.steps),
-                    "api": "cfr_submit_batch / cfr_wait_batch, three steps in flight, pinned host buffers",
-                    "single_call_value": n * world / e2e_single_s,
+                    "api": "cfr_submit_batch / cfr_wait_batch, three batches in flight, pinned host buffers",
+                    "single_call_value": bn / e2e_single_s,
                     "host_link_h2d_gbs": h2d_gbs},
             "gpu_launches": int(launches_resident + launches_e2e),
-            "roofline": {"bound": "hbm", "kernel": "k_search", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_kind": peak_kind,
+            "roofline": {"bound": "hbm" if hbm_resident else "l2/issue", "kernel": "k_search",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "peak_kind": peak_kind,
+                         "achieved_useful": achieved, "achieved_dram": achieved_dram,
+                         "frac_dram": (achieved_dram / peak) if achieved_dram else None,
+                         "traffic_source": traffic_src,
                          "algorithmic_bytes_per_launch": s_bytes / max(s_launch, 1),
                          "kernel_ms_per_launch": s_ms / max(s_launch, 1),
+                         "kernel_share_of_step": s_ms / max(sum(v[0] for v in stage.values()), 1e-9),
                          "reference_layout_gbs": achieved_ref,
-                         "note": ("index fits the 126 MB L2: the sectors are served from L2, DRAM traffic is in `traffic`"
-                                  if clf.hbm_bytes < (120 << 20) else "index larger than L2"),
+                         "note": ("occ sectors (%.0f MB) exceed the 126 MB L2: every rank is a DRAM line fill; `achieved` counts the "
+                                  "32 useful bytes of it, `achieved_dram` the bytes DRAM really moved (128-byte fills)" % (clf.info(15) / 1e6))
+                                 if hbm_resident else
+                                 ("occ sectors (%.0f MB) fit the 126 MB L2: `achieved` is L2 bandwidth, not HBM; DRAM traffic is in "
+                                  "`traffic`" % (clf.info(15) / 1e6)),
                          "pipeline_algorithmic_gbs": total_alg / (dev_ms_max / 1000.0) / 1e9 / world},
             "stage_ms_per_step": {k: v[0] / a.steps for k, v in stage.items()},
-            "e2e_stage_ms_per_step": {k: v[0] for k, v in e2e_stage.items()},
             "ops_per_read": {k: counters[k] / (n * a.steps) for k in
                              ("n_rank", "n_access", "n_search", "n_locate", "n_lf", "n_extend")},
             "clocks": sampler.summary(),
-            "wall_ms_per_step_incl_flush": wall_ms_max / a.steps,
+            "wall_ms_per_step": wall_ms_max / a.steps,
         }
         if not a.no_cpu_baseline and world == 1:
             cores = os.cpu_count() or 1
-            n_sample = a.cpu_sample or min(n, (250_000 if not w["paired"] else 100_000) * max(1, cores // 8))
+            seq1, off1, seq2, off2 = [x.numpy() if x is not None else None for x in pinned[0]]
+            n_sample = a.cpu_sample or min(bn, (250_000 if not w["paired"] else 100_000) * max(1, cores // 8))
             r = run_reference_cpu(idx, w, seq1, off1, seq2, off2, n_sample, cores)
             rep = 1
             if r is not None and r[1] < 10.0 and not a.cpu_sample:
                 # bounded sample of about 15 s of CPU work: the same reads taken several times over
                 rep = int(min(64, max(2, round(15.0 / max(r[1], 0.05)))))
-                r = run_reference_cpu(idx, w, seq1, off1, seq2, off2, n_sample, cores, repeat=rep)
+                r = run_reference_cpu(idx, w, seq1, off1, seq2, off2, n_sample, cores, repeat=rep, t_load=r[3])
             if r is not None:
                 line["cpu_baseline"] = {"value": r[0], "unit": unit, "cores": cores, "kind": "reference",
-                                        "sample": "first %d reads of the step batch x %d, centrifuger -t %d, %.1f s, index-load time subtracted" % (n_sample, rep, cores, r[1])}
+                                        "sample": "first %d reads of the step's first batch x %d, centrifuger -t %d, %.1f s, "
+                                                  "FASTQ in / TSV to /dev/null, index-load time subtracted" % (n_sample, rep, cores, r[1])}
         print(json.dumps(line))
-    batch.free()
+    for b in batches:
+        b.free()
     clf.close()
     if world > 1:
         dist.barrier()

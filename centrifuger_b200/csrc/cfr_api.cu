@@ -91,6 +91,9 @@ struct cfr_handle {
   int layout = CFR_LAYOUT_RUNBLOCK;
   std::vector<void *> index_allocs;
   size_t hbm_bytes = 0;
+  std::vector<size_t> index_alloc_bytes;  // parallel to index_allocs
+  size_t occ_bytes = 0, wide_bytes = 0, dense_bytes = 0, runblock_bytes = 0;
+  double open_seconds = 0.0;
   int sm_count = 148;
   int search_blocks = 10;  // resident 128-thread blocks per SM targeted by k_search (CFR_B200_SEARCH_BLOCKS)
   int occ_load = 4;    // how k_search / k_locate fetch a sector: 4 = one 256-bit load, 0 = two 128-bit loads (CFR_B200_OCC_LOAD)
@@ -146,9 +149,23 @@ int dev_alloc(cfr_handle *h, void **out, size_t bytes) {
   cudaError_t e = cudaMalloc(&p, bytes ? bytes : 16);
   if (e != cudaSuccess) return fail(CFR_ERR_NOMEM, std::string("cudaMalloc(index): ") + cudaGetErrorString(e));
   h->index_allocs.push_back(p);
+  h->index_alloc_bytes.push_back(bytes);
   h->hbm_bytes += bytes;
   *out = p;
   return CFR_OK;
+}
+
+// give one index array back (the run-block arrays once the occ sectors exist)
+void dev_release(cfr_handle *h, const void *p) {
+  if (!p) return;
+  for (size_t i = 0; i < h->index_allocs.size(); ++i)
+    if (h->index_allocs[i] == p) {
+      cudaFree(h->index_allocs[i]);
+      h->hbm_bytes -= h->index_alloc_bytes[i];
+      h->index_allocs.erase(h->index_allocs.begin() + i);
+      h->index_alloc_bytes.erase(h->index_alloc_bytes.begin() + i);
+      return;
+    }
 }
 
 // upload `bytes` from an (unaligned) host view, padded with `pad` zero bytes
@@ -308,6 +325,7 @@ int build_wide_lookup(cfr_handle *h, int WW) {
   CUDA_TRY(cudaStreamSynchronize(h->stream));
   h->ix.wide = (const u64x2 *)p;
   h->ix.wide_width = WW;
+  h->wide_bytes = n_keys * sizeof(u64x2);
   return CFR_OK;
 }
 
@@ -316,9 +334,9 @@ int build_wide_lookup(cfr_handle *h, int WW) {
 // for a denser table; its entries are computed by the reference's own walk, so results cannot change.
 int build_dense_locate(cfr_handle *h, int shift) {
   if (shift < 0 || h->ix.sample_shift < 0 || shift >= h->ix.sample_shift) return CFR_OK;
-  const u64 n_rows = (h->ix.n >> shift) + 1;
+  const u64 n_rows = ((h->ix.n - 1) >> shift) + 1;  // rows 0 .. n-1 only: row n does not exist
   void *p;
-  int st = dev_alloc(h, &p, n_rows * 4);
+  int st = dev_alloc(h, &p, n_rows * 4 + 16);
   if (st) return st;
   h->ix.dense_shift = -1;
   const int grid = grid_for(h, n_rows, 128, 16);
@@ -329,6 +347,7 @@ int build_dense_locate(cfr_handle *h, int shift) {
   CUDA_TRY(cudaStreamSynchronize(h->stream));
   h->ix.dense = (const u32 *)p;
   h->ix.dense_shift = shift;
+  h->dense_bytes = n_rows * 4;
   return CFR_OK;
 }
 
@@ -655,6 +674,7 @@ const char *cfr_last_error(void) { return g_err.c_str(); }
 int cfr_open(const char *idx_prefix, const cfr_params *p, int device, cfr_handle **out) {
   if (!idx_prefix || !out) return fail(CFR_ERR_ARG, "null argument");
   *out = nullptr;
+  const auto t_open0 = std::chrono::steady_clock::now();
   cfr_params params;
   if (p) params = *p; else cfr_default_params(&params);
   if (params.max_result <= 0) return fail(CFR_ERR_UNSUPPORTED, "-k must be >= 1 on the B200 path");
@@ -714,7 +734,25 @@ int cfr_open(const char *idx_prefix, const cfr_params *p, int device, cfr_handle
     if (params.layout == CFR_LAYOUT_OCCLINE) return bail(fail(CFR_ERR_UNSUPPORTED, "occ-sector layout needs n < 2^40"));
     h->layout = CFR_LAYOUT_RUNBLOCK;
   }
-  if (h->layout == CFR_LAYOUT_OCCLINE && (st = build_occ_lines(h))) return bail(st);
+  if (h->layout == CFR_LAYOUT_OCCLINE) {
+    if ((st = build_occ_lines(h))) return bail(st);
+    h->occ_bytes = (h->ix.n / 64 + 1) * sizeof(OccLine);
+    // the run-block arrays have served their purpose (k_transcode read them with the literal
+    // Sequence_RunBlock::Rank / Access); at 140 Gbp they are ~43 GB that the sectors replace.
+    // CFR_B200_KEEP_RUNBLOCK=1 keeps them (diagnostics).
+    const char *keep = getenv("CFR_B200_KEEP_RUNBLOCK");
+    if (!(keep && atoi(keep) != 0)) {
+      const size_t before = h->hbm_bytes;
+      DevBV *bvs[7] = {&h->ix.block_type, &h->ix.plain.node[0], &h->ix.plain.node[1], &h->ix.plain.node[2],
+                       &h->ix.run.node[0], &h->ix.run.node[1], &h->ix.run.node[2]};
+      for (DevBV *bv : bvs) {
+        dev_release(h, bv->B);
+        dev_release(h, bv->R);
+        bv->B = bv->R = nullptr;
+      }
+      h->runblock_bytes = before - h->hbm_bytes;
+    }
+  }
   {
     // wide lookup table: on by default when the BWT does not fit L2 (there the W-mer table and the
     // first extends are L2 hits and a 1 GB table would only add DRAM misses); CFR_B200_WIDE_LOOKUP=WW
@@ -749,6 +787,7 @@ int cfr_open(const char *idx_prefix, const cfr_params *p, int device, cfr_handle
     if ((st = build_dense_locate(h, shift))) return bail(st);
   }
   h->file.map1.close();  // everything needed from .1.cfr now lives in HBM
+  h->open_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_open0).count();
   *out = h;
   return CFR_OK;
 }
@@ -809,6 +848,14 @@ uint64_t cfr_index_info(const cfr_handle *h, int which) {
     case 12: return (uint64_t)h->P.max_result;
     case 13: return (uint64_t)h->h2d_bytes;
     case 14: return (uint64_t)h->d2h_bytes;
+    case 15: return (uint64_t)h->occ_bytes;
+    case 16: return (uint64_t)h->wide_bytes;
+    case 17: return (uint64_t)h->dense_bytes;
+    case 18: return (uint64_t)(h->open_seconds * 1e6);
+    case 19: return (uint64_t)h->runblock_bytes;
+    case 20: return (uint64_t)(h->ix.dense_shift < 0 ? 255 : h->ix.dense_shift);
+    case 21: return (uint64_t)h->ix.wide_width;
+    case 22: return h->pos32 ? 32u : 64u;
     default: return 0;
   }
 }

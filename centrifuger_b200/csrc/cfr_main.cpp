@@ -423,7 +423,8 @@ int main(int argc, char *argv[]) {
     return EXIT_FAILURE;
   }
   if (batchReads < 1) batchReads = 1;
-  params.max_batch_reads = (int32_t)(batchReads > (1 << 22) ? (1 << 22) : batchReads);
+  if (batchReads > (1 << 22)) batchReads = 1 << 22;  // the ingest loop cuts batches by this too
+  params.max_batch_reads = (int32_t)batchReads;
 
   {
     // The library's load-time tables (dense locate table, wide lookup table: DESIGN.md section 2) take
@@ -883,6 +884,8 @@ int main(int argc, char *argv[]) {
         rc = EXIT_FAILURE;
         bt->n = 0;
       }
+    } else if (rc != 0) {
+      bt->n = 0;  // after a device error no batch reaches the output stage unclassified (its result arrays are stale)
     }
     pending.push_back(std::make_pair(bt, ticket));
     if (pending.size() > 2) retire();

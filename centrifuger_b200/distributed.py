@@ -45,6 +45,18 @@ def device_counts_tensor(clf):
     return torch.as_tensor(_DevVec(ptr, n), device="cuda")
 
 
+def final_counts(clf, group=None):
+    """The path's one collective: SUM all-reduce of the per-taxon assignment counters, once, after the
+    last batch.  The library's live counter vector is snapshotted first (after a device
+    synchronize, so no scoring kernel is still adding to it) and the COPY is reduced: the live
+    vector stays this rank's own cumulative count and can be reduced again later without
+    double counting."""
+    import torch
+    torch.cuda.synchronize()
+    snap = device_counts_tensor(clf).clone()
+    return allreduce_counts(snap, group=group)
+
+
 def allreduce_counts(t, group=None):
     """SUM all-reduce of a counter tensor (NCCL for CUDA tensors, gloo for CPU tensors)."""
     import torch.distributed as dist

@@ -172,7 +172,11 @@ void cfr_host_free(void *p);
 /* index facts: 0 n, 1 b, 2 blockCnt, 3 firstISA, 4 min_hit_len in effect,
  * 5 nodeCnt, 6 seqCnt(+extra), 7 root ctid, 8 layout in use, 9 HBM bytes held,
  * 10 sampleRate, 11 precomputeWidth, 12 max_result,
- * 13 / 14 bytes the batch calls have moved host->device / device->host so far */
+ * 13 / 14 bytes the batch calls have moved host->device / device->host so far,
+ * 15 occ-sector bytes, 16 wide-lookup-table bytes, 17 dense-locate-table bytes,
+ * 18 microseconds cfr_open took, 19 run-block bytes released after the transcode,
+ * 20 dense-locate spacing (log2; 255 = none), 21 wide-lookup width (0 = none),
+ * 22 width of the BWT positions the kernels walk with (32 / 64) */
 uint64_t cfr_index_info(const cfr_handle *h, int which);
 
 /* Taxonomy look-ups used by ResultWriter (host tables) */
