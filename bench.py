@@ -53,6 +53,14 @@ WORKLOADS = {
                    desc="synthetic 700 Mbp / 175-taxa index, 1M x 2x150 bp pairs per step, -k 5"),
     "c3": dict(dataset="c3", reads=10_000_000, batch=1_000_000, rlen=150, paired=True, k=5,
                desc="synthetic 2 Gbp / 500-taxa index, 10M x 2x150 bp read pairs, -k 5 (BASELINE configs[2])"),
+    "c4": dict(dataset="c4", reads=10_000_000, batch=1_000_000, rlen=150, paired=True, k=5,
+               desc="synthetic 20 Gbp / 5000-sequence index (built on the GPU), 10M x 2x150 bp read pairs per GPU, -k 5 "
+                    "(BASELINE configs[3])"),
+    "c5": dict(dataset="c5", reads=10_000_000, batch=1_000_000, rlen=150, paired=True, k=5,
+               desc="synthetic 140 Gbp / 35000-sequence index (built on the GPU), 10M x 2x150 bp read pairs per GPU, -k 5 "
+                    "(BASELINE configs[4])"),
+    "s400": dict(dataset="s400", reads=2_000_000, batch=1_000_000, rlen=150, paired=True, k=5,
+                 desc="synthetic 400 Mbp / 100-sequence index (built on the GPU), 2M x 2x150 bp read pairs, -k 5"),
     "c3s": dict(dataset="c3", reads=1_000_000, batch=1_000_000, rlen=150, paired=True, k=5,
                 desc="synthetic 2 Gbp / 500-taxa index, 1M x 2x150 bp read pairs, -k 5 (one batch of BASELINE configs[2])"),
 }
@@ -158,6 +166,12 @@ class ReadSource:
         import gen_data
         import make_data
         self.w, self.gd = w, gen_data
+        self.syn = None
+        if w["dataset"] in make_data.SYNTHETIC:  # drawn from the device generator's definition, no text on the host
+            from centrifuger_b200 import builder
+            spec = make_data.SYNTHETIC[w["dataset"]]
+            self.syn = builder.SyntheticReads(spec["species"], spec["strains"], spec["genome_len"])
+            return
         self.genomes = make_data.genomes_of(w["dataset"])
         self.cat = gen_data.concat_genomes(self.genomes)
 
@@ -165,6 +179,9 @@ class ReadSource:
         """-> (seq1 bytes, off1, seq2 bytes | None, off2 | None), numpy arrays"""
         w, rl = self.w, self.w["rlen"]
         off = (np.arange(n + 1, dtype=np.uint64) * np.uint64(rl))
+        if self.syn is not None:
+            r1, r2, _ = self.syn.pairs(n, rl, seed)
+            return np.ascontiguousarray(r1).reshape(-1), off, np.ascontiguousarray(r2).reshape(-1), off.copy()
         if w["paired"]:
             r1, r2 = self.gd.make_reads_pe_fast(self.genomes, n, rl, seed=seed, cat=self.cat)
             return np.ascontiguousarray(r1).reshape(-1), off, np.ascontiguousarray(r2).reshape(-1), off.copy()

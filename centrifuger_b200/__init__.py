@@ -65,6 +65,11 @@ ABI_SYMBOLS = [
     "cfr_get_stage_counters", "cfr_debug_bwt_rank", "cfr_debug_bwt_access",
     "cfr_debug_locate", "cfr_debug_dust",
 ]
+# include/centrifuger_b200_build.h (the index builder, bound in centrifuger_b200/builder.py)
+BUILD_ABI_SYMBOLS = [
+    "cfr_build_default_params", "cfr_build_last_error", "cfr_build_fm_index", "cfr_build_synthetic_fm_index",
+    "cfr_synth_bases", "cfr_synth_fragments",
+]
 
 _lib = None
 

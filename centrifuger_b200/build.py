@@ -37,15 +37,36 @@ def _stale(target, deps):
 def sources():
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
     deps.append(os.path.join(ROOT, "include", "centrifuger_b200.h"))
+    deps.append(os.path.join(ROOT, "include", "centrifuger_b200_build.h"))
     return deps
+
+
+def _compile_objects(units, verbose):
+    """nvcc -c every translation unit (in parallel), return the object paths."""
+    from concurrent.futures import ThreadPoolExecutor
+    objdir = os.path.join(HERE, "build")
+    os.makedirs(objdir, exist_ok=True)
+
+    def one(src):
+        obj = os.path.join(objdir, os.path.basename(src) + ".o")
+        cmd = [_nvcc()] + NVCC_FLAGS + ["--extended-lambda", "-c", "-o", obj, src]
+        if verbose:
+            print(" ".join(cmd))
+        subprocess.check_call(cmd)
+        return obj
+
+    with ThreadPoolExecutor(max_workers=len(units)) as ex:
+        return list(ex.map(one, units))
 
 
 def build(force=False, verbose=False):
     deps = sources()
     if force or _stale(LIB, deps):
-        cmd = [_nvcc()] + NVCC_FLAGS + ["-shared", "-o", LIB,
-                                        os.path.join(CSRC, "cfr_api.cu"),
-                                        os.path.join(CSRC, "cfr_format.cpp")]  # cudart is linked statically (nvcc default)
+        # classification path (cfr_api.cu), index builder (cfr_build.cu), file grammar (cfr_format.cpp):
+        # one shared object, cudart linked statically (nvcc default)
+        objs = _compile_objects([os.path.join(CSRC, "cfr_api.cu"), os.path.join(CSRC, "cfr_build.cu"),
+                                 os.path.join(CSRC, "cfr_format.cpp")], verbose)
+        cmd = [_nvcc(), "-shared", "-o", LIB] + objs
         if verbose:
             print(" ".join(cmd))
         subprocess.check_call(cmd)

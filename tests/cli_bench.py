@@ -22,7 +22,7 @@ def main():
     w = dict(bench.WORKLOADS[wl])
     w["reads"] = n
     idx = bench.ensure_dataset(w["dataset"])
-    seq1, off1, seq2, off2 = bench.make_reads(w, 7)
+    seq1, off1, seq2, off2 = bench.ReadSource(w).batch(n, 7)
     d = tempfile.mkdtemp(prefix="cfr_cli_")
     f1 = os.path.join(d, "r_1.fq")
     bench.write_fastq_sample(seq1, off1, n, f1, "/1" if seq2 is not None else "")

@@ -11,14 +11,25 @@ import centrifuger_b200 as cb
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _declared_symbols():
-    hdr = open(os.path.join(ROOT, "include", "centrifuger_b200.h")).read()
+def _declared_in(header):
+    hdr = open(os.path.join(ROOT, "include", header)).read()
     hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
     return sorted(set(re.findall(r"\b(cfr_[a-z0-9_]+)\s*\(", hdr)))
 
 
+def _declared_symbols():
+    """every entry point declared by every header under include/"""
+    out = []
+    for h in sorted(os.listdir(os.path.join(ROOT, "include"))):
+        if h.endswith(".h"):
+            out += _declared_in(h)
+    return sorted(set(out))
+
+
 def test_header_and_binding_agree():
-    assert _declared_symbols() == sorted(cb.ABI_SYMBOLS)
+    assert _declared_in("centrifuger_b200.h") == sorted(cb.ABI_SYMBOLS)
+    assert _declared_in("centrifuger_b200_build.h") == sorted(cb.BUILD_ABI_SYMBOLS)
+    assert _declared_symbols() == sorted(cb.ABI_SYMBOLS + cb.BUILD_ABI_SYMBOLS)
 
 
 def test_library_exports_every_declared_symbol():

@@ -41,6 +41,45 @@ DATASETS = {
 }
 
 
+# Synthetic collections generated AND indexed on the GPU by this repo's builder (centrifuger_b200/builder.py,
+# csrc/cfr_build.cu): the text of a 20 - 140 Gbp collection never exists on the host, and the reference
+# builder would need hours and more memory than the box has (FMBuilder.hpp:328-329: n/2 bytes of samples
+# as size_t on top of the text and BWT).  The builder's parity with the reference builder is pinned on the
+# collections above (tests/test_builder.py: byte-identical files).
+SYNTHETIC = {
+    "s400": dict(species=20, strains=5, genome_len=4_000_000),      # 400 Mbp: quick checks
+    "c4": dict(species=1000, strains=5, genome_len=4_000_000),      # BASELINE configs[3]: 20 Gbp
+    "c5": dict(species=7000, strains=5, genome_len=4_000_000),      # BASELINE configs[4]: 140 Gbp
+}
+
+
+def ensure_synthetic(name, log=print, device=0):
+    """data/<name>/idx.{1,2,3,4}.cfr built on the GPU; returns the directory (None without a GPU)."""
+    d = os.path.join(DATA, name)
+    prefix = os.path.join(d, "idx")
+    if index_ready(prefix) and os.path.exists(prefix + ".ok"):
+        return d
+    try:
+        import torch
+        if not torch.cuda.is_available():
+            return None
+    except Exception:
+        return None
+    sys.path.insert(0, ROOT)
+    from centrifuger_b200 import builder
+    os.makedirs(d, exist_ok=True)
+    spec = SYNTHETIC[name]
+    t = time.time()
+    st = builder.build_synthetic(prefix, spec["species"], spec["strains"], spec["genome_len"], device=device,
+                                 verbose=bool(os.environ.get("CFR_BUILD_VERBOSE")))
+    with open(prefix + ".ok", "w") as f:
+        f.write("batches %d sort %.1f derive %.1f runblock %.1f write %.1f total %.1f\n" %
+                (st.batches, st.sort_seconds, st.derive_seconds, st.runblock_seconds, st.write_seconds, time.time() - t))
+    log("built data/%s on the GPU in %.1fs (%d batches: sort %.1fs, derive %.1fs, run blocks %.1fs, file %.1fs)" %
+        (name, time.time() - t, st.batches, st.sort_seconds, st.derive_seconds, st.runblock_seconds, st.write_seconds))
+    return d
+
+
 def have_builder():
     return os.path.exists(os.path.join(REF_BIN, "centrifuger-build"))
 
@@ -69,6 +108,8 @@ def genomes_of(name):
 def ensure(name, log=print):
     """Make sure data/<name>/ exists; returns its directory (or None if it cannot be built)."""
     d = os.path.join(DATA, name)
+    if name in SYNTHETIC:
+        return ensure_synthetic(name, log=log)
     if name == "example":
         prefix = os.path.join(d, "cfr_ref_idx")
         if index_ready(prefix):
