@@ -2,6 +2,8 @@
 // batch pipeline orchestration, result hand-back.  Host C++ + CUDA runtime only.
 #include <cuda_runtime.h>
 
+#include <cub/device/device_scan.cuh>
+
 #include <chrono>
 
 #include <algorithm>
@@ -92,10 +94,11 @@ struct cfr_handle {
   std::vector<void *> index_allocs;
   size_t hbm_bytes = 0;
   std::vector<size_t> index_alloc_bytes;  // parallel to index_allocs
-  size_t occ_bytes = 0, wide_bytes = 0, dense_bytes = 0, runblock_bytes = 0;
+  size_t occ_bytes = 0, wide_bytes = 0, dense_bytes = 0, runblock_bytes = 0, pair_bytes = 0;
   double open_seconds = 0.0;
   int sm_count = 148;
   int search_blocks = 10;  // resident 128-thread blocks per SM targeted by k_search (CFR_B200_SEARCH_BLOCKS)
+  int pair_search_blocks = 8;  // the same for the pair-line search kernel (CFR_B200_PAIR_SEARCH_BLOCKS)
   int occ_load = 4;    // how k_search / k_locate fetch a sector: 4 = one 256-bit load, 0 = two 128-bit loads (CFR_B200_OCC_LOAD)
   bool pos32 = false;  // 32-bit BWT positions in k_search / k_locate (collections below 2^32 rows; CFR_B200_POS64=1 disables)
   int dust_quorum = 0;  // quorum of the SDUST state machine (0 = the search quorum; CFR_B200_DUST_QUORUM)
@@ -305,6 +308,49 @@ int build_occ_lines(cfr_handle *h) {
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaStreamSynchronize(h->stream));
   h->ix.occ = (const OccLine *)p;
+  return CFR_OK;
+}
+
+// Pair lines (DevIndex::pairs, cfr_core.cuh "Layout 3"): built from the occ sectors; k_search then does two
+// BackwardExtend steps per DRAM line.  2 bytes per BWT row.
+int build_pair_lines(cfr_handle *h) {
+  const u64 n_lines = h->ix.n / 64 + 1, n_chunk = (n_lines + CFR_PAIR_CHUNK - 1) / CFR_PAIR_CHUNK;
+  const u64 n_sb = ((n_lines - 1) >> CFR_PAIR_SB_SHIFT) + 1;
+  void *p_lines, *p_sb;
+  int st = dev_alloc(h, &p_lines, n_lines * sizeof(PairLine));
+  if (st) return st;
+  if ((st = dev_alloc(h, &p_sb, n_sb * 20 * 8))) return st;
+  DevBuf tot, k18, tmp;
+  if ((st = tot.ensure(20 * n_chunk * 8))) return st;
+  if ((st = k18.ensure(18 * 8))) return st;
+  PairLine *lines = (PairLine *)p_lines;
+  u64 *d_tot = (u64 *)tot.p;
+  k_pair_planes<<<grid_for(h, n_lines, 128, 16), 128, 0, h->stream>>>(h->ix, lines, n_lines);
+  k_pair_totals<<<grid_for(h, n_chunk, 128, 16), 128, 0, h->stream>>>(h->ix, lines, n_lines, d_tot, n_chunk);
+  CUDA_TRY(cudaGetLastError());
+  if (n_chunk >= (1ull << 31)) return fail(CFR_ERR_UNSUPPORTED, "pair layout: too many chunks");
+  size_t tb = 0;
+  CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, tb, d_tot, d_tot, (int)n_chunk, h->stream));
+  if ((st = tmp.ensure(tb))) return st;
+  for (int k = 0; k < 20; ++k)
+    CUDA_TRY(cub::DeviceScan::ExclusiveSum(tmp.p, tb, d_tot + (u64)k * n_chunk, d_tot + (u64)k * n_chunk, (int)n_chunk, h->stream));
+  k_pair_sb<<<(unsigned)((n_sb * 20 + 127) / 128), 128, 0, h->stream>>>(d_tot, n_chunk, (u64 *)p_sb, n_sb);
+  k_pair_counters<<<grid_for(h, n_chunk, 128, 16), 128, 0, h->stream>>>(h->ix, lines, n_lines, d_tot, n_chunk, (const u64 *)p_sb);
+  k_pair_consts<<<1, 32, 0, h->stream>>>(h->ix, (u64 *)k18.p);
+  h->launches += 25;
+  CUDA_TRY(cudaGetLastError());
+  u64 host18[18];
+  CUDA_TRY(cudaMemcpyAsync(host18, k18.p, sizeof(host18), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  for (int i = 0; i < 16; ++i) h->ix.pair_D[i] = host18[i];
+  h->ix.pair_E = (int)host18[16];
+  h->ix.pair_F = (int)host18[17];
+  h->ix.pairs = lines;
+  h->ix.pair_sb = (const u64 *)p_sb;
+  h->pair_bytes = n_lines * sizeof(PairLine);
+  tot.release();
+  k18.release();
+  tmp.release();
   return CFR_OK;
 }
 
@@ -555,7 +601,8 @@ int run_pass(cfr_handle *h, const ChunkDev &B, int first_pass, cudaStream_t s) {
   return CFR_OK;
 }
 
-template <class Bwt, class BwtWide>
+// BwtSearch = policy of the search kernel (the pair lines when they were built)
+template <class Bwt, class BwtWide, class BwtSearch = BwtWide>
 int run_first(cfr_handle *h, cfr_device_batch *b, cudaStream_t s) {
   ChunkDev B;
   fill_chunk(h, b, B);
@@ -577,10 +624,12 @@ int run_first(cfr_handle *h, cfr_device_batch *b, cudaStream_t s) {
   CUDA_TRY(cudaMemsetAsync(B.task_counter, 0, 8, s));
   {
     StageScope sc(h, s, CFR_STAGE_SEARCH);
-    const int g = grid_for(h, B.n_reads * 2 * B.mates, 128, h->search_blocks);
-    if (h->search_blocks >= 12) k_search<BwtWide, 12><<<g, 128, 0, s>>>(h->ix, h->P, B);
-    else if (h->search_blocks >= 10) k_search<BwtWide, 10><<<g, 128, 0, s>>>(h->ix, h->P, B);
-    else k_search<BwtWide, 8><<<g, 128, 0, s>>>(h->ix, h->P, B);
+    // the pair policy keeps four lanes per task and more live registers: 8 resident blocks per SM do not spill
+    const int sblocks = BwtSearch::PAIR ? h->pair_search_blocks : h->search_blocks;
+    const int g = grid_for(h, B.n_reads * 2 * B.mates * BwtSearch::LANES, 128, sblocks);
+    if (sblocks >= 12) k_search<BwtSearch, 12><<<g, 128, 0, s>>>(h->ix, h->P, B);
+    else if (sblocks >= 10) k_search<BwtSearch, 10><<<g, 128, 0, s>>>(h->ix, h->P, B);
+    else k_search<BwtSearch, 8><<<g, 128, 0, s>>>(h->ix, h->P, B);
     ++h->launches;
   }
   CUDA_TRY(cudaGetLastError());
@@ -709,6 +758,7 @@ int cfr_open(const char *idx_prefix, const cfr_params *p, int device, cfr_handle
   if (const char *e = getenv("CFR_B200_TRACE")) h->trace = atoi(e) != 0;
   if (const char *e = getenv("CFR_B200_QUORUM")) h->P.quorum = std::max(1, atoi(e));
   if (const char *e = getenv("CFR_B200_SEARCH_BLOCKS")) h->search_blocks = std::max(1, atoi(e));
+  if (const char *e = getenv("CFR_B200_PAIR_SEARCH_BLOCKS")) h->pair_search_blocks = std::max(1, atoi(e));
   if (const char *e = getenv("CFR_B200_DUST_SCREEN")) h->dust_screen = atoi(e) != 0;
   if (const char *e = getenv("CFR_B200_DUST_QUORUM")) h->dust_quorum = std::max(0, atoi(e));
   if (const char *e = getenv("CFR_B200_DUST_LANES")) h->dust_lanes = std::min(32, std::max(1, atoi(e)));
@@ -772,6 +822,19 @@ int cfr_open(const char *idx_prefix, const cfr_params *p, int device, cfr_handle
     }
     if (const char *e = getenv("CFR_B200_WIDE_LOOKUP")) ww = atoi(e);
     if ((st = build_wide_lookup(h, ww))) return bail(st);
+  }
+  {
+    // pair lines for the search kernel: when the occ sectors do not fit L2 (every rank is a DRAM line fill)
+    // and 2 bytes per row fit next to everything else with 24 GiB to spare; CFR_B200_PAIRS=1 / 0 forces / forbids
+    bool want = false;
+    if (h->layout == CFR_LAYOUT_OCCLINE) {
+      size_t free_b = 0, total_b = 0;
+      cudaMemGetInfo(&free_b, &total_b);
+      const u64 need = (h->ix.n / 64 + 1) * sizeof(PairLine);
+      want = h->occ_bytes > (96ull << 20) && (u64)free_b > need + (24ull << 30);
+      if (const char *e = getenv("CFR_B200_PAIRS")) want = atoi(e) != 0;
+    }
+    if (want && (st = build_pair_lines(h))) return bail(st);
   }
   {
     // dense locate table: the densest spacing whose table (4 bytes per entry) stays below a quarter
@@ -856,6 +919,7 @@ uint64_t cfr_index_info(const cfr_handle *h, int which) {
     case 20: return (uint64_t)(h->ix.dense_shift < 0 ? 255 : h->ix.dense_shift);
     case 21: return (uint64_t)h->ix.wide_width;
     case 22: return h->pos32 ? 32u : 64u;
+    case 23: return (uint64_t)h->pair_bytes;
     default: return 0;
   }
 }
@@ -883,6 +947,10 @@ int cfr_classify_resident(cfr_handle *h, cfr_device_batch *b, void *stream) {
   h->host_bases += b->total_bases;
   b->classified = true;
   if (h->layout == CFR_LAYOUT_OCCLINE) {
+    if (h->ix.pairs) {
+      if (h->pos32) return run_first<BwtOccLine, BwtOccLine32T<4>, BwtPairT<true>>(h, b, s);
+      return run_first<BwtOccLine, BwtOccLineT<4>, BwtPairT<true>>(h, b, s);
+    }
     if (h->pos32) {
       if (h->occ_load == 0) return run_first<BwtOccLine, BwtOccLine32T<0>>(h, b, s);
       return run_first<BwtOccLine, BwtOccLine32T<4>>(h, b, s);

@@ -370,7 +370,7 @@ struct BwtRunBlock {
   static CFR_HD u64 rank(const DevIndex &ix, int c, u64 i, int inclusive) { return rb_rank(ix, c, i, inclusive); }
   static CFR_HD int access(const DevIndex &ix, u64 i) { return rb_access(ix, i); }
   static CFR_HD bool leader() { return true; }
-  enum { LANES = 1 };
+  enum { LANES = 1, PAIR = 0 };
 };
 
 // ---------------------------------------------------------------------------
@@ -531,7 +531,7 @@ struct BwtOccLineT {
     return occ_symbol(p.x, p.y, (int)(i & 63));
   }
   static CFR_HD bool leader() { return true; }
-  enum { LANES = 1 };
+  enum { LANES = 1, PAIR = 0 };
 };
 
 typedef BwtOccLineT<0> BwtOccLine;
@@ -596,7 +596,281 @@ struct BwtOccLine32T {
     return (u32)ix.C[c] + r + ((c == ix.last_code && i < (u32)ix.first_isa) ? 1u : 0u);
   }
   static CFR_HD bool leader() { return true; }
-  enum { LANES = 1 };
+  enum { LANES = 1, PAIR = 0 };
+};
+
+// ---------------------------------------------------------------------------
+// Layout 3 (search kernel only): 128-byte PAIR lines, two BackwardExtend steps per DRAM line
+// ---------------------------------------------------------------------------
+// For an index that lives in HBM every rank is one DRAM line fill whatever its size (128 bytes are
+// filled for a 32-byte sector), and the chip sustains a fixed number of such requests per second
+// (DESIGN.md section 3).  A line that four adjacent lanes fetch as ONE coalesced request costs the
+// same as a sector, so the line is spent on the second-order FM index: besides the row's own symbol
+// it holds the symbol of the row it maps to, and counters of the 16 symbol pairs.  From the line at
+// a boundary x both
+//     step(c1, x)            = C[c1] + occ(c1, x) + [c1 == lastChr && x <= firstISA]      (FMIndex.hpp:352-379)
+//     step(c2, step(c1, x))  = C[c2] + D[c1][c2] + P(c1, c2, x) + corrections            (derivation below)
+// follow, i.e. two steps of FMIndex::BackwardSearch's loop with their own stop tests
+// (FMIndex.hpp:495-508) for one request per boundary.
+//
+// Derivation of the second step.  step(c2, y) with y = step(c1, x) needs occ(c2, y) = occ(c2, C[c1]) +
+// #{j in [C[c1], y): B[j] = c2}.  The rows [C[c1], y) are the images img(i) = step(c1, i) of the rows
+// i < x with B[i] = c1, one each -- except that for c1 == lastChr (i) row C[c1] itself is the image of
+// the virtual '$' row, not of a stored row: its symbol E is added; (ii) the stored row firstISA (which
+// holds lastChr in place of '$') shares its image with the next c1 row, or maps just past y: once
+// x > firstISA its code2 F is taken out again.  tests/test_hostsim.py checks the identity for every
+// boundary and pair of the test indexes against the literal two steps.
+struct PairQuery {
+  u64 s1;    // occ(c1, x), absolute
+  u64 p;     // P(c1, c2, x), absolute
+  int sym1;  // code1 of row x (meaningful for x < n)
+  int sym2;  // code2 of row x
+};
+
+CFR_HD u64 pair_match(u64 lo, u64 hi, int c) { return occ_match(lo, hi, c); }
+
+// A lane's share of one line.  Device, cooperative: the 32 bytes at 32 * (lane & 3) of the line, fetched by the
+// four lanes of a task group as one coalesced 128-byte request.  Host twin / scalar form: the planes, the
+// counter words are read when needed.
+struct PairRegs {
+  u64 a, b, c, d;
+  const u64 *w;  // scalar form only
+};
+
+template <bool COOP>
+CFR_HD PairRegs pair_load(const DevIndex &ix, u64 L) {
+  PairRegs r;
+  r.w = ix.pairs[L].w;
+#if defined(__CUDA_ARCH__)
+  if (COOP) {
+    asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(r.a), "=l"(r.b), "=l"(r.c), "=l"(r.d)
+                 : "l"(reinterpret_cast<const char *>(r.w) + 32 * (threadIdx.x & 3)));
+    return r;
+  }
+#endif
+  r.a = ld64(r.w);
+  r.b = ld64(r.w + 1);
+  r.c = ld64(r.w + 2);
+  r.d = ld64(r.w + 3);
+  return r;
+}
+
+// everything one boundary x = 64 L + s needs from its line (all lanes of a group hold the same c1, c2, L, s)
+template <bool COOP>
+CFR_HD PairQuery pair_eval(const DevIndex &ix, const PairRegs &r, u64 L, int s, int c1, int c2) {
+  const int idx = c1 * 4 + c2;
+  const u64 *sb = ix.pair_sb + (L >> CFR_PAIR_SB_SHIFT) * 20;
+  const u64 below = (1ull << s) - 1ull;
+  PairQuery q;
+#if defined(__CUDA_ARCH__)
+  if (COOP) {
+    const int lane = threadIdx.x & 31, sub = lane & 3, base = lane & ~3;
+    const unsigned gmask = 0xfu << base;
+    // lane 0 holds the planes
+    const u64 m1 = pair_match(r.a, r.b, c1), m12 = m1 & pair_match(r.c, r.d, c2);
+    const u32 packed = (u32)popc64(m1 & below) | ((u32)popc64(m12 & below) << 8) |
+                       ((u32)(((r.a >> s) & 1ull) | (((r.b >> s) & 1ull) << 1)) << 16) |
+                       ((u32)(((r.c >> s) & 1ull) | (((r.d >> s) & 1ull) << 1)) << 18);
+    // lanes 1, 2: pair counter idx is in word (idx >> 1) & 3 of lane 1 + (idx >> 3); lane 3: S[c1] in word c1 >> 1
+    const int wsel = sub == 3 ? (c1 >> 1) : ((idx >> 1) & 3);
+    const u64 wv = wsel == 0 ? r.a : wsel == 1 ? r.b : wsel == 2 ? r.c : r.d;
+    const int half = sub == 3 ? (c1 & 1) : (idx & 1);
+    const u32 field = (u32)(half ? (wv >> 32) : wv);
+    const u32 v0 = __shfl_sync(gmask, packed, base);
+    const u32 vp = __shfl_sync(gmask, field, base + 1 + (idx >> 3));
+    const u32 vs = __shfl_sync(gmask, field, base + 3);
+    q.s1 = ld64(sb + 16 + c1) + (u64)vs + (u64)(v0 & 0xffu);
+    q.p = ld64(sb + idx) + (u64)vp + (u64)((v0 >> 8) & 0xffu);
+    q.sym1 = (int)((v0 >> 16) & 3u);
+    q.sym2 = (int)((v0 >> 18) & 3u);
+    return q;
+  }
+#endif
+  const u64 m1 = pair_match(r.a, r.b, c1), m12 = m1 & pair_match(r.c, r.d, c2);
+  const u64 pw = ld64(r.w + 4 + (idx >> 1)), sw = ld64(r.w + 12 + (c1 >> 1));
+  q.s1 = ld64(sb + 16 + c1) + (u64)(u32)((c1 & 1) ? (sw >> 32) : sw) + (u64)popc64(m1 & below);
+  q.p = ld64(sb + idx) + (u64)(u32)((idx & 1) ? (pw >> 32) : pw) + (u64)popc64(m12 & below);
+  q.sym1 = (int)(((r.a >> s) & 1ull) | (((r.b >> s) & 1ull) << 1));
+  q.sym2 = (int)(((r.c >> s) & 1ull) | (((r.d >> s) & 1ull) << 1));
+  return q;
+}
+
+// ---- building the pair lines at load time, from the occ sectors (which k_transcode derived from the
+// run-block arrays with the literal Sequence_RunBlock::Rank / Access)
+// planes of line L: code1 = B[i], code2 = B[img(i)] for the rows i of the line
+CFR_HD void pair_line_planes(const DevIndex &ix, u64 L, u64 &a, u64 &b, u64 &c, u64 &d) {
+  a = b = c = d = 0;
+  const u64 p0 = L * 64;
+  if (p0 >= ix.n) return;
+  u64 lo, hi, w2, w3;
+  occ_load<0>(ix.occ + L, lo, hi, w2, w3);
+  for (int w = 0; w < 64; ++w) {
+    const u64 pos = p0 + (u64)w;
+    if (pos >= ix.n) break;
+    const int c1 = occ_symbol(lo, hi, w);
+    const u64 occ = occ_base(w2, w3, c1, L) + (u64)popc64(occ_match(lo, hi, c1) & ((1ull << w) - 1ull));
+    const u64 img = ix.C[c1] + occ + ((c1 == ix.last_code && pos <= ix.first_isa) ? 1ull : 0ull);
+    int c2 = 0;
+    if (img < ix.n) {
+      const u64x2 pl = ld128(reinterpret_cast<const u64x2 *>(ix.occ + (img >> 6)));
+      c2 = occ_symbol(pl.x, pl.y, (int)(img & 63));
+    }
+    a |= (u64)(c1 & 1) << w;
+    b |= (u64)(c1 >> 1) << w;
+    c |= (u64)(c2 & 1) << w;
+    d |= (u64)(c2 >> 1) << w;
+  }
+}
+
+// rows of one line per pair (cnt[0..15]) and per code1 (cnt[16..19]); `valid` = mask of the rows below n
+CFR_HD void pair_line_counts(u64 a, u64 b, u64 c, u64 d, u64 valid, u32 *cnt) {
+  for (int c1 = 0; c1 < 4; ++c1) {
+    const u64 m1 = pair_match(a, b, c1) & valid;
+    cnt[16 + c1] = (u32)popc64(m1);
+    for (int c2 = 0; c2 < 4; ++c2) cnt[c1 * 4 + c2] = (u32)popc64(m1 & pair_match(c, d, c2));
+  }
+}
+
+CFR_HD u64 pair_valid_mask(const DevIndex &ix, u64 L) {
+  const u64 p0 = L * 64;
+  if (p0 >= ix.n) return 0;
+  const u64 left = ix.n - p0;
+  return left >= 64 ? ~0ull : ((1ull << left) - 1ull);
+}
+
+enum { CFR_PAIR_CHUNK = 64 };  // lines per chunk of the counter prefix passes
+
+// pass A: planes of every line of a chunk + the chunk's totals, tot[k * n_chunk + chunk]
+CFR_HD void pair_chunk_planes(const DevIndex &ix, PairLine *lines, u64 n_lines, u64 chunk, u64 *tot, u64 n_chunk) {
+  u64 sum[20];
+  for (int k = 0; k < 20; ++k) sum[k] = 0;
+  for (u64 L = chunk * CFR_PAIR_CHUNK; L < (chunk + 1) * CFR_PAIR_CHUNK && L < n_lines; ++L) {
+    u64 a, b, c, d;
+    pair_line_planes(ix, L, a, b, c, d);
+    lines[L].w[0] = a;
+    lines[L].w[1] = b;
+    lines[L].w[2] = c;
+    lines[L].w[3] = d;
+    u32 cnt[20];
+    pair_line_counts(a, b, c, d, pair_valid_mask(ix, L), cnt);
+    for (int k = 0; k < 20; ++k) sum[k] += cnt[k];
+  }
+  for (int k = 0; k < 20; ++k) tot[(u64)k * n_chunk + chunk] = sum[k];
+}
+
+// pass B (after the exclusive scan of tot over the chunks and the superblock table): the counters of every line
+CFR_HD void pair_chunk_counters(const DevIndex &ix, PairLine *lines, u64 n_lines, u64 chunk, const u64 *tot, u64 n_chunk,
+                                const u64 *sb_table) {
+  u64 run[20];
+  const u64 L0 = chunk * CFR_PAIR_CHUNK;
+  const u64 *sb = sb_table + (L0 >> CFR_PAIR_SB_SHIFT) * 20;  // a chunk never straddles a superblock
+  for (int k = 0; k < 20; ++k) run[k] = tot[(u64)k * n_chunk + chunk] - sb[k];
+  for (u64 L = L0; L < L0 + CFR_PAIR_CHUNK && L < n_lines; ++L) {
+    u64 *w = lines[L].w;
+    for (int k = 0; k < 10; ++k) w[4 + k] = (run[2 * k] & 0xffffffffull) | (run[2 * k + 1] << 32);
+    w[14] = 0;
+    w[15] = 0;
+    u32 cnt[20];
+    pair_line_counts(w[0], w[1], w[2], w[3], pair_valid_mask(ix, L), cnt);
+    for (int k = 0; k < 20; ++k) run[k] += cnt[k];
+  }
+}
+
+// the constants of the second step: out[c1*4+c2] = D, out[16] = E, out[17] = F (see the derivation above)
+CFR_HD void pair_constants(const DevIndex &ix, u64 *out) {
+  for (int c1 = 0; c1 < 4; ++c1)
+    for (int c2 = 0; c2 < 4; ++c2) out[c1 * 4 + c2] = occ_rank<0>(ix, c2, ix.C[c1]).count;
+  const int lc = ix.last_code;
+  {
+    const u64 r = ix.C[lc];
+    const u64x2 pl = ld128(reinterpret_cast<const u64x2 *>(ix.occ + (r >> 6)));
+    out[16] = (u64)occ_symbol(pl.x, pl.y, (int)(r & 63));
+  }
+  {
+    const u64 img = ix.C[lc] + occ_rank<0>(ix, lc, ix.first_isa).count + 1ull;
+    u64 f = 0;
+    if (img < ix.n) {
+      const u64x2 pl = ld128(reinterpret_cast<const u64x2 *>(ix.occ + (img >> 6)));
+      f = (u64)occ_symbol(pl.x, pl.y, (int)(img & 63));
+    }
+    out[17] = f;
+  }
+}
+
+// Two steps of FMIndex::BackwardSearch's loop (FMIndex.hpp:495-508) from the range [sp, ep]: first c1,
+// then -- if c2 >= 0 -- c2.  Returns how many succeeded (0, 1, 2) and leaves the range after the last
+// successful one in (sp, ep).  The operation counters advance as the reference's calls would.
+template <bool COOP>
+struct BwtPairT {
+  typedef u64 pos_t;
+  enum { LANES = COOP ? 4 : 1, PAIR = 1, STEPS_COUNTED_AT_CLOSE = 0 };
+  static CFR_HD bool leader() {
+#if defined(__CUDA_ARCH__)
+    return !COOP || (threadIdx.x & 3) == 0;
+#else
+    return true;
+#endif
+  }
+  // single-step form: not used by the search loop of a pair policy (Bwt::PAIR selects extend2)
+  static CFR_HD void extend_step(const DevIndex &ix, int c, u64 sp, u64 ep, u64 &nsp, u64 &nep, OpCount &oc) {
+    nsp = sp;
+    nep = ep;
+    if (extend2(ix, c, -1, nsp, nep, oc) == 0) {
+      nsp = 1;
+      nep = 0;
+    }
+  }
+  static CFR_HD int extend2(const DevIndex &ix, int c1, int c2, u64 &sp, u64 &ep, OpCount &oc) {
+    const bool two = c2 >= 0;
+    const int c2q = two ? c2 : 0;
+    const bool range = sp != ep;
+    const u64 xe = ep + 1;
+    const u64 La = sp >> 6, Le = xe >> 6;
+    const PairRegs ra = pair_load<COOP>(ix, La);
+    // the second boundary mostly lies in the line just fetched; all lanes of a group agree on `far`
+    const bool far = range && Le != La;
+    PairRegs re = ra;
+    if (far) re = pair_load<COOP>(ix, Le);
+    const PairQuery qa = pair_eval<COOP>(ix, ra, La, (int)(sp & 63), c1, c2q);
+    PairQuery qe = qa;
+    if (range) qe = pair_eval<COOP>(ix, re, Le, (int)(xe & 63), c1, c2q);
+    const u64 fisa = ix.first_isa;
+    const bool l1 = c1 == ix.last_code;
+    ++oc.xext;
+    oc.xsingle += range ? 0u : 1u;
+    const u64 y1 = ix.C[c1] + qa.s1 + ((l1 && sp <= fisa) ? 1ull : 0ull);
+    const u64 y2 = range ? ix.C[c1] + qe.s1 + ((l1 && xe <= fisa) ? 1ull : 0ull) - 1ull
+                         : y1 + ((qa.sym1 == c1) ? 0ull : ~0ull);
+    if (y1 > y2 || y2 > ix.n) return 0;
+    if (!two) {
+      sp = y1;
+      ep = y2;
+      return 1;
+    }
+    const bool l2 = c2 == ix.last_code;
+    const int idx = c1 * 4 + c2;
+    const u64 g0 = ix.C[c2] + ix.pair_D[idx];
+    const u64 e_add = (l1 && ix.pair_E == c2) ? 1ull : 0ull;
+    const u64 f_sub = (l1 && ix.pair_F == c2) ? 1ull : 0ull;
+    const bool range2 = y1 != y2;
+    ++oc.xext;
+    oc.xsingle += range2 ? 0u : 1u;
+    const u64 z1 = g0 + qa.p + e_add - (sp > fisa ? f_sub : 0ull) + ((l2 && y1 <= fisa) ? 1ull : 0ull);
+    u64 z2;
+    if (range) {
+      const u64 Y = y2 + 1;  // = step(c1, ep + 1)
+      z2 = g0 + qe.p + e_add - (xe > fisa ? f_sub : 0ull) + ((l2 && Y <= fisa) ? 1ull : 0ull) - 1ull;
+      if (!range2 && l2 && y1 == fisa) z2 += 1;  // single row y1: the reference tests B[y1] instead of ranking
+    } else {
+      z2 = z1 + ((qa.sym2 == c2) ? 0ull : ~0ull);  // code2(sp) = B[y1]
+    }
+    sp = y1;
+    ep = y2;
+    if (z1 > z2 || z2 > ix.n) return 1;
+    sp = z1;
+    ep = z2;
+    return 2;
+  }
 };
 
 // largest row count the 32-bit walkers accept

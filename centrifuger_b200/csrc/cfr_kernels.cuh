@@ -206,6 +206,58 @@ __global__ void __launch_bounds__(128) k_transcode(const __grid_constant__ DevIn
   }
 }
 
+// Pair lines at load time (cfr_core.cuh, layout 3): planes of every line, totals per chunk of 64 lines,
+// [exclusive scan of the totals on the host side of the launch sequence], superblock table, counters
+__global__ void __launch_bounds__(128) k_pair_planes(const __grid_constant__ DevIndex ix, PairLine *lines, u64 n_lines) {
+  const u64 stride = (u64)gridDim.x * blockDim.x;
+  for (u64 L = (u64)blockIdx.x * blockDim.x + threadIdx.x; L < n_lines; L += stride) {
+    u64 a, b, c, d;
+    pair_line_planes(ix, L, a, b, c, d);
+    u64 *w = lines[L].w;
+    w[0] = a;
+    w[1] = b;
+    w[2] = c;
+    w[3] = d;
+  }
+}
+
+__global__ void __launch_bounds__(128) k_pair_totals(const __grid_constant__ DevIndex ix, const PairLine *lines, u64 n_lines,
+                                                     u64 *tot, u64 n_chunk) {
+  const u64 stride = (u64)gridDim.x * blockDim.x;
+  for (u64 ch = (u64)blockIdx.x * blockDim.x + threadIdx.x; ch < n_chunk; ch += stride) {
+    u64 sum[20];
+#pragma unroll
+    for (int k = 0; k < 20; ++k) sum[k] = 0;
+    for (u64 L = ch * CFR_PAIR_CHUNK; L < (ch + 1) * CFR_PAIR_CHUNK && L < n_lines; ++L) {
+      const u64 *w = lines[L].w;
+      u32 cnt[20];
+      pair_line_counts(w[0], w[1], w[2], w[3], pair_valid_mask(ix, L), cnt);
+#pragma unroll
+      for (int k = 0; k < 20; ++k) sum[k] += cnt[k];
+    }
+#pragma unroll
+    for (int k = 0; k < 20; ++k) tot[(u64)k * n_chunk + ch] = sum[k];
+  }
+}
+
+__global__ void k_pair_sb(const u64 *tot, u64 n_chunk, u64 *sb_table, u64 n_sb) {
+  const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_sb * 20) return;
+  const u64 sb = t / 20, k = t % 20;
+  sb_table[t] = tot[k * n_chunk + ((sb << CFR_PAIR_SB_SHIFT) / CFR_PAIR_CHUNK)];
+}
+
+__global__ void __launch_bounds__(128) k_pair_counters(const __grid_constant__ DevIndex ix, PairLine *lines, u64 n_lines,
+                                                       const u64 *tot, u64 n_chunk, const u64 *sb_table) {
+  const u64 stride = (u64)gridDim.x * blockDim.x;
+  for (u64 ch = (u64)blockIdx.x * blockDim.x + threadIdx.x; ch < n_chunk; ch += stride)
+    pair_chunk_counters(ix, lines, n_lines, ch, tot, n_chunk, sb_table);
+}
+
+__global__ void k_pair_consts(const __grid_constant__ DevIndex ix, u64 *out18) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) pair_constants(ix, out18);
+}
+
 // Wide lookup table at load time: one entry per WW-mer (see wide_lookup_entry)
 template <class Bwt>
 __global__ void __launch_bounds__(128) k_build_wide(const __grid_constant__ DevIndex ix, u64x2 *out, int WW) {

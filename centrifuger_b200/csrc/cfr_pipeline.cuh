@@ -15,6 +15,8 @@
 // simulation harness, where a "warp" is one lane); cfr_kernels.cuh wraps them in __global__ kernels
 // that claim their work dynamically.
 #pragma once
+#include <type_traits>
+
 #include "cfr_core.cuh"
 
 namespace cfrb200 {
@@ -308,6 +310,17 @@ CFR_HD int adaptive_quorum(int quorum, u32 alive_mask, int lanes_per_task) {
 
 enum { CFR_ST_EXTEND = 0, CFR_ST_CLOSE = 1, CFR_ST_FETCH = 2, CFR_ST_DONE = 3 };
 
+// the pair policies implement extend2; the others never reach the call (Bwt::PAIR == 0)
+template <class Bwt>
+CFR_HD typename std::enable_if<(Bwt::PAIR != 0), int>::type pair_extend2(const DevIndex &ix, int c1, int c2, u64 &sp, u64 &ep,
+                                                                         OpCount &oc) {
+  return Bwt::extend2(ix, c1, c2, sp, ep, oc);
+}
+template <class Bwt>
+CFR_HD typename std::enable_if<(Bwt::PAIR == 0), int>::type pair_extend2(const DevIndex &, int, int, u64 &, u64 &, OpCount &) {
+  return 0;
+}
+
 template <class Bwt>
 CFR_HD void search_tasks(const DevIndex &ix, const DevParams &P, const ChunkDev &B, const u64 ntask, OpCount &oc) {
   const int W = ix.pre_width, WW = ix.wide_width, mhl = P.min_hit_len;
@@ -440,7 +453,30 @@ CFR_HD void search_tasks(const DevIndex &ix, const DevParams &P, const ChunkDev 
         }
       }
     }
-    if (st == CFR_ST_EXTEND) {  // one FMIndex::BackwardExtend; l < remaining holds here
+    if (Bwt::PAIR) {
+      if (st == CFR_ST_EXTEND) {  // up to two FMIndex::BackwardExtend steps from one line per boundary
+        const int c1 = s.peek();  // the cursor stands on strand position remaining - 1 - l
+        st = CFR_ST_CLOSE;
+        if (c1 <= 3) {
+          int c2 = -1;
+          const bool have2 = l + 1 < remaining;
+          if (have2) {
+            s.advance();
+            c2 = s.peek();
+            if (c2 > 3) c2 = -1;  // the search ends on this base (FMIndex.hpp:500)
+          }
+          u64 psp = (u64)sp, pep = (u64)ep;
+          const int done = pair_extend2<Bwt>(ix, c1, c2, psp, pep, oc);
+          sp = (pos_t)psp;
+          ep = (pos_t)pep;
+          l += done;
+          if (done == 2 && l < remaining) {
+            st = CFR_ST_EXTEND;
+            s.advance();
+          }
+        }
+      }
+    } else if (st == CFR_ST_EXTEND) {  // one FMIndex::BackwardExtend; l < remaining holds here
       const int c = s.peek();   // the cursor stands on strand position remaining - 1 - l
       st = CFR_ST_CLOSE;
       if (c <= 3) {

@@ -45,6 +45,21 @@ struct alignas(32) OccLine {
   u64 lo, hi, w2, w3;
 };
 
+// One 128-byte line of the PAIR layout (two BackwardExtend steps per DRAM line): 64 BWT rows.
+// code1 = the row's own symbol B[i]; code2 = B[img(i)], the symbol of the row that i maps to when it
+// is extended by its own symbol: img(i) = C[code1] + occ(code1, i) + FMIndex::Rank's correction.
+//   w[0..3]    bit planes: code1 low, code1 high, code2 low, code2 high
+//   w[4..11]   P[c1*4+c2]: rows before this line whose (code1, code2) is that pair; 32 bits each (pair 2k in
+//              the low half of w[4+k], pair 2k+1 in the high half), relative to the line's superblock
+//   w[12..13]  S[c1]: rows before this line with code1 = c1, stored the same way
+//   w[14..15]  unused
+// Four adjacent lanes fetch the line as ONE coalesced 128-byte request (32 bytes each): lane 0 the planes,
+// lanes 1 and 2 the pair counters of c1 = 0,1 / 2,3, lane 3 the single counters.
+struct alignas(128) PairLine {
+  u64 w[16];
+};
+#define CFR_PAIR_SB_SHIFT 26  // lines per superblock (2^32 rows): the 32-bit counters are relative to it
+
 struct DevIndex {
   // FM-index scalars (FMIndex.hpp:191-199)
   u64 n;
@@ -76,6 +91,12 @@ struct DevIndex {
   // {sp, ep | l << 56}: l < WW means the search ended inside them (l = W - 1: empty W-mer)
   int wide_width;  // 0 = none
   const u64x2 *wide;
+  // optional pair layout (nullptr when not built): k_search then does two BackwardExtend steps per line
+  const PairLine *pairs;
+  const u64 *pair_sb;  // [superblock][20]: absolute P[16] then S[4] at the superblock's first line
+  u64 pair_D[16];      // D[c1*4+c2] = # of c2 among the rows below C[c1]
+  int pair_E;          // B[C[last_code]]: the symbol at the row the virtual '$' row maps to
+  int pair_F;          // code2 of row first_isa
   // optional dense locate table, built at load by running FMIndex::BackwardToSampledSA once from
   // every row that is a multiple of 2^dense_shift: dense[row >> dense_shift] = its sequence id.  A walk
   // that reaches such a row ends there with the answer the reference's longer walk would find.

@@ -24,6 +24,9 @@ struct HostIndex {
   std::vector<unsigned char> rank;
   std::vector<u64> sel_filter;
   std::vector<OccLine> occ;
+  std::vector<PairLine> pairs;  // layout 4: the search stage walks pair lines (two extends per line)
+  std::vector<u64> pair_sb;
+  bool use_pairs = false;
   std::vector<u64x2> wide;
   std::vector<u32> dense;
   bool pos32 = false;
@@ -119,7 +122,9 @@ void *hostsim_open(const char *prefix, const cfr_params *p) {
   init_tax_rank_num(ix.rank_num);
   // layout 2 = occ sectors (32-bit positions when the index allows, as the library does), 3 = occ
   // sectors with 64-bit positions forced, anything else = the run-block arrays
-  h->layout = p->layout == CFR_LAYOUT_OCCLINE ? 2 : (p->layout == 3 ? 3 : 1);
+  // 4 = occ sectors + pair lines for the search stage
+  h->use_pairs = p->layout == 4;
+  h->layout = (p->layout == CFR_LAYOUT_OCCLINE || p->layout == 4) ? 2 : (p->layout == 3 ? 3 : 1);
   h->pos32 = h->layout == 2 && f.n < CFR_POS32_MAX_N;
   if (h->layout == 3) h->layout = 2;
   if (h->layout == 2) {  // same construction the transcode kernel performs
@@ -138,6 +143,32 @@ void *hostsim_open(const char *prefix, const cfr_params *p) {
       h->occ[L] = occ_pack(lo, hi, cnt[0], cnt[1], cnt[2]);
     }
     ix.occ = h->occ.data();
+  }
+  if (h->use_pairs) {  // the passes of the library's load-time kernels, run as loops
+    const u64 n_lines = f.n / 64 + 1, n_chunk = (n_lines + CFR_PAIR_CHUNK - 1) / CFR_PAIR_CHUNK;
+    h->pairs.resize(n_lines);
+    std::vector<u64> tot(20 * n_chunk);
+    for (u64 c = 0; c < n_chunk; ++c) pair_chunk_planes(ix, h->pairs.data(), n_lines, c, tot.data(), n_chunk);
+    for (int k = 0; k < 20; ++k) {
+      u64 run = 0;
+      for (u64 c = 0; c < n_chunk; ++c) {
+        const u64 x = tot[(u64)k * n_chunk + c];
+        tot[(u64)k * n_chunk + c] = run;
+        run += x;
+      }
+    }
+    const u64 n_sb = ((n_lines - 1) >> CFR_PAIR_SB_SHIFT) + 1;
+    h->pair_sb.assign(20 * n_sb, 0);
+    for (u64 sb = 0; sb < n_sb; ++sb)
+      for (int k = 0; k < 20; ++k) h->pair_sb[sb * 20 + k] = tot[(u64)k * n_chunk + ((sb << CFR_PAIR_SB_SHIFT) / CFR_PAIR_CHUNK)];
+    for (u64 c = 0; c < n_chunk; ++c) pair_chunk_counters(ix, h->pairs.data(), n_lines, c, tot.data(), n_chunk, h->pair_sb.data());
+    ix.pairs = h->pairs.data();
+    ix.pair_sb = h->pair_sb.data();
+    u64 k18[18];
+    pair_constants(ix, k18);
+    for (int i = 0; i < 16; ++i) ix.pair_D[i] = k18[i];
+    ix.pair_E = (int)k18[16];
+    ix.pair_F = (int)k18[17];
   }
   ix.dense_shift = -1;
   if (const char *e = getenv("HOSTSIM_DENSE_LOCATE")) {  // the library's dense locate table
@@ -171,6 +202,69 @@ void *hostsim_open(const char *prefix, const cfr_params *p) {
 }
 
 void hostsim_close(void *hh) { delete (HostIndex *)hh; }
+
+// Pair layout against the literal steps: for every boundary x and symbol pair, step(c2, step(c1, x)) from
+// the pair line equals two FMIndex::Rank-based steps; and for `n_ranges` pseudo-random ranges (single rows,
+// narrow and wide ranges, ranges around firstISA and the ends) extend2 equals two literal
+// BackwardExtend calls with their stop tests.  Returns the number of disagreements.
+u64 hostsim_pair_check(void *hh, u64 n_ranges, u64 seed) {
+  HostIndex *h = (HostIndex *)hh;
+  const DevIndex &ix = h->ix;
+  if (!ix.pairs) return ~0ull;
+  u64 bad = 0;
+  OpCount oc{}, oc2{};
+  auto literal = [&](int c, u64 sp, u64 ep, u64 &nsp, u64 &nep) {
+    BwtOccLine::extend(ix, c, sp, ep, nsp, nep, oc);
+    return !(nsp > nep || nep > ix.n);
+  };
+  auto one = [&](u64 sp, u64 ep) {
+    for (int c1 = 0; c1 < 4; ++c1)
+      for (int c2 = -1; c2 < 4; ++c2) {
+        u64 y1, y2, z1 = 0, z2 = 0;
+        int want = 0;
+        u64 wsp = sp, wep = ep;
+        if (literal(c1, sp, ep, y1, y2)) {
+          want = 1;
+          wsp = y1;
+          wep = y2;
+          if (c2 >= 0 && literal(c2, y1, y2, z1, z2)) {
+            want = 2;
+            wsp = z1;
+            wep = z2;
+          }
+        }
+        u64 gsp = sp, gep = ep;
+        const int got = BwtPairT<false>::extend2(ix, c1, c2, gsp, gep, oc2);
+        if (got != want || (want > 0 && (gsp != wsp || gep != wep))) ++bad;
+      }
+  };
+  // every boundary as a single row and as the low end of short ranges
+  for (u64 x = 0; x < ix.n; ++x) {
+    one(x, x);
+    if (x + 1 < ix.n) one(x, x + 1);
+    if (x + 5 < ix.n && (x % 7) == 0) one(x, x + 5);
+  }
+  u64 st = seed * 0x9E3779B97F4A7C15ull + 1;
+  auto rnd = [&]() {
+    st ^= st << 13;
+    st ^= st >> 7;
+    st ^= st << 17;
+    return st;
+  };
+  for (u64 i = 0; i < n_ranges; ++i) {
+    u64 a = rnd() % ix.n, len = (i & 3) == 0 ? rnd() % ix.n : rnd() % 300;
+    if ((i & 15) == 1) a = ix.first_isa > 100 ? ix.first_isa - rnd() % 100 : 0;
+    u64 b = a + len;
+    if (b >= ix.n) b = ix.n - 1;
+    one(a, b);
+  }
+  one(0, ix.n - 1);
+  // the counters advance as the literal calls do
+  oc_fold(oc);
+  oc_fold(oc2);
+  if (oc.rank != oc2.rank || oc.access != oc2.access || oc.extend != oc2.extend) ++bad;
+  return bad;
+}
 
 int hostsim_min_hit_len(void *hh) { return ((HostIndex *)hh)->P.min_hit_len; }
 
@@ -353,7 +447,8 @@ int hostsim_classify_expanded(void *hh, int dust, uint64_t arena_rows, const cfr
   u64 task_counter = 0, row_counter = 0;
   B.task_counter = &task_counter;
   B.row_counter = &row_counter;
-  if (h->layout == 2 && h->pos32) search_tasks<BwtOccLine32T<0>>(ix, P, B, n * S, oc);
+  if (h->use_pairs) search_tasks<BwtPairT<false>>(ix, P, B, n * S, oc);
+  else if (h->layout == 2 && h->pos32) search_tasks<BwtOccLine32T<0>>(ix, P, B, n * S, oc);
   else if (h->layout == 2) search_tasks<BwtOccLine>(ix, P, B, n * S, oc);
   else search_tasks<BwtRunBlock>(ix, P, B, n * S, oc);
   B.read_list = nullptr;

@@ -98,6 +98,8 @@ def lib():
         L.hostsim_bwt_access.argtypes = [C.c_void_p, C.c_uint64]
         L.hostsim_locate.restype = C.c_uint64
         L.hostsim_locate.argtypes = [C.c_void_p, C.c_uint64]
+        L.hostsim_pair_check.restype = C.c_uint64
+        L.hostsim_pair_check.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64]
         L.hostsim_reduce_taxids.restype = C.c_int
         L.hostsim_reduce_taxids.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.c_int, C.c_int, C.POINTER(C.c_uint64)]
         L.hostsim_expand_taxids.restype = C.c_int
@@ -160,6 +162,10 @@ class HostSim:
 
     def locate(self, row):
         return self.L.hostsim_locate(self.h, row)
+
+    def pair_check(self, n_ranges=20000, seed=1):
+        """disagreements between the pair layout's two-step extend and two literal BackwardExtend calls"""
+        return int(self.L.hostsim_pair_check(self.h, n_ranges, seed))
 
     def reduce_taxids(self, tax_ids, k):
         arr = (C.c_uint64 * len(tax_ids))(*tax_ids)

@@ -23,12 +23,17 @@ VARIANTS = {"default": {}, "pos64": {"CFR_B200_POS64": "1"}, "pos64_ld128": {"CF
             "ld128": {"CFR_B200_OCC_LOAD": "0"}, "noscreen": {"CFR_B200_DUST_SCREEN": "0"},
             "wide12": {"CFR_B200_WIDE_LOOKUP": "12"}, "wide11_pos64": {"CFR_B200_WIDE_LOOKUP": "11", "CFR_B200_POS64": "1"},
             "literal": {"CFR_B200_DENSE_LOCATE": "-1"}, "dense1_pos64": {"CFR_B200_DENSE_LOCATE": "1", "CFR_B200_POS64": "1"},
-            "dense3": {"CFR_B200_DENSE_LOCATE": "3"}, "dense2_ld128": {"CFR_B200_DENSE_LOCATE": "2", "CFR_B200_OCC_LOAD": "0"}}
+            "dense3": {"CFR_B200_DENSE_LOCATE": "3"}, "dense2_ld128": {"CFR_B200_DENSE_LOCATE": "2", "CFR_B200_OCC_LOAD": "0"},
+            # the pair lines (two BackwardExtend steps per 128-byte line, four lanes per strand task) in k_search
+            "pairs": {"CFR_B200_PAIRS": "1"}, "pairs_pos64_literal": {"CFR_B200_PAIRS": "1", "CFR_B200_POS64": "1",
+                                                                      "CFR_B200_DENSE_LOCATE": "-1"},
+            "pairs_wide12_sb10": {"CFR_B200_PAIRS": "1", "CFR_B200_WIDE_LOOKUP": "12", "CFR_B200_PAIR_SEARCH_BLOCKS": "10"}}
 
 
 @pytest.fixture(params=sorted(VARIANTS))
 def variant_env(request, monkeypatch):
-    for k in ("CFR_B200_POS64", "CFR_B200_OCC_LOAD", "CFR_B200_DUST_SCREEN", "CFR_B200_WIDE_LOOKUP", "CFR_B200_DENSE_LOCATE"):
+    for k in ("CFR_B200_POS64", "CFR_B200_OCC_LOAD", "CFR_B200_DUST_SCREEN", "CFR_B200_WIDE_LOOKUP", "CFR_B200_DENSE_LOCATE",
+              "CFR_B200_PAIRS", "CFR_B200_PAIR_SEARCH_BLOCKS"):
         monkeypatch.delenv(k, raising=False)
     for k, v in VARIANTS[request.param].items():
         monkeypatch.setenv(k, v)  # read by cfr_open
@@ -333,12 +338,14 @@ def test_kernel_variants_vs_oracle(small_dir, variant_env):
         assert _tuples(res, ids, g.k) == exp, (variant_env, kw)
         c = g.counters()
         assert c["n_search"] == oc["n_search"] and c["n_locate"] == oc["n_locate"], (variant_env, kw)
-        if variant_env == "literal":  # no load-time table skips a step: every count equals the oracle's
+        if variant_env in ("literal", "pairs_pos64_literal"):  # no load-time table skips a step: every count equals the oracle's
             for key in ("n_rank", "n_access", "n_lf", "n_extend"):
                 assert c[key] == oc[key], (variant_env, kw, key)
         else:  # the dense locate table (default) shortens LF walks, the wide lookup table skips extends
             assert c["n_lf"] < oc["n_lf"] and c["n_rank"] < oc["n_rank"], (variant_env, kw)
-            assert (c["n_extend"] < oc["n_extend"]) == variant_env.startswith("wide"), (variant_env, kw)
+            assert (c["n_extend"] < oc["n_extend"]) == ("wide" in variant_env), (variant_env, kw)
+        if variant_env.startswith("pairs"):
+            assert g.info(23) > 0  # the pair lines were built and k_search walked them
         g.close()
 
 

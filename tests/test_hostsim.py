@@ -38,7 +38,20 @@ def _compare(idx, files, layout, arena_rows=0, limit=None, check_counters=True, 
         o.close()
 
 
-@pytest.mark.parametrize("layout", [1, 2, 3])  # 3 = occ sectors walked with 64-bit positions
+@pytest.mark.parametrize("variant", ["idx", "idx_b1", "idx_b8", "idx_off3"])
+def test_pair_layout_two_steps_equal_two_literal_extends(tiny_dir, variant):
+    """The pair lines (two BackwardExtend steps per 128-byte line, cfr_core.cuh) against the literal
+    steps: every BWT row as a single-row range and as the low end of short ranges, 20 000 random
+    ranges (wide, narrow, around firstISA), every symbol pair and the one-symbol form; results, stop
+    tests and operation counters must agree."""
+    hs = HostSim(os.path.join(tiny_dir, variant), layout=4)
+    try:
+        assert hs.pair_check(20000, 7) == 0
+    finally:
+        hs.close()
+
+
+@pytest.mark.parametrize("layout", [1, 2, 3, 4])  # 3 = occ sectors walked with 64-bit positions, 4 = pair lines in the search
 @pytest.mark.parametrize("variant", ["idx", "idx_b1", "idx_b8", "idx_off3"])
 def test_tiny_all_read_sets(tiny_dir, layout, variant):
     idx = os.path.join(tiny_dir, variant)
