@@ -61,6 +61,7 @@ ABI_SYMBOLS = [
     "cfr_fetch_expanded", "cfr_batch_fetch_expanded",
     "cfr_host_alloc", "cfr_host_free", "cfr_index_info", "cfr_seq_name", "cfr_rank_name", "cfr_orig_taxid", "cfr_seq_taxid",
     "cfr_format_tsv", "cfr_taxon_counts_device", "cfr_taxon_counts_read", "cfr_taxon_counts_reset",
+    "cfr_counts_allreduce", "cfr_counts_allreduce_local",
     "cfr_get_counters", "cfr_reset_counters", "cfr_set_profiling", "cfr_get_stage_times",
     "cfr_get_stage_counters", "cfr_debug_bwt_rank", "cfr_debug_bwt_access",
     "cfr_debug_locate", "cfr_debug_dust",

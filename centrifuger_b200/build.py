@@ -66,7 +66,7 @@ def build(force=False, verbose=False):
         # one shared object, cudart linked statically (nvcc default)
         objs = _compile_objects([os.path.join(CSRC, "cfr_api.cu"), os.path.join(CSRC, "cfr_build.cu"),
                                  os.path.join(CSRC, "cfr_format.cpp")], verbose)
-        cmd = [_nvcc(), "-shared", "-o", LIB] + objs
+        cmd = [_nvcc(), "-shared", "-o", LIB] + objs + ["-ldl"]
         if verbose:
             print(" ".join(cmd))
         subprocess.check_call(cmd)

@@ -1,6 +1,7 @@
 // cfr_api.cu -- the C ABI of include/centrifuger_b200.h: index load into HBM,
 // batch pipeline orchestration, result hand-back.  Host C++ + CUDA runtime only.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <cub/device/device_scan.cuh>
 
@@ -105,6 +106,7 @@ struct cfr_handle {
   int dust_lanes = 16;  // lanes per warp that take mates in the post-screen SDUST launch (CFR_B200_DUST_LANES)
   bool dust_screen = true;  // register-only screen in front of the full SDUST (CFR_B200_DUST_SCREEN=0 disables)
   u64 *d_taxon = nullptr;
+  u64 *d_taxon_reduced = nullptr;  // snapshot the NCCL all-reduce works on
   DevCounters *d_counters = nullptr;
   u64 launches = 0;
   u64 host_bases = 0;
@@ -1286,6 +1288,123 @@ int cfr_taxon_counts_reset(cfr_handle *h, void *stream) {
   if (!h) return fail(CFR_ERR_ARG, "null argument");
   CUDA_TRY(cudaSetDevice(h->device));
   CUDA_TRY(cudaMemsetAsync(h->d_taxon, 0, (h->ix.node_cnt + 3) * 8, pick_stream(h, stream)));
+  return CFR_OK;
+}
+
+// ---------------------------------------------------------------------------
+// NCCL: the path's one collective -- SUM all-reduce of the per-taxon assignment counters, once, after the last
+// batch.  libnccl is loaded at run time (dlopen): the library itself has no link-time
+// dependency on it, and a process that never reduces never needs it.
+// ---------------------------------------------------------------------------
+namespace {
+struct NcclApi {
+  void *lib = nullptr;
+  int (*CommInitAll)(void **, int, const int *) = nullptr;
+  int (*CommDestroy)(void *) = nullptr;
+  int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  const char *(*GetErrorString)(int) = nullptr;
+  bool ok = false;
+};
+NcclApi &nccl_api() {
+  static NcclApi a;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    for (const char *name : {"libnccl.so.2", "libnccl.so"}) {
+      a.lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+      if (a.lib) break;
+    }
+    if (!a.lib) return;
+    a.CommInitAll = (int (*)(void **, int, const int *))dlsym(a.lib, "ncclCommInitAll");
+    a.CommDestroy = (int (*)(void *))dlsym(a.lib, "ncclCommDestroy");
+    a.AllReduce = (int (*)(const void *, void *, size_t, int, int, void *, cudaStream_t))dlsym(a.lib, "ncclAllReduce");
+    a.GroupStart = (int (*)())dlsym(a.lib, "ncclGroupStart");
+    a.GroupEnd = (int (*)())dlsym(a.lib, "ncclGroupEnd");
+    a.GetErrorString = (const char *(*)(int))dlsym(a.lib, "ncclGetErrorString");
+    a.ok = a.CommInitAll && a.CommDestroy && a.AllReduce && a.GroupStart && a.GroupEnd;
+  });
+  return a;
+}
+enum { CFR_NCCL_UINT64 = 5, CFR_NCCL_SUM = 0 };  // ncclUint64, ncclSum (nccl.h)
+
+int nccl_fail(int rc, const char *what) {
+  NcclApi &a = nccl_api();
+  return fail(CFR_ERR_CUDA, std::string(what) + ": " + (a.GetErrorString ? a.GetErrorString(rc) : "NCCL error"));
+}
+
+// snapshot of the live counters, taken after the handle's streams are idle: the copy is what gets reduced
+int snapshot_counts(cfr_handle *h) {
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaDeviceSynchronize());
+  const size_t bytes = (h->ix.node_cnt + 3) * 8;
+  if (!h->d_taxon_reduced) {
+    void *p;
+    int st = dev_alloc(h, &p, bytes);
+    if (st) return st;
+    h->d_taxon_reduced = (u64 *)p;
+  }
+  CUDA_TRY(cudaMemcpyAsync(h->d_taxon_reduced, h->d_taxon, bytes, cudaMemcpyDeviceToDevice, h->stream));
+  return CFR_OK;
+}
+}  // namespace
+
+int cfr_counts_allreduce(cfr_handle *h, void *nccl_comm, uint64_t *out, uint64_t n_entries) {
+  if (!h || !nccl_comm) return fail(CFR_ERR_ARG, "null argument");
+  NcclApi &a = nccl_api();
+  if (!a.ok) return fail(CFR_ERR_UNSUPPORTED, "libnccl.so.2 could not be loaded");
+  int st = snapshot_counts(h);
+  if (st) return st;
+  const size_t cnt = h->ix.node_cnt + 3;
+  int rc = a.AllReduce(h->d_taxon_reduced, h->d_taxon_reduced, cnt, CFR_NCCL_UINT64, CFR_NCCL_SUM, nccl_comm, h->stream);
+  if (rc != 0) return nccl_fail(rc, "ncclAllReduce");
+  if (out) {
+    if (n_entries > cnt) n_entries = cnt;
+    CUDA_TRY(cudaMemcpyAsync(out, h->d_taxon_reduced, n_entries * 8, cudaMemcpyDeviceToHost, h->stream));
+  }
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return CFR_OK;
+}
+
+int cfr_counts_allreduce_local(cfr_handle **handles, int n_handles, uint64_t *out, uint64_t n_entries) {
+  if (!handles || n_handles < 1 || !handles[0]) return fail(CFR_ERR_ARG, "null argument");
+  const size_t cnt = handles[0]->ix.node_cnt + 3;
+  for (int i = 0; i < n_handles; ++i) {
+    if (!handles[i] || handles[i]->ix.node_cnt + 3 != cnt) return fail(CFR_ERR_ARG, "handles do not share one index");
+    int st = snapshot_counts(handles[i]);
+    if (st) return st;
+  }
+  if (n_handles > 1) {
+    NcclApi &a = nccl_api();
+    if (!a.ok) return fail(CFR_ERR_UNSUPPORTED, "libnccl.so.2 could not be loaded");
+    std::vector<void *> comms(n_handles, nullptr);
+    std::vector<int> devs(n_handles);
+    for (int i = 0; i < n_handles; ++i) devs[i] = handles[i]->device;
+    int rc = a.CommInitAll(comms.data(), n_handles, devs.data());
+    if (rc != 0) return nccl_fail(rc, "ncclCommInitAll");
+    rc = a.GroupStart();
+    for (int i = 0; i < n_handles && rc == 0; ++i) {
+      cudaSetDevice(handles[i]->device);
+      rc = a.AllReduce(handles[i]->d_taxon_reduced, handles[i]->d_taxon_reduced, cnt, CFR_NCCL_UINT64, CFR_NCCL_SUM, comms[i],
+                       handles[i]->stream);
+    }
+    const int rc2 = a.GroupEnd();
+    for (int i = 0; i < n_handles; ++i) {
+      cudaSetDevice(handles[i]->device);
+      cudaStreamSynchronize(handles[i]->stream);
+    }
+    for (void *c : comms)
+      if (c) a.CommDestroy(c);
+    if (rc != 0) return nccl_fail(rc, "ncclAllReduce");
+    if (rc2 != 0) return nccl_fail(rc2, "ncclGroupEnd");
+  }
+  if (out) {
+    cfr_handle *h = handles[0];
+    if (n_entries > cnt) n_entries = cnt;
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaMemcpyAsync(out, h->d_taxon_reduced, n_entries * 8, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+  }
   return CFR_OK;
 }
 

@@ -61,13 +61,15 @@ static const char usage[] =
     "\t--hitk-factor INT: resolve at most <int>*k entries for each hit [40; use 0 for no restriction]\n"
     "\t--consider-secondary STR: in the format INT,FLOAT consider the secondary hit if its hitlen>=INT,score>=FLOAT*best_score [2000,0.995]\n"
     "\t--gpu INT: CUDA device ordinal [0]\n"
+    "\t--gpus INT: classify on INT GPUs (devices --gpu .. --gpu + INT - 1): the index is replicated per GPU, batch j goes\n"
+    "\t            to GPU j mod INT, rows stay in input order; the per-taxon counters are summed over NCCL at the end [1]\n"
     "\t--batch INT: reads per GPU batch [1048576]\n"
     "\t--layout STR: in-HBM BWT layout, occ|runblock|auto [auto]\n"
     "\t-h: print this usage message\n"
     "\t-v: print the version information and quit\n";
 
 enum {
-  ARGV_NO_DUST = 256, ARGV_MIN_HITLEN, ARGV_HITK, ARGV_SECONDARY, ARGV_GPU, ARGV_BATCH, ARGV_LAYOUT,
+  ARGV_NO_DUST = 256, ARGV_MIN_HITLEN, ARGV_HITK, ARGV_SECONDARY, ARGV_GPU, ARGV_GPUS, ARGV_BATCH, ARGV_LAYOUT,
   ARGV_UNSUPPORTED, ARGV_DRY_RUN, ARGV_DRY_PIPE, ARGV_UN, ARGV_CL, ARGV_MERGE, ARGV_EXPAND, ARGV_SAMPLE_SHEET, ARGV_DRY_OUT, ARGV_READ_FORMAT, ARGV_BARCODE, ARGV_UMI, ARGV_BC_WHITELIST, ARGV_BC_TRANSLATE
 };
 
@@ -78,6 +80,7 @@ static struct option long_options[] = {
     {"hitk-factor", required_argument, 0, ARGV_HITK},
     {"consider-secondary", required_argument, 0, ARGV_SECONDARY},
     {"gpu", required_argument, 0, ARGV_GPU},
+    {"gpus", required_argument, 0, ARGV_GPUS},
     {"batch", required_argument, 0, ARGV_BATCH},
     {"layout", required_argument, 0, ARGV_LAYOUT},
     {"dry-run", no_argument, 0, ARGV_DRY_RUN},
@@ -257,6 +260,7 @@ int main(int argc, char *argv[]) {
   bool hasWhitelist = false;
   bool hasMate = false, interleaved = false;
   int device = 0;
+  int nGpus = 1;
   long batchReads = 1 << 20;
   const char *unPrefix = NULL, *clPrefix = NULL;  // --un / --cl
   bool mergePairs = false;                        // --merge-readpair
@@ -328,6 +332,7 @@ int main(int argc, char *argv[]) {
       params.consider_secondary_hit_len = len;
       params.consider_secondary_score_factor = f;
     } else if (c == ARGV_GPU) device = atoi(optarg);
+    else if (c == ARGV_GPUS) nGpus = atoi(optarg);
     else if (c == ARGV_BATCH) batchReads = atol(optarg);
     else if (c == ARGV_LAYOUT) {
       if (!strcmp(optarg, "occ")) params.layout = CFR_LAYOUT_OCCLINE;
@@ -446,16 +451,31 @@ int main(int argc, char *argv[]) {
     if (known && bases < 3e9) {
       setenv("CFR_B200_DENSE_LOCATE", "-1", 0);
       setenv("CFR_B200_WIDE_LOOKUP", "0", 0);
+      setenv("CFR_B200_PAIRS", "0", 0);
     }
   }
+  if (nGpus < 1) nGpus = 1;
+  if (nGpus > 64) nGpus = 64;
+  std::vector<cfr_handle *> handles((size_t)nGpus, (cfr_handle *)NULL);  // one replica of the index per GPU
   cfr_handle *h = NULL;
   int st = CFR_OK;
   if (!dryPipe && !dryOut) {
-    st = cfr_open(idxPrefix, &params, device, &h);
-    if (st != CFR_OK) {
-      PrintLog("ERROR: %s", cfr_last_error());
-      return EXIT_FAILURE;
-    }
+    // the replicas load side by side (CentrifugerClass.cpp loads once; here each GPU reads the files from the page cache)
+    std::vector<int> rcs((size_t)nGpus, CFR_OK);
+    std::vector<std::string> errs((size_t)nGpus);
+    std::vector<std::thread> openers;
+    for (int g = 0; g < nGpus; ++g)
+      openers.emplace_back([&, g] {
+        rcs[g] = cfr_open(idxPrefix, &params, device + g, &handles[g]);
+        if (rcs[g] != CFR_OK) errs[g] = cfr_last_error();
+      });
+    for (auto &t : openers) t.join();
+    for (int g = 0; g < nGpus; ++g)
+      if (rcs[g] != CFR_OK) {
+        PrintLog("ERROR: %s", errs[g].c_str());
+        return EXIT_FAILURE;
+      }
+    h = handles[0];
     PrintLog("Finishes loading index.");
     if (params.min_hit_len <= 0) PrintLog("Inferred --min-hitlen: %d", (int)cfr_index_info(h, 4));
   }
@@ -465,9 +485,9 @@ int main(int argc, char *argv[]) {
   // ResultWriter.hpp:199-236; rows in input order as in CentrifugerClass.cpp:690).
   const int k = params.max_result;
   const bool expandTaxid = params.expand_taxid != 0;  // --expand-taxid: one more TSV column
-  enum { NBATCH = 5 };  // ingest (1) + in flight on the GPU (3) + output (1)
-  Batch batches[NBATCH];
-  Slot<Batch *> free_slots[NBATCH];
+  const int NBATCH = 2 + 3 * nGpus;  // ingest (1) + in flight on each GPU (3) + output (1)
+  std::vector<Batch> batches((size_t)NBATCH);
+  std::vector<Slot<Batch *>> free_slots((size_t)NBATCH);
   Slot<Batch *> to_gpu, to_out;
   for (auto &bt : batches) bt.clear();
   unsigned long totalCnt = 0, classifiedCnt = 0;
@@ -823,10 +843,17 @@ int main(int argc, char *argv[]) {
 
   int rc = 0;
   // submitted, not yet waited for: up to two stay behind the batch just submitted (three in flight)
-  std::deque<std::pair<Batch *, int>> pending;
+  struct InFlight {
+    Batch *bt;
+    int ticket;
+    cfr_handle *h;  // the replica the batch went to
+  };
+  std::deque<InFlight> pending;
+  size_t gpuBatchNo = 0;  // batch j is classified on GPU j mod nGpus (CentrifugerClass.cpp:674-691: batches in input order)
   auto retire = [&]() {
-    Batch *pb = pending.front().first;
-    const int tk = pending.front().second;
+    Batch *pb = pending.front().bt;
+    const int tk = pending.front().ticket;
+    cfr_handle *h = pending.front().h;
     pending.pop_front();
     if (tk >= 0 && cfr_wait_batch(h, tk) != CFR_OK) {
       PrintLog("ERROR: %s", cfr_last_error());
@@ -854,6 +881,7 @@ int main(int argc, char *argv[]) {
   for (;;) {
     Batch *bt = to_gpu.take();
     int ticket = -1;
+    cfr_handle *hb = h;
     if (dryOut) {  // no device: the output stage sees every read as unclassified
       bt->results.assign(bt->n, cfr_result());
       bt->assign.assign(bt->n * (size_t)k, 0);
@@ -862,6 +890,8 @@ int main(int argc, char *argv[]) {
       bt->masked1 = bt->seq1;
       bt->masked2 = bt->seq2;
     } else if (rc == 0 && bt->n > 0) {
+      cfr_handle *h = handles[gpuBatchNo++ % handles.size()];
+      hb = h;
       bt->results.resize(bt->n);
       bt->assign.resize(bt->n * (size_t)k);
       cfr_read_batch b;
@@ -887,8 +917,8 @@ int main(int argc, char *argv[]) {
     } else if (rc != 0) {
       bt->n = 0;  // after a device error no batch reaches the output stage unclassified (its result arrays are stale)
     }
-    pending.push_back(std::make_pair(bt, ticket));
-    if (pending.size() > 2) retire();
+    pending.push_back(InFlight{bt, ticket, hb});
+    if (pending.size() > 3 * handles.size() - 1) retire();  // three batches in flight per GPU
     if (bt->last) {
       while (!pending.empty()) retire();
       break;
@@ -907,7 +937,25 @@ int main(int argc, char *argv[]) {
   // ResultWriter::Finalize (ResultWriter.hpp:279-283)
   PrintLog("Processed %lu read fragments, and %lu (%.2lf%%) can be classified.", totalCnt, classifiedCnt,
            (double)classifiedCnt / (double)totalCnt * 100.0);
-  if (h) cfr_close(h);
+  if (h && nGpus > 1) {
+    // the path's one collective: the per-taxon counters of the replicas are summed over NCCL (NVLink); the totals
+    // the log line above printed are checked against the reduced vector's {reads, classified} entries
+    const uint64_t nodeCnt = cfr_index_info(h, 5);
+    std::vector<uint64_t> red(nodeCnt + 3, 0);
+    if (cfr_counts_allreduce_local(handles.data(), nGpus, red.data(), red.size()) != CFR_OK) {
+      PrintLog("ERROR: %s", cfr_last_error());
+      return EXIT_FAILURE;
+    }
+    if (red[nodeCnt + 1] != totalCnt || red[nodeCnt + 2] != classifiedCnt) {
+      PrintLog("WARNING: the counters reduced over %d GPUs (%lu reads, %lu classified) disagree with the rows written.",
+               nGpus, (unsigned long)red[nodeCnt + 1], (unsigned long)red[nodeCnt + 2]);
+    } else {
+      PrintLog("Reduced the per-taxon counters of %d GPUs over NCCL: %lu reads, %lu classified.", nGpus,
+               (unsigned long)red[nodeCnt + 1], (unsigned long)red[nodeCnt + 2]);
+    }
+  }
+  for (cfr_handle *hh : handles)
+    if (hh) cfr_close(hh);
   PrintLog("Centrifuger finishes.");
   return 0;
 }

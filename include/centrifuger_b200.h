@@ -198,6 +198,16 @@ int cfr_taxon_counts_device(cfr_handle *h, void **dev_ptr, uint64_t *n_entries);
 int cfr_taxon_counts_read(cfr_handle *h, uint64_t *out, uint64_t n_entries, void *stream);
 int cfr_taxon_counts_reset(cfr_handle *h, void *stream);
 
+/* The path's one collective: SUM all-reduce of the counter vector over NCCL, once, after the
+ * last batch.  A snapshot of the live counters is reduced, so the handle keeps its own cumulative counts.
+ * libnccl.so.2 is loaded at run time; CFR_ERR_UNSUPPORTED if it is not there.
+ *   cfr_counts_allreduce        one handle per process: `nccl_comm` is the caller's ncclComm_t (MPI / torchrun style);
+ *   cfr_counts_allreduce_local  one process, one handle per GPU (the CLI's --gpus): communicators are made with
+ *                               ncclCommInitAll for the call and the reduction runs grouped over NVLink.
+ * `out` (host, n_entries, may be NULL) receives the global sum. */
+int cfr_counts_allreduce(cfr_handle *h, void *nccl_comm, uint64_t *out, uint64_t n_entries);
+int cfr_counts_allreduce_local(cfr_handle **handles, int n_handles, uint64_t *out, uint64_t n_entries);
+
 int cfr_get_counters(cfr_handle *h, cfr_counters *c, void *stream);
 int cfr_reset_counters(cfr_handle *h, void *stream);
 
