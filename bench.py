@@ -59,6 +59,8 @@ WORKLOADS = {
     "c5": dict(dataset="c5", reads=10_000_000, batch=1_000_000, rlen=150, paired=True, k=5,
                desc="synthetic 140 Gbp / 35000-sequence index (built on the GPU), 10M x 2x150 bp read pairs per GPU, -k 5 "
                     "(BASELINE configs[4])"),
+    "s2g": dict(dataset="s2g", reads=1_000_000, batch=1_000_000, rlen=150, paired=True, k=5,
+                desc="synthetic 2 Gbp / 500-sequence index (built on the GPU), 1M x 2x150 bp read pairs, -k 5"),
     "s400": dict(dataset="s400", reads=2_000_000, batch=1_000_000, rlen=150, paired=True, k=5,
                  desc="synthetic 400 Mbp / 100-sequence index (built on the GPU), 2M x 2x150 bp read pairs, -k 5"),
     "c3s": dict(dataset="c3", reads=1_000_000, batch=1_000_000, rlen=150, paired=True, k=5,

@@ -629,71 +629,76 @@ struct PairQuery {
 
 CFR_HD u64 pair_match(u64 lo, u64 hi, int c) { return occ_match(lo, hi, c); }
 
-// A lane's share of one line.  Device, cooperative: the 32 bytes at 32 * (lane & 3) of the line, fetched by the
-// four lanes of a task group as one coalesced 128-byte request.  Host twin / scalar form: the planes, the
-// counter words are read when needed.
-struct PairRegs {
-  u64 a, b, c, d;
-  const u64 *w;  // scalar form only
-};
-
-template <bool COOP>
-CFR_HD PairRegs pair_load(const DevIndex &ix, u64 L) {
-  PairRegs r;
-  r.w = ix.pairs[L].w;
-#if defined(__CUDA_ARCH__)
-  if (COOP) {
-    asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(r.a), "=l"(r.b), "=l"(r.c), "=l"(r.d)
-                 : "l"(reinterpret_cast<const char *>(r.w) + 32 * (threadIdx.x & 3)));
-    return r;
-  }
-#endif
-  r.a = ld64(r.w);
-  r.b = ld64(r.w + 1);
-  r.c = ld64(r.w + 2);
-  r.d = ld64(r.w + 3);
-  return r;
-}
-
-// everything one boundary x = 64 L + s needs from its line (all lanes of a group hold the same c1, c2, L, s)
-template <bool COOP>
-CFR_HD PairQuery pair_eval(const DevIndex &ix, const PairRegs &r, u64 L, int s, int c1, int c2) {
+// what one boundary x = 64 L + s contributes, read from the whole line by one lane (host twin, load-time
+// kernels, and the reference the cooperative form is checked against)
+CFR_HD PairQuery pair_query_scalar(const DevIndex &ix, int c1, int c2, u64 x) {
+  const u64 L = x >> 6;
+  const int s = (int)(x & 63);
   const int idx = c1 * 4 + c2;
   const u64 *sb = ix.pair_sb + (L >> CFR_PAIR_SB_SHIFT) * 20;
+  const u64 *w = ix.pairs[L].w;
+  const u64 a = ld64(w), b = ld64(w + 1), c = ld64(w + 2), d = ld64(w + 3);
   const u64 below = (1ull << s) - 1ull;
+  const u64 m1 = pair_match(a, b, c1), m12 = m1 & pair_match(c, d, c2);
+  const u64 pw = ld64(w + 4 + (idx >> 1)), sw = ld64(w + 12 + (c1 >> 1));
   PairQuery q;
-#if defined(__CUDA_ARCH__)
-  if (COOP) {
-    const int lane = threadIdx.x & 31, sub = lane & 3, base = lane & ~3;
-    const unsigned gmask = 0xfu << base;
-    // lane 0 holds the planes
-    const u64 m1 = pair_match(r.a, r.b, c1), m12 = m1 & pair_match(r.c, r.d, c2);
-    const u32 packed = (u32)popc64(m1 & below) | ((u32)popc64(m12 & below) << 8) |
-                       ((u32)(((r.a >> s) & 1ull) | (((r.b >> s) & 1ull) << 1)) << 16) |
-                       ((u32)(((r.c >> s) & 1ull) | (((r.d >> s) & 1ull) << 1)) << 18);
-    // lanes 1, 2: pair counter idx is in word (idx >> 1) & 3 of lane 1 + (idx >> 3); lane 3: S[c1] in word c1 >> 1
-    const int wsel = sub == 3 ? (c1 >> 1) : ((idx >> 1) & 3);
-    const u64 wv = wsel == 0 ? r.a : wsel == 1 ? r.b : wsel == 2 ? r.c : r.d;
-    const int half = sub == 3 ? (c1 & 1) : (idx & 1);
-    const u32 field = (u32)(half ? (wv >> 32) : wv);
-    const u32 v0 = __shfl_sync(gmask, packed, base);
-    const u32 vp = __shfl_sync(gmask, field, base + 1 + (idx >> 3));
-    const u32 vs = __shfl_sync(gmask, field, base + 3);
-    q.s1 = ld64(sb + 16 + c1) + (u64)vs + (u64)(v0 & 0xffu);
-    q.p = ld64(sb + idx) + (u64)vp + (u64)((v0 >> 8) & 0xffu);
-    q.sym1 = (int)((v0 >> 16) & 3u);
-    q.sym2 = (int)((v0 >> 18) & 3u);
-    return q;
-  }
-#endif
-  const u64 m1 = pair_match(r.a, r.b, c1), m12 = m1 & pair_match(r.c, r.d, c2);
-  const u64 pw = ld64(r.w + 4 + (idx >> 1)), sw = ld64(r.w + 12 + (c1 >> 1));
   q.s1 = ld64(sb + 16 + c1) + (u64)(u32)((c1 & 1) ? (sw >> 32) : sw) + (u64)popc64(m1 & below);
   q.p = ld64(sb + idx) + (u64)(u32)((idx & 1) ? (pw >> 32) : pw) + (u64)popc64(m12 & below);
-  q.sym1 = (int)(((r.a >> s) & 1ull) | (((r.b >> s) & 1ull) << 1));
-  q.sym2 = (int)(((r.c >> s) & 1ull) | (((r.d >> s) & 1ull) << 1));
+  q.sym1 = (int)(((a >> s) & 1ull) | (((b >> s) & 1ull) << 1));
+  q.sym2 = (int)(((c >> s) & 1ull) | (((d >> s) & 1ull) << 1));
   return q;
 }
+
+#if defined(__CUDA_ARCH__)
+// The cooperative fetch.  Every lane of the warp owns one search (one lane per strand task, as in the
+// sector walkers); the lines are fetched by groups of four adjacent lanes in four rounds: in round j the
+// group fetches the line of its member j as ONE coalesced 128-byte request (32 bytes per lane), the lane
+// that holds the planes evaluates member j's two in-line boundaries, the lanes that hold the counters
+// pick member j's fields, and the four 32-bit results go to member j through shared memory.
+//   in:  want (this lane has a query), L (line), c1, c2, s1, s2 (bit positions of the two boundaries in the line)
+//   out: pk = popc1(s1) | popc12(s1) << 7 | sym1(s1) << 14 | sym2(s1) << 16 | popc1(s2) << 18 | popc12(s2) << 25
+//        fp = P[c1][c2] field, fs = S[c1] field (both relative to the superblock)
+// Must be called by all 32 lanes.
+CFR_D void pair_fetch_warp(const DevIndex &ix, bool want, u32 L, int c1, int c2, int s1, int s2, u32 &pk, u32 &fp, u32 &fs) {
+  __shared__ uint4 xchg[4][32];  // [warp of the block][lane]: {pk, fields of sub-lanes 1, 2, 3}
+  const int lane = threadIdx.x & 31, sub = lane & 3, gbase = lane & ~3, wid = (threadIdx.x >> 5) & 3;
+  const u32 prm = (u32)c1 | ((u32)c2 << 2) | ((u32)s1 << 4) | ((u32)s2 << 10) | (want ? 1u << 16 : 0u);
+  u32 *my = reinterpret_cast<u32 *>(&xchg[wid][0]);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const u32 pj = __shfl_sync(0xffffffffu, prm, gbase + j);
+    const u32 lj = __shfl_sync(0xffffffffu, L, gbase + j);
+    u32 val = 0;
+    if ((pj >> 16) & 1u) {  // uniform over the four lanes of the group
+      u64 a, b, c, d;
+      asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d)
+                   : "l"(reinterpret_cast<const char *>(ix.pairs + lj) + 32 * sub));
+      const int q1 = (int)(pj & 3u), q2 = (int)((pj >> 2) & 3u), idx = q1 * 4 + q2;
+      if (sub == 0) {
+        const int t1 = (int)((pj >> 4) & 63u), t2 = (int)((pj >> 10) & 63u);
+        const u64 m1 = pair_match(a, b, q1), m12 = m1 & pair_match(c, d, q2);
+        const u64 b1 = (1ull << t1) - 1ull, b2 = (1ull << t2) - 1ull;
+        val = (u32)popc64(m1 & b1) | ((u32)popc64(m12 & b1) << 7) |
+              ((u32)(((a >> t1) & 1ull) | (((b >> t1) & 1ull) << 1)) << 14) |
+              ((u32)(((c >> t1) & 1ull) | (((d >> t1) & 1ull) << 1)) << 16) |
+              ((u32)popc64(m1 & b2) << 18) | ((u32)popc64(m12 & b2) << 25);
+      } else {
+        const int wsel = sub == 3 ? (q1 >> 1) : ((idx >> 1) & 3);
+        const u64 wv = wsel == 0 ? a : wsel == 1 ? b : wsel == 2 ? c : d;
+        val = (u32)((sub == 3 ? (q1 & 1) : (idx & 1)) ? (wv >> 32) : wv);
+      }
+    }
+    my[(gbase + j) * 4 + sub] = val;  // slot of member j, component `sub`
+  }
+  __syncwarp();
+  const uint4 r = xchg[wid][lane];
+  __syncwarp();
+  const int idx = c1 * 4 + c2;
+  pk = r.x;
+  fp = (idx >> 3) ? r.z : r.y;
+  fs = r.w;
+}
+#endif
 
 // ---- building the pair lines at load time, from the occ sectors (which k_transcode derived from the
 // run-block arrays with the literal Sequence_RunBlock::Rank / Access)
@@ -800,40 +805,62 @@ CFR_HD void pair_constants(const DevIndex &ix, u64 *out) {
 // Two steps of FMIndex::BackwardSearch's loop (FMIndex.hpp:495-508) from the range [sp, ep]: first c1,
 // then -- if c2 >= 0 -- c2.  Returns how many succeeded (0, 1, 2) and leaves the range after the last
 // successful one in (sp, ep).  The operation counters advance as the reference's calls would.
+// COOP (device): one lane per search, lines fetched by the warp cooperatively (pair_fetch_warp); the call
+// is warp-uniform -- lanes without a step to do pass go = false.  !COOP: one lane reads whole lines.
 template <bool COOP>
 struct BwtPairT {
   typedef u64 pos_t;
-  enum { LANES = COOP ? 4 : 1, PAIR = 1, STEPS_COUNTED_AT_CLOSE = 0 };
-  static CFR_HD bool leader() {
-#if defined(__CUDA_ARCH__)
-    return !COOP || (threadIdx.x & 3) == 0;
-#else
-    return true;
-#endif
-  }
+  enum { LANES = 1, PAIR = 1, STEPS_COUNTED_AT_CLOSE = 0 };
+  static CFR_HD bool leader() { return true; }
   // single-step form: not used by the search loop of a pair policy (Bwt::PAIR selects extend2)
-  static CFR_HD void extend_step(const DevIndex &ix, int c, u64 sp, u64 ep, u64 &nsp, u64 &nep, OpCount &oc) {
+  static CFR_HD void extend_step(const DevIndex &, int, u64 sp, u64 ep, u64 &nsp, u64 &nep, OpCount &) {
     nsp = sp;
     nep = ep;
-    if (extend2(ix, c, -1, nsp, nep, oc) == 0) {
-      nsp = 1;
-      nep = 0;
-    }
   }
-  static CFR_HD int extend2(const DevIndex &ix, int c1, int c2, u64 &sp, u64 &ep, OpCount &oc) {
+  static CFR_HD int extend2(const DevIndex &ix, bool go, int c1, int c2, u64 &sp, u64 &ep, OpCount &oc) {
     const bool two = c2 >= 0;
     const int c2q = two ? c2 : 0;
     const bool range = sp != ep;
     const u64 xe = ep + 1;
     const u64 La = sp >> 6, Le = xe >> 6;
-    const PairRegs ra = pair_load<COOP>(ix, La);
-    // the second boundary mostly lies in the line just fetched; all lanes of a group agree on `far`
-    const bool far = range && Le != La;
-    PairRegs re = ra;
-    if (far) re = pair_load<COOP>(ix, Le);
-    const PairQuery qa = pair_eval<COOP>(ix, ra, La, (int)(sp & 63), c1, c2q);
-    PairQuery qe = qa;
-    if (range) qe = pair_eval<COOP>(ix, re, Le, (int)(xe & 63), c1, c2q);
+    PairQuery qa, qe;
+#if defined(__CUDA_ARCH__)
+    if (COOP) {
+      c1 &= 3;  // lanes with go == false carry anything
+      const bool near = range && Le == La;
+      u32 pk, fp, fs;
+      pair_fetch_warp(ix, go, (u32)La, c1, c2q, (int)(sp & 63), near ? (int)(xe & 63) : 0, pk, fp, fs);
+      const int idx = c1 * 4 + c2q;
+      {
+        const u64 *sb = ix.pair_sb + (La >> CFR_PAIR_SB_SHIFT) * 20;
+        const u64 bs = go ? ld64(sb + 16 + c1) : 0, bp = go ? ld64(sb + idx) : 0;
+        qa.s1 = bs + (u64)fs + (u64)(pk & 0x7fu);
+        qa.p = bp + (u64)fp + (u64)((pk >> 7) & 0x7fu);
+        qa.sym1 = (int)((pk >> 14) & 3u);
+        qa.sym2 = (int)((pk >> 16) & 3u);
+        qe = qa;
+        if (near) {
+          qe.s1 = bs + (u64)fs + (u64)((pk >> 18) & 0x7fu);
+          qe.p = bp + (u64)fp + (u64)((pk >> 25) & 0x7fu);
+        }
+      }
+      const bool far = go && range && Le != La;
+      if (__ballot_sync(0xffffffffu, far)) {  // rare once a search is past its first bases
+        pair_fetch_warp(ix, far, (u32)Le, c1, c2q, (int)(xe & 63), 0, pk, fp, fs);
+        if (far) {
+          const u64 *sb = ix.pair_sb + (Le >> CFR_PAIR_SB_SHIFT) * 20;
+          qe.s1 = ld64(sb + 16 + c1) + (u64)fs + (u64)(pk & 0x7fu);
+          qe.p = ld64(sb + idx) + (u64)fp + (u64)((pk >> 7) & 0x7fu);
+        }
+      }
+      if (!go) return 0;
+    } else
+#endif
+    {
+      if (!go) return 0;
+      qa = pair_query_scalar(ix, c1, c2q, sp);
+      qe = range ? pair_query_scalar(ix, c1, c2q, xe) : qa;
+    }
     const u64 fisa = ix.first_isa;
     const bool l1 = c1 == ix.last_code;
     ++oc.xext;
@@ -848,8 +875,8 @@ struct BwtPairT {
       return 1;
     }
     const bool l2 = c2 == ix.last_code;
-    const int idx = c1 * 4 + c2;
-    const u64 g0 = ix.C[c2] + ix.pair_D[idx];
+    const int idx2 = c1 * 4 + c2;
+    const u64 g0 = ix.C[c2] + ix.pair_D[idx2];
     const u64 e_add = (l1 && ix.pair_E == c2) ? 1ull : 0ull;
     const u64 f_sub = (l1 && ix.pair_F == c2) ? 1ull : 0ull;
     const bool range2 = y1 != y2;

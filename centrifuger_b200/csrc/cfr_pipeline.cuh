@@ -312,12 +312,12 @@ enum { CFR_ST_EXTEND = 0, CFR_ST_CLOSE = 1, CFR_ST_FETCH = 2, CFR_ST_DONE = 3 };
 
 // the pair policies implement extend2; the others never reach the call (Bwt::PAIR == 0)
 template <class Bwt>
-CFR_HD typename std::enable_if<(Bwt::PAIR != 0), int>::type pair_extend2(const DevIndex &ix, int c1, int c2, u64 &sp, u64 &ep,
-                                                                         OpCount &oc) {
-  return Bwt::extend2(ix, c1, c2, sp, ep, oc);
+CFR_HD typename std::enable_if<(Bwt::PAIR != 0), int>::type pair_extend2(const DevIndex &ix, bool go, int c1, int c2, u64 &sp,
+                                                                         u64 &ep, OpCount &oc) {
+  return Bwt::extend2(ix, go, c1, c2, sp, ep, oc);
 }
 template <class Bwt>
-CFR_HD typename std::enable_if<(Bwt::PAIR == 0), int>::type pair_extend2(const DevIndex &, int, int, u64 &, u64 &, OpCount &) {
+CFR_HD typename std::enable_if<(Bwt::PAIR == 0), int>::type pair_extend2(const DevIndex &, bool, int, int, u64 &, u64 &, OpCount &) {
   return 0;
 }
 
@@ -454,26 +454,29 @@ CFR_HD void search_tasks(const DevIndex &ix, const DevParams &P, const ChunkDev 
       }
     }
     if (Bwt::PAIR) {
-      if (st == CFR_ST_EXTEND) {  // up to two FMIndex::BackwardExtend steps from one line per boundary
-        const int c1 = s.peek();  // the cursor stands on strand position remaining - 1 - l
+      // up to two FMIndex::BackwardExtend steps from one line per boundary; the call is warp-uniform (the lines
+      // are fetched cooperatively), lanes outside a search pass go = false
+      const bool act = st == CFR_ST_EXTEND;
+      int c1 = 0, c2 = -1;
+      if (act) {
+        c1 = s.peek();  // the cursor stands on strand position remaining - 1 - l
         st = CFR_ST_CLOSE;
-        if (c1 <= 3) {
-          int c2 = -1;
-          const bool have2 = l + 1 < remaining;
-          if (have2) {
-            s.advance();
-            c2 = s.peek();
-            if (c2 > 3) c2 = -1;  // the search ends on this base (FMIndex.hpp:500)
-          }
-          u64 psp = (u64)sp, pep = (u64)ep;
-          const int done = pair_extend2<Bwt>(ix, c1, c2, psp, pep, oc);
-          sp = (pos_t)psp;
-          ep = (pos_t)pep;
-          l += done;
-          if (done == 2 && l < remaining) {
-            st = CFR_ST_EXTEND;
-            s.advance();
-          }
+        if (c1 <= 3 && l + 1 < remaining) {
+          s.advance();
+          c2 = s.peek();
+          if (c2 > 3) c2 = -1;  // the search ends on this base (FMIndex.hpp:500)
+        }
+      }
+      const bool go = act && c1 <= 3;
+      u64 psp = (u64)sp, pep = (u64)ep;
+      const int done = pair_extend2<Bwt>(ix, go, c1, c2, psp, pep, oc);
+      if (go) {
+        sp = (pos_t)psp;
+        ep = (pos_t)pep;
+        l += done;
+        if (done == 2 && l < remaining) {
+          st = CFR_ST_EXTEND;
+          s.advance();
         }
       }
     } else if (st == CFR_ST_EXTEND) {  // one FMIndex::BackwardExtend; l < remaining holds here

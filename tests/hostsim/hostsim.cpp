@@ -234,7 +234,7 @@ u64 hostsim_pair_check(void *hh, u64 n_ranges, u64 seed) {
           }
         }
         u64 gsp = sp, gep = ep;
-        const int got = BwtPairT<false>::extend2(ix, c1, c2, gsp, gep, oc2);
+        const int got = BwtPairT<false>::extend2(ix, true, c1, c2, gsp, gep, oc2);
         if (got != want || (want > 0 && (gsp != wsp || gep != wep))) ++bad;
       }
   };

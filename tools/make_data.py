@@ -48,6 +48,7 @@ DATASETS = {
 # collections above (tests/test_builder.py: byte-identical files).
 SYNTHETIC = {
     "s400": dict(species=20, strains=5, genome_len=4_000_000),      # 400 Mbp: quick checks
+    "s2g": dict(species=100, strains=5, genome_len=4_000_000),      # 2 Gbp: the shape of BASELINE configs[2]
     "c4": dict(species=1000, strains=5, genome_len=4_000_000),      # BASELINE configs[3]: 20 Gbp
     "c5": dict(species=7000, strains=5, genome_len=4_000_000),      # BASELINE configs[4]: 140 Gbp
 }
