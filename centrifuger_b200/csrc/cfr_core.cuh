@@ -650,53 +650,54 @@ CFR_HD PairQuery pair_query_scalar(const DevIndex &ix, int c1, int c2, u64 x) {
 }
 
 #if defined(__CUDA_ARCH__)
-// The cooperative fetch.  Every lane of the warp owns one search (one lane per strand task, as in the
-// sector walkers); the lines are fetched by groups of four adjacent lanes in four rounds: in round j the
-// group fetches the line of its member j as ONE coalesced 128-byte request (32 bytes per lane), the lane
-// that holds the planes evaluates member j's two in-line boundaries, the lanes that hold the counters
-// pick member j's fields, and the four 32-bit results go to member j through shared memory.
-//   in:  want (this lane has a query), L (line), c1, c2, s1, s2 (bit positions of the two boundaries in the line)
-//   out: pk = popc1(s1) | popc12(s1) << 7 | sym1(s1) << 14 | sym2(s1) << 16 | popc1(s2) << 18 | popc12(s2) << 25
-//        fp = P[c1][c2] field, fs = S[c1] field (both relative to the superblock)
-// Must be called by all 32 lanes.
-CFR_D void pair_fetch_warp(const DevIndex &ix, bool want, u32 L, int c1, int c2, int s1, int s2, u32 &pk, u32 &fp, u32 &fs) {
-  __shared__ uint4 xchg[4][32];  // [warp of the block][lane]: {pk, fields of sub-lanes 1, 2, 3}
-  const int lane = threadIdx.x & 31, sub = lane & 3, gbase = lane & ~3, wid = (threadIdx.x >> 5) & 3;
-  const u32 prm = (u32)c1 | ((u32)c2 << 2) | ((u32)s1 << 4) | ((u32)s2 << 10) | (want ? 1u << 16 : 0u);
-  u32 *my = reinterpret_cast<u32 *>(&xchg[wid][0]);
+// The cooperative fetch: lines are STAGED IN SHARED MEMORY.  Every lane of the warp owns one search (one lane
+// per strand task, as in the sector walkers) and names the line it needs; the lines are fetched by groups
+// of four adjacent lanes in four rounds -- in round j the group fetches the line of its member j as ONE
+// coalesced 128-byte request (32 bytes per lane) and stores it into member j's slot.  After the four
+// rounds every lane reads its own line from its slot and does the arithmetic once, 32 searches per
+// instruction.  Slots are 144 bytes apart (128 + 16 of padding): a lane's 16-byte reads of its own slot
+// fall on distinct banks within each quarter warp.
+#define CFR_PAIR_SLOT_WORDS 36
+#define CFR_PAIR_NO_LINE 0xffffffffu
+
+// must be called by all 32 lanes; `slots` = this warp's 32 slots
+CFR_D void pair_stage_warp(const DevIndex &ix, u32 L, u32 *slots) {
+  const int lane = threadIdx.x & 31, sub = lane & 3, gbase = lane & ~3;
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    const u32 pj = __shfl_sync(0xffffffffu, prm, gbase + j);
     const u32 lj = __shfl_sync(0xffffffffu, L, gbase + j);
-    u32 val = 0;
-    if ((pj >> 16) & 1u) {  // uniform over the four lanes of the group
+    if (lj != CFR_PAIR_NO_LINE) {  // uniform over the four lanes of the group
       u64 a, b, c, d;
       asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d)
                    : "l"(reinterpret_cast<const char *>(ix.pairs + lj) + 32 * sub));
-      const int q1 = (int)(pj & 3u), q2 = (int)((pj >> 2) & 3u), idx = q1 * 4 + q2;
-      if (sub == 0) {
-        const int t1 = (int)((pj >> 4) & 63u), t2 = (int)((pj >> 10) & 63u);
-        const u64 m1 = pair_match(a, b, q1), m12 = m1 & pair_match(c, d, q2);
-        const u64 b1 = (1ull << t1) - 1ull, b2 = (1ull << t2) - 1ull;
-        val = (u32)popc64(m1 & b1) | ((u32)popc64(m12 & b1) << 7) |
-              ((u32)(((a >> t1) & 1ull) | (((b >> t1) & 1ull) << 1)) << 14) |
-              ((u32)(((c >> t1) & 1ull) | (((d >> t1) & 1ull) << 1)) << 16) |
-              ((u32)popc64(m1 & b2) << 18) | ((u32)popc64(m12 & b2) << 25);
-      } else {
-        const int wsel = sub == 3 ? (q1 >> 1) : ((idx >> 1) & 3);
-        const u64 wv = wsel == 0 ? a : wsel == 1 ? b : wsel == 2 ? c : d;
-        val = (u32)((sub == 3 ? (q1 & 1) : (idx & 1)) ? (wv >> 32) : wv);
-      }
+      ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(slots + (gbase + j) * CFR_PAIR_SLOT_WORDS + sub * 8);
+      dst[0] = make_ulonglong2(a, b);
+      dst[1] = make_ulonglong2(c, d);
     }
-    my[(gbase + j) * 4 + sub] = val;  // slot of member j, component `sub`
   }
   __syncwarp();
-  const uint4 r = xchg[wid][lane];
-  __syncwarp();
+}
+
+// the boundaries x1 = 64 L + s1 and (if two) x2 = 64 L + s2 from the lane's staged line
+CFR_D void pair_query_slot(const DevIndex &ix, const u32 *slot, u64 L, int c1, int c2, int s1, int s2, bool two, PairQuery &q1,
+                           PairQuery &q2) {
   const int idx = c1 * 4 + c2;
-  pk = r.x;
-  fp = (idx >> 3) ? r.z : r.y;
-  fs = r.w;
+  const u64 *sb = ix.pair_sb + (L >> CFR_PAIR_SB_SHIFT) * 20;
+  const ulonglong2 p01 = *reinterpret_cast<const ulonglong2 *>(slot);
+  const ulonglong2 p23 = *reinterpret_cast<const ulonglong2 *>(slot + 4);
+  const u64 m1 = pair_match(p01.x, p01.y, c1), m12 = m1 & pair_match(p23.x, p23.y, c2);
+  const u64 bs = ld64(sb + 16 + c1) + (u64)slot[24 + c1], bp = ld64(sb + idx) + (u64)slot[8 + idx];
+  const u64 b1 = (1ull << s1) - 1ull;
+  q1.s1 = bs + (u64)popc64(m1 & b1);
+  q1.p = bp + (u64)popc64(m12 & b1);
+  q1.sym1 = (int)(((p01.x >> s1) & 1ull) | (((p01.y >> s1) & 1ull) << 1));
+  q1.sym2 = (int)(((p23.x >> s1) & 1ull) | (((p23.y >> s1) & 1ull) << 1));
+  q2 = q1;
+  if (two) {
+    const u64 b2 = (1ull << s2) - 1ull;
+    q2.s1 = bs + (u64)popc64(m1 & b2);
+    q2.p = bp + (u64)popc64(m12 & b2);
+  }
 }
 #endif
 
@@ -826,32 +827,22 @@ struct BwtPairT {
     PairQuery qa, qe;
 #if defined(__CUDA_ARCH__)
     if (COOP) {
+      __shared__ __align__(16) u32 pair_slots[4][32 * CFR_PAIR_SLOT_WORDS];  // [warp of the block][lane slot]
+      u32 *slots = pair_slots[(threadIdx.x >> 5) & 3];
+      const u32 *mine = slots + (threadIdx.x & 31) * CFR_PAIR_SLOT_WORDS;
       c1 &= 3;  // lanes with go == false carry anything
       const bool near = range && Le == La;
-      u32 pk, fp, fs;
-      pair_fetch_warp(ix, go, (u32)La, c1, c2q, (int)(sp & 63), near ? (int)(xe & 63) : 0, pk, fp, fs);
-      const int idx = c1 * 4 + c2q;
-      {
-        const u64 *sb = ix.pair_sb + (La >> CFR_PAIR_SB_SHIFT) * 20;
-        const u64 bs = go ? ld64(sb + 16 + c1) : 0, bp = go ? ld64(sb + idx) : 0;
-        qa.s1 = bs + (u64)fs + (u64)(pk & 0x7fu);
-        qa.p = bp + (u64)fp + (u64)((pk >> 7) & 0x7fu);
-        qa.sym1 = (int)((pk >> 14) & 3u);
-        qa.sym2 = (int)((pk >> 16) & 3u);
-        qe = qa;
-        if (near) {
-          qe.s1 = bs + (u64)fs + (u64)((pk >> 18) & 0x7fu);
-          qe.p = bp + (u64)fp + (u64)((pk >> 25) & 0x7fu);
-        }
-      }
+      pair_stage_warp(ix, go ? (u32)La : CFR_PAIR_NO_LINE, slots);
+      if (go) pair_query_slot(ix, mine, La, c1, c2q, (int)(sp & 63), (int)(xe & 63), near, qa, qe);
+      __syncwarp();
       const bool far = go && range && Le != La;
-      if (__ballot_sync(0xffffffffu, far)) {  // rare once a search is past its first bases
-        pair_fetch_warp(ix, far, (u32)Le, c1, c2q, (int)(xe & 63), 0, pk, fp, fs);
+      if (__ballot_sync(0xffffffffu, far)) {  // the second boundary lies in another line: a few lanes per step
+        pair_stage_warp(ix, far ? (u32)Le : CFR_PAIR_NO_LINE, slots);
         if (far) {
-          const u64 *sb = ix.pair_sb + (Le >> CFR_PAIR_SB_SHIFT) * 20;
-          qe.s1 = ld64(sb + 16 + c1) + (u64)fs + (u64)(pk & 0x7fu);
-          qe.p = ld64(sb + idx) + (u64)fp + (u64)((pk >> 7) & 0x7fu);
+          PairQuery dummy;
+          pair_query_slot(ix, mine, Le, c1, c2q, (int)(xe & 63), 0, false, qe, dummy);
         }
+        __syncwarp();
       }
       if (!go) return 0;
     } else
