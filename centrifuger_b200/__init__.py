@@ -62,6 +62,7 @@ ABI_SYMBOLS = [
     "cfr_host_alloc", "cfr_host_free", "cfr_index_info", "cfr_seq_name", "cfr_rank_name", "cfr_orig_taxid", "cfr_seq_taxid",
     "cfr_format_tsv", "cfr_taxon_counts_device", "cfr_taxon_counts_read", "cfr_taxon_counts_reset",
     "cfr_counts_allreduce", "cfr_counts_allreduce_local",
+    "cfr_quant_enable", "cfr_quant_reset", "cfr_quant_stats", "cfr_quant_report",
     "cfr_get_counters", "cfr_reset_counters", "cfr_set_profiling", "cfr_get_stage_times",
     "cfr_get_stage_counters", "cfr_debug_bwt_rank", "cfr_debug_bwt_access",
     "cfr_debug_locate", "cfr_debug_dust",
@@ -425,6 +426,30 @@ class Classifier:
 
     def taxon_counts_reset(self, stream=None):
         self._check(self.L.cfr_taxon_counts_reset(self.h, stream))
+
+    # -- quantification (replaces centrifuger-quant) --------------------------
+    def quant_enable(self, min_score=0, min_hit_length=0):
+        """from now on every finished batch is coalesced on the device (Quantifier.hpp:490-622)"""
+        self.L.cfr_quant_enable.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64]
+        self._check(self.L.cfr_quant_enable(self.h, min_score, min_hit_length))
+
+    def quant_reset(self):
+        self.L.cfr_quant_reset.argtypes = [C.c_void_p]
+        self._check(self.L.cfr_quant_reset(self.h))
+
+    def quant_stats(self):
+        a, b, c = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+        self.L.cfr_quant_stats.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        self._check(self.L.cfr_quant_stats(self.h, C.byref(a), C.byref(b), C.byref(c)))
+        return {"distinct_records": a.value, "batches": b.value, "records_moved": c.value}
+
+    def quant_report(self, idx_prefix, path, fmt=0, others=()):
+        """abundance report of everything classified since quant_enable / quant_reset (with `others`: more
+        Classifier objects, one per GPU, whose records are merged in)"""
+        hs = [self.h] + [o.h for o in others]
+        arr = (C.c_void_p * len(hs))(*hs)
+        self.L.cfr_quant_report.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_int, C.c_char_p]
+        self._check(self.L.cfr_quant_report(arr, len(hs), idx_prefix.encode(), fmt, path.encode()))
 
     def taxon_counts_device(self):
         """(device pointer, entries) of the uint64 per-taxon counters (for NCCL all-reduce)."""

@@ -77,6 +77,13 @@ def build(force=False, verbose=False):
         if verbose:
             print(" ".join(cmd))
         subprocess.check_call(cmd)
+    quant_cpp = os.path.join(CSRC, "cfr_quant_main.cpp")
+    quant_cli = os.path.join(HERE, "centrifuger-b200-quant")
+    if os.path.exists(quant_cpp) and (force or _stale(quant_cli, deps)):
+        cmd = ["g++", "-std=c++17", "-O2", "-Wall", "-o", quant_cli, quant_cpp, os.path.join(CSRC, "cfr_format.cpp"), "-lz"]
+        if verbose:
+            print(" ".join(cmd))
+        subprocess.check_call(cmd)  # host-only drop-in for centrifuger-quant (TSV in, report out)
     return LIB
 
 

@@ -3,7 +3,10 @@
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 
+#include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
+#include <cub/device/device_select.cuh>
+#include <cub/iterator/counting_input_iterator.cuh>
 
 #include <chrono>
 
@@ -11,6 +14,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -18,6 +22,7 @@
 #include "../../include/centrifuger_b200.h"
 #include "cfr_format.hpp"
 #include "cfr_kernels.cuh"
+#include "cfr_quant.hpp"
 
 using namespace cfrb200;
 
@@ -63,6 +68,7 @@ struct DevBuf {
 
 // One device-resident chunk of reads with all the work areas its pipeline needs.
 struct cfr_device_batch {
+  bool quant_counted = false;  // quantification has seen this classification of the batch
   u64 n_reads = 0;
   int mates = 1;
   int cap_h = 1;
@@ -107,6 +113,15 @@ struct cfr_handle {
   bool dust_screen = true;  // register-only screen in front of the full SDUST (CFR_B200_DUST_SCREEN=0 disables)
   u64 *d_taxon = nullptr;
   u64 *d_taxon_reduced = nullptr;  // snapshot the NCCL all-reduce works on
+  // quantification (cfr_quant_enable): every finished batch is coalesced on the device, the distinct
+  // assignment records and their multiplicities accumulate here
+  struct Quant {
+    bool on = false;
+    u64 min_score = 0, min_hit = 0;
+    DevBuf words, keys_a, keys_b, idx_a, idx_b, flags, heads, num, out, tmp;
+    std::map<std::vector<u32>, u64> table;
+    u64 batches = 0, entries_moved = 0;
+  } quant;
   DevCounters *d_counters = nullptr;
   u64 launches = 0;
   u64 host_bases = 0;
@@ -948,6 +963,7 @@ int cfr_classify_resident(cfr_handle *h, cfr_device_batch *b, void *stream) {
   cudaStream_t s = pick_stream(h, stream);
   h->host_bases += b->total_bases;
   b->classified = true;
+  b->quant_counted = false;
   if (h->layout == CFR_LAYOUT_OCCLINE) {
     if (h->ix.pairs) {
       if (h->pos32) return run_first<BwtOccLine, BwtOccLine32T<4>, BwtPairT<true>>(h, b, s);
@@ -962,6 +978,8 @@ int cfr_classify_resident(cfr_handle *h, cfr_device_batch *b, void *stream) {
   }
   return run_first<BwtRunBlock, BwtRunBlock>(h, b, s);
 }
+
+static int quant_coalesce_batch(cfr_handle *h, cfr_device_batch *b, cudaStream_t s);
 
 int cfr_batch_fetch(cfr_handle *h, cfr_device_batch *b, cfr_result *results, uint64_t *ids, void *stream) {
   if (!h || !b || !results || !ids) return fail(CFR_ERR_ARG, "null argument");
@@ -980,7 +998,10 @@ int cfr_batch_fetch(cfr_handle *h, cfr_device_batch *b, cfr_result *results, uin
     CUDA_TRY(cudaMemcpyAsync(ids, b->out_ids.p, b->n_reads * (u64)h->P.max_result * 8, cudaMemcpyDeviceToHost, s));
     h->d2h_bytes += b->n_reads * (sizeof(DevResult) + (u64)h->P.max_result * 8);
   }
-  return check_device_errors(h, s);
+  if ((st = check_device_errors(h, s))) return st;
+  if (b->quant_counted) return CFR_OK;  // a resident batch counts once per classification, however often it is fetched
+  b->quant_counted = true;
+  return quant_coalesce_batch(h, b, s);
 }
 
 int cfr_batch_fetch_expanded(cfr_handle *h, cfr_device_batch *b, uint32_t *exp_cnt, uint64_t *exp_off,
@@ -1019,6 +1040,62 @@ static int pipeline_init(cfr_handle *h) {
   return CFR_OK;
 }
 
+// Quantification, per finished batch: the reads' assignment records (k_quant_keys) are sorted by LSD radix passes
+// over pairs of words, equal neighbours are counted, and only the distinct records with their counts cross to
+// the host -- CoalesceAssignments (Quantifier.hpp:490-513) where the reads are.
+static int quant_coalesce_batch(cfr_handle *h, cfr_device_batch *b, cudaStream_t s) {
+  cfr_handle::Quant &q = h->quant;
+  const u64 n = b->n_reads;
+  if (!q.on || n == 0) return CFR_OK;
+  if (n >= (1ull << 31)) return fail(CFR_ERR_UNSUPPORTED, "quantification: batch too large");
+  const int K = h->P.max_result, W = K + 1;
+  int st;
+  if ((st = q.words.ensure(n * W * 4)) || (st = q.keys_a.ensure(n * 8)) || (st = q.keys_b.ensure(n * 8)) ||
+      (st = q.idx_a.ensure(n * 4)) || (st = q.idx_b.ensure(n * 4)) || (st = q.flags.ensure(n)) || (st = q.heads.ensure(n * 4)) ||
+      (st = q.num.ensure(16)) || (st = q.out.ensure(n * (W + 1) * 4)))
+    return st;
+  u32 *words = (u32 *)q.words.p;
+  const int grid = grid_for(h, n, 256, 8);
+  k_quant_keys<<<grid, 256, 0, s>>>(h->ix, (const DevResult *)b->results.p, (const u64 *)b->out_ids.p, n, K, q.min_score, q.min_hit, words);
+  cub::DoubleBuffer<u64> dk((u64 *)q.keys_a.p, (u64 *)q.keys_b.p);
+  cub::DoubleBuffer<u32> di((u32 *)q.idx_a.p, (u32 *)q.idx_b.p);
+  size_t tb = 0, tb2 = 0;
+  CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tb, dk, di, (int)n, 0, 64, s));
+  CUDA_TRY(cub::DeviceSelect::Flagged(nullptr, tb2, cub::CountingInputIterator<u32>(0), (unsigned char *)q.flags.p, (u32 *)q.heads.p,
+                                      (u32 *)q.num.p, (int)n, s));
+  if ((st = q.tmp.ensure(std::max(tb, tb2)))) return st;
+  const int passes = (W + 1) / 2;
+  for (int p = 0; p < passes; ++p) {
+    k_quant_gather<<<grid, 256, 0, s>>>(words, p == 0 ? nullptr : di.Current(), n, W, p, dk.Current(), p == 0 ? di.Current() : nullptr);
+    size_t t = q.tmp.bytes;
+    CUDA_TRY(cub::DeviceRadixSort::SortPairs(q.tmp.p, t, dk, di, (int)n, 0, 64, s));
+  }
+  k_quant_heads<<<grid, 256, 0, s>>>(words, di.Current(), n, W, (unsigned char *)q.flags.p);
+  {
+    size_t t = q.tmp.bytes;
+    CUDA_TRY(cub::DeviceSelect::Flagged(q.tmp.p, t, cub::CountingInputIterator<u32>(0), (unsigned char *)q.flags.p, (u32 *)q.heads.p,
+                                        (u32 *)q.num.p, (int)n, s));
+  }
+  k_quant_emit<<<grid, 256, 0, s>>>(words, di.Current(), (const u32 *)q.heads.p, (const u32 *)q.num.p, n, W, (u32 *)q.out.p);
+  h->launches += 3 + 2 * passes + 1;
+  CUDA_TRY(cudaGetLastError());
+  u32 num = 0;
+  CUDA_TRY(cudaMemcpyAsync(&num, q.num.p, 4, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  std::vector<u32> host((size_t)num * (W + 1));
+  if (num) {
+    CUDA_TRY(cudaMemcpyAsync(host.data(), q.out.p, host.size() * 4, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+  }
+  for (u32 e = 0; e < num; ++e) {
+    const u32 *o = host.data() + (size_t)e * (W + 1);
+    q.table[std::vector<u32>(o, o + W)] += o[W];
+  }
+  ++q.batches;
+  q.entries_moved += num;
+  return CFR_OK;
+}
+
 // wait for a chunk's results; run the (rare) follow-up passes for reads that did not fit the arena
 static int pipeline_drain(cfr_handle *h, int slot, cfr_result *results, uint64_t *ids, cudaStream_t sc) {
   cfr_device_batch *b = &h->slots[slot];
@@ -1031,7 +1108,7 @@ static int pipeline_drain(cfr_handle *h, int slot, cfr_result *results, uint64_t
     CUDA_TRY(cudaMemcpyAsync(ids, b->out_ids.p, b->n_reads * (u64)h->P.max_result * 8, cudaMemcpyDeviceToHost, sc));
     CUDA_TRY(cudaStreamSynchronize(sc));
   }
-  return CFR_OK;
+  return quant_coalesce_batch(h, b, sc);
 }
 
 static int job_finish(cfr_handle *h, int slot) {
@@ -1405,6 +1482,60 @@ int cfr_counts_allreduce_local(cfr_handle **handles, int n_handles, uint64_t *ou
     CUDA_TRY(cudaMemcpyAsync(out, h->d_taxon_reduced, n_entries * 8, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
   }
+  return CFR_OK;
+}
+
+int cfr_quant_enable(cfr_handle *h, uint64_t min_score, uint64_t min_hit_length) {
+  if (!h) return fail(CFR_ERR_ARG, "null argument");
+  if (h->P.max_result > 64) return fail(CFR_ERR_UNSUPPORTED, "quantification keeps at most 64 targets per read");
+  h->quant.on = true;
+  h->quant.min_score = min_score;
+  h->quant.min_hit = min_hit_length;
+  return CFR_OK;
+}
+
+int cfr_quant_reset(cfr_handle *h) {
+  if (!h) return fail(CFR_ERR_ARG, "null argument");
+  h->quant.table.clear();
+  h->quant.batches = h->quant.entries_moved = 0;
+  return CFR_OK;
+}
+
+int cfr_quant_stats(cfr_handle *h, uint64_t *distinct, uint64_t *batches, uint64_t *entries_moved) {
+  if (!h) return fail(CFR_ERR_ARG, "null argument");
+  if (distinct) *distinct = h->quant.table.size();
+  if (batches) *batches = h->quant.batches;
+  if (entries_moved) *entries_moved = h->quant.entries_moved;
+  return CFR_OK;
+}
+
+int cfr_quant_report(cfr_handle **handles, int n_handles, const char *idx_prefix, int format, const char *path) {
+  if (!handles || n_handles < 1 || !handles[0] || !idx_prefix) return fail(CFR_ERR_ARG, "null argument");
+  Quantifier q;
+  std::string err;
+  if (q.init(idx_prefix, err) != 0) return fail(CFR_ERR_IO, err);
+  const int W = handles[0]->P.max_result + 1;
+  std::map<std::vector<u32>, u64> all;  // the replicas' tables merged (one process, one handle per GPU)
+  for (int g = 0; g < n_handles; ++g) {
+    if (!handles[g] || handles[g]->P.max_result + 1 != W) return fail(CFR_ERR_ARG, "handles differ in -k");
+    for (auto &kv : handles[g]->quant.table) all[kv.first] += kv.second;
+  }
+  for (auto &kv : all) {
+    const std::vector<u32> &w = kv.first;
+    if (w[0] == 0xffffffffu) {
+      q.add_unclassified(kv.second);
+      continue;
+    }
+    const size_t nt = w[0] & 0xffu;
+    uint64_t targets[64];
+    for (size_t j = 0; j < nt; ++j) targets[j] = w[1 + j];
+    q.add(targets, nt, (int)((w[0] >> 8) & 0xffu), ((w[0] >> 16) & 1u) != 0, kv.second);
+  }
+  q.quantify();
+  FILE *fp = (!path || !strcmp(path, "-")) ? stdout : fopen(path, "w");
+  if (!fp) return fail(CFR_ERR_IO, std::string("cannot write ") + path);
+  q.output(fp, format);
+  if (fp != stdout) fclose(fp); else fflush(fp);
   return CFR_OK;
 }
 

@@ -197,10 +197,12 @@ int parse_taxonomy(const std::string &path, TaxonomyHost &t, std::string &err) {
   }
   t.parent.resize(t.node_cnt);
   t.rank.resize(t.node_cnt);
+  t.leaf.resize(t.node_cnt);
   for (uint64_t i = 0; i < t.node_cnt; ++i) {  // TaxonomyNode: u64 parent, u8 rank, u8 leaf, pad[6]
     t.parent[i] = c.get<uint64_t>();
     t.rank[i] = c.get<uint8_t>();
-    c.bytes(7);
+    t.leaf[i] = c.get<uint8_t>();
+    c.bytes(6);
   }
   uint64_t map_n = c.get<uint64_t>();
   if (!c.need(map_n * 8)) {
@@ -392,6 +394,8 @@ void init_tax_rank_num(uint8_t r[32]) {
   r[FORMA] = k; r[SUB_TRIBE] = k; r[TRIBE] = k; r[VARIETAS] = k; r[LIFE] = k; r[UNKNOWN] = k;
   r[31] = k;  // slot 31: level of "unknown" for ids beyond the table
 }
+
+int load_taxonomy_file(const std::string &path, TaxonomyHost &t, std::string &err) { return parse_taxonomy(path, t, err); }
 
 const char *tax_rank_string(uint8_t rank) {
   static const char *names[] = {

@@ -54,6 +54,7 @@ struct TaxonomyHost {
   uint64_t node_cnt = 0, seq_cnt = 0, extra_seq_cnt = 0, root = 0;
   std::vector<uint64_t> parent;     // TaxonomyNode::parentTid
   std::vector<uint8_t> rank;        // TaxonomyNode::rank
+  std::vector<uint8_t> leaf;        // TaxonomyNode::leaf
   std::vector<uint64_t> orig_taxid; // MapID<uint64_t>::_toOrigElem
   std::vector<std::string> tax_name;
   std::vector<uint64_t> seq_to_tax;
@@ -95,6 +96,17 @@ int infer_min_hit_len(uint64_t n);
 void init_tax_rank_num(uint8_t out[32]);
 // Taxonomy::GetTaxRankString (Taxonomy.hpp:497-532)
 const char *tax_rank_string(uint8_t rank);
+// rank numbers of Taxonomy.hpp:25-58 that the quantifier's reports name
+enum { TAX_RANK_STRAIN = 1, TAX_RANK_SPECIES = 2, TAX_RANK_GENUS = 3, TAX_RANK_FAMILY = 4, TAX_RANK_ORDER = 5, TAX_RANK_CLASS = 6,
+       TAX_RANK_PHYLUM = 7, TAX_RANK_KINGDOM = 8, TAX_RANK_DOMAIN = 9, TAX_RANK_SUPER_KINGDOM = 24, TAX_RANK_ACELLULAR_ROOT = 30 };
+// Taxonomy::IsCanonicalRankNum (Taxonomy.hpp:435-443)
+inline bool tax_rank_is_canonical(uint8_t r) {
+  return r == TAX_RANK_STRAIN || r == TAX_RANK_SPECIES || r == TAX_RANK_GENUS || r == TAX_RANK_FAMILY || r == TAX_RANK_ORDER ||
+         r == TAX_RANK_CLASS || r == TAX_RANK_PHYLUM || r == TAX_RANK_KINGDOM || r == TAX_RANK_SUPER_KINGDOM ||
+         r == TAX_RANK_DOMAIN || r == TAX_RANK_ACELLULAR_ROOT;
+}
+// <prefix>.2.cfr alone (Taxonomy::Load, Taxonomy.hpp:1259-1290): 0 or a negative status with `err` set
+int load_taxonomy_file(const std::string &path, TaxonomyHost &t, std::string &err);
 
 inline uint64_t load_u64(const uint8_t *p) {
   uint64_t v;

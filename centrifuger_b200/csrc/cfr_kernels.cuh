@@ -206,6 +206,82 @@ __global__ void __launch_bounds__(128) k_transcode(const __grid_constant__ DevIn
   }
 }
 
+// ---- quantification: a read's assignment as the quantifier keys it
+// (Quantifier.hpp:515-622): record of W = K + 1 words per read --
+//   word 0      number of targets | weight class << 8 | unique flag << 16; 0xffffffff for a read that does not count
+//               (unclassified, or below --min-score / --min-length)
+//   word 1..K   compact taxonomy ids of the targets in row order (unknown -> the root), 0xffffffff beyond
+// weight class d: weight 4^-d, CalculateAssignmentWeight (:283-293)
+__global__ void __launch_bounds__(256) k_quant_keys(const __grid_constant__ DevIndex ix, const DevResult *res, const u64 *ids, u64 n,
+                                                    int K, u64 min_score, u64 min_hit, u32 *words) {
+  const u64 stride = (u64)gridDim.x * blockDim.x;
+  const int W = K + 1;
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const DevResult r = res[i];
+    u32 *w = words + i * (u64)W;
+    const int na = r.n_assign < K ? r.n_assign : K;
+    if (na <= 0 || (u64)(long long)r.hit_length < min_hit || r.score < min_score) {
+      for (int j = 0; j < W; ++j) w[j] = 0xffffffffu;
+      continue;
+    }
+    int diff = r.query_length - r.hit_length;
+    const int slack = (int)((double)(u64)(long long)r.query_length * 0.01);
+    int wc = 0;
+    if (diff >= slack) {
+      diff -= slack;
+      wc = diff > 10 ? 11 : diff;
+    }
+    w[0] = (u32)na | ((u32)wc << 8) | (r.score > r.secondary_score ? 1u << 16 : 0u);
+    for (int j = 0; j < K; ++j) {
+      u32 t = 0xffffffffu;
+      if (j < na) {
+        const u64 id = ids[i * (u64)K + j];
+        u64 ct = r.by_rank ? id : (id < ix.seq_cnt ? (u64)ix.seq_to_tax[id] : ix.node_cnt);
+        if (ct >= ix.node_cnt) ct = ix.root;  // printed as the root's id, read back as the root (Taxonomy.hpp:633-652)
+        t = (u32)ct;
+      }
+      w[1 + j] = t;
+    }
+  }
+}
+
+// one pass of the record sort: the 64-bit key made of words (2p, 2p+1) of the records in their current order
+__global__ void __launch_bounds__(256) k_quant_gather(const u32 *words, const u32 *idx, u64 n, int W, int p, u64 *keys, u32 *idx_init) {
+  const u64 stride = (u64)gridDim.x * blockDim.x;
+  for (u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
+    const u32 i = idx ? idx[j] : (u32)j;
+    if (idx_init) idx_init[j] = (u32)j;
+    const u32 *w = words + (u64)i * W;
+    const u64 lo = w[2 * p], hi = 2 * p + 1 < W ? w[2 * p + 1] : 0;
+    keys[j] = lo | (hi << 32);
+  }
+}
+
+__global__ void __launch_bounds__(256) k_quant_heads(const u32 *words, const u32 *idx, u64 n, int W, unsigned char *flags) {
+  const u64 stride = (u64)gridDim.x * blockDim.x;
+  for (u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
+    bool head = j == 0;
+    if (!head) {
+      const u32 *a = words + (u64)idx[j] * W, *b = words + (u64)idx[j - 1] * W;
+      for (int k = 0; k < W; ++k) head |= a[k] != b[k];
+    }
+    flags[j] = head ? 1 : 0;
+  }
+}
+
+// entry e: the record of run e followed by its length
+__global__ void __launch_bounds__(256) k_quant_emit(const u32 *words, const u32 *idx, const u32 *heads, const u32 *num, u64 n, int W,
+                                                    u32 *out) {
+  const u64 m = *num, stride = (u64)gridDim.x * blockDim.x;
+  for (u64 e = (u64)blockIdx.x * blockDim.x + threadIdx.x; e < m; e += stride) {
+    const u32 h0 = heads[e], h1 = e + 1 < m ? heads[e + 1] : (u32)n;
+    const u32 *w = words + (u64)idx[h0] * W;
+    u32 *o = out + e * (u64)(W + 1);
+    for (int k = 0; k < W; ++k) o[k] = w[k];
+    o[W] = h1 - h0;
+  }
+}
+
 // Pair lines at load time (cfr_core.cuh, layout 3): planes of every line, totals per chunk of 64 lines,
 // [exclusive scan of the totals on the host side of the launch sequence], superblock table, counters
 __global__ void __launch_bounds__(128) k_pair_planes(const __grid_constant__ DevIndex ix, PairLine *lines, u64 n_lines) {

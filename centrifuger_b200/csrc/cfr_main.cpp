@@ -61,6 +61,9 @@ static const char usage[] =
     "\t--hitk-factor INT: resolve at most <int>*k entries for each hit [40; use 0 for no restriction]\n"
     "\t--consider-secondary STR: in the format INT,FLOAT consider the secondary hit if its hitlen>=INT,score>=FLOAT*best_score [2000,0.995]\n"
     "\t--gpu INT: CUDA device ordinal [0]\n"
+    "\t--quant-report FILE: also write the abundance report `centrifuger-quant` computes from this output (- = stderr is not\n"
+    "\t            touched; the report goes to FILE); --quant-format INT (0:centrifuge 1:metaphlan 2:CAMI 3:kraken-report) [0],\n"
+    "\t            --quant-min-score INT, --quant-min-length INT as centrifuger-quant's --min-score / --min-length [0]\n"
     "\t--gpus INT: classify on INT GPUs (devices --gpu .. --gpu + INT - 1): the index is replicated per GPU, batch j goes\n"
     "\t            to GPU j mod INT, rows stay in input order; the per-taxon counters are summed over NCCL at the end [1]\n"
     "\t--batch INT: reads per GPU batch [1048576]\n"
@@ -69,7 +72,7 @@ static const char usage[] =
     "\t-v: print the version information and quit\n";
 
 enum {
-  ARGV_NO_DUST = 256, ARGV_MIN_HITLEN, ARGV_HITK, ARGV_SECONDARY, ARGV_GPU, ARGV_GPUS, ARGV_BATCH, ARGV_LAYOUT,
+  ARGV_NO_DUST = 256, ARGV_MIN_HITLEN, ARGV_HITK, ARGV_SECONDARY, ARGV_GPU, ARGV_GPUS, ARGV_QUANT_REPORT, ARGV_QUANT_FORMAT, ARGV_QUANT_MIN_SCORE, ARGV_QUANT_MIN_LENGTH, ARGV_BATCH, ARGV_LAYOUT,
   ARGV_UNSUPPORTED, ARGV_DRY_RUN, ARGV_DRY_PIPE, ARGV_UN, ARGV_CL, ARGV_MERGE, ARGV_EXPAND, ARGV_SAMPLE_SHEET, ARGV_DRY_OUT, ARGV_READ_FORMAT, ARGV_BARCODE, ARGV_UMI, ARGV_BC_WHITELIST, ARGV_BC_TRANSLATE
 };
 
@@ -81,6 +84,10 @@ static struct option long_options[] = {
     {"consider-secondary", required_argument, 0, ARGV_SECONDARY},
     {"gpu", required_argument, 0, ARGV_GPU},
     {"gpus", required_argument, 0, ARGV_GPUS},
+    {"quant-report", required_argument, 0, ARGV_QUANT_REPORT},
+    {"quant-format", required_argument, 0, ARGV_QUANT_FORMAT},
+    {"quant-min-score", required_argument, 0, ARGV_QUANT_MIN_SCORE},
+    {"quant-min-length", required_argument, 0, ARGV_QUANT_MIN_LENGTH},
     {"batch", required_argument, 0, ARGV_BATCH},
     {"layout", required_argument, 0, ARGV_LAYOUT},
     {"dry-run", no_argument, 0, ARGV_DRY_RUN},
@@ -261,6 +268,9 @@ int main(int argc, char *argv[]) {
   bool hasMate = false, interleaved = false;
   int device = 0;
   int nGpus = 1;
+  const char *quantReport = NULL;
+  int quantFormat = 0;
+  unsigned long quantMinScore = 0, quantMinLength = 0;
   long batchReads = 1 << 20;
   const char *unPrefix = NULL, *clPrefix = NULL;  // --un / --cl
   bool mergePairs = false;                        // --merge-readpair
@@ -333,6 +343,10 @@ int main(int argc, char *argv[]) {
       params.consider_secondary_score_factor = f;
     } else if (c == ARGV_GPU) device = atoi(optarg);
     else if (c == ARGV_GPUS) nGpus = atoi(optarg);
+    else if (c == ARGV_QUANT_REPORT) quantReport = optarg;
+    else if (c == ARGV_QUANT_FORMAT) quantFormat = atoi(optarg);
+    else if (c == ARGV_QUANT_MIN_SCORE) quantMinScore = strtoul(optarg, NULL, 10);
+    else if (c == ARGV_QUANT_MIN_LENGTH) quantMinLength = strtoul(optarg, NULL, 10);
     else if (c == ARGV_BATCH) batchReads = atol(optarg);
     else if (c == ARGV_LAYOUT) {
       if (!strcmp(optarg, "occ")) params.layout = CFR_LAYOUT_OCCLINE;
@@ -476,6 +490,12 @@ int main(int argc, char *argv[]) {
         return EXIT_FAILURE;
       }
     h = handles[0];
+    if (quantReport)
+      for (cfr_handle *hh : handles)
+        if (cfr_quant_enable(hh, quantMinScore, quantMinLength) != CFR_OK) {
+          PrintLog("ERROR: %s", cfr_last_error());
+          return EXIT_FAILURE;
+        }
     PrintLog("Finishes loading index.");
     if (params.min_hit_len <= 0) PrintLog("Inferred --min-hitlen: %d", (int)cfr_index_info(h, 4));
   }
@@ -953,6 +973,13 @@ int main(int argc, char *argv[]) {
       PrintLog("Reduced the per-taxon counters of %d GPUs over NCCL: %lu reads, %lu classified.", nGpus,
                (unsigned long)red[nodeCnt + 1], (unsigned long)red[nodeCnt + 2]);
     }
+  }
+  if (h && quantReport) {  // Quantifier::Quantification + Output over the records the GPUs coalesced
+    if (cfr_quant_report(handles.data(), nGpus, idxPrefix, quantFormat, quantReport) != CFR_OK) {
+      PrintLog("ERROR: %s", cfr_last_error());
+      return EXIT_FAILURE;
+    }
+    PrintLog("Wrote the abundance report to %s.", quantReport);
   }
   for (cfr_handle *hh : handles)
     if (hh) cfr_close(hh);

@@ -208,6 +208,18 @@ int cfr_taxon_counts_reset(cfr_handle *h, void *stream);
 int cfr_counts_allreduce(cfr_handle *h, void *nccl_comm, uint64_t *out, uint64_t n_entries);
 int cfr_counts_allreduce_local(cfr_handle **handles, int n_handles, uint64_t *out, uint64_t n_entries);
 
+/* Quantification (replaces `centrifuger-quant`, Quantifier.hpp: LoadReadAssignments :515, Quantification :640,
+ * EstimateAbundanceWithEM :236, Output :746) without the round trip through a classification file.  After
+ * cfr_quant_enable every batch a handle finishes is coalesced ON THE DEVICE into distinct (targets, weight,
+ * unique) records with their multiplicities; cfr_quant_report merges the records of the given handles (one per
+ * GPU), runs the reference's abundance estimation over them and writes the report -- byte for byte what
+ * centrifuger-quant prints for the TSV of the same reads.  format: 0 centrifuge, 1 metaphlan, 2 CAMI,
+ * 3 kraken-report (--output-format); path NULL or "-" = stdout.  min_score / min_hit_length = --min-score / --min-length. */
+int cfr_quant_enable(cfr_handle *h, uint64_t min_score, uint64_t min_hit_length);
+int cfr_quant_reset(cfr_handle *h);
+int cfr_quant_stats(cfr_handle *h, uint64_t *distinct_records, uint64_t *batches, uint64_t *records_moved);
+int cfr_quant_report(cfr_handle **handles, int n_handles, const char *idx_prefix, int format, const char *path);
+
 int cfr_get_counters(cfr_handle *h, cfr_counters *c, void *stream);
 int cfr_reset_counters(cfr_handle *h, void *stream);
 
