@@ -380,38 +380,76 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step_resident():
-        for b in batches:
-            clf.classify_resident(b, stream=sptr)
+    # Resident stepping: the step's device batches are independent units of work, so they go round-robin over
+    # three streams (what cfr_submit_batch does internally for host batches): the latency-bound stages of one batch
+    # (SDUST, scoring) fill the SMs next to the memory-bound search of another.  One extra single-stream pass with
+    # per-kernel CUDA events gives the stage times and the search kernel's own duration for the roofline.
+    NSTREAM = 3
+    streams = [stream] + [torch.cuda.Stream() for _ in range(NSTREAM - 1)]
+
+    def step_resident(multi):
+        for j, b in enumerate(batches):
+            clf.classify_resident(b, stream=streams[j % NSTREAM].cuda_stream if multi else sptr)
+
+    def fork():
+        ev = torch.cuda.Event()
+        ev.record(stream)
+        for s2 in streams[1:]:
+            s2.wait_event(ev)
+
+    def join():
+        for s2 in streams[1:]:
+            ev = torch.cuda.Event()
+            ev.record(s2)
+            stream.wait_event(ev)
+
+    # ---- profiling pass (single stream, every kernel bracketed by events) ----
+    for _ in range(max(1, a.warmup)):
+        flush.zero_()
+        step_resident(False)
+    sync_all()
+    clf.reset_counters()
+    clf.stage_times(reset=True)
+    clf.set_profiling(True)
+    prof_steps = max(1, min(a.steps, 3))
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record(stream)
+    for _ in range(prof_steps):
+        step_resident(False)
+    p1.record(stream)
+    sync_all()
+    single_stream_ms = p0.elapsed_time(p1) / prof_steps
+    stage = clf.stage_times(reset=True)
+    clf.set_profiling(False)
+    counters = clf.counters()
+    search_c = clf.stage_counters("search")
+    launches_prof = counters["n_launches"]
 
     # ---- kernel-resident timing ----
     for _ in range(a.warmup):
-        flush.zero_()
-        step_resident()
+        fork()
+        step_resident(True)
+        join()
     sync_all()
     clf.reset_counters()
     clf.taxon_counts_reset()
-    clf.stage_times(reset=True)
-    clf.set_profiling(True)
     sampler = ClockSampler(local_rank)
     sampler.start()
     t_wall0 = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
+    fork()
     for _ in range(a.steps):
-        step_resident()  # no L2 flush needed: index and the step's distinct batches are each larger than L2
+        step_resident(True)  # no L2 flush needed: index and the step's distinct batches are each larger than L2
+    join()
     final_reduce()
     e1.record(stream)
     sync_all()
     t_wall = time.perf_counter() - t_wall0
     dev_ms = e0.elapsed_time(e1)
-    stage = clf.stage_times(reset=True)
-    clf.set_profiling(False)
-    counters = clf.counters()
-    search_c = clf.stage_counters("search")
     # results must be complete (no reads left deferred) -- fetch also checks device error flags
     clf.fetch(batches[0], stream=sptr, out=outs[0])
-    launches_resident = counters["n_launches"]
+    launches_resident = clf.counters()["n_launches"] + launches_prof
     tax_total = int(clf.taxon_counts()[clf.node_cnt + 1]) if world == 1 else int(reduced[0][clf.node_cnt + 1])
 
     # ---- end-to-end timing (pinned host buffers in, host results out) ----
@@ -486,8 +524,8 @@ def main():
         per_rank = 32 if occ else 120
         per_access = 0 if occ else 72
         s_bytes = (per_rank * search_c["n_rank"] + per_access * search_c["n_access"] + 16 * search_c["n_search"]
-                   + (bases * a.steps * 9) // 32)
-        s_bytes_ref = 120 * search_c["n_rank"] + 72 * search_c["n_access"] + 16 * search_c["n_search"] + bases * a.steps
+                   + (bases * prof_steps * 9) // 32)
+        s_bytes_ref = 120 * search_c["n_rank"] + 72 * search_c["n_access"] + 16 * search_c["n_search"] + bases * prof_steps
         per_launch_s = (s_ms / max(s_launch, 1)) / 1000.0
         achieved = (s_bytes / max(s_launch, 1)) / per_launch_s / 1e9 if s_ms > 0 else 0.0
         achieved_ref = (s_bytes_ref / max(s_launch, 1)) / per_launch_s / 1e9 if s_ms > 0 else 0.0
@@ -505,7 +543,7 @@ def main():
         index_bytes = clf.info(15) if occ else clf.info(19) or clf.hbm_bytes
         hbm_resident = index_bytes > L2_BYTES
         achieved_dram = (traffic / per_launch_s / 1e9) if (traffic and s_ms > 0) else None
-        total_alg = algorithmic_bytes(counters, n * a.steps, bases * a.steps)
+        total_alg = algorithmic_bytes(counters, n * prof_steps, bases * prof_steps) * (a.steps / prof_steps)
         line = {
             "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": dev_ms_max / a.steps, "higher_is_better": True, "scaling": "weak",
@@ -548,8 +586,10 @@ def main():
                                  ("occ sectors (%.0f MB) fit the 126 MB L2: `achieved` is L2 bandwidth, not HBM; DRAM traffic is in "
                                   "`traffic`" % (clf.info(15) / 1e6)),
                          "pipeline_algorithmic_gbs": total_alg / (dev_ms_max / 1000.0) / 1e9 / world},
-            "stage_ms_per_step": {k: v[0] / a.steps for k, v in stage.items()},
-            "ops_per_read": {k: counters[k] / (n * a.steps) for k in
+            "stage_ms_per_step": {k: v[0] / prof_steps for k, v in stage.items()},
+            "single_stream_ms_per_step": single_stream_ms,
+            "resident_streams": NSTREAM,
+            "ops_per_read": {k: counters[k] / (n * prof_steps) for k in
                              ("n_rank", "n_access", "n_search", "n_locate", "n_lf", "n_extend")},
             "clocks": sampler.summary(),
             "wall_ms_per_step": wall_ms_max / a.steps,
