@@ -31,7 +31,7 @@ class Params(C.Structure):
                 ("consider_secondary_hit_len", C.c_uint64),
                 ("consider_secondary_score_factor", C.c_double),
                 ("layout", C.c_int32), ("max_batch_reads", C.c_int32),
-                ("arena_rows", C.c_uint64), ("expand_taxid", C.c_int32), ("reserved_", C.c_int32)]
+                ("arena_rows", C.c_uint64), ("expand_taxid", C.c_int32), ("unlimited_cap", C.c_int32)]
 
 
 class ReadBatch(C.Structure):
@@ -201,12 +201,14 @@ class Classifier:
         p.layout, p.max_batch_reads, p.arena_rows = layout, max_batch_reads, arena_rows
         p.expand_taxid = 1 if expand_taxid else 0
         self.params = p
-        self.k = k
+        self.max_result = k
+        self.k = k if k > 0 else 64  # id slots per read (the stride of the ids arrays); -k <= 0 = unlimited, see info(24)
         self.h = C.c_void_p()
         st = self.L.cfr_open(idx_prefix.encode(), C.byref(p), device, C.byref(self.h))
         if st != 0:
             self.h = None
             raise CfrError(st, self.L.cfr_last_error().decode())
+        self.k = int(self.L.cfr_index_info(self.h, 24))
 
     # -- lifetime ----------------------------------------------------------
     def close(self):

@@ -105,6 +105,7 @@ struct cfr_handle {
   double open_seconds = 0.0;
   int sm_count = 148;
   int search_blocks = 10;  // resident 128-thread blocks per SM targeted by k_search (CFR_B200_SEARCH_BLOCKS)
+  int pair_fetch = 2;  // 2 = cp.async staging rounds, 1 = LDG + STS rounds (CFR_B200_PAIR_FETCH)
   int pair_search_blocks = 8;  // the same for the pair-line search kernel (CFR_B200_PAIR_SEARCH_BLOCKS)
   int occ_load = 4;    // how k_search / k_locate fetch a sector: 4 = one 256-bit load, 0 = two 128-bit loads (CFR_B200_OCC_LOAD)
   bool pos32 = false;  // 32-bit BWT positions in k_search / k_locate (collections below 2^32 rows; CFR_B200_POS64=1 disables)
@@ -508,7 +509,7 @@ int upload_chunk(cfr_handle *h, const cfr_read_batch *in, u64 r0, u64 r1, cfr_de
   if ((st = b->best.ensure(arena * 8))) return st;
   if ((st = b->tmp.ensure(arena * 8))) return st;
   if ((st = b->results.ensure(n * sizeof(DevResult)))) return st;
-  if ((st = b->out_ids.ensure(n * (u64)h->P.max_result * 8))) return st;
+  if ((st = b->out_ids.ensure(n * (u64)h->P.ids_stride * 8))) return st;
   if ((st = b->deferred.ensure(n * 4 * 2))) return st;
   if ((st = b->dust_list.ensure(n * 4 * (u64)mates))) return st;
   if ((st = b->scalars.ensure(64))) return st;
@@ -517,7 +518,7 @@ int upload_chunk(cfr_handle *h, const cfr_read_batch *in, u64 r0, u64 r1, cfr_de
     if ((st = b->masked.ensure(b->seq_bytes + 64))) return st;
   }
   if (h->params.expand_taxid) {  // a read's lists hold at most as many ids as it has arena rows
-    if ((st = b->exp_cnt.ensure(n * (u64)h->P.max_result * 4))) return st;
+    if ((st = b->exp_cnt.ensure(n * (u64)h->P.ids_stride * 4))) return st;
     if ((st = b->exp_off.ensure(n * 8))) return st;
     if ((st = b->exp_ids.ensure(arena * 8))) return st;
   }
@@ -690,6 +691,7 @@ int check_device_errors(cfr_handle *h, cudaStream_t s) {
   CUDA_TRY(cudaStreamSynchronize(s));
   if (flags & 1ull) return fail(CFR_ERR_OVERFLOW, "taxonomy lineage deeper than the device path capacity");
   if (flags & 2ull) return fail(CFR_ERR_OVERFLOW, "expanded tax id lists exceed the batch's list area; raise cfr_params.arena_rows");
+  if (flags & 4ull) return fail(CFR_ERR_OVERFLOW, "a read has more best-scoring sequences than cfr_params.unlimited_cap keeps (-k 0)");
   return CFR_OK;
 }
 
@@ -705,7 +707,7 @@ int fetch_expanded(cfr_handle *h, cfr_device_batch *b, uint32_t *exp_cnt, uint64
   CUDA_TRY(cudaStreamSynchronize(s));
   *exp_n = used;
   if (used > exp_cap) return fail(CFR_ERR_OVERFLOW, "exp_ids is too small for this batch (see *exp_n)");
-  const u64 k = (u64)h->P.max_result;
+  const u64 k = (u64)h->P.ids_stride;
   CUDA_TRY(cudaMemcpyAsync(exp_cnt, b->exp_cnt.p, b->n_reads * k * 4, cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaMemcpyAsync(exp_off, b->exp_off.p, b->n_reads * 8, cudaMemcpyDeviceToHost, s));
   if (used) CUDA_TRY(cudaMemcpyAsync(exp_ids, b->exp_ids.p, used * 8, cudaMemcpyDeviceToHost, s));
@@ -743,7 +745,6 @@ int cfr_open(const char *idx_prefix, const cfr_params *p, int device, cfr_handle
   const auto t_open0 = std::chrono::steady_clock::now();
   cfr_params params;
   if (p) params = *p; else cfr_default_params(&params);
-  if (params.max_result <= 0) return fail(CFR_ERR_UNSUPPORTED, "-k must be >= 1 on the B200 path");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     return fail(CFR_ERR_CUDA, "no CUDA device available (this library has no CPU path)");
@@ -767,6 +768,9 @@ int cfr_open(const char *idx_prefix, const cfr_params *p, int device, cfr_handle
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess)
     return bail(fail(CFR_ERR_CUDA, "cudaStreamCreate failed"));
   h->P.max_result = params.max_result;
+  // -k <= 0 reports every best-scoring sequence (Classifier.hpp:620-623, :784-785): the id area then keeps
+  // unlimited_cap slots per read (a read with more raises CFR_ERR_OVERFLOW, never a silently shortened list)
+  h->P.ids_stride = params.max_result > 0 ? params.max_result : (params.unlimited_cap > 0 ? params.unlimited_cap : 64);
   h->P.min_hit_len = params.min_hit_len > 0 ? params.min_hit_len : infer_min_hit_len(h->file.n);
   h->P.hitk_factor = params.max_result_per_hit_factor;
   h->P.secondary_len = params.consider_secondary_hit_len;
@@ -776,6 +780,7 @@ int cfr_open(const char *idx_prefix, const cfr_params *p, int device, cfr_handle
   if (const char *e = getenv("CFR_B200_QUORUM")) h->P.quorum = std::max(1, atoi(e));
   if (const char *e = getenv("CFR_B200_SEARCH_BLOCKS")) h->search_blocks = std::max(1, atoi(e));
   if (const char *e = getenv("CFR_B200_PAIR_SEARCH_BLOCKS")) h->pair_search_blocks = std::max(1, atoi(e));
+  if (const char *e = getenv("CFR_B200_PAIR_FETCH")) h->pair_fetch = atoi(e) == 1 ? 1 : 2;
   if (const char *e = getenv("CFR_B200_DUST_SCREEN")) h->dust_screen = atoi(e) != 0;
   if (const char *e = getenv("CFR_B200_DUST_QUORUM")) h->dust_quorum = std::max(0, atoi(e));
   if (const char *e = getenv("CFR_B200_DUST_LANES")) h->dust_lanes = std::min(32, std::max(1, atoi(e)));
@@ -861,7 +866,7 @@ int cfr_open(const char *idx_prefix, const cfr_params *p, int device, cfr_handle
     int shift = 0;
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
-    const u64 budget = std::min<u64>((u64)free_b / 4, 24ull << 30);
+    const u64 budget = std::min<u64>((u64)free_b * 2 / 5, 48ull << 30);
     while (shift < 8 && ((h->ix.n >> shift) + 1) * 4 > budget) ++shift;
     if (const char *e = getenv("CFR_B200_DENSE_LOCATE")) shift = atoi(e);
     if ((st = build_dense_locate(h, shift))) return bail(st);
@@ -937,6 +942,7 @@ uint64_t cfr_index_info(const cfr_handle *h, int which) {
     case 21: return (uint64_t)h->ix.wide_width;
     case 22: return h->pos32 ? 32u : 64u;
     case 23: return (uint64_t)h->pair_bytes;
+    case 24: return (uint64_t)h->P.ids_stride;
     default: return 0;
   }
 }
@@ -965,9 +971,13 @@ int cfr_classify_resident(cfr_handle *h, cfr_device_batch *b, void *stream) {
   b->classified = true;
   b->quant_counted = false;
   if (h->layout == CFR_LAYOUT_OCCLINE) {
-    if (h->ix.pairs) {
-      if (h->pos32) return run_first<BwtOccLine, BwtOccLine32T<4>, BwtPairT<true>>(h, b, s);
-      return run_first<BwtOccLine, BwtOccLineT<4>, BwtPairT<true>>(h, b, s);
+    if (h->ix.pairs) {  // pair lines in the search kernel; staged by cp.async rounds (CFR_B200_PAIR_FETCH=1: LDG + STS rounds)
+      if (h->pair_fetch == 1) {
+        if (h->pos32) return run_first<BwtOccLine, BwtOccLine32T<4>, BwtPairT<1>>(h, b, s);
+        return run_first<BwtOccLine, BwtOccLineT<4>, BwtPairT<1>>(h, b, s);
+      }
+      if (h->pos32) return run_first<BwtOccLine, BwtOccLine32T<4>, BwtPairT<2>>(h, b, s);
+      return run_first<BwtOccLine, BwtOccLineT<4>, BwtPairT<2>>(h, b, s);
     }
     if (h->pos32) {
       if (h->occ_load == 0) return run_first<BwtOccLine, BwtOccLine32T<0>>(h, b, s);
@@ -995,8 +1005,8 @@ int cfr_batch_fetch(cfr_handle *h, cfr_device_batch *b, cfr_result *results, uin
   static_assert(sizeof(cfr_result) == sizeof(DevResult), "result layout");
   if (b->n_reads) {
     CUDA_TRY(cudaMemcpyAsync(results, b->results.p, b->n_reads * sizeof(DevResult), cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaMemcpyAsync(ids, b->out_ids.p, b->n_reads * (u64)h->P.max_result * 8, cudaMemcpyDeviceToHost, s));
-    h->d2h_bytes += b->n_reads * (sizeof(DevResult) + (u64)h->P.max_result * 8);
+    CUDA_TRY(cudaMemcpyAsync(ids, b->out_ids.p, b->n_reads * (u64)h->P.ids_stride * 8, cudaMemcpyDeviceToHost, s));
+    h->d2h_bytes += b->n_reads * (sizeof(DevResult) + (u64)h->P.ids_stride * 8);
   }
   if ((st = check_device_errors(h, s))) return st;
   if (b->quant_counted) return CFR_OK;  // a resident batch counts once per classification, however often it is fetched
@@ -1048,7 +1058,7 @@ static int quant_coalesce_batch(cfr_handle *h, cfr_device_batch *b, cudaStream_t
   const u64 n = b->n_reads;
   if (!q.on || n == 0) return CFR_OK;
   if (n >= (1ull << 31)) return fail(CFR_ERR_UNSUPPORTED, "quantification: batch too large");
-  const int K = h->P.max_result, W = K + 1;
+  const int K = h->P.ids_stride, W = K + 1;
   int st;
   if ((st = q.words.ensure(n * W * 4)) || (st = q.keys_a.ensure(n * 8)) || (st = q.keys_b.ensure(n * 8)) ||
       (st = q.idx_a.ensure(n * 4)) || (st = q.idx_b.ensure(n * 4)) || (st = q.flags.ensure(n)) || (st = q.heads.ensure(n * 4)) ||
@@ -1105,7 +1115,7 @@ static int pipeline_drain(cfr_handle *h, int slot, cfr_result *results, uint64_t
                                              : finish_deferred<BwtRunBlock, BwtRunBlock>(h, b, sc);
     if (st) return st;
     CUDA_TRY(cudaMemcpyAsync(results, b->results.p, b->n_reads * sizeof(DevResult), cudaMemcpyDeviceToHost, sc));
-    CUDA_TRY(cudaMemcpyAsync(ids, b->out_ids.p, b->n_reads * (u64)h->P.max_result * 8, cudaMemcpyDeviceToHost, sc));
+    CUDA_TRY(cudaMemcpyAsync(ids, b->out_ids.p, b->n_reads * (u64)h->P.ids_stride * 8, cudaMemcpyDeviceToHost, sc));
     CUDA_TRY(cudaStreamSynchronize(sc));
   }
   return quant_coalesce_batch(h, b, sc);
@@ -1157,7 +1167,7 @@ int cfr_classify_batch(cfr_handle *h, const cfr_read_batch *in, cfr_result *resu
     capped.push_back(n);
     bounds.swap(capped);
   }
-  const u64 k = (u64)h->P.max_result;
+  const u64 k = (u64)h->P.ids_stride;
   CUDA_TRY(cudaEventRecord(h->ev_start, sc));  // everything below is ordered after the caller's stream
   CUDA_TRY(cudaStreamWaitEvent(h->s_in, h->ev_start, 0));
   CUDA_TRY(cudaStreamWaitEvent(h->s_comp[0], h->ev_start, 0));
@@ -1241,7 +1251,7 @@ int cfr_submit_batch_masked(cfr_handle *h, const cfr_read_batch *in, cfr_result 
     h->tr_host_submit[slot] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count();
   }
   CUDA_TRY(cudaStreamWaitEvent(h->s_out, h->ev_comp[slot], 0));
-  const u64 k = (u64)h->P.max_result;
+  const u64 k = (u64)h->P.ids_stride;
   if (in->n_reads) {
     CUDA_TRY(cudaMemcpyAsync(results, b->results.p, in->n_reads * sizeof(DevResult), cudaMemcpyDeviceToHost, h->s_out));
     CUDA_TRY(cudaMemcpyAsync(ids, b->out_ids.p, in->n_reads * k * 8, cudaMemcpyDeviceToHost, h->s_out));
@@ -1326,7 +1336,7 @@ int cfr_format_tsv(const cfr_handle *h, const char *read_id, const cfr_result *r
   if (!h || !read_id || !r || !buf) return CFR_ERR_ARG;
   size_t off = 0;
   if (r->n_assign > 0) {
-    const int m = std::min<int>(r->n_assign, h->P.max_result);
+    const int m = std::min<int>(r->n_assign, h->P.ids_stride);
     for (int i = 0; i < m; ++i) {
       const char *name = r->by_rank ? cfr_rank_name(h, ids[i]) : cfr_seq_name(h, ids[i]);
       const uint64_t tax = r->by_rank ? cfr_orig_taxid(h, ids[i]) : cfr_orig_taxid(h, cfr_seq_taxid(h, ids[i]));
@@ -1487,7 +1497,7 @@ int cfr_counts_allreduce_local(cfr_handle **handles, int n_handles, uint64_t *ou
 
 int cfr_quant_enable(cfr_handle *h, uint64_t min_score, uint64_t min_hit_length) {
   if (!h) return fail(CFR_ERR_ARG, "null argument");
-  if (h->P.max_result > 64) return fail(CFR_ERR_UNSUPPORTED, "quantification keeps at most 64 targets per read");
+  if (h->P.ids_stride > 64) return fail(CFR_ERR_UNSUPPORTED, "quantification keeps at most 64 targets per read");
   h->quant.on = true;
   h->quant.min_score = min_score;
   h->quant.min_hit = min_hit_length;
@@ -1514,10 +1524,10 @@ int cfr_quant_report(cfr_handle **handles, int n_handles, const char *idx_prefix
   Quantifier q;
   std::string err;
   if (q.init(idx_prefix, err) != 0) return fail(CFR_ERR_IO, err);
-  const int W = handles[0]->P.max_result + 1;
+  const int W = handles[0]->P.ids_stride + 1;
   std::map<std::vector<u32>, u64> all;  // the replicas' tables merged (one process, one handle per GPU)
   for (int g = 0; g < n_handles; ++g) {
-    if (!handles[g] || handles[g]->P.max_result + 1 != W) return fail(CFR_ERR_ARG, "handles differ in -k");
+    if (!handles[g] || handles[g]->P.ids_stride + 1 != W) return fail(CFR_ERR_ARG, "handles differ in -k");
     for (auto &kv : handles[g]->quant.table) all[kv.first] += kv.second;
   }
   for (auto &kv : all) {

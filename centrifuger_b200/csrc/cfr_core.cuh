@@ -660,6 +660,25 @@ CFR_HD PairQuery pair_query_scalar(const DevIndex &ix, int c1, int c2, u64 x) {
 #define CFR_PAIR_SLOT_WORDS 36
 #define CFR_PAIR_NO_LINE 0xffffffffu
 
+// The same staging with asynchronous copies (cp.async, 16 bytes per lane): groups of EIGHT adjacent lanes fetch
+// one line per round as one coalesced 128-byte request, eight rounds, and no round waits for the one
+// before it -- all 32 lines of the warp are in flight together, without passing through registers.
+CFR_D void pair_stage_warp_async(const DevIndex &ix, u32 L, u32 *slots) {
+  const int lane = threadIdx.x & 31, sub = lane & 7, gbase = lane & ~7;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const u32 lj = __shfl_sync(0xffffffffu, L, gbase + j);
+    if (lj != CFR_PAIR_NO_LINE) {  // uniform over the eight lanes of the group
+      const char *src = reinterpret_cast<const char *>(ix.pairs + lj) + 16 * sub;
+      const u32 dst = (u32)__cvta_generic_to_shared(slots + (gbase + j) * CFR_PAIR_SLOT_WORDS + sub * 4);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+    }
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncwarp();
+}
+
 // must be called by all 32 lanes; `slots` = this warp's 32 slots
 CFR_D void pair_stage_warp(const DevIndex &ix, u32 L, u32 *slots) {
   const int lane = threadIdx.x & 31, sub = lane & 3, gbase = lane & ~3;
@@ -806,10 +825,12 @@ CFR_HD void pair_constants(const DevIndex &ix, u64 *out) {
 // Two steps of FMIndex::BackwardSearch's loop (FMIndex.hpp:495-508) from the range [sp, ep]: first c1,
 // then -- if c2 >= 0 -- c2.  Returns how many succeeded (0, 1, 2) and leaves the range after the last
 // successful one in (sp, ep).  The operation counters advance as the reference's calls would.
-// COOP (device): one lane per search, lines fetched by the warp cooperatively (pair_fetch_warp); the call
-// is warp-uniform -- lanes without a step to do pass go = false.  !COOP: one lane reads whole lines.
-template <bool COOP>
+// MODE 1 / 2 (device): one lane per search, lines staged in shared memory by the warp cooperatively
+// (pair_stage_warp / pair_stage_warp_async); the call is warp-uniform -- lanes without a step to do pass
+// go = false.  MODE 0: one lane reads whole lines (host twin).
+template <int MODE>
 struct BwtPairT {
+  enum { COOP = MODE != 0 };
   typedef u64 pos_t;
   enum { LANES = 1, PAIR = 1, STEPS_COUNTED_AT_CLOSE = 0 };
   static CFR_HD bool leader() { return true; }
@@ -832,12 +853,14 @@ struct BwtPairT {
       const u32 *mine = slots + (threadIdx.x & 31) * CFR_PAIR_SLOT_WORDS;
       c1 &= 3;  // lanes with go == false carry anything
       const bool near = range && Le == La;
-      pair_stage_warp(ix, go ? (u32)La : CFR_PAIR_NO_LINE, slots);
+      if (MODE == 2) pair_stage_warp_async(ix, go ? (u32)La : CFR_PAIR_NO_LINE, slots);
+      else pair_stage_warp(ix, go ? (u32)La : CFR_PAIR_NO_LINE, slots);
       if (go) pair_query_slot(ix, mine, La, c1, c2q, (int)(sp & 63), (int)(xe & 63), near, qa, qe);
       __syncwarp();
       const bool far = go && range && Le != La;
       if (__ballot_sync(0xffffffffu, far)) {  // the second boundary lies in another line: a few lanes per step
-        pair_stage_warp(ix, far ? (u32)Le : CFR_PAIR_NO_LINE, slots);
+        if (MODE == 2) pair_stage_warp_async(ix, far ? (u32)Le : CFR_PAIR_NO_LINE, slots);
+        else pair_stage_warp(ix, far ? (u32)Le : CFR_PAIR_NO_LINE, slots);
         if (far) {
           PairQuery dummy;
           pair_query_slot(ix, mine, Le, c1, c2q, (int)(xe & 63), 0, false, qe, dummy);
@@ -1681,7 +1704,11 @@ CFR_HD void score_read(const DevIndex &ix, const DevParams &p, const FinalHit *h
     res.secondary_score = second;
   }
 
-  if (nb <= p.max_result) {  // Classifier.hpp:784-797
+  if (nb <= p.max_result || p.max_result <= 0) {  // Classifier.hpp:784-797 (-k 0: all of them, never reduced)
+    if (nb > p.ids_stride) {
+      *err_flags |= 4ull;  // more best-scoring sequences than the unlimited form keeps per read
+      nb = p.ids_stride;
+    }
     for (int i = 0; i < nb; ++i) out_ids[i] = best[i];
     res.n_assign = nb;
     res.by_rank = 0;

@@ -161,8 +161,8 @@ __global__ void __launch_bounds__(128) k_score(const __grid_constant__ DevIndex 
     if (na > 0) {
       ++n_cls;
       const DevResult &res = B.results[read];
-      const u64 *ids = B.out_ids + read * (u64)P.max_result;
-      const int m = na < P.max_result ? na : P.max_result;
+      const u64 *ids = B.out_ids + read * (u64)P.ids_stride;
+      const int m = na < P.ids_stride ? na : P.ids_stride;
       for (int i = 0; i < m; ++i) {
         u64 ct = ids[i];
         if (!res.by_rank) ct = ct < ix.seq_cnt ? (u64)ld32(ix.seq_to_tax + ct) : ix.node_cnt;

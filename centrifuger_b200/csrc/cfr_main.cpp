@@ -503,7 +503,7 @@ int main(int argc, char *argv[]) {
   // Three-stage pipeline over three rotating batches: the ingest thread parses batch i+1 while
   // the GPU classifies batch i and the output thread formats batch i-1 (ResultWriter::Output,
   // ResultWriter.hpp:199-236; rows in input order as in CentrifugerClass.cpp:690).
-  const int k = params.max_result;
+  const int k = h ? (int)cfr_index_info(h, 24) : (params.max_result > 0 ? params.max_result : 64);  // id slots per read
   const bool expandTaxid = params.expand_taxid != 0;  // --expand-taxid: one more TSV column
   const int NBATCH = 2 + 3 * nGpus;  // ingest (1) + in flight on each GPU (3) + output (1)
   std::vector<Batch> batches((size_t)NBATCH);

@@ -670,15 +670,15 @@ CFR_HD int score_stage(const DevIndex &ix, const DevParams &P, const ChunkDev &B
   res.hit_length = 0;
   res.n_assign = 0;
   res.by_rank = 0;
-  u64 *out = B.out_ids + read * (u64)P.max_result;
+  u64 *out = B.out_ids + read * (u64)P.ids_stride;
   const u64 a = w.arena_base;
   int nb = 0;
   score_read(ix, P, fh, (int)w.n_hits, B.seq_ids + a, B.rec0 + a, B.rec1 + a, B.best + a, B.tmp + a, res, out,
              err_flags, &nb);
-  for (int i = res.n_assign; i < P.max_result; ++i) out[i] = 0;  // unused id slots read as 0
+  for (int i = res.n_assign; i < P.ids_stride; ++i) out[i] = 0;  // unused id slots read as 0
   if (B.exp_cnt) {
-    u32 *cc = B.exp_cnt + read * (u64)P.max_result;
-    for (int i = 0; i < P.max_result; ++i) cc[i] = 0;
+    u32 *cc = B.exp_cnt + read * (u64)P.ids_stride;
+    for (int i = 0; i < P.ids_stride; ++i) cc[i] = 0;
     B.exp_off[read] = 0;
     if (res.by_rank) {  // the scoring records are done with: their space holds the lists until they are copied out
       u64 *lists = reinterpret_cast<u64 *>(B.rec0 + a);

@@ -111,7 +111,8 @@ struct DevIndex {
 };
 
 struct DevParams {
-  int max_result;
+  int max_result;  // -k; <= 0 = every best-scoring sequence is reported (Classifier.hpp:620-623, :784-785)
+  int ids_stride;  // id slots per read in out_ids: max_result, or the cap of the unlimited form
   int min_hit_len;
   int hitk_factor;
   u64 secondary_len;

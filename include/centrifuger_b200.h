@@ -48,7 +48,8 @@ typedef enum {
 /* replaces _classifierParam (Classifier.hpp:17-38) + the --no-dust switch
  * (CentrifugerClass.cpp:367) */
 typedef struct {
-  int32_t max_result;                /* -k            [1]  */
+  int32_t max_result;                /* -k            [1]; <= 0: every best-scoring sequence, never reduced by rank
+                                        (Classifier.hpp:620-623, :784-785) */
   int32_t min_hit_len;               /* --min-hitlen  [0 = infer, Classifier.hpp:113-129] */
   int32_t max_result_per_hit_factor; /* --hitk-factor [40] */
   int32_t dust;                      /* 1 = SDUST-mask reads first (reference default) */
@@ -60,7 +61,7 @@ typedef struct {
   int32_t expand_taxid;              /* --expand-taxid (_classifierParam.outputExpandedResult, Classifier.hpp:22):
                                         keep the ids that were promoted into each reported id; read them
                                         with cfr_fetch_expanded / cfr_batch_fetch_expanded  [0] */
-  int32_t reserved_;
+  int32_t unlimited_cap;             /* id slots per read when max_result <= 0 (report every best-scoring sequence) [0 = 64] */
 } cfr_params;
 
 /* One batch of reads, structure-of-arrays, HOST memory (pinned recommended).
@@ -76,7 +77,8 @@ typedef struct {
 } cfr_read_batch;
 
 /* replaces _classifierResult (Classifier.hpp:41-59).  The assignment ids of
- * read i are ids[i*max_result .. i*max_result + min(n_assign, max_result)). */
+ * read i are ids[i*S .. i*S + n_assign), S = the id stride: max_result, or with max_result <= 0
+ * unlimited_cap (cfr_index_info(h, 24) tells). */
 typedef struct {
   uint64_t score;
   uint64_t secondary_score;
@@ -176,7 +178,8 @@ void cfr_host_free(void *p);
  * 15 occ-sector bytes, 16 wide-lookup-table bytes, 17 dense-locate-table bytes,
  * 18 microseconds cfr_open took, 19 run-block bytes released after the transcode,
  * 20 dense-locate spacing (log2; 255 = none), 21 wide-lookup width (0 = none),
- * 22 width of the BWT positions the kernels walk with (32 / 64) */
+ * 22 width of the BWT positions the kernels walk with (32 / 64), 23 pair-line bytes,
+ * 24 id slots per read in the `ids` arrays (the stride) */
 uint64_t cfr_index_info(const cfr_handle *h, int which);
 
 /* Taxonomy look-ups used by ResultWriter (host tables) */

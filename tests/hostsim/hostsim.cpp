@@ -193,6 +193,7 @@ void *hostsim_open(const char *prefix, const cfr_params *p) {
     }
   }
   h->P.max_result = p->max_result;
+  h->P.ids_stride = p->max_result > 0 ? p->max_result : (p->unlimited_cap > 0 ? p->unlimited_cap : 64);
   h->P.min_hit_len = p->min_hit_len > 0 ? p->min_hit_len : infer_min_hit_len(f.n);
   h->P.hitk_factor = p->max_result_per_hit_factor;
   h->P.secondary_len = p->consider_secondary_hit_len;
@@ -234,7 +235,7 @@ u64 hostsim_pair_check(void *hh, u64 n_ranges, u64 seed) {
           }
         }
         u64 gsp = sp, gep = ep;
-        const int got = BwtPairT<false>::extend2(ix, true, c1, c2, gsp, gep, oc2);
+        const int got = BwtPairT<0>::extend2(ix, true, c1, c2, gsp, gep, oc2);
         if (got != want || (want > 0 && (gsp != wsp || gep != wep))) ++bad;
       }
   };
@@ -397,7 +398,7 @@ int hostsim_classify_expanded(void *hh, int dust, uint64_t arena_rows, const cfr
   std::vector<u32> seq_ids(arena_rows);
   std::vector<SeqRec> rec0(arena_rows), rec1(arena_rows);
   std::vector<DevResult> res(n + 1);
-  std::vector<u64> out_ids(n * P.max_result + 1);
+  std::vector<u64> out_ids(n * P.ids_stride + 1);
   std::vector<u64> taxon(ix.node_cnt + 3, 0);
   DevCounters cnt;
   memset(&cnt, 0, sizeof(cnt));
@@ -447,7 +448,7 @@ int hostsim_classify_expanded(void *hh, int dust, uint64_t arena_rows, const cfr
   u64 task_counter = 0, row_counter = 0;
   B.task_counter = &task_counter;
   B.row_counter = &row_counter;
-  if (h->use_pairs) search_tasks<BwtPairT<false>>(ix, P, B, n * S, oc);
+  if (h->use_pairs) search_tasks<BwtPairT<0>>(ix, P, B, n * S, oc);
   else if (h->layout == 2 && h->pos32) search_tasks<BwtOccLine32T<0>>(ix, P, B, n * S, oc);
   else if (h->layout == 2) search_tasks<BwtOccLine>(ix, P, B, n * S, oc);
   else search_tasks<BwtRunBlock>(ix, P, B, n * S, oc);
@@ -503,7 +504,7 @@ int hostsim_classify_expanded(void *hh, int dust, uint64_t arena_rows, const cfr
     results[i].query_length = res[i].query_length;
     results[i].n_assign = res[i].n_assign;
     results[i].by_rank = res[i].by_rank;
-    for (int k = 0; k < P.max_result; ++k) ids[i * P.max_result + k] = out_ids[i * P.max_result + k];
+    for (int k = 0; k < P.ids_stride; ++k) ids[i * P.ids_stride + k] = out_ids[i * P.ids_stride + k];
   }
   oc_fold(oc);
   if (counters) {

@@ -23,7 +23,7 @@ class Params(C.Structure):
                 ("consider_secondary_hit_len", C.c_uint64),
                 ("consider_secondary_score_factor", C.c_double),
                 ("layout", C.c_int32), ("max_batch_reads", C.c_int32),
-                ("arena_rows", C.c_uint64), ("expand_taxid", C.c_int32), ("reserved_", C.c_int32)]
+                ("arena_rows", C.c_uint64), ("expand_taxid", C.c_int32), ("unlimited_cap", C.c_int32)]
 
 
 class ReadBatch(C.Structure):
@@ -145,6 +145,7 @@ class HostSim:
     def __init__(self, prefix, **kw):
         self.L = lib()
         self.p = default_params(**kw)
+        self.stride = self.p.max_result if self.p.max_result > 0 else (self.p.unlimited_cap or 64)
         self.h = self.L.hostsim_open(prefix.encode(), C.byref(self.p))
         if not self.h:
             raise RuntimeError("hostsim_open failed for " + prefix)
@@ -191,7 +192,7 @@ class HostSim:
     def classify_expanded(self, reads1, reads2=None, arena_rows=0):
         """classify() plus, per read, the list of child-id lists (one per reported id)"""
         b, keep = make_batch(reads1, reads2)
-        n, k = len(reads1), self.p.max_result
+        n, k = len(reads1), self.stride
         res = np.zeros(n, dtype=RESULT_DTYPE)
         ids = np.zeros(max(1, n * k), dtype=np.uint64)
         exp_cnt = np.zeros(max(1, n * k), dtype=np.uint32)
@@ -210,13 +211,13 @@ class HostSim:
         b, keep = make_batch(reads1, reads2)
         n = len(reads1)
         res = np.zeros(n, dtype=RESULT_DTYPE)
-        ids = np.zeros(max(1, n * self.p.max_result), dtype=np.uint64)
+        ids = np.zeros(max(1, n * self.stride), dtype=np.uint64)
         cnt = Counters()
         st = self.L.hostsim_classify(self.h, self.p.dust, arena_rows, C.byref(b), res.ctypes.data,
                                      ids.ctypes.data, C.byref(cnt))
         if st != 0:
             raise RuntimeError("hostsim_classify status %d" % st)
-        return res, ids.reshape(-1, self.p.max_result) if n else ids, \
+        return res, ids.reshape(-1, self.stride) if n else ids, \
             {k: getattr(cnt, k) for k, _ in Counters._fields_}
 
 

@@ -25,7 +25,7 @@ def _compare(idx, files, layout, arena_rows=0, limit=None, check_counters=True, 
             t = o.result_tuple(o.query(r1[i], r2[i] if r2 else None))
             exp.append(t[:7])
         res, ids, cnt = hs.classify(r1, r2, arena_rows=arena_rows)
-        got = result_tuples(res, ids, hs.p.max_result)
+        got = result_tuples(res, ids, hs.stride)
         assert got == exp
         oc = o.counters()
         for k in ("n_rank", "n_access", "n_search", "n_locate", "n_lf", "n_extend"):
@@ -60,6 +60,17 @@ def test_tiny_all_read_sets(tiny_dir, layout, variant):
         fs = [os.path.join(tiny_dir, f) for f in files]
         for kw in (dict(), dict(k=5), dict(k=3, hitk_factor=2), dict(dust=False, min_hit_len=16),
                    dict(k=2, hitk_factor=0)):
+            _compare(idx, fs, layout, **kw)
+
+
+@pytest.mark.parametrize("layout", [1, 2, 4])
+def test_unlimited_results_k0(tiny_dir, layout):
+    """-k 0 (and negative -k): every best-scoring sequence is reported, nothing is reduced by rank, every row of a
+    hit is resolved (Classifier.hpp:620-623, :784-785)"""
+    idx = os.path.join(tiny_dir, "idx")
+    for files in (["se_100.fq"], ["pe_100_1.fq", "pe_100_2.fq"], ["edge.fq"], ["se_com.fq"]):
+        fs = [os.path.join(tiny_dir, f) for f in files]
+        for kw in (dict(k=0), dict(k=-3, hitk_factor=2), dict(k=0, dust=False, min_hit_len=16)):
             _compare(idx, fs, layout, **kw)
 
 
