@@ -1,29 +1,31 @@
 #!/usr/bin/env python
 """bench.py -- read pairs/s of the classification hot path on B200 (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c3|c2|...]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c4|c5|c3|c2|...]
 
-One "step" = one pass of the hot path over the workload's reads.  Default workload (every N):
-BASELINE.json configs[2] -- synthetic 2 Gbp / 500-taxa index (HBM-resident: 1 GB of occ sectors,
-larger than the 126 MB L2), 10 M x 2x150 bp read pairs per step per GPU as ten distinct 1 M-pair
-device batches, -k 5.  Reads come from the seeded generator (tools/gen_data.py); the index is
-built by the unmodified reference builder (tools/make_data.py) and loaded unchanged.
+One "step" = one pass of the hot path over the workload's reads.  Default workload (every N): BASELINE.json
+configs[3] -- a synthetic 20 Gbp / 5000-sequence collection generated AND indexed on the GPU by this repo's
+builder (tools/make_data.py: the files are ordinary *.cfr, the reference binary loads them too), HBM-resident
+(10 GB of occ sectors + 40 GB of pair lines, far larger than the 126 MB L2), 10 M x 2x150 bp read pairs per
+step per GPU as ten distinct 1 M-pair device batches, -k 5.  `--workload c5` is configs[4] (140 Gbp, one replica
+per GPU), `c3` configs[2] (2 Gbp, index from the unmodified reference builder), `c2` configs[1].  Reads come from
+seeded generators.
 
 Numbers on the JSON line:
   value     pairs/s with the batches resident in HBM (cfr_classify_resident), CUDA-event time
   e2e       pairs/s through cfr_submit_batch / cfr_wait_batch with pinned HOST buffers: H2D of the
             reads, all kernels, D2H of the results, every step
-  roofline  dominant kernel (k_search).  `achieved` = its ALGORITHMIC bytes in this library's HBM
-            layout (32 B occ sector per rank, 16 B per lookup probe, 2.25 bits per read base; the
-            operations are counted in-kernel) / its CUDA-event time.  `achieved_dram` = the DRAM
-            bytes ncu measured for the same launch (profiles/traffic.json) / the same time.  `bound`
-            says "hbm" only when the sector array is larger than L2.
-  cpu_baseline  the reference binary (oracle/_ref/centrifuger -t <cores>) on a bounded
-            sample of the same reads, same box
+  cli_e2e   the drop-in binary, FASTQ files -> TSV, on the step's reads (20 M reads at the default workload): process
+            start to exit, with the seconds each pipeline stage (ingest / device / output) was busy
+  roofline  dominant kernel (k_search).  `achieved` = its ALGORITHMIC bytes in this library's HBM layout
+            (32 B per rank -- the pair lines serve the four ranks of two BackwardExtend steps with one 128-byte
+            line --, 16 B per lookup probe, 2.25 bits per read base; the operations are counted in-kernel) / its
+            CUDA-event time.  `achieved_dram` = the DRAM bytes ncu measured for the same launch
+            (profiles/traffic.json) / the same time.  `bound` says "hbm" only when the sector array is larger than L2.
+  cpu_baseline  the reference binary (oracle/_ref/centrifuger -t <cores>) on a bounded sample of the same reads, same box
 
-Multi-GPU (torchrun, one rank per GPU): reads shard across ranks, the index is replicated per
-GPU, no data-path collective; NCCL all-reduces the per-taxon counters ONCE, after the last step
-(inside the timed region); weak scaling.
+Multi-GPU (torchrun, one rank per GPU): reads shard across ranks, the index is replicated per GPU, no data-path
+collective; NCCL all-reduces the per-taxon counters ONCE, after the last step (inside the timed region); weak scaling.
 """
 import argparse
 import json
@@ -209,6 +211,70 @@ def write_fastq_sample(seq, off, n, path, suffix=""):
                 f.write(b"@r%d%s\n%s\n+\n%s\n" % (i, suffix.encode(), s, b"I" * len(s)))
 
 
+def write_fastq_fixed(f, seq, n, rl, first_id, suffix):
+    """n reads of one length appended to the open file f as 4-line FASTQ records with fixed-width ids
+    (@r%09d<suffix>), built with numpy (20 M reads in seconds instead of a Python loop)."""
+    sfx = np.frombuffer(suffix.encode(), dtype=np.uint8)
+    head = 2 + 9 + len(sfx) + 1
+    rec = head + rl + 3 + rl + 1
+    a = np.empty((n, rec), dtype=np.uint8)
+    a[:, 0], a[:, 1] = ord("@"), ord("r")
+    ids = np.arange(first_id, first_id + n, dtype=np.int64)
+    for d in range(9):
+        a[:, 2 + d] = (ids // 10 ** (8 - d)) % 10 + 48
+    a[:, 11:11 + len(sfx)] = sfx
+    a[:, head - 1] = 10
+    a[:, head:head + rl] = np.asarray(seq[:n * rl]).reshape(n, rl)
+    a[:, head + rl:head + rl + 3] = np.frombuffer(b"\n+\n", dtype=np.uint8)
+    a[:, head + rl + 3:head + 2 * rl + 3] = ord("I")
+    a[:, rec - 1] = 10
+    f.write(a.data)
+
+
+def run_cli_e2e(idx, w, batches_np, n_gpus=1):
+    """The drop-in binary end to end: FASTQ files -> centrifuger-b200 -> TSV (to /dev/null, like the reference arm), process
+    start to exit, index load included; the stage seconds come from the binary itself (CFR_B200_STAGE_REPORT)."""
+    exe = os.path.join(ROOT, "centrifuger_b200", "centrifuger-b200")
+    if not os.path.exists(exe):
+        return None
+    d = tempfile.mkdtemp(prefix="cfr_cli_e2e_")
+    try:
+        rl = w["rlen"]
+        t0 = time.perf_counter()
+        f1p, f2p = os.path.join(d, "r_1.fq"), os.path.join(d, "r_2.fq")
+        n_total = 0
+        with open(f1p, "wb") as f1, open(f2p, "wb") as f2:
+            for seq1, off1, seq2, off2 in batches_np:
+                n = len(off1) - 1
+                write_fastq_fixed(f1, seq1, n, rl, n_total, "/1" if seq2 is not None else "")
+                if seq2 is not None:
+                    write_fastq_fixed(f2, seq2, n, rl, n_total, "/2")
+                n_total += n
+        t_write = time.perf_counter() - t0
+        files = ["-1", f1p, "-2", f2p] if w["paired"] else ["-u", f1p]
+        cmd = [exe, "-x", idx, "-k", str(w["k"])] + files + (["--gpus", str(n_gpus)] if n_gpus > 1 else [])
+        env = dict(os.environ, CFR_B200_STAGE_REPORT="1")
+        t0 = time.perf_counter()
+        with open(os.devnull, "wb") as dn:
+            r = subprocess.run(cmd, stdout=dn, stderr=subprocess.PIPE, env=env)
+        wall = time.perf_counter() - t0
+        if r.returncode != 0:
+            return {"error": r.stderr.decode()[-300:]}
+        stages = {}
+        for ln in r.stderr.decode().splitlines():
+            if ln.startswith("[cfr-stages]"):
+                stages = json.loads(ln[len("[cfr-stages]"):])
+        pipe = stages.get("pipeline_s", wall)
+        fq_bytes = os.path.getsize(f1p) + (os.path.getsize(f2p) if w["paired"] else 0)
+        return {"value": n_total / wall, "unit": "pairs/s" if w["paired"] else "reads/s", "value_after_index_load": n_total / pipe,
+                "reads": n_total * (2 if w["paired"] else 1), "fastq_bytes": fq_bytes, "wall_s": wall, "index_load_s": wall - pipe,
+                "fastq_gb_per_s_after_load": fq_bytes / pipe / 1e9, "stages": stages, "fastq_write_s": t_write,
+                "command": "centrifuger-b200 -x IDX -k %d %s > /dev/null" % (w["k"], "-1 r_1.fq -2 r_2.fq" if w["paired"] else "-u r.fq")}
+    finally:
+        import shutil
+        shutil.rmtree(d, ignore_errors=True)
+
+
 def run_reference_cpu(idx, w, seq1, off1, seq2, off2, n_sample, threads, repeat=1, t_load=None):
     """Time oracle/_ref/centrifuger (the unmodified reference) on the first n_sample reads of a
     batch, taken `repeat` times over (one process, `repeat` x n_sample reads).
@@ -268,6 +334,7 @@ def main():
     ap.add_argument("--reads", type=int, default=0, help="override reads per step per GPU")
     ap.add_argument("--cpu-sample", type=int, default=0, help="reads in the CPU-baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cli", action="store_true", help="skip the drop-in binary's FASTQ -> TSV run (cli_e2e)")
     ap.add_argument("--no-dust", action="store_true")
     ap.add_argument("--chunk", type=int, default=0, help="reads per device chunk in the end-to-end path (0 = auto)")
     a = ap.parse_args()
@@ -479,6 +546,34 @@ def main():
     sync_all()
     e2e_s = time.perf_counter() - t0
     link1 = (clf.info(13), clf.info(14))
+    # The same loop with the bases packed by the producer (cfr_pack_reads -> cfr_submit_packed): 2-bit codes + N bits, 12 bytes
+    # per 32 bases over the host link instead of 32.  Packing happens where the reads are produced (the CLI's ingest stage
+    # does it while parsing), here before the timed region; what is timed is H2D of the packed words, kernels, D2H.
+    t0 = time.perf_counter()
+    packed = [cb.pack_batch(*p, threads=min(16, os.cpu_count() or 1), pinned=True) for p in pinned]
+    pack_s = time.perf_counter() - t0
+
+    def run_e2e_packed(k_steps):
+        inflight = []
+        i = 0
+        for _ in range(k_steps):
+            for pk, _keep in packed:
+                inflight.append(clf.submit_packed(pk, stream=sptr, out=outs[i % NOUT]))
+                i += 1
+                if len(inflight) == NOUT:
+                    clf.wait(inflight.pop(0)[0])
+        while inflight:
+            clf.wait(inflight.pop(0)[0])
+        final_reduce()
+
+    run_e2e_packed(min(a.warmup, 2))
+    sync_all()
+    plink0 = (clf.info(13), clf.info(14))
+    t0 = time.perf_counter()
+    run_e2e_packed(a.steps)
+    sync_all()
+    e2e_packed_s = time.perf_counter() - t0
+    plink1 = (clf.info(13), clf.info(14))
     # single-call latency form (cfr_classify_batch: chunked copy/compute overlap inside one call)
     clf.classify_packed(*pinned[0], stream=sptr, out=outs[0])
     sync_all()
@@ -504,10 +599,10 @@ def main():
     launches_e2e = clf.counters()["n_launches"]
 
     # ---- reduce over ranks (max time) ----
-    t = torch.tensor([dev_ms, e2e_s * 1000.0, t_wall * 1000.0], dtype=torch.float64, device="cuda")
+    t = torch.tensor([dev_ms, e2e_s * 1000.0, t_wall * 1000.0, e2e_packed_s * 1000.0], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms_max, e2e_ms_max, wall_ms_max = [float(x) for x in t.tolist()]
+    dev_ms_max, e2e_ms_max, wall_ms_max, e2e_packed_ms_max = [float(x) for x in t.tolist()]
     total_reads = n * a.steps * world
     value = total_reads / (dev_ms_max / 1000.0)
     e2e_value = total_reads / (e2e_ms_max / 1000.0)
@@ -569,6 +664,12 @@ def main():
                     "api": "cfr_submit_batch / cfr_wait_batch, three batches in flight, pinned host buffers",
                     "single_call_value": bn / e2e_single_s,
                     "host_link_h2d_gbs": h2d_gbs},
+            "e2e_packed": {"value": total_reads / (e2e_packed_ms_max / 1000.0), "unit": unit,
+                           "h2d_bytes_per_step": int((plink1[0] - plink0[0]) // a.steps),
+                           "d2h_bytes_per_step": int((plink1[1] - plink0[1]) // a.steps),
+                           "api": "cfr_submit_packed / cfr_wait_batch: the producer hands over 2-bit codes + N bits (cfr_pack_reads, "
+                                  "%.2f s for the step's reads with %d host threads, outside the timed region)"
+                                  % (pack_s, min(16, os.cpu_count() or 1))},
             "gpu_launches": int(launches_resident + launches_e2e),
             "roofline": {"bound": "hbm" if hbm_resident else "l2/issue", "kernel": "k_search",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -608,10 +709,16 @@ def main():
                 line["cpu_baseline"] = {"value": r[0], "unit": unit, "cores": cores, "kind": "reference",
                                         "sample": "first %d reads of the step's first batch x %d, centrifuger -t %d, %.1f s, "
                                                   "FASTQ in / TSV to /dev/null, index-load time subtracted" % (n_sample, rep, cores, r[1])}
-        print(json.dumps(line))
     for b in batches:
         b.free()
     clf.close()
+    if rank == 0:
+        if not a.no_cli and world == 1:
+            # the drop-in binary on the step's reads as FASTQ files (20 M reads at the default workload): a separate
+            # process, so this one's handle is closed first (two replicas of a 20 Gbp index do not fit one GPU)
+            torch.cuda.empty_cache()
+            line["cli_e2e"] = run_cli_e2e(idx, w, [[x.numpy() if x is not None else None for x in p] for p in pinned])
+        print(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

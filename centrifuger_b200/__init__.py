@@ -39,6 +39,12 @@ class ReadBatch(C.Structure):
                 ("seq2", C.c_void_p), ("off2", C.c_void_p)]
 
 
+class PackedBatch(C.Structure):
+    """cfr_packed_batch: 2-bit codes + N bits per base, offsets = positions in the batch buffer"""
+    _fields_ = [("n_reads", C.c_uint64), ("codes", C.c_void_p), ("nmask", C.c_void_p), ("n_words", C.c_uint64),
+                ("off1", C.c_void_p), ("off2", C.c_void_p)]
+
+
 class Counters(C.Structure):
     _fields_ = [(k, C.c_uint64) for k in
                 ("n_rank", "n_access", "n_search", "n_locate", "n_lf", "n_extend",
@@ -57,7 +63,7 @@ RESULT_DTYPE = np.dtype([("score", "<u8"), ("secondary_score", "<u8"), ("hit_len
 # every symbol include/centrifuger_b200.h declares
 ABI_SYMBOLS = [
     "cfr_default_params", "cfr_open", "cfr_close", "cfr_last_error", "cfr_classify_batch",
-    "cfr_submit_batch", "cfr_submit_batch_masked", "cfr_wait_batch", "cfr_batch_upload", "cfr_classify_resident", "cfr_batch_fetch", "cfr_batch_free",
+    "cfr_submit_batch", "cfr_submit_batch_masked", "cfr_wait_batch", "cfr_packed_words", "cfr_pack_reads", "cfr_submit_packed", "cfr_batch_upload", "cfr_classify_resident", "cfr_batch_fetch", "cfr_batch_free",
     "cfr_fetch_expanded", "cfr_batch_fetch_expanded",
     "cfr_host_alloc", "cfr_host_free", "cfr_index_info", "cfr_seq_name", "cfr_rank_name", "cfr_orig_taxid", "cfr_seq_taxid",
     "cfr_format_tsv", "cfr_taxon_counts_device", "cfr_taxon_counts_read", "cfr_taxon_counts_reset",
@@ -96,6 +102,10 @@ def load_library():
     L.cfr_submit_batch.argtypes = [vp, C.POINTER(ReadBatch), vp, vp, vp, C.POINTER(C.c_int)]
     L.cfr_submit_batch_masked.argtypes = [vp, C.POINTER(ReadBatch), vp, vp, vp, vp, vp, C.POINTER(C.c_int)]
     L.cfr_wait_batch.argtypes = [vp, C.c_int]
+    L.cfr_packed_words.argtypes = [C.POINTER(ReadBatch)]
+    L.cfr_packed_words.restype = u64
+    L.cfr_pack_reads.argtypes = [C.POINTER(ReadBatch), vp, vp, vp, vp, i32, C.POINTER(PackedBatch)]
+    L.cfr_submit_packed.argtypes = [vp, C.POINTER(PackedBatch), vp, vp, vp, C.POINTER(C.c_int)]
     L.cfr_batch_upload.argtypes = [vp, C.POINTER(ReadBatch), vp, C.POINTER(vp)]
     L.cfr_classify_resident.argtypes = [vp, vp, vp]
     L.cfr_batch_fetch.argtypes = [vp, vp, vp, vp, vp]
@@ -145,6 +155,28 @@ def pack_reads(reads):
     return buf, off
 
 
+def pack_batch(seq1, off1, seq2=None, off2=None, threads=8, pinned=False):
+    """cfr_pack_reads: host buffers -> (PackedBatch, keep): the bases as 2-bit codes + N bits (what the producer of a batch
+    hands to cfr_submit_packed; 2.25 bits per base over the host link).  `keep` holds the arrays the struct points into."""
+    L = load_library()
+    n = len(off1) - 1
+    b = make_batch(seq1, off1, seq2, off2, n)
+    nw = int(L.cfr_packed_words(C.byref(b)))
+    if pinned:
+        import torch
+        alloc = lambda k, dt: torch.empty(k, dtype=dt).pin_memory()
+        codes, nmask = alloc(nw, torch.int64), alloc(nw, torch.int32)
+        o1, o2 = alloc(n + 1, torch.int64), (alloc(n + 1, torch.int64) if seq2 is not None else None)
+    else:
+        codes, nmask = np.zeros(nw, dtype=np.uint64), np.zeros(nw, dtype=np.uint32)
+        o1, o2 = np.zeros(n + 1, dtype=np.uint64), (np.zeros(n + 1, dtype=np.uint64) if seq2 is not None else None)
+    pk = PackedBatch()
+    st = L.cfr_pack_reads(C.byref(b), _ptr(codes), _ptr(nmask), _ptr(o1), _ptr(o2), threads, C.byref(pk))
+    if st != 0:
+        raise CfrError(st, L.cfr_last_error().decode())
+    return pk, (codes, nmask, o1, o2)
+
+
 def _ptr(a):
     """host pointer of a numpy array or a (pinned) torch CPU tensor"""
     if a is None:
@@ -190,7 +222,7 @@ class Classifier:
 
     def __init__(self, idx_prefix, k=1, min_hit_len=0, hitk_factor=40, dust=True,
                  secondary_len=2000, secondary_factor=0.995, layout=LAYOUT_AUTO,
-                 device=0, max_batch_reads=0, arena_rows=0, expand_taxid=False):
+                 device=0, max_batch_reads=0, arena_rows=0, expand_taxid=False, unlimited_cap=0):
         self.L = load_library()
         p = Params()
         self.L.cfr_default_params(C.byref(p))
@@ -200,6 +232,7 @@ class Classifier:
         p.consider_secondary_score_factor = secondary_factor
         p.layout, p.max_batch_reads, p.arena_rows = layout, max_batch_reads, arena_rows
         p.expand_taxid = 1 if expand_taxid else 0
+        p.unlimited_cap = unlimited_cap  # id slots per read when k <= 0 (0 = the library's default, 64)
         self.params = p
         self.max_result = k
         self.k = k if k > 0 else 64  # id slots per read (the stride of the ids arrays); -k <= 0 = unlimited, see info(24)
@@ -288,6 +321,18 @@ class Classifier:
         t = C.c_int(-1)
         self._check(self.L.cfr_submit_batch(self.h, C.byref(b), _ptr(res), _ptr(ids), stream, C.byref(t)))
         return t.value, res, ids, (b, seq1, off1, seq2, off2)
+
+    def submit_packed(self, packed, stream=None, out=None):
+        """cfr_submit_packed: `packed` = the PackedBatch of pack_batch (keep its arrays alive until wait)"""
+        n = int(packed.n_reads)
+        if out is None:
+            res = np.zeros(n, dtype=RESULT_DTYPE)
+            ids = np.zeros(max(1, n * self.k), dtype=np.uint64)
+        else:
+            res, ids = out
+        t = C.c_int(-1)
+        self._check(self.L.cfr_submit_packed(self.h, C.byref(packed), _ptr(res), _ptr(ids), stream, C.byref(t)))
+        return t.value, res, ids
 
     def wait(self, ticket):
         self._check(self.L.cfr_wait_batch(self.h, ticket))

@@ -17,6 +17,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/centrifuger_b200.h"
@@ -82,6 +83,7 @@ struct cfr_device_batch {
   int ticket = -1;                   // streaming ticket this slot last served
   bool want_masked = false;
   bool classified = false;
+  bool packed = false;  // uploaded as 2-bit codes + N bits (cfr_submit_packed): no k_encode pass
   void release() {
     DevBuf *all[] = {&seq_raw, &codes, &mask_raw, &mask, &off, &strand_hits, &strand_nhits, &fhits, &work, &rows, &seq_ids,
                      &rec0, &rec1, &best, &tmp, &results, &out_ids, &deferred, &dust_list, &scalars, &dust_bits, &masked,
@@ -105,8 +107,12 @@ struct cfr_handle {
   double open_seconds = 0.0;
   int sm_count = 148;
   int search_blocks = 10;  // resident 128-thread blocks per SM targeted by k_search (CFR_B200_SEARCH_BLOCKS)
-  int pair_fetch = 2;  // 2 = cp.async staging rounds, 1 = LDG + STS rounds (CFR_B200_PAIR_FETCH)
-  int pair_search_blocks = 8;  // the same for the pair-line search kernel (CFR_B200_PAIR_SEARCH_BLOCKS)
+  // how the pair-line search kernel waits for memory (CFR_B200_PAIR_FETCH): 3 = one wait per iteration (lines, far lines and
+  // wide-table entries in one group of cp.async copies), 2 = cp.async staging rounds per request kind, 1 = LDG + STS rounds
+  int pair_fetch = 3;
+  // the same for the pair-line search kernel (CFR_B200_PAIR_SEARCH_BLOCKS): six blocks keep the memory system as busy as
+  // eight do and leave registers for the latency-bound kernels of the neighbouring batches (SDUST, scoring) on the same SMs
+  int pair_search_blocks = 6;
   int occ_load = 4;    // how k_search / k_locate fetch a sector: 4 = one 256-bit load, 0 = two 128-bit loads (CFR_B200_OCC_LOAD)
   bool pos32 = false;  // 32-bit BWT positions in k_search / k_locate (collections below 2^32 rows; CFR_B200_POS64=1 disables)
   int dust_quorum = 0;  // quorum of the SDUST state machine (0 = the search quorum; CFR_B200_DUST_QUORUM)
@@ -396,22 +402,24 @@ int build_wide_lookup(cfr_handle *h, int WW) {
 // Dense locate table (DevIndex::dense): the stored samples are 2^offrate rows apart, so a locate walks
 // 2^offrate - 1 LF steps on average, each one a sector from wherever the BWT lives.  HBM has room
 // for a denser table; its entries are computed by the reference's own walk, so results cannot change.
-int build_dense_locate(cfr_handle *h, int shift) {
+int build_dense_locate(cfr_handle *h, int shift, bool e16) {
   if (shift < 0 || h->ix.sample_shift < 0 || shift >= h->ix.sample_shift) return CFR_OK;
   const u64 n_rows = ((h->ix.n - 1) >> shift) + 1;  // rows 0 .. n-1 only: row n does not exist
+  const u64 esz = e16 ? 2 : 4;
   void *p;
-  int st = dev_alloc(h, &p, n_rows * 4 + 16);
+  int st = dev_alloc(h, &p, n_rows * esz + 16);
   if (st) return st;
   h->ix.dense_shift = -1;
   const int grid = grid_for(h, n_rows, 128, 16);
-  if (h->layout == CFR_LAYOUT_OCCLINE) k_build_dense<BwtOccLine><<<grid, 128, 0, h->stream>>>(h->ix, (u32 *)p, shift, n_rows);
-  else k_build_dense<BwtRunBlock><<<grid, 128, 0, h->stream>>>(h->ix, (u32 *)p, shift, n_rows);
+  if (h->layout == CFR_LAYOUT_OCCLINE) k_build_dense<BwtOccLine><<<grid, 128, 0, h->stream>>>(h->ix, (u32 *)p, shift, n_rows, e16 ? 1 : 0);
+  else k_build_dense<BwtRunBlock><<<grid, 128, 0, h->stream>>>(h->ix, (u32 *)p, shift, n_rows, e16 ? 1 : 0);
   ++h->launches;
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaStreamSynchronize(h->stream));
   h->ix.dense = (const u32 *)p;
   h->ix.dense_shift = shift;
-  h->dense_bytes = n_rows * 4;
+  h->ix.dense16 = e16 ? 1 : 0;
+  h->dense_bytes = n_rows * esz;
   return CFR_OK;
 }
 
@@ -453,13 +461,16 @@ struct StageScope {
 // -------------------------------------------------------------------------------------
 // batch upload: copies reads [r0, r1) of `in` into device batch `b` and sizes the work areas
 // -------------------------------------------------------------------------------------
-int upload_chunk(cfr_handle *h, const cfr_read_batch *in, u64 r0, u64 r1, cfr_device_batch *b, cudaStream_t s) {
+// `pk` != nullptr: the reads arrive packed (cfr_packed_batch; `in` then carries only its offsets, r0 = 0)
+int upload_chunk(cfr_handle *h, const cfr_read_batch *in, u64 r0, u64 r1, cfr_device_batch *b, cudaStream_t s,
+                 const cfr_packed_batch *pk = nullptr) {
   const u64 n = r1 - r0;
-  const int mates = in->seq2 ? 2 : 1;
+  const int mates = (pk ? pk->off2 != nullptr : in->seq2 != nullptr) ? 2 : 1;
   if (mates == 2 && !in->off2) return fail(CFR_ERR_ARG, "seq2 given without off2");
   b->n_reads = n;
   b->mates = mates;
   b->classified = false;
+  b->packed = pk != nullptr;
   const u64 s1 = in->off1[r0], e1 = in->off1[r1];
   const u64 s2 = mates == 2 ? in->off2[r0] : 0, e2 = mates == 2 ? in->off2[r1] : 0;
   if (e1 < s1 || e2 < s2) return fail(CFR_ERR_ARG, "read offsets are not ascending");
@@ -491,7 +502,11 @@ int upload_chunk(cfr_handle *h, const cfr_read_batch *in, u64 r0, u64 r1, cfr_de
   const u64 S = 2 * (u64)mates;
   int st;
   const u64 n_words = b->seq_bytes / 32 + 2;
-  if ((st = b->seq_raw.ensure(b->seq_bytes + 64))) return st;
+  if (pk) {
+    if (n && (s1 != 0 || (mates == 2 && s2 != pos2))) return fail(CFR_ERR_ARG, "packed batch: off1[0] must be 0 and off2[0] the next multiple of 32 after mate 1");
+    if (pk->n_words < n_words) return fail(CFR_ERR_ARG, "packed batch: codes / nmask hold fewer words than the offsets need");
+  }
+  if (!pk && (st = b->seq_raw.ensure(b->seq_bytes + 64))) return st;
   if ((st = b->codes.ensure(n_words * 8))) return st;
   if ((st = b->mask_raw.ensure(n_words * 4))) return st;
   if ((st = b->mask.ensure(n_words * 4))) return st;
@@ -523,9 +538,15 @@ int upload_chunk(cfr_handle *h, const cfr_read_batch *in, u64 r0, u64 r1, cfr_de
     if ((st = b->exp_ids.ensure(arena * 8))) return st;
   }
   // H2D
-  if (len1) CUDA_TRY(cudaMemcpyAsync(b->seq_raw.p, in->seq1 + s1, len1, cudaMemcpyHostToDevice, s));
-  if (len2) CUDA_TRY(cudaMemcpyAsync((char *)b->seq_raw.p + pos2, in->seq2 + s2, len2, cudaMemcpyHostToDevice, s));
-  h->h2d_bytes += len1 + len2;
+  if (pk) {
+    CUDA_TRY(cudaMemcpyAsync(b->codes.p, pk->codes, n_words * 8, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(b->mask_raw.p, pk->nmask, n_words * 4, cudaMemcpyHostToDevice, s));
+    h->h2d_bytes += n_words * 12;
+  } else {
+    if (len1) CUDA_TRY(cudaMemcpyAsync(b->seq_raw.p, in->seq1 + s1, len1, cudaMemcpyHostToDevice, s));
+    if (len2) CUDA_TRY(cudaMemcpyAsync((char *)b->seq_raw.p + pos2, in->seq2 + s2, len2, cudaMemcpyHostToDevice, s));
+    h->h2d_bytes += len1 + len2;
+  }
   for (int m = 0; m < mates; ++m) {
     u64 *dst = (u64 *)b->off.p + (m ? n + 1 : 0);
     const uint64_t *src = (m ? in->off2 : in->off1) + r0;
@@ -626,7 +647,9 @@ int run_first(cfr_handle *h, cfr_device_batch *b, cudaStream_t s) {
   fill_chunk(h, b, B);
   if (b->n_reads == 0) return CFR_OK;
   CUDA_TRY(cudaMemsetAsync(b->scalars.p, 0, 64, s));
-  {
+  if (b->packed) {  // the producer encoded the bases: the masks the searches see start as the uploaded ones
+    if (B.mask != B.mask_raw) CUDA_TRY(cudaMemcpyAsync(B.mask, B.mask_raw, B.n_words * 4, cudaMemcpyDeviceToDevice, s));
+  } else {
     StageScope sc(h, s, CFR_STAGE_OTHER);
     k_encode<<<grid_for(h, B.n_words, 256, 8), 256, 0, s>>>(B, b->seq_bytes);
     ++h->launches;
@@ -780,7 +803,7 @@ int cfr_open(const char *idx_prefix, const cfr_params *p, int device, cfr_handle
   if (const char *e = getenv("CFR_B200_QUORUM")) h->P.quorum = std::max(1, atoi(e));
   if (const char *e = getenv("CFR_B200_SEARCH_BLOCKS")) h->search_blocks = std::max(1, atoi(e));
   if (const char *e = getenv("CFR_B200_PAIR_SEARCH_BLOCKS")) h->pair_search_blocks = std::max(1, atoi(e));
-  if (const char *e = getenv("CFR_B200_PAIR_FETCH")) h->pair_fetch = atoi(e) == 1 ? 1 : 2;
+  if (const char *e = getenv("CFR_B200_PAIR_FETCH")) h->pair_fetch = std::min(3, std::max(1, atoi(e)));
   if (const char *e = getenv("CFR_B200_DUST_SCREEN")) h->dust_screen = atoi(e) != 0;
   if (const char *e = getenv("CFR_B200_DUST_QUORUM")) h->dust_quorum = std::max(0, atoi(e));
   if (const char *e = getenv("CFR_B200_DUST_LANES")) h->dust_lanes = std::min(32, std::max(1, atoi(e)));
@@ -867,9 +890,14 @@ int cfr_open(const char *idx_prefix, const cfr_params *p, int device, cfr_handle
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
     const u64 budget = std::min<u64>((u64)free_b * 2 / 5, 48ull << 30);
-    while (shift < 8 && ((h->ix.n >> shift) + 1) * 4 > budget) ++shift;
+    // 16-bit entries when every id a locate can return fits: the sampled SA's ids (sa_bits wide), the boundary
+    // table's, and the id of row firstISA (CFR_B200_DENSE16=0 keeps 32-bit entries)
+    bool e16 = h->file.sa_bits <= 16 && h->file.adjusted_sa0 < 65536;
+    for (u64 i = 0; e16 && i < h->file.sel_cnt; ++i) e16 = load_u64(h->file.sel + i * 16 + 8) < 65536;
+    if (const char *e = getenv("CFR_B200_DENSE16")) e16 = e16 && atoi(e) != 0;
+    while (shift < 8 && ((h->ix.n >> shift) + 1) * (e16 ? 2 : 4) > budget) ++shift;
     if (const char *e = getenv("CFR_B200_DENSE_LOCATE")) shift = atoi(e);
-    if ((st = build_dense_locate(h, shift))) return bail(st);
+    if ((st = build_dense_locate(h, shift, e16))) return bail(st);
   }
   h->file.map1.close();  // everything needed from .1.cfr now lives in HBM
   h->open_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_open0).count();
@@ -971,13 +999,17 @@ int cfr_classify_resident(cfr_handle *h, cfr_device_batch *b, void *stream) {
   b->classified = true;
   b->quant_counted = false;
   if (h->layout == CFR_LAYOUT_OCCLINE) {
-    if (h->ix.pairs) {  // pair lines in the search kernel; staged by cp.async rounds (CFR_B200_PAIR_FETCH=1: LDG + STS rounds)
+    if (h->ix.pairs) {  // pair lines in the search kernel (CFR_B200_PAIR_FETCH picks how they are awaited)
       if (h->pair_fetch == 1) {
         if (h->pos32) return run_first<BwtOccLine, BwtOccLine32T<4>, BwtPairT<1>>(h, b, s);
         return run_first<BwtOccLine, BwtOccLineT<4>, BwtPairT<1>>(h, b, s);
       }
-      if (h->pos32) return run_first<BwtOccLine, BwtOccLine32T<4>, BwtPairT<2>>(h, b, s);
-      return run_first<BwtOccLine, BwtOccLineT<4>, BwtPairT<2>>(h, b, s);
+      if (h->pair_fetch == 2) {
+        if (h->pos32) return run_first<BwtOccLine, BwtOccLine32T<4>, BwtPairT<2>>(h, b, s);
+        return run_first<BwtOccLine, BwtOccLineT<4>, BwtPairT<2>>(h, b, s);
+      }
+      if (h->pos32) return run_first<BwtOccLine, BwtOccLine32T<4>, BwtPairT<3>>(h, b, s);
+      return run_first<BwtOccLine, BwtOccLineT<4>, BwtPairT<3>>(h, b, s);
     }
     if (h->pos32) {
       if (h->occ_load == 0) return run_first<BwtOccLine, BwtOccLine32T<0>>(h, b, s);
@@ -1208,15 +1240,118 @@ int cfr_classify_batch(cfr_handle *h, const cfr_read_batch *in, cfr_result *resu
   return check_device_errors(h, sc);
 }
 
+// ---- host side of the packed form: bytes -> 2-bit codes + N bits, exactly what k_encode (encode_stage) writes
+uint64_t cfr_packed_words(const cfr_read_batch *in) {
+  if (!in || !in->off1) return 2;
+  const u64 n = in->n_reads;
+  const u64 len1 = in->off1[n] - in->off1[0];
+  const u64 len2 = (in->seq2 && in->off2) ? in->off2[n] - in->off2[0] : 0;
+  return (((len1 + 31) & ~31ull) + len2) / 32 + 2;
+}
+
+int cfr_pack_reads(const cfr_read_batch *in, uint64_t *codes, uint32_t *nmask, uint64_t *off1, uint64_t *off2, int threads,
+                   cfr_packed_batch *out) {
+  if (!in || !codes || !nmask || !off1 || !out || !in->off1 || (in->n_reads && !in->seq1)) return fail(CFR_ERR_ARG, "null argument");
+  const bool two = in->seq2 != nullptr;
+  if (two && (!in->off2 || !off2)) return fail(CFR_ERR_ARG, "seq2 given without off2");
+  const u64 n = in->n_reads;
+  const u64 s1 = in->off1[0], len1 = in->off1[n] - s1;
+  const u64 s2 = two ? in->off2[0] : 0, len2 = two ? in->off2[n] - s2 : 0;
+  const u64 pos2 = (len1 + 31) & ~31ull;
+  const u64 n_words = (pos2 + len2) / 32 + 2;
+  static const struct Lut {
+    unsigned char v[256];  // 0..3 = code, 4 = not one of "ACGT"
+    Lut() {
+      memset(v, 4, sizeof(v));
+      v[(unsigned char)'A'] = 0;
+      v[(unsigned char)'C'] = 1;
+      v[(unsigned char)'G'] = 2;
+      v[(unsigned char)'T'] = 3;
+    }
+  } lut;
+  const unsigned char *a1 = reinterpret_cast<const unsigned char *>(in->seq1) + s1;
+  const unsigned char *a2 = two ? reinterpret_cast<const unsigned char *>(in->seq2) + s2 : nullptr;
+  auto words = [&](u64 w0, u64 w1) {
+    for (u64 w = w0; w < w1; ++w) {
+      const u64 p0 = w * 32;
+      u64 c = 0;
+      u32 m = 0;
+      // pos2 is a multiple of 32, so a word lies in one mate's region (or in the padding)
+      const unsigned char *src = nullptr;
+      int cnt = 0;
+      if (p0 < len1) {
+        src = a1 + p0;
+        cnt = (int)std::min<u64>(32, len1 - p0);
+      } else if (p0 >= pos2 && p0 - pos2 < len2) {
+        src = a2 + (p0 - pos2);
+        cnt = (int)std::min<u64>(32, len2 - (p0 - pos2));
+      }
+      m = cnt >= 32 ? 0u : ~((1u << cnt) - 1u);  // padding reads as N
+      for (int i = 0; i < cnt; ++i) {
+        const unsigned char x = lut.v[src[i]];
+        if (x > 3) m |= 1u << i;
+        else c |= (u64)x << (2 * i);
+      }
+      codes[w] = c;
+      nmask[w] = m;
+    }
+  };
+  auto offsets = [&](u64 i0, u64 i1) {
+    for (u64 i = i0; i < i1; ++i) {
+      off1[i] = in->off1[i] - s1;
+      if (two) off2[i] = in->off2[i] - s2 + pos2;
+    }
+  };
+  const unsigned T = (unsigned)std::max(1, std::min(threads, 256));
+  if (T == 1 || n_words < 4096) {
+    words(0, n_words);
+    offsets(0, n + 1);
+  } else {
+    std::vector<std::thread> pool;
+    for (unsigned t = 0; t < T; ++t)
+      pool.emplace_back([&, t] {
+        words(n_words * t / T, n_words * (t + 1) / T);
+        offsets((n + 1) * t / T, (n + 1) * (t + 1) / T);
+      });
+    for (auto &th : pool) th.join();
+  }
+  out->n_reads = n;
+  out->codes = codes;
+  out->nmask = nmask;
+  out->n_words = n_words;
+  out->off1 = off1;
+  out->off2 = two ? off2 : nullptr;
+  return CFR_OK;
+}
+
 int cfr_submit_batch(cfr_handle *h, const cfr_read_batch *in, cfr_result *results, uint64_t *ids, void *stream,
                      int *ticket) {
   return cfr_submit_batch_masked(h, in, results, ids, nullptr, nullptr, stream, ticket);
 }
 
+static int submit_impl(cfr_handle *h, const cfr_read_batch *in, const cfr_packed_batch *pk, cfr_result *results, uint64_t *ids,
+                       char *masked1, char *masked2, void *stream, int *ticket);
+
 int cfr_submit_batch_masked(cfr_handle *h, const cfr_read_batch *in, cfr_result *results, uint64_t *ids,
                             char *masked1, char *masked2, void *stream, int *ticket) {
   if (!h || !in || !ticket || (in->n_reads && (!results || !ids))) return fail(CFR_ERR_ARG, "null argument");
   if (in->n_reads && (!in->seq1 || !in->off1)) return fail(CFR_ERR_ARG, "seq1/off1 missing");
+  return submit_impl(h, in, nullptr, results, ids, masked1, masked2, stream, ticket);
+}
+
+int cfr_submit_packed(cfr_handle *h, const cfr_packed_batch *pk, cfr_result *results, uint64_t *ids, void *stream, int *ticket) {
+  if (!h || !pk || !ticket || (pk->n_reads && (!results || !ids))) return fail(CFR_ERR_ARG, "null argument");
+  if (pk->n_reads && (!pk->codes || !pk->nmask || !pk->off1)) return fail(CFR_ERR_ARG, "codes / nmask / off1 missing");
+  cfr_read_batch view;  // the offsets only: the bases travel packed
+  view.n_reads = pk->n_reads;
+  view.seq1 = view.seq2 = nullptr;
+  view.off1 = pk->off1;
+  view.off2 = pk->off2;
+  return submit_impl(h, &view, pk, results, ids, nullptr, nullptr, stream, ticket);
+}
+
+static int submit_impl(cfr_handle *h, const cfr_read_batch *in, const cfr_packed_batch *pk, cfr_result *results, uint64_t *ids,
+                       char *masked1, char *masked2, void *stream, int *ticket) {
   const u64 cap = h->params.max_batch_reads > 0 ? (u64)h->params.max_batch_reads : (1ull << 20);
   if (in->n_reads > cap) return fail(CFR_ERR_ARG, "cfr_submit_batch: n_reads exceeds max_batch_reads");
   CUDA_TRY(cudaSetDevice(h->device));
@@ -1240,7 +1375,7 @@ int cfr_submit_batch_masked(cfr_handle *h, const cfr_read_batch *in, cfr_result 
     }
     cudaEventRecord(h->tr_ev[slot][0], h->s_in);
   }
-  if ((st = upload_chunk(h, in, 0, in->n_reads, b, h->s_in))) return st;
+  if ((st = upload_chunk(h, in, 0, in->n_reads, b, h->s_in, pk))) return st;
   CUDA_TRY(cudaEventRecord(h->ev_h2d[slot], h->s_in));
   if (h->trace) cudaEventRecord(h->tr_ev[slot][1], h->s_in);
   CUDA_TRY(cudaStreamWaitEvent(h->s_comp[slot], h->ev_h2d[slot], 0));
@@ -1257,7 +1392,7 @@ int cfr_submit_batch_masked(cfr_handle *h, const cfr_read_batch *in, cfr_result 
     CUDA_TRY(cudaMemcpyAsync(ids, b->out_ids.p, in->n_reads * k * 8, cudaMemcpyDeviceToHost, h->s_out));
     h->d2h_bytes += in->n_reads * (sizeof(DevResult) + k * 8);
   }
-  if (b->want_masked && in->n_reads) {
+  if (b->want_masked && in->n_reads) {  // (never with a packed batch: masked1 is null there)
     const u64 len1 = in->off1[in->n_reads] - in->off1[0];
     const u64 len2 = in->seq2 ? in->off2[in->n_reads] - in->off2[0] : 0;
     h->d2h_bytes += len1 + (masked2 ? len2 : 0);

@@ -52,6 +52,14 @@ CFR_HD u32 ld32(const u32 *p) {
 #endif
 }
 
+CFR_HD u32 ld16(const unsigned short *p) {
+#if defined(__CUDA_ARCH__)
+  return (u32)__ldg(p);
+#else
+  return (u32)*p;
+#endif
+}
+
 CFR_HD unsigned char ld8(const unsigned char *p) {
 #if defined(__CUDA_ARCH__)
   return __ldg(p);
@@ -659,6 +667,7 @@ CFR_HD PairQuery pair_query_scalar(const DevIndex &ix, int c1, int c2, u64 x) {
 // fall on distinct banks within each quarter warp.
 #define CFR_PAIR_SLOT_WORDS 36
 #define CFR_PAIR_NO_LINE 0xffffffffu
+#define CFR_PAIR_FAR 8  // far slots per warp (MODE 3)
 
 // The same staging with asynchronous copies (cp.async, 16 bytes per lane): groups of EIGHT adjacent lanes fetch
 // one line per round as one coalesced 128-byte request, eight rounds, and no round waits for the one
@@ -822,6 +831,50 @@ CFR_HD void pair_constants(const DevIndex &ix, u64 *out) {
   }
 }
 
+// the arithmetic of the two steps once the line contents at both boundaries are known (qa at sp, qe at ep + 1;
+// qe is ignored when sp == ep)
+CFR_HD int pair_finish(const DevIndex &ix, int c1, int c2, u64 &sp, u64 &ep, const PairQuery &qa, const PairQuery &qe, OpCount &oc) {
+  const bool two = c2 >= 0;
+  const bool range = sp != ep;
+  const u64 xe = ep + 1;
+  const u64 fisa = ix.first_isa;
+  const bool l1 = c1 == ix.last_code;
+  ++oc.xext;
+  oc.xsingle += range ? 0u : 1u;
+  const u64 y1 = ix.C[c1] + qa.s1 + ((l1 && sp <= fisa) ? 1ull : 0ull);
+  const u64 y2 = range ? ix.C[c1] + qe.s1 + ((l1 && xe <= fisa) ? 1ull : 0ull) - 1ull
+                       : y1 + ((qa.sym1 == c1) ? 0ull : ~0ull);
+  if (y1 > y2 || y2 > ix.n) return 0;
+  if (!two) {
+    sp = y1;
+    ep = y2;
+    return 1;
+  }
+  const bool l2 = c2 == ix.last_code;
+  const int idx2 = c1 * 4 + c2;
+  const u64 g0 = ix.C[c2] + ix.pair_D[idx2];
+  const u64 e_add = (l1 && ix.pair_E == c2) ? 1ull : 0ull;
+  const u64 f_sub = (l1 && ix.pair_F == c2) ? 1ull : 0ull;
+  const bool range2 = y1 != y2;
+  ++oc.xext;
+  oc.xsingle += range2 ? 0u : 1u;
+  const u64 z1 = g0 + qa.p + e_add - (sp > fisa ? f_sub : 0ull) + ((l2 && y1 <= fisa) ? 1ull : 0ull);
+  u64 z2;
+  if (range) {
+    const u64 Y = y2 + 1;  // = step(c1, ep + 1)
+    z2 = g0 + qe.p + e_add - (xe > fisa ? f_sub : 0ull) + ((l2 && Y <= fisa) ? 1ull : 0ull) - 1ull;
+    if (!range2 && l2 && y1 == fisa) z2 += 1;  // single row y1: the reference tests B[y1] instead of ranking
+  } else {
+    z2 = z1 + ((qa.sym2 == c2) ? 0ull : ~0ull);  // code2(sp) = B[y1]
+  }
+  sp = y1;
+  ep = y2;
+  if (z1 > z2 || z2 > ix.n) return 1;
+  sp = z1;
+  ep = z2;
+  return 2;
+}
+
 // Two steps of FMIndex::BackwardSearch's loop (FMIndex.hpp:495-508) from the range [sp, ep]: first c1,
 // then -- if c2 >= 0 -- c2.  Returns how many succeeded (0, 1, 2) and leaves the range after the last
 // successful one in (sp, ep).  The operation counters advance as the reference's calls would.
@@ -832,7 +885,8 @@ template <int MODE>
 struct BwtPairT {
   enum { COOP = MODE != 0 };
   typedef u64 pos_t;
-  enum { LANES = 1, PAIR = 1, STEPS_COUNTED_AT_CLOSE = 0 };
+  // PAIR = 2: the search loop calls round() (one memory wait per iteration) instead of extend2()
+  enum { LANES = 1, PAIR = (MODE == 3 ? 2 : 1), STEPS_COUNTED_AT_CLOSE = 0 };
   static CFR_HD bool leader() { return true; }
   // single-step form: not used by the search loop of a pair policy (Bwt::PAIR selects extend2)
   static CFR_HD void extend_step(const DevIndex &, int, u64 sp, u64 ep, u64 &nsp, u64 &nep, OpCount &) {
@@ -875,43 +929,92 @@ struct BwtPairT {
       qa = pair_query_scalar(ix, c1, c2q, sp);
       qe = range ? pair_query_scalar(ix, c1, c2q, xe) : qa;
     }
-    const u64 fisa = ix.first_isa;
-    const bool l1 = c1 == ix.last_code;
-    ++oc.xext;
-    oc.xsingle += range ? 0u : 1u;
-    const u64 y1 = ix.C[c1] + qa.s1 + ((l1 && sp <= fisa) ? 1ull : 0ull);
-    const u64 y2 = range ? ix.C[c1] + qe.s1 + ((l1 && xe <= fisa) ? 1ull : 0ull) - 1ull
-                         : y1 + ((qa.sym1 == c1) ? 0ull : ~0ull);
-    if (y1 > y2 || y2 > ix.n) return 0;
-    if (!two) {
-      sp = y1;
-      ep = y2;
-      return 1;
-    }
-    const bool l2 = c2 == ix.last_code;
-    const int idx2 = c1 * 4 + c2;
-    const u64 g0 = ix.C[c2] + ix.pair_D[idx2];
-    const u64 e_add = (l1 && ix.pair_E == c2) ? 1ull : 0ull;
-    const u64 f_sub = (l1 && ix.pair_F == c2) ? 1ull : 0ull;
-    const bool range2 = y1 != y2;
-    ++oc.xext;
-    oc.xsingle += range2 ? 0u : 1u;
-    const u64 z1 = g0 + qa.p + e_add - (sp > fisa ? f_sub : 0ull) + ((l2 && y1 <= fisa) ? 1ull : 0ull);
-    u64 z2;
-    if (range) {
-      const u64 Y = y2 + 1;  // = step(c1, ep + 1)
-      z2 = g0 + qe.p + e_add - (xe > fisa ? f_sub : 0ull) + ((l2 && Y <= fisa) ? 1ull : 0ull) - 1ull;
-      if (!range2 && l2 && y1 == fisa) z2 += 1;  // single row y1: the reference tests B[y1] instead of ranking
-    } else {
-      z2 = z1 + ((qa.sym2 == c2) ? 0ull : ~0ull);  // code2(sp) = B[y1]
-    }
-    sp = y1;
-    ep = y2;
-    if (z1 > z2 || z2 > ix.n) return 1;
-    sp = z1;
-    ep = z2;
-    return 2;
+    return pair_finish(ix, c1, c2, sp, ep, qa, qe, oc);
   }
+#if defined(__CUDA_ARCH__)
+  // MODE 3: ONE memory round of the warp per iteration of the search loop.  Everything a lane can be waiting for
+  // travels in the same group of asynchronous copies and is awaited once:
+  //   * the line at sp of a lane that extends (`go`; eight lanes fetch it as one 128-byte request, as in MODE 2),
+  //   * the line at ep + 1 when that lies in another line ("far"): up to CFR_PAIR_FAR of them per round go to
+  //     extra slots handed out by ballot rank (in MODEs 1 / 2 they cost every iteration a second, dependent
+  //     DRAM round trip -- three quarters of all iterations have such a lane); the rare surplus takes a second round,
+  //   * the 16-byte wide-lookup-table entry of a lane that starts a search (`probe`), copied by the lane itself.
+  // Returns the steps done (as extend2) for go lanes; `entry` = the table entry for probe lanes.
+  static CFR_D int round(const DevIndex &ix, bool go, int c1, int c2, u64 &sp, u64 &ep, bool probe, u64 key, u64x2 &entry,
+                         OpCount &oc) {
+    enum { F = CFR_PAIR_FAR, SLOTS = 32 + F };
+    __shared__ __align__(16) u32 pair_slots[4][SLOTS * CFR_PAIR_SLOT_WORDS];  // [warp of the block][lane slots, far slots]
+    const unsigned full = 0xffffffffu;
+    u32 *slots = pair_slots[(threadIdx.x >> 5) & 3];
+    const int lane = threadIdx.x & 31, sub = lane & 7, gbase = lane & ~7;
+    u32 *mine = slots + lane * CFR_PAIR_SLOT_WORDS;
+    const bool two = c2 >= 0;
+    const int c2q = two ? c2 : 0;
+    const bool range = sp != ep;
+    const u64 xe = ep + 1;
+    const u64 La = sp >> 6, Le = xe >> 6;
+    c1 &= 3;  // lanes with go == false carry anything
+    const bool near = range && Le == La;
+    const bool far = go && range && Le != La;
+    const u32 farmask = __ballot_sync(full, far);
+    const int frank = __popc(farmask & ((1u << lane) - 1u));
+    const int nfar = min(__popc(farmask), (int)F);
+    const bool fslot = far && frank < F;
+    u32 *fmine = slots + (32 + (fslot ? frank : 0)) * CFR_PAIR_SLOT_WORDS;
+    if (fslot) fmine[32] = (u32)Le;  // a padding word of the far slot names its line
+    __syncwarp();
+    const u32 L = go ? (u32)La : CFR_PAIR_NO_LINE;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const u32 lj = __shfl_sync(full, L, gbase + j);
+      if (lj != CFR_PAIR_NO_LINE) {  // uniform over the eight lanes of the group
+        const char *src = reinterpret_cast<const char *>(ix.pairs + lj) + 16 * sub;
+        const u32 dst = (u32)__cvta_generic_to_shared(slots + (gbase + j) * CFR_PAIR_SLOT_WORDS + sub * 4);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < F / 4; ++j) {  // far slot r is fetched by the group r mod 4
+      const int r = (lane >> 3) + 4 * j;
+      if (r < nfar) {
+        u32 *fs = slots + (32 + r) * CFR_PAIR_SLOT_WORDS;
+        const char *src = reinterpret_cast<const char *>(ix.pairs + fs[32]) + 16 * sub;
+        const u32 dst = (u32)__cvta_generic_to_shared(fs + sub * 4);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+      }
+    }
+    if (probe) {
+      const u32 dst = (u32)__cvta_generic_to_shared(mine);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(ix.wide + key) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+    PairQuery qa, qe;
+    if (go) pair_query_slot(ix, mine, La, c1, c2q, (int)(sp & 63), (int)(xe & 63), near, qa, qe);
+    if (fslot) {
+      PairQuery dummy;
+      pair_query_slot(ix, fmine, Le, c1, c2q, (int)(xe & 63), 0, false, qe, dummy);
+    }
+    if (probe) {
+      const ulonglong2 e = *reinterpret_cast<const ulonglong2 *>(mine);
+      entry.x = e.x;
+      entry.y = e.y;
+    }
+    __syncwarp();
+    const bool surplus = far && !fslot;
+    if (__ballot_sync(full, surplus)) {  // more than F far lines in one round
+      pair_stage_warp_async(ix, surplus ? (u32)Le : CFR_PAIR_NO_LINE, slots);
+      if (surplus) {
+        PairQuery dummy;
+        pair_query_slot(ix, mine, Le, c1, c2q, (int)(xe & 63), 0, false, qe, dummy);
+      }
+      __syncwarp();
+    }
+    if (!go) return 0;
+    return pair_finish(ix, c1, c2, sp, ep, qa, qe, oc);
+  }
+#endif
 };
 
 // largest row count the 32-bit walkers accept
@@ -1052,11 +1155,16 @@ CFR_HD bool is_dense_row(const DevIndex &ix, Pos i) {
   return ix.dense_shift >= 0 && (i & (((Pos)1 << ix.dense_shift) - (Pos)1)) == 0;
 }
 
+// entry j of the dense locate table: 16-bit entries when every sequence id fits (half the HBM, so twice the density)
+CFR_HD u32 dense_read(const DevIndex &ix, u64 j) {
+  return ix.dense16 ? ld16(reinterpret_cast<const unsigned short *>(ix.dense) + j) : ld32(ix.dense + j);
+}
+
 // GetSampledSA with the dense table in front: a dense row's entry is what the literal procedure
 // below returns for the walk that starts there (checks at the row itself included)
 CFR_HD bool get_located(const DevIndex &ix, u64 i, u64 &sa) {
   if (is_dense_row(ix, i)) {
-    sa = (u64)ld32(ix.dense + (i >> ix.dense_shift));
+    sa = (u64)dense_read(ix, i >> ix.dense_shift);
     return true;
   }
   return get_sampled_sa(ix, i, sa);

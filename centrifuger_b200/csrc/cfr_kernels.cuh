@@ -346,11 +346,14 @@ __global__ void __launch_bounds__(128) k_build_wide(const __grid_constant__ DevI
 // Dense locate table at load time: the literal walk (FMIndex::BackwardToSampledSA over the stored
 // samples only) from every row that is a multiple of 2^shift
 template <class Bwt>
-__global__ void __launch_bounds__(128) k_build_dense(const __grid_constant__ DevIndex ix, u32 *out, int shift, u64 n_rows) {
+__global__ void __launch_bounds__(128) k_build_dense(const __grid_constant__ DevIndex ix, u32 *out, int shift, u64 n_rows, int e16) {
   const u64 stride = (u64)gridDim.x * blockDim.x;
   OpCount oc{};
-  for (u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x; j < n_rows; j += stride)
-    out[j] = (u32)locate_row<Bwt>(ix, j << shift, oc);  // ix.dense_shift is still -1 here
+  for (u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x; j < n_rows; j += stride) {
+    const u32 id = (u32)locate_row<Bwt>(ix, j << shift, oc);  // ix.dense_shift is still -1 here
+    if (e16) reinterpret_cast<unsigned short *>(out)[j] = (unsigned short)id;
+    else out[j] = id;
+  }
 }
 
 // ---- diagnostics for the parity tests ----

@@ -23,6 +23,7 @@
 #include <ctime>
 #include <mutex>
 #include <string>
+#include <chrono>
 #include <thread>
 #include <unordered_map>
 #include <deque>
@@ -116,6 +117,11 @@ struct Batch {
   std::vector<uint64_t> off1, off2;
   std::vector<cfr_result> results;
   std::vector<uint64_t> assign;
+  // the bases as the device wants them (cfr_pack_reads, written by the ingest stage): 2.25 bits per base cross the host link
+  std::vector<uint64_t> pcodes, poff1, poff2;
+  std::vector<uint32_t> pmask;
+  cfr_packed_batch packed;
+  bool isPacked = false;
   // --barcode / --UMI / bc,um stretches of --read-format: the strings printed for each read
   std::string bc, um;
   std::vector<uint32_t> bc_off, um_off;
@@ -531,13 +537,28 @@ int main(int argc, char *argv[]) {
     }
   }
 
+  // The reads cross the host link packed (cfr_submit_packed) unless the masked reads must come back for --un / --cl
+  // (CFR_B200_PACK_INPUT=0 sends the bytes instead)
+  const bool packInput = !writeReads && !dryOut && !dryPipe && !(getenv("CFR_B200_PACK_INPUT") && atoi(getenv("CFR_B200_PACK_INPUT")) == 0);
+  const unsigned packThreads = std::max(1u, std::min(16u, std::thread::hardware_concurrency() / 2));
+  // CFR_B200_STAGE_REPORT=1: seconds each pipeline stage was busy (waits for the neighbouring stages excluded)
+  const bool stageReport = getenv("CFR_B200_STAGE_REPORT") && atoi(getenv("CFR_B200_STAGE_REPORT")) != 0;
+  typedef std::chrono::steady_clock StageClock;
+  auto secondsSince = [](StageClock::time_point t0) { return std::chrono::duration<double>(StageClock::now() - t0).count(); };
+  const StageClock::time_point tPipe0 = StageClock::now();
+  double ingestWait = 0, ingestTotal = 0, outputWait = 0, outputTotal = 0, gpuWaitIn = 0, gpuWaitDev = 0;
+  size_t batchCnt = 0;
+
   std::thread ingest([&] {
     std::string name, name2, tmp, comment1;
     int bi = 0;
     bool eof = false;
     const bool twoFiles = hasMate && !interleaved;
+    const StageClock::time_point tStage0 = StageClock::now();
     for (;;) {
+      const StageClock::time_point tw = StageClock::now();
       Batch *bt = free_slots[bi].take();
+      ingestWait += secondsSince(tw);
       bi = (bi + 1) % NBATCH;
       bt->clear();
       // a batch ends after batchReads reads or 2^28 bases per mate, whichever comes first (long reads: the
@@ -655,9 +676,26 @@ int main(int argc, char *argv[]) {
       }
       bt->last = eof || mate_mismatch;
       if (mergePairs && hasMate && bt->n) MergeBatch(*bt, true, std::thread::hardware_concurrency());
+      bt->isPacked = false;
+      if (packInput && bt->n) {  // 2-bit codes + N bits for the device, packed here while the GPU works on the batches before
+        cfr_read_batch rb;
+        rb.n_reads = bt->n;
+        rb.seq1 = bt->seq1.data();
+        rb.off1 = bt->off1.data();
+        rb.seq2 = hasMate ? bt->seq2.data() : NULL;
+        rb.off2 = hasMate ? bt->off2.data() : NULL;
+        const uint64_t nw = cfr_packed_words(&rb);
+        bt->pcodes.resize(nw);
+        bt->pmask.resize(nw);
+        bt->poff1.resize(bt->n + 1);
+        if (hasMate) bt->poff2.resize(bt->n + 1);
+        bt->isPacked = cfr_pack_reads(&rb, bt->pcodes.data(), bt->pmask.data(), bt->poff1.data(), hasMate ? bt->poff2.data() : NULL,
+                                      (int)packThreads, &bt->packed) == CFR_OK;
+      }
       to_gpu.put(bt);
       if (bt->last) break;
     }
+    ingestTotal = secondsSince(tStage0);
   });
 
   for (int i = 0; i < NBATCH; ++i) free_slots[i].put(&batches[i]);
@@ -716,8 +754,11 @@ int main(int argc, char *argv[]) {
     std::vector<std::string> sheetSeen;
     if (useSheet) sheetSeen.push_back(sheetOutputs[0]);
     int bi = 0;
+    const StageClock::time_point tStage0 = StageClock::now();
     for (;;) {
+      const StageClock::time_point tw = StageClock::now();
       Batch *bt = to_out.take();
+      outputWait += secondsSince(tw);
       for (size_t i = 0; i < bt->n; ++i) {
         const cfr_result &r = bt->results[i];
         const char *id = bt->ids.data() + bt->id_off[i];
@@ -859,6 +900,7 @@ int main(int argc, char *argv[]) {
       fflush(fpOut);
       if (fpOut != stdout) fclose(fpOut);
     }
+    outputTotal = secondsSince(tStage0);
   });
 
   int rc = 0;
@@ -875,7 +917,10 @@ int main(int argc, char *argv[]) {
     const int tk = pending.front().ticket;
     cfr_handle *h = pending.front().h;
     pending.pop_front();
-    if (tk >= 0 && cfr_wait_batch(h, tk) != CFR_OK) {
+    const StageClock::time_point tw = StageClock::now();
+    const int wst = tk >= 0 ? cfr_wait_batch(h, tk) : CFR_OK;
+    gpuWaitDev += secondsSince(tw);
+    if (wst != CFR_OK) {
       PrintLog("ERROR: %s", cfr_last_error());
       rc = EXIT_FAILURE;
       pb->n = 0;
@@ -899,7 +944,10 @@ int main(int argc, char *argv[]) {
     to_out.put(pb);
   };
   for (;;) {
+    const StageClock::time_point tw = StageClock::now();
     Batch *bt = to_gpu.take();
+    gpuWaitIn += secondsSince(tw);
+    ++batchCnt;
     int ticket = -1;
     cfr_handle *hb = h;
     if (dryOut) {  // no device: the output stage sees every read as unclassified
@@ -926,6 +974,8 @@ int main(int argc, char *argv[]) {
         bt->masked2.resize(bt->seq2.size());
         st = cfr_submit_batch_masked(h, &b, bt->results.data(), bt->assign.data(), &bt->masked1[0],
                                      hasMate ? &bt->masked2[0] : NULL, NULL, &ticket);
+      } else if (bt->isPacked) {
+        st = cfr_submit_packed(h, &bt->packed, bt->results.data(), bt->assign.data(), NULL, &ticket);
       } else {
         st = cfr_submit_batch(h, &b, bt->results.data(), bt->assign.data(), NULL, &ticket);
       }
@@ -954,6 +1004,14 @@ int main(int argc, char *argv[]) {
     return EXIT_FAILURE;
   }
   if (rc) return rc;
+  if (stageReport) {
+    // ingest / output: seconds spent parsing / formatting (total minus waits for a free or finished batch); gpu: seconds
+    // the submitting thread waited for the device, and for the ingest stage (a large share = the parser is the bottleneck)
+    fprintf(stderr, "[cfr-stages] {\"batches\": %zu, \"pipeline_s\": %.3f, \"ingest_busy_s\": %.3f, \"ingest_wait_s\": %.3f, "
+                    "\"gpu_wait_device_s\": %.3f, \"gpu_wait_ingest_s\": %.3f, \"output_busy_s\": %.3f, \"output_wait_s\": %.3f}\n",
+            batchCnt, secondsSince(tPipe0), ingestTotal - ingestWait, ingestWait, gpuWaitDev, gpuWaitIn, outputTotal - outputWait,
+            outputWait);
+  }
   // ResultWriter::Finalize (ResultWriter.hpp:279-283)
   PrintLog("Processed %lu read fragments, and %lu (%.2lf%%) can be classified.", totalCnt, classifiedCnt,
            (double)classifiedCnt / (double)totalCnt * 100.0);

@@ -308,7 +308,8 @@ CFR_HD int adaptive_quorum(int quorum, u32 alive_mask, int lanes_per_task) {
   return (q < quorum ? (q < 1 ? 1 : q) : quorum) * lanes_per_task;
 }
 
-enum { CFR_ST_EXTEND = 0, CFR_ST_CLOSE = 1, CFR_ST_FETCH = 2, CFR_ST_DONE = 3 };
+// CFR_ST_PROBE (single-wait pair policy only): the search has its wide-table key (kept in sp) and waits for the entry
+enum { CFR_ST_EXTEND = 0, CFR_ST_CLOSE = 1, CFR_ST_FETCH = 2, CFR_ST_DONE = 3, CFR_ST_PROBE = 4 };
 
 // the pair policies implement extend2; the others never reach the call (Bwt::PAIR == 0)
 template <class Bwt>
@@ -318,6 +319,21 @@ CFR_HD typename std::enable_if<(Bwt::PAIR != 0), int>::type pair_extend2(const D
 }
 template <class Bwt>
 CFR_HD typename std::enable_if<(Bwt::PAIR == 0), int>::type pair_extend2(const DevIndex &, bool, int, int, u64 &, u64 &, OpCount &) {
+  return 0;
+}
+// the single-wait pair policy (Bwt::PAIR == 2, device only) implements round(); the others never reach the call
+template <class Bwt>
+CFR_HD typename std::enable_if<(Bwt::PAIR == 2), int>::type pair_round(const DevIndex &ix, bool go, int c1, int c2, u64 &sp, u64 &ep,
+                                                                       bool probe, u64 key, u64x2 &entry, OpCount &oc) {
+#if defined(__CUDA_ARCH__)
+  return Bwt::round(ix, go, c1, c2, sp, ep, probe, key, entry, oc);
+#else
+  return 0;
+#endif
+}
+template <class Bwt>
+CFR_HD typename std::enable_if<(Bwt::PAIR != 2), int>::type pair_round(const DevIndex &, bool, int, int, u64 &, u64 &, bool, u64, u64x2 &,
+                                                                       OpCount &) {
   return 0;
 }
 
@@ -334,7 +350,7 @@ CFR_HD void search_tasks(const DevIndex &ix, const DevParams &P, const ChunkDev 
   int l0 = 0;  // bases of the current search that came out of a lookup table (no BackwardExtend ran for them)
   int st = CFR_ST_FETCH;
   for (;;) {
-    const u32 ext = CFR_BALLOT(st == CFR_ST_EXTEND);
+    const u32 ext = CFR_BALLOT(st == CFR_ST_EXTEND || st == CFR_ST_PROBE);
     const u32 trn = CFR_BALLOT(st == CFR_ST_CLOSE || st == CFR_ST_FETCH);
     if ((ext | trn) == 0) break;
     // warp-uniform: does the deferred transition block run in this iteration?
@@ -399,7 +415,16 @@ CFR_HD void search_tasks(const DevIndex &ix, const DevParams &P, const ChunkDev 
         if (WW > 0 && remaining >= WW) {  // the wide table answers for the last WW bases unless one is not ACGT
           u64 key;
           int nvalid;
-          if (s.init_key(remaining, WW, key, nvalid)) {
+          if (Bwt::PAIR == 2 && s.init_key(remaining, WW, key, nvalid)) {
+            // the entry is fetched with this iteration's lines (pair_round below); the cursor is placed where the
+            // search continues if it does (the table covered WW bases), so its words are loading meanwhile
+            ++oc.search;
+            st = CFR_ST_PROBE;
+            sp = (pos_t)key;
+            wide_done = true;
+            l0 = WW;
+            if (WW < remaining) s.seek(remaining - 1 - WW);
+          } else if (Bwt::PAIR != 2 && s.init_key(remaining, WW, key, nvalid)) {
             ++oc.search;
             const u64x2 e = ld128(ix.wide + key);
             l = (int)(e.y >> 56);
@@ -453,7 +478,41 @@ CFR_HD void search_tasks(const DevIndex &ix, const DevParams &P, const ChunkDev 
         }
       }
     }
-    if (Bwt::PAIR) {
+    if (Bwt::PAIR == 2) {
+      // one memory round for the whole warp: the lines of the lanes that extend and the table entries of the lanes
+      // that start a search arrive together
+      const bool act = st == CFR_ST_EXTEND, probe = st == CFR_ST_PROBE;
+      int c1 = 0, c2 = -1;
+      if (act) {
+        c1 = s.peek();  // the cursor stands on strand position remaining - 1 - l
+        st = CFR_ST_CLOSE;
+        if (c1 <= 3 && l + 1 < remaining) {
+          s.advance();
+          c2 = s.peek();
+          if (c2 > 3) c2 = -1;  // the search ends on this base (FMIndex.hpp:500)
+        }
+      }
+      const bool go = act && c1 <= 3;
+      u64 psp = (u64)sp, pep = (u64)ep;
+      u64x2 e;
+      e.x = e.y = 0;
+      const int done = pair_round<Bwt>(ix, go, c1, c2, psp, pep, probe, (u64)sp, e, oc);
+      if (go) {
+        sp = (pos_t)psp;
+        ep = (pos_t)pep;
+        l += done;
+        if (done == 2 && l < remaining) {
+          st = CFR_ST_EXTEND;
+          s.advance();
+        }
+      }
+      if (probe) {  // where FMIndex::BackwardSearch stands after the last WW bases
+        l = (int)(e.y >> 56);
+        sp = (pos_t)e.x;
+        ep = (pos_t)(e.y & 0xffffffffffffffull);
+        st = (l == WW && l < remaining) ? CFR_ST_EXTEND : CFR_ST_CLOSE;
+      }
+    } else if (Bwt::PAIR) {
       // up to two FMIndex::BackwardExtend steps from one line per boundary; the call is warp-uniform (the lines
       // are fetched cooperatively), lanes outside a search pass go = false
       const bool act = st == CFR_ST_EXTEND;
@@ -651,7 +710,7 @@ CFR_HD u32 select_write_rows(const DevIndex &ix, const DevParams &P, const Chunk
     for (u64 t = 0; t < rp.total; ++t) {
       const u64 row = plan_row_at(fh[i].sp, fh[i].ep, rp, t);
       if (direct)
-        B.seq_ids[o++] = ld32(ix.dense + row);
+        B.seq_ids[o++] = dense_read(ix, row);
       else
         B.rows[o++] = row;
     }

@@ -31,7 +31,7 @@ typedef enum {
   CFR_ERR_ARG = -1,          /* bad argument */
   CFR_ERR_IO = -2,           /* index file missing / short */
   CFR_ERR_FORMAT = -3,       /* .cfr grammar mismatch */
-  CFR_ERR_UNSUPPORTED = -4,  /* protein index, non-ACGT alphabet, k <= 0 ... */
+  CFR_ERR_UNSUPPORTED = -4,  /* protein index, non-ACGT alphabet ... */
   CFR_ERR_CUDA = -5,         /* no device / CUDA runtime error */
   CFR_ERR_NOMEM = -6,
   CFR_ERR_OVERFLOW = -7      /* a per-read device work area was exceeded; the condition stays raised on the
@@ -132,6 +132,30 @@ int cfr_classify_batch(cfr_handle *h, const cfr_read_batch *in, cfr_result *resu
 int cfr_submit_batch(cfr_handle *h, const cfr_read_batch *in, cfr_result *results, uint64_t *ids, void *stream,
                      int *ticket);
 int cfr_wait_batch(cfr_handle *h, int ticket);
+
+/* The same batch with the bases already packed by the producer: 2-bit codes plus one "not ACGT" bit per base,
+ * 2.25 bits per base over the host link instead of 8 (what the device works on anyway: on this path a byte
+ * outside "ACGT" only stops a match, complements to N and is DUST's fifth symbol -- FMIndex.hpp:396,500,
+ * Classifier.hpp:846-856, Dustmasker.hpp:298-302 --, so nothing is lost).  The batch buffer holds mate 1's reads
+ * from position 0 and mate 2's from the next multiple of 32 after them; position j lives in word j / 32:
+ *   codes[j / 32] bits 2(j % 32) ..   A = 0, C = 1, G = 2, T = 3 (0 for any other byte)
+ *   nmask[j / 32] bit  j % 32         1 = the byte was not one of "ACGT" (set for every padding position too)
+ * off1 / off2 are positions in that buffer (off1[0] = 0, off2[0] = (off1[n_reads] + 31) & ~31).
+ * cfr_pack_reads produces all of it from a cfr_read_batch with `threads` host threads (the CLI's ingest stage
+ * calls it per parsed batch); n_words = cfr_packed_words(in) sizes codes / nmask, off1 / off2 hold n_reads + 1. */
+typedef struct {
+  uint64_t n_reads;
+  const uint64_t *codes;
+  const uint32_t *nmask;
+  uint64_t n_words;
+  const uint64_t *off1;
+  const uint64_t *off2; /* NULL for single-end */
+} cfr_packed_batch;
+uint64_t cfr_packed_words(const cfr_read_batch *in);
+int cfr_pack_reads(const cfr_read_batch *in, uint64_t *codes, uint32_t *nmask, uint64_t *off1, uint64_t *off2, int threads,
+                   cfr_packed_batch *out);
+/* cfr_submit_batch for a packed batch (same tickets, same cfr_wait_batch / cfr_fetch_expanded) */
+int cfr_submit_packed(cfr_handle *h, const cfr_packed_batch *in, cfr_result *results, uint64_t *ids, void *stream, int *ticket);
 
 /* cfr_submit_batch that also returns the reads as Classifier::Query saw them: the bytes of seq1 / seq2
  * with the DUST-masked intervals replaced by 'N' (CentrifugerClass.cpp:276-316 masks the reads in

@@ -171,13 +171,20 @@ void *hostsim_open(const char *prefix, const cfr_params *p) {
     ix.pair_F = (int)k18[17];
   }
   ix.dense_shift = -1;
+  ix.dense16 = 0;
   if (const char *e = getenv("HOSTSIM_DENSE_LOCATE")) {  // the library's dense locate table
     const int shift = atoi(e);
     if (shift >= 0 && ix.sample_shift > shift) {
-      h->dense.resize((ix.n >> shift) + 1);
+      const u64 n_rows = ((ix.n - 1) >> shift) + 1;
+      const char *e16 = getenv("HOSTSIM_DENSE16");  // 16-bit entries (the library picks them when every id fits)
+      ix.dense16 = e16 && atoi(e16) != 0 ? 1 : 0;
+      h->dense.resize(n_rows + 1);
       OpCount oc{};
-      for (u64 j = 0; j < h->dense.size(); ++j)
-        h->dense[j] = (u32)(h->layout == 2 ? locate_row<BwtOccLine>(ix, j << shift, oc) : locate_row<BwtRunBlock>(ix, j << shift, oc));
+      for (u64 j = 0; j < n_rows; ++j) {
+        const u32 id = (u32)(h->layout == 2 ? locate_row<BwtOccLine>(ix, j << shift, oc) : locate_row<BwtRunBlock>(ix, j << shift, oc));
+        if (ix.dense16) reinterpret_cast<unsigned short *>(h->dense.data())[j] = (unsigned short)id;
+        else h->dense[j] = id;
+      }
       ix.dense = h->dense.data();
       ix.dense_shift = shift;
     }

@@ -70,3 +70,48 @@ def test_product_does_not_reference_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h")):
                 txt = open(os.path.join(dp, f), errors="ignore").read()
                 assert "oracle" not in txt.lower() or f == "__init__.py" and "oracle" not in txt, os.path.join(dp, f)
+
+
+def _encode_reference(s1, o1, s2, o2):
+    """numpy restatement of the device's k_encode over the batch buffer (mate 1 from 0, mate 2 from the next
+    multiple of 32): 2-bit codes, N bits (padding reads as N)"""
+    import numpy as np
+    len1 = int(o1[-1] - o1[0])
+    len2 = int(o2[-1] - o2[0]) if o2 is not None else 0
+    pos2 = (len1 + 31) & ~31
+    n_words = (pos2 + len2) // 32 + 2
+    buf = np.full(n_words * 32, ord("N"), dtype=np.uint8)
+    buf[:len1] = s1[int(o1[0]):int(o1[0]) + len1]
+    if len2:
+        buf[pos2:pos2 + len2] = s2[int(o2[0]):int(o2[0]) + len2]
+    lut = np.full(256, 4, dtype=np.int64)
+    for i, c in enumerate(b"ACGT"):
+        lut[c] = i
+    x = lut[buf].reshape(-1, 32)
+    nmask = ((x > 3).astype(np.uint64) << np.arange(32, dtype=np.uint64)).sum(axis=1).astype(np.uint32)
+    codes = (np.where(x > 3, 0, x).astype(np.uint64) << (2 * np.arange(32, dtype=np.uint64))).sum(axis=1).astype(np.uint64)
+    return codes, nmask, pos2
+
+
+@pytest.mark.parametrize("threads", [1, 5])
+def test_pack_reads_matches_the_encode_stage(threads):
+    """cfr_pack_reads (the host side of cfr_submit_packed) writes what k_encode writes: ragged and empty reads,
+    lowercase / IUPAC / N bytes, single-end, an empty batch, a batch that starts in the middle of its buffers"""
+    import numpy as np
+    rng = np.random.default_rng(5 + threads)
+    alpha, p = list(b"ACGTNacgtRY-"), [.225, .225, .225, .225, .02, .01, .01, .01, .01, .02, .01, .01]
+    for n, hi, two in ((300, 200, True), (1, 1, True), (0, 1, True), (40000, 160, False), (500, 40, True)):
+        r1 = [bytes(rng.choice(alpha, p=p, size=int(L)).astype(np.uint8)) for L in rng.integers(0, hi, size=n)]
+        r2 = [bytes(rng.choice(alpha, p=p, size=int(L)).astype(np.uint8)) for L in rng.integers(0, hi, size=n)]
+        s1, o1 = cb.pack_reads([b"GATTACA"] + r1)  # the batch proper starts at offset 7 of the caller's buffer
+        s2, o2 = cb.pack_reads(r2) if two else (None, None)
+        o1 = o1[1:]
+        pk, (codes, nmask, p1, p2) = cb.pack_batch(s1, o1, s2, o2, threads=threads)
+        ec, em, pos2 = _encode_reference(s1, o1, s2, o2)
+        assert pk.n_words == len(ec) == len(codes) and pk.n_reads == n
+        assert (codes == ec).all() and (nmask == em).all()
+        assert (p1 == o1 - o1[0]).all()
+        if two:
+            assert (p2 == o2 + np.uint64(pos2)).all()
+        else:
+            assert pk.off2 is None

@@ -23,17 +23,22 @@ VARIANTS = {"default": {}, "pos64": {"CFR_B200_POS64": "1"}, "pos64_ld128": {"CF
             "ld128": {"CFR_B200_OCC_LOAD": "0"}, "noscreen": {"CFR_B200_DUST_SCREEN": "0"},
             "wide12": {"CFR_B200_WIDE_LOOKUP": "12"}, "wide11_pos64": {"CFR_B200_WIDE_LOOKUP": "11", "CFR_B200_POS64": "1"},
             "literal": {"CFR_B200_DENSE_LOCATE": "-1"}, "dense1_pos64": {"CFR_B200_DENSE_LOCATE": "1", "CFR_B200_POS64": "1"},
-            "dense3": {"CFR_B200_DENSE_LOCATE": "3"}, "dense2_ld128": {"CFR_B200_DENSE_LOCATE": "2", "CFR_B200_OCC_LOAD": "0"},
+            "dense3": {"CFR_B200_DENSE_LOCATE": "3", "CFR_B200_DENSE16": "0"}, "dense0_32bit": {"CFR_B200_DENSE16": "0"}, "dense2_ld128": {"CFR_B200_DENSE_LOCATE": "2", "CFR_B200_OCC_LOAD": "0"},
             # the pair lines (two BackwardExtend steps per 128-byte line, four lanes per strand task) in k_search
             "pairs": {"CFR_B200_PAIRS": "1"}, "pairs_pos64_literal": {"CFR_B200_PAIRS": "1", "CFR_B200_POS64": "1",
                                                                       "CFR_B200_DENSE_LOCATE": "-1"},
-            "pairs_wide12_sb10": {"CFR_B200_PAIRS": "1", "CFR_B200_WIDE_LOOKUP": "12", "CFR_B200_PAIR_SEARCH_BLOCKS": "10"}}
+            "pairs_wide12_sb10": {"CFR_B200_PAIRS": "1", "CFR_B200_WIDE_LOOKUP": "12", "CFR_B200_PAIR_SEARCH_BLOCKS": "10"},
+            # pair lines staged by LDG + STS rounds instead of the cp.async rounds
+            "pairs_ldg_dense1": {"CFR_B200_PAIRS": "1", "CFR_B200_PAIR_FETCH": "1", "CFR_B200_DENSE_LOCATE": "1"},
+            # ... or by one cp.async round per request kind (the default is one wait per iteration for everything)
+            "pairs_rounds_wide11": {"CFR_B200_PAIRS": "1", "CFR_B200_PAIR_FETCH": "2", "CFR_B200_WIDE_LOOKUP": "11"},
+            "pairs_wide11_pos64": {"CFR_B200_PAIRS": "1", "CFR_B200_WIDE_LOOKUP": "11", "CFR_B200_POS64": "1"}}
 
 
 @pytest.fixture(params=sorted(VARIANTS))
 def variant_env(request, monkeypatch):
     for k in ("CFR_B200_POS64", "CFR_B200_OCC_LOAD", "CFR_B200_DUST_SCREEN", "CFR_B200_WIDE_LOOKUP", "CFR_B200_DENSE_LOCATE",
-              "CFR_B200_PAIRS", "CFR_B200_PAIR_SEARCH_BLOCKS"):
+              "CFR_B200_PAIRS", "CFR_B200_PAIR_SEARCH_BLOCKS", "CFR_B200_PAIR_FETCH", "CFR_B200_DENSE16"):
         monkeypatch.delenv(k, raising=False)
     for k, v in VARIANTS[request.param].items():
         monkeypatch.setenv(k, v)  # read by cfr_open
@@ -240,8 +245,6 @@ def test_edge_inputs(tiny_dir):
     g.close()
     o.close()
     with pytest.raises(cb.CfrError):
-        cb.Classifier(idx, k=0)
-    with pytest.raises(cb.CfrError):
         cb.Classifier(os.path.join(tiny_dir, "does_not_exist"))
 
 
@@ -369,6 +372,47 @@ def test_streaming_submit_wait(small_dir):
     g.close()
 
 
+def test_packed_submit_same_results(tiny_dir, small_dir):
+    """cfr_submit_packed (bases packed on the host by cfr_pack_reads: 2-bit codes + N bits, no k_encode pass) gives what
+    cfr_submit_batch gives for the same reads, and the oracle's answers: paired and single-end, the edge-case reads
+    (empty reads, non-ACGT bytes, low complexity), with and without DUST, with --expand-taxid lists"""
+    idx = os.path.join(small_dir, "idx")
+    _, r1 = read_fastx(os.path.join(small_dir, "pe_150_1.fq"))
+    _, r2 = read_fastx(os.path.join(small_dir, "pe_150_2.fq"))
+    _, e1 = read_fastx(os.path.join(small_dir, "edge_1.fq"))
+    _, e2 = read_fastx(os.path.join(small_dir, "edge_2.fq"))
+    r1, r2 = r1[:4000] + e1 + [b"", b"acgtn" * 30], r2[:4000] + e2 + [b"ACGT" * 40, b""]
+    for dust in (True, False):
+        g = cb.Classifier(idx, k=5, dust=dust, arena_rows=9000)
+        o = Oracle(idx, k=5, dust=dust)
+        for a, b in ((r1, r2), (r2, None), ([], None)):
+            s1, o1 = cb.pack_reads(a)
+            s2, o2 = cb.pack_reads(b) if b is not None else (None, None)
+            pk, keep = cb.pack_batch(s1, o1, s2, o2, threads=3)
+            h0 = g.info(13)
+            tk, res, ids = g.submit_packed(pk)
+            g.wait(tk)
+            if len(a):
+                # bytes over the host link: 12 per 32 bases, plus the offsets of reads that differ in length
+                assert 0 <= g.info(13) - h0 - int(pk.n_words) * 12 <= 16 * (len(a) + 1)
+                eres, eids = g.classify(a, b)
+                assert np.array_equal(res, eres) and np.array_equal(ids.reshape(-1, 5), eids)
+                assert _tuples(res, ids.reshape(-1, 5), 5) == _oracle_tuples(o, a, b)
+        g.close()
+        o.close()
+    tidx = os.path.join(tiny_dir, "idx")
+    _, c1 = read_fastx(golden_path("tiny", "se_com.fq"))
+    g = cb.Classifier(tidx, k=1, expand_taxid=True)
+    eres, eids, elists = g.classify_expanded(c1)
+    s1, o1 = cb.pack_reads(c1)
+    pk, keep = cb.pack_batch(s1, o1)
+    tk, res, ids = g.submit_packed(pk)
+    g.wait(tk)
+    lists = g._expansion_lists(res, lambda c, o_, i, cap, n: g.L.cfr_fetch_expanded(g.h, tk, c, o_, i, cap, n))
+    assert np.array_equal(res, eres) and lists == elists and sum(len(x) for l in lists for x in l) > 0
+    g.close()
+
+
 def _oracle_expansion(o, r1, r2, k):
     tup, lists = [], []
     for i in range(len(r1)):
@@ -433,6 +477,46 @@ def test_cli_expand_taxid(tiny_dir, manifest):
             assert r.returncode == 0, r.stderr.decode()
             assert r.stdout.decode() == open(golden_path("tiny", "expanded", name + ".tsv")).read(), (name, batch)
             assert hashlib.md5(r.stdout).hexdigest() == m["md5"], name
+
+
+def test_unlimited_results_k0(tiny_dir, manifest, monkeypatch):
+    """-k 0 / negative -k (Classifier.hpp:620-623, :784-785): the CLI's TSV is byte for byte the reference binary's
+    (also with the pair lines in the search kernel and a small arena), the C ABI agrees with the oracle, and a
+    read with more best-scoring sequences than unlimited_cap keeps is an error, never a shortened list"""
+    import subprocess
+    exe = os.path.join(os.path.dirname(cb.LIB_PATH), "centrifuger-b200")
+    for pairs in ("0", "1"):
+        monkeypatch.setenv("CFR_B200_PAIRS", pairs)
+        for name, m in sorted(manifest["k0"].items()):
+            files = [golden_path("tiny", f) for f in m["files"]]
+            cmd = [exe, "-x", os.path.join(tiny_dir, m["index"])] + m["args"] + (["--batch", "37"] if pairs == "1" else [])
+            cmd += ["-u", files[0]] if len(files) == 1 else ["-1", files[0], "-2", files[1]]
+            r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+            assert r.returncode == 0, r.stderr.decode()
+            assert r.stdout.decode() == open(golden_path("tiny", "k0", name + ".tsv")).read(), (name, pairs)
+            assert hashlib.md5(r.stdout).hexdigest() == m["md5"], name
+    monkeypatch.delenv("CFR_B200_PAIRS")
+    idx = os.path.join(tiny_dir, "idx")
+    _, r1 = read_fastx(golden_path("tiny", "pe_100_1.fq"))
+    _, r2 = read_fastx(golden_path("tiny", "pe_100_2.fq"))
+    _, com = read_fastx(golden_path("tiny", "se_com.fq"))
+    for layout in LAYOUTS:
+        for kw, reads in ((dict(k=0), (r1, r2)), (dict(k=-2, hitk_factor=3), (r1, r2)), (dict(k=0, dust=False), (com, None))):
+            o = Oracle(idx, **kw)
+            exp = _oracle_tuples(o, *reads)
+            o.close()
+            assert max(t[4] for t in exp) > 5
+            for cap, arena in ((0, 0), (16, 300)):
+                g = cb.Classifier(idx, layout=layout, unlimited_cap=cap, arena_rows=arena, **kw)
+                assert g.k == (cap or 64)
+                res, ids = g.classify(*reads)
+                g.close()
+                assert _tuples(res, ids, g.k) == exp, (layout, kw, cap)
+    g = cb.Classifier(idx, k=0, unlimited_cap=4)
+    with pytest.raises(cb.CfrError) as e:
+        g.classify(com)
+    assert e.value.code == -7 and "unlimited_cap" in str(e.value)
+    g.close()
 
 
 def test_cli_long_reads_and_consider_secondary(tiny_dir, manifest):

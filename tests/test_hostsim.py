@@ -102,6 +102,7 @@ def test_dense_locate_table_same_answers(tiny_dir, layout, shift, monkeypatch):
     """the dense locate table (answers of the reference's own walk, stored for every 2^shift-th row)
     changes no result; idx_off3 samples every 8th row, the others every 16th"""
     monkeypatch.setenv("HOSTSIM_DENSE_LOCATE", str(shift))
+    monkeypatch.setenv("HOSTSIM_DENSE16", str(shift & 1))  # 16-bit entries at the odd spacings
     for variant in ("idx", "idx_off3", "idx_b8"):
         idx = os.path.join(tiny_dir, variant)
         for files in (["se_100.fq"], ["pe_100_1.fq", "pe_100_2.fq"], ["edge_1.fq", "edge_2.fq"]):

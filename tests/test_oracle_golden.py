@@ -88,6 +88,21 @@ def test_tiny_expand_taxid_outputs(tiny_dir, manifest):
     assert with_lists > 400
 
 
+def test_unlimited_results_k0(tiny_dir, manifest):
+    """-k 0 and negative -k: every row of a hit is resolved and every best-scoring sequence is reported, never
+    reduced by rank (Classifier.hpp:620-623, :784-785); goldens of the reference binary (tests/golden/make_golden_k0.py)"""
+    for name, m in sorted(manifest["k0"].items()):
+        files = [golden_path("tiny", f) for f in m["files"]]
+        args = [a for a in m["args"] if a != "--expand-taxid"]
+        ids, r1 = read_fastx(files[0])
+        r2 = read_fastx(files[1])[1] if len(files) == 2 else None
+        o = Oracle(os.path.join(tiny_dir, m["index"]), **_args_to_kw(args))
+        got = o.classify_tsv_expanded(ids, r1, r2) if "--expand-taxid" in m["args"] else o.classify_tsv(ids, r1, r2)
+        o.close()
+        assert got == open(golden_path("tiny", "k0", name + ".tsv")).read(), name
+        assert hashlib.md5(got.encode()).hexdigest() == m["md5"], name
+
+
 def test_long_reads_and_consider_secondary(tiny_dir, manifest):
     """reads of 2 - 9 kbp, and the near-tie rule (Classifier.hpp:763-781, `2nd >= (size_t)(factor * best)`
     once the second hit length passes the bar) with the bar lowered so that short reads reach it"""
