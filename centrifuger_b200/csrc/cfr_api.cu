@@ -58,6 +58,20 @@ struct DevBuf {
     bytes = want;
     return CFR_OK;
   }
+  // grow keeping the first `keep` bytes (ordered after the work already enqueued on `s`)
+  int grow_keeping(size_t need, size_t keep, cudaStream_t s) {
+    if (need <= bytes) return CFR_OK;
+    void *q = nullptr;
+    const size_t want = need + need / 8 + 256;
+    cudaError_t e = cudaMalloc(&q, want);
+    if (e != cudaSuccess) return fail(CFR_ERR_NOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    if (p && keep) cudaMemcpyAsync(q, p, std::min(keep, bytes), cudaMemcpyDeviceToDevice, s);
+    cudaStreamSynchronize(s);
+    if (p) cudaFree(p);
+    p = q;
+    bytes = want;
+    return CFR_OK;
+  }
   void release() {
     if (p) cudaFree(p);
     p = nullptr;
@@ -295,6 +309,7 @@ int upload_index(cfr_handle *h) {
     ix.sel_filter = (const u64 *)p;
   }
   ix.dense_shift = -1;
+  ix.dense_idx_shift = 0;
   ix.pre_width = (int)f.precompute_width;
   if ((st = dev_upload(h, f.lookup, f.precompute_size * 16, 16, &p))) return st;
   ix.lookup = (const u64x2 *)p;
@@ -409,14 +424,23 @@ int build_dense_locate(cfr_handle *h, int shift, bool e16) {
   void *p;
   int st = dev_alloc(h, &p, n_rows * esz + 16);
   if (st) return st;
-  h->ix.dense_shift = -1;
-  const int grid = grid_for(h, n_rows, 128, 16);
-  if (h->layout == CFR_LAYOUT_OCCLINE) k_build_dense<BwtOccLine><<<grid, 128, 0, h->stream>>>(h->ix, (u32 *)p, shift, n_rows, e16 ? 1 : 0);
-  else k_build_dense<BwtRunBlock><<<grid, 128, 0, h->stream>>>(h->ix, (u32 *)p, shift, n_rows, e16 ? 1 : 0);
-  ++h->launches;
-  CUDA_TRY(cudaGetLastError());
-  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  // level by level, coarsest first: every 2^(sample_shift-1)-th row walks to the stored samples, the rows of each finer
+  // level walk to the level before (k_build_dense)
   h->ix.dense = (const u32 *)p;
+  h->ix.dense16 = e16 ? 1 : 0;
+  h->ix.dense_idx_shift = shift;
+  h->ix.dense_shift = -1;
+  for (int level = h->ix.sample_shift - 1; level >= shift; --level) {
+    const u64 rows_l = ((h->ix.n - 1) >> level) + 1;
+    const int grid = grid_for(h, rows_l, 128, 16);
+    const int skip = h->ix.dense_shift >= 0 ? 1 : 0;
+    if (h->layout == CFR_LAYOUT_OCCLINE) k_build_dense<BwtOccLine><<<grid, 128, 0, h->stream>>>(h->ix, (u32 *)p, level, skip, rows_l, e16 ? 1 : 0);
+    else k_build_dense<BwtRunBlock><<<grid, 128, 0, h->stream>>>(h->ix, (u32 *)p, level, skip, rows_l, e16 ? 1 : 0);
+    ++h->launches;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    h->ix.dense_shift = level;
+  }
   h->ix.dense_shift = shift;
   h->ix.dense16 = e16 ? 1 : 0;
   h->dense_bytes = n_rows * esz;
@@ -605,7 +629,7 @@ void fill_chunk(cfr_handle *h, cfr_device_batch *b, ChunkDev &B) {
     B.exp_cnt = (u32 *)b->exp_cnt.p;
     B.exp_off = (u64 *)b->exp_off.p;
     B.exp_ids = (u64 *)b->exp_ids.p;
-    B.exp_cap = b->arena_cap;
+    B.exp_cap = b->exp_ids.bytes / 8;
     B.exp_used = (u64 *)((char *)b->scalars.p + 56);
   }
   B.read_list = nullptr;
@@ -690,18 +714,50 @@ int finish_deferred(cfr_handle *h, cfr_device_batch *b, cudaStream_t s) {
       u64 used;
       u32 n_def;
       u32 pad;
+      u64 other[5];
+      u64 exp_used;
     } sc;
-    CUDA_TRY(cudaMemcpyAsync(&sc, b->scalars.p, 16, cudaMemcpyDeviceToHost, s));
+    static_assert(sizeof(sc) == 64, "scalars block");
+    CUDA_TRY(cudaMemcpyAsync(&sc, b->scalars.p, 64, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
     if (sc.n_def == 0) return CFR_OK;
-    if ((u64)sc.n_def == B.n_list) {
-      // nothing fitted: the first read of the list alone exceeds the arena
-      return fail(CFR_ERR_OVERFLOW, "a single read needs more locate rows than arena_rows; raise cfr_params.arena_rows");
-    }
     B.read_list = lists[cur];
+    const bool none_fitted = (u64)sc.n_def == B.n_list;
     B.n_list = sc.n_def;
     cur ^= 1;
     B.deferred = lists[cur];
+    if (none_fitted) {
+      // nothing fitted: the first read of the list alone exceeds the arena (a hit with a wide range under -k 0 or
+      // --hitk-factor 0, a small last batch).  The reference classifies such reads, so the arena grows to the largest
+      // slice a deferred read needs; the rows of the reads scored so far are done with.
+      unsigned long long *d_max = reinterpret_cast<unsigned long long *>((char *)b->scalars.p + 16);  // the search kernel's task counter: done with
+      unsigned long long need = 0;
+      CUDA_TRY(cudaMemsetAsync(d_max, 0, 8, s));
+      k_max_arena_rows<<<grid_for(h, B.n_list, 256, 4), 256, 0, s>>>(B, d_max);
+      ++h->launches;
+      CUDA_TRY(cudaMemcpyAsync(&need, d_max, 8, cudaMemcpyDeviceToHost, s));
+      CUDA_TRY(cudaStreamSynchronize(s));
+      if (need <= b->arena_cap) return fail(CFR_ERR_OVERFLOW, "deferral made no progress although every read fits the arena");
+      const u64 arena = need + need / 4;
+      int st;
+      if ((st = b->rows.ensure(arena * 8)) || (st = b->seq_ids.ensure(arena * 4)) || (st = b->rec0.ensure(arena * sizeof(SeqRec))) ||
+          (st = b->rec1.ensure(arena * sizeof(SeqRec))) || (st = b->best.ensure(arena * 8)) || (st = b->tmp.ensure(arena * 8)))
+        return fail(CFR_ERR_OVERFLOW, "a single read needs more locate rows than the device can hold");
+      b->arena_cap = arena;
+      const u32 *keep_list = B.read_list;
+      u32 *keep_def = B.deferred;
+      const u64 keep_n = B.n_list;
+      fill_chunk(h, b, B);
+      B.read_list = keep_list;
+      B.deferred = keep_def;
+      B.n_list = keep_n;
+    }
+    if (h->params.expand_taxid) {
+      // the lists of the reads scored so far stay in exp_ids until they are fetched: room for one more arena of them
+      if (b->exp_ids.grow_keeping((sc.exp_used + b->arena_cap) * 8, sc.exp_used * 8, s)) return CFR_ERR_NOMEM;
+      B.exp_ids = (u64 *)b->exp_ids.p;
+      B.exp_cap = b->exp_ids.bytes / 8;
+    }
     int st = run_pass<Bwt, BwtWide>(h, B, 0, s);
     if (st) return st;
   }

@@ -44,6 +44,14 @@ class SeqReader {
     if (fp_) gzclose(fp_);
     fp_ = nullptr;
   }
+  // continue at byte `offset` of the (uncompressed) file: the block-parallel reader hands over here
+  bool seek(size_t offset) {
+    if (offset == 0) return true;
+    if (gzseek(fp_, (z_off_t)offset, SEEK_SET) < 0) return false;
+    len_ = pos_ = 0;
+    eof_ = false;
+    return true;
+  }
   // appends the record's sequence to `seq` (and, for FASTQ records, its quality string to `qual` when
   // given: a FASTA record appends nothing there); returns false at end of file
   bool next(std::string &name, std::string &seq, std::string *qual = nullptr, std::string *comment = nullptr) {

@@ -1164,7 +1164,7 @@ CFR_HD u32 dense_read(const DevIndex &ix, u64 j) {
 // below returns for the walk that starts there (checks at the row itself included)
 CFR_HD bool get_located(const DevIndex &ix, u64 i, u64 &sa) {
   if (is_dense_row(ix, i)) {
-    sa = (u64)dense_read(ix, i >> ix.dense_shift);
+    sa = (u64)dense_read(ix, i >> ix.dense_idx_shift);
     return true;
   }
   return get_sampled_sa(ix, i, sa);

@@ -183,6 +183,18 @@ __global__ void __launch_bounds__(128) k_score(const __grid_constant__ DevIndex 
   if (err) atomicOr(&B.counters[CFR_STAGE_SCORE].error_flags, err);
 }
 
+// the largest arena slice any read of the list needs (a read that alone exceeds the arena: the arena is regrown to it)
+__global__ void __launch_bounds__(256) k_max_arena_rows(const __grid_constant__ ChunkDev B, unsigned long long *out) {
+  const u64 stride = (u64)gridDim.x * blockDim.x;
+  u32 m = 0;
+  for (u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x; t < B.n_list; t += stride) {
+    const u32 r = B.work[chunk_read_id(B, t)].arena_rows;
+    m = r > m ? r : m;
+  }
+  m = __reduce_max_sync(0xffffffffu, m);
+  if ((threadIdx.x & 31) == 0 && m) atomicMax(out, (unsigned long long)m);
+}
+
 // Index transcoding at load time: run-block BWT (as stored) -> 32-byte occ sectors.
 // One thread per sector: 3 exclusive Sequence_RunBlock::Rank queries give the
 // counters, 64 Sequence_RunBlock::Access queries give the symbols -- the literal
@@ -345,14 +357,22 @@ __global__ void __launch_bounds__(128) k_build_wide(const __grid_constant__ DevI
 
 // Dense locate table at load time: the literal walk (FMIndex::BackwardToSampledSA over the stored
 // samples only) from every row that is a multiple of 2^shift
+// One level of the table: the rows that are multiples of 2^level (`skip_coarser`: except the multiples of 2^(level+1),
+// which the level before wrote).  `ix` carries the table as built so far -- dense_shift = level + 1, or -1 at the first
+// level -- so a walk ends at the first row of a coarser level with the answer the literal walk from there found: the
+// levels together cost ~4 LF steps per row instead of the 15 of a walk to the stored samples.
 template <class Bwt>
-__global__ void __launch_bounds__(128) k_build_dense(const __grid_constant__ DevIndex ix, u32 *out, int shift, u64 n_rows, int e16) {
+__global__ void __launch_bounds__(128) k_build_dense(const __grid_constant__ DevIndex ix, u32 *out, int level, int skip_coarser,
+                                                     u64 n_rows, int e16) {
   const u64 stride = (u64)gridDim.x * blockDim.x;
   OpCount oc{};
   for (u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x; j < n_rows; j += stride) {
-    const u32 id = (u32)locate_row<Bwt>(ix, j << shift, oc);  // ix.dense_shift is still -1 here
-    if (e16) reinterpret_cast<unsigned short *>(out)[j] = (unsigned short)id;
-    else out[j] = id;
+    if (skip_coarser && (j & 1ull) == 0) continue;
+    u64 i = j << level, sa = 0;
+    while (!get_located(ix, i, sa)) i = Bwt::lf(ix, i, oc);
+    const u64 at = (j << level) >> ix.dense_idx_shift;
+    if (e16) reinterpret_cast<unsigned short *>(out)[at] = (unsigned short)sa;
+    else out[at] = (u32)sa;
   }
 }
 

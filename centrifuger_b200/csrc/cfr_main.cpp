@@ -106,6 +106,7 @@ static struct option long_options[] = {
     {"sample-sheet", required_argument, 0, ARGV_SAMPLE_SHEET},
     {(char *)0, 0, 0, 0}};
 #include "cfr_cli_reads.hpp"   // PrintLog, SeqReader, ReadSource: FASTA/FASTQ ingest
+#include "cfr_cli_bulk.hpp"    // BulkReader: block-parallel ingest of plain four-line FASTQ files
 #include "cfr_cli_format.hpp"  // ReadFormat, BarcodeWhitelist, BarcodeTranslation
 #include "cfr_cli_merge.hpp"   // PairMerger
 
@@ -549,6 +550,42 @@ int main(int argc, char *argv[]) {
   double ingestWait = 0, ingestTotal = 0, outputWait = 0, outputTotal = 0, gpuWaitIn = 0, gpuWaitDev = 0;
   size_t batchCnt = 0;
 
+  // Plain FASTQ files without read-format / barcode / UMI work are parsed block-parallel (cfr_cli_bulk.hpp); anything its
+  // strict parser does not accept falls back, per file, to the serial reader below.  CFR_B200_BULK_INGEST=0 disables it.
+  const bool bulkIngest = !useSheet && !interleaved && !hasBarcode && !hasUmi && !fmt.NeedExtract(ReadFormat::R1) &&
+                          !fmt.NeedExtract(ReadFormat::R2) && !(getenv("CFR_B200_BULK_INGEST") && atoi(getenv("CFR_B200_BULK_INGEST")) == 0);
+  const unsigned ingestThreads = getenv("CFR_B200_INGEST_THREADS") ? (unsigned)std::max(1, atoi(getenv("CFR_B200_INGEST_THREADS")))
+                                                                    : std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+  // Sizes a batch's arrays for batchReads records like its first `seen` ones: a string that grows to 150 MB by doubling is
+  // copied and page-faulted several times over, which costs more than parsing the reads
+  auto reserveBatch = [&](Batch &bt, size_t seen) {
+    const size_t target = (size_t)batchReads;
+    auto scaled = [&](size_t bytes) { return std::min<size_t>((size_t)((double)bytes / (double)seen * (double)target * 1.03) + 4096, 272u << 20); };
+    bt.seq1.reserve(scaled(bt.seq1.size()));
+    bt.ids.reserve(scaled(bt.ids.size()));
+    bt.off1.reserve(target + 1);
+    bt.id_off.reserve(target + 1);
+    if (hasMate) {
+      bt.seq2.reserve(scaled(bt.seq1.size()));
+      bt.off2.reserve(target + 1);
+    }
+    if (keepReads) {
+      bt.qual1.reserve(scaled(bt.seq1.size()));
+      bt.qoff1.reserve(target + 1);
+      if (hasMate) {
+        bt.qual2.reserve(scaled(bt.seq1.size()));
+        bt.qoff2.reserve(target + 1);
+      }
+    }
+  };
+  BulkReader bulk1, bulk2;
+  if (bulkIngest) {
+    bulk1.init(reads.files, ingestThreads, true);
+    bulk2.init(mates.files, ingestThreads, true);
+    bulk1.set_want_qual(keepReads);
+    bulk2.set_want_qual(keepReads);
+  }
+
   std::thread ingest([&] {
     std::string name, name2, tmp, comment1;
     int bi = 0;
@@ -561,6 +598,60 @@ int main(int argc, char *argv[]) {
       ingestWait += secondsSince(tw);
       bi = (bi + 1) % NBATCH;
       bt->clear();
+      if (bulkIngest) {
+        // the same batch limits as the record-by-record loop below, applied per slice of records
+        const size_t maxBasesB = 256u << 20;
+        static const size_t slotBudgetB = getenv("CFR_B200_SLOT_BUDGET") ? (size_t)atoll(getenv("CFR_B200_SLOT_BUDGET")) : (64u << 20);
+        size_t maxLenB = 0;
+        const BulkSink s1{&bt->ids, &bt->id_off, &bt->seq1, &bt->off1, keepReads ? &bt->qual1 : nullptr, keepReads ? &bt->qoff1 : nullptr};
+        while ((long)bt->n < batchReads && bt->seq1.size() < maxBasesB &&
+               (bt->n == 0 || (bt->n + 1) * (maxLenB / 24 + 1) <= slotBudgetB)) {
+          size_t want = std::min<size_t>((size_t)batchReads - bt->n, 65536);
+          if (maxLenB > 0) want = std::max<size_t>(1, std::min(want, slotBudgetB / (maxLenB / 24 + 1) > bt->n ? slotBudgetB / (maxLenB / 24 + 1) - bt->n : 1));
+          else want = std::min<size_t>(want, 4096);  // the first slice is short: it tells how long the reads are
+          const bool firstSlice = bt->n == 0;
+          const size_t got = bulk1.take(want, maxBasesB, s1, &maxLenB);
+          bt->n += got;
+          if (firstSlice && got > 0) reserveBatch(*bt, got);  // the batch's arrays are sized once, from the first records
+          if (got < want && bt->seq1.size() < maxBasesB) {
+            eof = true;
+            break;
+          }
+        }
+        if (twoFiles) {
+          const BulkSink s2{nullptr, nullptr, &bt->seq2, &bt->off2, keepReads ? &bt->qual2 : nullptr, keepReads ? &bt->qoff2 : nullptr};
+          const size_t n2 = bulk2.take(bt->n, ~(size_t)0, s2, &maxLenB);
+          if (n2 < bt->n) {  // mate 2 ended first: keep the batch consistent for the stages behind
+            mate_mismatch = true;
+            bt->n = n2;
+            bt->off1.resize(bt->n + 1);
+            bt->id_off.resize(bt->n + 1);
+          } else if (eof && !bulk2.exhausted()) {
+            mate_mismatch = true;  // mate 1 ended: mate 2 must end here too
+          }
+        }
+        bt->last = eof || mate_mismatch;
+        if (mergePairs && hasMate && bt->n) MergeBatch(*bt, true, std::thread::hardware_concurrency());
+        bt->isPacked = false;
+        if (packInput && bt->n) {
+          cfr_read_batch rb;
+          rb.n_reads = bt->n;
+          rb.seq1 = bt->seq1.data();
+          rb.off1 = bt->off1.data();
+          rb.seq2 = hasMate ? bt->seq2.data() : NULL;
+          rb.off2 = hasMate ? bt->off2.data() : NULL;
+          const uint64_t nw = cfr_packed_words(&rb);
+          bt->pcodes.resize(nw);
+          bt->pmask.resize(nw);
+          bt->poff1.resize(bt->n + 1);
+          if (hasMate) bt->poff2.resize(bt->n + 1);
+          bt->isPacked = cfr_pack_reads(&rb, bt->pcodes.data(), bt->pmask.data(), bt->poff1.data(), hasMate ? bt->poff2.data() : NULL,
+                                        (int)packThreads, &bt->packed) == CFR_OK;
+        }
+        to_gpu.put(bt);
+        if (bt->last) break;
+        continue;
+      }
       // a batch ends after batchReads reads or 2^28 bases per mate, whichever comes first (long reads: the
       // device work areas grow with the bases and with the longest read of a batch)
       const size_t maxBases = 256u << 20;
@@ -657,6 +748,7 @@ int main(int argc, char *argv[]) {
           if (keepReads) bt->qoff2.push_back(bt->qual2.size());
         }
         ++bt->n;
+        if (bt->n == 4096 && !twoFiles) reserveBatch(*bt, 4096);  // (with a second parser thread appending, the arrays are left alone)
         n1.store((long)bt->n, std::memory_order_release);
       }
       if (twoFiles) {
@@ -1008,9 +1100,10 @@ int main(int argc, char *argv[]) {
     // ingest / output: seconds spent parsing / formatting (total minus waits for a free or finished batch); gpu: seconds
     // the submitting thread waited for the device, and for the ingest stage (a large share = the parser is the bottleneck)
     fprintf(stderr, "[cfr-stages] {\"batches\": %zu, \"pipeline_s\": %.3f, \"ingest_busy_s\": %.3f, \"ingest_wait_s\": %.3f, "
-                    "\"gpu_wait_device_s\": %.3f, \"gpu_wait_ingest_s\": %.3f, \"output_busy_s\": %.3f, \"output_wait_s\": %.3f}\n",
+                    "\"gpu_wait_device_s\": %.3f, \"gpu_wait_ingest_s\": %.3f, \"output_busy_s\": %.3f, \"output_wait_s\": %.3f, "
+                    "\"ingest_parse_s\": %.3f, \"ingest_threads\": %u, \"block_parallel_ingest\": %s}\n",
             batchCnt, secondsSince(tPipe0), ingestTotal - ingestWait, ingestWait, gpuWaitDev, gpuWaitIn, outputTotal - outputWait,
-            outputWait);
+            outputWait, bulk1.parse_seconds() + bulk2.parse_seconds(), ingestThreads, bulk1.used_fast_path() ? "true" : "false");
   }
   // ResultWriter::Finalize (ResultWriter.hpp:279-283)
   PrintLog("Processed %lu read fragments, and %lu (%.2lf%%) can be classified.", totalCnt, classifiedCnt,

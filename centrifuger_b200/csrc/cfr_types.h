@@ -101,6 +101,8 @@ struct DevIndex {
   // every row that is a multiple of 2^dense_shift: dense[row >> dense_shift] = its sequence id.  A walk
   // that reaches such a row ends there with the answer the reference's longer walk would find.
   int dense_shift;  // -1 = none
+  int dense_idx_shift;  // the entry of dense row i is dense[i >> dense_idx_shift] (= dense_shift once the table is built; while
+                        // it is being built level by level the rows of the coarser levels are the dense ones)
   int dense16;      // entries are 16 bits wide (every sequence id of the index is below 2^16)
   const u32 *dense;
   // taxonomy (Taxonomy.hpp)

@@ -171,6 +171,7 @@ void *hostsim_open(const char *prefix, const cfr_params *p) {
     ix.pair_F = (int)k18[17];
   }
   ix.dense_shift = -1;
+  ix.dense_idx_shift = 0;
   ix.dense16 = 0;
   if (const char *e = getenv("HOSTSIM_DENSE_LOCATE")) {  // the library's dense locate table
     const int shift = atoi(e);
@@ -187,6 +188,7 @@ void *hostsim_open(const char *prefix, const cfr_params *p) {
       }
       ix.dense = h->dense.data();
       ix.dense_shift = shift;
+      ix.dense_idx_shift = shift;
     }
   }
   if (const char *e = getenv("HOSTSIM_WIDE_LOOKUP")) {  // the library's wide lookup table, any width

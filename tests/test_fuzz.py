@@ -44,3 +44,9 @@ def test_merge_readpair_cli_against_reference_binary():
     if not os.path.exists(os.path.join(REF_DIR, "centrifuger")):
         pytest.skip("oracle/_ref/centrifuger not built")
     _run("fuzz_merge_cli.py", 15, 606)
+
+
+def test_block_parallel_ingest_against_serial_reader():
+    """the CLI's block-parallel FASTQ reader (tiny byte ranges, 1 - 8 threads, irregular records mid-file) gives what
+    its serial reader gives -- which test_cli_parser_against_reference_binary pins to the reference"""
+    _run("fuzz_bulk_ingest.py", 40, 707)

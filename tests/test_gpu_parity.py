@@ -248,14 +248,27 @@ def test_edge_inputs(tiny_dir):
         cb.Classifier(os.path.join(tiny_dir, "does_not_exist"))
 
 
-def test_single_huge_read_overflows_loudly(tiny_dir):
-    """a read whose rows exceed the whole arena is an error, never a silent truncation"""
-    g = cb.Classifier(os.path.join(tiny_dir, "idx"), k=5, arena_rows=8)
+def test_arena_regrows_for_a_read_that_exceeds_it(tiny_dir):
+    """a read whose rows exceed the whole arena is classified all the same (the reference has no such limit): the arena
+    grows to the read's need; with --expand-taxid the lists of the reads scored before survive the regrowth"""
+    idx = os.path.join(tiny_dir, "idx")
     _, r1 = read_fastx(os.path.join(tiny_dir, "edge.fq"))
-    with pytest.raises(cb.CfrError) as e:
-        g.classify(r1)
-    assert e.value.code == -7
+    _, com = read_fastx(golden_path("tiny", "se_com.fq"))
+    for kw in (dict(k=5), dict(k=0), dict(k=2, hitk_factor=0)):
+        o = Oracle(idx, **kw)
+        exp = _oracle_tuples(o, r1 + com[:80], None)
+        o.close()
+        g = cb.Classifier(idx, arena_rows=8, **kw)
+        res, ids = g.classify(r1 + com[:80])
+        assert _tuples(res, ids, g.k) == exp, kw
+        g.close()
+    big = cb.Classifier(idx, k=1, expand_taxid=True)
+    eres, eids, elists = big.classify_expanded(com)
+    big.close()
+    g = cb.Classifier(idx, k=1, expand_taxid=True, arena_rows=5)
+    res, ids, lists = g.classify_expanded(com)
     g.close()
+    assert np.array_equal(res, eres) and np.array_equal(ids, eids) and lists == elists
 
 
 # ---------------------------------------------------------------- drop-in CLI

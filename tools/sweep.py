@@ -33,11 +33,14 @@ def main():
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     sptr = stream.cuda_stream
-    streams = [stream, torch.cuda.Stream(), torch.cuda.Stream()]
+    nstream = int(os.environ.get("SWEEP_STREAMS", "3"))
+    streams = [stream] + [torch.cuda.Stream() for _ in range(nstream - 1)]
     steps = int(os.environ.get("SWEEP_STEPS", "4"))
     ref_sig = None
     for setting in settings:
         keys = []
+        if setting in ("default", '""'):
+            setting = ""
         for kv in filter(None, setting.split(",")):
             k, v = kv.split("=")
             os.environ[k] = v
@@ -49,7 +52,7 @@ def main():
 
         def step(multi):
             for j, b in enumerate(batches):
-                clf.classify_resident(b, stream=streams[j % 3].cuda_stream if multi else sptr)
+                clf.classify_resident(b, stream=streams[j % nstream].cuda_stream if multi else sptr)
 
         for _ in range(2):
             step(False)
@@ -83,6 +86,14 @@ def main():
         e1.record(stream)
         torch.cuda.synchronize()
         multi = e0.elapsed_time(e1) / steps
+        # the same three-stream step with every stage bracketed by events: how long each stage takes next to the others
+        clf.stage_times(reset=True)
+        clf.set_profiling(True)
+        for _ in range(2):
+            step(True)
+        torch.cuda.synchronize()
+        stage3 = clf.stage_times(reset=True)
+        clf.set_profiling(False)
         res, ids = clf.fetch(batches[0], stream=sptr)
         sig = (int(res["score"].astype("uint64").sum()), int(ids.sum()), int(res["n_assign"].sum()))
         if ref_sig is None:
@@ -92,6 +103,7 @@ def main():
                "ms_per_batch_3streams": round(multi / nb, 3),
                "Mpairs_s_1stream": round(bn * nb / single / 1e3, 2), "Mpairs_s_3streams": round(bn * nb / multi / 1e3, 2),
                "stage_ms_per_batch": {k: round(v[0] / steps / nb, 3) for k, v in stage.items()},
+               "stage_ms_per_batch_3streams": {k: round(v[0] / 2 / nb, 3) for k, v in stage3.items()},
                "same_results_as_first": sig == ref_sig}
         print(json.dumps(out), flush=True)
         for b in batches:
