@@ -98,7 +98,12 @@ struct cfr_device_batch {
   bool want_masked = false;
   bool classified = false;
   bool packed = false;  // uploaded as 2-bit codes + N bits (cfr_submit_packed): no k_encode pass
+  cudaEvent_t ev_lane[4] = {nullptr, nullptr, nullptr, nullptr};  // in, masked, searched, scored (stage lanes, run_first)
   void release() {
+    for (cudaEvent_t &e : ev_lane) {
+      if (e) cudaEventDestroy(e);
+      e = nullptr;
+    }
     DevBuf *all[] = {&seq_raw, &codes, &mask_raw, &mask, &off, &strand_hits, &strand_nhits, &fhits, &work, &rows, &seq_ids,
                      &rec0, &rec1, &best, &tmp, &results, &out_ids, &deferred, &dust_list, &scalars, &dust_bits, &masked,
                      &exp_cnt, &exp_off, &exp_ids};
@@ -153,6 +158,11 @@ struct cfr_handle {
   enum { NSLOT = 3 };
   cfr_device_batch slots[NSLOT];
   cudaStream_t s_in = nullptr, s_out = nullptr, s_comp[NSLOT] = {nullptr, nullptr, nullptr};
+  // Stage lanes (CFR_B200_LANES=0 disables): the stages of a batch run on three streams BY KIND -- encode + SDUST, search,
+  // select + locate + score -- chained by events, so that the memory-bound search of batch i always has the latency-bound
+  // stages of batches i+1 / i-1 next to it on the SMs, whatever streams the caller's batches arrive on
+  cudaStream_t lane[3] = {nullptr, nullptr, nullptr};
+  bool lanes = true;
   cudaEvent_t ev_start = nullptr, ev_h2d[NSLOT] = {nullptr, nullptr, nullptr}, ev_comp[NSLOT] = {nullptr, nullptr, nullptr},
               ev_d2h[NSLOT] = {nullptr, nullptr, nullptr};
   struct PinnedScalars {
@@ -670,35 +680,62 @@ int run_first(cfr_handle *h, cfr_device_batch *b, cudaStream_t s) {
   ChunkDev B;
   fill_chunk(h, b, B);
   if (b->n_reads == 0) return CFR_OK;
-  CUDA_TRY(cudaMemsetAsync(b->scalars.p, 0, 64, s));
+  // the three stage lanes (or the caller's stream for everything)
+  cudaStream_t s_pre = s, s_search = s, s_post = s;
+  if (h->lanes) {
+    for (cudaStream_t &l : h->lane)
+      if (!l) CUDA_TRY(cudaStreamCreateWithFlags(&l, cudaStreamNonBlocking));
+    for (cudaEvent_t &e : b->ev_lane)
+      if (!e) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    s_pre = h->lane[0];
+    s_search = h->lane[1];
+    s_post = h->lane[2];
+    CUDA_TRY(cudaEventRecord(b->ev_lane[0], s));  // ordered after what the caller's stream holds so far
+    CUDA_TRY(cudaStreamWaitEvent(s_pre, b->ev_lane[0], 0));
+  }
+  CUDA_TRY(cudaMemsetAsync(b->scalars.p, 0, 64, s_pre));
   if (b->packed) {  // the producer encoded the bases: the masks the searches see start as the uploaded ones
-    if (B.mask != B.mask_raw) CUDA_TRY(cudaMemcpyAsync(B.mask, B.mask_raw, B.n_words * 4, cudaMemcpyDeviceToDevice, s));
+    if (B.mask != B.mask_raw) CUDA_TRY(cudaMemcpyAsync(B.mask, B.mask_raw, B.n_words * 4, cudaMemcpyDeviceToDevice, s_pre));
   } else {
-    StageScope sc(h, s, CFR_STAGE_OTHER);
-    k_encode<<<grid_for(h, B.n_words, 256, 8), 256, 0, s>>>(B, b->seq_bytes);
+    StageScope sc(h, s_pre, CFR_STAGE_OTHER);
+    k_encode<<<grid_for(h, B.n_words, 256, 8), 256, 0, s_pre>>>(B, b->seq_bytes);
     ++h->launches;
   }
   if (h->params.dust) {
-    StageScope sc(h, s, CFR_STAGE_DUST);
-    launch_dust(h, B, s);
+    StageScope sc(h, s_pre, CFR_STAGE_DUST);
+    launch_dust(h, B, s_pre);
   }
   if (b->want_masked) {  // the reads as the searches see them, for the caller's --un / --cl files
-    k_apply_dust<<<grid_for(h, b->seq_bytes, 256, 8), 256, 0, s>>>(B, (unsigned char *)b->masked.p, b->seq_bytes);
+    k_apply_dust<<<grid_for(h, b->seq_bytes, 256, 8), 256, 0, s_pre>>>(B, (unsigned char *)b->masked.p, b->seq_bytes);
     ++h->launches;
   }
-  CUDA_TRY(cudaMemsetAsync(B.task_counter, 0, 8, s));
+  CUDA_TRY(cudaMemsetAsync(B.task_counter, 0, 8, s_pre));
+  if (h->lanes) {
+    CUDA_TRY(cudaEventRecord(b->ev_lane[1], s_pre));
+    CUDA_TRY(cudaStreamWaitEvent(s_search, b->ev_lane[1], 0));
+  }
   {
-    StageScope sc(h, s, CFR_STAGE_SEARCH);
+    StageScope sc(h, s_search, CFR_STAGE_SEARCH);
     // the pair policy keeps four lanes per task and more live registers: 8 resident blocks per SM do not spill
     const int sblocks = BwtSearch::PAIR ? h->pair_search_blocks : h->search_blocks;
     const int g = grid_for(h, B.n_reads * 2 * B.mates * BwtSearch::LANES, 128, sblocks);
-    if (sblocks >= 12) k_search<BwtSearch, 12><<<g, 128, 0, s>>>(h->ix, h->P, B);
-    else if (sblocks >= 10) k_search<BwtSearch, 10><<<g, 128, 0, s>>>(h->ix, h->P, B);
-    else k_search<BwtSearch, 8><<<g, 128, 0, s>>>(h->ix, h->P, B);
+    if (sblocks >= 12) k_search<BwtSearch, 12><<<g, 128, 0, s_search>>>(h->ix, h->P, B);
+    else if (sblocks >= 10) k_search<BwtSearch, 10><<<g, 128, 0, s_search>>>(h->ix, h->P, B);
+    else k_search<BwtSearch, 8><<<g, 128, 0, s_search>>>(h->ix, h->P, B);
     ++h->launches;
   }
   CUDA_TRY(cudaGetLastError());
-  return run_pass<Bwt, BwtWide>(h, B, 1, s);
+  if (h->lanes) {
+    CUDA_TRY(cudaEventRecord(b->ev_lane[2], s_search));
+    CUDA_TRY(cudaStreamWaitEvent(s_post, b->ev_lane[2], 0));
+  }
+  const int st = run_pass<Bwt, BwtWide>(h, B, 1, s_post);
+  if (st) return st;
+  if (h->lanes) {  // the caller's stream continues when the batch is scored
+    CUDA_TRY(cudaEventRecord(b->ev_lane[3], s_post));
+    CUDA_TRY(cudaStreamWaitEvent(s, b->ev_lane[3], 0));
+  }
+  return CFR_OK;
 }
 
 // after the first pass: re-run select/locate/score for reads that did not fit the arena
@@ -860,6 +897,7 @@ int cfr_open(const char *idx_prefix, const cfr_params *p, int device, cfr_handle
   if (const char *e = getenv("CFR_B200_SEARCH_BLOCKS")) h->search_blocks = std::max(1, atoi(e));
   if (const char *e = getenv("CFR_B200_PAIR_SEARCH_BLOCKS")) h->pair_search_blocks = std::max(1, atoi(e));
   if (const char *e = getenv("CFR_B200_PAIR_FETCH")) h->pair_fetch = std::min(3, std::max(1, atoi(e)));
+  if (const char *e = getenv("CFR_B200_LANES")) h->lanes = atoi(e) != 0;
   if (const char *e = getenv("CFR_B200_DUST_SCREEN")) h->dust_screen = atoi(e) != 0;
   if (const char *e = getenv("CFR_B200_DUST_QUORUM")) h->dust_quorum = std::max(0, atoi(e));
   if (const char *e = getenv("CFR_B200_DUST_LANES")) h->dust_lanes = std::min(32, std::max(1, atoi(e)));
@@ -965,6 +1003,8 @@ void cfr_close(cfr_handle *h) {
   if (!h) return;
   cudaSetDevice(h->device);
   for (int i = 0; i < cfr_handle::NSLOT; ++i) h->slots[i].release();
+  for (cudaStream_t &l : h->lane)
+    if (l) cudaStreamDestroy(l);
   if (h->s_in) cudaStreamDestroy(h->s_in);
   if (h->s_out) cudaStreamDestroy(h->s_out);
   for (int i = 0; i < cfr_handle::NSLOT; ++i)
@@ -1589,6 +1629,9 @@ NcclApi &nccl_api() {
   static NcclApi a;
   static std::once_flag once;
   std::call_once(once, [] {
+    // NCCL writes its debug lines -- with NCCL_DEBUG=VERSION, which some images set, its version banner -- to STDOUT, where a
+    // caller of this library (the CLI) has its TSV: a library keeps out of its caller's stdout
+    if (!getenv("NCCL_DEBUG_FILE")) setenv("NCCL_DEBUG_FILE", "/dev/stderr", 0);
     for (const char *name : {"libnccl.so.2", "libnccl.so"}) {
       a.lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
       if (a.lib) break;
