@@ -129,10 +129,10 @@ struct cfr_handle {
   // how the pair-line search kernel waits for memory (CFR_B200_PAIR_FETCH): 3 = one wait per iteration (lines, far lines and
   // wide-table entries in one group of cp.async copies), 2 = cp.async staging rounds per request kind, 1 = LDG + STS rounds
   int pair_fetch = 3;
-  // the same for the pair-line search kernel (CFR_B200_PAIR_SEARCH_BLOCKS): five blocks keep the memory system nearly as busy
-  // as eight do (5.9 vs 5.5 ms alone) and leave registers for the latency-bound kernels of the neighbouring batches (SDUST,
-  // scoring) on the same SMs: with the stage lanes the step is 7.5 ms per batch against 7.7 (six) and 8.9 (eight)
-  int pair_search_blocks = 5;
+  // the same for the pair-line search kernel (CFR_B200_PAIR_SEARCH_BLOCKS): six blocks keep the memory system as busy as
+  // eight do (5.4 vs 5.5 ms alone) and leave registers for the latency-bound kernels of the neighbouring batches (SDUST,
+  // scoring) on the same SMs; five make the kernel itself slower (5.9 ms) for no gain of the whole step (profiles/r02_sweeps.md)
+  int pair_search_blocks = 6;
   int occ_load = 4;    // how k_search / k_locate fetch a sector: 4 = one 256-bit load, 0 = two 128-bit loads (CFR_B200_OCC_LOAD)
   bool pos32 = false;  // 32-bit BWT positions in k_search / k_locate (collections below 2^32 rows; CFR_B200_POS64=1 disables)
   int dust_quorum = 0;  // quorum of the SDUST state machine (0 = the search quorum; CFR_B200_DUST_QUORUM)
