@@ -14,6 +14,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <strings.h>
 #include <map>
 #include <mutex>
 #include <string>
@@ -89,6 +90,7 @@ struct cfr_device_batch {
   int cap_h = 1;
   u64 seq_bytes = 0, total_bases = 0;
   u64 off_bias[2] = {0, 0};
+  u64 uni_len[2] = {0, 0}, uni_pos0[2] = {0, 0};
   u64 arena_cap = 0;
   DevBuf seq_raw, codes, mask_raw, mask, off, strand_hits, strand_nhits, fhits, work, rows, seq_ids, rec0, rec1, best, tmp,
       results, out_ids, deferred, dust_list, scalars;  // scalars: {u64 arena_used, u32 n_deferred, pad}
@@ -164,6 +166,7 @@ struct cfr_handle {
   // stages of batches i+1 / i-1 next to it on the SMs, whatever streams the caller's batches arrive on
   cudaStream_t lane[3] = {nullptr, nullptr, nullptr};
   bool lanes = true;
+  bool slim = false;  // 32-register variants of the SDUST and scoring kernels (CFR_B200_SLIM=1)
   cudaEvent_t ev_start = nullptr, ev_h2d[NSLOT] = {nullptr, nullptr, nullptr}, ev_comp[NSLOT] = {nullptr, nullptr, nullptr},
               ev_d2h[NSLOT] = {nullptr, nullptr, nullptr};
   struct PinnedScalars {
@@ -270,15 +273,18 @@ int grid_for(const cfr_handle *h, u64 tasks, int threads, int blocks_per_sm) {
 void launch_dust(cfr_handle *h, const ChunkDev &B, cudaStream_t s) {
   const u64 ntask = B.n_reads * (u64)B.mates;
   if (B.dust_list) {
-    k_dust_screen<<<grid_for(h, ntask, 128, 16), 128, 0, s>>>(B);
+    if (h->slim) k_dust_screen<16><<<grid_for(h, ntask, 128, 16), 128, 0, s>>>(B);
+    else k_dust_screen<8><<<grid_for(h, ntask, 128, 16), 128, 0, s>>>(B);
     ++h->launches;
   }
   // after the screen only the few mates that need the whole algorithm are left: 16 lanes per warp
   const int q = h->dust_quorum ? h->dust_quorum : h->P.quorum;
-  if (B.dust_list && h->dust_lanes <= 16)
-    k_dust<16><<<grid_for(h, ntask, CFR_DUST_THREADS, 10), CFR_DUST_THREADS, dust_smem_bytes<16>(), s>>>(B, q);
-  else
-    k_dust<32><<<grid_for(h, ntask, CFR_DUST_THREADS, 5), CFR_DUST_THREADS, dust_smem_bytes<32>(), s>>>(B, q);
+  if (B.dust_list && h->dust_lanes <= 16) {
+    if (h->slim) k_dust<16, 16><<<grid_for(h, ntask, CFR_DUST_THREADS, 10), CFR_DUST_THREADS, dust_smem_bytes<16>(), s>>>(B, q);
+    else k_dust<16, 10><<<grid_for(h, ntask, CFR_DUST_THREADS, 10), CFR_DUST_THREADS, dust_smem_bytes<16>(), s>>>(B, q);
+  } else {
+    k_dust<32, 10><<<grid_for(h, ntask, CFR_DUST_THREADS, 5), CFR_DUST_THREADS, dust_smem_bytes<32>(), s>>>(B, q);
+  }
   ++h->launches;
 }
 
@@ -534,6 +540,10 @@ int upload_chunk(cfr_handle *h, const cfr_read_batch *in, u64 r0, u64 r1, cfr_de
       uniform[1] = uniform[1] && l == ulen[1];
     }
   b->cap_h = std::max(1, max_hits_for_len(max_len, h->P.min_hit_len));
+  b->uni_len[0] = uniform[0] ? ulen[0] : 0;
+  b->uni_len[1] = uniform[1] ? ulen[1] : 0;
+  b->uni_pos0[0] = 0;
+  b->uni_pos0[1] = pos2;
   const u64 S = 2 * (u64)mates;
   int st;
   const u64 n_words = b->seq_bytes / 32 + 2;
@@ -612,6 +622,10 @@ void fill_chunk(cfr_handle *h, cfr_device_batch *b, ChunkDev &B) {
   B.off[1] = (const u64 *)b->off.p + (b->n_reads + 1);
   B.off_bias[0] = b->off_bias[0];
   B.off_bias[1] = b->off_bias[1];
+  for (int m = 0; m < 2; ++m) {
+    B.uni_len[m] = b->uni_len[m];
+    B.uni_pos0[m] = b->uni_pos0[m];
+  }
   B.strand_hits = (Hit *)b->strand_hits.p;
   B.strand_nhits = (int *)b->strand_nhits.p;
   B.fhits = (FinalHit *)b->fhits.p;
@@ -668,7 +682,8 @@ int run_pass(cfr_handle *h, const ChunkDev &B, int first_pass, cudaStream_t s) {
   }
   {
     StageScope sc(h, s, CFR_STAGE_SCORE);
-    k_score<<<grid_for(h, B.n_list, 128, 16), 128, 0, s>>>(h->ix, h->P, B);
+    if (h->slim) k_score<16><<<grid_for(h, B.n_list, 128, 16), 128, 0, s>>>(h->ix, h->P, B);
+    else k_score<10><<<grid_for(h, B.n_list, 128, 16), 128, 0, s>>>(h->ix, h->P, B);
   }
   h->launches += need_locate ? 3 : 2;
   CUDA_TRY(cudaGetLastError());
@@ -899,6 +914,7 @@ int cfr_open(const char *idx_prefix, const cfr_params *p, int device, cfr_handle
   if (const char *e = getenv("CFR_B200_PAIR_SEARCH_BLOCKS")) h->pair_search_blocks = std::max(1, atoi(e));
   if (const char *e = getenv("CFR_B200_PAIR_FETCH")) h->pair_fetch = std::min(3, std::max(1, atoi(e)));
   if (const char *e = getenv("CFR_B200_LANES")) h->lanes = atoi(e) != 0;
+  if (const char *e = getenv("CFR_B200_SLIM")) h->slim = atoi(e) != 0;
   if (const char *e = getenv("CFR_B200_DUST_SCREEN")) h->dust_screen = atoi(e) != 0;
   if (const char *e = getenv("CFR_B200_DUST_QUORUM")) h->dust_quorum = std::max(0, atoi(e));
   if (const char *e = getenv("CFR_B200_DUST_LANES")) h->dust_lanes = std::min(32, std::max(1, atoi(e)));
@@ -1633,6 +1649,8 @@ NcclApi &nccl_api() {
     // NCCL writes its debug lines -- with NCCL_DEBUG=VERSION, which some images set, its version banner -- to STDOUT, where a
     // caller of this library (the CLI) has its TSV: a library keeps out of its caller's stdout
     if (!getenv("NCCL_DEBUG_FILE")) setenv("NCCL_DEBUG_FILE", "/dev/stderr", 0);
+    if (const char *d = getenv("NCCL_DEBUG"))  // the version banner is a plain printf to stdout: ask for warnings instead
+      if (strcasecmp(d, "VERSION") == 0) setenv("NCCL_DEBUG", "WARN", 1);
     for (const char *name : {"libnccl.so.2", "libnccl.so"}) {
       a.lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
       if (a.lib) break;

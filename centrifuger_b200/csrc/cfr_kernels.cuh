@@ -45,7 +45,10 @@ __global__ void k_apply_dust(const __grid_constant__ ChunkDev B, unsigned char *
 
 // SDUST screen: one mate per thread, registers only.  Mates that may hold a masked interval are
 // appended to B.dust_list (one atomic per warp); k_dust then runs the full SDUST on those only.
-__global__ void __launch_bounds__(128) k_dust_screen(const __grid_constant__ ChunkDev B) {
+// MINB (here and in k_dust / k_score): resident blocks per SM the register allocation must allow.  The "slim" variants
+// (16: 32 registers) spill a few words but fit twice as often beside the search kernel of a neighbouring batch.
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) k_dust_screen(const __grid_constant__ ChunkDev B) {
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const u64 ntask = B.n_reads * (u64)B.mates;
@@ -69,8 +72,8 @@ __global__ void __launch_bounds__(128) k_dust_screen(const __grid_constant__ Chu
 //       which stall the other mates of its warp, so the mates are spread over twice as many warps;
 //       columns only for the active lanes (20 KiB per block) let twice as many blocks be resident
 enum { CFR_DUST_THREADS = 128 };
-template <int AL>
-__global__ void __launch_bounds__(CFR_DUST_THREADS) k_dust(const __grid_constant__ ChunkDev B, const int quorum) {
+template <int AL, int MINB>
+__global__ void __launch_bounds__(CFR_DUST_THREADS, MINB) k_dust(const __grid_constant__ ChunkDev B, const int quorum) {
   extern __shared__ u32 dust_sm[];
   constexpr int COLS = (CFR_DUST_THREADS / 32) * AL;  // active threads per block
   const int lane = threadIdx.x & 31;
@@ -147,8 +150,9 @@ __global__ void __launch_bounds__(128) k_locate(const __grid_constant__ DevIndex
   flush_counts(oc, B.counters + CFR_STAGE_LOCATE);
 }
 
-__global__ void __launch_bounds__(128) k_score(const __grid_constant__ DevIndex ix, const __grid_constant__ DevParams P,
-                                               const __grid_constant__ ChunkDev B) {
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) k_score(const __grid_constant__ DevIndex ix, const __grid_constant__ DevParams P,
+                                                     const __grid_constant__ ChunkDev B) {
   const unsigned full = 0xffffffffu;
   u64 err = 0;
   u32 n_done = 0, n_cls = 0;

@@ -35,6 +35,8 @@ struct ChunkDev {
   u32 *dust_bits;                // optional: just the DUST intervals (diagnostics)
   const u64 *off[2];             // per mate: n_reads + 1 offsets as given by the caller
   u64 off_bias[2];               // position in seq = off[m][i] - off_bias[m]
+  u64 uni_len[2], uni_pos0[2];   // every read of mate m has uni_len[m] bases (0 = lengths differ): read i stands at
+                                 // uni_pos0[m] + i * uni_len[m] -- the search kernel then needs no offset loads
   Hit *strand_hits;              // [n_reads * 2*mates * cap_h]
   int *strand_nhits;             // [n_reads * 2*mates]
   FinalHit *fhits;               // [n_reads * 2*mates * cap_h]
@@ -391,10 +393,16 @@ CFR_HD void search_tasks(const DevIndex &ix, const DevParams &P, const ChunkDev 
           const u64 read = cur >> sshift;
           const int w = (int)(cur & ((1ull << sshift) - 1ull));
           const int mate = w >> 1;
-          const u64 *off = mate ? B.off[1] : B.off[0];
-          const u64 o0 = off[read], o1 = off[read + 1];
-          s.base = o0 - (mate ? B.off_bias[1] : B.off_bias[0]);
-          s.len = (int)(o1 - o0);
+          const u64 ulen = mate ? B.uni_len[1] : B.uni_len[0];
+          if (ulen) {  // one read length: no loads on the way to the first search of the task
+            s.base = (mate ? B.uni_pos0[1] : B.uni_pos0[0]) + read * ulen;
+            s.len = (int)ulen;
+          } else {
+            const u64 *off = mate ? B.off[1] : B.off[0];
+            const u64 o0 = off[read], o1 = off[read + 1];
+            s.base = o0 - (mate ? B.off_bias[1] : B.off_bias[0]);
+            s.len = (int)(o1 - o0);
+          }
           s.rc = (w & 1) ? 0 : 1;
           s.widx = ~0ull;
           nh = 0;
