@@ -166,7 +166,6 @@ struct cfr_handle {
   // stages of batches i+1 / i-1 next to it on the SMs, whatever streams the caller's batches arrive on
   cudaStream_t lane[3] = {nullptr, nullptr, nullptr};
   bool lanes = true;
-  bool slim = false;  // 32-register variants of the SDUST and scoring kernels (CFR_B200_SLIM=1)
   cudaEvent_t ev_start = nullptr, ev_h2d[NSLOT] = {nullptr, nullptr, nullptr}, ev_comp[NSLOT] = {nullptr, nullptr, nullptr},
               ev_d2h[NSLOT] = {nullptr, nullptr, nullptr};
   struct PinnedScalars {
@@ -273,15 +272,13 @@ int grid_for(const cfr_handle *h, u64 tasks, int threads, int blocks_per_sm) {
 void launch_dust(cfr_handle *h, const ChunkDev &B, cudaStream_t s) {
   const u64 ntask = B.n_reads * (u64)B.mates;
   if (B.dust_list) {
-    if (h->slim) k_dust_screen<16><<<grid_for(h, ntask, 128, 16), 128, 0, s>>>(B);
-    else k_dust_screen<8><<<grid_for(h, ntask, 128, 16), 128, 0, s>>>(B);
+    k_dust_screen<8><<<grid_for(h, ntask, 128, 16), 128, 0, s>>>(B);
     ++h->launches;
   }
   // after the screen only the few mates that need the whole algorithm are left: 16 lanes per warp
   const int q = h->dust_quorum ? h->dust_quorum : h->P.quorum;
   if (B.dust_list && h->dust_lanes <= 16) {
-    if (h->slim) k_dust<16, 16><<<grid_for(h, ntask, CFR_DUST_THREADS, 10), CFR_DUST_THREADS, dust_smem_bytes<16>(), s>>>(B, q);
-    else k_dust<16, 10><<<grid_for(h, ntask, CFR_DUST_THREADS, 10), CFR_DUST_THREADS, dust_smem_bytes<16>(), s>>>(B, q);
+    k_dust<16, 10><<<grid_for(h, ntask, CFR_DUST_THREADS, 10), CFR_DUST_THREADS, dust_smem_bytes<16>(), s>>>(B, q);
   } else {
     k_dust<32, 10><<<grid_for(h, ntask, CFR_DUST_THREADS, 5), CFR_DUST_THREADS, dust_smem_bytes<32>(), s>>>(B, q);
   }
@@ -682,8 +679,7 @@ int run_pass(cfr_handle *h, const ChunkDev &B, int first_pass, cudaStream_t s) {
   }
   {
     StageScope sc(h, s, CFR_STAGE_SCORE);
-    if (h->slim) k_score<16><<<grid_for(h, B.n_list, 128, 16), 128, 0, s>>>(h->ix, h->P, B);
-    else k_score<10><<<grid_for(h, B.n_list, 128, 16), 128, 0, s>>>(h->ix, h->P, B);
+    k_score<10><<<grid_for(h, B.n_list, 128, 16), 128, 0, s>>>(h->ix, h->P, B);
   }
   h->launches += need_locate ? 3 : 2;
   CUDA_TRY(cudaGetLastError());
@@ -914,7 +910,6 @@ int cfr_open(const char *idx_prefix, const cfr_params *p, int device, cfr_handle
   if (const char *e = getenv("CFR_B200_PAIR_SEARCH_BLOCKS")) h->pair_search_blocks = std::max(1, atoi(e));
   if (const char *e = getenv("CFR_B200_PAIR_FETCH")) h->pair_fetch = std::min(3, std::max(1, atoi(e)));
   if (const char *e = getenv("CFR_B200_LANES")) h->lanes = atoi(e) != 0;
-  if (const char *e = getenv("CFR_B200_SLIM")) h->slim = atoi(e) != 0;
   if (const char *e = getenv("CFR_B200_DUST_SCREEN")) h->dust_screen = atoi(e) != 0;
   if (const char *e = getenv("CFR_B200_DUST_QUORUM")) h->dust_quorum = std::max(0, atoi(e));
   if (const char *e = getenv("CFR_B200_DUST_LANES")) h->dust_lanes = std::min(32, std::max(1, atoi(e)));

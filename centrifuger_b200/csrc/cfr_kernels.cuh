@@ -45,8 +45,9 @@ __global__ void k_apply_dust(const __grid_constant__ ChunkDev B, unsigned char *
 
 // SDUST screen: one mate per thread, registers only.  Mates that may hold a masked interval are
 // appended to B.dust_list (one atomic per warp); k_dust then runs the full SDUST on those only.
-// MINB (here and in k_dust / k_score): resident blocks per SM the register allocation must allow.  The "slim" variants
-// (16: 32 registers) spill a few words but fit twice as often beside the search kernel of a neighbouring batch.
+// MINB (here and in k_dust / k_score): resident blocks per SM the register allocation must allow.  32-register variants
+// (MINB 16) fit twice as often beside the search kernel of a neighbouring batch but spill: SDUST alone 2.0 -> 2.7 ms per
+// batch and the overlapped step 7.5 -> 8.6 ms (profiles/r02_sweeps.md) -- not used.
 template <int MINB>
 __global__ void __launch_bounds__(128, MINB) k_dust_screen(const __grid_constant__ ChunkDev B) {
   const unsigned full = 0xffffffffu;
