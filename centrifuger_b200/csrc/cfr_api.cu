@@ -906,7 +906,11 @@ int cfr_open(const char *idx_prefix, const cfr_params *p, int device, cfr_handle
   h->P.quorum = 8;
   if (const char *e = getenv("CFR_B200_TRACE")) h->trace = atoi(e) != 0;
   if (const char *e = getenv("CFR_B200_QUORUM")) h->P.quorum = std::max(1, atoi(e));
-  if (const char *e = getenv("CFR_B200_SEARCH_BLOCKS")) h->search_blocks = std::max(1, atoi(e));
+  bool search_blocks_given = false;
+  if (const char *e = getenv("CFR_B200_SEARCH_BLOCKS")) {
+    h->search_blocks = std::max(1, atoi(e));
+    search_blocks_given = true;
+  }
   if (const char *e = getenv("CFR_B200_PAIR_SEARCH_BLOCKS")) h->pair_search_blocks = std::max(1, atoi(e));
   if (const char *e = getenv("CFR_B200_PAIR_FETCH")) h->pair_fetch = std::min(3, std::max(1, atoi(e)));
   if (const char *e = getenv("CFR_B200_LANES")) h->lanes = atoi(e) != 0;
@@ -938,6 +942,9 @@ int cfr_open(const char *idx_prefix, const cfr_params *p, int device, cfr_handle
   if (h->layout == CFR_LAYOUT_OCCLINE) {
     if ((st = build_occ_lines(h))) return bail(st);
     h->occ_bytes = (h->ix.n / 64 + 1) * sizeof(OccLine);
+    // sectors beyond L2: the walker is bound by DRAM requests, six resident blocks per SM issue as many as ten do (7.3 ms
+    // per 1 M pairs either way on the 20 Gbp index) and leave room for the other stage lanes' kernels (14.3 -> 13.0 ms per batch)
+    if (!search_blocks_given && h->occ_bytes > (96ull << 20)) h->search_blocks = 6;
     // the run-block arrays have served their purpose (k_transcode read them with the literal
     // Sequence_RunBlock::Rank / Access); at 140 Gbp they are ~43 GB that the sectors replace.
     // CFR_B200_KEEP_RUNBLOCK=1 keeps them (diagnostics).

@@ -19,7 +19,7 @@ LAYOUTS = [cb.LAYOUT_RUNBLOCK, cb.LAYOUT_OCCLINE]
 # kernel variants the library picks by index size or environment: the occ sectors walked with 32-bit
 # positions (default below 2^32 rows) or 64-bit positions, one 256-bit sector load or two 128-bit
 # loads, SDUST with or without the register-only screen
-VARIANTS = {"default": {}, "pos64": {"CFR_B200_POS64": "1"}, "pos64_ld128": {"CFR_B200_POS64": "1", "CFR_B200_OCC_LOAD": "0"},
+VARIANTS = {"default": {}, "nolanes_pairs": {"CFR_B200_LANES": "0", "CFR_B200_PAIRS": "1"}, "pos64": {"CFR_B200_POS64": "1"}, "pos64_ld128": {"CFR_B200_POS64": "1", "CFR_B200_OCC_LOAD": "0"},
             "ld128": {"CFR_B200_OCC_LOAD": "0"}, "noscreen": {"CFR_B200_DUST_SCREEN": "0"},
             "wide12": {"CFR_B200_WIDE_LOOKUP": "12"}, "wide11_pos64": {"CFR_B200_WIDE_LOOKUP": "11", "CFR_B200_POS64": "1"},
             "literal": {"CFR_B200_DENSE_LOCATE": "-1"}, "dense1_pos64": {"CFR_B200_DENSE_LOCATE": "1", "CFR_B200_POS64": "1"},
@@ -38,7 +38,7 @@ VARIANTS = {"default": {}, "pos64": {"CFR_B200_POS64": "1"}, "pos64_ld128": {"CF
 @pytest.fixture(params=sorted(VARIANTS))
 def variant_env(request, monkeypatch):
     for k in ("CFR_B200_POS64", "CFR_B200_OCC_LOAD", "CFR_B200_DUST_SCREEN", "CFR_B200_WIDE_LOOKUP", "CFR_B200_DENSE_LOCATE",
-              "CFR_B200_PAIRS", "CFR_B200_PAIR_SEARCH_BLOCKS", "CFR_B200_PAIR_FETCH", "CFR_B200_DENSE16"):
+              "CFR_B200_PAIRS", "CFR_B200_PAIR_SEARCH_BLOCKS", "CFR_B200_PAIR_FETCH", "CFR_B200_DENSE16", "CFR_B200_LANES"):
         monkeypatch.delenv(k, raising=False)
     for k, v in VARIANTS[request.param].items():
         monkeypatch.setenv(k, v)  # read by cfr_open

@@ -1,8 +1,5 @@
 #!/bin/bash
+# one-process sweep of CFR_B200_* settings (space-separated in $SWEEP_SETTINGS, switches of one setting joined by commas)
 mkdir -p gpurun_out
-timeout 1500 python tools/sweep.py c4 3 CFR_B200_PAIR_SEARCH_BLOCKS=5 CFR_B200_PAIR_SEARCH_BLOCKS=5,CFR_B200_DUST_LANES=32 CFR_B200_PAIR_SEARCH_BLOCKS=5,CFR_B200_DUST_QUORUM=4 CFR_B200_PAIR_SEARCH_BLOCKS=5,CFR_B200_DUST_QUORUM=16 CFR_B200_PAIR_SEARCH_BLOCKS=5,CFR_B200_QUORUM=12 > gpurun_out/sweep2_c4.jsonl 2> gpurun_out/sweep2_c4.err
-tail -2 gpurun_out/sweep2_c4.err; cat gpurun_out/sweep2_c4.jsonl
-SWEEP_STREAMS=4 timeout 900 python tools/sweep.py c4 4 CFR_B200_PAIR_SEARCH_BLOCKS=5 > gpurun_out/sweep2_c4_s4.jsonl 2>> gpurun_out/sweep2_c4.err
-cat gpurun_out/sweep2_c4_s4.jsonl
-SWEEP_STREAMS=2 timeout 900 python tools/sweep.py c4 4 CFR_B200_PAIR_SEARCH_BLOCKS=5 > gpurun_out/sweep2_c4_s2.jsonl 2>> gpurun_out/sweep2_c4.err
-cat gpurun_out/sweep2_c4_s2.jsonl
+timeout 1500 python tools/sweep.py ${SWEEP_WORKLOAD:-c4} ${SWEEP_BATCHES:-3} $SWEEP_SETTINGS > gpurun_out/sweep_last.jsonl 2> gpurun_out/sweep_last.err
+tail -2 gpurun_out/sweep_last.err; cat gpurun_out/sweep_last.jsonl
