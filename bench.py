@@ -58,8 +58,9 @@ WORKLOADS = {
     "c4": dict(dataset="c4", reads=10_000_000, batch=1_000_000, rlen=150, paired=True, k=5,
                desc="synthetic 20 Gbp / 5000-sequence index (built on the GPU), 10M x 2x150 bp read pairs per GPU, -k 5 "
                     "(BASELINE configs[3])"),
-    "c5": dict(dataset="c5", reads=10_000_000, batch=1_000_000, rlen=150, paired=True, k=5,
-               desc="synthetic 140 Gbp / 35000-sequence index (built on the GPU), 10M x 2x150 bp read pairs per GPU, -k 5 "
+    # five resident batches: the index takes 140 of the 180 GB (70 GB of sectors, 17 GB lookup table, 17 GB sampled SA, 35 GB dense table)
+    "c5": dict(dataset="c5", reads=5_000_000, batch=1_000_000, rlen=150, paired=True, k=5,
+               desc="synthetic 140 Gbp / 35000-sequence index (built on the GPU), 5M x 2x150 bp read pairs per GPU and step, -k 5 "
                     "(BASELINE configs[4])"),
     "s2g": dict(dataset="s2g", reads=1_000_000, batch=1_000_000, rlen=150, paired=True, k=5,
                 desc="synthetic 2 Gbp / 500-sequence index (built on the GPU), 1M x 2x150 bp read pairs, -k 5"),

@@ -995,14 +995,14 @@ int cfr_open(const char *idx_prefix, const cfr_params *p, int device, cfr_handle
     if (want && (st = build_pair_lines(h))) return bail(st);
   }
   {
-    // dense locate table: the densest spacing whose table (4 bytes per entry) stays below a quarter
-    // of the free HBM and 24 GB -- every row for collections up to 6 Gbp; CFR_B200_DENSE_LOCATE=shift
+    // dense locate table: the densest spacing whose table (2 or 4 bytes per entry) stays below half of the
+    // free HBM and 48 GB -- every row up to 20 Gbp, every 8th row at 140 Gbp; CFR_B200_DENSE_LOCATE=shift
     // forces a spacing (-1 = off).  Measured on configs[1]: every 8th / 4th / 2nd row -> 0.39 / 0.33 /
     // 0.24 ms per 1 M reads (0.49 with the stored samples only, every 16th row).
     int shift = 0;
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
-    const u64 budget = std::min<u64>((u64)free_b * 2 / 5, 48ull << 30);
+    const u64 budget = std::min<u64>((u64)free_b / 2, 48ull << 30);
     // 16-bit entries when every id a locate can return fits: the sampled SA's ids (sa_bits wide), the boundary
     // table's, and the id of row firstISA (CFR_B200_DENSE16=0 keeps 32-bit entries)
     bool e16 = h->file.sa_bits <= 16 && h->file.adjusted_sa0 < 65536;
