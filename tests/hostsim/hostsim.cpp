@@ -276,6 +276,69 @@ u64 hostsim_pair_check(void *hh, u64 n_ranges, u64 seed) {
   return bad;
 }
 
+// ---- primitives with positions beyond 2^32 (no index of that size exists on the CPU side of the tests; the GPU suite
+// loads real ones).  Each function answers ONE query so that the Python test states the expected value itself.
+// occ sector: pack the counts of A, C, G before sector `sec` and read the count of symbol c back
+uint64_t hostsim_occ_roundtrip(uint64_t a, uint64_t c, uint64_t g, uint64_t sec, int sym) {
+  const OccLine o = occ_pack(0x0123456789abcdefull, 0xfedcba9876543210ull, a, c, g);
+  return occ_base(o.w2, o.w3, sym, sec);
+}
+// the 32-bit walker's view of the same sector (valid below 2^32 rows: the high bytes are zero)
+uint32_t hostsim_occ_roundtrip32(uint64_t a, uint64_t c, uint64_t g, uint64_t sec, int sym) {
+  const OccLine o = occ_pack(0, 0, a, c, g);
+  return occ_base32(o.w2, o.w3, sym, (u32)sec);
+}
+// FixedSizeElemArray::Read at element i of a bit-packed array of `bits`-wide elements (words = the array)
+uint64_t hostsim_sa_read(const uint64_t *words, int bits, uint64_t i) {
+  DevIndex ix;
+  memset(&ix, 0, sizeof(ix));
+  ix.sampled_sa = reinterpret_cast<const u64 *>(words);
+  ix.sa_bits = bits;
+  return sa_read(ix, i);
+}
+// the row plan of one hit (Classifier.hpp:620-666): out = {step, fwd, total, row(t0), row(t1)}
+void hostsim_plan_rows(uint64_t sp, uint64_t ep, int k, int hitk, uint64_t t0, uint64_t t1, uint64_t *out) {
+  DevParams P;
+  memset(&P, 0, sizeof(P));
+  P.max_result = k;
+  P.hitk_factor = hitk;
+  const RowPlan rp = plan_rows(sp, ep, P);
+  out[0] = rp.step;
+  out[1] = rp.fwd;
+  out[2] = rp.total;
+  out[3] = plan_row_at(sp, ep, rp, t0);
+  out[4] = plan_row_at(sp, ep, rp, t1);
+}
+// one occ-sector extend step (FMIndex::BackwardExtend) on a two-sector toy BWT placed at sector `sec0` of a virtual
+// index of n rows: the sectors' counts carry the rows before them, so every product of the step has high bits
+void hostsim_extend_high(uint64_t sec0, uint64_t n, const uint64_t *C5, uint64_t first_isa, int last_code, uint64_t lo0,
+                         uint64_t hi0, uint64_t lo1, uint64_t hi1, const uint64_t *cnt0, int c, uint64_t sp, uint64_t ep,
+                         uint64_t *out) {
+  // cnt0 = counts of A, C, G before sector sec0; the counts before sec0 + 1 follow from sector sec0's symbols
+  std::vector<OccLine> lines(3);
+  u64 cnt1[3];
+  for (int s = 0; s < 3; ++s) cnt1[s] = cnt0[s] + (u64)popc64(occ_match(lo0, hi0, s));
+  lines[0] = occ_pack(lo0, hi0, cnt0[0], cnt0[1], cnt0[2]);
+  lines[1] = occ_pack(lo1, hi1, cnt1[0], cnt1[1], cnt1[2]);
+  lines[2] = occ_pack(0, 0, 0, 0, 0);
+  DevIndex ix;
+  memset(&ix, 0, sizeof(ix));
+  ix.n = n;
+  for (int i = 0; i < 5; ++i) ix.C[i] = C5[i];
+  ix.first_isa = first_isa;
+  ix.last_code = last_code;
+  ix.occ = lines.data() - sec0;  // sector sec0 of the virtual index is lines[0]
+  OpCount oc{};
+  u64 nsp = 0, nep = 0;
+  BwtOccLine::extend(ix, c, sp, ep, nsp, nep, oc);
+  out[0] = nsp;
+  out[1] = nep;
+  BwtOccLineT<4>::extend(ix, c, sp, ep, nsp, nep, oc);
+  out[2] = nsp;
+  out[3] = nep;
+  out[4] = BwtOccLine::lf(ix, sp, oc);
+}
+
 int hostsim_min_hit_len(void *hh) { return ((HostIndex *)hh)->P.min_hit_len; }
 
 uint64_t hostsim_bwt_rank(void *hh, int c, uint64_t i, int inclusive) {

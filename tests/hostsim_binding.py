@@ -98,6 +98,17 @@ def lib():
         L.hostsim_bwt_access.argtypes = [C.c_void_p, C.c_uint64]
         L.hostsim_locate.restype = C.c_uint64
         L.hostsim_locate.argtypes = [C.c_void_p, C.c_uint64]
+        L.hostsim_occ_roundtrip.restype = C.c_uint64
+        L.hostsim_occ_roundtrip.argtypes = [C.c_uint64] * 4 + [C.c_int]
+        L.hostsim_occ_roundtrip32.restype = C.c_uint32
+        L.hostsim_occ_roundtrip32.argtypes = [C.c_uint64] * 4 + [C.c_int]
+        L.hostsim_sa_read.restype = C.c_uint64
+        L.hostsim_sa_read.argtypes = [C.c_void_p, C.c_int, C.c_uint64]
+        L.hostsim_plan_rows.restype = None
+        L.hostsim_plan_rows.argtypes = [C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_void_p]
+        L.hostsim_extend_high.restype = None
+        L.hostsim_extend_high.argtypes = [C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint64, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64,
+                                          C.c_uint64, C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.c_void_p]
         L.hostsim_pair_check.restype = C.c_uint64
         L.hostsim_pair_check.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64]
         L.hostsim_reduce_taxids.restype = C.c_int

@@ -493,3 +493,112 @@ def test_device_pipeline_against_reference_header(tiny_dir, layout, k, hitk, sec
         assert classified > 300
         hs.close()
         names.close()
+
+
+def test_positions_beyond_2_pow_32():
+    """the arithmetic that only a collection of more than 2^32 rows exercises, stated here with Python integers: 40-bit
+    sector counters (occ_pack / occ_base: the three high bytes share a word), FixedSizeElemArray::Read past bit 2^32
+    (FixedSizeElemArray.hpp:102), the row plan of a wide hit (Classifier.hpp:620-666), and one FMIndex::BackwardExtend /
+    LF step (FMIndex.hpp:352-386) on sectors whose counts and C[] offsets have high bits.  (Real indexes of 2 * 10^10 and
+    1.4 * 10^11 rows are compared with the reference binary on the GPU box: tests/test_gpu_reference_at_scale.py,
+    tests/cli_bench.py c5.)"""
+    import ctypes as C
+
+    import numpy as np
+
+    from hostsim_binding import lib
+    L = lib()
+    rng = random.Random(77)
+    M40 = (1 << 40) - 1
+    for _ in range(20000):
+        a, c, g = (rng.randrange(0, 1 << rng.choice([8, 31, 32, 33, 39, 40])) for _ in range(3))
+        a, c, g = a & M40, c & M40, g & M40
+        sec = (a + c + g + 63) // 64 + rng.randrange(0, 1 << 20)
+        want = [a, c, g, sec * 64 - (a + c + g)]
+        for sym in range(4):
+            assert L.hostsim_occ_roundtrip(a, c, g, sec, sym) == want[sym], (a, c, g, sec, sym)
+    for _ in range(5000):  # the 32-bit walker below 2^32 rows
+        a, c, g = (rng.randrange(0, 1 << 30) for _ in range(3))
+        sec = (a + c + g + 63) // 64 + rng.randrange(0, 1 << 10)
+        want = [a, c, g, sec * 64 - (a + c + g)]
+        for sym in range(4):
+            assert L.hostsim_occ_roundtrip32(a, c, g, sec, sym) == want[sym] & 0xffffffff
+
+    # sampled SA: 17-bit elements, element indexes around 2^32 / 17 .. 2^33 / 17 bits (the array is lazily committed)
+    bits = 17
+    n_elem = (1 << 33) // bits + 64
+    words = np.zeros((n_elem * bits + 63) // 64 + 2, dtype=np.uint64)
+    probes = [rng.randrange((1 << 32) // bits - 40, (1 << 32) // bits + 40) for _ in range(200)] + \
+             [rng.randrange(0, n_elem) for _ in range(300)]
+    vals = {}
+    for i in sorted(set(probes)):
+        v = rng.randrange(1, 1 << bits)
+        vals[i] = v
+        s = i * bits
+        w, r = s >> 6, s & 63
+        words[w] |= np.uint64((v << r) & 0xffffffffffffffff)
+        if r + bits > 64:
+            words[w + 1] |= np.uint64(v >> (64 - r))
+    for i, v in vals.items():
+        assert L.hostsim_sa_read(words.ctypes.data, bits, i) == v, i
+
+    # row plans of hits with ranges up to 2^37 rows, at row numbers up to 2^38
+    out = (C.c_uint64 * 5)()
+    for _ in range(3000):
+        k, hitk = rng.choice([1, 5, 40]), rng.choice([0, 2, 40])
+        sp = rng.randrange(0, 1 << 38)
+        rng_rows = rng.choice([1, 7, k * max(hitk, 1), k * max(hitk, 1) + 1, rng.randrange(1, 1 << 37)])
+        ep = sp + rng_rows - 1
+        mx = k * hitk
+        if rng_rows <= mx or hitk <= 0 or k <= 0:
+            step, fwd, total = 0, rng_rows, rng_rows
+        else:
+            step = rng_rows // mx + (1 if rng_rows % mx else 0)
+            fwd = (rng_rows - 1) // step + 1
+            down = 1 if fwd >= mx else mx - fwd
+            total = fwd + min(down, (rng_rows - 1) // step + 1)
+        t0, t1 = rng.randrange(0, total), total - 1
+
+        def row(t):
+            if step == 0:
+                return sp + t
+            return sp + t * step if t < fwd else ep - (t - fwd) * step
+        L.hostsim_plan_rows(sp, ep, k, hitk, t0, t1, out)
+        assert list(out) == [step, fwd, total, row(t0), row(t1)], (sp, ep, k, hitk)
+
+    # one extend / LF step on two sectors at sector 2^28 + ... of a virtual index of 2^36 rows
+    n = 1 << 36
+    C5 = (C.c_uint64 * 5)(0, n // 4 + 12345, n // 2 + 777, 3 * n // 4 + 99, n)
+    res = (C.c_uint64 * 5)()
+    for _ in range(3000):
+        sec0 = (1 << 28) + rng.randrange(0, 1 << 27)
+        lo = [rng.getrandbits(64) for _ in range(2)]
+        hi = [rng.getrandbits(64) for _ in range(2)]
+        before = sec0 * 64
+        cnt0 = [rng.randrange(0, before // 4) for _ in range(3)]
+        sym = [[((lo[s] >> i) & 1) | (((hi[s] >> i) & 1) << 1) for i in range(64)] for s in range(2)]
+        flat = sym[0] + sym[1]
+
+        def rank(c, p, inclusive):  # Sequence::Rank over the virtual BWT: rows before sec0 counted by cnt0
+            upto = p - before + (1 if inclusive else 0)
+            base = cnt0[c] if c < 3 else before - sum(cnt0)
+            return base + sum(1 for x in flat[:upto] if x == c)
+        last_code = rng.randrange(4)
+        first_isa = before + rng.randrange(0, 128) if rng.random() < 0.7 else rng.randrange(0, n)
+
+        def fm_rank(c, p, inclusive):
+            r = rank(c, p, inclusive)
+            if c == last_code and (p < first_isa or (not inclusive and p == first_isa)):
+                r += 1
+            return r
+        c = rng.randrange(4)
+        sp = before + rng.randrange(0, 127)
+        ep = sp if rng.random() < 0.3 else before + rng.randrange(sp - before, 127)
+        nsp = C5[c] + fm_rank(c, sp, 0)
+        nep = (C5[c] + fm_rank(c, ep, 1) - 1) if sp != ep else nsp + (0 if flat[ep - before] == c else -1)
+        lf = C5[flat[sp - before]] + fm_rank(flat[sp - before], sp, 1) - 1
+        cnt = (C.c_uint64 * 3)(*cnt0)
+        L.hostsim_extend_high(sec0, n, C5, first_isa, last_code, lo[0], hi[0], lo[1], hi[1], cnt, c, sp, ep, res)
+        m = (1 << 64) - 1
+        assert [res[0], res[1]] == [nsp & m, nep & m] and [res[2], res[3]] == [nsp & m, nep & m], (sec0, c, sp, ep)
+        assert res[4] == lf & m
