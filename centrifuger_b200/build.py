@@ -72,7 +72,7 @@ def build(force=False, verbose=False):
         subprocess.check_call(cmd)
     main_cpp = os.path.join(CSRC, "cfr_main.cpp")
     if os.path.exists(main_cpp) and (force or _stale(CLI, deps + [LIB])):
-        cmd = ["g++", "-std=c++17", "-O2", "-Wall", "-o", CLI, main_cpp, "-L" + HERE, "-lcfrb200",
+        cmd = ["g++", "-std=c++23", "-O2", "-Wall", "-o", CLI, main_cpp, "-L" + HERE, "-lcfrb200",  # (string::resize_and_overwrite)
                "-Wl,-rpath,$ORIGIN", "-lz", "-lpthread"]  # host-only C++: no CUDA code in the CLI
         if verbose:
             print(" ".join(cmd))

@@ -499,6 +499,8 @@ struct StageScope {
 // -------------------------------------------------------------------------------------
 // batch upload: copies reads [r0, r1) of `in` into device batch `b` and sizes the work areas
 // -------------------------------------------------------------------------------------
+void fill_chunk(cfr_handle *h, cfr_device_batch *b, ChunkDev &B);
+
 // `pk` != nullptr: the reads arrive packed (cfr_packed_batch; `in` then carries only its offsets, r0 = 0)
 int upload_chunk(cfr_handle *h, const cfr_read_batch *in, u64 r0, u64 r1, cfr_device_batch *b, cudaStream_t s,
                  const cfr_packed_batch *pk = nullptr) {
@@ -599,6 +601,14 @@ int upload_chunk(cfr_handle *h, const cfr_read_batch *in, u64 r0, u64 r1, cfr_de
       CUDA_TRY(cudaMemcpyAsync(dst, src, (n + 1) * 8, cudaMemcpyHostToDevice, s));
       h->h2d_bytes += (n + 1) * 8;
     }
+  }
+  if (!pk && n) {
+    // layout is part of the upload: bytes -> 2-bit codes + N bits right behind the copy, on the copy's stream; a batch
+    // that stays resident is encoded once however often it is classified
+    ChunkDev B;
+    fill_chunk(h, b, B);
+    k_encode<<<grid_for(h, B.n_words, 256, 8), 256, 0, s>>>(B, b->seq_bytes);
+    ++h->launches;
   }
   CUDA_TRY(cudaGetLastError());
   return CFR_OK;
@@ -706,12 +716,10 @@ int run_first(cfr_handle *h, cfr_device_batch *b, cudaStream_t s) {
     CUDA_TRY(cudaStreamWaitEvent(s_pre, b->ev_lane[0], 0));
   }
   CUDA_TRY(cudaMemsetAsync(b->scalars.p, 0, 64, s_pre));
-  if (b->packed) {  // the producer encoded the bases: the masks the searches see start as the uploaded ones
-    if (B.mask != B.mask_raw) CUDA_TRY(cudaMemcpyAsync(B.mask, B.mask_raw, B.n_words * 4, cudaMemcpyDeviceToDevice, s_pre));
-  } else {
+  {  // the bases were encoded at upload (or by the producer): the masks the searches see start as the uploaded ones
     StageScope sc(h, s_pre, CFR_STAGE_OTHER);
-    k_encode<<<grid_for(h, B.n_words, 256, 8), 256, 0, s_pre>>>(B, b->seq_bytes);
-    ++h->launches;
+    if (B.mask != B.mask_raw) CUDA_TRY(cudaMemcpyAsync(B.mask, B.mask_raw, B.n_words * 4, cudaMemcpyDeviceToDevice, s_pre));
+    if (B.dust_bits) CUDA_TRY(cudaMemsetAsync(B.dust_bits, 0, B.n_words * 4, s_pre));
   }
   if (h->params.dust) {
     StageScope sc(h, s_pre, CFR_STAGE_DUST);

@@ -77,41 +77,85 @@ class BulkReader {
         ++got;
         continue;
       }
-      Sub &sb = subs_[sub_at_];
-      // as many records of this sub-block as wanted and as the byte limit lets through (at least one)
-      size_t n = std::min(want - got, sb.n - sb.taken);
-      const uint64_t s0 = sb.off[sb.taken];
-      const size_t room = max_bases - out.seq->size();
-      if (sb.off[sb.taken + n] - s0 > room) {
-        const auto it = std::upper_bound(sb.off.begin() + (long)sb.taken, sb.off.begin() + (long)(sb.taken + n) + 1, s0 + room);
-        n = std::max<size_t>(1, (size_t)(it - (sb.off.begin() + (long)sb.taken)) - 1);
+      // Fast mode: plan which record ranges of the parsed sub-blocks go into the sink (as many as wanted and as the byte limit
+      // lets through, at least one record), size the sink's arrays once without touching the new bytes, and let the
+      // threads copy the ranges side by side -- a serial memcpy of the batch costs more than parsing it did.
+      struct Seg {
+        Sub *sb;
+        size_t from, n, seq_dst, id_dst, rec_dst, qual_dst;
+      };
+      std::vector<Seg> segs;
+      size_t seq_at = out.seq->size(), id_at = out.ids ? out.ids->size() : 0, rec_at = out.off->size();
+      size_t qual_at = out.qual ? out.qual->size() : 0;  // (FASTA records served by the serial reader have no qualities)
+      const size_t qrec0 = out.qoff ? out.qoff->size() : 0, rec0 = rec_at;
+      size_t planned = 0;
+      for (size_t si = sub_at_; si < subs_.size() && got + planned < want && seq_at < max_bases; ++si) {
+        Sub &sb = subs_[si];
+        if (sb.taken >= sb.n) continue;
+        size_t n = std::min(want - got - planned, sb.n - sb.taken);
+        const uint64_t s0 = sb.off[sb.taken];
+        const size_t room = max_bases - seq_at;
+        if (sb.off[sb.taken + n] - s0 > room) {
+          const auto it = std::upper_bound(sb.off.begin() + (long)sb.taken, sb.off.begin() + (long)(sb.taken + n) + 1, s0 + room);
+          n = std::max<size_t>(1, (size_t)(it - (sb.off.begin() + (long)sb.taken)) - 1);
+        }
+        segs.push_back(Seg{&sb, sb.taken, n, seq_at, id_at, rec_at, qual_at});
+        seq_at += (size_t)(sb.off[sb.taken + n] - s0);
+        qual_at += (size_t)(sb.off[sb.taken + n] - s0);
+        id_at += sb.id_off[sb.taken + n] - sb.id_off[sb.taken];
+        rec_at += n;
+        planned += n;
+        if (max_len) *max_len = std::max(*max_len, sb.max_len);
       }
-      const uint64_t s1 = sb.off[sb.taken + n];
-      const uint64_t base = out.seq->size() - s0;
-      out.seq->append(sb.seq, (size_t)s0, (size_t)(s1 - s0));
-      const size_t o0 = out.off->size();
-      out.off->resize(o0 + n);
-      for (size_t i = 0; i < n; ++i) (*out.off)[o0 + i] = sb.off[sb.taken + 1 + i] + base;
-      if (out.ids) {
-        const uint32_t i0 = sb.id_off[sb.taken], i1 = sb.id_off[sb.taken + n];
-        const uint32_t ibase = (uint32_t)out.ids->size() - i0;
-        out.ids->append(sb.ids, i0, i1 - i0);
-        const size_t q0 = out.id_off->size();
-        out.id_off->resize(q0 + n);
-        for (size_t i = 0; i < n; ++i) (*out.id_off)[q0 + i] = sb.id_off[sb.taken + 1 + i] + ibase;
+      grow_uninitialized(*out.seq, seq_at);
+      if (out.ids) grow_uninitialized(*out.ids, id_at);
+      if (out.qual) grow_uninitialized(*out.qual, qual_at);
+      out.off->resize(rec_at);
+      if (out.ids) out.id_off->resize(rec_at);
+      if (out.qoff) out.qoff->resize(qrec0 + (rec_at - rec0));
+      auto copy = [&](const Seg &g) {
+        const Sub &sb = *g.sb;
+        const uint64_t s0 = sb.off[g.from], s1 = sb.off[g.from + g.n];
+        memcpy(&(*out.seq)[g.seq_dst], sb.seq.data() + s0, (size_t)(s1 - s0));
+        const uint64_t base = g.seq_dst - s0;
+        for (size_t i = 0; i < g.n; ++i) (*out.off)[g.rec_dst + i] = sb.off[g.from + 1 + i] + base;
+        if (out.ids) {
+          const uint32_t i0 = sb.id_off[g.from], i1 = sb.id_off[g.from + g.n];
+          memcpy(&(*out.ids)[g.id_dst], sb.ids.data() + i0, i1 - i0);
+          const uint32_t ibase = (uint32_t)g.id_dst - i0;
+          for (size_t i = 0; i < g.n; ++i) (*out.id_off)[g.rec_dst + i] = sb.id_off[g.from + 1 + i] + ibase;
+        }
+        if (out.qual) {  // a quality string is as long as its read: the same offsets
+          memcpy(&(*out.qual)[g.qual_dst], sb.qual.data() + s0, (size_t)(s1 - s0));
+          const uint64_t qbase = g.qual_dst - s0;
+          for (size_t i = 0; i < g.n; ++i) (*out.qoff)[qrec0 + (g.rec_dst - rec0) + i] = sb.off[g.from + 1 + i] + qbase;
+        }
+      };
+      if (segs.size() > 1 && threads_ > 1 && seq_at - segs[0].seq_dst > (1u << 20)) {
+        std::vector<std::thread> pool;
+        const size_t T = std::min<size_t>(threads_, segs.size());
+        for (size_t t = 1; t < T; ++t)
+          pool.emplace_back([&, t] {
+            for (size_t k = t; k < segs.size(); k += T) copy(segs[k]);
+          });
+        for (size_t k = 0; k < segs.size(); k += T) copy(segs[k]);
+        for (auto &th : pool) th.join();
+      } else {
+        for (const Seg &g : segs) copy(g);
       }
-      if (out.qual) {  // a quality string is as long as its read: the same offsets
-        const uint64_t qbase = out.qual->size() - s0;
-        out.qual->append(sb.qual, (size_t)s0, (size_t)(s1 - s0));
-        const size_t q0 = out.qoff->size();
-        out.qoff->resize(q0 + n);
-        for (size_t i = 0; i < n; ++i) (*out.qoff)[q0 + i] = sb.off[sb.taken + 1 + i] + qbase;
-      }
-      if (max_len) *max_len = std::max(*max_len, sb.max_len);
-      sb.taken += n;
-      got += n;
+      for (const Seg &g : segs) g.sb->taken += g.n;
+      got += planned;
     }
     return got;
+  }
+
+  // std::string::resize writes zeros over the new bytes -- a pass over a 150 MB batch that the copy repeats at once
+  static void grow_uninitialized(std::string &str, size_t n) {
+#if defined(__cpp_lib_string_resize_and_overwrite)
+    str.resize_and_overwrite(n, [n](char *, size_t) { return n; });
+#else
+    str.resize(n);
+#endif
   }
 
   // true when no record is left in any file
@@ -137,6 +181,8 @@ class BulkReader {
     }
   }
   bool used_fast_path() const { return fast_blocks_ > 0; }
+  // records are being served from parsed sub-blocks (reads of at most 1000 bases): a caller may ask for many at once
+  bool in_fast_mode() const { return !serial_ && !parked_ && map_ != nullptr; }
   double parse_seconds() const { return parse_seconds_; }  // wall time inside the parallel parse
 
  private:

@@ -606,7 +606,9 @@ int main(int argc, char *argv[]) {
         const BulkSink s1{&bt->ids, &bt->id_off, &bt->seq1, &bt->off1, keepReads ? &bt->qual1 : nullptr, keepReads ? &bt->qoff1 : nullptr};
         while ((long)bt->n < batchReads && bt->seq1.size() < maxBasesB &&
                (bt->n == 0 || (bt->n + 1) * (maxLenB / 24 + 1) <= slotBudgetB)) {
-          size_t want = std::min<size_t>((size_t)batchReads - bt->n, 65536);
+          // slices of 64 k records let the slot budget see a long read soon; the block-parallel reader serves short reads only
+          // and copies large slices with all its threads
+          size_t want = std::min<size_t>((size_t)batchReads - bt->n, bulk1.in_fast_mode() ? (size_t)batchReads : 65536);
           if (maxLenB > 0) want = std::max<size_t>(1, std::min(want, slotBudgetB / (maxLenB / 24 + 1) > bt->n ? slotBudgetB / (maxLenB / 24 + 1) - bt->n : 1));
           else want = std::min<size_t>(want, 4096);  // the first slice is short: it tells how long the reads are
           const bool firstSlice = bt->n == 0;
