@@ -95,9 +95,11 @@ class BulkReader {
         size_t n = std::min(want - got - planned, sb.n - sb.taken);
         const uint64_t s0 = sb.off[sb.taken];
         const size_t room = max_bases - seq_at;
+        bool cut = false;  // the byte limit ends the plan inside this sub-block: nothing behind it may be taken
         if (sb.off[sb.taken + n] - s0 > room) {
           const auto it = std::upper_bound(sb.off.begin() + (long)sb.taken, sb.off.begin() + (long)(sb.taken + n) + 1, s0 + room);
           n = std::max<size_t>(1, (size_t)(it - (sb.off.begin() + (long)sb.taken)) - 1);
+          cut = true;
         }
         segs.push_back(Seg{&sb, sb.taken, n, seq_at, id_at, rec_at, qual_at});
         seq_at += (size_t)(sb.off[sb.taken + n] - s0);
@@ -106,6 +108,7 @@ class BulkReader {
         rec_at += n;
         planned += n;
         if (max_len) *max_len = std::max(*max_len, sb.max_len);
+        if (cut) break;
       }
       grow_uninitialized(*out.seq, seq_at);
       if (out.ids) grow_uninitialized(*out.ids, id_at);

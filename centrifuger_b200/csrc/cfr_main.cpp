@@ -600,7 +600,7 @@ int main(int argc, char *argv[]) {
       bt->clear();
       if (bulkIngest) {
         // the same batch limits as the record-by-record loop below, applied per slice of records
-        const size_t maxBasesB = 256u << 20;
+        static const size_t maxBasesB = getenv("CFR_B200_MAX_BATCH_BASES") ? (size_t)std::max(1ll, atoll(getenv("CFR_B200_MAX_BATCH_BASES"))) : (256u << 20);  // (tests shrink it)
         static const size_t slotBudgetB = getenv("CFR_B200_SLOT_BUDGET") ? (size_t)atoll(getenv("CFR_B200_SLOT_BUDGET")) : (64u << 20);
         size_t maxLenB = 0;
         const BulkSink s1{&bt->ids, &bt->id_off, &bt->seq1, &bt->off1, keepReads ? &bt->qual1 : nullptr, keepReads ? &bt->qoff1 : nullptr};
@@ -656,7 +656,7 @@ int main(int argc, char *argv[]) {
       }
       // a batch ends after batchReads reads or 2^28 bases per mate, whichever comes first (long reads: the
       // device work areas grow with the bases and with the longest read of a batch)
-      const size_t maxBases = 256u << 20;
+      static const size_t maxBases = getenv("CFR_B200_MAX_BATCH_BASES") ? (size_t)std::max(1ll, atoll(getenv("CFR_B200_MAX_BATCH_BASES"))) : (256u << 20);
       // the device hit tables hold (longest read / (minHitLen + 1)) slots for every read of a batch, so one
       // very long read among short ones must not share a batch with a million of them: a batch also ends
       // when reads x (longest / 24 + 1) would pass 2^26 slots (CFR_B200_SLOT_BUDGET overrides, for tests)

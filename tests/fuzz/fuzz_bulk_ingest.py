@@ -92,10 +92,13 @@ def main():
             args += ["--batch", str(rng.choice([7, 64, 1000]))]
             modes = [["--dry-run-pipeline"], ["--dry-run-output", "--un", os.path.join(d, "un")]]
             for mode in modes:
-                serial = run(mode + args, {"CFR_B200_BULK_INGEST": "0"})
+                # a batch also ends at a byte budget (256 MB of bases per mate; here a few hundred to a few thousand bytes)
+                cap = {"CFR_B200_MAX_BATCH_BASES": str(rng.choice([150, 700, 4000]))} if rng.random() < 0.4 else {}
+                serial = run(mode + args, dict(cap, CFR_B200_BULK_INGEST="0"))
                 un_serial = {f: hashlib.md5(open(os.path.join(d, f), "rb").read()).hexdigest() for f in os.listdir(d) if f.startswith("un")}
                 env = {"CFR_B200_BULK_INGEST": "1", "CFR_B200_INGEST_BLOCK": str(rng.choice([16, 100, 333, 1000, 5000, 1 << 20])),
                        "CFR_B200_INGEST_THREADS": str(rng.randrange(1, 9)), "CFR_B200_STAGE_REPORT": "1"}
+                env.update(cap)
                 bulk = run(mode + args, env)
                 un_bulk = {f: hashlib.md5(open(os.path.join(d, f), "rb").read()).hexdigest() for f in os.listdir(d) if f.startswith("un")}
                 if serial[:2] != bulk[:2] or un_serial != un_bulk:
