@@ -920,7 +920,7 @@ int cfr_open(const char *idx_prefix, const cfr_params *p, int device, cfr_handle
     search_blocks_given = true;
   }
   if (const char *e = getenv("CFR_B200_PAIR_SEARCH_BLOCKS")) h->pair_search_blocks = std::max(1, atoi(e));
-  if (const char *e = getenv("CFR_B200_PAIR_FETCH")) h->pair_fetch = std::min(3, std::max(1, atoi(e)));
+  if (const char *e = getenv("CFR_B200_PAIR_FETCH")) h->pair_fetch = std::min(4, std::max(1, atoi(e)));
   if (const char *e = getenv("CFR_B200_LANES")) h->lanes = atoi(e) != 0;
   if (const char *e = getenv("CFR_B200_DUST_SCREEN")) h->dust_screen = atoi(e) != 0;
   if (const char *e = getenv("CFR_B200_DUST_QUORUM")) h->dust_quorum = std::max(0, atoi(e));
@@ -1130,6 +1130,10 @@ int cfr_classify_resident(cfr_handle *h, cfr_device_batch *b, void *stream) {
       if (h->pair_fetch == 2) {
         if (h->pos32) return run_first<BwtOccLine, BwtOccLine32T<4>, BwtPairT<2>>(h, b, s);
         return run_first<BwtOccLine, BwtOccLineT<4>, BwtPairT<2>>(h, b, s);
+      }
+      if (h->pair_fetch == 4) {  // bulk (TMA) copies, one per lane, counted on an mbarrier per warp: measured, not the default
+        if (h->pos32) return run_first<BwtOccLine, BwtOccLine32T<4>, BwtPairT<4>>(h, b, s);
+        return run_first<BwtOccLine, BwtOccLineT<4>, BwtPairT<4>>(h, b, s);
       }
       if (h->pos32) return run_first<BwtOccLine, BwtOccLine32T<4>, BwtPairT<3>>(h, b, s);
       return run_first<BwtOccLine, BwtOccLineT<4>, BwtPairT<3>>(h, b, s);

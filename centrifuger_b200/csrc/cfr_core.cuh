@@ -886,7 +886,7 @@ struct BwtPairT {
   enum { COOP = MODE != 0 };
   typedef u64 pos_t;
   // PAIR = 2: the search loop calls round() (one memory wait per iteration) instead of extend2()
-  enum { LANES = 1, PAIR = (MODE == 3 ? 2 : 1), STEPS_COUNTED_AT_CLOSE = 0 };
+  enum { LANES = 1, PAIR = (MODE >= 3 ? 2 : 1), STEPS_COUNTED_AT_CLOSE = 0 };
   static CFR_HD bool leader() { return true; }
   // single-step form: not used by the search loop of a pair policy (Bwt::PAIR selects extend2)
   static CFR_HD void extend_step(const DevIndex &, int, u64 sp, u64 ep, u64 &nsp, u64 &nep, OpCount &) {
@@ -940,6 +940,28 @@ struct BwtPairT {
   //     DRAM round trip -- three quarters of all iterations have such a lane); the rare surplus takes a second round,
   //   * the 16-byte wide-lookup-table entry of a lane that starts a search (`probe`), copied by the lane itself.
   // Returns the steps done (as extend2) for go lanes; `entry` = the table entry for probe lanes.
+  // MODE 4 state: one mbarrier and its phase parity per warp of the block (function-scope shared memory: one copy per block)
+  static CFR_D unsigned long long *tma_bar() {
+    __shared__ __align__(8) unsigned long long bar[4];
+    return bar;
+  }
+  static CFR_D unsigned *tma_phase() {
+    __shared__ unsigned phase[4];
+    return phase;
+  }
+  // called once by every thread at the start of the search kernel
+  static CFR_D void block_init() {
+    if (MODE == 4) {
+      if ((threadIdx.x & 31) == 0) {
+        const int wi = (threadIdx.x >> 5) & 3;
+        const u32 mb = (u32)__cvta_generic_to_shared(tma_bar() + wi);
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb) : "memory");
+        tma_phase()[wi] = 0;
+      }
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      __syncthreads();
+    }
+  }
   static CFR_D int round(const DevIndex &ix, bool go, int c1, int c2, u64 &sp, u64 &ep, bool probe, u64 key, u64x2 &entry,
                          OpCount &oc) {
     enum { F = CFR_PAIR_FAR, SLOTS = 32 + F };
@@ -963,6 +985,46 @@ struct BwtPairT {
     u32 *fmine = slots + (32 + (fslot ? frank : 0)) * CFR_PAIR_SLOT_WORDS;
     if (fslot) fmine[32] = (u32)Le;  // a padding word of the far slot names its line
     __syncwarp();
+    if (MODE == 4) {
+      // the same round with bulk (TMA) copies: every lane copies its own line(s) / table entry with one cp.async.bulk each,
+      // completion is counted in bytes on one mbarrier per warp (no cooperation between lanes, no shuffles)
+      const int wi = (threadIdx.x >> 5) & 3;
+      const u32 mb = (u32)__cvta_generic_to_shared(tma_bar() + wi);
+      const unsigned parity = tma_phase()[wi] & 1u;
+      const u32 bytes = 128u * (u32)(__popc(__ballot_sync(full, go)) + nfar) + 16u * (u32)__popc(__ballot_sync(full, probe));
+      if (bytes) {
+        if (lane == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(bytes) : "memory");
+        __syncwarp();
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the slots were last touched through the generic proxy
+        if (go) {
+          const u32 dst = (u32)__cvta_generic_to_shared(mine);
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], 128, [%2];" ::"r"(dst),
+                       "l"(ix.pairs + La), "r"(mb)
+                       : "memory");
+        }
+        if (fslot) {
+          const u32 dst = (u32)__cvta_generic_to_shared(fmine);
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], 128, [%2];" ::"r"(dst),
+                       "l"(ix.pairs + Le), "r"(mb)
+                       : "memory");
+        }
+        if (probe) {
+          const u32 dst = (u32)__cvta_generic_to_shared(mine);
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], 16, [%2];" ::"r"(dst),
+                       "l"(ix.wide + key), "r"(mb)
+                       : "memory");
+        }
+        unsigned done = 0;
+        while (!done)
+          asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                       : "=r"(done)
+                       : "r"(mb), "r"(parity)
+                       : "memory");
+        __syncwarp();
+        if (lane == 0) tma_phase()[wi] = parity ^ 1u;
+        __syncwarp();
+      }
+    } else {
     const u32 L = go ? (u32)La : CFR_PAIR_NO_LINE;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -990,6 +1052,7 @@ struct BwtPairT {
     asm volatile("cp.async.commit_group;" ::: "memory");
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncwarp();
+    }
     PairQuery qa, qe;
     if (go) pair_query_slot(ix, mine, La, c1, c2q, (int)(sp & 63), (int)(xe & 63), near, qa, qe);
     if (fslot) {

@@ -96,6 +96,7 @@ __global__ void __launch_bounds__(128, MINB) k_search(const __grid_constant__ De
                                                       const __grid_constant__ ChunkDev B) {
   OpCount oc{};
   const u64 ntask = B.n_reads * (u64)(2 * B.mates);
+  if constexpr (Bwt::PAIR == 2) Bwt::block_init();
   search_tasks<Bwt>(ix, P, B, ntask, oc);  // tasks are claimed dynamically from B.task_counter
   if (!Bwt::leader()) oc = OpCount{};
   flush_counts(oc, B.counters + CFR_STAGE_SEARCH);

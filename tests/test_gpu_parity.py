@@ -32,7 +32,9 @@ VARIANTS = {"default": {}, "nolanes_pairs": {"CFR_B200_LANES": "0", "CFR_B200_PA
             "pairs_ldg_dense1": {"CFR_B200_PAIRS": "1", "CFR_B200_PAIR_FETCH": "1", "CFR_B200_DENSE_LOCATE": "1"},
             # ... or by one cp.async round per request kind (the default is one wait per iteration for everything)
             "pairs_rounds_wide11": {"CFR_B200_PAIRS": "1", "CFR_B200_PAIR_FETCH": "2", "CFR_B200_WIDE_LOOKUP": "11"},
-            "pairs_wide11_pos64": {"CFR_B200_PAIRS": "1", "CFR_B200_WIDE_LOOKUP": "11", "CFR_B200_POS64": "1"}}
+            "pairs_wide11_pos64": {"CFR_B200_PAIRS": "1", "CFR_B200_WIDE_LOOKUP": "11", "CFR_B200_POS64": "1"},
+            # ... or by one bulk (TMA) copy per lane counted on an mbarrier per warp
+            "pairs_tma_wide12": {"CFR_B200_PAIRS": "1", "CFR_B200_PAIR_FETCH": "4", "CFR_B200_WIDE_LOOKUP": "12"}}
 
 
 @pytest.fixture(params=sorted(VARIANTS))
