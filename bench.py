@@ -411,7 +411,10 @@ def main():
             idx = ensure_dataset(w["dataset"])
     t0 = time.perf_counter()
     src = ReadSource(w)
-    host = [src.batch(bn, 7 + 1000 * rank + 100003 * j) for j in range(nb)]
+    # the batches are independent seeded draws: a few of them are generated side by side (numpy releases the GIL in its kernels)
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=max(1, min(4, nb, (os.cpu_count() or 4) // max(1, world)))) as ex:
+        host = list(ex.map(lambda j: src.batch(bn, 7 + 1000 * rank + 100003 * j), range(nb)))
     log("rank %d: %d batches of %d reads generated in %.1f s" % (rank, nb, bn, time.perf_counter() - t0))
     bases = int(sum(b[0].size + (b[2].size if b[2] is not None else 0) for b in host))
 

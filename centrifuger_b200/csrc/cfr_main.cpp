@@ -46,7 +46,7 @@ static const char usage[] =
     "\t\tor\n"
     "\t--sample-sheet FILE: list of sample files, each row: \"read1 read2 barcode UMI output\". Use dot(.) to represent no such file\n"
     "Optional:\n"
-    "\t-t INT: number of threads [1] (accepted for compatibility; the work runs on the GPU)\n"
+    "\t-t INT: number of threads [1] (the classification runs on the GPU; given, it caps the host threads that parse the reads)\n"
     "\t-k INT: report upto <int> distinct, primary assignments for each read pair [1]\n"
     "\t--un STR: output unclassified reads to files with the prefix of <str>\n"
     "\t--cl STR: output classified reads to files with the prefix of <str>\n"
@@ -278,6 +278,7 @@ int main(int argc, char *argv[]) {
   const char *quantReport = NULL;
   int quantFormat = 0;
   unsigned long quantMinScore = 0, quantMinLength = 0;
+  int hostThreads = 0;  // -t: 0 = not given (the ingest stage then uses every core)
   long batchReads = 1 << 20;
   const char *unPrefix = NULL, *clPrefix = NULL;  // --un / --cl
   bool mergePairs = false;                        // --merge-readpair
@@ -332,7 +333,7 @@ int main(int argc, char *argv[]) {
       useSheet = true;
     }
     else if (c == 'o') { /* parsed but unused by the reference as well (CentrifugerClass.cpp:416) */ }
-    else if (c == 't') { /* host thread count of the reference; nothing to do */ }
+    else if (c == 't') hostThreads = atoi(optarg);  // the reference's worker threads: here the cap on the ingest stage's threads
     else if (c == 'k') params.max_result = atoi(optarg);
     else if (c == 'h') { fprintf(stdout, "%s", usage); return 0; }  // the reference prints -h to stdout (CentrifugerClass.cpp:987-991)
     else if (c == 'v') { printf("Centrifuger v" CENTRIFUGER_VERSION "\n"); return 0; }  // :428-432
@@ -555,7 +556,8 @@ int main(int argc, char *argv[]) {
   const bool bulkIngest = !useSheet && !interleaved && !hasBarcode && !hasUmi && !fmt.NeedExtract(ReadFormat::R1) &&
                           !fmt.NeedExtract(ReadFormat::R2) && !(getenv("CFR_B200_BULK_INGEST") && atoi(getenv("CFR_B200_BULK_INGEST")) == 0);
   const unsigned ingestThreads = getenv("CFR_B200_INGEST_THREADS") ? (unsigned)std::max(1, atoi(getenv("CFR_B200_INGEST_THREADS")))
-                                                                    : std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+                                 : hostThreads > 0          ? (unsigned)std::min(hostThreads, 64)
+                                                            : std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
   // Sizes a batch's arrays for batchReads records like its first `seen` ones: a string that grows to 150 MB by doubling is
   // copied and page-faulted several times over, which costs more than parsing the reads
   auto reserveBatch = [&](Batch &bt, size_t seen) {
