@@ -115,3 +115,18 @@ def test_pack_reads_matches_the_encode_stage(threads):
             assert (p2 == o2 + np.uint64(pos2)).all()
         else:
             assert pk.off2 is None
+
+
+@pytest.mark.skipif(_has_cuda(), reason="checks the no-GPU failure mode")
+def test_patched_reference_binary_links_and_fails_loudly_without_a_gpu(tiny_dir):
+    """INTEGRATION.md, Option 2, applied for real (oracle/patch_reference.py): the reference's own CentrifugerClass.cpp with its
+    batch loop calling libcfrb200.so builds against the unmodified reference headers; without a device it exits with the
+    library's error instead of classifying on the CPU"""
+    import subprocess
+    exe = os.path.join(ROOT, "oracle", "_ref", "centrifuger_patched")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/centrifuger_patched not built (needs /root/reference)")
+    r = subprocess.run([exe, "-x", os.path.join(tiny_dir, "idx"), "-u", os.path.join(tiny_dir, "se_100.fq")],
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert r.returncode != 0
+    assert "no CUDA device" in r.stderr.decode() and "no CPU path" in r.stderr.decode()

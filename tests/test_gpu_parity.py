@@ -534,6 +534,31 @@ def test_unlimited_results_k0(tiny_dir, manifest, monkeypatch):
     g.close()
 
 
+def test_patched_reference_binary(tiny_dir, manifest):
+    """INTEGRATION.md's Option 2 applied for real: oracle/_ref/centrifuger_patched is the REFERENCE's binary (its argv
+    handling, kseq ingest and ResultWriter, compiled from /root/reference by oracle/patch_reference.py) with the batch
+    fan-out of CentrifugerClass.cpp:681-688 replaced by one call into libcfrb200.so.  Its TSV is the unmodified binary's."""
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "centrifuger_patched")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/centrifuger_patched not built")
+    n = 0
+    for section, sub in (("tiny", "expected"), ("expanded", "expanded"), ("k0", "k0"), ("long", "long")):
+        for name, m in sorted(manifest[section].items()):
+            if section == "tiny" and (m["index"] != "idx" or name.split("__")[2] not in ("default", "k5", "k2_hitk0", "mhl16_nodust")):
+                continue
+            files = [golden_path("tiny", f) for f in m["files"]]
+            cmd = [exe, "-x", os.path.join(tiny_dir, m.get("index", "idx"))] + m["args"]
+            if section == "expanded" and "--expand-taxid" not in m["args"]:
+                cmd += ["--expand-taxid"]
+            cmd += ["-u", files[0]] if len(files) == 1 else ["-1", files[0], "-2", files[1]]
+            r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+            assert r.returncode == 0, (name, r.stderr.decode()[-400:])
+            assert r.stdout.decode() == open(golden_path("tiny", sub, name + ".tsv")).read(), (section, name)
+            n += 1
+    assert n >= 40
+
+
 def test_cli_long_reads_and_consider_secondary(tiny_dir, manifest):
     """reads of 2 - 9 kbp and the near-tie rule of --consider-secondary (Classifier.hpp:763-781; bars lowered
     so short reads reach it): the CLI's TSV is byte for byte the reference binary's"""
