@@ -78,11 +78,11 @@ def main():
     total = 0
     for it in range(rounds):
         variant = rng.choice(["idx", "idx", "idx_b1", "idx_b8", "idx_off3"]) if dataset == "tiny" else "idx"
-        kw = dict(k=rng.choice([1, 1, 2, 3, 5]), hitk_factor=rng.choice([40, 40, 2, 0, 1]),
+        kw = dict(k=rng.choice([1, 1, 2, 3, 5, 0, -1]), hitk_factor=rng.choice([40, 40, 2, 0, 1]),
                   min_hit_len=rng.choice([0, 0, 16, 20, 30]), dust=rng.random() < 0.7)
         if rng.random() < 0.4:
             kw.update(secondary_len=rng.choice([30, 60, 100, 500]), secondary_factor=rng.choice([0.5, 0.8, 0.9, 0.995]))
-        layout = rng.choice([1, 2, 3])
+        layout = rng.choice([1, 2, 3, 4])
         paired = rng.random() < 0.5
         n = rng.randrange(50, 400)
         lens = [rng.choice([rng.randrange(1, 40), rng.randrange(40, 160), rng.randrange(100, 320), 100, 150,
@@ -95,7 +95,7 @@ def main():
         idx = os.path.join(d if dataset == "tiny" else big, variant)
         # the load-time tables and the SDUST screen of the product, as hostsim exposes them
         for key, choices in (("HOSTSIM_WIDE_LOOKUP", [None, None, "7", "9"]), ("HOSTSIM_DENSE_LOCATE", [None, "0", "1", "2", "3"]),
-                             ("HOSTSIM_NO_DUST_SCREEN", [None, None, "1"])):
+                             ("HOSTSIM_NO_DUST_SCREEN", [None, None, "1"]), ("HOSTSIM_DENSE16", [None, "1"])):
             v = rng.choice(choices)
             if v is None:
                 os.environ.pop(key, None)
@@ -103,7 +103,7 @@ def main():
                 os.environ[key] = v
         o = Oracle(idx, **kw)
         hs = HostSim(idx, layout=layout, **kw)
-        k = kw["k"]
+        k = hs.stride  # id slots per read: -k, or 64 for -k <= 0 (every best-scoring sequence)
         try:
             res, ids, lists = hs.classify_expanded(r1, r2, arena_rows=arena)
         except RuntimeError as e:
