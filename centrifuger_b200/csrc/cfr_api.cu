@@ -1414,10 +1414,30 @@ int cfr_pack_reads(const cfr_read_batch *in, uint64_t *codes, uint32_t *nmask, u
         cnt = (int)std::min<u64>(32, len2 - (p0 - pos2));
       }
       m = cnt >= 32 ? 0u : ~((1u << cnt) - 1u);  // padding reads as N
-      for (int i = 0; i < cnt; ++i) {
-        const unsigned char x = lut.v[src[i]];
-        if (x > 3) m |= 1u << i;
-        else c |= (u64)x << (2 * i);
+      int i = 0;
+      for (; i + 8 <= cnt; i += 8) {  // eight bases per step, branch-free (SWAR)
+        u64 x;
+        memcpy(&x, src + i, 8);
+        const u64 ONES = 0x0101010101010101ull, LOW7 = 0x7f7f7f7f7f7f7f7full, HIGH = 0x8080808080808080ull;
+        // bytes equal to 'A', 'C', 'G' or 'T': exact per-byte zero test of x ^ letter
+        u64 ok = 0;
+        for (const u64 letter : {0x41ull, 0x43ull, 0x47ull, 0x54ull}) {
+          const u64 z = x ^ (letter * ONES);
+          ok |= ~(((z & LOW7) + LOW7) | z) & HIGH;
+        }
+        const u32 valid8 = (u32)((((ok >> 7) & ONES) * 0x0102040810204080ull) >> 56);  // byte j -> bit j (terms 8j + 56 - 7j, no two collide)
+        // 2-bit codes: ((b >> 1) ^ (b >> 2)) & 3 maps A, C, G, T to 0, 1, 2, 3; bytes that are not ACGT give 0
+        u64 q = ((x >> 1) ^ (x >> 2)) & (3ull * ONES) & ((ok >> 7) * 3ull);
+        q = (q | (q >> 6)) & 0x000f000f000f000full;
+        q = (q | (q >> 12)) & 0x000000ff000000ffull;
+        q = (q | (q >> 24)) & 0xffffull;
+        c |= q << (2 * i);
+        m |= (~valid8 & 0xffu) << i;
+      }
+      for (; i < cnt; ++i) {
+        const unsigned char xb = lut.v[src[i]];
+        if (xb > 3) m |= 1u << i;
+        else c |= (u64)xb << (2 * i);
       }
       codes[w] = c;
       nmask[w] = m;

@@ -542,7 +542,7 @@ int main(int argc, char *argv[]) {
   // The reads cross the host link packed (cfr_submit_packed) unless the masked reads must come back for --un / --cl
   // (CFR_B200_PACK_INPUT=0 sends the bytes instead)
   const bool packInput = !writeReads && !dryOut && !dryPipe && !(getenv("CFR_B200_PACK_INPUT") && atoi(getenv("CFR_B200_PACK_INPUT")) == 0);
-  const unsigned packThreads = std::max(1u, std::min(16u, std::thread::hardware_concurrency() / 2));
+  const unsigned packThreads = hostThreads > 0 ? (unsigned)std::min(hostThreads, 64) : std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
   // CFR_B200_STAGE_REPORT=1: seconds each pipeline stage was busy (waits for the neighbouring stages excluded)
   const bool stageReport = getenv("CFR_B200_STAGE_REPORT") && atoi(getenv("CFR_B200_STAGE_REPORT")) != 0;
   typedef std::chrono::steady_clock StageClock;

@@ -99,7 +99,8 @@ def test_pack_reads_matches_the_encode_stage(threads):
     lowercase / IUPAC / N bytes, single-end, an empty batch, a batch that starts in the middle of its buffers"""
     import numpy as np
     rng = np.random.default_rng(5 + threads)
-    alpha, p = list(b"ACGTNacgtRY-"), [.225, .225, .225, .225, .02, .01, .01, .01, .01, .02, .01, .01]
+    alpha = list(b"ACGTNacgtRY-") + [0, 255, 0x40, 0x42, 0x55, 0xc1]  # neighbours of the four letters, bytes with the high bit
+    p = [.22, .22, .22, .22, .02, .01, .01, .01, .01, .01, .01, .01] + [.005] * 6
     for n, hi, two in ((300, 200, True), (1, 1, True), (0, 1, True), (40000, 160, False), (500, 40, True)):
         r1 = [bytes(rng.choice(alpha, p=p, size=int(L)).astype(np.uint8)) for L in rng.integers(0, hi, size=n)]
         r2 = [bytes(rng.choice(alpha, p=p, size=int(L)).astype(np.uint8)) for L in rng.integers(0, hi, size=n)]
